@@ -1,0 +1,88 @@
+/* scpb.h -- C ABI of libscpb (B200-native SCP inner loop).
+ *
+ * Drop-in boundary for the hot path of UW-ACL/SCPToolbox.jl (file:line relative to the
+ * reference tree):
+ *   scpb_discretize*     replaces discretize!(ref, pbm)      src/solvers/discretization.jl:160-217
+ *                        (derivs_foh :235-286, set_update_matrices :354-406, rk4 helper.jl:411-501)
+ *   scpb_cone_*          replaces solve!(prg)=JuMP.optimize! src/parser/program.jl:419-424
+ *                        reached from solve_subproblem!      src/solvers/scp.jl:942-950
+ *   scpb_ptr_*           replaces the PTR loop body          src/solvers/ptr.jl:448-532
+ *                        (formulate :470-478 + solve :484 + discretize :380) for a batch of seeds
+ *
+ * Conventions: plain C, every entry point returns int32 status (0 = OK, <0 = error; text via
+ * scpb_last_error), never throws or aborts.  Host arrays are caller-owned.  Per-seed blocks use
+ * Julia's column-major memory so that a batch of one maps 1:1 onto `ref.dyn.A` etc.
+ * A handle is bound to one CUDA device + stream and is not thread-safe; different handles are.
+ */
+#ifndef SCPB_H
+#define SCPB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct scpb_handle_s *scpb_handle;
+
+/* ---- device model packs (the device-side twin of traj.f/A/B/F, problem.jl:432-450) ---- */
+enum {
+    SCPB_MODEL_DBLINT = 1,    /* x=[pos,vel] u=[acc] p=[tf];      par: g                          */
+    SCPB_MODEL_ROCKET = 2,    /* x=[r3,v3,z] u=[a3,xi] p=[tf];    par: g[3], omega[3], alpha      */
+    SCPB_MODEL_STARSHIP = 3,  /* starship_flip/definition.jl:498-637;
+                                 par: m, J, lcg, lcp, CD, alpha_e, rate_delay, g0, tau_s           */
+    SCPB_MODEL_QUADROTOR = 4, /* quadrotor/definition.jl:140-186; par: g[3]                        */
+    SCPB_MODEL_FREEFLYER = 5  /* freeflyer/definition.jl:224-284; par: mass, J[9], Jinv[9] (col-major) */
+};
+#define SCPB_MAX_PAR 64
+
+enum { SCPB_FOH = 0, SCPB_IMPULSE = 1 };
+
+/* status codes */
+enum {
+    SCPB_OK = 0,
+    SCPB_ERR_ARG = -1,
+    SCPB_ERR_CUDA = -2,
+    SCPB_ERR_MODEL = -3,
+    SCPB_ERR_UNSUPPORTED = -4,
+    SCPB_ERR_STATE = -5
+};
+
+/* ---- lifetime ---- */
+int32_t scpb_create(int32_t device, scpb_handle *out);
+int32_t scpb_destroy(scpb_handle h);
+int32_t scpb_last_error(scpb_handle h, char *buf, size_t len);
+int32_t scpb_version(void);
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+int64_t scpb_launch_count(scpb_handle h);
+/* CUDA stream the handle launches on (cudaStream_t as void*), for event timing by the caller */
+void *scpb_stream(scpb_handle h);
+int32_t scpb_sync(scpb_handle h);
+
+/* ---- model selection ---- */
+int32_t scpb_model_set(scpb_handle h, int32_t model_id, const double *par, int32_t npar,
+                       int32_t nx, int32_t nu, int32_t np);
+
+/* ---- discretize!  (host buffers; H2D + kernel + D2H inside) ----
+ * t_grid[N]; xd[B][N][nx]; ud[B][N][nu]; p[B][np]; iSx_diag[nx];
+ * A[B][N-1][nx*nx], Bm/Bp[B][N-1][nx*nu], F[B][N-1][nx*np], r[B][N-1][nx], E[B][N-1][nx*nx],
+ * defect[B][N-1][nx], feas[B] (1 = dynamically feasible); *seconds = device time of the kernel. */
+int32_t scpb_discretize(scpb_handle h, int32_t method, int32_t B, int32_t N, int32_t Nsub,
+                        const double *t_grid, const double *xd, const double *ud, const double *p,
+                        const double *iSx_diag, double feas_tol,
+                        double *A, double *Bm, double *Bp, double *F, double *r, double *E,
+                        double *defect, int32_t *feas, double *seconds);
+
+/* same, all pointers are DEVICE pointers in the same layouts (inputs resident in HBM);
+ * asynchronous on the handle's stream. */
+int32_t scpb_discretize_dev(scpb_handle h, int32_t method, int32_t B, int32_t N, int32_t Nsub,
+                            const double *t_grid, const double *xd, const double *ud, const double *p,
+                            const double *iSx_diag, double feas_tol,
+                            double *A, double *Bm, double *Bp, double *F, double *r, double *E,
+                            double *defect, int32_t *feas);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

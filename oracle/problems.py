@@ -1,0 +1,325 @@
+"""Oracle-side problem data (numpy restatement of the example parameter files).
+TEST INFRASTRUCTURE ONLY -- see oracle/scp_oracle.h.
+
+Each problem object carries
+  * the dimensions and the dynamics parameter vector `par` (layout shared with the
+    product's device model packs, documented in include/scpb.h),
+  * the variable ranges handed to problem_advise_scale! (-> compute_scaling, scp.jl:376-517),
+  * numpy closures for the nonconvex constraints s/C/D/G, boundary conditions and cost,
+  * `emit_X` / `emit_U`: the convex path constraints as rows added to an oracle cone program.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from . import orc
+
+
+def deg2rad(d):
+    return d * math.pi / 180.0
+
+
+class StarshipProblem:
+    """starship_flip/parameters.jl:100-212 and definition.jl (PTR / SCvx flavour)."""
+
+    name = "starship"
+    model_id = orc.MODEL_STARSHIP
+    nx, nu, np = 8, 3, 10
+
+    def __init__(self, N: int):
+        self.N = N
+        g0 = 9.81
+        self.g0 = g0
+        rs, ls = 4.5, 50.0
+        self.m = 120e3
+        self.lcg = 0.4 * ls
+        self.lcp = 0.45 * ls
+        self.J = 1 / 12 * self.m * (6 * rs ** 2 + ls ** 2)
+        vterm = 85
+        CD = self.m * g0 / vterm ** 2
+        CD *= 1.2
+        self.CD = CD
+        Isp = 330
+        self.T_min1 = 880e3
+        self.T_max1 = 2210e3
+        self.T_min3 = 3 * self.T_min1
+        self.T_max3 = 3 * self.T_max1
+        self.alpha_e = -1 / (Isp * g0)
+        self.delta_max = deg2rad(10.0)
+        self.deltadot_max = 2 * self.delta_max
+        self.rate_delay = 0.05
+        # trajectory
+        self.r0 = np.array([100.0, 600.0])
+        self.v0 = np.array([0.0, -float(vterm)])
+        self.theta0 = deg2rad(90.0)
+        self.theta_s = deg2rad(-10.0)
+        self.vs = np.array([0.0, -10.0])
+        self.vf = np.array([0.0, -0.1])
+        self.tf_min = 0.0
+        self.tf_max = 40.0
+        self.gamma_gs = deg2rad(27.0)
+        self.thetamax2 = deg2rad(15.0)
+        self.tau_s = 0.5
+        self.hs = 100.0  # overwritten by the initial guess (definition.jl:195)
+        self.ey = np.array([0.0, 1.0])
+
+    # -- dynamics parameter vector (indices: scp_oracle.c enum SS_*) --
+    def par(self):
+        return np.array([self.m, self.J, self.lcg, self.lcp, self.CD, self.alpha_e, self.rate_delay,
+                         self.g0, self.tau_s])
+
+    def orc_model(self):
+        return orc.make_model(self.model_id, self.nx, self.nu, self.np, self.par())
+
+    # -- set_scale!, definition.jl:50-79 --
+    def ranges(self):
+        xrg = [(-100.0, 100.0), (0.0, self.r0[1]), (-10.0, 10.0), (self.v0[1], 0.0),
+               (0.0, self.theta0), (deg2rad(-10.0), deg2rad(10.0)), (self.m - 1e3, self.m),
+               (-self.delta_max, self.delta_max)]
+        urg = [(self.T_min1, self.T_max3), (-self.delta_max, self.delta_max),
+               (-self.deltadot_max, self.deltadot_max)]
+        prg = [(0.0, self.tf_max), (0.0, self.tf_max)] + list(xrg)
+        return xrg, urg, prg
+
+    # -- terminal cost, definition.jl:454-478: phi(x, p) = c_x'x + c_p'p --
+    def cost_terminal_lin(self):
+        cx = np.zeros(self.nx)
+        cp = np.zeros(self.np)
+        mu = 0.3
+        cp[2 + 1] = -mu / self.hs          # -mu * alt / hs, alt = p[id_xs][id_r][2]
+        cx[6] = -1.0 / 10e3                # (0 - mf)/1e4
+        return cx, cp, 0.0
+
+    has_running_cost = False
+
+    # -- phase helpers, definition.jl:707-721 --
+    def phase_switch(self, t):
+        dt = 1 / (self.N - 1)
+        tol = 1e-3
+        return (self.tau_s - dt) + tol <= t and t <= self.tau_s + tol
+
+    def phase2(self, t):
+        return self.phase_switch(t) or t > self.tau_s
+
+    ns = 7 + 2 * 8
+
+    # -- nonconvex path constraints, definition.jl:725-807 --
+    def s(self, t, k, x, u, p):
+        s = np.zeros(self.ns)
+        r = x[0:2]
+        th = x[4]
+        dd = x[7]
+        de, ddot = u[1], u[2]
+        s[0] = (de - dd) - ddot * self.rate_delay
+        s[1] = ddot * self.rate_delay - (de - dd)
+        s[2] = ddot - self.deltadot_max
+        s[3] = -self.deltadot_max - ddot
+        s[4] = np.linalg.norm(r) * math.cos(self.gamma_gs) - r @ self.ey
+        if self.phase_switch(t):
+            s[5:13] = p[2:10] - x
+            s[13:21] = x - p[2:10]
+        if self.phase2(t):
+            s[-2] = th - self.thetamax2
+            s[-1] = -self.thetamax2 - th
+        return s
+
+    def C(self, t, k, x, u, p):
+        Cm = np.zeros((self.ns, self.nx))
+        r = x[0:2]
+        nr = np.linalg.norm(r)
+        gn = np.zeros(2) if nr < math.sqrt(np.finfo(float).eps) else r / nr
+        Cm[0, 7] = -1.0
+        Cm[1, 7] = 1.0
+        Cm[4, 0:2] = gn * math.cos(self.gamma_gs) - self.ey
+        if self.phase_switch(t):
+            Cm[5:13, :] = -np.eye(8)
+            Cm[13:21, :] = np.eye(8)
+        if self.phase2(t):
+            Cm[-2, 4] = 1.0
+            Cm[-1, 4] = -1.0
+        return Cm
+
+    def D(self, t, k, x, u, p):
+        Dm = np.zeros((self.ns, self.nu))
+        Dm[0, 1] = 1.0
+        Dm[0, 2] = -self.rate_delay
+        Dm[1, 1] = -1.0
+        Dm[1, 2] = self.rate_delay
+        Dm[2, 2] = 1.0
+        Dm[3, 2] = -1.0
+        return Dm
+
+    def G(self, t, k, x, u, p):
+        Gm = np.zeros((self.ns, self.np))
+        if self.phase_switch(t):
+            Gm[5:13, 2:10] = np.eye(8)
+            Gm[13:21, 2:10] = -np.eye(8)
+        return Gm
+
+    # -- boundary conditions, definition.jl:812-873 --
+    def gic(self, x, p):
+        rhs = np.array([self.r0[0], self.r0[1], self.v0[0], self.v0[1], self.theta0, 0.0, 0.0])
+        return x[0:7] - rhs
+
+    def H0(self, x, p):
+        H = np.zeros((7, self.nx))
+        H[np.arange(7), np.arange(7)] = 1.0
+        return H
+
+    K0 = None
+
+    def gtc(self, x, p):
+        rhs = np.array([0.0, 0.0, self.vf[0], self.vf[1], 0.0, 0.0])
+        return x[0:6] - rhs
+
+    def Hf(self, x, p):
+        H = np.zeros((6, self.nx))
+        H[np.arange(6), np.arange(6)] = 1.0
+        return H
+
+    Kf = None
+
+    # -- convex constraints, definition.jl:639-702.  `prg` is an oracle ConeProgram;
+    #    x/u/p are affine-expression vectors in physical units --
+    def emit_X(self, prg, t, k, x, p):
+        v = x[2:4]
+        tf1, tf2 = p[0], p[1]
+        prg.nonpos([v[1] * 1.0], "no_climb")
+        prg.nonpos([tf1 + tf2 - self.tf_max], "max_time")
+        prg.nonpos([self.tf_min - (tf1 + tf2)], "min_time")
+
+    def emit_U(self, prg, t, k, u, p):
+        T, de = u[0], u[1]
+        flip = t <= self.tau_s
+        T_max = self.T_max3 if flip else self.T_max1
+        T_min = self.T_min3 if flip else self.T_min1
+        prg.nonpos([T - T_max], "max_thrust")
+        prg.nonpos([T_min - T], "min_thrust")
+        prg.l1([self.delta_max + 0.0 * de, de], "gimbal")
+
+
+class _DynOnly:
+    """Dynamics-only problem data (used by the discretization parity tests)."""
+
+    def orc_model(self):
+        return orc.make_model(self.model_id, self.nx, self.nu, self.np, self.par())
+
+
+class DoubleIntegratorProblem(_DynOnly):
+    """double_integrator/parameters.jl:50-64 (friction g), free-final-time variant."""
+    name = "dblint"
+    model_id = orc.MODEL_DBLINT
+    nx, nu, np = 2, 1, 1
+
+    def __init__(self, N: int, choice: int = 1):
+        self.N = N
+        self.g = 0.1 if choice == 1 else 0.6
+        self.s = 47.0 if choice == 1 else 30.0
+        self.T = 10.0
+
+    def par(self):
+        return np.array([self.g])
+
+
+class RocketProblem(_DynOnly):
+    """rocket_landing/parameters.jl:78-150 (Mars powered descent), free-final-time variant."""
+    name = "rocket"
+    model_id = orc.MODEL_ROCKET
+    nx, nu, np = 7, 4, 1
+
+    def __init__(self, N: int):
+        self.N = N
+        ex, ey, ez = np.eye(3)
+        self.g = -3.7114 * ez
+        th = 30 * math.pi / 180
+        T_sidereal_mars = 24.6229 * 3600
+        self.omega = (2 * math.pi / T_sidereal_mars) * (ex * math.cos(th) + ey * 0 + ez * math.sin(th))
+        self.m_dry, self.m_wet, self.Isp = 1505.0, 1905.0, 225.0
+        n_eng = 6
+        self.phi = 27 * math.pi / 180
+        T_max = 3.1e3
+        self.rho_min = n_eng * 0.3 * T_max * math.cos(self.phi)
+        self.rho_max = n_eng * 0.8 * T_max * math.cos(self.phi)
+        self.gamma_gs = 86 * math.pi / 180
+        self.gamma_p = 40 * math.pi / 180
+        self.v_max = 500 * 1e3 / 3600
+        self.r0 = (2 * ex + 0 * ey + 1.5 * ez) * 1e3
+        self.v0 = 80 * ex + 30 * ey - 75 * ez
+        self.alpha = 1 / (self.Isp * 9.807 * math.cos(self.phi))
+
+    def par(self):
+        return np.concatenate([self.g, self.omega, [self.alpha]])
+
+
+class QuadrotorProblem(_DynOnly):
+    """quadrotor/parameters.jl:96-135."""
+    name = "quadrotor"
+    model_id = orc.MODEL_QUADROTOR
+    nx, nu, np = 6, 4, 1
+
+    def __init__(self, N: int):
+        self.N = N
+        self.g = np.array([0.0, 0.0, -9.81])   # parameters.jl:83-84: g = -gnrm * e_z
+        self.u_max, self.u_min, self.tilt_max = 23.2, 0.6, deg2rad(60)
+        self.tf_min, self.tf_max = 0.0, 2.5
+
+    def par(self):
+        return self.g.copy()
+
+
+class FreeFlyerProblem(_DynOnly):
+    """freeflyer/parameters.jl:105-190; np = 1 + 6N (room SDF slack per node)."""
+    name = "freeflyer"
+    model_id = orc.MODEL_FREEFLYER
+    nx, nu = 13, 6
+
+    def __init__(self, N: int):
+        self.N = N
+        self.n_iss = 6
+        self.np = 1 + self.n_iss * N
+        self.mass = 7.2
+        self.J = np.diag([0.1083, 0.1083, 0.1083])
+        self.v_max, self.omega_max = 0.4, deg2rad(1)
+        self.T_max, self.M_max = 20e-3, 1e-4
+        self.tf_min, self.tf_max = 60.0, 200.0
+
+    def par(self):
+        return np.concatenate([[self.mass], self.J.flatten(order="F"), np.linalg.inv(self.J).flatten(order="F")])
+
+
+def test_trajectory(pb, nb: int, N: int, seed: int = 0):
+    """Seeded, physically plausible random trajectories for parity tests: (xd, ud, p)."""
+    rng = np.random.default_rng(seed)
+    nx, nu, np_ = pb.nx, pb.nu, pb.np
+    if pb.name == "starship":
+        x0 = np.array([50., 300., 3., -40., 0.7, 0.02, -100., 0.05])
+        u0 = np.array([3e6, 0.05, 0.01])
+        p0 = np.concatenate([[12., 15.], x0])
+    elif pb.name == "dblint":
+        x0 = np.array([10., 2.]); u0 = np.array([0.5]); p0 = np.array([10.])
+    elif pb.name == "rocket":
+        x0 = np.array([1500., 100., 1200., 60., 20., -50., math.log(1800.)])
+        u0 = np.array([1., 0.5, 5., 6.]); p0 = np.array([60.])
+    elif pb.name == "quadrotor":
+        x0 = np.array([1., 2., 0.5, 1., -0.5, 0.2]); u0 = np.array([0.5, -0.3, 9.9, 10.]); p0 = np.array([2.])
+    elif pb.name == "freeflyer":
+        q = np.array([0.1, -0.3, 0.2, 0.9]); q /= np.linalg.norm(q)
+        x0 = np.concatenate([[7., 0.5, 4.8], [0.03, 0.02, -0.01], q, [0.005, -0.004, 0.003]])
+        u0 = np.array([5e-3, -3e-3, 2e-3, 2e-5, -1e-5, 3e-5])
+        p0 = np.concatenate([[100.], -1.0 + 0.1 * np.arange(np_ - 1) / max(np_ - 1, 1)])
+    else:
+        raise KeyError(pb.name)
+    xd = x0 * (1 + 0.03 * rng.standard_normal((nb, N, nx))) + 1e-3 * rng.standard_normal((nb, N, nx))
+    ud = u0 * (1 + 0.05 * rng.standard_normal((nb, N, nu)))
+    p = p0 * (1 + 0.05 * rng.standard_normal((nb, np_)))
+    if pb.name == "freeflyer":
+        xd[..., 6:10] /= np.linalg.norm(xd[..., 6:10], axis=-1, keepdims=True)
+    return xd, ud, p
+
+
+def make_problem(name: str, N: int):
+    cls = {"starship": StarshipProblem, "dblint": DoubleIntegratorProblem, "rocket": RocketProblem,
+           "quadrotor": QuadrotorProblem, "freeflyer": FreeFlyerProblem}[name]
+    return cls(N)

@@ -1,0 +1,7 @@
+"""scptoolbox.jl_b200 -- B200-native SCP inner loop (discretize! + subproblem solve) behind a C ABI.
+
+The directory name carries a dot, so the package is imported under the alias
+`scptoolbox_jl_b200` (see __graft_entry__.load_package()).
+"""
+from . import lib  # noqa: F401
+from .lib import Handle, ScpbError  # noqa: F401
