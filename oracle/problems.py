@@ -94,6 +94,22 @@ class StarshipProblem:
 
     has_running_cost = False
 
+    def cost_aff(self, x, u, p, t):
+        """Original cost as an affine expression (terminal only; no running cost)."""
+        cx, cp, c0 = self.cost_terminal_lin()
+        e = c0
+        for i in range(self.nx):
+            if cx[i] != 0.0:
+                e = e + x[i, -1] * cx[i]
+        for i in range(self.np):
+            if cp[i] != 0.0:
+                e = e + p[i] * cp[i]
+        return e
+
+    def guess(self, N):
+        from .starship_guess import starship_initial_guess
+        return starship_initial_guess(self, N)
+
     # -- phase helpers, definition.jl:707-721 --
     def phase_switch(self, t):
         dt = 1 / (self.N - 1)
