@@ -82,6 +82,52 @@ int32_t scpb_discretize_dev(scpb_handle h, int32_t method, int32_t B, int32_t N,
                             double *A, double *Bm, double *Bp, double *F, double *r, double *E,
                             double *defect, int32_t *feas);
 
+/* ---- batched cone solver: replaces solve!(prg) -> JuMP.optimize! -> ECOS (program.jl:419-424) ----
+ *   min c'x  s.t.  A x = b,  G x + s = h,  s in K = R+^l x SOC(q_1) x ... x SOC(q_nsoc)
+ * (the standard form MathOptInterface hands to ECOS).  The sparsity pattern and the cone partition are
+ * shared by the whole batch; values differ per seed.  perm (nullable) is the elimination order of
+ * the n variables followed by the p equality rows (perm[k] = node eliminated k-th, variables are
+ * 0..n-1, equality rows n..n+p-1); the host template supplies a stage-wise nested dissection. */
+typedef struct scpb_cone_s *scpb_cone;
+
+typedef struct {
+    double feastol, abstol, reltol; /* <=0: ECOS defaults 1e-8                          */
+    double delta, delta_dyn;        /* <=0: static 1e-9 / dynamic 1e-13 regularisation   */
+    int32_t maxit;                  /* <=0: 100 ("maxit" of solver_opts)                 */
+    int32_t nref;                   /* <0: 2 iterative-refinement steps                  */
+    int32_t verbose;                /* accepted, ignored ("verbose" of solver_opts)      */
+    int32_t group;                  /* seeds per CTA (power of two <= 32); 0 = automatic */
+} scpb_cone_opts;
+
+/* per-seed status (termination_status, program.jl:427-428): */
+enum { SCPB_CONE_OPTIMAL = 0, SCPB_CONE_ITERATION_LIMIT = 1, SCPB_CONE_NUMERICAL_ERROR = 2 };
+
+int32_t scpb_cone_setup(scpb_handle h, int32_t n, int32_t p, int32_t m,
+                        const int32_t *A_rowptr, const int32_t *A_colind,
+                        const int32_t *G_rowptr, const int32_t *G_colind,
+                        int32_t l, int32_t nsoc, const int32_t *soc_dims, const int32_t *perm,
+                        scpb_cone *out);
+/* info[8] = {n+p, nnz(L), elimination-tree levels, factor ops, assembly ops, |W^-2|, group, capacity} */
+int32_t scpb_cone_info(scpb_cone c, int64_t *info);
+int32_t scpb_cone_free(scpb_cone c);
+/* host arrays, seed-major: Avals[B][nnzA], Gvals[B][nnzG], c[B][n], b[B][p], h[B][m];
+ * outputs x[B][n], y[B][p], z[B][m], s[B][m], pobj[B], dobj[B], status[B], iters[B] (each nullable). */
+int32_t scpb_cone_solve(scpb_cone c, int32_t B, const double *Avals, const double *Gvals,
+                        const double *cvec, const double *bvec, const double *hvec,
+                        const scpb_cone_opts *opts, double *x, double *y, double *z, double *s,
+                        double *pobj, double *dobj, int32_t *status, int32_t *iters, double *seconds);
+
+/* ---- test hook: CPU interpreter of the solver's index programs for ONE seed (no GPU needed) ----
+ * Assembles M = [dI + G'W^-2 G, A'; A, -dI] from (Av, Gv, wm), factors it with the level-scheduled
+ * LDL' program and solves M sol = rhs (natural node order: n variables then p equality rows).
+ * Used by the CPU test-suite only; never called by the product path.
+ * info[4] = {nnz(L), levels, factor ops, assembly ops}. */
+int32_t scpb_debug_kkt_solve(int32_t n, int32_t p, int32_t m, const int32_t *A_rowptr, const int32_t *A_colind,
+                             const int32_t *G_rowptr, const int32_t *G_colind, int32_t l, int32_t nsoc,
+                             const int32_t *soc_dims, const int32_t *perm, const double *Avals,
+                             const double *Gvals, const double *wm, double delta, const double *rhs,
+                             double *sol, int64_t *info);
+
 #ifdef __cplusplus
 }
 #endif

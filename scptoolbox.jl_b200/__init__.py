@@ -3,5 +3,5 @@
 The directory name carries a dot, so the package is imported under the alias
 `scptoolbox_jl_b200` (see __graft_entry__.load_package()).
 """
-from . import lib  # noqa: F401
+from . import lib, ordering  # noqa: F401
 from .lib import Handle, ScpbError  # noqa: F401

@@ -1,0 +1,254 @@
+// conic_api.cu -- C ABI of the batched cone solver (scpb_cone_*), host orchestration.
+#include "handle.cuh"
+#include "conic_symbolic.h"
+#include "conic_ipm.cuh"
+
+struct scpb_cone_s {
+    scpb_handle_s *h = nullptr;
+    ConeSymbolic S;
+    IpmProgram P{};
+    std::vector<void *> dev_ints;
+    // data buffers (grow-only), sized for (ngroups*G) seeds
+    int capB = 0, capG = 0;
+    std::vector<double *> bufs;
+    IpmData D{};
+    double *stage = nullptr;  // seed-major staging on device
+    size_t stage_cap = 0;
+    int *d_status = nullptr, *d_iters = nullptr;
+    double *d_scal = nullptr;  // pobj, dobj, res[3]
+};
+
+static const int *upload_ints(scpb_cone_s *c, const std::vector<int> &v)
+{
+    void *d = nullptr;
+    size_t bytes = sizeof(int) * (v.size() + 1);
+    if (cudaMalloc(&d, bytes) != cudaSuccess) return nullptr;
+    if (!v.empty()) cudaMemcpy(d, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice);
+    c->dev_ints.push_back(d);
+    return (const int *)d;
+}
+
+// seed-major [B][E] <-> group-blocked [(B/G)][E][G]; padded seeds replicate seed B-1
+__global__ void k_to_grouped(const double *src, double *dst, int E, int B, int G, int Bpad)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)E * Bpad) return;
+    const int sd = (int)(i % Bpad), e = (int)(i / Bpad);
+    const int ssrc = sd < B ? sd : B - 1;
+    dst[((size_t)(sd / G) * E + e) * G + (sd % G)] = src[(size_t)ssrc * E + e];
+}
+__global__ void k_from_grouped(const double *src, double *dst, int E, int B, int G)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)E * B) return;
+    const int sd = (int)(i % B), e = (int)(i / B);
+    dst[(size_t)sd * E + e] = src[((size_t)(sd / G) * E + e) * G + (sd % G)];
+}
+
+static int pick_group(int B, int want)
+{
+    if (want > 0) {
+        int g = 1;
+        while (g < want && g < IPM_MAXG) g <<= 1;
+        return g;
+    }
+    int g = 1;
+    while ((B + g - 1) / g > 444 && g < IPM_MAXG) g <<= 1;
+    return g;
+}
+
+static int cone_reserve(scpb_cone_s *c, int B, int G)
+{
+    scpb_handle_s *h = c->h;
+    const int ng = (B + G - 1) / G, Bpad = ng * G;
+    if (c->capB >= Bpad && c->capG == G) { c->D.B = B; c->D.G = G; return SCPB_OK; }
+    for (double *p : c->bufs) cudaFree(p);
+    c->bufs.clear();
+    if (c->d_status) cudaFree(c->d_status);
+    if (c->d_iters) cudaFree(c->d_iters);
+    if (c->d_scal) cudaFree(c->d_scal);
+    const ConeSymbolic &S = c->S;
+    auto al = [&](size_t E) -> double * {
+        double *p = nullptr;
+        if (cudaMalloc((void **)&p, sizeof(double) * (E + 1) * Bpad) != cudaSuccess) return nullptr;
+        c->bufs.push_back(p);
+        return p;
+    };
+    IpmData &D = c->D;
+    const size_t n = S.n, p = S.p, m = S.m, nk = S.nk, nm = std::max(S.n, S.m);
+    double *Av = al(S.A_ci.size()), *Gv = al(S.G_ci.size()), *cc = al(n), *bb = al(p), *hh = al(m);
+    D.Av = Av; D.Gv = Gv; D.c = cc; D.b = bb; D.h = hh;
+    D.x = al(n); D.y = al(p); D.z = al(m); D.s = al(m);
+    D.rx = al(n); D.ry = al(p); D.rz = al(m); D.lam = al(m); D.wm = al(S.nwm); D.socw = al(m - S.l + 1);
+    D.soceta = al(S.nsoc + 1);
+    D.dx = al(n); D.dy = al(p); D.dz = al(m); D.ds = al(m); D.dsa = al(m); D.dza = al(m); D.tm = al(m); D.gm = al(m);
+    D.r1 = al(n); D.r2 = al(p); D.e1 = al(nm); D.e2 = al(p); D.rhs = al(nk);
+    D.Y = al(S.nnzL + nk); D.Ls = al(S.nnzL + 1); D.invD = al(nk);
+    for (double *q : c->bufs)
+        if (!q) return set_err(h, SCPB_ERR_CUDA, "cone solver: device allocation failed (B=%d)", B);
+    if (cudaMalloc((void **)&c->d_status, sizeof(int) * Bpad) != cudaSuccess ||
+        cudaMalloc((void **)&c->d_iters, sizeof(int) * Bpad) != cudaSuccess ||
+        cudaMalloc((void **)&c->d_scal, sizeof(double) * 5 * Bpad) != cudaSuccess)
+        return set_err(h, SCPB_ERR_CUDA, "cone solver: device allocation failed");
+    D.status = c->d_status; D.iters = c->d_iters;
+    D.pobj = c->d_scal; D.dobj = c->d_scal + Bpad; D.res = c->d_scal + 2 * (size_t)Bpad;
+    c->capB = Bpad; c->capG = G;
+    D.B = B; D.G = G;
+    return SCPB_OK;
+}
+
+// run the solver on the data currently in the grouped buffers (device-resident entry, internal API)
+int scpb_internal_cone_run(scpb_cone_s *c, const IpmOpts &o)
+{
+    scpb_handle_s *h = c->h;
+    const int ng = (c->D.B + c->D.G - 1) / c->D.G;
+    k_ipm_solve<<<ng, IPM_NT, 0, h->stream>>>(c->P, c->D, o);
+    h->launches++;
+    SCPB_CUDA(h, cudaGetLastError());
+    return SCPB_OK;
+}
+
+static IpmOpts make_opts(const scpb_cone_opts *o)
+{
+    IpmOpts r;
+    r.feastol = (o && o->feastol > 0) ? o->feastol : 1e-8;
+    r.abstol = (o && o->abstol > 0) ? o->abstol : 1e-8;
+    r.reltol = (o && o->reltol > 0) ? o->reltol : 1e-8;
+    r.delta = (o && o->delta > 0) ? o->delta : 1e-9;
+    r.delta_dyn = (o && o->delta_dyn > 0) ? o->delta_dyn : 1e-13;
+    r.maxit = (o && o->maxit > 0) ? o->maxit : 100;
+    r.nref = (o && o->nref >= 0) ? o->nref : 2;
+    return r;
+}
+
+extern "C" {
+
+int32_t scpb_cone_setup(scpb_handle h, int32_t n, int32_t p, int32_t m, const int32_t *A_rowptr,
+                        const int32_t *A_colind, const int32_t *G_rowptr, const int32_t *G_colind, int32_t l,
+                        int32_t nsoc, const int32_t *soc_dims, const int32_t *perm, scpb_cone *out)
+{
+    if (!h || !out) return SCPB_ERR_ARG;
+    *out = nullptr;
+    if (n <= 0 || p < 0 || m < 0 || !A_rowptr || !G_rowptr || l < 0 || nsoc < 0 || (nsoc > 0 && !soc_dims))
+        return set_err(h, SCPB_ERR_ARG, "cone_setup: bad arguments");
+    SCPB_CUDA(h, cudaSetDevice(h->device));
+    scpb_cone_s *c = new (std::nothrow) scpb_cone_s();
+    if (!c) return set_err(h, SCPB_ERR_CUDA, "out of host memory");
+    c->h = h;
+    static const int zero = 0;
+    if (!cone_symbolic_build(c->S, n, p, m, A_rowptr, A_colind ? A_colind : &zero, G_rowptr,
+                             G_colind ? G_colind : &zero, l, nsoc, soc_dims, perm)) {
+        int rc = set_err(h, SCPB_ERR_ARG, "cone_setup: %s", c->S.err.c_str());
+        delete c;
+        return rc;
+    }
+    const ConeSymbolic &S = c->S;
+    IpmProgram &P = c->P;
+    P.n = n; P.p = p; P.m = m; P.l = l; P.nsoc = nsoc; P.nk = S.nk; P.nnzL = S.nnzL; P.nlevels = S.nlevels;
+    P.nwm = S.nwm; P.nnzA = (int)S.A_ci.size(); P.nnzG = (int)S.G_ci.size();
+#define UP(f) P.f = upload_ints(c, S.f)
+    UP(soc_dim); UP(soc_off); UP(soc_woff); UP(A_rp); UP(A_ci); UP(G_rp); UP(G_ci);
+    UP(At_rp); UP(At_ri); UP(At_vi); UP(Gt_rp); UP(Gt_ri); UP(Gt_vi); UP(iperm);
+    UP(L_cp); UP(L_ri); UP(Lr_rp); UP(Lr_pos); UP(Lr_col); UP(lvl_ptr); UP(lvl_nodes);
+    UP(ft_lvl_ptr); UP(ft_target); UP(ft_op_ptr); UP(ft_op_a); UP(ft_op_b);
+    UP(sc_lvl_ptr); UP(sc_pos); UP(sc_col); UP(as_ptr); UP(as_a); UP(as_b); UP(as_c); UP(as_src); UP(as_sign);
+#undef UP
+    for (void *d : c->dev_ints)
+        if (!d) {
+            scpb_cone_free(c);
+            return set_err(h, SCPB_ERR_CUDA, "cone_setup: device allocation failed");
+        }
+    *out = c;
+    return SCPB_OK;
+}
+
+int32_t scpb_cone_info(scpb_cone c, int64_t *info)
+{
+    if (!c || !info) return SCPB_ERR_ARG;
+    info[0] = c->S.nk; info[1] = c->S.nnzL; info[2] = c->S.nlevels; info[3] = c->S.factor_ops;
+    info[4] = (int64_t)c->S.as_a.size(); info[5] = c->S.nwm; info[6] = c->capG; info[7] = c->capB;
+    return SCPB_OK;
+}
+
+int32_t scpb_cone_free(scpb_cone c)
+{
+    if (!c) return SCPB_ERR_ARG;
+    cudaSetDevice(c->h->device);
+    cudaStreamSynchronize(c->h->stream);
+    for (void *d : c->dev_ints)
+        if (d) cudaFree(d);
+    for (double *p : c->bufs)
+        if (p) cudaFree(p);
+    if (c->stage) cudaFree(c->stage);
+    if (c->d_status) cudaFree(c->d_status);
+    if (c->d_iters) cudaFree(c->d_iters);
+    if (c->d_scal) cudaFree(c->d_scal);
+    delete c;
+    return SCPB_OK;
+}
+
+int32_t scpb_cone_solve(scpb_cone c, int32_t B, const double *Avals, const double *Gvals, const double *cvec,
+                        const double *bvec, const double *hvec, const scpb_cone_opts *opts, double *x, double *y,
+                        double *z, double *s, double *pobj, double *dobj, int32_t *status, int32_t *iters,
+                        double *seconds)
+{
+    if (!c) return SCPB_ERR_ARG;
+    scpb_handle_s *h = c->h;
+    if (B <= 0 || !cvec || (c->S.p > 0 && !bvec) || (c->S.m > 0 && !hvec)) return set_err(h, SCPB_ERR_ARG, "cone_solve: bad arguments");
+    SCPB_CUDA(h, cudaSetDevice(h->device));
+    const int G = pick_group(B, opts ? opts->group : 0);
+    int rc = cone_reserve(c, B, G);
+    if (rc) return rc;
+    const ConeSymbolic &S = c->S;
+    const int Bpad = c->capB;
+    const size_t maxE = std::max<size_t>({S.A_ci.size(), S.G_ci.size(), (size_t)S.n, (size_t)S.m, (size_t)S.p, 1});
+    if (c->stage_cap < maxE * B) {
+        if (c->stage) cudaFree(c->stage);
+        c->stage = nullptr; c->stage_cap = 0;
+        SCPB_CUDA(h, cudaMalloc((void **)&c->stage, sizeof(double) * maxE * B));
+        c->stage_cap = maxE * B;
+    }
+    cudaStream_t st = h->stream;
+    auto put = [&](const double *src, const double *dstc, size_t E) -> int {
+        if (E == 0) return SCPB_OK;
+        double *dst = const_cast<double *>(dstc);
+        if (!src) { SCPB_CUDA(h, cudaMemsetAsync(dst, 0, sizeof(double) * E * Bpad, st)); return SCPB_OK; }
+        SCPB_CUDA(h, cudaMemcpyAsync(c->stage, src, sizeof(double) * E * B, cudaMemcpyHostToDevice, st));
+        const long long tot = (long long)E * Bpad;
+        k_to_grouped<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(c->stage, dst, (int)E, B, G, Bpad);
+        h->launches++;
+        return SCPB_OK;
+    };
+    if ((rc = put(Avals, c->D.Av, S.A_ci.size())) || (rc = put(Gvals, c->D.Gv, S.G_ci.size())) ||
+        (rc = put(cvec, c->D.c, S.n)) || (rc = put(bvec, c->D.b, S.p)) || (rc = put(hvec, c->D.h, S.m)))
+        return rc;
+    IpmOpts o = make_opts(opts);
+    SCPB_CUDA(h, cudaEventRecord(h->ev0, st));
+    rc = scpb_internal_cone_run(c, o);
+    if (rc) return rc;
+    SCPB_CUDA(h, cudaEventRecord(h->ev1, st));
+    auto get = [&](double *dst, const double *src, size_t E) -> int {
+        if (!dst || E == 0) return SCPB_OK;
+        const long long tot = (long long)E * B;
+        k_from_grouped<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(src, c->stage, (int)E, B, G);
+        h->launches++;
+        SCPB_CUDA(h, cudaMemcpyAsync(dst, c->stage, sizeof(double) * E * B, cudaMemcpyDeviceToHost, st));
+        return SCPB_OK;
+    };
+    if ((rc = get(x, c->D.x, S.n)) || (rc = get(y, c->D.y, S.p)) || (rc = get(z, c->D.z, S.m)) ||
+        (rc = get(s, c->D.s, S.m)))
+        return rc;
+    if (pobj) SCPB_CUDA(h, cudaMemcpyAsync(pobj, c->D.pobj, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+    if (dobj) SCPB_CUDA(h, cudaMemcpyAsync(dobj, c->D.dobj, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+    if (status) SCPB_CUDA(h, cudaMemcpyAsync(status, c->D.status, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    if (iters) SCPB_CUDA(h, cudaMemcpyAsync(iters, c->D.iters, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    SCPB_CUDA(h, cudaStreamSynchronize(st));
+    if (seconds) {
+        float ms = 0.f;
+        SCPB_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        *seconds = ms * 1e-3;
+    }
+    return SCPB_OK;
+}
+
+}  // extern "C"

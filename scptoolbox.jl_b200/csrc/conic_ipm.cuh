@@ -1,0 +1,646 @@
+// conic_ipm.cuh -- batched primal-dual interior-point solver for
+//     min c'x  s.t.  A x = b,  G x + s = h,  s in K = R+^l x SOC(q_1) x ... x SOC(q_nsoc)
+// Replaces solve!(prg) = JuMP.optimize! -> ECOS (src/parser/program.jl:419-424) for a batch of
+// seeds that share one sparsity pattern.  Algorithm family: the one ECOS implements (Mehrotra
+// predictor-corrector, Nesterov-Todd scaling, static + dynamic regularisation of a quasi-definite
+// KKT system, iterative refinement) -- ECOS is an unvendored dependency of the reference, so this
+// is written from the published algorithm (Domahidi et al. 2013; CVXOPT conelp), not from its code.
+//
+// B200 execution model: seeds are independent, so ALL synchronisation is kept inside a CTA.
+// One persistent CTA owns a group of G seeds and runs the complete interior-point solve for them:
+// residual SpMVs, cone scaling, KKT assembly, numeric LDL', triangular solves, line search.
+// Every sparse operation is a "gather program" generated on the host from the shared pattern
+// (conic_symbolic.h); data arrays are group-blocked [group][entry][G] so the G lanes that execute
+// the same program step touch adjacent doubles.  The factorisation and the substitutions are
+// level-scheduled on the elimination tree: a level costs one __syncthreads, never a grid sync.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+struct IpmProgram {  // device copies of ConeSymbolic index arrays
+    int n, p, m, l, nsoc, nk, nnzL, nlevels, nwm, nnzA, nnzG;
+    const int *soc_dim, *soc_off, *soc_woff;
+    const int *A_rp, *A_ci, *G_rp, *G_ci;
+    const int *At_rp, *At_ri, *At_vi, *Gt_rp, *Gt_ri, *Gt_vi;
+    const int *iperm;
+    const int *L_cp, *L_ri, *Lr_rp, *Lr_pos, *Lr_col;
+    const int *lvl_ptr, *lvl_nodes;
+    const int *ft_lvl_ptr, *ft_target, *ft_op_ptr, *ft_op_a, *ft_op_b;
+    const int *sc_lvl_ptr, *sc_pos, *sc_col;
+    const int *as_ptr, *as_a, *as_b, *as_c, *as_src, *as_sign;
+};
+
+struct IpmOpts {
+    double feastol, abstol, reltol;   // ECOS defaults 1e-8
+    double delta;                     // static regularisation
+    double delta_dyn;                 // dynamic regularisation threshold / value
+    int maxit, nref;
+};
+
+struct IpmData {  // group-blocked device arrays, all for B seeds
+    int B, G;
+    // problem data
+    const double *Av, *Gv, *c, *b, *h;
+    // iterates
+    double *x, *y, *z, *s;
+    // work
+    double *rx, *ry, *rz, *lam, *wm, *socw, *soceta;
+    double *dx, *dy, *dz, *ds, *dsa, *dza, *tm, *gm, *r1, *r2, *e1, *e2, *rhs, *Y, *Ls, *invD;
+    // per-seed outputs
+    double *pobj, *dobj, *res;   // res: [3][B] pres, dres, gap
+    int *status, *iters;
+};
+
+enum { IPM_OPTIMAL = 0, IPM_MAXIT = 1, IPM_NUMERICAL = 2 };
+
+#define IPM_MAXG 32
+#define IPM_NT 512
+
+// ---------------------------------------------------------------------------------------------
+struct Ctx {
+    int G, sg, slot, nslots, tid;
+    double *red;   // shared: [8][IPM_NT/32][IPM_MAXG]
+    double *out;   // shared: [8][IPM_MAXG]
+};
+
+// per-seed reduction of up to K values; op 0 = sum, 1 = min, 2 = max. Result in c.out[k*MAXG + sg].
+template <int K>
+__device__ __forceinline__ void seed_reduce(const Ctx &c, double (&v)[K], int op)
+{
+    const int lane = c.tid & 31, warp = c.tid >> 5;
+    const int G = c.G;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        double a = v[k];
+        for (int o = 16; o >= G; o >>= 1) {
+            const double t = __shfl_xor_sync(0xffffffffu, a, o);
+            a = (op == 0) ? a + t : ((op == 1) ? fmin(a, t) : fmax(a, t));
+        }
+        v[k] = a;
+    }
+    __syncthreads();  // protect red/out from the previous use
+    if (lane < G) {
+#pragma unroll
+        for (int k = 0; k < K; k++) c.red[(k * (IPM_NT / 32) + warp) * IPM_MAXG + lane] = v[k];
+    }
+    __syncthreads();
+    if (c.tid < G) {
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            double a = c.red[(k * (IPM_NT / 32)) * IPM_MAXG + c.tid];
+            for (int w = 1; w < IPM_NT / 32; w++) {
+                const double t = c.red[(k * (IPM_NT / 32) + w) * IPM_MAXG + c.tid];
+                a = (op == 0) ? a + t : ((op == 1) ? fmin(a, t) : fmax(a, t));
+            }
+            c.out[k * IPM_MAXG + c.tid] = a;
+        }
+    }
+    __syncthreads();
+}
+
+#define GI(e) ((size_t)(e) * G + sg)
+
+// y = alpha * (M x) [+ y0]  row-wise CSR; M values Mv group-blocked
+__device__ __forceinline__ double row_dot(const int *rp, const int *ci, const double *Mv, const double *x, int r,
+                                          int G, int sg)
+{
+    double acc = 0.0;
+    for (int k = rp[r]; k < rp[r + 1]; k++) acc = fma(Mv[GI(k)], x[GI(ci[k])], acc);
+    return acc;
+}
+// (M' y)_v via the transposed pattern with value map
+__device__ __forceinline__ double col_dot(const int *trp, const int *tri, const int *tvi, const double *Mv,
+                                          const double *y, int v, int G, int sg)
+{
+    double acc = 0.0;
+    for (int k = trp[v]; k < trp[v + 1]; k++) acc = fma(Mv[GI(tvi[k])], y[GI(tri[k])], acc);
+    return acc;
+}
+
+// ---- cone operators (one thread per LP row / per SOC cone, per seed) ----
+// out = W^-2 * in
+__device__ void apply_winv2(const IpmProgram &P, const Ctx &c, const double *wm, const double *socw,
+                            const double *soceta, const double *in, double *out)
+{
+    const int G = c.G, sg = c.sg;
+    for (int r = c.slot; r < P.l; r += c.nslots) out[GI(r)] = wm[GI(r)] * in[GI(r)];
+    for (int k = c.slot; k < P.nsoc; k += c.nslots) {
+        const int o = P.soc_off[k], q = P.soc_dim[k], wo = o - P.l;
+        const double ie2 = 1.0 / soceta[GI(k)];  // soceta holds eta^2
+        double vd = socw[GI(wo)] * in[GI(o)];
+        for (int i = 1; i < q; i++) vd -= socw[GI(wo + i)] * in[GI(o + i)];
+        // (2 v v' - J) in, v = (w0, -w1)
+        out[GI(o)] = ie2 * (2.0 * socw[GI(wo)] * vd - in[GI(o)]);
+        for (int i = 1; i < q; i++) out[GI(o + i)] = ie2 * (-2.0 * socw[GI(wo + i)] * vd + in[GI(o + i)]);
+    }
+}
+// out = W^2 * in
+__device__ void apply_w2(const IpmProgram &P, const Ctx &c, const double *wm, const double *socw,
+                         const double *soceta, const double *in, double *out)
+{
+    const int G = c.G, sg = c.sg;
+    for (int r = c.slot; r < P.l; r += c.nslots) out[GI(r)] = in[GI(r)] / wm[GI(r)];
+    for (int k = c.slot; k < P.nsoc; k += c.nslots) {
+        const int o = P.soc_off[k], q = P.soc_dim[k], wo = o - P.l;
+        const double e2 = soceta[GI(k)];
+        double wd = 0.0;
+        for (int i = 0; i < q; i++) wd += socw[GI(wo + i)] * in[GI(o + i)];
+        out[GI(o)] = e2 * (2.0 * socw[GI(wo)] * wd - in[GI(o)]);
+        for (int i = 1; i < q; i++) out[GI(o + i)] = e2 * (2.0 * socw[GI(wo + i)] * wd + in[GI(o + i)]);
+    }
+}
+
+// ---- LDL' : assemble, factor, solve ----
+__device__ void kkt_assemble(const IpmProgram &P, const Ctx &c, const IpmData &D, const double *Av, const double *Gv,
+                             const double *wmx, double *Y, double delta)
+{
+    const int G = c.G, sg = c.sg;
+    const int ntgt = P.nnzL + P.nk;
+    for (int t = c.slot; t < ntgt; t += c.nslots) {
+        double acc = delta * (double)P.as_sign[t];
+        const int src = P.as_src[t];
+        if (src >= 0) acc += Av[GI(src)];
+        for (int k = P.as_ptr[t]; k < P.as_ptr[t + 1]; k++)
+            acc = fma(Gv[GI(P.as_a[k])] * Gv[GI(P.as_b[k])], wmx[GI(P.as_c[k])], acc);
+        Y[GI(t)] = acc;
+    }
+    __syncthreads();
+}
+
+__device__ void kkt_factor(const IpmProgram &P, const Ctx &c, double *Y, double *Ls, double *invD, double delta_dyn)
+{
+    const int G = c.G, sg = c.sg;
+    for (int lv = 0; lv < P.nlevels; lv++) {
+        for (int w = P.ft_lvl_ptr[lv] + c.slot; w < P.ft_lvl_ptr[lv + 1]; w += c.nslots) {
+            const int t = P.ft_target[w];
+            double acc = Y[GI(t)];
+            for (int k = P.ft_op_ptr[w]; k < P.ft_op_ptr[w + 1]; k++)
+                acc = fma(-Y[GI(P.ft_op_a[k])], Ls[GI(P.ft_op_b[k])], acc);
+            if (t >= P.nnzL) {  // diagonal: dynamic regularisation keeps the expected inertia
+                const double sgn = (double)P.as_sign[t];
+                if (!(sgn * acc > delta_dyn)) acc = sgn * delta_dyn;
+                invD[GI(t - P.nnzL)] = 1.0 / acc;
+            }
+            Y[GI(t)] = acc;
+        }
+        __syncthreads();
+        for (int w = P.sc_lvl_ptr[lv] + c.slot; w < P.sc_lvl_ptr[lv + 1]; w += c.nslots) {
+            const int q = P.sc_pos[w];
+            Ls[GI(q)] = Y[GI(q)] * invD[GI(P.sc_col[w])];
+        }
+        __syncthreads();
+    }
+}
+
+// in-place solve of (L D L') v = rhs on the permuted vector v
+__device__ void kkt_ldl_solve(const IpmProgram &P, const Ctx &c, const double *Ls, const double *invD, double *v)
+{
+    const int G = c.G, sg = c.sg;
+    for (int lv = 0; lv < P.nlevels; lv++) {   // forward, rows of L
+        for (int w = P.lvl_ptr[lv] + c.slot; w < P.lvl_ptr[lv + 1]; w += c.nslots) {
+            const int i = P.lvl_nodes[w];
+            double acc = v[GI(i)];
+            for (int k = P.Lr_rp[i]; k < P.Lr_rp[i + 1]; k++) acc = fma(-Ls[GI(P.Lr_pos[k])], v[GI(P.Lr_col[k])], acc);
+            v[GI(i)] = acc;
+        }
+        __syncthreads();
+    }
+    for (int i = c.slot; i < P.nk; i += c.nslots) v[GI(i)] *= invD[GI(i)];
+    __syncthreads();
+    for (int lv = P.nlevels - 1; lv >= 0; lv--) {   // backward, columns of L
+        for (int w = P.lvl_ptr[lv] + c.slot; w < P.lvl_ptr[lv + 1]; w += c.nslots) {
+            const int j = P.lvl_nodes[w];
+            double acc = v[GI(j)];
+            for (int k = P.L_cp[j]; k < P.L_cp[j + 1]; k++) acc = fma(-Ls[GI(k)], v[GI(P.L_ri[k])], acc);
+            v[GI(j)] = acc;
+        }
+        __syncthreads();
+    }
+}
+
+// Solve [0 A' G'; A 0 0; G 0 -W'W][dx;dy;dz] = [bx;by;bz] through the reduced system
+//   (G' W^-2 G) dx + A' dy = bx + G' W^-2 bz ,  A dx = by ,  dz = W^-2 (G dx - bz)
+// with nref steps of iterative refinement against the unregularised reduced operator.
+// bx,by,bz are overwritten/consumed: bx -> r1 (in place), by -> r2 (kept), bz kept.
+__device__ void kkt_solve(const IpmProgram &P, const Ctx &c, const IpmData &D, const double *Av, const double *Gv,
+                          const double *wm, const double *socw, const double *soceta, double *bx, const double *by,
+                          const double *bz, double *dx, double *dy, double *dz, double *tm, double *gm, double *e1,
+                          double *e2, double *rhs, const double *Ls, const double *invD, int nref)
+{
+    const int G = c.G, sg = c.sg;
+    // tm = W^-2 bz ; r1 = bx + G' tm
+    apply_winv2(P, c, wm, socw, soceta, bz, tm);
+    __syncthreads();
+    for (int v = c.slot; v < P.n; v += c.nslots) {
+        const double r = bx[GI(v)] + col_dot(P.Gt_rp, P.Gt_ri, P.Gt_vi, Gv, tm, v, G, sg);
+        bx[GI(v)] = r;
+        rhs[GI(P.iperm[v])] = r;
+        dx[GI(v)] = 0.0;
+    }
+    for (int r = c.slot; r < P.p; r += c.nslots) { rhs[GI(P.iperm[P.n + r])] = by[GI(r)]; dy[GI(r)] = 0.0; }
+    __syncthreads();
+    for (int it = 0;; it++) {
+        kkt_ldl_solve(P, c, Ls, invD, rhs);
+        for (int v = c.slot; v < P.n; v += c.nslots) dx[GI(v)] += rhs[GI(P.iperm[v])];
+        for (int r = c.slot; r < P.p; r += c.nslots) dy[GI(r)] += rhs[GI(P.iperm[P.n + r])];
+        __syncthreads();
+        if (it >= nref) break;
+        // residual of the reduced system: e1 = r1 - (G' W^-2 G dx + A' dy), e2 = by - A dx
+        for (int r = c.slot; r < P.m; r += c.nslots) gm[GI(r)] = row_dot(P.G_rp, P.G_ci, Gv, dx, r, G, sg);
+        __syncthreads();
+        apply_winv2(P, c, wm, socw, soceta, gm, e1);  // e1: max(n,m)-sized scratch holding W^-2 G dx
+        __syncthreads();
+        for (int v = c.slot; v < P.n; v += c.nslots) {
+            const double r = bx[GI(v)] - col_dot(P.Gt_rp, P.Gt_ri, P.Gt_vi, Gv, e1, v, G, sg) -
+                             col_dot(P.At_rp, P.At_ri, P.At_vi, Av, dy, v, G, sg);
+            rhs[GI(P.iperm[v])] = r;
+        }
+        for (int r = c.slot; r < P.p; r += c.nslots)
+            rhs[GI(P.iperm[P.n + r])] = by[GI(r)] - row_dot(P.A_rp, P.A_ci, Av, dx, r, G, sg);
+        __syncthreads();
+    }
+    // dz = W^-2 (G dx - bz)
+    for (int r = c.slot; r < P.m; r += c.nslots) gm[GI(r)] = row_dot(P.G_rp, P.G_ci, Gv, dx, r, G, sg) - bz[GI(r)];
+    __syncthreads();
+    apply_winv2(P, c, wm, socw, soceta, gm, dz);
+    __syncthreads();
+    (void)e2; (void)D;
+}
+
+// smallest t with u + t e in K  (max over cones); thread-partial, to be max-reduced
+__device__ double cone_shift_partial(const IpmProgram &P, const Ctx &c, const double *u)
+{
+    const int G = c.G, sg = c.sg;
+    double t = -CUDART_INF;
+    for (int r = c.slot; r < P.l; r += c.nslots) t = fmax(t, -u[GI(r)]);
+    for (int k = c.slot; k < P.nsoc; k += c.nslots) {
+        const int o = P.soc_off[k], q = P.soc_dim[k];
+        double nn = 0.0;
+        for (int i = 1; i < q; i++) nn += u[GI(o + i)] * u[GI(o + i)];
+        t = fmax(t, sqrt(nn) - u[GI(o)]);
+    }
+    return t;
+}
+
+// largest alpha with u + alpha*du in K (thread-partial min)
+__device__ double cone_alpha_partial(const IpmProgram &P, const Ctx &c, const double *u, const double *du)
+{
+    const int G = c.G, sg = c.sg;
+    double a = CUDART_INF;
+    for (int r = c.slot; r < P.l; r += c.nslots) {
+        const double d = du[GI(r)];
+        if (d < 0.0) a = fmin(a, -u[GI(r)] / d);
+    }
+    for (int k = c.slot; k < P.nsoc; k += c.nslots) {
+        const int o = P.soc_off[k], q = P.soc_dim[k];
+        const double l0 = u[GI(o)], v0 = du[GI(o)];
+        double aa = v0 * v0, bb = l0 * v0, cc = l0 * l0;
+        for (int i = 1; i < q; i++) {
+            const double l1 = u[GI(o + i)], v1 = du[GI(o + i)];
+            aa -= v1 * v1; bb -= l1 * v1; cc -= l1 * l1;
+        }
+        bb *= 2.0;
+        if (fabs(aa) < 1e-300) { if (bb < 0.0) a = fmin(a, -cc / bb); continue; }
+        const double disc = bb * bb - 4.0 * aa * cc;
+        if (aa < 0.0) a = fmin(a, (-bb - sqrt(fmax(disc, 0.0))) / (2.0 * aa));
+        else if (disc >= 0.0 && bb < 0.0) a = fmin(a, (-bb - sqrt(disc)) / (2.0 * aa));
+    }
+    return a;
+}
+
+// Nesterov-Todd scaling from (s, z): lam = W z, W^-2 data.  LP: wm = z/s; SOC: wbar, eta^2.
+__device__ void nt_scaling(const IpmProgram &P, const Ctx &c, const double *s, const double *z, double *lam,
+                           double *wm, double *socw, double *soceta)
+{
+    const int G = c.G, sg = c.sg;
+    for (int r = c.slot; r < P.l; r += c.nslots) {
+        const double sv = s[GI(r)], zv = z[GI(r)];
+        wm[GI(r)] = zv / sv;
+        lam[GI(r)] = sqrt(sv * zv);
+    }
+    for (int k = c.slot; k < P.nsoc; k += c.nslots) {
+        const int o = P.soc_off[k], q = P.soc_dim[k], wo = o - P.l, wb = P.soc_woff[k];
+        double ss = s[GI(o)] * s[GI(o)], zz = z[GI(o)] * z[GI(o)], sz = s[GI(o)] * z[GI(o)];
+        for (int i = 1; i < q; i++) {
+            ss -= s[GI(o + i)] * s[GI(o + i)];
+            zz -= z[GI(o + i)] * z[GI(o + i)];
+            sz += s[GI(o + i)] * z[GI(o + i)];
+        }
+        const double sn = sqrt(ss), zn = sqrt(zz);
+        const double gam = sqrt(0.5 * (1.0 + sz / (sn * zn)));
+        const double ig = 1.0 / (2.0 * gam);
+        const double e2 = sn / zn;  // eta^2
+        const double eta = sqrt(e2);
+        const double w0 = (s[GI(o)] / sn + z[GI(o)] / zn) * ig;
+        socw[GI(wo)] = w0;
+        double w1z = 0.0;
+        for (int i = 1; i < q; i++) {
+            const double w1 = (s[GI(o + i)] / sn - z[GI(o + i)] / zn) * ig;
+            socw[GI(wo + i)] = w1;
+            w1z += w1 * z[GI(o + i)];
+        }
+        soceta[GI(k)] = e2;
+        // lam = W z = eta [w0 z0 + w1.z1 ; z0 w1 + z1 + w1 (w1.z1)/(1+w0)]
+        lam[GI(o)] = eta * (w0 * z[GI(o)] + w1z);
+        for (int i = 1; i < q; i++)
+            lam[GI(o + i)] = eta * (z[GI(o)] * socw[GI(wo + i)] + z[GI(o + i)] + socw[GI(wo + i)] * w1z / (1.0 + w0));
+        // dense W^-2 block for the KKT assembly: (2 v v' - J)/eta^2, v = (w0, -w1)
+        for (int i = 0; i < q; i++)
+            for (int j = 0; j < q; j++) {
+                const double vi = (i == 0) ? w0 : -socw[GI(wo + i)], vj = (j == 0) ? w0 : -socw[GI(wo + j)];
+                const double Jij = (i == j) ? ((i == 0) ? 1.0 : -1.0) : 0.0;
+                wm[GI(wb + i * q + j)] = (2.0 * vi * vj - Jij) / e2;
+            }
+    }
+}
+
+__device__ void set_identity_scaling(const IpmProgram &P, const Ctx &c, double *wm, double *socw, double *soceta)
+{
+    const int G = c.G, sg = c.sg;
+    for (int r = c.slot; r < P.l; r += c.nslots) wm[GI(r)] = 1.0;
+    for (int k = c.slot; k < P.nsoc; k += c.nslots) {
+        const int o = P.soc_off[k], q = P.soc_dim[k], wo = o - P.l, wb = P.soc_woff[k];
+        soceta[GI(k)] = 1.0;
+        for (int i = 0; i < q; i++) socw[GI(wo + i)] = (i == 0) ? 1.0 : 0.0;
+        for (int i = 0; i < q; i++)
+            for (int j = 0; j < q; j++) wm[GI(wb + i * q + j)] = (i == j) ? 1.0 : 0.0;
+    }
+}
+
+// tmp = -s + W( lam \ (sigma*mu*e - (W^-1 dsa) o (W dza)) )   (combined-direction right-hand side)
+__device__ void combined_tmp(const IpmProgram &P, const Ctx &c, const double *s, const double *z, const double *lam,
+                             const double *socw, const double *soceta, const double *dsa, const double *dza,
+                             const double *sigmu /*shared per seed*/, double *tmp)
+{
+    const int G = c.G, sg = c.sg;
+    const double sm = sigmu[sg];
+    for (int r = c.slot; r < P.l; r += c.nslots)
+        tmp[GI(r)] = -s[GI(r)] + (sm - dsa[GI(r)] * dza[GI(r)]) / z[GI(r)];
+    for (int k = c.slot; k < P.nsoc; k += c.nslots) {
+        const int o = P.soc_off[k], q = P.soc_dim[k], wo = o - P.l;
+        const double eta = sqrt(soceta[GI(k)]), w0 = socw[GI(wo)];
+        // a = W^-1 dsa, b = W dza  (computed on the fly, q small)
+        double w1ds = 0.0, w1dz = 0.0;
+        for (int i = 1; i < q; i++) { w1ds += socw[GI(wo + i)] * dsa[GI(o + i)]; w1dz += socw[GI(wo + i)] * dza[GI(o + i)]; }
+        const double a0 = (w0 * dsa[GI(o)] - w1ds) / eta, b0 = eta * (w0 * dza[GI(o)] + w1dz);
+        // Jordan product a o b = (a'b, a0 b1 + b0 a1)
+        double ab = a0 * b0;
+        for (int i = 1; i < q; i++) {
+            const double w1 = socw[GI(wo + i)];
+            const double a1 = (-dsa[GI(o)] * w1 + dsa[GI(o + i)] + w1 * w1ds / (1.0 + w0)) / eta;
+            const double b1 = eta * (dza[GI(o)] * w1 + dza[GI(o + i)] + w1 * w1dz / (1.0 + w0));
+            ab += a1 * b1;
+        }
+        // d = sigma*mu*e - a o b ; u = lam \ d ; tmp = -s + W u.   Two passes over the cone (q small).
+        const double l0 = lam[GI(o)];
+        double l1l1 = 0.0, l1d1 = 0.0;
+        const double d0 = sm - ab;
+        for (int i = 1; i < q; i++) {
+            const double w1 = socw[GI(wo + i)];
+            const double a1 = (-dsa[GI(o)] * w1 + dsa[GI(o + i)] + w1 * w1ds / (1.0 + w0)) / eta;
+            const double b1 = eta * (dza[GI(o)] * w1 + dza[GI(o + i)] + w1 * w1dz / (1.0 + w0));
+            const double d1 = -(a0 * b1 + b0 * a1);
+            l1l1 += lam[GI(o + i)] * lam[GI(o + i)];
+            l1d1 += lam[GI(o + i)] * d1;
+        }
+        const double det = l0 * l0 - l1l1;
+        const double u0 = (l0 * d0 - l1d1) / det;
+        double w1u = 0.0;
+        for (int i = 1; i < q; i++) {
+            const double w1 = socw[GI(wo + i)];
+            const double a1 = (-dsa[GI(o)] * w1 + dsa[GI(o + i)] + w1 * w1ds / (1.0 + w0)) / eta;
+            const double b1 = eta * (dza[GI(o)] * w1 + dza[GI(o + i)] + w1 * w1dz / (1.0 + w0));
+            const double d1 = -(a0 * b1 + b0 * a1);
+            const double u1 = (d1 - u0 * lam[GI(o + i)]) / l0;
+            tmp[GI(o + i)] = u1;  // stash u1
+            w1u += w1 * u1;
+        }
+        const double t0 = eta * (w0 * u0 + w1u);
+        for (int i = 1; i < q; i++) {
+            const double w1 = socw[GI(wo + i)], u1 = tmp[GI(o + i)];
+            tmp[GI(o + i)] = -s[GI(o + i)] + eta * (u0 * w1 + u1 + w1 * w1u / (1.0 + w0));
+        }
+        tmp[GI(o)] = -s[GI(o)] + t0;
+    }
+}
+
+// =============================================================================================
+__global__ void __launch_bounds__(IPM_NT) k_ipm_solve(const IpmProgram P, const IpmData D, const IpmOpts O)
+{
+    __shared__ double s_red[8 * (IPM_NT / 32) * IPM_MAXG];
+    __shared__ double s_out[8 * IPM_MAXG];
+    __shared__ double s_nb[IPM_MAXG], s_nh[IPM_MAXG], s_nc[IPM_MAXG];
+    __shared__ double s_mu[IPM_MAXG], s_sigmu[IPM_MAXG], s_alpha[IPM_MAXG], s_scale[IPM_MAXG];
+    __shared__ int s_done[IPM_MAXG], s_status[IPM_MAXG], s_iters[IPM_MAXG], s_alldone;
+
+    Ctx c;
+    c.G = D.G; c.tid = threadIdx.x; c.sg = c.tid % c.G; c.slot = c.tid / c.G; c.nslots = IPM_NT / c.G;
+    c.red = s_red; c.out = s_out;
+    const int G = c.G, sg = c.sg;
+    const size_t g = blockIdx.x;
+    const int seed = (int)g * G + sg;
+    const bool live = seed < D.B;  // padded seeds replicate work harmlessly (arrays are padded)
+    (void)live;
+
+#define GP(arr, E) ((arr) + g * (size_t)(E) * G)
+    const double *Av = GP(D.Av, P.nnzA), *Gv = GP(D.Gv, P.nnzG), *cc = GP(D.c, P.n), *bb = GP(D.b, P.p), *hh = GP(D.h, P.m);
+    double *x = GP(D.x, P.n), *y = GP(D.y, P.p), *z = GP(D.z, P.m), *s = GP(D.s, P.m);
+    double *rx = GP(D.rx, P.n), *ry = GP(D.ry, P.p), *rz = GP(D.rz, P.m), *lam = GP(D.lam, P.m);
+    double *wm = GP(D.wm, P.nwm), *socw = GP(D.socw, P.m - P.l + 1), *soceta = GP(D.soceta, P.nsoc + 1);
+    double *dx = GP(D.dx, P.n), *dy = GP(D.dy, P.p), *dz = GP(D.dz, P.m), *ds = GP(D.ds, P.m);
+    double *dsa = GP(D.dsa, P.m), *dza = GP(D.dza, P.m), *tm = GP(D.tm, P.m), *gm = GP(D.gm, P.m);
+    double *r1 = GP(D.r1, P.n), *r2 = GP(D.r2, P.p);
+    const int nm = (P.n > P.m ? P.n : P.m);
+    double *e1 = GP(D.e1, nm), *e2 = GP(D.e2, P.p), *rhs = GP(D.rhs, P.nk);
+    double *Y = GP(D.Y, P.nnzL + P.nk), *Ls = GP(D.Ls, P.nnzL + 1), *invD = GP(D.invD, P.nk);
+#undef GP
+
+    if (c.tid < G) { s_done[c.tid] = 0; s_status[c.tid] = IPM_MAXIT; s_iters[c.tid] = 0; }
+    // ---- data norms ----
+    {
+        double v[3] = {0.0, 0.0, 0.0};
+        for (int i = c.slot; i < P.p; i += c.nslots) v[0] += bb[GI(i)] * bb[GI(i)];
+        for (int i = c.slot; i < P.m; i += c.nslots) v[1] += hh[GI(i)] * hh[GI(i)];
+        for (int i = c.slot; i < P.n; i += c.nslots) v[2] += cc[GI(i)] * cc[GI(i)];
+        seed_reduce<3>(c, v, 0);
+        if (c.tid < G) {
+            s_nb[c.tid] = fmax(1.0, sqrt(s_out[0 * IPM_MAXG + c.tid]));
+            s_nh[c.tid] = fmax(1.0, sqrt(s_out[1 * IPM_MAXG + c.tid]));
+            s_nc[c.tid] = fmax(1.0, sqrt(s_out[2 * IPM_MAXG + c.tid]));
+        }
+        __syncthreads();
+    }
+    // ---- starting point (CVXOPT conelp 7.1 / ECOS init): factor with W = I ----
+    set_identity_scaling(P, c, wm, socw, soceta);
+    __syncthreads();
+    kkt_assemble(P, c, D, Av, Gv, wm, Y, O.delta);
+    kkt_factor(P, c, Y, Ls, invD, O.delta_dyn);
+    // solve 1: [0;b;h] -> x, s = h - G x
+    for (int v = c.slot; v < P.n; v += c.nslots) r1[GI(v)] = 0.0;
+    __syncthreads();
+    kkt_solve(P, c, D, Av, Gv, wm, socw, soceta, r1, bb, hh, x, dy, dz, tm, gm, e1, e2, rhs, Ls, invD, O.nref);
+    for (int r = c.slot; r < P.m; r += c.nslots) s[GI(r)] = -dz[GI(r)];
+    __syncthreads();
+    {
+        double vv[1] = {cone_shift_partial(P, c, s)};
+        double w2[1] = {0.0};
+        for (int r = c.slot; r < P.m; r += c.nslots) w2[0] += s[GI(r)] * s[GI(r)];
+        seed_reduce<1>(c, vv, 2);
+        const double ts = s_out[sg];
+        __syncthreads();
+        seed_reduce<1>(c, w2, 0);
+        const double ns = sqrt(s_out[sg]);
+        if (ts >= -1e-8 * fmax(1.0, ns)) {
+            const double sh = 1.0 + ts;
+            for (int r = c.slot; r < P.l; r += c.nslots) s[GI(r)] += sh;
+            for (int k = c.slot; k < P.nsoc; k += c.nslots) s[GI(P.soc_off[k])] += sh;
+        }
+        __syncthreads();
+    }
+    // solve 2: [-c;0;0] -> y, z
+    for (int v = c.slot; v < P.n; v += c.nslots) r1[GI(v)] = -cc[GI(v)];
+    for (int r = c.slot; r < P.p; r += c.nslots) r2[GI(r)] = 0.0;
+    for (int r = c.slot; r < P.m; r += c.nslots) rz[GI(r)] = 0.0;
+    __syncthreads();
+    kkt_solve(P, c, D, Av, Gv, wm, socw, soceta, r1, r2, rz, dx, y, z, tm, gm, e1, e2, rhs, Ls, invD, O.nref);
+    {
+        double vv[1] = {cone_shift_partial(P, c, z)};
+        double w2[1] = {0.0};
+        for (int r = c.slot; r < P.m; r += c.nslots) w2[0] += z[GI(r)] * z[GI(r)];
+        seed_reduce<1>(c, vv, 2);
+        const double tz = s_out[sg];
+        __syncthreads();
+        seed_reduce<1>(c, w2, 0);
+        const double nz = sqrt(s_out[sg]);
+        if (tz >= -1e-8 * fmax(1.0, nz)) {
+            const double sh = 1.0 + tz;
+            for (int r = c.slot; r < P.l; r += c.nslots) z[GI(r)] += sh;
+            for (int k = c.slot; k < P.nsoc; k += c.nslots) z[GI(P.soc_off[k])] += sh;
+        }
+        __syncthreads();
+    }
+
+    const double deg = (double)(P.l + P.nsoc);
+    for (int it = 0; it <= O.maxit; it++) {
+        // ---- residuals + objective pieces ----
+        double v[7] = {0, 0, 0, 0, 0, 0, 0};
+        for (int i = c.slot; i < P.n; i += c.nslots) {
+            const double r = cc[GI(i)] + col_dot(P.At_rp, P.At_ri, P.At_vi, Av, y, i, G, sg) +
+                             col_dot(P.Gt_rp, P.Gt_ri, P.Gt_vi, Gv, z, i, G, sg);
+            rx[GI(i)] = r;
+            v[0] += r * r;
+            v[3] += cc[GI(i)] * x[GI(i)];
+        }
+        for (int i = c.slot; i < P.p; i += c.nslots) {
+            const double r = row_dot(P.A_rp, P.A_ci, Av, x, i, G, sg) - bb[GI(i)];
+            ry[GI(i)] = r;
+            v[1] += r * r;
+            v[4] += bb[GI(i)] * y[GI(i)];
+        }
+        for (int i = c.slot; i < P.m; i += c.nslots) {
+            const double r = row_dot(P.G_rp, P.G_ci, Gv, x, i, G, sg) + s[GI(i)] - hh[GI(i)];
+            rz[GI(i)] = r;
+            v[2] += r * r;
+            v[5] += hh[GI(i)] * z[GI(i)];
+            v[6] += s[GI(i)] * z[GI(i)];
+        }
+        seed_reduce<7>(c, v, 0);
+        if (c.tid < G) {
+            const int q = c.tid;
+            const double nrx = sqrt(s_out[0 * IPM_MAXG + q]), nry = sqrt(s_out[1 * IPM_MAXG + q]),
+                         nrz = sqrt(s_out[2 * IPM_MAXG + q]);
+            const double pcost = s_out[3 * IPM_MAXG + q], dcost = -s_out[4 * IPM_MAXG + q] - s_out[5 * IPM_MAXG + q];
+            const double gap = s_out[6 * IPM_MAXG + q];
+            const double pres = fmax(nry / s_nb[q], nrz / s_nh[q]), dres = nrx / s_nc[q];
+            const double relgap = gap / fmax(fmax(fabs(pcost), fabs(dcost)), 1.0);
+            s_mu[q] = gap / deg;
+            if (!s_done[q]) {
+                const int sd = (int)g * G + q;
+                if (sd < D.B) {
+                    D.pobj[sd] = pcost; D.dobj[sd] = dcost;
+                    D.res[sd] = pres; D.res[D.B + sd] = dres; D.res[2 * D.B + sd] = gap;
+                }
+                s_iters[q] = it;
+                if (!(isfinite(pres) && isfinite(dres) && isfinite(gap))) { s_done[q] = 1; s_status[q] = IPM_NUMERICAL; }
+                else if (pres <= O.feastol && dres <= O.feastol && (gap <= O.abstol || relgap <= O.reltol)) {
+                    s_done[q] = 1; s_status[q] = IPM_OPTIMAL;
+                } else if (it == O.maxit) { s_done[q] = 1; s_status[q] = IPM_MAXIT; }
+            }
+        }
+        __syncthreads();
+        if (c.tid == 0) {
+            int all = 1;
+            for (int q = 0; q < G; q++) all &= (s_done[q] || ((int)g * G + q >= D.B));
+            s_alldone = all;
+        }
+        __syncthreads();
+        if (s_alldone) break;
+
+        // ---- scaling, KKT assembly, factorisation ----
+        nt_scaling(P, c, s, z, lam, wm, socw, soceta);
+        __syncthreads();
+        kkt_assemble(P, c, D, Av, Gv, wm, Y, O.delta);
+        kkt_factor(P, c, Y, Ls, invD, O.delta_dyn);
+
+        // ---- affine direction: bx=-rx, by=-ry, bz=-rz+s ; ds = -s - W^2 dz ----
+        for (int i = c.slot; i < P.n; i += c.nslots) r1[GI(i)] = -rx[GI(i)];
+        for (int i = c.slot; i < P.p; i += c.nslots) r2[GI(i)] = -ry[GI(i)];
+        for (int i = c.slot; i < P.m; i += c.nslots) ds[GI(i)] = -rz[GI(i)] + s[GI(i)];  // ds used as bz scratch
+        __syncthreads();
+        kkt_solve(P, c, D, Av, Gv, wm, socw, soceta, r1, r2, ds, dx, dy, dza, tm, gm, e1, e2, rhs, Ls, invD, O.nref);
+        apply_w2(P, c, wm, socw, soceta, dza, dsa);
+        __syncthreads();
+        for (int i = c.slot; i < P.m; i += c.nslots) dsa[GI(i)] = -s[GI(i)] - dsa[GI(i)];
+        __syncthreads();
+        {
+            double a[1] = {fmin(cone_alpha_partial(P, c, s, dsa), cone_alpha_partial(P, c, z, dza))};
+            seed_reduce<1>(c, a, 1);
+            if (c.tid < G) {
+                const double al = fmin(1.0, s_out[c.tid]);
+                const double sig = (1.0 - al) * (1.0 - al) * (1.0 - al);
+                s_sigmu[c.tid] = sig * s_mu[c.tid];
+                s_scale[c.tid] = 1.0 - sig;
+            }
+            __syncthreads();
+        }
+        // ---- combined direction ----
+        combined_tmp(P, c, s, z, lam, socw, soceta, dsa, dza, s_sigmu, tm);
+        __syncthreads();
+        {
+            const double sc = s_scale[sg];
+            for (int i = c.slot; i < P.n; i += c.nslots) r1[GI(i)] = -sc * rx[GI(i)];
+            for (int i = c.slot; i < P.p; i += c.nslots) r2[GI(i)] = -sc * ry[GI(i)];
+            for (int i = c.slot; i < P.m; i += c.nslots) {
+                const double t = tm[GI(i)];
+                dsa[GI(i)] = t;                        // keep tmp
+                ds[GI(i)] = -sc * rz[GI(i)] - t;       // bz
+            }
+        }
+        __syncthreads();
+        kkt_solve(P, c, D, Av, Gv, wm, socw, soceta, r1, r2, ds, dx, dy, dz, tm, gm, e1, e2, rhs, Ls, invD, O.nref);
+        apply_w2(P, c, wm, socw, soceta, dz, ds);
+        __syncthreads();
+        for (int i = c.slot; i < P.m; i += c.nslots) ds[GI(i)] = dsa[GI(i)] - ds[GI(i)];
+        __syncthreads();
+        {
+            double a[1] = {fmin(cone_alpha_partial(P, c, s, ds), cone_alpha_partial(P, c, z, dz))};
+            seed_reduce<1>(c, a, 1);
+            if (c.tid < G) s_alpha[c.tid] = s_done[c.tid] ? 0.0 : fmin(1.0, 0.99 * s_out[c.tid]);
+            __syncthreads();
+        }
+        {
+            const double al = s_alpha[sg];
+            if (al > 0.0) {
+                for (int i = c.slot; i < P.n; i += c.nslots) x[GI(i)] += al * dx[GI(i)];
+                for (int i = c.slot; i < P.p; i += c.nslots) y[GI(i)] += al * dy[GI(i)];
+                for (int i = c.slot; i < P.m; i += c.nslots) { z[GI(i)] += al * dz[GI(i)]; s[GI(i)] += al * ds[GI(i)]; }
+            }
+        }
+        __syncthreads();
+    }
+    if (c.tid < G) {
+        const int sd = (int)g * G + c.tid;
+        if (sd < D.B) { D.status[sd] = s_status[c.tid]; D.iters[sd] = s_iters[c.tid]; }
+    }
+}
+#undef GI

@@ -1,0 +1,290 @@
+// conic_symbolic.h -- host-side (C++) symbolic analysis for the batched interior-point solver.
+//
+// The cone program   min c'x  s.t.  A x = b,  G x + s = h,  s in K = R+^l x SOC(q_1) x ...
+// (the form ECOS receives from JuMP/MOI in the reference: src/parser/program.jl:419-424) has a
+// sparsity pattern that is SHARED by every seed of a batch.  Everything that depends only on the
+// pattern is computed once here and uploaded as index programs:
+//   * the reduced KKT matrix   M = [ dI + G' W^-2 G   A' ; A   -dI ]   in a caller-supplied
+//     elimination order (stage-wise nested dissection from the host template),
+//   * its elimination tree, the fill pattern of L (M = L D L'), the level schedule (etree height),
+//   * gather programs: KKT assembly (triples G*G*W^-2 / direct A entries), numeric factorisation
+//     (pairs Y_ik * L_jk per target), forward / backward substitution (row / column lists).
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <numeric>
+#include <string>
+#include <vector>
+
+struct ConeSymbolic {
+    int n = 0, p = 0, m = 0, l = 0, nsoc = 0;
+    int nk = 0;                       // n + p  (KKT dimension)
+    std::vector<int> soc_dim, soc_off;   // row offset (within G rows) of each SOC
+    std::vector<int> soc_woff;           // offset of each SOC's dense W^-2 block inside the Wm array
+    int nwm = 0;                      // l + sum q^2
+    // patterns (CSR) and transposes (CSC as CSR of the transpose, with value index map)
+    std::vector<int> A_rp, A_ci, G_rp, G_ci;
+    std::vector<int> At_rp, At_ri, At_vi, Gt_rp, Gt_ri, Gt_vi;
+    // permutation: perm[k] = node eliminated k-th; iperm[node] = k
+    std::vector<int> perm, iperm;
+    // L pattern: CSC over permuted nodes, strictly lower part; D separate
+    std::vector<int> L_cp, L_ri;      // size nk+1, nnzL
+    std::vector<int> Lr_rp, Lr_pos, Lr_col;  // CSR view of L: for each row the (position, column) list
+    int nnzL = 0;
+    // level schedule
+    int nlevels = 0;
+    std::vector<int> lvl_ptr;         // nlevels+1 -> index into lvl_nodes
+    std::vector<int> lvl_nodes;       // nodes (permuted index) sorted by level
+    // factor program: targets ordered by level; target t < nk_targets are (pos) ids:
+    //   target id = position in L (0..nnzL-1) for off-diagonals, nnzL + j for diagonal of column j
+    std::vector<int> ft_lvl_ptr;      // nlevels+1 -> index into ft_target
+    std::vector<int> ft_target;       // target ids in level order
+    std::vector<int> ft_op_ptr;       // per entry of ft_target: ops range
+    std::vector<int> ft_op_a, ft_op_b;   // op: acc -= Y[a] * Ls[b]   (positions in L)
+    // per-level list of L positions to scale after the level's targets are final
+    std::vector<int> sc_lvl_ptr, sc_pos, sc_col;
+    // assembly program over the same target ids: Y[target] = cst + sum G[a]*G[b]*Wm[c] + A[src]
+    std::vector<int> as_ptr;          // size nnzL + nk + 1 (targets in natural id order)
+    std::vector<int> as_a, as_b, as_c;
+    std::vector<int> as_src;          // per target: index into A values or -1
+    std::vector<int> as_sign;         // per target: +1 / -1 / 0 times delta (diagonal regularisation)
+    long long factor_ops = 0;
+    std::string err;
+};
+
+namespace conic_detail {
+
+inline void transpose_pattern(int nrow, int ncol, const std::vector<int> &rp, const std::vector<int> &ci,
+                              std::vector<int> &t_rp, std::vector<int> &t_ri, std::vector<int> &t_vi)
+{
+    t_rp.assign(ncol + 1, 0);
+    for (int v : ci) t_rp[v + 1]++;
+    for (int j = 0; j < ncol; j++) t_rp[j + 1] += t_rp[j];
+    t_ri.resize(ci.size());
+    t_vi.resize(ci.size());
+    std::vector<int> nxt(t_rp.begin(), t_rp.end() - 1);
+    for (int r = 0; r < nrow; r++)
+        for (int k = rp[r]; k < rp[r + 1]; k++) {
+            int q = nxt[ci[k]]++;
+            t_ri[q] = r;
+            t_vi[q] = k;
+        }
+}
+
+}  // namespace conic_detail
+
+// Build everything. Returns false and sets S.err on failure.
+inline bool cone_symbolic_build(ConeSymbolic &S, int n, int p, int m, const int *A_rp, const int *A_ci,
+                                const int *G_rp, const int *G_ci, int l, int nsoc, const int *soc_dims,
+                                const int *perm_in)
+{
+    using namespace conic_detail;
+    S.n = n; S.p = p; S.m = m; S.l = l; S.nsoc = nsoc; S.nk = n + p;
+    const int nk = S.nk;
+    S.A_rp.assign(A_rp, A_rp + p + 1);
+    S.A_ci.assign(A_ci, A_ci + A_rp[p]);
+    S.G_rp.assign(G_rp, G_rp + m + 1);
+    S.G_ci.assign(G_ci, G_ci + G_rp[m]);
+    S.soc_dim.assign(soc_dims, soc_dims + nsoc);
+    S.soc_off.resize(nsoc);
+    S.soc_woff.resize(nsoc);
+    int off = l, woff = l;
+    for (int i = 0; i < nsoc; i++) {
+        if (soc_dims[i] < 2) { S.err = "SOC dimension < 2"; return false; }
+        S.soc_off[i] = off; S.soc_woff[i] = woff;
+        off += soc_dims[i]; woff += soc_dims[i] * soc_dims[i];
+    }
+    if (off != m) { S.err = "cone dimensions do not sum to m"; return false; }
+    S.nwm = woff;
+    transpose_pattern(p, n, S.A_rp, S.A_ci, S.At_rp, S.At_ri, S.At_vi);
+    transpose_pattern(m, n, S.G_rp, S.G_ci, S.Gt_rp, S.Gt_ri, S.Gt_vi);
+
+    // ---- permutation ----
+    S.perm.resize(nk);
+    if (perm_in) S.perm.assign(perm_in, perm_in + nk);
+    else std::iota(S.perm.begin(), S.perm.end(), 0);
+    S.iperm.assign(nk, -1);
+    for (int k = 0; k < nk; k++) {
+        int v = S.perm[k];
+        if (v < 0 || v >= nk || S.iperm[v] != -1) { S.err = "perm is not a permutation of 0..n+p-1"; return false; }
+        S.iperm[v] = k;
+    }
+
+    // ---- KKT entries (lower triangle, permuted): records (col j, row i, a, b, c) ----
+    struct Rec { int j, i, a, b, c; };   // a>=0,b>=0: triple; a=-1: direct A source b
+    std::vector<Rec> recs;
+    auto add_block = [&](int r0, int q, int wbase, bool dense) {
+        for (int r1 = r0; r1 < r0 + q; r1++)
+            for (int r2 = r0; r2 < r0 + q; r2++) {
+                if (!dense && r1 != r2) continue;
+                const int c = dense ? wbase + (r1 - r0) * q + (r2 - r0) : wbase;
+                for (int ka = S.G_rp[r1]; ka < S.G_rp[r1 + 1]; ka++)
+                    for (int kb = S.G_rp[r2]; kb < S.G_rp[r2 + 1]; kb++) {
+                        const int pi = S.iperm[S.G_ci[ka]], pj = S.iperm[S.G_ci[kb]];
+                        if (pi >= pj) recs.push_back({pj, pi, ka, kb, c});
+                    }
+            }
+    };
+    for (int r = 0; r < l; r++) add_block(r, 1, r, false);
+    for (int i = 0; i < nsoc; i++) add_block(S.soc_off[i], S.soc_dim[i], S.soc_woff[i], true);
+    for (int r = 0; r < p; r++)
+        for (int k = S.A_rp[r]; k < S.A_rp[r + 1]; k++) {
+            int pi = S.iperm[n + r], pj = S.iperm[S.A_ci[k]];
+            if (pi < pj) std::swap(pi, pj);
+            recs.push_back({pj, pi, -1, k, 0});
+        }
+    std::sort(recs.begin(), recs.end(), [](const Rec &x, const Rec &y) {
+        return x.j != y.j ? x.j < y.j : x.i < y.i;
+    });
+
+    // ---- M pattern (strict lower, CSC) ----
+    std::vector<std::vector<int>> mcol(nk);
+    for (const Rec &r : recs)
+        if (r.i != r.j && (mcol[r.j].empty() || mcol[r.j].back() != r.i)) mcol[r.j].push_back(r.i);
+
+    // ---- elimination tree + column structures of L ----
+    std::vector<int> parent(nk, -1);
+    std::vector<std::vector<int>> lcol(nk);
+    {
+        std::vector<std::vector<int>> children(nk);
+        std::vector<int> mark(nk, -1);
+        for (int j = 0; j < nk; j++) {
+            std::vector<int> &s = lcol[j];
+            mark[j] = j;
+            for (int i : mcol[j])
+                if (mark[i] != j) { mark[i] = j; s.push_back(i); }
+            for (int c : children[j]) {
+                for (int i : lcol[c])
+                    if (i != j && mark[i] != j) { mark[i] = j; s.push_back(i); }
+            }
+            std::sort(s.begin(), s.end());
+            if (!s.empty()) {
+                parent[j] = s.front();
+                children[s.front()].push_back(j);
+            }
+        }
+    }
+    S.L_cp.assign(nk + 1, 0);
+    for (int j = 0; j < nk; j++) S.L_cp[j + 1] = S.L_cp[j] + (int)lcol[j].size();
+    S.nnzL = S.L_cp[nk];
+    S.L_ri.resize(S.nnzL);
+    for (int j = 0; j < nk; j++) std::copy(lcol[j].begin(), lcol[j].end(), S.L_ri.begin() + S.L_cp[j]);
+    auto lpos = [&](int i, int j) -> int {  // position of (i,j), i>j, in L
+        auto b = S.L_ri.begin() + S.L_cp[j], e = S.L_ri.begin() + S.L_cp[j + 1];
+        auto it = std::lower_bound(b, e, i);
+        return (it != e && *it == i) ? (int)(it - S.L_ri.begin()) : -1;
+    };
+
+    // ---- levels = etree height ----
+    std::vector<int> height(nk, 0);
+    for (int j = 0; j < nk; j++)
+        if (parent[j] >= 0) height[parent[j]] = std::max(height[parent[j]], height[j] + 1);
+    S.nlevels = nk ? *std::max_element(height.begin(), height.end()) + 1 : 0;
+    S.lvl_ptr.assign(S.nlevels + 1, 0);
+    for (int j = 0; j < nk; j++) S.lvl_ptr[height[j] + 1]++;
+    for (int k = 0; k < S.nlevels; k++) S.lvl_ptr[k + 1] += S.lvl_ptr[k];
+    S.lvl_nodes.resize(nk);
+    {
+        std::vector<int> nxt(S.lvl_ptr.begin(), S.lvl_ptr.end() - 1);
+        for (int j = 0; j < nk; j++) S.lvl_nodes[nxt[height[j]]++] = j;
+    }
+
+    // ---- CSR view of L ----
+    S.Lr_rp.assign(nk + 1, 0);
+    for (int q = 0; q < S.nnzL; q++) S.Lr_rp[S.L_ri[q] + 1]++;
+    for (int i = 0; i < nk; i++) S.Lr_rp[i + 1] += S.Lr_rp[i];
+    S.Lr_pos.resize(S.nnzL);
+    S.Lr_col.resize(S.nnzL);
+    {
+        std::vector<int> nxt(S.Lr_rp.begin(), S.Lr_rp.end() - 1);
+        for (int j = 0; j < nk; j++)
+            for (int q = S.L_cp[j]; q < S.L_cp[j + 1]; q++) {
+                int w = nxt[S.L_ri[q]]++;
+                S.Lr_pos[w] = q;
+                S.Lr_col[w] = j;
+            }
+    }
+
+    // ---- factor program: per target the (a,b) op pairs, generated column by column ----
+    const int ntgt = S.nnzL + nk;
+    std::vector<int> cnt(ntgt, 0);
+    S.factor_ops = 0;
+    for (int k = 0; k < nk; k++) {
+        const int b0 = S.L_cp[k], e0 = S.L_cp[k + 1];
+        for (int qa = b0; qa < e0; qa++) {
+            cnt[S.nnzL + S.L_ri[qa]]++;  // diagonal of row_a
+            for (int qb = qa + 1; qb < e0; qb++) {
+                int t = lpos(S.L_ri[qb], S.L_ri[qa]);
+                if (t < 0) { S.err = "internal: fill entry missing"; return false; }
+                cnt[t]++;
+            }
+        }
+    }
+    std::vector<long long> optr(ntgt + 1, 0);
+    for (int t = 0; t < ntgt; t++) optr[t + 1] = optr[t] + cnt[t];
+    S.factor_ops = optr[ntgt];
+    if (S.factor_ops > 2000000000LL) { S.err = "factor program too large (bad ordering?)"; return false; }
+    std::vector<int> opa(S.factor_ops), opb(S.factor_ops);
+    {
+        std::vector<long long> nxt(optr.begin(), optr.end() - 1);
+        for (int k = 0; k < nk; k++) {
+            const int b0 = S.L_cp[k], e0 = S.L_cp[k + 1];
+            for (int qa = b0; qa < e0; qa++) {
+                long long w = nxt[S.nnzL + S.L_ri[qa]]++;
+                opa[w] = qa; opb[w] = qa;
+                for (int qb = qa + 1; qb < e0; qb++) {
+                    int t = lpos(S.L_ri[qb], S.L_ri[qa]);
+                    long long w2 = nxt[t]++;
+                    opa[w2] = qb;   // Y_ik  (row_b = i)
+                    opb[w2] = qa;   // L_jk  (row_a = j)
+                }
+            }
+        }
+    }
+    // order targets by level of their column; diagonal target belongs to its own column
+    S.ft_lvl_ptr.assign(S.nlevels + 1, 0);
+    S.ft_target.clear(); S.ft_op_ptr.clear(); S.ft_op_a.clear(); S.ft_op_b.clear();
+    S.ft_target.reserve(ntgt);
+    S.ft_op_a.reserve(S.factor_ops); S.ft_op_b.reserve(S.factor_ops);
+    S.sc_lvl_ptr.assign(S.nlevels + 1, 0);
+    S.sc_pos.clear(); S.sc_col.clear();
+    S.ft_op_ptr.push_back(0);
+    for (int lv = 0; lv < S.nlevels; lv++) {
+        for (int w = S.lvl_ptr[lv]; w < S.lvl_ptr[lv + 1]; w++) {
+            const int j = S.lvl_nodes[w];
+            auto emit = [&](int t) {
+                S.ft_target.push_back(t);
+                for (long long o = optr[t]; o < optr[t + 1]; o++) { S.ft_op_a.push_back(opa[o]); S.ft_op_b.push_back(opb[o]); }
+                S.ft_op_ptr.push_back((int)S.ft_op_a.size());
+            };
+            emit(S.nnzL + j);
+            for (int q = S.L_cp[j]; q < S.L_cp[j + 1]; q++) { emit(q); S.sc_pos.push_back(q); S.sc_col.push_back(j); }
+        }
+        S.ft_lvl_ptr[lv + 1] = (int)S.ft_target.size();
+        S.sc_lvl_ptr[lv + 1] = (int)S.sc_pos.size();
+    }
+
+    // ---- assembly program (targets in natural id order) ----
+    S.as_ptr.assign(ntgt + 1, 0);
+    S.as_src.assign(ntgt, -1);
+    S.as_sign.assign(ntgt, 0);
+    std::vector<int> tcount(ntgt, 0);
+    auto tid = [&](int i, int j) { return i == j ? S.nnzL + j : lpos(i, j); };
+    for (const Rec &r : recs) {
+        int t = tid(r.i, r.j);
+        if (t < 0) { S.err = "internal: KKT entry outside L pattern"; return false; }
+        if (r.a >= 0) tcount[t]++;
+    }
+    for (int t = 0; t < ntgt; t++) S.as_ptr[t + 1] = S.as_ptr[t] + tcount[t];
+    S.as_a.resize(S.as_ptr[ntgt]); S.as_b.resize(S.as_ptr[ntgt]); S.as_c.resize(S.as_ptr[ntgt]);
+    {
+        std::vector<int> nxt(S.as_ptr.begin(), S.as_ptr.end() - 1);
+        for (const Rec &r : recs) {
+            int t = tid(r.i, r.j);
+            if (r.a >= 0) { int w = nxt[t]++; S.as_a[w] = r.a; S.as_b[w] = r.b; S.as_c[w] = r.c; }
+            else S.as_src[t] = r.b;
+        }
+    }
+    for (int k = 0; k < nk; k++) S.as_sign[S.nnzL + k] = (S.perm[k] < n) ? 1 : -1;
+    return true;
+}

@@ -39,7 +39,24 @@ SIGNATURES = {
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p]),
+    "scpb_cone_setup": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _ip, _ip, _ip, _ip, C.c_int32,
+                                    C.c_int32, _ip, _ip, C.POINTER(C.c_void_p)]),
+    "scpb_cone_info": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "scpb_cone_free": (C.c_int32, [C.c_void_p]),
+    "scpb_cone_solve": (C.c_int32, [C.c_void_p, C.c_int32, _dp, _dp, _dp, _dp, _dp, C.c_void_p,
+                                    _dp, _dp, _dp, _dp, _dp, _dp, _ip, _ip, _dp]),
+    "scpb_debug_kkt_solve": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _ip, _ip, _ip, _ip, C.c_int32, C.c_int32,
+                                         _ip, _ip, _dp, _dp, _dp, C.c_double, _dp, _dp, C.POINTER(C.c_int64)]),
 }
+
+
+class ConeOpts(C.Structure):
+    _fields_ = [("feastol", C.c_double), ("abstol", C.c_double), ("reltol", C.c_double),
+                ("delta", C.c_double), ("delta_dyn", C.c_double), ("maxit", C.c_int32), ("nref", C.c_int32),
+                ("verbose", C.c_int32), ("group", C.c_int32)]
+
+
+CONE_STATUS = {0: "OPTIMAL", 1: "ITERATION_LIMIT", 2: "NUMERICAL_ERROR"}
 
 
 class ScpbError(RuntimeError):
@@ -147,3 +164,83 @@ class Handle:
         rc = self.lib.scpb_discretize_dev(self.h, method, B, N, Nsub, t_grid, xd, ud, p, iSx_diag,
                                           float(feas_tol), A, Bm, Bp, F, r, E, defect, feas)
         self._check(rc, "scpb_discretize_dev")
+
+
+def _i32(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(_ip)
+
+
+class ConeProblem:
+    """Pattern-shared batched cone program (scpb_cone_*).  A, G: scipy CSR patterns (values ignored)."""
+
+    def __init__(self, handle: "Handle", A, G, l: int, soc_dims=(), perm=None):
+        self.hd = handle
+        self.lib = handle.lib
+        self.n, self.p, self.m = A.shape[1], A.shape[0], G.shape[0]
+        A = A.tocsr(); G = G.tocsr()
+        A.sort_indices(); G.sort_indices()
+        self.nnzA, self.nnzG = A.nnz, G.nnz
+        self._keep = [_i32(A.indptr), _i32(A.indices), _i32(G.indptr), _i32(G.indices), _i32(list(soc_dims) or [0])]
+        pp = None
+        if perm is not None:
+            self._keep.append(_i32(perm))
+            pp = self._keep[-1][1]
+        c = C.c_void_p()
+        k = self._keep
+        rc = self.lib.scpb_cone_setup(handle.h, self.n, self.p, self.m, k[0][1], k[1][1], k[2][1], k[3][1],
+                                      int(l), len(soc_dims), k[4][1], pp, C.byref(c))
+        handle._check(rc, "scpb_cone_setup")
+        self.c = c
+        self.l, self.soc_dims = int(l), list(soc_dims)
+
+    def info(self):
+        buf = (C.c_int64 * 8)()
+        self.lib.scpb_cone_info(self.c, buf)
+        keys = ["nk", "nnzL", "levels", "factor_ops", "assembly_ops", "nwm", "group", "capacity"]
+        return dict(zip(keys, [int(v) for v in buf]))
+
+    def close(self):
+        if getattr(self, "c", None) is not None and self.c.value:
+            self.lib.scpb_cone_free(self.c)
+            self.c = C.c_void_p()
+
+    def solve(self, Avals, Gvals, c, b, h, **opts):
+        """Batched solve; arrays are (B, nnzA), (B, nnzG), (B, n), (B, p), (B, m)."""
+        Avals, pA = _f64(Avals); Gvals, pG = _f64(Gvals)
+        c, pc = _f64(c); b, pb = _f64(b); h, ph = _f64(h)
+        B = c.shape[0]
+        assert Avals.shape == (B, self.nnzA) and Gvals.shape == (B, self.nnzG), (Avals.shape, Gvals.shape)
+        assert c.shape == (B, self.n) and b.shape == (B, self.p) and h.shape == (B, self.m)
+        o = ConeOpts()
+        for k_, v in opts.items():
+            setattr(o, k_, v)
+        out = dict(x=np.empty((B, self.n)), y=np.empty((B, self.p)), z=np.empty((B, self.m)),
+                   s=np.empty((B, self.m)), pobj=np.empty(B), dobj=np.empty(B),
+                   status=np.zeros(B, dtype=np.int32), iters=np.zeros(B, dtype=np.int32))
+        sec = C.c_double(0.0)
+        g = lambda k_: out[k_].ctypes.data_as(_dp)
+        rc = self.lib.scpb_cone_solve(self.c, B, pA, pG, pc, pb, ph, C.cast(C.byref(o), C.c_void_p), g("x"), g("y"),
+                                      g("z"), g("s"), g("pobj"), g("dobj"), out["status"].ctypes.data_as(_ip),
+                                      out["iters"].ctypes.data_as(_ip), C.byref(sec))
+        self.hd._check(rc, "scpb_cone_solve")
+        out["seconds"] = sec.value
+        return out
+
+
+def debug_kkt_solve(A, G, l, soc_dims, perm, Avals, Gvals, wm, delta, rhs):
+    """CPU interpreter of the index programs for one seed (test hook, see include/scpb.h)."""
+    lib = load()
+    A = A.tocsr(); G = G.tocsr(); A.sort_indices(); G.sort_indices()
+    n, p, m = A.shape[1], A.shape[0], G.shape[0]
+    a0, a1, g0, g1 = _i32(A.indptr), _i32(A.indices), _i32(G.indptr), _i32(G.indices)
+    sd = _i32(list(soc_dims) or [0])
+    pm = _i32(perm) if perm is not None else (None, None)
+    Av, pAv = _f64(Avals); Gv, pGv = _f64(Gvals); wmv, pwm = _f64(wm); r, pr = _f64(rhs)
+    sol = np.zeros(n + p)
+    info = (C.c_int64 * 4)()
+    rc = lib.scpb_debug_kkt_solve(n, p, m, a0[1], a1[1], g0[1], g1[1], int(l), len(soc_dims), sd[1], pm[1],
+                                  pAv, pGv, pwm, float(delta), pr, sol.ctypes.data_as(_dp), info)
+    if rc != 0:
+        raise ScpbError(f"scpb_debug_kkt_solve failed ({rc})")
+    return sol, dict(nnzL=int(info[0]), levels=int(info[1]), factor_ops=int(info[2]), assembly_ops=int(info[3]))

@@ -1,0 +1,122 @@
+"""GPU parity: batched interior-point solver (scpb_cone_solve through the C ABI) vs the CPU oracle.
+
+Tolerances (fp64): objective 1e-7 relative to max(1,|obj|) against HiGHS / the oracle IPM, primal and
+dual residuals <= 1e-7 (solver tolerance is ECOS' default 1e-8 on scaled residuals), and -- where the
+optimum is unique (random programs) -- x within 1e-5 of the oracle solution.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import conic
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def _feasible_program(rng, n, p, l, soc, dens=0.35):
+    m = l + sum(soc)
+    A = sp.random(p, n, density=dens, random_state=rng.integers(1 << 30), format="csr")
+    A = (A + sp.csr_matrix((np.ones(p), (np.arange(p), rng.permutation(n)[:p])), shape=(p, n))).tocsr()
+    G = sp.random(m, n, density=dens, random_state=rng.integers(1 << 30), format="csr")
+    G = (G + sp.csr_matrix((np.ones(m), (np.arange(m), rng.integers(0, n, m))), shape=(m, n))).tocsr()
+    # box rows make the problem bounded
+    G = sp.vstack([G[:l], sp.eye(n), -sp.eye(n), G[l:]]).tocsr()
+    l2 = l + 2 * n
+    A.sort_indices(); G.sort_indices()
+
+    def interior(k):
+        v = rng.uniform(0.5, 2.0, l2)
+        parts = [v]
+        for q in soc:
+            w = rng.standard_normal(q); w[0] = np.linalg.norm(w[1:]) + rng.uniform(0.5, 1.5)
+            parts.append(w)
+        return np.concatenate(parts)
+
+    x0, s0, z0, y0 = rng.standard_normal(n), interior(0), interior(1), rng.standard_normal(p)
+    h = G @ x0 + s0
+    b = A @ x0
+    c = -(A.T @ y0) - (G.T @ z0)
+    return A, G, l2, c, b, h
+
+
+def _kkt_check(A, G, l, soc, c, b, h, x, y, z, s):
+    pres = max(np.abs(A @ x - b).max(initial=0.0), np.abs(G @ x + s - h).max(initial=0.0))
+    dres = np.abs(c + A.T @ y + G.T @ z).max()
+    return pres, dres
+
+
+@pytest.mark.parametrize("seed,n,p,l,soc", [(0, 10, 3, 8, []), (1, 16, 5, 10, [3, 4]), (2, 24, 8, 6, [5, 3, 3]),
+                                            (3, 12, 0, 9, [4])])
+def test_random_programs_match_oracle(handle, pkg, seed, n, p, l, soc):
+    rng = np.random.default_rng(seed)
+    nb = 5
+    progs = [_feasible_program(np.random.default_rng(1000 * seed + 7), n, p, l, soc) for _ in range(1)]
+    A, G, l2, c0, b0, h0 = progs[0]
+    # batch: same pattern, perturbed values / data per seed
+    Av = np.array([A.data * (1 + 0.05 * rng.standard_normal(A.nnz) * (k > 0)) for k in range(nb)])
+    Gv = np.array([G.data.copy() for k in range(nb)])
+    cs = np.array([c0 * (1 + 0.1 * rng.standard_normal(n) * (k > 0)) for k in range(nb)])
+    hs = np.array([h0 + 0.1 * np.abs(rng.standard_normal(h0.size)) * (k > 0) * (np.arange(h0.size) < l2) for k in range(nb)])
+    bs = []
+    for k in range(nb):
+        Ak = sp.csr_matrix((Av[k], A.indices, A.indptr), shape=A.shape)
+        bs.append(b0 if k == 0 else Ak @ np.linalg.lstsq(A.toarray(), b0, rcond=None)[0] if p else b0)
+    bs = np.array(bs).reshape(nb, p)
+    cone = pkg.lib.ConeProblem(handle, A, G, l2, soc, perm=pkg.ordering.rcm_order(A, G))
+    out = cone.solve(Av, Gv, cs, bs, hs)
+    for k in range(nb):
+        Ak = sp.csr_matrix((Av[k], A.indices, A.indptr), shape=A.shape)
+        cp = dict(c=cs[k], c0=0.0, A=Ak, b=bs[k], G=G, h=hs[k], l=l2, q=list(soc))
+        ref = conic.solve_ipm(cp, tol=1e-9)
+        assert ref["status"] in ("OPTIMAL", "ALMOST_OPTIMAL")
+        assert out["status"][k] == 0, (k, out["status"], out["iters"])
+        assert abs(out["pobj"][k] - ref["obj"]) <= 1e-7 * max(1.0, abs(ref["obj"]))
+        pres, dres = _kkt_check(Ak, G, l2, soc, cs[k], bs[k], hs[k], out["x"][k], out["y"][k], out["z"][k], out["s"][k])
+        assert pres <= 1e-6 * max(1.0, np.abs(hs[k]).max()) and dres <= 1e-6 * max(1.0, np.abs(cs[k]).max())
+        assert np.abs(out["x"][k] - ref["z"]).max() <= 1e-5 * max(1.0, np.abs(ref["z"]).max())
+        assert (out["s"][k][:l2] > -1e-9).all() and (out["z"][k][:l2] > -1e-9).all()
+    cone.close()
+
+
+@pytest.mark.parametrize("N,group", [(12, 0), (31, 2), (31, 4)])
+def test_starship_ptr_subproblem_matches_highs(handle, pkg, N, group):
+    """The reference's own subproblem (starship PTR, q_tr = Inf => LP): batch of perturbed references."""
+    nb = 6
+    pb, P, subs = helpers.starship_subproblems(N, nb, seed=N)
+    Apat, Avals = helpers.union_pattern([s["cp"]["A"] for s in subs])
+    Gpat, Gvals = helpers.union_pattern([s["cp"]["G"] for s in subs])
+    lab = helpers.labels_from_program(subs[0]["prg"], N)
+    perm = pkg.ordering.stage_order(Apat, Gpat, lab, N)
+    cone = pkg.lib.ConeProblem(handle, Apat, Gpat, subs[0]["cp"]["l"], [], perm=perm)
+    info = cone.info()
+    assert info["nnzL"] < 40 * info["nk"] and info["levels"] < 200, info
+    c = np.array([s["cp"]["c"] for s in subs]); b = np.array([s["cp"]["b"] for s in subs])
+    h = np.array([s["cp"]["h"] for s in subs])
+    out = cone.solve(Avals, Gvals, c, b, h, group=group)
+    for k, sub in enumerate(subs):
+        ref = conic.solve_highs(sub["cp"], tol=1e-9)
+        assert ref["status"] == "OPTIMAL"
+        assert out["status"][k] == 0, (out["status"], out["iters"])
+        want = ref["obj"] - sub["cp"]["c0"]
+        assert abs(out["pobj"][k] - want) <= 1e-7 * max(1.0, abs(want)), (k, out["pobj"][k], want)
+        assert abs(out["pobj"][k] - out["dobj"][k]) <= 1e-6 * max(1.0, abs(want))
+        x = out["x"][k]
+        cpk = sub["cp"]
+        assert np.abs(cpk["A"] @ x - cpk["b"]).max() <= 1e-7 * max(1.0, np.abs(cpk["b"]).max())
+        assert (cpk["G"] @ x - cpk["h"]).max() <= 1e-7 * max(1.0, np.abs(cpk["h"]).max())
+    assert out["iters"].max() <= 60
+    cone.close()
+
+
+def test_cone_error_paths(handle, pkg):
+    A = sp.csr_matrix(np.array([[1.0, 1.0]])); G = sp.csr_matrix(-np.eye(2))
+    with pytest.raises(pkg.ScpbError):
+        pkg.lib.ConeProblem(handle, A, G, 1, [2])           # cone sizes do not add up to m
+    with pytest.raises(pkg.ScpbError):
+        pkg.lib.ConeProblem(handle, A, G, 2, [], perm=[0, 0, 1])  # not a permutation
+    cone = pkg.lib.ConeProblem(handle, A, G, 2, [])
+    out = cone.solve([[1.0, 1.0]], [G.data], [[1.0, 2.0]], [[1.0]], [[0.0, 0.0]])   # min x1+2x2, x1+x2=1, x>=0
+    assert out["status"][0] == 0 and abs(out["pobj"][0] - 1.0) < 1e-7
+    assert np.abs(out["x"][0] - [1.0, 0.0]).max() < 1e-6
+    cone.close()
