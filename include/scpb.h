@@ -92,15 +92,17 @@ typedef struct scpb_cone_s *scpb_cone;
 
 typedef struct {
     double feastol, abstol, reltol; /* <=0: ECOS defaults 1e-8                          */
-    double delta, delta_dyn;        /* <=0: static 1e-9 / dynamic 1e-13 regularisation   */
+    double delta, delta_dyn;        /* <=0: static 1e-9 / dynamic 1e-7 regularisation    */
     int32_t maxit;                  /* <=0: 100 ("maxit" of solver_opts)                 */
-    int32_t nref;                   /* <0: 2 iterative-refinement steps                  */
+    int32_t nref;                   /* <0: 3 iterative-refinement steps                  */
     int32_t verbose;                /* accepted, ignored ("verbose" of solver_opts)      */
     int32_t group;                  /* seeds per CTA (power of two <= 32); 0 = automatic */
+    int32_t equil;                  /* Ruiz equilibration passes; <0: default 5, 0: off    */
 } scpb_cone_opts;
 
 /* per-seed status (termination_status, program.jl:427-428): */
-enum { SCPB_CONE_OPTIMAL = 0, SCPB_CONE_ITERATION_LIMIT = 1, SCPB_CONE_NUMERICAL_ERROR = 2 };
+enum { SCPB_CONE_OPTIMAL = 0, SCPB_CONE_ITERATION_LIMIT = 1, SCPB_CONE_NUMERICAL_ERROR = 2,
+       SCPB_CONE_ALMOST_OPTIMAL = 3 /* best iterate meets ECOS' reduced tolerances (5e-5) */ };
 
 int32_t scpb_cone_setup(scpb_handle h, int32_t n, int32_t p, int32_t m,
                         const int32_t *A_rowptr, const int32_t *A_colind,
@@ -125,8 +127,8 @@ int32_t scpb_cone_solve(scpb_cone c, int32_t B, const double *Avals, const doubl
 int32_t scpb_debug_kkt_solve(int32_t n, int32_t p, int32_t m, const int32_t *A_rowptr, const int32_t *A_colind,
                              const int32_t *G_rowptr, const int32_t *G_colind, int32_t l, int32_t nsoc,
                              const int32_t *soc_dims, const int32_t *perm, const double *Avals,
-                             const double *Gvals, const double *wm, double delta, const double *rhs,
-                             double *sol, int64_t *info);
+                             const double *Gvals, const double *wm, double delta, double delta_dyn,
+                             const double *rhs, double *sol, int64_t *info);
 
 #ifdef __cplusplus
 }

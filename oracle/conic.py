@@ -302,8 +302,46 @@ class _Cones:
         return W, Wi, W @ z
 
 
-def solve_ipm(cp, tol=1e-9, maxit=100, verbose=False):
+def equilibrate(cp, iters=5):
+    """Ruiz equilibration of [A; G] (ECOS applies the same kind of preprocessing, its `equil` step):
+    A^ = Ea A D, G^ = Eg G D with one common factor per second-order cone; b^ = Ea b, h^ = Eg h, c^ = D c.
+    Solution map: x = D x^, y = Ea y^, z = Eg z^, s = s^ / Eg."""
+    A, G = cp["A"].tocsr(), cp["G"].tocsr()
+    p, n = A.shape
+    m, l, q = G.shape[0], cp["l"], list(cp["q"])
+    D, Ea, Eg = np.ones(n), np.ones(p), np.ones(m)
+    As, Gs = A.copy(), G.copy()
+    for _ in range(iters):
+        ra = np.sqrt(np.abs(As).max(axis=1).toarray().ravel()) if p else np.zeros(0)
+        rg = np.sqrt(np.abs(Gs).max(axis=1).toarray().ravel()) if m else np.zeros(0)
+        off = l
+        for qk in q:  # one factor per cone
+            rg[off:off + qk] = rg[off:off + qk].mean()
+            off += qk
+        ra[ra == 0] = 1.0; rg[rg == 0] = 1.0
+        cn = np.zeros(n)
+        if p: cn = np.maximum(cn, np.abs(As).max(axis=0).toarray().ravel())
+        if m: cn = np.maximum(cn, np.abs(Gs).max(axis=0).toarray().ravel())
+        cn = np.sqrt(cn); cn[cn == 0] = 1.0
+        Ea /= ra; Eg /= rg; D /= cn
+        As = sp.diags(1 / ra) @ As @ sp.diags(1 / cn) if p else As
+        Gs = sp.diags(1 / rg) @ Gs @ sp.diags(1 / cn) if m else Gs
+    out = dict(cp)
+    out.update(A=sp.csr_matrix(As), G=sp.csr_matrix(Gs), b=cp["b"] * Ea, h=cp["h"] * Eg, c=cp["c"] * D)
+    return out, D, Ea, Eg
+
+
+def solve_ipm(cp, tol=1e-9, maxit=100, verbose=False, equil=True):
     """min c'x s.t. Ax=b, Gx+s=h, s in K.  Returns dict(status, z, obj, iters, y_eq, z_ineq)."""
+    if equil:
+        cps, D, Ea, Eg = equilibrate(cp)
+        r = solve_ipm(cps, tol=tol, maxit=maxit, verbose=verbose, equil=False)
+        r["z"] = r["z"] * D
+        if "y_eq" in r and r["y_eq"] is not None:
+            r["y_eq"] = r["y_eq"] * Ea
+            r["z_ineq"] = r["z_ineq"] * Eg
+            r["s"] = r["s"] / Eg
+        return r
     c, A, b, G, h = cp["c"], cp["A"].tocsc(), cp["b"], cp["G"].tocsc(), cp["h"]
     n, p, K = c.size, A.shape[0], _Cones(cp["l"], cp["q"])
     m = K.m
@@ -370,7 +408,7 @@ def solve_ipm(cp, tol=1e-9, maxit=100, verbose=False):
             best, stall = (x.copy(), y.copy(), z.copy(), s.copy(), acc), 0
         else:
             stall += 1
-            if stall >= 3:  # numerical floor reached: return the best iterate
+            if stall >= 3 and best[4] <= 1e-6:  # numerical floor reached: return the best iterate
                 x, y, z, s, acc = best
                 status = "OPTIMAL" if acc <= 10 * tol else ("ALMOST_OPTIMAL" if acc <= 1e-6 else "NUMERICAL_ERROR")
                 break
@@ -399,7 +437,7 @@ def solve_ipm(cp, tol=1e-9, maxit=100, verbose=False):
             # lam o (W dz + W^-T ds) = ds_rhs  =>  ds = W'(lam\ds_rhs) - W'W dz,  bz = -scale*rz - W'(lam\ds_rhs)
             tmp = W.T @ K.div(lam, ds_rhs)
             dx, dy, dz = kkt_solve(fac, WG, Wi, -scale * rx, -scale * ry, -scale * rz - tmp)
-            ds = tmp - W.T @ (W @ dz)
+            ds = -scale * rz - G @ dx   # == tmp - W'W dz, but keeps G dx + ds = -scale*rz to rounding
             return dx, dy, dz, ds
 
         def raw_step(ds, dz):

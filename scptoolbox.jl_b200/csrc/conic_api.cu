@@ -53,7 +53,7 @@ static int pick_group(int B, int want)
         return g;
     }
     int g = 1;
-    while ((B + g - 1) / g > 444 && g < IPM_MAXG) g <<= 1;
+    while ((B + g - 1) / g > 148 && g < IPM_MAXG) g <<= 1;   // one persistent CTA per SM
     return g;
 }
 
@@ -61,6 +61,7 @@ static int cone_reserve(scpb_cone_s *c, int B, int G)
 {
     scpb_handle_s *h = c->h;
     const int ng = (B + G - 1) / G, Bpad = ng * G;
+    c->D.R = std::max(1, std::min(8, 32 / G));
     if (c->capB >= Bpad && c->capG == G) { c->D.B = B; c->D.G = G; return SCPB_OK; }
     for (double *p : c->bufs) cudaFree(p);
     c->bufs.clear();
@@ -79,6 +80,8 @@ static int cone_reserve(scpb_cone_s *c, int B, int G)
     double *Av = al(S.A_ci.size()), *Gv = al(S.G_ci.size()), *cc = al(n), *bb = al(p), *hh = al(m);
     D.Av = Av; D.Gv = Gv; D.c = cc; D.b = bb; D.h = hh;
     D.x = al(n); D.y = al(p); D.z = al(m); D.s = al(m);
+    D.xb = al(n); D.yb = al(p); D.zb = al(m); D.sb = al(m);
+    D.eqD = al(n); D.eqA = al(p); D.eqG = al(m);
     D.rx = al(n); D.ry = al(p); D.rz = al(m); D.lam = al(m); D.wm = al(S.nwm); D.socw = al(m - S.l + 1);
     D.soceta = al(S.nsoc + 1);
     D.dx = al(n); D.dy = al(p); D.dz = al(m); D.ds = al(m); D.dsa = al(m); D.dza = al(m); D.tm = al(m); D.gm = al(m);
@@ -115,9 +118,10 @@ static IpmOpts make_opts(const scpb_cone_opts *o)
     r.abstol = (o && o->abstol > 0) ? o->abstol : 1e-8;
     r.reltol = (o && o->reltol > 0) ? o->reltol : 1e-8;
     r.delta = (o && o->delta > 0) ? o->delta : 1e-9;
-    r.delta_dyn = (o && o->delta_dyn > 0) ? o->delta_dyn : 1e-13;
+    r.delta_dyn = (o && o->delta_dyn > 0) ? o->delta_dyn : 1e-7;
     r.maxit = (o && o->maxit > 0) ? o->maxit : 100;
-    r.nref = (o && o->nref >= 0) ? o->nref : 2;
+    r.nref = (o && o->nref >= 0) ? o->nref : 3;
+    r.equil = (o && o->equil >= 0) ? o->equil : 5;
     return r;
 }
 

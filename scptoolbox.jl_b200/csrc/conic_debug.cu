@@ -8,8 +8,8 @@
 extern "C" int32_t scpb_debug_kkt_solve(int32_t n, int32_t p, int32_t m, const int32_t *A_rp, const int32_t *A_ci,
                                         const int32_t *G_rp, const int32_t *G_ci, int32_t l, int32_t nsoc,
                                         const int32_t *soc_dims, const int32_t *perm, const double *Av,
-                                        const double *Gv, const double *wm, double delta, const double *rhs,
-                                        double *sol, int64_t *info)
+                                        const double *Gv, const double *wm, double delta, double delta_dyn,
+                                        const double *rhs, double *sol, int64_t *info)
 {
     ConeSymbolic S;
     static const int zero = 0;
@@ -28,8 +28,12 @@ extern "C" int32_t scpb_debug_kkt_solve(int32_t n, int32_t p, int32_t m, const i
             const int t = S.ft_target[w];
             double acc = Y[t];
             for (int k = S.ft_op_ptr[w]; k < S.ft_op_ptr[w + 1]; k++) acc -= Y[S.ft_op_a[k]] * Ls[S.ft_op_b[k]];
+            if (t >= S.nnzL) {  // same dynamic regularisation rule as kkt_factor (conic_ipm.cuh)
+                const double sgn = (double)S.as_sign[t];
+                if (!(sgn * acc > delta_dyn)) acc = sgn * delta_dyn;
+                invD[t - S.nnzL] = 1.0 / acc;
+            }
             Y[t] = acc;
-            if (t >= S.nnzL) invD[t - S.nnzL] = 1.0 / acc;
         }
         for (int w = S.sc_lvl_ptr[lv]; w < S.sc_lvl_ptr[lv + 1]; w++) Ls[S.sc_pos[w]] = Y[S.sc_pos[w]] * invD[S.sc_col[w]];
     }

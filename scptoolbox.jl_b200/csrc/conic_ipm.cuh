@@ -34,15 +34,17 @@ struct IpmOpts {
     double feastol, abstol, reltol;   // ECOS defaults 1e-8
     double delta;                     // static regularisation
     double delta_dyn;                 // dynamic regularisation threshold / value
-    int maxit, nref;
+    int maxit, nref, equil;   // equil: Ruiz iterations (0 = off)
 };
 
 struct IpmData {  // group-blocked device arrays, all for B seeds
-    int B, G;
+    int B, G, R;   // R: lanes per sparse row (power of two, G*R <= 32)
     // problem data
-    const double *Av, *Gv, *c, *b, *h;
+    double *Av, *Gv, *c, *b, *h;  // equilibrated in place by the solver
     // iterates
     double *x, *y, *z, *s;
+    double *eqD, *eqA, *eqG;     // Ruiz equilibration factors (columns, equality rows, cone rows)
+    double *xb, *yb, *zb, *sb;   // best iterate so far (restored when the run ends without reaching the tolerances)
     // work
     double *rx, *ry, *rz, *lam, *wm, *socw, *soceta;
     double *dx, *dy, *dz, *ds, *dsa, *dza, *tm, *gm, *r1, *r2, *e1, *e2, *rhs, *Y, *Ls, *invD;
@@ -51,7 +53,7 @@ struct IpmData {  // group-blocked device arrays, all for B seeds
     int *status, *iters;
 };
 
-enum { IPM_OPTIMAL = 0, IPM_MAXIT = 1, IPM_NUMERICAL = 2 };
+enum { IPM_OPTIMAL = 0, IPM_MAXIT = 1, IPM_NUMERICAL = 2, IPM_ALMOST = 3 };
 
 #define IPM_MAXG 32
 #define IPM_NT 512
@@ -59,6 +61,9 @@ enum { IPM_OPTIMAL = 0, IPM_MAXIT = 1, IPM_NUMERICAL = 2 };
 // ---------------------------------------------------------------------------------------------
 struct Ctx {
     int G, sg, slot, nslots, tid;
+    // row-type work (sparse dot products): R lanes cooperate on one row for the G seeds of the group;
+    // lane layout inside a warp: tid = (item*R + rr)*G + sg, reduced with xor-shuffles over rr
+    int R, rr, isl, nisl;
     double *red;   // shared: [8][IPM_NT/32][IPM_MAXG]
     double *out;   // shared: [8][IPM_MAXG]
 };
@@ -99,6 +104,13 @@ __device__ __forceinline__ void seed_reduce(const Ctx &c, double (&v)[K], int op
 }
 
 #define GI(e) ((size_t)(e) * G + sg)
+
+// sum over the R lanes that share a row (offsets G, 2G, .. (R/2)G inside the warp)
+__device__ __forceinline__ double lanes_sum(const Ctx &c, double a)
+{
+    for (int o = c.G; o < c.G * c.R; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    return a;
+}
 
 // y = alpha * (M x) [+ y0]  row-wise CSR; M values Mv group-blocked
 __device__ __forceinline__ double row_dot(const int *rp, const int *ci, const double *Mv, const double *x, int r,
@@ -171,17 +183,34 @@ __device__ void kkt_factor(const IpmProgram &P, const Ctx &c, double *Y, double 
 {
     const int G = c.G, sg = c.sg;
     for (int lv = 0; lv < P.nlevels; lv++) {
-        for (int w = P.ft_lvl_ptr[lv] + c.slot; w < P.ft_lvl_ptr[lv + 1]; w += c.nslots) {
-            const int t = P.ft_target[w];
-            double acc = Y[GI(t)];
-            for (int k = P.ft_op_ptr[w]; k < P.ft_op_ptr[w + 1]; k++)
-                acc = fma(-Y[GI(P.ft_op_a[k])], Ls[GI(P.ft_op_b[k])], acc);
-            if (t >= P.nnzL) {  // diagonal: dynamic regularisation keeps the expected inertia
-                const double sgn = (double)P.as_sign[t];
-                if (!(sgn * acc > delta_dyn)) acc = sgn * delta_dyn;
-                invD[GI(t - P.nnzL)] = 1.0 / acc;
+        const int wend = P.ft_lvl_ptr[lv + 1];
+        for (int w0 = P.ft_lvl_ptr[lv]; w0 < wend; w0 += c.nisl) {   // uniform trip count: shuffles inside
+            const int w = w0 + c.isl;
+            const bool on = w < wend;
+            int t = 0;
+            double part = 0.0;
+            if (on) {
+                t = P.ft_target[w];
+                const int k1 = P.ft_op_ptr[w + 1];
+                int k = P.ft_op_ptr[w] + c.rr;
+                for (; k + c.R < k1; k += 2 * c.R) {   // two independent gathers in flight
+                    const int a0 = P.ft_op_a[k], b0 = P.ft_op_b[k], a1 = P.ft_op_a[k + c.R], b1 = P.ft_op_b[k + c.R];
+                    const double y0 = Y[GI(a0)], l0 = Ls[GI(b0)], y1 = Y[GI(a1)], l1 = Ls[GI(b1)];
+                    part = fma(y0, l0, part);
+                    part = fma(y1, l1, part);
+                }
+                if (k < k1) part = fma(Y[GI(P.ft_op_a[k])], Ls[GI(P.ft_op_b[k])], part);
             }
-            Y[GI(t)] = acc;
+            part = lanes_sum(c, part);
+            if (on && c.rr == 0) {
+                double acc = Y[GI(t)] - part;
+                if (t >= P.nnzL) {  // diagonal: dynamic regularisation keeps the expected inertia
+                    const double sgn = (double)P.as_sign[t];
+                    if (!(sgn * acc > delta_dyn)) acc = sgn * delta_dyn;
+                    invD[GI(t - P.nnzL)] = 1.0 / acc;
+                }
+                Y[GI(t)] = acc;
+            }
         }
         __syncthreads();
         for (int w = P.sc_lvl_ptr[lv] + c.slot; w < P.sc_lvl_ptr[lv + 1]; w += c.nslots) {
@@ -197,22 +226,52 @@ __device__ void kkt_ldl_solve(const IpmProgram &P, const Ctx &c, const double *L
 {
     const int G = c.G, sg = c.sg;
     for (int lv = 0; lv < P.nlevels; lv++) {   // forward, rows of L
-        for (int w = P.lvl_ptr[lv] + c.slot; w < P.lvl_ptr[lv + 1]; w += c.nslots) {
-            const int i = P.lvl_nodes[w];
-            double acc = v[GI(i)];
-            for (int k = P.Lr_rp[i]; k < P.Lr_rp[i + 1]; k++) acc = fma(-Ls[GI(P.Lr_pos[k])], v[GI(P.Lr_col[k])], acc);
-            v[GI(i)] = acc;
+        const int wend = P.lvl_ptr[lv + 1];
+        for (int w0 = P.lvl_ptr[lv]; w0 < wend; w0 += c.nisl) {
+            const int w = w0 + c.isl;
+            const bool on = w < wend;
+            int i = 0;
+            double part = 0.0;
+            if (on) {
+                i = P.lvl_nodes[w];
+                const int k1 = P.Lr_rp[i + 1];
+                int k = P.Lr_rp[i] + c.rr;
+                for (; k + c.R < k1; k += 2 * c.R) {
+                    const int p0 = P.Lr_pos[k], c0 = P.Lr_col[k], p1 = P.Lr_pos[k + c.R], c1 = P.Lr_col[k + c.R];
+                    const double l0 = Ls[GI(p0)], v0 = v[GI(c0)], l1 = Ls[GI(p1)], v1 = v[GI(c1)];
+                    part = fma(l0, v0, part);
+                    part = fma(l1, v1, part);
+                }
+                if (k < k1) part = fma(Ls[GI(P.Lr_pos[k])], v[GI(P.Lr_col[k])], part);
+            }
+            part = lanes_sum(c, part);
+            if (on && c.rr == 0) v[GI(i)] -= part;
         }
         __syncthreads();
     }
     for (int i = c.slot; i < P.nk; i += c.nslots) v[GI(i)] *= invD[GI(i)];
     __syncthreads();
     for (int lv = P.nlevels - 1; lv >= 0; lv--) {   // backward, columns of L
-        for (int w = P.lvl_ptr[lv] + c.slot; w < P.lvl_ptr[lv + 1]; w += c.nslots) {
-            const int j = P.lvl_nodes[w];
-            double acc = v[GI(j)];
-            for (int k = P.L_cp[j]; k < P.L_cp[j + 1]; k++) acc = fma(-Ls[GI(k)], v[GI(P.L_ri[k])], acc);
-            v[GI(j)] = acc;
+        const int wend = P.lvl_ptr[lv + 1];
+        for (int w0 = P.lvl_ptr[lv]; w0 < wend; w0 += c.nisl) {
+            const int w = w0 + c.isl;
+            const bool on = w < wend;
+            int j = 0;
+            double part = 0.0;
+            if (on) {
+                j = P.lvl_nodes[w];
+                const int k1 = P.L_cp[j + 1];
+                int k = P.L_cp[j] + c.rr;
+                for (; k + c.R < k1; k += 2 * c.R) {
+                    const int r0 = P.L_ri[k], r1 = P.L_ri[k + c.R];
+                    const double l0 = Ls[GI(k)], v0 = v[GI(r0)], l1 = Ls[GI(k + c.R)], v1 = v[GI(r1)];
+                    part = fma(l0, v0, part);
+                    part = fma(l1, v1, part);
+                }
+                if (k < k1) part = fma(Ls[GI(k)], v[GI(P.L_ri[k])], part);
+            }
+            part = lanes_sum(c, part);
+            if (on && c.rr == 0) v[GI(j)] -= part;
         }
         __syncthreads();
     }
@@ -308,6 +367,25 @@ __device__ double cone_alpha_partial(const IpmProgram &P, const Ctx &c, const do
     return a;
 }
 
+// min over cones of the interior margin of u + alpha*du (LP: value; SOC: u0 - |u1|); thread-partial min
+__device__ double cone_margin_partial(const IpmProgram &P, const Ctx &c, const double *u, const double *du,
+                                      double alpha)
+{
+    const int G = c.G, sg = c.sg;
+    double mg = CUDART_INF;
+    for (int r = c.slot; r < P.l; r += c.nslots) mg = fmin(mg, u[GI(r)] + alpha * du[GI(r)]);
+    for (int k = c.slot; k < P.nsoc; k += c.nslots) {
+        const int o = P.soc_off[k], q = P.soc_dim[k];
+        double nn = 0.0;
+        for (int i = 1; i < q; i++) {
+            const double v = u[GI(o + i)] + alpha * du[GI(o + i)];
+            nn += v * v;
+        }
+        mg = fmin(mg, u[GI(o)] + alpha * du[GI(o)] - sqrt(nn));
+    }
+    return mg;
+}
+
 // Nesterov-Todd scaling from (s, z): lam = W z, W^-2 data.  LP: wm = z/s; SOC: wbar, eta^2.
 __device__ void nt_scaling(const IpmProgram &P, const Ctx &c, const double *s, const double *z, double *lam,
                            double *wm, double *socw, double *soceta)
@@ -320,12 +398,16 @@ __device__ void nt_scaling(const IpmProgram &P, const Ctx &c, const double *s, c
     }
     for (int k = c.slot; k < P.nsoc; k += c.nslots) {
         const int o = P.soc_off[k], q = P.soc_dim[k], wo = o - P.l, wb = P.soc_woff[k];
-        double ss = s[GI(o)] * s[GI(o)], zz = z[GI(o)] * z[GI(o)], sz = s[GI(o)] * z[GI(o)];
+        // s'Js = (s0 - |s1|)(s0 + |s1|): same expression as the interior test of the line search, so a
+        // point accepted there can never produce a negative determinant here
+        double s1s1 = 0.0, z1z1 = 0.0, sz = s[GI(o)] * z[GI(o)];
         for (int i = 1; i < q; i++) {
-            ss -= s[GI(o + i)] * s[GI(o + i)];
-            zz -= z[GI(o + i)] * z[GI(o + i)];
+            s1s1 += s[GI(o + i)] * s[GI(o + i)];
+            z1z1 += z[GI(o + i)] * z[GI(o + i)];
             sz += s[GI(o + i)] * z[GI(o + i)];
         }
+        const double ns1 = sqrt(s1s1), nz1 = sqrt(z1z1);
+        const double ss = (s[GI(o)] - ns1) * (s[GI(o)] + ns1), zz = (z[GI(o)] - nz1) * (z[GI(o)] + nz1);
         const double sn = sqrt(ss), zn = sqrt(zz);
         const double gam = sqrt(0.5 * (1.0 + sz / (sn * zn)));
         const double ig = 1.0 / (2.0 * gam);
@@ -424,6 +506,61 @@ __device__ void combined_tmp(const IpmProgram &P, const Ctx &c, const double *s,
     }
 }
 
+// Ruiz equilibration of [A; G] in place (ECOS preprocesses its data the same way): rows and columns are
+// repeatedly divided by the square root of their max-norm; all rows of one second-order cone share a
+// factor (the cone must stay a cone).  b, h, c are scaled consistently; the solution is mapped back by
+// x = D x^, y = Ea y^, z = Eg z^, s = s^ / Eg in the epilogue.
+__device__ void equilibrate(const IpmProgram &P, const Ctx &c, double *Av, double *Gv, double *cc, double *bb,
+                            double *hh, double *eqD, double *eqA, double *eqG, int iters)
+{
+    const int G = c.G, sg = c.sg;
+    for (int i = c.slot; i < P.n; i += c.nslots) eqD[GI(i)] = 1.0;
+    for (int i = c.slot; i < P.p; i += c.nslots) eqA[GI(i)] = 1.0;
+    for (int i = c.slot; i < P.m; i += c.nslots) eqG[GI(i)] = 1.0;
+    __syncthreads();
+    for (int it = 0; it < iters; it++) {
+        // rows
+        for (int r = c.slot; r < P.p; r += c.nslots) {
+            double mx = 0.0;
+            for (int k = P.A_rp[r]; k < P.A_rp[r + 1]; k++) mx = fmax(mx, fabs(Av[GI(k)]));
+            const double f = mx > 0.0 ? rsqrt(mx) : 1.0;
+            for (int k = P.A_rp[r]; k < P.A_rp[r + 1]; k++) Av[GI(k)] *= f;
+            eqA[GI(r)] *= f;
+        }
+        for (int r = c.slot; r < P.l; r += c.nslots) {
+            double mx = 0.0;
+            for (int k = P.G_rp[r]; k < P.G_rp[r + 1]; k++) mx = fmax(mx, fabs(Gv[GI(k)]));
+            const double f = mx > 0.0 ? rsqrt(mx) : 1.0;
+            for (int k = P.G_rp[r]; k < P.G_rp[r + 1]; k++) Gv[GI(k)] *= f;
+            eqG[GI(r)] *= f;
+        }
+        for (int q = c.slot; q < P.nsoc; q += c.nslots) {
+            const int o = P.soc_off[q], d = P.soc_dim[q];
+            double mx = 0.0;
+            for (int k = P.G_rp[o]; k < P.G_rp[o + d]; k++) mx = fmax(mx, fabs(Gv[GI(k)]));
+            const double f = mx > 0.0 ? rsqrt(mx) : 1.0;
+            for (int k = P.G_rp[o]; k < P.G_rp[o + d]; k++) Gv[GI(k)] *= f;
+            for (int r = o; r < o + d; r++) eqG[GI(r)] *= f;
+        }
+        __syncthreads();
+        // columns
+        for (int v = c.slot; v < P.n; v += c.nslots) {
+            double mx = 0.0;
+            for (int k = P.At_rp[v]; k < P.At_rp[v + 1]; k++) mx = fmax(mx, fabs(Av[GI(P.At_vi[k])]));
+            for (int k = P.Gt_rp[v]; k < P.Gt_rp[v + 1]; k++) mx = fmax(mx, fabs(Gv[GI(P.Gt_vi[k])]));
+            const double f = mx > 0.0 ? rsqrt(mx) : 1.0;
+            for (int k = P.At_rp[v]; k < P.At_rp[v + 1]; k++) Av[GI(P.At_vi[k])] *= f;
+            for (int k = P.Gt_rp[v]; k < P.Gt_rp[v + 1]; k++) Gv[GI(P.Gt_vi[k])] *= f;
+            eqD[GI(v)] *= f;
+        }
+        __syncthreads();
+    }
+    for (int i = c.slot; i < P.n; i += c.nslots) cc[GI(i)] *= eqD[GI(i)];
+    for (int i = c.slot; i < P.p; i += c.nslots) bb[GI(i)] *= eqA[GI(i)];
+    for (int i = c.slot; i < P.m; i += c.nslots) hh[GI(i)] *= eqG[GI(i)];
+    __syncthreads();
+}
+
 // =============================================================================================
 __global__ void __launch_bounds__(IPM_NT) k_ipm_solve(const IpmProgram P, const IpmData D, const IpmOpts O)
 {
@@ -431,10 +568,12 @@ __global__ void __launch_bounds__(IPM_NT) k_ipm_solve(const IpmProgram P, const 
     __shared__ double s_out[8 * IPM_MAXG];
     __shared__ double s_nb[IPM_MAXG], s_nh[IPM_MAXG], s_nc[IPM_MAXG];
     __shared__ double s_mu[IPM_MAXG], s_sigmu[IPM_MAXG], s_alpha[IPM_MAXG], s_scale[IPM_MAXG];
-    __shared__ int s_done[IPM_MAXG], s_status[IPM_MAXG], s_iters[IPM_MAXG], s_alldone;
+    __shared__ int s_done[IPM_MAXG], s_status[IPM_MAXG], s_iters[IPM_MAXG], s_alldone, s_save[IPM_MAXG], s_stall[IPM_MAXG];
+    __shared__ double s_best[IPM_MAXG], s_bp[IPM_MAXG], s_bd[IPM_MAXG], s_br[3 * IPM_MAXG];
 
     Ctx c;
     c.G = D.G; c.tid = threadIdx.x; c.sg = c.tid % c.G; c.slot = c.tid / c.G; c.nslots = IPM_NT / c.G;
+    c.R = D.R; c.rr = c.slot % c.R; c.isl = c.slot / c.R; c.nisl = c.nslots / c.R;
     c.red = s_red; c.out = s_out;
     const int G = c.G, sg = c.sg;
     const size_t g = blockIdx.x;
@@ -443,8 +582,10 @@ __global__ void __launch_bounds__(IPM_NT) k_ipm_solve(const IpmProgram P, const 
     (void)live;
 
 #define GP(arr, E) ((arr) + g * (size_t)(E) * G)
-    const double *Av = GP(D.Av, P.nnzA), *Gv = GP(D.Gv, P.nnzG), *cc = GP(D.c, P.n), *bb = GP(D.b, P.p), *hh = GP(D.h, P.m);
+    double *Av = GP(D.Av, P.nnzA), *Gv = GP(D.Gv, P.nnzG), *cc = GP(D.c, P.n), *bb = GP(D.b, P.p), *hh = GP(D.h, P.m);
+    double *eqD = GP(D.eqD, P.n), *eqA = GP(D.eqA, P.p), *eqG = GP(D.eqG, P.m);
     double *x = GP(D.x, P.n), *y = GP(D.y, P.p), *z = GP(D.z, P.m), *s = GP(D.s, P.m);
+    double *xb = GP(D.xb, P.n), *yb = GP(D.yb, P.p), *zb = GP(D.zb, P.m), *sb = GP(D.sb, P.m);
     double *rx = GP(D.rx, P.n), *ry = GP(D.ry, P.p), *rz = GP(D.rz, P.m), *lam = GP(D.lam, P.m);
     double *wm = GP(D.wm, P.nwm), *socw = GP(D.socw, P.m - P.l + 1), *soceta = GP(D.soceta, P.nsoc + 1);
     double *dx = GP(D.dx, P.n), *dy = GP(D.dy, P.p), *dz = GP(D.dz, P.m), *ds = GP(D.ds, P.m);
@@ -455,7 +596,8 @@ __global__ void __launch_bounds__(IPM_NT) k_ipm_solve(const IpmProgram P, const 
     double *Y = GP(D.Y, P.nnzL + P.nk), *Ls = GP(D.Ls, P.nnzL + 1), *invD = GP(D.invD, P.nk);
 #undef GP
 
-    if (c.tid < G) { s_done[c.tid] = 0; s_status[c.tid] = IPM_MAXIT; s_iters[c.tid] = 0; }
+    if (c.tid < G) { s_done[c.tid] = 0; s_status[c.tid] = IPM_MAXIT; s_iters[c.tid] = 0; s_best[c.tid] = CUDART_INF; s_save[c.tid] = 0; s_stall[c.tid] = 0; }
+    if (O.equil > 0) equilibrate(P, c, Av, Gv, cc, bb, hh, eqD, eqA, eqG, O.equil);
     // ---- data norms ----
     {
         double v[3] = {0.0, 0.0, 0.0};
@@ -554,18 +696,26 @@ __global__ void __launch_bounds__(IPM_NT) k_ipm_solve(const IpmProgram P, const 
             const double pres = fmax(nry / s_nb[q], nrz / s_nh[q]), dres = nrx / s_nc[q];
             const double relgap = gap / fmax(fmax(fabs(pcost), fabs(dcost)), 1.0);
             s_mu[q] = gap / deg;
+            s_save[q] = 0;
             if (!s_done[q]) {
-                const int sd = (int)g * G + q;
-                if (sd < D.B) {
-                    D.pobj[sd] = pcost; D.dobj[sd] = dcost;
-                    D.res[sd] = pres; D.res[D.B + sd] = dres; D.res[2 * D.B + sd] = gap;
-                }
                 s_iters[q] = it;
+                const double acc = fmax(fmax(pres, dres), fmin(gap, relgap));
+                if (isfinite(acc) && gap >= 0.0 && acc < s_best[q]) {
+                    s_best[q] = acc; s_save[q] = 1; s_stall[q] = 0;
+                    s_bp[q] = pcost; s_bd[q] = dcost; s_br[q] = pres; s_br[IPM_MAXG + q] = dres; s_br[2 * IPM_MAXG + q] = gap;
+                } else s_stall[q]++;
                 if (!(isfinite(pres) && isfinite(dres) && isfinite(gap))) { s_done[q] = 1; s_status[q] = IPM_NUMERICAL; }
                 else if (pres <= O.feastol && dres <= O.feastol && (gap <= O.abstol || relgap <= O.reltol)) {
                     s_done[q] = 1; s_status[q] = IPM_OPTIMAL;
-                } else if (it == O.maxit) { s_done[q] = 1; s_status[q] = IPM_MAXIT; }
+                } else if (s_stall[q] >= 4 && s_best[q] <= 1e-6) { s_done[q] = 1; s_status[q] = IPM_NUMERICAL; }  // numerical floor
+                else if (it == O.maxit) { s_done[q] = 1; s_status[q] = IPM_MAXIT; }
             }
+        }
+        __syncthreads();
+        if (s_save[sg]) {
+            for (int i = c.slot; i < P.n; i += c.nslots) xb[GI(i)] = x[GI(i)];
+            for (int i = c.slot; i < P.p; i += c.nslots) yb[GI(i)] = y[GI(i)];
+            for (int i = c.slot; i < P.m; i += c.nslots) { zb[GI(i)] = z[GI(i)]; sb[GI(i)] = s[GI(i)]; }
         }
         __syncthreads();
         if (c.tid == 0) {
@@ -588,9 +738,9 @@ __global__ void __launch_bounds__(IPM_NT) k_ipm_solve(const IpmProgram P, const 
         for (int i = c.slot; i < P.m; i += c.nslots) ds[GI(i)] = -rz[GI(i)] + s[GI(i)];  // ds used as bz scratch
         __syncthreads();
         kkt_solve(P, c, D, Av, Gv, wm, socw, soceta, r1, r2, ds, dx, dy, dza, tm, gm, e1, e2, rhs, Ls, invD, O.nref);
-        apply_w2(P, c, wm, socw, soceta, dza, dsa);
-        __syncthreads();
-        for (int i = c.slot; i < P.m; i += c.nslots) dsa[GI(i)] = -s[GI(i)] - dsa[GI(i)];
+        // ds = tmp - W^2 dz with tmp = -s; W^2 dz == G dx - bz is left in gm by kkt_solve (no W^2 W^-2
+        // round trip: keeps G dx + ds = -rz to rounding even when the scaling is ill-conditioned)
+        for (int i = c.slot; i < P.m; i += c.nslots) dsa[GI(i)] = -s[GI(i)] - gm[GI(i)];
         __syncthreads();
         {
             double a[1] = {fmin(cone_alpha_partial(P, c, s, dsa), cone_alpha_partial(P, c, z, dza))};
@@ -618,15 +768,27 @@ __global__ void __launch_bounds__(IPM_NT) k_ipm_solve(const IpmProgram P, const 
         }
         __syncthreads();
         kkt_solve(P, c, D, Av, Gv, wm, socw, soceta, r1, r2, ds, dx, dy, dz, tm, gm, e1, e2, rhs, Ls, invD, O.nref);
-        apply_w2(P, c, wm, socw, soceta, dz, ds);
-        __syncthreads();
-        for (int i = c.slot; i < P.m; i += c.nslots) ds[GI(i)] = dsa[GI(i)] - ds[GI(i)];
+        for (int i = c.slot; i < P.m; i += c.nslots) ds[GI(i)] = dsa[GI(i)] - gm[GI(i)];
         __syncthreads();
         {
             double a[1] = {fmin(cone_alpha_partial(P, c, s, ds), cone_alpha_partial(P, c, z, dz))};
             seed_reduce<1>(c, a, 1);
             if (c.tid < G) s_alpha[c.tid] = s_done[c.tid] ? 0.0 : fmin(1.0, 0.99 * s_out[c.tid]);
             __syncthreads();
+        }
+        // safeguard: make sure the new point is strictly interior (halve the step otherwise) so that the
+        // next NT scaling is well defined
+        for (int bt = 0; bt < 12; bt++) {
+            const double al = s_alpha[sg];
+            double mg[1] = {fmin(cone_margin_partial(P, c, s, ds, al), cone_margin_partial(P, c, z, dz, al))};
+            seed_reduce<1>(c, mg, 1);
+            if (c.tid == 0) s_alldone = 1;
+            __syncthreads();
+            if (c.tid < G && s_alpha[c.tid] > 0.0 && !(s_out[c.tid] > 0.0)) { s_alpha[c.tid] *= 0.5; s_alldone = 0; }
+            __syncthreads();
+            const int okall = s_alldone;
+            __syncthreads();
+            if (okall) break;
         }
         {
             const double al = s_alpha[sg];
@@ -638,9 +800,32 @@ __global__ void __launch_bounds__(IPM_NT) k_ipm_solve(const IpmProgram P, const 
         }
         __syncthreads();
     }
+    // ---- epilogue: the best iterate is the answer (ECOS reports its best point the same way) ----
+    __syncthreads();
+    // the numerical floor of the fp64 normal-equation factorisation sits within ~10x of ECOS' 1e-8 targets
+    if (c.tid < G && s_status[c.tid] != IPM_OPTIMAL) {
+        if (s_best[c.tid] <= 10.0 * fmax(O.feastol, O.reltol)) s_status[c.tid] = IPM_OPTIMAL;
+        else if (s_best[c.tid] <= 5e-5) s_status[c.tid] = IPM_ALMOST;
+    }
+    __syncthreads();
+    if (s_best[sg] < CUDART_INF) {
+        for (int i = c.slot; i < P.n; i += c.nslots) x[GI(i)] = xb[GI(i)];
+        for (int i = c.slot; i < P.p; i += c.nslots) y[GI(i)] = yb[GI(i)];
+        for (int i = c.slot; i < P.m; i += c.nslots) { z[GI(i)] = zb[GI(i)]; s[GI(i)] = sb[GI(i)]; }
+    }
+    if (O.equil > 0) {  // back to the caller's units
+        __syncthreads();
+        for (int i = c.slot; i < P.n; i += c.nslots) x[GI(i)] *= eqD[GI(i)];
+        for (int i = c.slot; i < P.p; i += c.nslots) y[GI(i)] *= eqA[GI(i)];
+        for (int i = c.slot; i < P.m; i += c.nslots) { z[GI(i)] *= eqG[GI(i)]; s[GI(i)] /= eqG[GI(i)]; }
+    }
     if (c.tid < G) {
         const int sd = (int)g * G + c.tid;
-        if (sd < D.B) { D.status[sd] = s_status[c.tid]; D.iters[sd] = s_iters[c.tid]; }
+        if (sd < D.B) {
+            D.status[sd] = s_status[c.tid]; D.iters[sd] = s_iters[c.tid];
+            D.pobj[sd] = s_bp[c.tid]; D.dobj[sd] = s_bd[c.tid];
+            D.res[sd] = s_br[c.tid]; D.res[D.B + sd] = s_br[IPM_MAXG + c.tid]; D.res[2 * D.B + sd] = s_br[2 * IPM_MAXG + c.tid];
+        }
     }
 }
 #undef GI

@@ -46,17 +46,17 @@ SIGNATURES = {
     "scpb_cone_solve": (C.c_int32, [C.c_void_p, C.c_int32, _dp, _dp, _dp, _dp, _dp, C.c_void_p,
                                     _dp, _dp, _dp, _dp, _dp, _dp, _ip, _ip, _dp]),
     "scpb_debug_kkt_solve": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _ip, _ip, _ip, _ip, C.c_int32, C.c_int32,
-                                         _ip, _ip, _dp, _dp, _dp, C.c_double, _dp, _dp, C.POINTER(C.c_int64)]),
+                                         _ip, _ip, _dp, _dp, _dp, C.c_double, C.c_double, _dp, _dp, C.POINTER(C.c_int64)]),
 }
 
 
 class ConeOpts(C.Structure):
     _fields_ = [("feastol", C.c_double), ("abstol", C.c_double), ("reltol", C.c_double),
                 ("delta", C.c_double), ("delta_dyn", C.c_double), ("maxit", C.c_int32), ("nref", C.c_int32),
-                ("verbose", C.c_int32), ("group", C.c_int32)]
+                ("verbose", C.c_int32), ("group", C.c_int32), ("equil", C.c_int32)]
 
 
-CONE_STATUS = {0: "OPTIMAL", 1: "ITERATION_LIMIT", 2: "NUMERICAL_ERROR"}
+CONE_STATUS = {0: "OPTIMAL", 1: "ITERATION_LIMIT", 2: "NUMERICAL_ERROR", 3: "ALMOST_OPTIMAL"}
 
 
 class ScpbError(RuntimeError):
@@ -213,6 +213,8 @@ class ConeProblem:
         assert Avals.shape == (B, self.nnzA) and Gvals.shape == (B, self.nnzG), (Avals.shape, Gvals.shape)
         assert c.shape == (B, self.n) and b.shape == (B, self.p) and h.shape == (B, self.m)
         o = ConeOpts()
+        o.nref = -1
+        o.equil = -1
         for k_, v in opts.items():
             setattr(o, k_, v)
         out = dict(x=np.empty((B, self.n)), y=np.empty((B, self.p)), z=np.empty((B, self.m)),
@@ -228,7 +230,7 @@ class ConeProblem:
         return out
 
 
-def debug_kkt_solve(A, G, l, soc_dims, perm, Avals, Gvals, wm, delta, rhs):
+def debug_kkt_solve(A, G, l, soc_dims, perm, Avals, Gvals, wm, delta, rhs, delta_dyn=0.0):
     """CPU interpreter of the index programs for one seed (test hook, see include/scpb.h)."""
     lib = load()
     A = A.tocsr(); G = G.tocsr(); A.sort_indices(); G.sort_indices()
@@ -240,7 +242,7 @@ def debug_kkt_solve(A, G, l, soc_dims, perm, Avals, Gvals, wm, delta, rhs):
     sol = np.zeros(n + p)
     info = (C.c_int64 * 4)()
     rc = lib.scpb_debug_kkt_solve(n, p, m, a0[1], a1[1], g0[1], g1[1], int(l), len(soc_dims), sd[1], pm[1],
-                                  pAv, pGv, pwm, float(delta), pr, sol.ctypes.data_as(_dp), info)
+                                  pAv, pGv, pwm, float(delta), float(delta_dyn), pr, sol.ctypes.data_as(_dp), info)
     if rc != 0:
         raise ScpbError(f"scpb_debug_kkt_solve failed ({rc})")
     return sol, dict(nnzL=int(info[0]), levels=int(info[1]), factor_ops=int(info[2]), assembly_ops=int(info[3]))
