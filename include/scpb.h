@@ -119,6 +119,38 @@ int32_t scpb_cone_solve(scpb_cone c, int32_t B, const double *Avals, const doubl
                         const scpb_cone_opts *opts, double *x, double *y, double *z, double *s,
                         double *pobj, double *dobj, int32_t *status, int32_t *iters, double *seconds);
 
+/* ---- batched PTR loop: replaces the body of PTR.solve (src/solvers/ptr.jl:448-532) for B seeds ----
+ * The host template (scptoolbox.jl_b200/ptr.py, mirror of ptr.jl:213-293,565-895 + scp.jl:657-895) supplies
+ * the fill matrix W with [Avals; Gvals; c; b; h; c0] = W * src, where src is the per-seed vector of
+ * device-computed quantities laid out by the offsets below (source 0 is the constant 1):
+ *   oA,oBm,oBp,oF,or_,oE : DLTV blocks per segment (column-major nx*nx, nx*nu, nx*nf, nx) -- discretize!
+ *   oC,oD,oG,ors         : ds/dx, ds/du, ds/dp (row-major) and r = s - Cx - Du - Gp per node (scp.jl:763-773)
+ *   oxh,ouh,oph          : scaled reference trajectory (ptr.jl:575-577)
+ * vx,vu,vp are the offsets of the scaled x, u, p variable blocks inside the cone program's variables. */
+typedef struct scpb_ptr_s *scpb_ptr;
+
+typedef struct {
+    int32_t N, Nsub, nx, nu, np, ns, nf;
+    int32_t nsrc, oA, oBm, oBp, oF, or_, oE, oC, oD, oG, ors, oxh, ouh, oph;
+    int32_t nval, vx, vu, vp;
+    int32_t q_exit;          /* stopping-criterion norm: 0 = Inf, 1, 2 (pars.q_exit) */
+    int32_t iter_max;
+    double eps_abs, eps_rel, feas_tol;
+} scpb_ptr_desc;
+
+/* scale = [Sx,Su,Sp | cx,cu,cp | iSx] (diagonals, scp.jl:483-516); t_grid[N]. */
+int32_t scpb_ptr_setup(scpb_handle h, scpb_cone cone, const scpb_ptr_desc *desc, const int32_t *W_rowptr,
+                       const int32_t *W_colind, const double *W_vals, const double *scale, const double *t_grid,
+                       scpb_ptr *out);
+int32_t scpb_ptr_free(scpb_ptr s);
+/* host arrays: initial guesses xd0[B][N][nx], ud0[B][N][nu], p0[B][np]; outputs the final iterates, per-seed
+ * status (0 = stopping criterion met, 1 = iter_max reached [the reference still reports SCP_SOLVED],
+ * 2+16*cone_status = SCP_FAILED), iteration counts, J_aug, deviation, dynamic feasibility flags and
+ * timing[8] = {discretize, formulate, solve, overhead, total seconds, lock-step iterations, 0, 0}. */
+int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *ud0, const double *p0,
+                       const scpb_cone_opts *opts, double *xd, double *ud, double *p, int32_t *status,
+                       int32_t *iters, double *J, double *deviation, int32_t *feas, double *timing);
+
 /* ---- test hook: CPU interpreter of the solver's index programs for ONE seed (no GPU needed) ----
  * Assembles M = [dI + G'W^-2 G, A'; A, -dI] from (Av, Gv, wm), factors it with the level-scheduled
  * LDL' program and solves M sol = rhs (natural node order: n variables then p equality rows).

@@ -3,5 +3,7 @@
 The directory name carries a dot, so the package is imported under the alias
 `scptoolbox_jl_b200` (see __graft_entry__.load_package()).
 """
-from . import lib, ordering  # noqa: F401
+from . import lib, ordering, parser, problem, ptr  # noqa: F401
+from . import examples  # noqa: F401
+from .examples import starship as _starship  # noqa: F401
 from .lib import Handle, ScpbError  # noqa: F401

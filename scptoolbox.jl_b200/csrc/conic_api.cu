@@ -1,6 +1,7 @@
 // conic_api.cu -- C ABI of the batched cone solver (scpb_cone_*), host orchestration.
 #include "handle.cuh"
 #include "conic_symbolic.h"
+#define CONIC_IPM_IMPL
 #include "conic_ipm.cuh"
 
 struct scpb_cone_s {
@@ -45,7 +46,7 @@ __global__ void k_from_grouped(const double *src, double *dst, int E, int B, int
     dst[(size_t)sd * E + e] = src[((size_t)(sd / G) * E + e) * G + (sd % G)];
 }
 
-static int pick_group(int B, int want)
+int scpb_internal_pick_group(int B, int want)
 {
     if (want > 0) {
         int g = 1;
@@ -111,7 +112,7 @@ int scpb_internal_cone_run(scpb_cone_s *c, const IpmOpts &o)
     return SCPB_OK;
 }
 
-static IpmOpts make_opts(const scpb_cone_opts *o)
+IpmOpts scpb_internal_make_opts(const scpb_cone_opts *o)
 {
     IpmOpts r;
     r.feastol = (o && o->feastol > 0) ? o->feastol : 1e-8;
@@ -124,6 +125,11 @@ static IpmOpts make_opts(const scpb_cone_opts *o)
     r.equil = (o && o->equil >= 0) ? o->equil : 5;
     return r;
 }
+
+int scpb_internal_cone_reserve(scpb_cone_s *c, int B, int G) { return cone_reserve(c, B, G); }
+IpmData *scpb_internal_cone_data(scpb_cone_s *c) { return &c->D; }
+const ConeSymbolic *scpb_internal_cone_sym(scpb_cone_s *c) { return &c->S; }
+scpb_handle_s *scpb_internal_cone_handle(scpb_cone_s *c) { return c->h; }
 
 extern "C" {
 
@@ -200,7 +206,7 @@ int32_t scpb_cone_solve(scpb_cone c, int32_t B, const double *Avals, const doubl
     scpb_handle_s *h = c->h;
     if (B <= 0 || !cvec || (c->S.p > 0 && !bvec) || (c->S.m > 0 && !hvec)) return set_err(h, SCPB_ERR_ARG, "cone_solve: bad arguments");
     SCPB_CUDA(h, cudaSetDevice(h->device));
-    const int G = pick_group(B, opts ? opts->group : 0);
+    const int G = scpb_internal_pick_group(B, opts ? opts->group : 0);
     int rc = cone_reserve(c, B, G);
     if (rc) return rc;
     const ConeSymbolic &S = c->S;
@@ -226,7 +232,7 @@ int32_t scpb_cone_solve(scpb_cone c, int32_t B, const double *Avals, const doubl
     if ((rc = put(Avals, c->D.Av, S.A_ci.size())) || (rc = put(Gvals, c->D.Gv, S.G_ci.size())) ||
         (rc = put(cvec, c->D.c, S.n)) || (rc = put(bvec, c->D.b, S.p)) || (rc = put(hvec, c->D.h, S.m)))
         return rc;
-    IpmOpts o = make_opts(opts);
+    IpmOpts o = scpb_internal_make_opts(opts);
     SCPB_CUDA(h, cudaEventRecord(h->ev0, st));
     rc = scpb_internal_cone_run(c, o);
     if (rc) return rc;

@@ -58,6 +58,7 @@ enum { IPM_OPTIMAL = 0, IPM_MAXIT = 1, IPM_NUMERICAL = 2, IPM_ALMOST = 3 };
 #define IPM_MAXG 32
 #define IPM_NT 512
 
+#ifdef CONIC_IPM_IMPL   // the kernel itself is compiled in conic_api.cu only
 // ---------------------------------------------------------------------------------------------
 struct Ctx {
     int G, sg, slot, nslots, tid;
@@ -829,3 +830,4 @@ __global__ void __launch_bounds__(IPM_NT) k_ipm_solve(const IpmProgram P, const 
     }
 }
 #undef GI
+#endif  // CONIC_IPM_IMPL

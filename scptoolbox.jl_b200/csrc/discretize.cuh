@@ -25,7 +25,13 @@
 
 struct OutView {
     double *ptr;
-    long long sB, sK, sE;  // strides (in doubles) over seed, segment, element
+    long long sB, sK, sE;  // strides (in doubles) over seed-in-group, segment, element
+    long long sGrp = 0;    // stride over seed groups
+    int Gq = 1;            // seeds per group: address = (b/Gq)*sGrp + (b%Gq)*sB + k*sK + e*sE
+    __host__ __device__ long long at(int b, int k, long long e) const
+    {
+        return (long long)(b / Gq) * sGrp + (long long)(b % Gq) * sB + (long long)k * sK + e * sE;
+    }
 };
 
 struct DiscArgs {
@@ -271,7 +277,7 @@ __global__ void __launch_bounds__(128) k_discretize_foh(const DiscArgs a)
         else if (c == NX + 2 * NU + NF) { ov = &a.r; e0 = 0; }
         else { ov = &a.E; e0 = (long long)(c - (NX + 2 * NU + NF + 1)) * NX; }
         if (ov->ptr == nullptr) continue;
-        double *dst = ov->ptr + b * ov->sB + k * ov->sK + e0 * ov->sE;
+        double *dst = ov->ptr + ov->at(b, k, e0);
 #pragma unroll
         for (int r = 0; r < NX; r++) dst[r * ov->sE] = raw ? colv[s][r] : outc[s][r];
     }
@@ -283,7 +289,7 @@ __global__ void __launch_bounds__(128) k_discretize_foh(const DiscArgs a)
         for (int i = 0; i < NX; i++) {
             const double xn = a.xd[b * a.xsB + (k + 1) * a.xsK + i * a.xsE];
             const double df = xn - xv[i];
-            if (a.defect.ptr) a.defect.ptr[b * a.defect.sB + k * a.defect.sK + i * a.defect.sE] = df;
+            if (a.defect.ptr) a.defect.ptr[a.defect.at(b, k, i)] = df;
             const double av = fabs(a.iSx[i] * df);
             if (av > nrm || av != av) nrm = av;
         }
@@ -293,7 +299,7 @@ __global__ void __launch_bounds__(128) k_discretize_foh(const DiscArgs a)
 }
 
 // feas[b] = all_k !(dnorm[b][k] > feas_tol)   (NaN compares false, as in the reference)
-__global__ void k_feas_reduce(const double *dnorm, int B, int nseg, double feas_tol, int *feas)
+static __global__ void k_feas_reduce(const double *dnorm, int B, int nseg, double feas_tol, int *feas)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;

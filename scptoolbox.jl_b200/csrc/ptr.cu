@@ -1,0 +1,428 @@
+// ptr.cu -- native batched PTR loop (scpb_ptr_*): the device-resident replacement of the loop body of
+// PTR.solve (src/solvers/ptr.jl:448-532) for a batch of independent seeds in lock step:
+//   formulate  : k_linearize (s,C,D,G at the reference, scp.jl:744-794; scaled references for the trust
+//                region, ptr.jl:575-577) + k_assemble ([Avals;Gvals;c;b;h] = W * src -- kernel K6, replaces
+//                the per-iteration JuMP rebuild ptr.jl:470-478)
+//   solve      : k_ipm_solve (conic_ipm.cuh)                       -- solve_subproblem!, scp.jl:942-950
+//   discretize : k_discretize_foh on the new iterate (ptr.jl:380)  -- writes the DLTV straight into `src`
+//   accept/stop: k_ptr_step -- solution_deviation (scp.jl:909-931) + check_stopping_criterion! (ptr.jl:908-932)
+// Seeds that have stopped are frozen (their iterate is re-extracted unchanged) so a finished or failed
+// seed never stalls the batch.
+#include "handle.cuh"
+#include "discretize.cuh"
+#include "constraints.cuh"
+#include "conic_symbolic.h"
+#include "conic_ipm.cuh"
+
+// pieces of conic_api.cu used here
+struct scpb_cone_s;
+int scpb_internal_cone_run(scpb_cone_s *c, const IpmOpts &o);
+int scpb_internal_cone_reserve(scpb_cone_s *c, int B, int G);
+IpmData *scpb_internal_cone_data(scpb_cone_s *c);
+const ConeSymbolic *scpb_internal_cone_sym(scpb_cone_s *c);
+scpb_handle_s *scpb_internal_cone_handle(scpb_cone_s *c);
+IpmOpts scpb_internal_make_opts(const scpb_cone_opts *o);
+int scpb_internal_pick_group(int B, int want);
+int scpb_internal_discretize(scpb_handle_s *h, DiscArgs &a, double feas_tol, int *feas);
+
+struct PtrDev {
+    int B, G, N, nx, nu, np, ns;
+    int nsrc, oC, oD, oG, ors, oxh, ouh, oph;
+    const double *t_grid, *Sx, *cx, *Su, *cu, *Sp, *cp;
+    double *src;
+    ModelPar par;
+};
+
+__device__ __forceinline__ size_t gaddr(int b, int G, long long E, long long e)
+{
+    return ((size_t)(b / G) * E + e) * G + (b % G);
+}
+
+// one thread per (seed, node): nonconvex constraint linearisation + scaled reference
+template <class CP>
+__global__ void k_linearize(const PtrDev d, const double *xd, const double *ud, const double *p)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)d.B * d.N) return;
+    const int b = (int)(i / d.N), k = (int)(i % d.N);
+    const double *x = xd + ((size_t)b * d.N + k) * d.nx, *u = ud + ((size_t)b * d.N + k) * d.nu, *pp = p + (size_t)b * d.np;
+    const int G = d.G;
+    const long long E = d.nsrc;
+    if constexpr (CP::NS > 0) {
+        constexpr int NS = CP::NS, NX = CP::NX, NU = CP::NU, NP = CP::NP;
+        double s[NS], C[NS * NX], D[NS * NU], Gm[NS * NP];
+        CP::eval(d.par, d.t_grid[k], d.N, x, u, pp, s, C, D, Gm);
+        for (int r = 0; r < NS; r++) {
+            double rs = s[r];
+            for (int j = 0; j < NX; j++) { rs -= C[r * NX + j] * x[j]; d.src[gaddr(b, G, E, d.oC + ((long long)k * NS + r) * NX + j)] = C[r * NX + j]; }
+            for (int j = 0; j < NU; j++) { rs -= D[r * NU + j] * u[j]; d.src[gaddr(b, G, E, d.oD + ((long long)k * NS + r) * NU + j)] = D[r * NU + j]; }
+            for (int j = 0; j < NP; j++) { rs -= Gm[r * NP + j] * pp[j]; d.src[gaddr(b, G, E, d.oG + ((long long)k * NS + r) * NP + j)] = Gm[r * NP + j]; }
+            d.src[gaddr(b, G, E, d.ors + (long long)k * NS + r)] = rs;
+        }
+    }
+    for (int j = 0; j < d.nx; j++) d.src[gaddr(b, G, E, d.oxh + (long long)k * d.nx + j)] = (x[j] - d.cx[j]) / d.Sx[j];
+    for (int j = 0; j < d.nu; j++) d.src[gaddr(b, G, E, d.ouh + (long long)k * d.nu + j)] = (u[j] - d.cu[j]) / d.Su[j];
+    if (k == 0) {
+        for (int j = 0; j < d.np; j++) d.src[gaddr(b, G, E, d.oph + j)] = (pp[j] - d.cp[j]) / d.Sp[j];
+        d.src[gaddr(b, G, E, 0)] = 1.0;
+    }
+}
+
+struct AsmDev {
+    int B, G, nsrc, nval, nnzA, nnzG, n, p, m;
+    const int *W_rp, *W_ci;
+    const double *W_v;
+    const double *src;
+    double *Av, *Gv, *c, *b, *h, *c0;
+};
+
+// K6: [Avals; Gvals; c; b; h; c0] = W * src, one thread per (value row, seed); seed is the fast index
+__global__ void k_assemble(const AsmDev a)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int Bp = ((a.B + a.G - 1) / a.G) * a.G;
+    if (i >= (long long)a.nval * Bp) return;
+    const int sd = (int)(i % Bp);
+    long long e = i / Bp;
+    const int G = a.G, gq = sd / G, sg = sd % G;
+    const double *s = a.src + (size_t)gq * a.nsrc * G + sg;
+    double acc = 0.0;
+    for (int k = a.W_rp[e]; k < a.W_rp[e + 1]; k++) acc = fma(a.W_v[k], s[(size_t)a.W_ci[k] * G], acc);
+    double *dst; long long E;
+    if (e < a.nnzA) { dst = a.Av; E = a.nnzA; }
+    else if ((e -= a.nnzA) < a.nnzG) { dst = a.Gv; E = a.nnzG; }
+    else if ((e -= a.nnzG) < a.n) { dst = a.c; E = a.n; }
+    else if ((e -= a.n) < a.p) { dst = a.b; E = a.p; }
+    else if ((e -= a.p) < a.m) { dst = a.h; E = a.m; }
+    else { if (sd < a.B) a.c0[sd] = acc; return; }
+    dst[((size_t)gq * E + e) * G + sg] = acc;
+}
+
+struct StepDev {
+    int B, G, N, nx, nu, np, n, vx, vu, vp, iter, q_exit;  // q_exit: 0 = Inf, 1, 2
+    double eps_abs, eps_rel;
+    const double *Sx, *cx, *Su, *cu, *Sp, *cp;
+    const double *xsol;       // grouped solver x (scaled variables)
+    const double *pobj, *c0;
+    const int *cone_status;
+    double *xd, *ud, *p;      // reference (accepted) trajectory, Julia layout
+    double *xn, *un, *pn;     // new trajectory
+    double *J_ref, *J_new, *dev, *imp;
+    const int *feas_new;
+    int *done, *status, *iters, *nactive;
+};
+
+// extract the new iterate (physical units) for active seeds; frozen seeds re-emit their accepted iterate
+__global__ void k_extract(const StepDev d)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)d.B * d.N) return;
+    const int b = (int)(i / d.N), k = (int)(i % d.N);
+    const bool frozen = d.done[b] != 0;
+    const int G = d.G;
+    for (int j = 0; j < d.nx; j++) {
+        const size_t o = ((size_t)b * d.N + k) * d.nx + j;
+        d.xn[o] = frozen ? d.xd[o] : d.Sx[j] * d.xsol[gaddr(b, G, d.n, d.vx + j + (long long)d.nx * k)] + d.cx[j];
+    }
+    for (int j = 0; j < d.nu; j++) {
+        const size_t o = ((size_t)b * d.N + k) * d.nu + j;
+        d.un[o] = frozen ? d.ud[o] : d.Su[j] * d.xsol[gaddr(b, G, d.n, d.vu + j + (long long)d.nu * k)] + d.cu[j];
+    }
+    if (k == 0) {
+        for (int j = 0; j < d.np; j++) {
+            const size_t o = (size_t)b * d.np + j;
+            d.pn[o] = frozen ? d.p[o] : d.Sp[j] * d.xsol[gaddr(b, G, d.n, d.vp + j)] + d.cp[j];
+        }
+        if (!frozen) d.J_new[b] = d.pobj[b] + d.c0[b];
+    }
+}
+
+__device__ __forceinline__ double qnorm_acc(double acc, double v, int q)
+{
+    v = fabs(v);
+    return q == 0 ? fmax(acc, v) : (q == 1 ? acc + v : acc + v * v);
+}
+
+// one thread per seed: deviation, predicted improvement, stopping rule, acceptance (ptr.jl:908-932, 509)
+__global__ void k_ptr_step(const StepDev d)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= d.B) return;
+    if (d.done[b]) return;
+    const int cs = d.cone_status[b];
+    if (!(cs == IPM_OPTIMAL || cs == IPM_ALMOST)) {  // unsafe_solution, scp.jl:965-980
+        d.done[b] = 1; d.status[b] = 2 + 16 * cs; d.iters[b] = d.iter;
+        return;
+    }
+    const int q = d.q_exit;
+    double dp = 0.0;
+    for (int j = 0; j < d.np; j++) dp = qnorm_acc(dp, (d.pn[(size_t)b * d.np + j] - d.p[(size_t)b * d.np + j]) / d.Sp[j], q);
+    if (q == 2) dp = sqrt(dp);
+    double dx = 0.0;
+    for (int k = 0; k < d.N; k++) {
+        double a = 0.0;
+        for (int j = 0; j < d.nx; j++) {
+            const size_t o = ((size_t)b * d.N + k) * d.nx + j;
+            a = qnorm_acc(a, (d.xn[o] - d.xd[o]) / d.Sx[j], q);
+        }
+        if (q == 2) a = sqrt(a);
+        dx = fmax(dx, a);
+    }
+    const double deviation = dp + dx;
+    const double Jr = d.J_ref[b], Jn = d.J_new[b];
+    const double imp = (Jr - Jn) / fabs(Jr);
+    d.dev[b] = deviation; d.imp[b] = imp;
+    const bool stop = d.iter > 1 && d.feas_new[b] && (fabs(imp) <= d.eps_rel || deviation <= d.eps_abs);
+    // accept: ref <- sol
+    for (int k = 0; k < d.N; k++) {
+        for (int j = 0; j < d.nx; j++) { const size_t o = ((size_t)b * d.N + k) * d.nx + j; d.xd[o] = d.xn[o]; }
+        for (int j = 0; j < d.nu; j++) { const size_t o = ((size_t)b * d.N + k) * d.nu + j; d.ud[o] = d.un[o]; }
+    }
+    for (int j = 0; j < d.np; j++) d.p[(size_t)b * d.np + j] = d.pn[(size_t)b * d.np + j];
+    d.J_ref[b] = Jn;
+    d.iters[b] = d.iter;
+    if (stop) { d.done[b] = 1; d.status[b] = 0; }
+    else atomicAdd(d.nactive, 1);
+}
+
+// ----------------------------------------------------------------------------------------------
+struct scpb_ptr_s {
+    scpb_handle_s *h = nullptr;
+    scpb_cone_s *cone = nullptr;
+    scpb_ptr_desc d{};
+    std::vector<void *> dev;
+    int *W_rp = nullptr, *W_ci = nullptr;
+    double *W_v = nullptr;
+    double *scale = nullptr, *tgrid = nullptr;
+    // batch buffers
+    int capB = 0, capG = 0;
+    std::vector<void *> bb;
+    double *src = nullptr, *xd = nullptr, *ud = nullptr, *p = nullptr, *xn = nullptr, *un = nullptr, *pn = nullptr;
+    double *defect = nullptr, *J_ref = nullptr, *J_new = nullptr, *devi = nullptr, *imp = nullptr, *c0 = nullptr;
+    int *feas = nullptr, *done = nullptr, *status = nullptr, *iters = nullptr, *nactive = nullptr;
+};
+
+template <class T>
+static T *up(scpb_ptr_s *s, const T *src, size_t n)
+{
+    void *d = nullptr;
+    if (cudaMalloc(&d, sizeof(T) * (n + 1)) != cudaSuccess) return nullptr;
+    if (n) cudaMemcpy(d, src, sizeof(T) * n, cudaMemcpyHostToDevice);
+    s->dev.push_back(d);
+    return (T *)d;
+}
+
+static int ptr_reserve(scpb_ptr_s *s, int B, int G)
+{
+    scpb_handle_s *h = s->h;
+    const int Bpad = ((B + G - 1) / G) * G;
+    if (s->capB >= Bpad && s->capG == G) return SCPB_OK;
+    for (void *q : s->bb) cudaFree(q);
+    s->bb.clear();
+    const scpb_ptr_desc &d = s->d;
+    bool ok = true;
+    auto al = [&](size_t bytes) { void *q = nullptr; if (cudaMalloc(&q, bytes + 64) != cudaSuccess) { ok = false; return (void *)nullptr; } s->bb.push_back(q); return q; };
+    const size_t NB = (size_t)Bpad * d.N;
+    s->src = (double *)al(sizeof(double) * (size_t)d.nsrc * Bpad);
+    s->xd = (double *)al(sizeof(double) * NB * d.nx); s->xn = (double *)al(sizeof(double) * NB * d.nx);
+    s->ud = (double *)al(sizeof(double) * NB * d.nu); s->un = (double *)al(sizeof(double) * NB * d.nu);
+    s->p = (double *)al(sizeof(double) * (size_t)Bpad * d.np); s->pn = (double *)al(sizeof(double) * (size_t)Bpad * d.np);
+    s->defect = (double *)al(sizeof(double) * NB * d.nx);
+    s->J_ref = (double *)al(sizeof(double) * Bpad); s->J_new = (double *)al(sizeof(double) * Bpad);
+    s->devi = (double *)al(sizeof(double) * Bpad); s->imp = (double *)al(sizeof(double) * Bpad);
+    s->c0 = (double *)al(sizeof(double) * Bpad);
+    s->feas = (int *)al(sizeof(int) * Bpad); s->done = (int *)al(sizeof(int) * Bpad);
+    s->status = (int *)al(sizeof(int) * Bpad); s->iters = (int *)al(sizeof(int) * Bpad);
+    s->nactive = (int *)al(sizeof(int));
+    if (!ok) return set_err(h, SCPB_ERR_CUDA, "ptr: device allocation failed (B=%d)", B);
+    s->capB = Bpad; s->capG = G;
+    return SCPB_OK;
+}
+
+static OutView grouped(double *src, int G, long long nsrc, long long off, long long blk)
+{
+    OutView v{};
+    v.ptr = src + off * G; v.Gq = G; v.sGrp = nsrc * G; v.sB = 1; v.sK = blk * G; v.sE = G;
+    return v;
+}
+
+static int run_discretize(scpb_ptr_s *s, int B, int G, const double *xd, const double *ud, const double *p)
+{
+    const scpb_ptr_desc &d = s->d;
+    DiscArgs a{};
+    a.B = B; a.N = d.N; a.Nsub = d.Nsub;
+    a.t_grid = s->tgrid; a.xd = xd; a.ud = ud; a.p = p;
+    a.iSx = s->scale + 2 * (size_t)(d.nx + d.nu + d.np);  // iSx stored after S and c blocks
+    a.xsB = (long long)d.N * d.nx; a.xsK = d.nx; a.xsE = 1;
+    a.usB = (long long)d.N * d.nu; a.usK = d.nu; a.usE = 1;
+    a.psB = d.np; a.psE = 1;
+    a.f_packed = 1;
+    const long long nx = d.nx, nu = d.nu;
+    a.A = grouped(s->src, G, d.nsrc, d.oA, nx * nx);
+    a.Bm = grouped(s->src, G, d.nsrc, d.oBm, nx * nu);
+    a.Bp = grouped(s->src, G, d.nsrc, d.oBp, nx * nu);
+    a.F = grouped(s->src, G, d.nsrc, d.oF, nx * d.nf);
+    a.r = grouped(s->src, G, d.nsrc, d.or_, nx);
+    a.E = grouped(s->src, G, d.nsrc, d.oE, nx * nx);
+    OutView df{}; df.ptr = s->defect; df.Gq = 1; df.sGrp = (long long)(d.N - 1) * nx; df.sB = 0; df.sK = nx; df.sE = 1;
+    a.defect = df;
+    return scpb_internal_discretize(s->h, a, d.feas_tol, s->feas);
+}
+
+extern "C" {
+
+int32_t scpb_ptr_setup(scpb_handle h, scpb_cone cone, const scpb_ptr_desc *desc, const int32_t *W_rowptr,
+                       const int32_t *W_colind, const double *W_vals, const double *scale, const double *t_grid,
+                       scpb_ptr *out)
+{
+    if (!h || !cone || !desc || !W_rowptr || !scale || !t_grid || !out) return SCPB_ERR_ARG;
+    *out = nullptr;
+    if (scpb_internal_cone_handle(cone) != h) return set_err(h, SCPB_ERR_ARG, "ptr_setup: cone belongs to another handle");
+    if (desc->nx != h->nx || desc->nu != h->nu || desc->np != h->np)
+        return set_err(h, SCPB_ERR_STATE, "ptr_setup: dimensions differ from the selected model pack");
+    const ConeSymbolic *S = scpb_internal_cone_sym(cone);
+    if (desc->nval != (int)(S->A_ci.size() + S->G_ci.size()) + S->n + S->p + S->m + 1)
+        return set_err(h, SCPB_ERR_ARG, "ptr_setup: nval does not match the cone program (%d)", desc->nval);
+    if (desc->ns > 0 && !(h->model_id == SCPB_MODEL_STARSHIP && desc->ns == Constr<SCPB_MODEL_STARSHIP>::NS))
+        return set_err(h, SCPB_ERR_UNSUPPORTED, "ptr_setup: no constraint pack for model %d with ns=%d", h->model_id, desc->ns);
+    SCPB_CUDA(h, cudaSetDevice(h->device));
+    scpb_ptr_s *s = new (std::nothrow) scpb_ptr_s();
+    if (!s) return SCPB_ERR_CUDA;
+    s->h = h; s->cone = cone; s->d = *desc;
+    const int nnzW = W_rowptr[desc->nval];
+    s->W_rp = up(s, W_rowptr, (size_t)desc->nval + 1);
+    s->W_ci = up(s, W_colind, (size_t)nnzW);
+    s->W_v = up(s, W_vals, (size_t)nnzW);
+    const size_t nsc = (size_t)(desc->nx + desc->nu + desc->np);
+    s->scale = up(s, scale, 2 * nsc + desc->nx);
+    s->tgrid = up(s, t_grid, (size_t)desc->N);
+    for (void *q : s->dev)
+        if (!q) { scpb_ptr_free(s); return set_err(h, SCPB_ERR_CUDA, "ptr_setup: device allocation failed"); }
+    *out = s;
+    return SCPB_OK;
+}
+
+int32_t scpb_ptr_free(scpb_ptr s)
+{
+    if (!s) return SCPB_ERR_ARG;
+    cudaSetDevice(s->h->device);
+    cudaStreamSynchronize(s->h->stream);
+    for (void *q : s->dev) if (q) cudaFree(q);
+    for (void *q : s->bb) if (q) cudaFree(q);
+    delete s;
+    return SCPB_OK;
+}
+
+int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *ud0, const double *p0,
+                       const scpb_cone_opts *opts, double *xd, double *ud, double *p, int32_t *status,
+                       int32_t *iters, double *J, double *deviation, int32_t *feas, double *timing)
+{
+    if (!s) return SCPB_ERR_ARG;
+    scpb_handle_s *h = s->h;
+    if (B <= 0 || !xd0 || !ud0 || !p0) return set_err(h, SCPB_ERR_ARG, "ptr_solve: bad arguments");
+    SCPB_CUDA(h, cudaSetDevice(h->device));
+    const scpb_ptr_desc &d = s->d;
+    const int G = scpb_internal_pick_group(B, opts ? opts->group : 0);
+    int rc = scpb_internal_cone_reserve(s->cone, B, G);
+    if (rc) return rc;
+    if ((rc = ptr_reserve(s, B, G))) return rc;
+    IpmData *D = scpb_internal_cone_data(s->cone);
+    const ConeSymbolic *S = scpb_internal_cone_sym(s->cone);
+    const IpmOpts o = scpb_internal_make_opts(opts);
+    cudaStream_t st = h->stream;
+    const size_t nX = (size_t)B * d.N * d.nx, nU = (size_t)B * d.N * d.nu, nP = (size_t)B * d.np;
+    SCPB_CUDA(h, cudaMemcpyAsync(s->xd, xd0, sizeof(double) * nX, cudaMemcpyHostToDevice, st));
+    SCPB_CUDA(h, cudaMemcpyAsync(s->ud, ud0, sizeof(double) * nU, cudaMemcpyHostToDevice, st));
+    SCPB_CUDA(h, cudaMemcpyAsync(s->p, p0, sizeof(double) * nP, cudaMemcpyHostToDevice, st));
+    SCPB_CUDA(h, cudaMemsetAsync(s->src, 0, sizeof(double) * (size_t)d.nsrc * s->capB, st));
+    SCPB_CUDA(h, cudaMemsetAsync(s->done, 0, sizeof(int) * s->capB, st));
+    SCPB_CUDA(h, cudaMemsetAsync(s->iters, 0, sizeof(int) * s->capB, st));
+    std::vector<int> init_status(s->capB, 1);
+    SCPB_CUDA(h, cudaMemcpyAsync(s->status, init_status.data(), sizeof(int) * s->capB, cudaMemcpyHostToDevice, st));
+    std::vector<double> nanv(s->capB, nan(""));
+    SCPB_CUDA(h, cudaMemcpyAsync(s->J_ref, nanv.data(), sizeof(double) * s->capB, cudaMemcpyHostToDevice, st));
+    SCPB_CUDA(h, cudaMemcpyAsync(s->devi, nanv.data(), sizeof(double) * s->capB, cudaMemcpyHostToDevice, st));
+
+    const size_t nsc = (size_t)(d.nx + d.nu + d.np);
+    const double *Sx = s->scale, *Su = Sx + d.nx, *Sp = Su + d.nu, *cx = s->scale + nsc, *cu = cx + d.nx, *cp = cu + d.nu;
+    PtrDev pd{};
+    pd.B = B; pd.G = G; pd.N = d.N; pd.nx = d.nx; pd.nu = d.nu; pd.np = d.np; pd.ns = d.ns;
+    pd.nsrc = d.nsrc; pd.oC = d.oC; pd.oD = d.oD; pd.oG = d.oG; pd.ors = d.ors; pd.oxh = d.oxh; pd.ouh = d.ouh; pd.oph = d.oph;
+    pd.t_grid = s->tgrid; pd.Sx = Sx; pd.cx = cx; pd.Su = Su; pd.cu = cu; pd.Sp = Sp; pd.cp = cp;
+    pd.src = s->src; pd.par = h->par;
+    AsmDev ad{};
+    ad.B = B; ad.G = G; ad.nsrc = d.nsrc; ad.nval = d.nval; ad.nnzA = (int)S->A_ci.size(); ad.nnzG = (int)S->G_ci.size();
+    ad.n = S->n; ad.p = S->p; ad.m = S->m; ad.W_rp = s->W_rp; ad.W_ci = s->W_ci; ad.W_v = s->W_v; ad.src = s->src;
+    ad.Av = D->Av; ad.Gv = D->Gv; ad.c = D->c; ad.b = D->b; ad.h = D->h; ad.c0 = s->c0;
+    StepDev sd{};
+    sd.B = B; sd.G = G; sd.N = d.N; sd.nx = d.nx; sd.nu = d.nu; sd.np = d.np; sd.n = S->n; sd.vx = d.vx; sd.vu = d.vu; sd.vp = d.vp;
+    sd.q_exit = d.q_exit; sd.eps_abs = d.eps_abs; sd.eps_rel = d.eps_rel;
+    sd.Sx = Sx; sd.cx = cx; sd.Su = Su; sd.cu = cu; sd.Sp = Sp; sd.cp = cp;
+    sd.xsol = D->x; sd.pobj = D->pobj; sd.c0 = s->c0; sd.cone_status = D->status;
+    sd.xd = s->xd; sd.ud = s->ud; sd.p = s->p; sd.xn = s->xn; sd.un = s->un; sd.pn = s->pn;
+    sd.J_ref = s->J_ref; sd.J_new = s->J_new; sd.dev = s->devi; sd.imp = s->imp; sd.feas_new = s->feas;
+    sd.done = s->done; sd.status = s->status; sd.iters = s->iters; sd.nactive = s->nactive;
+
+    // phase timers (the reference's keys: discretize / formulate / solve / overhead, scp.jl:177-178,990-995)
+    std::vector<cudaEvent_t> ev;
+    auto mark = [&]() { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev.push_back(e); };
+    std::vector<int> phase;   // phase id of the interval that ENDS at event i
+    mark(); phase.push_back(-1);
+    if ((rc = run_discretize(s, B, G, s->xd, s->ud, s->p))) return rc;   // generate_initial_guess -> discretize!
+    mark(); phase.push_back(0);
+    const int nbn = (int)(((long long)B * d.N + 127) / 128);
+    const int Bpad = s->capB;
+    int it = 1, nact = B, total_it = 0;
+    for (; it <= d.iter_max; it++) {
+        if (h->model_id == SCPB_MODEL_STARSHIP && d.ns > 0)
+            k_linearize<Constr<SCPB_MODEL_STARSHIP>><<<nbn, 128, 0, st>>>(pd, s->xd, s->ud, s->p);
+        else
+            k_linearize<Constr<0>><<<nbn, 128, 0, st>>>(pd, s->xd, s->ud, s->p);
+        const long long tot = (long long)d.nval * Bpad;
+        k_assemble<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ad);
+        h->launches += 2;
+        mark(); phase.push_back(1);
+        if ((rc = scpb_internal_cone_run(s->cone, o))) return rc;
+        mark(); phase.push_back(2);
+        sd.iter = it;
+        k_extract<<<nbn, 128, 0, st>>>(sd);
+        h->launches++;
+        mark(); phase.push_back(3);
+        if ((rc = run_discretize(s, B, G, s->xn, s->un, s->pn))) return rc;
+        mark(); phase.push_back(0);
+        SCPB_CUDA(h, cudaMemsetAsync(s->nactive, 0, sizeof(int), st));
+        k_ptr_step<<<(B + 127) / 128, 128, 0, st>>>(sd);
+        h->launches++;
+        SCPB_CUDA(h, cudaMemcpyAsync(&nact, s->nactive, sizeof(int), cudaMemcpyDeviceToHost, st));
+        mark(); phase.push_back(3);
+        SCPB_CUDA(h, cudaStreamSynchronize(st));
+        total_it++;
+        if (nact == 0) break;
+    }
+    SCPB_CUDA(h, cudaGetLastError());
+    if (xd) SCPB_CUDA(h, cudaMemcpyAsync(xd, s->xd, sizeof(double) * nX, cudaMemcpyDeviceToHost, st));
+    if (ud) SCPB_CUDA(h, cudaMemcpyAsync(ud, s->ud, sizeof(double) * nU, cudaMemcpyDeviceToHost, st));
+    if (p) SCPB_CUDA(h, cudaMemcpyAsync(p, s->p, sizeof(double) * nP, cudaMemcpyDeviceToHost, st));
+    if (status) SCPB_CUDA(h, cudaMemcpyAsync(status, s->status, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    if (iters) SCPB_CUDA(h, cudaMemcpyAsync(iters, s->iters, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    if (J) SCPB_CUDA(h, cudaMemcpyAsync(J, s->J_ref, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+    if (deviation) SCPB_CUDA(h, cudaMemcpyAsync(deviation, s->devi, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+    if (feas) SCPB_CUDA(h, cudaMemcpyAsync(feas, s->feas, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    SCPB_CUDA(h, cudaStreamSynchronize(st));
+    double acc[4] = {0, 0, 0, 0};
+    for (size_t i = 1; i < ev.size(); i++) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+        if (phase[i] >= 0) acc[phase[i]] += ms * 1e-3;
+    }
+    float tot_ms = 0.f;
+    cudaEventElapsedTime(&tot_ms, ev.front(), ev.back());
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    if (timing) {
+        timing[0] = acc[0]; timing[1] = acc[1]; timing[2] = acc[2]; timing[3] = acc[3];
+        timing[4] = tot_ms * 1e-3; timing[5] = (double)total_it; timing[6] = 0.0; timing[7] = 0.0;
+    }
+    return SCPB_OK;
+}
+
+}  // extern "C"

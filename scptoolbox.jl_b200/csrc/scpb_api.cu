@@ -54,13 +54,14 @@ static void julia_views(DiscArgs &a, int nx, int nu, int np, double *A, double *
                         double *r, double *E, double *defect)
 {
     const long long M = a.N - 1;
-    a.A = {A, M * nx * nx, (long long)nx * nx, 1};
-    a.Bm = {Bm, M * nx * nu, (long long)nx * nu, 1};
-    a.Bp = {Bp, M * nx * nu, (long long)nx * nu, 1};
-    a.F = {F, M * nx * np, (long long)nx * np, 1};
-    a.r = {r, M * nx, (long long)nx, 1};
-    a.E = {E, M * nx * nx, (long long)nx * nx, 1};
-    a.defect = {defect, M * nx, (long long)nx, 1};
+    auto jl = [&](double *ptr, long long sz) { OutView v{}; v.ptr = ptr; v.sB = 0; v.sK = sz; v.sE = 1; v.sGrp = M * sz; v.Gq = 1; return v; };
+    a.A = jl(A, (long long)nx * nx);
+    a.Bm = jl(Bm, (long long)nx * nu);
+    a.Bp = jl(Bp, (long long)nx * nu);
+    a.F = jl(F, (long long)nx * np);
+    a.r = jl(r, nx);
+    a.E = jl(E, (long long)nx * nx);
+    a.defect = jl(defect, nx);
     a.f_packed = 0;
     a.xsB = (long long)a.N * nx; a.xsK = nx; a.xsE = 1;
     a.usB = (long long)a.N * nu; a.usK = nu; a.usE = 1;

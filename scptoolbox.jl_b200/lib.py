@@ -45,6 +45,10 @@ SIGNATURES = {
     "scpb_cone_free": (C.c_int32, [C.c_void_p]),
     "scpb_cone_solve": (C.c_int32, [C.c_void_p, C.c_int32, _dp, _dp, _dp, _dp, _dp, C.c_void_p,
                                     _dp, _dp, _dp, _dp, _dp, _dp, _ip, _ip, _dp]),
+    "scpb_ptr_setup": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, _ip, _ip, _dp, _dp, _dp, C.POINTER(C.c_void_p)]),
+    "scpb_ptr_free": (C.c_int32, [C.c_void_p]),
+    "scpb_ptr_solve": (C.c_int32, [C.c_void_p, C.c_int32, _dp, _dp, _dp, C.c_void_p, _dp, _dp, _dp, _ip, _ip,
+                                   _dp, _dp, _ip, _dp]),
     "scpb_debug_kkt_solve": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _ip, _ip, _ip, _ip, C.c_int32, C.c_int32,
                                          _ip, _ip, _dp, _dp, _dp, C.c_double, C.c_double, _dp, _dp, C.POINTER(C.c_int64)]),
 }
@@ -54,6 +58,13 @@ class ConeOpts(C.Structure):
     _fields_ = [("feastol", C.c_double), ("abstol", C.c_double), ("reltol", C.c_double),
                 ("delta", C.c_double), ("delta_dyn", C.c_double), ("maxit", C.c_int32), ("nref", C.c_int32),
                 ("verbose", C.c_int32), ("group", C.c_int32), ("equil", C.c_int32)]
+
+
+class PtrDesc(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in
+                ("N", "Nsub", "nx", "nu", "np", "ns", "nf", "nsrc", "oA", "oBm", "oBp", "oF", "or_", "oE", "oC", "oD",
+                 "oG", "ors", "oxh", "ouh", "oph", "nval", "vx", "vu", "vp", "q_exit", "iter_max")] + \
+               [(k, C.c_double) for k in ("eps_abs", "eps_rel", "feas_tol")]
 
 
 CONE_STATUS = {0: "OPTIMAL", 1: "ITERATION_LIMIT", 2: "NUMERICAL_ERROR", 3: "ALMOST_OPTIMAL"}

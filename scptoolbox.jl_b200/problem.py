@@ -1,0 +1,93 @@
+"""TrajectoryProblem -- host-side mirror of src/parser/problem.jl (struct :64-121, setters :241-659).
+
+The reference stores Julia closures for the dynamics and constraints; a GPU kernel cannot call them, so
+here the *dynamics* (f, A, B, F) and the *nonconvex constraints* (s, C, D, G) are selected as device
+packs (csrc/models.cuh, csrc/constraints.cuh) by `problem_set_dynamics!` / `problem_set_s!`, while
+everything that only shapes the cone program -- convex sets X / U, boundary conditions, cost, scaling
+advice, the initial guess -- keeps the reference's closure style and is evaluated once, symbolically,
+when the subproblem template is built (parser.py).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+class TrajectoryProblem:
+    def __init__(self, mdl=None):
+        self.mdl = mdl
+        self.nx = self.nu = self.np = 0
+        self.xrg, self.urg, self.prg = [], [], []
+        self.model_id = 0
+        self.model_par = None
+        self.fcols = [0]
+        self.guess = None
+        self.phi = None          # terminal cost  phi(x_expr, p_expr, pbm) -> Expr     (problem.jl:365-368)
+        self.Gamma = None        # running cost   Gamma(t,k,x,u,p,pbm) -> Expr          (problem.jl:392-394)
+        self.X = None            # X(t,k,x,p,pbm,ocp): emits cone rows into ocp        (problem.jl:487-523)
+        self.U = None            # U(t,k,u,p,pbm,ocp)                                  (problem.jl:534-543)
+        self.ns = 0
+        self.s_struct = None     # (Cmask, Dmask, Gmask) structural non-zeros of the constraint pack
+        self.gic = None          # affine boundary conditions g(x_expr, p_expr, pbm) -> list[Expr]
+        self.gtc = None
+        self.scp = None
+
+
+def problem_set_dims(pbm, nx, nu, np_):
+    """problem_set_dims! (problem.jl:241-249)"""
+    pbm.nx, pbm.nu, pbm.np = nx, nu, np_
+    pbm.xrg = [None] * nx
+    pbm.urg = [None] * nu
+    pbm.prg = [None] * np_
+
+
+def problem_advise_scale(pbm, which, idx, rg):
+    """problem_advise_scale! (problem.jl:262-282)"""
+    if rg[1] < rg[0]:
+        raise ValueError("min must be less than max")
+    tgt = {"state": pbm.xrg, "input": pbm.urg, "parameter": pbm.prg}[which]
+    for i in (idx if hasattr(idx, "__iter__") else [idx]):
+        tgt[i] = (float(rg[0]), float(rg[1]))
+
+
+def problem_set_guess(pbm, guess):
+    """problem_set_guess! (problem.jl:316-319)"""
+    pbm.guess = lambda N: guess(N, pbm)
+
+
+def problem_set_terminal_cost(pbm, phi):
+    pbm.phi = lambda x, p: phi(x, p, pbm)
+
+
+def problem_set_running_cost(pbm, Gamma):
+    pbm.Gamma = lambda t, k, x, u, p: Gamma(t, k, x, u, p, pbm)
+
+
+def problem_set_dynamics(pbm, model_id, par, fcols=(0,)):
+    """problem_set_dynamics! (problem.jl:425-450): selects the device pack that evaluates f, A, B, F.
+    fcols: parameter index of each active (time-dilation) column of F."""
+    pbm.model_id = int(model_id)
+    pbm.model_par = np.asarray(par, dtype=np.float64)
+    pbm.fcols = list(fcols)
+
+
+def problem_set_X(pbm, X):
+    pbm.X = lambda ocp, t, k, x, p: X(t, k, x, p, pbm, ocp)
+
+
+def problem_set_U(pbm, U):
+    pbm.U = lambda ocp, t, k, u, p: U(t, k, u, p, pbm, ocp)
+
+
+def problem_set_s(pbm, ns, Cmask, Dmask, Gmask):
+    """problem_set_s! (problem.jl:560-587): the constraint pack of the selected model evaluates s, C, D, G on the
+    device; the masks give their structural non-zeros (row-major ns x nx / nu / np)."""
+    pbm.ns = int(ns)
+    pbm.s_struct = (np.asarray(Cmask, bool), np.asarray(Dmask, bool), np.asarray(Gmask, bool))
+
+
+def problem_set_bc(pbm, kind, g):
+    """problem_set_bc! (problem.jl:600-627) for affine boundary conditions g(x, p) = 0."""
+    if kind == "ic":
+        pbm.gic = lambda x, p: g(x, p, pbm)
+    else:
+        pbm.gtc = lambda x, p: g(x, p, pbm)

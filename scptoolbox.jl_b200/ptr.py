@@ -1,0 +1,328 @@
+"""PTR -- host-side mirror of src/solvers/ptr.jl for the B200 path.
+
+  Parameters           ptr.jl:57-71
+  create(pars, traj)   ptr.jl:148-195 + SCPProblem / compute_scaling (scp.jl:140-157, 376-517)
+  solve(pbm, guesses)  ptr.jl:448-532, for a BATCH of initial guesses in lock step on the GPU
+
+`create` builds the subproblem once, symbolically (Subproblem ctor ptr.jl:213-293, add_dynamics! scp.jl:657-674,
+add_convex_*! :685-734, add_nonconvex_constraints! :744-794, add_bcs! :808-895, add_trust_region! ptr.jl:565-743,
+add_cost! :753-895) with device-computed quantities as symbolic sources, compiles it to the shared sparsity
+pattern + fill matrix W, orders the KKT system stage-wise and hands everything to libscpb.  `solve` is one C-ABI
+call (scpb_ptr_solve) that runs discretize! -> formulate -> solve -> discretize! -> stopping test on the device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import lib, ordering
+from .parser import ConicTemplate, Expr, Lin, matvec
+
+FOH = lib.FOH
+
+
+@dataclass
+class Parameters:            # ptr.jl:57-71
+    N: int
+    Nsub: int
+    iter_max: int
+    disc_method: int
+    wvc: float
+    wtr: float
+    eps_abs: float
+    eps_rel: float
+    feas_tol: float
+    q_tr: float
+    q_exit: float
+    solver: object = None            # kept for signature compatibility (the solver is libscpb)
+    solver_opts: dict = None         # {"verbose":.., "maxit":..} as in the reference tests
+
+
+class SCPScaling:            # scp.jl:39-49, 483-516 (user-advised ranges)
+    def __init__(self, traj):
+        zero_tol = np.sqrt(np.finfo(float).eps)
+
+        def mk(rg, what):
+            if any(r is None for r in rg):
+                raise lib.ScpbError(f"advise a range for every {what} (automatic bounding-box solves are not implemented)")
+            lo = np.array([r[0] for r in rg], dtype=float)
+            hi = np.array([r[1] for r in rg], dtype=float)
+            S = hi - lo
+            S[S < zero_tol] = 1.0
+            return S, lo.copy()
+
+        self.Sx, self.cx = mk(traj.xrg, "state")
+        self.Su, self.cu = mk(traj.urg, "input")
+        self.Sp, self.cp = mk(traj.prg, "parameter")
+
+
+def t_grid(N):
+    """RealVector(LinRange(0, 1, N)) with Julia's lerpi arithmetic (scp.jl:147)."""
+    j = np.arange(N, dtype=np.float64) / float(N - 1)
+    return (1.0 - j) * 0.0 + j * 1.0
+
+
+def trapz(f, grid):          # helper.jl:560-568
+    F = Expr()
+    for k in range(len(grid) - 1):
+        d = grid[k + 1] - grid[k]
+        F = F + (f[k + 1] + f[k]) * (0.5 * d)
+    return F
+
+
+class SourceMap:
+    """Layout of the per-seed source vector (see include/scpb.h, scpb_ptr_desc)."""
+
+    def __init__(self, N, nx, nu, np_, ns, nf):
+        M = N - 1
+        o = 1
+        self.oA = o; o += M * nx * nx
+        self.oBm = o; o += M * nx * nu
+        self.oBp = o; o += M * nx * nu
+        self.oF = o; o += M * nx * nf
+        self.or_ = o; o += M * nx
+        self.oE = o; o += M * nx * nx
+        self.oC = o; o += N * ns * nx
+        self.oD = o; o += N * ns * nu
+        self.oG = o; o += N * ns * np_
+        self.ors = o; o += N * ns
+        self.oxh = o; o += N * nx
+        self.ouh = o; o += N * nu
+        self.oph = o; o += np_
+        self.nsrc = o
+        self.N, self.nx, self.nu, self.np, self.ns, self.nf = N, nx, nu, np_, ns, nf
+
+    def mat(self, off, k, rows, cols, colmajor=True, mask=None):
+        blk = rows * cols
+        M = [[None] * cols for _ in range(rows)]
+        for i in range(rows):
+            for j in range(cols):
+                if mask is not None and not mask[i, j]:
+                    continue
+                e = (i + rows * j) if colmajor else (i * cols + j)
+                M[i][j] = Lin.src(off + k * blk + e)
+        return M
+
+    def vec(self, off, k, n):
+        return [Lin.src(off + k * n + i) for i in range(n)]
+
+
+class SCPProblem:
+    """pbm returned by create(): template, device objects, scaling."""
+
+    def __init__(self, pars, traj, handle):
+        self.pars, self.traj, self.handle = pars, traj, handle
+        self.scale = SCPScaling(traj)
+        self.t = t_grid(pars.N)
+        traj.scp = pars
+        if pars.disc_method != FOH:
+            raise lib.ScpbError("only FOH discretization is implemented on the device")
+        self._build()
+
+    # ------------------------------------------------------------------ template (ptr.jl:213-293, 565-895)
+    def _build(self):
+        pars, traj, sc, t = self.pars, self.traj, self.scale, self.t
+        N, nx, nu, np_ = pars.N, traj.nx, traj.nu, traj.np
+        ns, nf = traj.ns, len(traj.fcols)
+        sm = SourceMap(N, nx, nu, np_, ns, nf)
+        self.sm = sm
+        prg = ConicTemplate(sm.nsrc)
+        x = prg.new_variable((nx, N), "x", sc.Sx, sc.cx, stage="col")
+        u = prg.new_variable((nu, N), "u", sc.Su, sc.cu, stage="col")
+        p = prg.new_variable(np_, "p", sc.Sp, sc.cp, stage=None)
+        vd = prg.new_variable((nx, N - 1), "vd", stage="col")
+        eta_x = prg.new_variable(N, "eta_x", stage="idx")
+        eta_u = prg.new_variable(N, "eta_u", stage="idx")
+        eta_p = prg.new_variable(1, "eta_p", stage=None)
+        # add_dynamics! / state_update! (discretization.jl:424-497)
+        for k in range(N - 1):
+            A = sm.mat(sm.oA, k, nx, nx)
+            Bm = sm.mat(sm.oBm, k, nx, nu)
+            Bp = sm.mat(sm.oBp, k, nx, nu)
+            E = sm.mat(sm.oE, k, nx, nx)
+            r = sm.vec(sm.or_, k, nx)
+            Fp = sm.mat(sm.oF, k, nx, nf)
+            rhs = [a + b + c + d for a, b, c, d in zip(matvec(A, x[:, k]), matvec(Bm, u[:, k]),
+                                                       matvec(Bp, u[:, k + 1]), matvec(E, vd[:, k]))]
+            Fpv = matvec(Fp, [p[j] for j in traj.fcols])
+            prg.zero([x[i, k + 1] - (rhs[i] + Fpv[i] + Expr(None, r[i])) for i in range(nx)], "dynamics")
+        # convex state / input constraints (scp.jl:685-734)
+        if traj.X is not None:
+            for k in range(N):
+                traj.X(prg, t[k], k + 1, x[:, k], p)
+        if traj.U is not None:
+            for k in range(N):
+                traj.U(prg, t[k], k + 1, u[:, k], p)
+        # nonconvex constraints (scp.jl:744-794)
+        vs = None
+        if ns:
+            Cm, Dm, Gm = traj.s_struct
+            vs = prg.new_variable((ns, N), "vs", stage="col")
+            for k in range(N):
+                Cs = sm.mat(sm.oC, k, ns, nx, colmajor=False, mask=Cm)
+                Ds = sm.mat(sm.oD, k, ns, nu, colmajor=False, mask=Dm)
+                Gs = sm.mat(sm.oG, k, ns, np_, colmajor=False, mask=Gm)
+                rs = sm.vec(sm.ors, k, ns)
+                lhs = [a + b + c for a, b, c in zip(matvec(Cs, x[:, k]), matvec(Ds, u[:, k]), matvec(Gs, p))]
+                prg.nonpos([lhs[i] + Expr(None, rs[i]) - vs[i, k] for i in range(ns)], "path_ncvx")
+        # boundary conditions, relaxed (scp.jl:808-895); affine g => exact linearisation
+        vic = vtc = None
+        if traj.gic is not None:
+            g = traj.gic(x[:, 0], p)
+            vic = prg.new_variable(len(g), "vic", stage=0)
+            prg.zero([g[i] + vic[i] for i in range(len(g))], "initial_condition")
+        if traj.gtc is not None:
+            g = traj.gtc(x[:, N - 1], p)
+            vtc = prg.new_variable(len(g), "vtc", stage=N - 1)
+            prg.zero([g[i] + vtc[i] for i in range(len(g))], "terminal_condition")
+        # trust region (ptr.jl:565-743)
+        q = pars.q_tr
+        cone = {1: prg.l1, 2: prg.soc, np.inf: prg.linf}[q]
+        dp_lq = prg.new_variable(1, "dp_lq", stage=None)
+        ph_ref = sm.vec(sm.oph, 0, np_)
+        cone([dp_lq[0]] + [(p[i] - sc.cp[i]) * (1.0 / sc.Sp[i]) - Expr(None, ph_ref[i]) for i in range(np_)],
+             "parameter_trust_region")
+        prg.nonpos([dp_lq[0] - eta_p[0]])
+        dx_lq = prg.new_variable(N, "dx_lq", stage="idx")
+        for k in range(N):
+            xr = sm.vec(sm.oxh, k, nx)
+            cone([dx_lq[k]] + [(x[i, k] - sc.cx[i]) * (1.0 / sc.Sx[i]) - Expr(None, xr[i]) for i in range(nx)],
+                 "state_trust_region")
+            prg.nonpos([dx_lq[k] - eta_x[k]])
+        du_lq = prg.new_variable(N, "du_lq", stage="idx")
+        for k in range(N):
+            ur = sm.vec(sm.ouh, k, nu)
+            cone([du_lq[k]] + [(u[i, k] - sc.cu[i]) * (1.0 / sc.Su[i]) - Expr(None, ur[i]) for i in range(nu)],
+                 "input_trust_region")
+            prg.nonpos([du_lq[k] - eta_u[k]])
+        # cost (ptr.jl:753-895, scp.jl:552-601)
+        J = Expr()
+        if traj.phi is not None:
+            J = J + traj.phi(x[:, N - 1], p)
+        if traj.Gamma is not None:
+            J = J + trapz([traj.Gamma(t[k], k + 1, x[:, k], u[:, k], p) for k in range(N)], t)
+        prg.add_cost(J)
+        prg.add_cost((trapz(list(eta_x), t) + trapz(list(eta_u), t) + eta_p[0]) * pars.wtr)
+        P = prg.new_variable(N, "P", stage="idx")
+        Pf = prg.new_variable(2, "Pf", stage=None)
+        for k in range(N):
+            if k < N - 1:
+                E = sm.mat(sm.oE, k, nx, nx)
+                Ev = matvec(E, vd[:, k])
+                prg.l1([P[k]] + list(Ev) + (list(vs[:, k]) if vs is not None else []), "vd_vs_penalty", stage=k)
+            elif vs is not None:
+                prg.l1([P[k]] + list(vs[:, k]), "vd_vs_penalty", stage=k)
+            else:
+                prg.zero([P[k]])
+        if vic is not None:
+            prg.l1([Pf[0]] + list(vic), "vic_penalty", stage=0)
+        else:
+            prg.zero([Pf[0]])
+        if vtc is not None:
+            prg.l1([Pf[1]] + list(vtc), "vtc_penalty", stage=N - 1)
+        else:
+            prg.zero([Pf[1]])
+        prg.add_cost((trapz(list(P), t) + Pf[0] + Pf[1]) * pars.wvc)
+        self.template = prg
+        self.cp = cp = prg.compile()
+        # one extra W row for the cost constant c0
+        import scipy.sparse as sp
+        c0 = cp["cost_const"]
+        row = sp.csr_matrix((list(c0.t.values()), ([0] * len(c0.t), list(c0.t.keys()))), shape=(1, sm.nsrc))
+        self.W = sp.vstack([cp["W"], row]).tocsr()
+        self.W.sort_indices()
+        self.nval = self.W.shape[0]
+        # ---- device objects ----
+        h = self.handle
+        h.model_set(traj.model_id, traj.model_par, nx, nu, np_)
+        self.perm = ordering.stage_order(cp["A"], cp["G"], cp["var_stage"], N)
+        self.cone = lib.ConeProblem(h, cp["A"], cp["G"], cp["l"], cp["soc_dims"], perm=self.perm)
+        d = lib.PtrDesc()
+        d.N, d.Nsub, d.nx, d.nu, d.np, d.ns, d.nf = N, pars.Nsub, nx, nu, np_, ns, nf
+        for k_ in ("nsrc", "oA", "oBm", "oBp", "oF", "or_", "oE", "oC", "oD", "oG", "ors", "oxh", "ouh", "oph"):
+            setattr(d, k_, getattr(sm, k_))
+        d.nval = self.nval
+        d.vx, d.vu, d.vp = prg.blocks["x"][0], prg.blocks["u"][0], prg.blocks["p"][0]
+        d.q_exit = {np.inf: 0, 1: 1, 2: 2}[pars.q_exit]
+        d.iter_max = pars.iter_max
+        d.eps_abs, d.eps_rel, d.feas_tol = pars.eps_abs, pars.eps_rel, pars.feas_tol
+        self.desc = d
+        scale = np.concatenate([sc.Sx, sc.Su, sc.Sp, sc.cx, sc.cu, sc.cp, 1.0 / sc.Sx])
+        self._keep = [np.ascontiguousarray(self.W.indptr, dtype=np.int32),
+                      np.ascontiguousarray(self.W.indices, dtype=np.int32),
+                      np.ascontiguousarray(self.W.data, dtype=np.float64),
+                      np.ascontiguousarray(scale, dtype=np.float64), np.ascontiguousarray(self.t)]
+        ptr = C.c_void_p()
+        k = self._keep
+        rc = h.lib.scpb_ptr_setup(h.h, self.cone.c, C.cast(C.byref(d), C.c_void_p), k[0].ctypes.data_as(lib._ip),
+                                  k[1].ctypes.data_as(lib._ip), k[2].ctypes.data_as(lib._dp),
+                                  k[3].ctypes.data_as(lib._dp), k[4].ctypes.data_as(lib._dp), C.byref(ptr))
+        h._check(rc, "scpb_ptr_setup")
+        self.ptr = ptr
+
+    def close(self):
+        if getattr(self, "ptr", None) is not None and self.ptr.value:
+            self.handle.lib.scpb_ptr_free(self.ptr)
+            self.ptr = C.c_void_p()
+        if getattr(self, "cone", None) is not None:
+            self.cone.close()
+
+
+@dataclass
+class SCPBatchSolution:      # batched SCPSolution (scp.jl:105-119)
+    status: list
+    iterations: np.ndarray
+    cost: np.ndarray
+    td: np.ndarray
+    xd: np.ndarray
+    ud: np.ndarray
+    p: np.ndarray
+    deviation: np.ndarray
+    feas: np.ndarray
+    timing: dict
+    raw_status: np.ndarray
+
+
+def create(pars: Parameters, traj, handle) -> SCPProblem:
+    """PTR.create (ptr.jl:148-195)."""
+    return SCPProblem(pars, traj, handle)
+
+
+def solve(pbm: SCPProblem, guesses=None, **cone_opts) -> SCPBatchSolution:
+    """PTR.solve (ptr.jl:448-532) for a batch: guesses = (xd0 (B,N,nx), ud0 (B,N,nu), p0 (B,np));
+    None => the problem's own guess (one seed)."""
+    traj, pars, h = pbm.traj, pbm.pars, pbm.handle
+    if guesses is None:
+        x0, u0, p0 = traj.guess(pars.N)
+        guesses = (x0[None], u0[None], p0[None])
+    xd0 = np.ascontiguousarray(guesses[0], dtype=np.float64)
+    ud0 = np.ascontiguousarray(guesses[1], dtype=np.float64)
+    p0 = np.ascontiguousarray(guesses[2], dtype=np.float64)
+    B, N = xd0.shape[0], pars.N
+    assert xd0.shape == (B, N, traj.nx) and ud0.shape == (B, N, traj.nu) and p0.shape == (B, traj.np)
+    o = lib.ConeOpts()
+    o.nref = -1
+    o.equil = -1
+    if pars.solver_opts and "maxit" in pars.solver_opts:
+        o.maxit = int(pars.solver_opts["maxit"])
+    for k_, v in cone_opts.items():
+        setattr(o, k_, v)
+    xd, ud, p = np.empty_like(xd0), np.empty_like(ud0), np.empty_like(p0)
+    status = np.zeros(B, dtype=np.int32); iters = np.zeros(B, dtype=np.int32); feas = np.zeros(B, dtype=np.int32)
+    J = np.empty(B); dev = np.empty(B); timing = np.zeros(8)
+    dp = lambda a: a.ctypes.data_as(lib._dp)
+    ip = lambda a: a.ctypes.data_as(lib._ip)
+    rc = h.lib.scpb_ptr_solve(pbm.ptr, B, dp(xd0), dp(ud0), dp(p0), C.cast(C.byref(o), C.c_void_p), dp(xd), dp(ud),
+                              dp(p), ip(status), ip(iters), dp(J), dp(dev), ip(feas), dp(timing))
+    h._check(rc, "scpb_ptr_solve")
+    names = []
+    for s_ in status:
+        if s_ in (0, 1):
+            names.append("SCP_SOLVED")     # scp.jl:221-222: anything but an unsafe solver status is reported solved
+        else:
+            names.append(f"SCP_FAILED ({lib.CONE_STATUS.get((int(s_) - 2) // 16, '?')})")
+    tm = dict(discretize=timing[0], formulate=timing[1], solve=timing[2], overhead=timing[3], total=timing[4],
+              lockstep_iterations=int(timing[5]))
+    return SCPBatchSolution(names, iters, J, pbm.t, xd, ud, p, dev, feas, tm, status)
