@@ -252,7 +252,7 @@ def starship_initial_guess(N, pbm, handle):
     one = np.ones(1)
     vals = np.array([cp["W"] @ one for _, cp in progs])
     from .. import ordering
-    perm = ordering.stage_order(cp0["A"], cp0["G"], cp0["var_stage"], N2, soc_dims=cp0["soc_dims"], l=cp0["l"])
+    perm = ordering.stage_order(cp0["A"], cp0["G"], cp0["var_stage"], N2)
     cone = lib.ConeProblem(handle, cp0["A"], cp0["G"], cp0["l"], cp0["soc_dims"], perm=perm)
     nA, nG, n, p_, m = cp0["nnzA"], cp0["nnzG"], cp0["n"], cp0["p"], cp0["m"]
     out = cone.solve(vals[:, :nA], vals[:, nA:nA + nG], vals[:, cp0["off_c"]:cp0["off_c"] + n],
