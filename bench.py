@@ -1,11 +1,15 @@
 #!/usr/bin/env python
-"""bench.py -- SCP hot-path benchmark (contract in the task statement).
+"""bench.py -- SCP hot-path benchmark (contract in the task statement / DESIGN.md section 6).
 
   python bench.py --gpus N --steps K --warmup W            our arm  (CUDA path through the C ABI)
-  python bench.py --impl reference --gpus N --steps K ...   reference arm (CPU oracle port)
+  python bench.py --impl reference --gpus N --steps K ...   reference arm (CPU oracle port, all host threads)
 
-One "step" = one pass of the hot path over one batch of synthetic seeds.  Seeds are independent, so
-N GPUs shard the batch with a fixed per-GPU batch ("scaling": "weak"), no data-path collective.
+Workload (config.workload): BASELINE.json's north-star case -- starship_flip PTR, N=100 nodes, Nsub=100,
+256 randomly perturbed initial guesses ("seeds") per GPU, fp64.  One "step" = one complete batched PTR solve
+of those seeds (discretize! + formulate + conic solve + discretize! + stopping test, in lock step until every
+seed stops); the metric is SCP iterations per second = sum over seeds of PTR iterations / time.
+Seeds are independent, so N GPUs each take their own 256 seeds ("scaling": "weak"); the only collective
+is the final NCCL all_gather of the per-seed results.
 """
 from __future__ import annotations
 
@@ -23,39 +27,37 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+METRIC = "SCP iterations/sec (batch)"
+UNIT = "SCP iterations/s"
 
-# ----------------------------------------------------------------------------------------------
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="seeds per GPU")
-    ap.add_argument("--workload", default="starship_discretize")
-    ap.add_argument("--cpu-seeds", type=int, default=0, help="seeds in the CPU sample (0 = auto)")
+    ap.add_argument("--N", type=int, default=100)
+    ap.add_argument("--Nsub", type=int, default=100)
+    ap.add_argument("--cpu-seeds", type=int, default=0, help="seeds in the CPU sample (0 = one per host thread)")
     return ap.parse_args()
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
-
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.index = index
-        self.rows = []
-        self.proc = None
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
-            self.th.start()
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
@@ -66,12 +68,8 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.25)
         self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
@@ -89,111 +87,91 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def measured_peaks():
+def measured_peak():
     try:
-        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        return float(pk["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+# PTR constants of the reference test (starship_flip/tests.jl:33-47)
+PTR = dict(iter_max=15, wvc=1e3, wtr=0.1, eps_abs=1e-5, eps_rel=0.01 / 100, feas_tol=5e-3)
+
+
+def make_seeds(base, Sx, Su, nb, seed):
+    """Synthetic seeds: the nominal guess plus N(0, 0.01*range) perturbations of states and inputs
+    and +-2 % of the parameters; seed 0 of rank 0 is the unperturbed nominal guess."""
+    rng = np.random.default_rng(seed)
+    x, u, p = base
+    X = np.array([x + (0.01 * Sx * rng.standard_normal(x.shape) if (b or seed) else 0.0) for b in range(nb)])
+    U = np.array([u + (0.01 * Su * rng.standard_normal(u.shape) if (b or seed) else 0.0) for b in range(nb)])
+    P = np.array([p * (1 + (0.02 * rng.uniform(-1, 1, p.shape) if (b or seed) else 0.0)) for b in range(nb)])
+    return X, U, P
+
+
 # ----------------------------------------------------------------------------------------------
-class StarshipDiscretize:
-    """C3-sized discretize!: starship N=100, Nsub=100, `batch` seeds per GPU."""
-
-    N, Nsub = 100, 100
-    name = "starship_flip discretize! N=100 Nsub=100 (first slice of the SCP iteration)"
-
-    def __init__(self, batch: int, rank: int):
-        from oracle import problems  # synthetic-input generator shared with the tests (not compute)
-        self.pb = problems.make_problem("starship", self.N)
-        self.B = batch
-        self.xd, self.ud, self.p = problems.test_trajectory(self.pb, batch, self.N, seed=100 + rank)
-        self.iS = np.ones(self.pb.nx)
-        j = np.arange(self.N) / (self.N - 1)
-        self.tg = (1.0 - j) * 0.0 + j * 1.0
-        nx, nu, np_ = self.pb.nx, self.pb.nu, self.pb.np
-        M = self.N - 1
-        # algorithmic work / bytes per seed (SURVEY 8d)
-        V = nx * (2 + 2 * nx + 2 * nu + np_)
-        self.flops_per_seed = M * (self.Nsub - 1) * 4 * (2 * nx ** 3 + (8 / 3) * nx ** 3 +
-                                                        2 * nx * nx * (2 * nu + np_ + 1 + nx) +
-                                                        2 * nx * (nx + nu + np_) + 8 * V)
-        self.bytes_per_seed = 8 * (self.N * (nx + nu) + np_) + 8 * M * (2 * nx * nx + 2 * nx * nu + nx * np_ + 2 * nx)
-        self.units_per_step = batch  # one discretize! call per seed
-
-    # ---- our arm ----
-    def setup_gpu(self, pkg, device):
-        import torch
-        self.torch = torch
-        self.h = pkg.Handle(device)
-        self.h.model_set(self.pb.model_id, self.pb.par(), self.pb.nx, self.pb.nu, self.pb.np)
-        dev = torch.device("cuda", device)
-        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-        self.d = dict(tg=t(self.tg), xd=t(self.xd), ud=t(self.ud), p=t(self.p), iS=t(self.iS))
-        nx, nu, np_, M, B = self.pb.nx, self.pb.nu, self.pb.np, self.N - 1, self.B
-        z = lambda *s: torch.zeros(*s, dtype=torch.float64, device=dev)
-        self.o = dict(A=z(B, M, nx * nx), Bm=z(B, M, nx * nu), Bp=z(B, M, nx * nu), F=z(B, M, nx * np_),
-                      r=z(B, M, nx), E=z(B, M, nx * nx), defect=z(B, M, nx),
-                      feas=torch.zeros(B, dtype=torch.int32, device=dev))
-        self.stream = torch.cuda.ExternalStream(self.h.stream, device=dev)
-        # pinned host staging for the e2e leg
-        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        self.hp = dict(xd=pin(self.xd), ud=pin(self.ud), p=pin(self.p))
-        self.h2d = sum(v.numel() * 8 for v in self.hp.values()) + (self.N + nx) * 8
-        self.d2h = sum(v.numel() * v.element_size() for v in self.o.values())
-        self.l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-
-    def flush_l2(self):
-        with self.torch.cuda.stream(self.stream):
-            self.l2_flush.zero_()
-
-    def step_resident(self):
-        d, o = self.d, self.o
-        self.h.discretize_dev(d["tg"].data_ptr(), d["xd"].data_ptr(), d["ud"].data_ptr(), d["p"].data_ptr(),
-                              d["iS"].data_ptr(), 5e-3, self.Nsub, o["A"].data_ptr(), o["Bm"].data_ptr(),
-                              o["Bp"].data_ptr(), o["F"].data_ptr(), o["r"].data_ptr(), o["E"].data_ptr(),
-                              o["defect"].data_ptr(), o["feas"].data_ptr(), self.B, self.N)
-
-    def step_e2e(self):
-        out = self.h.discretize(self.tg, self.hp["xd"].numpy(), self.hp["ud"].numpy(), self.hp["p"].numpy(),
-                                self.iS, 5e-3, self.Nsub)
-        return out["seconds"]
-
-    launches_per_step = 2
-
-    # ---- CPU arm (oracle port) ----
-    def cpu_step(self, nseeds, nthreads):
-        from oracle import orc
-        m = self.pb.orc_model()
-        t0 = time.perf_counter()
-        orc.discretize_batch(m, self.xd[:nseeds], self.ud[:nseeds], self.p[:nseeds], self.Nsub, self.iS, 5e-3,
-                             nthreads=nthreads)
-        return time.perf_counter() - t0
+def oracle_worker(args):
+    """One seed through the oracle PTR (C discretize + HiGHS LP); returns (iterations, phase seconds)."""
+    N, Nsub, hs, xd, ud, p = args
+    from oracle import problems, ptr as optr
+    pb = problems.StarshipProblem(N)
+    pb.hs = hs
+    pars = optr.Parameters(N=N, Nsub=Nsub, solver_tol=1e-9, **PTR)
+    P = optr.PTR(pb, pars)
+    out = P.solve((xd, ud, p))
+    tm = {"discretize": 0.0, "formulate": 0.0, "solve": 0.0}
+    for s in out["history"]:
+        for k in tm:
+            tm[k] += s.timing.get(k, 0.0)
+    return out["iterations"], tm, out["status"]
 
 
-METRIC = "discretize! calls/sec (batch)"
-UNIT = "seed-discretizations/s"
+def cpu_run(N, Nsub, hs, X, U, P, nproc):
+    import multiprocessing as mp
+    jobs = [(N, Nsub, hs, X[b], U[b], P[b]) for b in range(X.shape[0])]
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(nproc) as pool:
+        res = pool.map(oracle_worker, jobs, chunksize=1)
+    wall = time.perf_counter() - t0
+    its = sum(r[0] for r in res)
+    ph = {k: sum(r[1][k] for r in res) for k in ("discretize", "formulate", "solve")}
+    return its, wall, ph, [r[2] for r in res]
 
 
-def run_reference(args, rank, world):
-    """Reference arm: the CPU oracle port on all host threads, bounded sample per step."""
+def oracle_base_guess(N):
+    from oracle import problems
+    pb = problems.StarshipProblem(N)
+    g = pb.guess(N)
+    return pb, g
+
+
+def run_reference(args, rank):
+    """Reference arm: the CPU restatement of the reference (Julia + ECOS are not installable here) on all host
+    threads, one seed per process, on a bounded sample of the same workload."""
     if rank != 0:
         return
-    wl = StarshipDiscretize(args.batch, 0)
     cores = os.cpu_count() or 1
-    nseeds = args.cpu_seeds or min(args.batch, max(cores, 8))
-    for _ in range(max(args.warmup, 1)):
-        wl.cpu_step(min(nseeds, cores), cores)
-    ts = [wl.cpu_step(nseeds, cores) for _ in range(args.steps)]
-    tot = sum(ts)
-    val = nseeds * args.steps / tot
+    pb, g = oracle_base_guess(args.N)
+    from oracle import ptr as optr
+    sc = optr.Scaling(pb)
+    nseeds = args.cpu_seeds or min(args.batch, cores)
+    X, U, P = make_seeds(g, sc.Sx, sc.Su, nseeds, 0)
+    vals, walls = [], []
+    cpu_run(args.N, args.Nsub, pb.hs, X[:min(8, nseeds)], U[:min(8, nseeds)], P[:min(8, nseeds)], min(cores, 8))  # warm-up
+    for _ in range(args.steps):
+        its, wall, ph, st = cpu_run(args.N, args.Nsub, pb.hs, X, U, P, min(cores, nseeds))
+        vals.append(its); walls.append(wall)
+    tot = sum(walls)
+    val = sum(vals) / tot
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl.name, "batch_per_gpu": args.batch, "N": wl.N, "Nsub": wl.Nsub},
+            "config": {"workload": f"starship_flip PTR N={args.N} Nsub={args.Nsub}", "batch_per_gpu": args.batch,
+                       "ptr": PTR},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{nseeds} of {args.batch} seeds per step, OpenMP over seeds"},
+                             "sample": f"{nseeds} of {args.batch} seeds per step, one process per seed "
+                                       f"(oracle: C discretize + Python formulate + HiGHS LP)",
+                             "phase_cpu_seconds": ph},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -208,79 +186,114 @@ def run_ours(args, rank, local_rank, world):
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
-    wl = StarshipDiscretize(args.batch, rank)
-    wl.setup_gpu(pkg, local_rank)
     tc = torch.cuda
+    N, Nsub, B = args.N, args.Nsub, args.batch
+    h = pkg.Handle(local_rank)
+    ex = pkg.examples.starship
+    mdl = ex.StarshipProblem()
+    traj = pkg.problem.TrajectoryProblem(mdl)
+    ex.define_problem(traj, "ptr", handle=h)
+    pars = pkg.ptr.Parameters(N=N, Nsub=Nsub, disc_method=pkg.ptr.FOH, q_tr=np.inf, q_exit=np.inf,
+                              solver_opts={"verbose": 0, "maxit": 100}, **PTR)
+    base = traj.guess(N)                     # nominal guess (GPU SOCP batch); outside the timed region
+    pbm = pkg.ptr.create(pars, traj, h)
+    X, U, P = make_seeds(base, pbm.scale.Sx, pbm.scale.Su, B, rank)
+    info = pbm.cone.info()
 
     def barrier():
         if dist is not None:
             dist.barrier()
         tc.synchronize()
 
-    # ---- device-resident timing ----
-    for _ in range(max(args.warmup, 3)):
-        wl.flush_l2(); wl.step_resident()
+    l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        l2_flush.zero_()
+        sol = pkg.ptr.solve(pbm, (X, U, P))
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ev = [(tc.Event(enable_timing=True), tc.Event(enable_timing=True)) for _ in range(args.steps)]
-    n0 = wl.h.launches
+    n0 = h.launches
+    dev_t, wall_t, its, ipm, phases = 0.0, 0.0, 0, 0, {"discretize": 0.0, "formulate": 0.0, "solve": 0.0, "overhead": 0.0}
+    lock = 0
     barrier()
-    for i in range(args.steps):
-        wl.flush_l2()
-        with tc.stream(wl.stream):
-            ev[i][0].record(wl.stream)
-            wl.step_resident()
-            ev[i][1].record(wl.stream)
-    barrier()
-    launches = wl.h.launches - n0
-    ms = [a.elapsed_time(b) for a, b in ev]
-    t_res = torch.tensor([sum(ms) * 1e-3], dtype=torch.float64, device="cuda")
-    # ---- end-to-end timing (host buffers through the C ABI, copies inside) ----
-    for _ in range(2):
-        wl.step_e2e()
-    barrier()
-    t0 = time.perf_counter()
     for _ in range(args.steps):
-        wl.step_e2e()
-    tc.synchronize()
-    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        l2_flush.zero_(); tc.synchronize()
+        t0 = time.perf_counter()
+        sol = pkg.ptr.solve(pbm, (X, U, P))   # host buffers in, host buffers out: the reference-facing call
+        wall_t += time.perf_counter() - t0
+        dev_t += sol.timing["total"]          # CUDA events on the library's stream, H2D/D2H copies excluded
+        its += int(sol.iterations.sum())
+        ipm += sol.timing["ipm_iterations"]; lock += sol.timing["lockstep_iterations"]
+        for k in phases:
+            phases[k] += sol.timing[k]
+    barrier()
+    launches = h.launches - n0
     clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([dev_t, wall_t], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(its)], dtype=torch.float64, device="cuda")
+    solved = torch.tensor([float(sum(s == "SCP_SOLVED" for s in sol.status))], dtype=torch.float64, device="cuda")
     if dist is not None:
-        dist.all_reduce(t_res, op=dist.ReduceOp.MAX)
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    t_res, t_e2e = float(t_res.item()), float(t_e2e.item())
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
-    units = wl.units_per_step * world * args.steps
-    value = units / t_res
-    peak, peak_src = measured_peaks()
-    k_ms = float(np.mean(ms))
-    ach_gbs = wl.bytes_per_seed * wl.B / (k_ms * 1e-3) / 1e9
-    cores = os.cpu_count() or 1
-    nseeds = args.cpu_seeds or min(args.batch, max(cores, 8))
-    wl.cpu_step(min(nseeds, cores), cores)
-    t_cpu = wl.cpu_step(nseeds, cores)
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl.name, "batch_per_gpu": wl.B, "N": wl.N, "Nsub": wl.Nsub,
-                       "l2": "256 MiB buffer written between timed iterations"},
-            "gpu_launches": int(launches),
-            "e2e": {"value": units / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(wl.h2d),
-                    "d2h_bytes_per_step": int(wl.d2h)},
-            "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": peak, "unit": "GB/s", "frac": ach_gbs / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "k_discretize_foh",
-                         "kernel_ms": k_ms,
-                         "note": "K1 is fp64-FMA bound (AI~1.4 kflop/B), not HBM bound; fp64 figure below",
-                         "fp64_tflops_algorithmic": wl.flops_per_seed * wl.B / (k_ms * 1e-3) / 1e12},
-            "cpu_baseline": {"value": nseeds / t_cpu, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{nseeds} of {wl.B} seeds, one discretize! each, OpenMP over seeds"},
-            "clocks": clocks}
-    print(json.dumps(line))
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        dist.all_reduce(solved, op=dist.ReduceOp.SUM)
+        # the path's only collective: gather the converged trajectories on every rank (K7)
+        res = torch.from_numpy(np.concatenate([sol.xd.reshape(B, -1), sol.ud.reshape(B, -1), sol.p], axis=1)).cuda()
+        allres = [torch.empty_like(res) for _ in range(world)]
+        dist.all_gather(allres, res)
+    dev_t, wall_t = float(t[0]), float(t[1])
+    if rank == 0:
+        value = float(cnt[0]) / dev_t
+        e2e = float(cnt[0]) / wall_t
+        # ---- roofline of the dominant kernel (k_ipm_solve): algorithmic bytes per interior-point iteration ----
+        nnzK = pbm.cp["nnzA"] + pbm.cp["nnzG"]
+        n_, p_, m_ = pbm.cp["n"], pbm.cp["p"], pbm.cp["m"]
+        nnzL, nk = info["nnzL"], info["nk"]
+        nsolve = 2 * (1 + 2)                               # 2 directions x (1 + nref) triangular solve pairs
+        q_it = 8 * (nnzK + 3 * (nnzL + nk)                 # KKT assembly (read K, write Y) + factor (rw Y, write L)
+                    + nsolve * (2 * nnzL + 4 * nk)         # forward+backward substitutions
+                    + (2 + 2 * 2 * 2) * nnzK               # residual / refinement SpMVs (K and K')
+                    + 12 * (n_ + p_ + 2 * m_))             # vector updates
+        k_ms = 1e3 * phases["solve"] / max(lock, 1)
+        ach = q_it * ipm / max(phases["solve"], 1e-12) / 1e9
+        peak, peak_src = measured_peak()
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_ipm_ncu_summary.json")))["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ----
+        cpu = None
+        if world == 1:
+            cores = os.cpu_count() or 1
+            nseeds = args.cpu_seeds or min(B, cores)
+            from oracle import ptr as optr, problems
+            pbo = problems.StarshipProblem(N); pbo.hs = mdl.hs
+            cits, cwall, cph, _ = cpu_run(N, Nsub, mdl.hs, X[:nseeds], U[:nseeds], P[:nseeds], min(cores, nseeds))
+            cpu = {"value": cits / cwall, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{nseeds} of {B} seeds, full PTR solve each, one process per seed "
+                             f"(oracle: C discretize + Python formulate + HiGHS LP)",
+                   "phase_cpu_seconds": cph}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+                "ms_per_step": 1e3 * dev_t / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"starship_flip PTR N={N} Nsub={Nsub}", "batch_per_gpu": B, "ptr": PTR,
+                           "seeds_solved": int(solved[0]), "seeds_total": B * world,
+                           "scp_iterations_per_step": float(cnt[0]) / args.steps,
+                           "l2": "256 MiB buffer written between timed steps; per-seed working set (1.4 GB) >> L2"},
+                "gpu_launches": int(launches),
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(X.nbytes + U.nbytes + P.nbytes),
+                        "d2h_bytes_per_step": int(X.nbytes + U.nbytes + P.nbytes + B * (4 * 3 + 8 * 2))},
+                "ms_per_socp_solve": k_ms,
+                "phase_seconds_per_step": {k: v / args.steps for k, v in phases.items()},
+                "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                             "traffic": traffic, "peak_source": peak_src, "kernel": "k_ipm_solve",
+                             "kernel_ms": k_ms, "algorithmic_bytes_per_ipm_iteration_per_seed": q_it,
+                             "ipm_iterations_per_launch": ipm / max(lock, 1)},
+                "cpu_baseline": cpu, "clocks": clocks}
+        print(json.dumps(line))
+    pbm.close()
     if dist is not None:
         dist.destroy_process_group()
 
@@ -291,7 +304,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank)
     else:
         run_ours(args, rank, local_rank, world)
 

@@ -94,7 +94,7 @@ typedef struct {
     double feastol, abstol, reltol; /* <=0: ECOS defaults 1e-8                          */
     double delta, delta_dyn;        /* <=0: static 1e-9 / dynamic 1e-7 regularisation    */
     int32_t maxit;                  /* <=0: 100 ("maxit" of solver_opts)                 */
-    int32_t nref;                   /* <0: 3 iterative-refinement steps                  */
+    int32_t nref;                   /* <0: 2 iterative-refinement steps                  */
     int32_t verbose;                /* accepted, ignored ("verbose" of solver_opts)      */
     int32_t group;                  /* seeds per CTA (power of two <= 32); 0 = automatic */
     int32_t equil;                  /* Ruiz equilibration passes; <0: default 5, 0: off    */
@@ -146,7 +146,8 @@ int32_t scpb_ptr_free(scpb_ptr s);
 /* host arrays: initial guesses xd0[B][N][nx], ud0[B][N][nu], p0[B][np]; outputs the final iterates, per-seed
  * status (0 = stopping criterion met, 1 = iter_max reached [the reference still reports SCP_SOLVED],
  * 2+16*cone_status = SCP_FAILED), iteration counts, J_aug, deviation, dynamic feasibility flags and
- * timing[8] = {discretize, formulate, solve, overhead, total seconds, lock-step iterations, 0, 0}. */
+ * timing[8] = {discretize, formulate, solve, overhead, total seconds, lock-step iterations,
+ * interior-point iterations summed over seeds and subproblems, 0}. */
 int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *ud0, const double *p0,
                        const scpb_cone_opts *opts, double *xd, double *ud, double *p, int32_t *status,
                        int32_t *iters, double *J, double *deviation, int32_t *feas, double *timing);

@@ -106,7 +106,8 @@ int scpb_internal_cone_run(scpb_cone_s *c, const IpmOpts &o)
 {
     scpb_handle_s *h = c->h;
     const int ng = (c->D.B + c->D.G - 1) / c->D.G;
-    k_ipm_solve<<<ng, IPM_NT, 0, h->stream>>>(c->P, c->D, o);
+    const size_t smem = sizeof(int) * 3 * (size_t)(c->S.nlevels + 1);
+    k_ipm_solve<<<ng, IPM_NT, smem, h->stream>>>(c->P, c->D, o);
     h->launches++;
     SCPB_CUDA(h, cudaGetLastError());
     return SCPB_OK;
@@ -121,7 +122,7 @@ IpmOpts scpb_internal_make_opts(const scpb_cone_opts *o)
     r.delta = (o && o->delta > 0) ? o->delta : 1e-9;
     r.delta_dyn = (o && o->delta_dyn > 0) ? o->delta_dyn : 1e-7;
     r.maxit = (o && o->maxit > 0) ? o->maxit : 100;
-    r.nref = (o && o->nref >= 0) ? o->nref : 3;
+    r.nref = (o && o->nref >= 0) ? o->nref : 2;
     r.equil = (o && o->equil >= 0) ? o->equil : 5;
     return r;
 }
@@ -163,6 +164,9 @@ int32_t scpb_cone_setup(scpb_handle h, int32_t n, int32_t p, int32_t m, const in
     UP(ft_lvl_ptr); UP(ft_target); UP(ft_op_ptr); UP(ft_op_a); UP(ft_op_b);
     UP(sc_lvl_ptr); UP(sc_pos); UP(sc_col); UP(as_ptr); UP(as_a); UP(as_b); UP(as_c); UP(as_src); UP(as_sign);
 #undef UP
+    P.fw_item = (const int4 *)upload_ints(c, S.fw_item); P.bw_item = (const int4 *)upload_ints(c, S.bw_item);
+    P.ft_item = (const int4 *)upload_ints(c, S.ft_item);
+    P.Lr_pc = (const int2 *)upload_ints(c, S.Lr_pc); P.ft_op = (const int2 *)upload_ints(c, S.ft_op);
     for (void *d : c->dev_ints)
         if (!d) {
             scpb_cone_free(c);

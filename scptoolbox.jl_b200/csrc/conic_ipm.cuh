@@ -28,6 +28,8 @@ struct IpmProgram {  // device copies of ConeSymbolic index arrays
     const int *ft_lvl_ptr, *ft_target, *ft_op_ptr, *ft_op_a, *ft_op_b;
     const int *sc_lvl_ptr, *sc_pos, *sc_col;
     const int *as_ptr, *as_a, *as_b, *as_c, *as_src, *as_sign;
+    const int4 *fw_item, *bw_item, *ft_item;
+    const int2 *Lr_pc, *ft_op;
 };
 
 struct IpmOpts {
@@ -65,6 +67,7 @@ struct Ctx {
     // row-type work (sparse dot products): R lanes cooperate on one row for the G seeds of the group;
     // lane layout inside a warp: tid = (item*R + rr)*G + sg, reduced with xor-shuffles over rr
     int R, rr, isl, nisl;
+    const int *s_lvl, *s_ftl, *s_scl;   // level pointers staged in shared memory
     double *red;   // shared: [8][IPM_NT/32][IPM_MAXG]
     double *out;   // shared: [8][IPM_MAXG]
 };
@@ -184,29 +187,31 @@ __device__ void kkt_factor(const IpmProgram &P, const Ctx &c, double *Y, double 
 {
     const int G = c.G, sg = c.sg;
     for (int lv = 0; lv < P.nlevels; lv++) {
-        const int wend = P.ft_lvl_ptr[lv + 1];
-        for (int w0 = P.ft_lvl_ptr[lv]; w0 < wend; w0 += c.nisl) {   // uniform trip count: shuffles inside
+        const int wend = c.s_ftl[lv + 1];
+        for (int w0 = c.s_ftl[lv]; w0 < wend; w0 += c.nisl) {   // uniform trip count: shuffles inside
             const int w = w0 + c.isl;
             const bool on = w < wend;
-            int t = 0;
-            double part = 0.0;
+            int4 item = make_int4(0, 0, 0, 0);
+            double part = 0.0, y0t = 0.0;
             if (on) {
-                t = P.ft_target[w];
-                const int k1 = P.ft_op_ptr[w + 1];
-                int k = P.ft_op_ptr[w] + c.rr;
+                item = P.ft_item[w];
+                if (c.rr == 0) y0t = Y[GI(item.x)];
+                const int k1 = item.z;
+                int k = item.y + c.rr;
                 for (; k + c.R < k1; k += 2 * c.R) {   // two independent gathers in flight
-                    const int a0 = P.ft_op_a[k], b0 = P.ft_op_b[k], a1 = P.ft_op_a[k + c.R], b1 = P.ft_op_b[k + c.R];
-                    const double y0 = Y[GI(a0)], l0 = Ls[GI(b0)], y1 = Y[GI(a1)], l1 = Ls[GI(b1)];
-                    part = fma(y0, l0, part);
-                    part = fma(y1, l1, part);
+                    const int2 o0 = P.ft_op[k], o1 = P.ft_op[k + c.R];
+                    const double ya = Y[GI(o0.x)], la = Ls[GI(o0.y)], yb = Y[GI(o1.x)], lb = Ls[GI(o1.y)];
+                    part = fma(ya, la, part);
+                    part = fma(yb, lb, part);
                 }
-                if (k < k1) part = fma(Y[GI(P.ft_op_a[k])], Ls[GI(P.ft_op_b[k])], part);
+                if (k < k1) { const int2 o0 = P.ft_op[k]; part = fma(Y[GI(o0.x)], Ls[GI(o0.y)], part); }
             }
             part = lanes_sum(c, part);
             if (on && c.rr == 0) {
-                double acc = Y[GI(t)] - part;
+                const int t = item.x;
+                double acc = y0t - part;
                 if (t >= P.nnzL) {  // diagonal: dynamic regularisation keeps the expected inertia
-                    const double sgn = (double)P.as_sign[t];
+                    const double sgn = (double)item.w;
                     if (!(sgn * acc > delta_dyn)) acc = sgn * delta_dyn;
                     invD[GI(t - P.nnzL)] = 1.0 / acc;
                 }
@@ -214,7 +219,7 @@ __device__ void kkt_factor(const IpmProgram &P, const Ctx &c, double *Y, double 
             }
         }
         __syncthreads();
-        for (int w = P.sc_lvl_ptr[lv] + c.slot; w < P.sc_lvl_ptr[lv + 1]; w += c.nslots) {
+        for (int w = c.s_scl[lv] + c.slot; w < c.s_scl[lv + 1]; w += c.nslots) {
             const int q = P.sc_pos[w];
             Ls[GI(q)] = Y[GI(q)] * invD[GI(P.sc_col[w])];
         }
@@ -227,42 +232,44 @@ __device__ void kkt_ldl_solve(const IpmProgram &P, const Ctx &c, const double *L
 {
     const int G = c.G, sg = c.sg;
     for (int lv = 0; lv < P.nlevels; lv++) {   // forward, rows of L
-        const int wend = P.lvl_ptr[lv + 1];
-        for (int w0 = P.lvl_ptr[lv]; w0 < wend; w0 += c.nisl) {
+        const int wend = c.s_lvl[lv + 1];
+        for (int w0 = c.s_lvl[lv]; w0 < wend; w0 += c.nisl) {
             const int w = w0 + c.isl;
             const bool on = w < wend;
-            int i = 0;
-            double part = 0.0;
+            int4 item = make_int4(0, 0, 0, 0);
+            double part = 0.0, vi = 0.0;
             if (on) {
-                i = P.lvl_nodes[w];
-                const int k1 = P.Lr_rp[i + 1];
-                int k = P.Lr_rp[i] + c.rr;
+                item = P.fw_item[w];
+                if (c.rr == 0) vi = v[GI(item.x)];
+                const int k1 = item.z;
+                int k = item.y + c.rr;
                 for (; k + c.R < k1; k += 2 * c.R) {
-                    const int p0 = P.Lr_pos[k], c0 = P.Lr_col[k], p1 = P.Lr_pos[k + c.R], c1 = P.Lr_col[k + c.R];
-                    const double l0 = Ls[GI(p0)], v0 = v[GI(c0)], l1 = Ls[GI(p1)], v1 = v[GI(c1)];
+                    const int2 a = P.Lr_pc[k], b = P.Lr_pc[k + c.R];
+                    const double l0 = Ls[GI(a.x)], v0 = v[GI(a.y)], l1 = Ls[GI(b.x)], v1 = v[GI(b.y)];
                     part = fma(l0, v0, part);
                     part = fma(l1, v1, part);
                 }
-                if (k < k1) part = fma(Ls[GI(P.Lr_pos[k])], v[GI(P.Lr_col[k])], part);
+                if (k < k1) { const int2 a = P.Lr_pc[k]; part = fma(Ls[GI(a.x)], v[GI(a.y)], part); }
             }
             part = lanes_sum(c, part);
-            if (on && c.rr == 0) v[GI(i)] -= part;
+            if (on && c.rr == 0) v[GI(item.x)] = vi - part;
         }
         __syncthreads();
     }
     for (int i = c.slot; i < P.nk; i += c.nslots) v[GI(i)] *= invD[GI(i)];
     __syncthreads();
     for (int lv = P.nlevels - 1; lv >= 0; lv--) {   // backward, columns of L
-        const int wend = P.lvl_ptr[lv + 1];
-        for (int w0 = P.lvl_ptr[lv]; w0 < wend; w0 += c.nisl) {
+        const int wend = c.s_lvl[lv + 1];
+        for (int w0 = c.s_lvl[lv]; w0 < wend; w0 += c.nisl) {
             const int w = w0 + c.isl;
             const bool on = w < wend;
-            int j = 0;
-            double part = 0.0;
+            int4 item = make_int4(0, 0, 0, 0);
+            double part = 0.0, vj = 0.0;
             if (on) {
-                j = P.lvl_nodes[w];
-                const int k1 = P.L_cp[j + 1];
-                int k = P.L_cp[j] + c.rr;
+                item = P.bw_item[w];
+                if (c.rr == 0) vj = v[GI(item.x)];
+                const int k1 = item.z;
+                int k = item.y + c.rr;
                 for (; k + c.R < k1; k += 2 * c.R) {
                     const int r0 = P.L_ri[k], r1 = P.L_ri[k + c.R];
                     const double l0 = Ls[GI(k)], v0 = v[GI(r0)], l1 = Ls[GI(k + c.R)], v1 = v[GI(r1)];
@@ -272,7 +279,7 @@ __device__ void kkt_ldl_solve(const IpmProgram &P, const Ctx &c, const double *L
                 if (k < k1) part = fma(Ls[GI(k)], v[GI(P.L_ri[k])], part);
             }
             part = lanes_sum(c, part);
-            if (on && c.rr == 0) v[GI(j)] -= part;
+            if (on && c.rr == 0) v[GI(item.x)] = vj - part;
         }
         __syncthreads();
     }
@@ -572,7 +579,13 @@ __global__ void __launch_bounds__(IPM_NT) k_ipm_solve(const IpmProgram P, const 
     __shared__ int s_done[IPM_MAXG], s_status[IPM_MAXG], s_iters[IPM_MAXG], s_alldone, s_save[IPM_MAXG], s_stall[IPM_MAXG];
     __shared__ double s_best[IPM_MAXG], s_bp[IPM_MAXG], s_bd[IPM_MAXG], s_br[3 * IPM_MAXG];
 
+    extern __shared__ int s_lv[];   // [3][nlevels+1]: lvl_ptr, ft_lvl_ptr, sc_lvl_ptr
+    for (int i = threadIdx.x; i <= P.nlevels; i += IPM_NT) {
+        s_lv[i] = P.lvl_ptr[i]; s_lv[P.nlevels + 1 + i] = P.ft_lvl_ptr[i]; s_lv[2 * (P.nlevels + 1) + i] = P.sc_lvl_ptr[i];
+    }
+    __syncthreads();
     Ctx c;
+    c.s_lvl = s_lv; c.s_ftl = s_lv + P.nlevels + 1; c.s_scl = s_lv + 2 * (P.nlevels + 1);
     c.G = D.G; c.tid = threadIdx.x; c.sg = c.tid % c.G; c.slot = c.tid / c.G; c.nslots = IPM_NT / c.G;
     c.R = D.R; c.rr = c.slot % c.R; c.isl = c.slot / c.R; c.nisl = c.nslots / c.R;
     c.red = s_red; c.out = s_out;

@@ -48,6 +48,11 @@ struct ConeSymbolic {
     std::vector<int> as_a, as_b, as_c;
     std::vector<int> as_src;          // per target: index into A values or -1
     std::vector<int> as_sign;         // per target: +1 / -1 / 0 times delta (diagonal regularisation)
+    // packed work items for the kernels (fewer dependent global loads per level):
+    std::vector<int> fw_item, bw_item;   // int4 per level node: {node, start, end, 0} into Lr_pc / (Ls, L_ri)
+    std::vector<int> Lr_pc;              // int2 per L entry in row order: {position, column}
+    std::vector<int> ft_item;            // int4 per factor target: {target id, op start, op end, sign}
+    std::vector<int> ft_op;              // int2 per op: {a, b}
     long long factor_ops = 0;
     std::string err;
 };
@@ -286,5 +291,24 @@ inline bool cone_symbolic_build(ConeSymbolic &S, int n, int p, int m, const int 
         }
     }
     for (int k = 0; k < nk; k++) S.as_sign[S.nnzL + k] = (S.perm[k] < n) ? 1 : -1;
+
+    // ---- packed items ----
+    S.fw_item.resize(4 * (size_t)nk); S.bw_item.resize(4 * (size_t)nk);
+    for (int w = 0; w < nk; w++) {
+        const int i = S.lvl_nodes[w];
+        S.fw_item[4 * w] = i; S.fw_item[4 * w + 1] = S.Lr_rp[i]; S.fw_item[4 * w + 2] = S.Lr_rp[i + 1]; S.fw_item[4 * w + 3] = 0;
+        S.bw_item[4 * w] = i; S.bw_item[4 * w + 1] = S.L_cp[i]; S.bw_item[4 * w + 2] = S.L_cp[i + 1]; S.bw_item[4 * w + 3] = 0;
+    }
+    S.Lr_pc.resize(2 * (size_t)S.nnzL);
+    for (int q = 0; q < S.nnzL; q++) { S.Lr_pc[2 * q] = S.Lr_pos[q]; S.Lr_pc[2 * q + 1] = S.Lr_col[q]; }
+    const size_t nft = S.ft_target.size();
+    S.ft_item.resize(4 * nft);
+    for (size_t w = 0; w < nft; w++) {
+        const int t = S.ft_target[w];
+        S.ft_item[4 * w] = t; S.ft_item[4 * w + 1] = S.ft_op_ptr[w]; S.ft_item[4 * w + 2] = S.ft_op_ptr[w + 1];
+        S.ft_item[4 * w + 3] = S.as_sign[t];
+    }
+    S.ft_op.resize(2 * S.ft_op_a.size());
+    for (size_t k = 0; k < S.ft_op_a.size(); k++) { S.ft_op[2 * k] = S.ft_op_a[k]; S.ft_op[2 * k + 1] = S.ft_op_b[k]; }
     return true;
 }

@@ -373,6 +373,8 @@ int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *u
     const int nbn = (int)(((long long)B * d.N + 127) / 128);
     const int Bpad = s->capB;
     int it = 1, nact = B, total_it = 0;
+    long long ipm_iters = 0;
+    std::vector<int> hit(B);
     for (; it <= d.iter_max; it++) {
         if (h->model_id == SCPB_MODEL_STARSHIP && d.ns > 0)
             k_linearize<Constr<SCPB_MODEL_STARSHIP>><<<nbn, 128, 0, st>>>(pd, s->xd, s->ud, s->p);
@@ -384,6 +386,7 @@ int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *u
         mark(); phase.push_back(1);
         if ((rc = scpb_internal_cone_run(s->cone, o))) return rc;
         mark(); phase.push_back(2);
+        SCPB_CUDA(h, cudaMemcpyAsync(hit.data(), D->iters, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
         sd.iter = it;
         k_extract<<<nbn, 128, 0, st>>>(sd);
         h->launches++;
@@ -396,6 +399,7 @@ int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *u
         SCPB_CUDA(h, cudaMemcpyAsync(&nact, s->nactive, sizeof(int), cudaMemcpyDeviceToHost, st));
         mark(); phase.push_back(3);
         SCPB_CUDA(h, cudaStreamSynchronize(st));
+        for (int b = 0; b < B; b++) ipm_iters += hit[b];
         total_it++;
         if (nact == 0) break;
     }
@@ -420,7 +424,7 @@ int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *u
     for (cudaEvent_t e : ev) cudaEventDestroy(e);
     if (timing) {
         timing[0] = acc[0]; timing[1] = acc[1]; timing[2] = acc[2]; timing[3] = acc[3];
-        timing[4] = tot_ms * 1e-3; timing[5] = (double)total_it; timing[6] = 0.0; timing[7] = 0.0;
+        timing[4] = tot_ms * 1e-3; timing[5] = (double)total_it; timing[6] = (double)ipm_iters; timing[7] = 0.0;
     }
     return SCPB_OK;
 }

@@ -324,5 +324,5 @@ def solve(pbm: SCPProblem, guesses=None, **cone_opts) -> SCPBatchSolution:
         else:
             names.append(f"SCP_FAILED ({lib.CONE_STATUS.get((int(s_) - 2) // 16, '?')})")
     tm = dict(discretize=timing[0], formulate=timing[1], solve=timing[2], overhead=timing[3], total=timing[4],
-              lockstep_iterations=int(timing[5]))
+              lockstep_iterations=int(timing[5]), ipm_iterations=int(timing[6]))
     return SCPBatchSolution(names, iters, J, pbm.t, xd, ud, p, dev, feas, tm, status)
