@@ -128,6 +128,10 @@ def oracle_worker(args):
 
 def cpu_run(N, Nsub, hs, X, U, P, nproc):
     import multiprocessing as mp
+    # one seed per process, every process single-threaded (no BLAS / OpenMP / HiGHS thread pools fighting
+    # over the cores): the reference is a single-threaded Julia process per trajectory
+    for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "HIGHS_NUM_THREADS"):
+        os.environ[v] = "1"
     jobs = [(N, Nsub, hs, X[b], U[b], P[b]) for b in range(X.shape[0])]
     t0 = time.perf_counter()
     with mp.get_context("fork").Pool(nproc) as pool:
