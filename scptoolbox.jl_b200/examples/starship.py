@@ -13,7 +13,7 @@ import scipy.sparse as sp
 
 from .. import lib
 from ..parser import ConicTemplate, Expr, matvec
-from ..problem import (TrajectoryProblem, problem_advise_scale, problem_set_bc, problem_set_dims,
+from ..problem import (TrajectoryProblem, problem_advise_parameter_stage, problem_advise_scale, problem_set_bc, problem_set_dims,
                        problem_set_dynamics, problem_set_guess, problem_set_s, problem_set_terminal_cost,
                        problem_set_U, problem_set_X)
 
@@ -81,7 +81,13 @@ def define_problem(pbm: TrajectoryProblem, algo: str = "ptr", handle=None):
         return alt_cost * 0.3 + dm_cost
 
     problem_set_terminal_cost(pbm, phi)
-    problem_set_dynamics(pbm, lib.MODEL_STARSHIP, mdl.par(), fcols=(0, 1))
+    # structure of df/dx, df/du (definition.jl:582-620): x = [r(2) v(2) theta omega m delta_d], u = [T delta delta_dot]
+    As = np.zeros((8, 8), bool); Bs = np.zeros((8, 3), bool)
+    As[0, 2] = As[1, 3] = As[4, 5] = As[7, 7] = True
+    As[2:4, 2:5] = True
+    As[5, 2:5] = True
+    Bs[2:4, 0:2] = True; Bs[5, 0:2] = True; Bs[6, 0] = True; Bs[7, 1] = True
+    problem_set_dynamics(pbm, lib.MODEL_STARSHIP, mdl.par(), fcols=(0, 1), A_struct=As, B_struct=Bs)
 
     # set_convex_constraints!
     def X(t, k, x, p, pbm, ocp):
@@ -102,17 +108,36 @@ def define_problem(pbm: TrajectoryProblem, algo: str = "ptr", handle=None):
     problem_set_X(pbm, X)
     problem_set_U(pbm, U)
 
-    # set_nonconvex_constraints!: structure of the device pack Constr<STARSHIP> (union over nodes)
+    # set_nonconvex_constraints!: node-dependent structure of the device pack Constr<STARSHIP>
     ns = 7 + 2 * 8
-    Cm = np.zeros((ns, 8), bool); Dm = np.zeros((ns, 3), bool); Gm = np.zeros((ns, 10), bool)
-    Cm[0, 7] = Cm[1, 7] = True
-    Cm[4, 0] = Cm[4, 1] = True
-    for i in range(8):
-        Cm[5 + i, i] = Cm[13 + i, i] = True
-        Gm[5 + i, 2 + i] = Gm[13 + i, 2 + i] = True
-    Cm[21, 4] = Cm[22, 4] = True
-    Dm[0, 1] = Dm[0, 2] = Dm[1, 1] = Dm[1, 2] = Dm[2, 2] = Dm[3, 2] = True
-    problem_set_s(pbm, ns, Cm, Dm, Gm)
+
+    def phase_switch(t, N):          # definition.jl:707-714
+        dt = 1 / (N - 1)
+        return (mdl.tau_s - dt) + 1e-3 <= t and t <= mdl.tau_s + 1e-3
+
+    def s_struct(t, k, pbm_):
+        N = pbm_.scp.N
+        Cm = np.zeros((ns, 8), bool); Dm = np.zeros((ns, 3), bool); Gm = np.zeros((ns, 10), bool)
+        Cm[0, 7] = Cm[1, 7] = True
+        Cm[4, 0] = Cm[4, 1] = True
+        Dm[0, 1] = Dm[0, 2] = Dm[1, 1] = Dm[1, 2] = Dm[2, 2] = Dm[3, 2] = True
+        psw = phase_switch(t, N)
+        if psw:
+            for i in range(8):
+                Cm[5 + i, i] = Cm[13 + i, i] = True
+                Gm[5 + i, 2 + i] = Gm[13 + i, 2 + i] = True
+        if psw or t > mdl.tau_s:
+            Cm[21, 4] = Cm[22, 4] = True
+        return Cm, Dm, Gm
+
+    problem_set_s(pbm, ns, s_struct)
+
+    def p_stage(N):
+        tg = np.arange(N) / (N - 1)
+        ksw = [k for k in range(N) if phase_switch(tg[k], N)]
+        return [-1, -1] + [ksw[0] if ksw else -1] * 8
+
+    problem_advise_parameter_stage(pbm, p_stage)
 
     # set_bcs!
     def gic(x, p, pbm):

@@ -37,11 +37,36 @@ def propagate_labels(var_stage, G):
     return lab
 
 
-def stage_order(A, G, var_stage, nstages):
+def _local_min_degree(nodes, adj, A, n):
+    """Greedy minimum-degree order of one stage's local nodes (fill tracked inside the stage only).  Equality rows
+    become eligible once one of their variables has been eliminated (their pivot is -delta before that)."""
+    ladj = {v: set(adj[v]) for v in nodes}
+    elim, order, remaining = set(), [], set(nodes)
+    rowcols = {v: set(A.indices[A.indptr[v - n]:A.indptr[v - n + 1]].tolist()) for v in nodes if v >= n}
+    while remaining:
+        best, bd = None, None
+        for v in remaining:
+            if v >= n and not (rowcols[v] & elim):
+                continue
+            d = len(ladj[v] - elim)
+            if bd is None or d < bd or (d == bd and v < best):
+                best, bd = v, d
+        if best is None:
+            best = min(remaining)
+        nb = [w for w in ladj[best] if w not in elim and w in ladj]
+        for a_ in nb:
+            ladj[a_].update(nb)
+            ladj[a_].discard(a_)
+        elim.add(best); remaining.discard(best); order.append(best)
+    return order
+
+
+def stage_order(A, G, var_stage, nstages, local_md=True):
     """perm (length n+p): node eliminated k-th; variables 0..n-1, equality rows n..n+p-1.
 
-    var_stage[v]: stage index 0..nstages-1, -1 for global variables, -2 for 'derive from neighbours'."""
-    A = A.tocsr()
+    var_stage[v]: stage index 0..nstages-1, -1 for global variables, -2 for 'derive from neighbours'.
+    local_md: order each stage's local nodes by greedy minimum degree (about halves the fill)."""
+    A = A.tocsr(); G = G.tocsr()
     p, n = A.shape
     lab = propagate_labels(var_stage, G)
     rlo = np.full(p, -1, dtype=np.int64)
@@ -62,9 +87,15 @@ def stage_order(A, G, var_stage, nstages):
             local_rows[rlo[r]].append(n + r)
         else:
             strad.setdefault((int(rlo[r]), int(rhi[r])), []).append(n + r)
+    adj = None
+    if local_md:
+        Gb = sp.csr_matrix((np.ones(G.nnz, dtype=np.int32), G.indices, G.indptr), shape=G.shape)
+        Ab = sp.csr_matrix((np.ones(A.nnz, dtype=np.int32), A.indices, A.indptr), shape=A.shape)
+        K = sp.bmat([[Gb.T @ Gb, Ab.T], [Ab, None]], format="csr")
+        adj = [set(K.indices[K.indptr[i]:K.indptr[i + 1]].tolist()) - {i} for i in range(n + p)]
     for k in range(nstages):
-        order.extend(np.where(lab == k)[0].tolist())
-        order.extend(local_rows[k])
+        nodes = np.where(lab == k)[0].tolist() + local_rows[k]
+        order.extend(_local_min_degree(nodes, adj, A, n) if local_md else nodes)
     placed = set()
 
     def nd(lo, hi):

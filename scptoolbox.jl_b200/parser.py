@@ -146,8 +146,11 @@ def matvec(M, v):
 class ConicTemplate:
     """Symbolic ConicProgram (program.jl:63-76): variables, cone rows, cost -- with Lin coefficients."""
 
-    def __init__(self, nsrc: int):
+    def __init__(self, nsrc: int, l1_block: int = 0):
         self.nsrc = nsrc
+        # l1_block > 0: lower |x|_1 <= t through partial sums of l1_block epigraph variables (an equivalent
+        # program whose normal-equation matrix has no dense (dim x dim) block; 0 = MOI's NormOneBridge form)
+        self.l1_block = int(l1_block)
         self.nvar = 0
         self.blocks = {}
         self.var_stage = []       # stage label per variable (-1 global, -2 derive from neighbours)
@@ -175,6 +178,8 @@ class ConicTemplate:
                 self.var_stage.append(int(idx[0]))
             elif stage is None:
                 self.var_stage.append(-1)
+            elif hasattr(stage, "__len__"):
+                self.var_stage.append(int(stage[i]))
             else:
                 self.var_stage.append(int(stage))
         return arr
@@ -195,10 +200,22 @@ class ConicTemplate:
     def l1(self, exprs, name="", stage=-2):
         t, xs = Expr.lift(exprs[0]), [Expr.lift(e) for e in exprs[1:]]
         y = self._aux(len(xs), stage)
-        tot = Expr()
         for xi, yi in zip(xs, y):
             self.ineq.append(xi - yi)
             self.ineq.append(-xi - yi)
+        blk = self.l1_block
+        if blk > 0 and len(y) > blk + 1:
+            parts = []
+            for j in range(0, len(y), blk):
+                b = self._aux(1, stage)[0]
+                tot = Expr()
+                for yi in y[j:j + blk]:
+                    tot = tot + yi
+                self.ineq.append(tot - b)
+                parts.append(b)
+            y = parts
+        tot = Expr()
+        for yi in y:
             tot = tot + yi
         self.ineq.append(tot - t)
 

@@ -20,6 +20,9 @@ class TrajectoryProblem:
         self.model_id = 0
         self.model_par = None
         self.fcols = [0]
+        self.A_struct = None
+        self.B_struct = None
+        self.p_stage = None
         self.guess = None
         self.phi = None          # terminal cost  phi(x_expr, p_expr, pbm) -> Expr     (problem.jl:365-368)
         self.Gamma = None        # running cost   Gamma(t,k,x,u,p,pbm) -> Expr          (problem.jl:392-394)
@@ -62,12 +65,29 @@ def problem_set_running_cost(pbm, Gamma):
     pbm.Gamma = lambda t, k, x, u, p: Gamma(t, k, x, u, p, pbm)
 
 
-def problem_set_dynamics(pbm, model_id, par, fcols=(0,)):
+def problem_set_dynamics(pbm, model_id, par, fcols=(0,), A_struct=None, B_struct=None):
     """problem_set_dynamics! (problem.jl:425-450): selects the device pack that evaluates f, A, B, F.
-    fcols: parameter index of each active (time-dilation) column of F."""
+    fcols: parameter index of each active (time-dilation) column of F.
+    A_struct / B_struct: optional structural non-zero patterns of df/dx (nx x nx) and df/du (nx x nu); the
+    discrete-time blocks inherit the reachability closure (Phi = closure(I + A), B_k = Phi*B, E_k ~ Phi), which
+    removes structurally zero coefficients from the dynamics rows of the subproblem."""
     pbm.model_id = int(model_id)
     pbm.model_par = np.asarray(par, dtype=np.float64)
     pbm.fcols = list(fcols)
+    pbm.A_struct = None if A_struct is None else np.asarray(A_struct, bool)
+    pbm.B_struct = None if B_struct is None else np.asarray(B_struct, bool)
+
+
+def dltv_masks(pbm):
+    """Structural patterns (A_k, B_k, E_k) implied by A_struct/B_struct; None = dense."""
+    if getattr(pbm, "A_struct", None) is None:
+        return None, None, None
+    nx = pbm.nx
+    R = np.eye(nx, dtype=bool) | pbm.A_struct
+    for _ in range(nx):                       # transitive closure
+        R = R | ((R.astype(int) @ R.astype(int)) > 0)
+    Bm = None if pbm.B_struct is None else ((R.astype(int) @ pbm.B_struct.astype(int)) > 0)
+    return R, Bm, R
 
 
 def problem_set_X(pbm, X):
@@ -78,11 +98,19 @@ def problem_set_U(pbm, U):
     pbm.U = lambda ocp, t, k, u, p: U(t, k, u, p, pbm, ocp)
 
 
-def problem_set_s(pbm, ns, Cmask, Dmask, Gmask):
+def problem_set_s(pbm, ns, struct):
     """problem_set_s! (problem.jl:560-587): the constraint pack of the selected model evaluates s, C, D, G on the
-    device; the masks give their structural non-zeros (row-major ns x nx / nu / np)."""
+    device; struct(t, k, pbm) -> (Cmask, Dmask, Gmask) gives their structural non-zeros at node k
+    (row-major ns x nx / nu / np).  Node-dependent structure keeps e.g. phase-switch rows from coupling a
+    parameter to every stage."""
     pbm.ns = int(ns)
-    pbm.s_struct = (np.asarray(Cmask, bool), np.asarray(Dmask, bool), np.asarray(Gmask, bool))
+    pbm.s_struct = lambda t, k: struct(t, k, pbm)
+
+
+def problem_advise_parameter_stage(pbm, stage_of):
+    """B200-specific ordering advice: stage_of(N) -> list (len np) with the time node a parameter is tied to, or
+    -1 for a genuinely global parameter (used only for the elimination order of the KKT factorisation)."""
+    pbm.p_stage = stage_of
 
 
 def problem_set_bc(pbm, kind, g):

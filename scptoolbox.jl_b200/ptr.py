@@ -112,8 +112,9 @@ class SourceMap:
 class SCPProblem:
     """pbm returned by create(): template, device objects, scaling."""
 
-    def __init__(self, pars, traj, handle):
+    def __init__(self, pars, traj, handle, l1_block=4):
         self.pars, self.traj, self.handle = pars, traj, handle
+        self.l1_block = l1_block
         self.scale = SCPScaling(traj)
         self.t = t_grid(pars.N)
         traj.scp = pars
@@ -128,20 +129,22 @@ class SCPProblem:
         ns, nf = traj.ns, len(traj.fcols)
         sm = SourceMap(N, nx, nu, np_, ns, nf)
         self.sm = sm
-        prg = ConicTemplate(sm.nsrc)
+        prg = ConicTemplate(sm.nsrc, l1_block=self.l1_block)
         x = prg.new_variable((nx, N), "x", sc.Sx, sc.cx, stage="col")
         u = prg.new_variable((nu, N), "u", sc.Su, sc.cu, stage="col")
-        p = prg.new_variable(np_, "p", sc.Sp, sc.cp, stage=None)
+        p = prg.new_variable(np_, "p", sc.Sp, sc.cp, stage=(traj.p_stage(N) if traj.p_stage else None))
         vd = prg.new_variable((nx, N - 1), "vd", stage="col")
         eta_x = prg.new_variable(N, "eta_x", stage="idx")
         eta_u = prg.new_variable(N, "eta_u", stage="idx")
         eta_p = prg.new_variable(1, "eta_p", stage=None)
         # add_dynamics! / state_update! (discretization.jl:424-497)
+        from .problem import dltv_masks
+        mA, mB, mE = dltv_masks(traj)
         for k in range(N - 1):
-            A = sm.mat(sm.oA, k, nx, nx)
-            Bm = sm.mat(sm.oBm, k, nx, nu)
-            Bp = sm.mat(sm.oBp, k, nx, nu)
-            E = sm.mat(sm.oE, k, nx, nx)
+            A = sm.mat(sm.oA, k, nx, nx, mask=mA)
+            Bm = sm.mat(sm.oBm, k, nx, nu, mask=mB)
+            Bp = sm.mat(sm.oBp, k, nx, nu, mask=mB)
+            E = sm.mat(sm.oE, k, nx, nx, mask=mE)
             r = sm.vec(sm.or_, k, nx)
             Fp = sm.mat(sm.oF, k, nx, nf)
             rhs = [a + b + c + d for a, b, c, d in zip(matvec(A, x[:, k]), matvec(Bm, u[:, k]),
@@ -158,9 +161,9 @@ class SCPProblem:
         # nonconvex constraints (scp.jl:744-794)
         vs = None
         if ns:
-            Cm, Dm, Gm = traj.s_struct
             vs = prg.new_variable((ns, N), "vs", stage="col")
             for k in range(N):
+                Cm, Dm, Gm = traj.s_struct(t[k], k + 1)
                 Cs = sm.mat(sm.oC, k, ns, nx, colmajor=False, mask=Cm)
                 Ds = sm.mat(sm.oD, k, ns, nu, colmajor=False, mask=Dm)
                 Gs = sm.mat(sm.oG, k, ns, np_, colmajor=False, mask=Gm)
@@ -209,7 +212,7 @@ class SCPProblem:
         Pf = prg.new_variable(2, "Pf", stage=None)
         for k in range(N):
             if k < N - 1:
-                E = sm.mat(sm.oE, k, nx, nx)
+                E = sm.mat(sm.oE, k, nx, nx, mask=mE)
                 Ev = matvec(E, vd[:, k])
                 prg.l1([P[k]] + list(Ev) + (list(vs[:, k]) if vs is not None else []), "vd_vs_penalty", stage=k)
             elif vs is not None:
@@ -285,9 +288,10 @@ class SCPBatchSolution:      # batched SCPSolution (scp.jl:105-119)
     raw_status: np.ndarray
 
 
-def create(pars: Parameters, traj, handle) -> SCPProblem:
-    """PTR.create (ptr.jl:148-195)."""
-    return SCPProblem(pars, traj, handle)
+def create(pars: Parameters, traj, handle, l1_block=4) -> SCPProblem:
+    """PTR.create (ptr.jl:148-195).  l1_block: see parser.ConicTemplate (0 reproduces the reference's exact
+    NormOneBridge cone program; the default 4 is an equivalent, sparser lowering for the GPU factorisation)."""
+    return SCPProblem(pars, traj, handle, l1_block=l1_block)
 
 
 def solve(pbm: SCPProblem, guesses=None, **cone_opts) -> SCPBatchSolution:

@@ -63,7 +63,7 @@ def test_template_matches_oracle_subproblem(pkg, N, monkeypatch):
     monkeypatch.setattr(pkg.lib, "ConeProblem", lambda *a, **k: type("C", (), {"c": None, "close": lambda s: None})())
     fake = FakeHandle(); fake.lib = type("L", (), {"scpb_ptr_setup": staticmethod(lambda *a: 0)})(); fake.h = None
     fake._check = lambda rc, what: None
-    pbm = pkg.ptr.SCPProblem(pars, traj, fake)
+    pbm = pkg.ptr.SCPProblem(pars, traj, fake, l1_block=0)   # the reference's exact (NormOneBridge) program
     cp, sm = pbm.cp, pbm.sm
     src = _sources(sm, pbo, P, ref)
     vals = pbm.W @ src
