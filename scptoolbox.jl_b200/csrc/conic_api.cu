@@ -107,7 +107,8 @@ int scpb_internal_cone_run(scpb_cone_s *c, const IpmOpts &o)
     scpb_handle_s *h = c->h;
     const int ng = (c->D.B + c->D.G - 1) / c->D.G;
     const size_t smem = sizeof(int) * 3 * (size_t)(c->S.nlevels + 1);
-    k_ipm_solve<<<ng, IPM_NT, smem, h->stream>>>(c->P, c->D, o);
+    if (o.threads >= 1024) k_ipm_solve<1024><<<ng, 1024, smem, h->stream>>>(c->P, c->D, o);
+    else k_ipm_solve<512><<<ng, 512, smem, h->stream>>>(c->P, c->D, o);
     h->launches++;
     SCPB_CUDA(h, cudaGetLastError());
     return SCPB_OK;
@@ -124,6 +125,9 @@ IpmOpts scpb_internal_make_opts(const scpb_cone_opts *o)
     r.maxit = (o && o->maxit > 0) ? o->maxit : 100;
     r.nref = (o && o->nref >= 0) ? o->nref : 2;
     r.equil = (o && o->equil >= 0) ? o->equil : 5;
+    r.threads = (o && o->threads > 0) ? o->threads : 512;
+    r.nref_aff = 0;
+    r.reftol = 1e-13;
     return r;
 }
 

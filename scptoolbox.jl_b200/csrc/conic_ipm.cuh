@@ -37,6 +37,9 @@ struct IpmOpts {
     double delta;                     // static regularisation
     double delta_dyn;                 // dynamic regularisation threshold / value
     int maxit, nref, equil;   // equil: Ruiz iterations (0 = off)
+    int threads;              // CTA size: 512 or 1024
+    int nref_aff;             // refinement steps for the predictor (affine) direction
+    double reftol;
 };
 
 struct IpmData {  // group-blocked device arrays, all for B seeds
@@ -57,18 +60,20 @@ struct IpmData {  // group-blocked device arrays, all for B seeds
 
 enum { IPM_OPTIMAL = 0, IPM_MAXIT = 1, IPM_NUMERICAL = 2, IPM_ALMOST = 3 };
 
-#define IPM_MAXG 32
-#define IPM_NT 512
+#define IPM_MAXG 8
+#define IPM_NT_MAX 1024
 
 #ifdef CONIC_IPM_IMPL   // the kernel itself is compiled in conic_api.cu only
 // ---------------------------------------------------------------------------------------------
 struct Ctx {
-    int G, sg, slot, nslots, tid;
+    int G, sg, slot, nslots, tid, nwarps;
     // row-type work (sparse dot products): R lanes cooperate on one row for the G seeds of the group;
     // lane layout inside a warp: tid = (item*R + rr)*G + sg, reduced with xor-shuffles over rr
     int R, rr, isl, nisl;
     const int *s_lvl, *s_ftl, *s_scl;   // level pointers staged in shared memory
-    double *red;   // shared: [8][IPM_NT/32][IPM_MAXG]
+    int *flag;                          // shared scratch word for CTA-uniform decisions
+    double reftol;                      // iterative refinement stops once |residual|_inf <= reftol*(1+|rhs|_inf)
+    double *red;   // shared: [8][IPM_NT_MAX/32][IPM_MAXG]
     double *out;   // shared: [8][IPM_MAXG]
 };
 
@@ -90,15 +95,15 @@ __device__ __forceinline__ void seed_reduce(const Ctx &c, double (&v)[K], int op
     __syncthreads();  // protect red/out from the previous use
     if (lane < G) {
 #pragma unroll
-        for (int k = 0; k < K; k++) c.red[(k * (IPM_NT / 32) + warp) * IPM_MAXG + lane] = v[k];
+        for (int k = 0; k < K; k++) c.red[(k * (IPM_NT_MAX / 32) + warp) * IPM_MAXG + lane] = v[k];
     }
     __syncthreads();
     if (c.tid < G) {
 #pragma unroll
         for (int k = 0; k < K; k++) {
-            double a = c.red[(k * (IPM_NT / 32)) * IPM_MAXG + c.tid];
-            for (int w = 1; w < IPM_NT / 32; w++) {
-                const double t = c.red[(k * (IPM_NT / 32) + w) * IPM_MAXG + c.tid];
+            double a = c.red[(k * (IPM_NT_MAX / 32)) * IPM_MAXG + c.tid];
+            for (int w = 1; w < c.nwarps; w++) {
+                const double t = c.red[(k * (IPM_NT_MAX / 32) + w) * IPM_MAXG + c.tid];
                 a = (op == 0) ? a + t : ((op == 1) ? fmin(a, t) : fmax(a, t));
             }
             c.out[k * IPM_MAXG + c.tid] = a;
@@ -317,14 +322,31 @@ __device__ void kkt_solve(const IpmProgram &P, const Ctx &c, const IpmData &D, c
         __syncthreads();
         apply_winv2(P, c, wm, socw, soceta, gm, e1);  // e1: max(n,m)-sized scratch holding W^-2 G dx
         __syncthreads();
+        double nrm[2] = {0.0, 0.0};   // |residual|_inf, |rhs|_inf
         for (int v = c.slot; v < P.n; v += c.nslots) {
             const double r = bx[GI(v)] - col_dot(P.Gt_rp, P.Gt_ri, P.Gt_vi, Gv, e1, v, G, sg) -
                              col_dot(P.At_rp, P.At_ri, P.At_vi, Av, dy, v, G, sg);
             rhs[GI(P.iperm[v])] = r;
+            nrm[0] = fmax(nrm[0], fabs(r)); nrm[1] = fmax(nrm[1], fabs(bx[GI(v)]));
         }
-        for (int r = c.slot; r < P.p; r += c.nslots)
-            rhs[GI(P.iperm[P.n + r])] = by[GI(r)] - row_dot(P.A_rp, P.A_ci, Av, dx, r, G, sg);
+        for (int r = c.slot; r < P.p; r += c.nslots) {
+            const double rr = by[GI(r)] - row_dot(P.A_rp, P.A_ci, Av, dx, r, G, sg);
+            rhs[GI(P.iperm[P.n + r])] = rr;
+            nrm[0] = fmax(nrm[0], fabs(rr)); nrm[1] = fmax(nrm[1], fabs(by[GI(r)]));
+        }
+        seed_reduce<2>(c, nrm, 2);   // ends with a barrier: rhs is complete as well
+        if (c.tid == 0) {
+            int again = 0;
+            for (int q = 0; q < G; q++) {
+                const double res = c.out[q], ref = c.out[IPM_MAXG + q];
+                if (!(res <= c.reftol * (1.0 + ref))) again = 1;   // NaN counts as "not converged"
+            }
+            *c.flag = again;
+        }
         __syncthreads();
+        const int again = *c.flag;
+        __syncthreads();
+        if (!again) break;
     }
     // dz = W^-2 (G dx - bz)
     for (int r = c.slot; r < P.m; r += c.nslots) gm[GI(r)] = row_dot(P.G_rp, P.G_ci, Gv, dx, r, G, sg) - bz[GI(r)];
@@ -570,23 +592,26 @@ __device__ void equilibrate(const IpmProgram &P, const Ctx &c, double *Av, doubl
 }
 
 // =============================================================================================
-__global__ void __launch_bounds__(IPM_NT) k_ipm_solve(const IpmProgram P, const IpmData D, const IpmOpts O)
+template <int NT>
+__global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmData D, const IpmOpts O)
 {
-    __shared__ double s_red[8 * (IPM_NT / 32) * IPM_MAXG];
+    __shared__ double s_red[8 * (IPM_NT_MAX / 32) * IPM_MAXG];
     __shared__ double s_out[8 * IPM_MAXG];
     __shared__ double s_nb[IPM_MAXG], s_nh[IPM_MAXG], s_nc[IPM_MAXG];
     __shared__ double s_mu[IPM_MAXG], s_sigmu[IPM_MAXG], s_alpha[IPM_MAXG], s_scale[IPM_MAXG];
+    __shared__ int s_flag;
     __shared__ int s_done[IPM_MAXG], s_status[IPM_MAXG], s_iters[IPM_MAXG], s_alldone, s_save[IPM_MAXG], s_stall[IPM_MAXG];
     __shared__ double s_best[IPM_MAXG], s_bp[IPM_MAXG], s_bd[IPM_MAXG], s_br[3 * IPM_MAXG];
 
     extern __shared__ int s_lv[];   // [3][nlevels+1]: lvl_ptr, ft_lvl_ptr, sc_lvl_ptr
-    for (int i = threadIdx.x; i <= P.nlevels; i += IPM_NT) {
+    for (int i = threadIdx.x; i <= P.nlevels; i += NT) {
         s_lv[i] = P.lvl_ptr[i]; s_lv[P.nlevels + 1 + i] = P.ft_lvl_ptr[i]; s_lv[2 * (P.nlevels + 1) + i] = P.sc_lvl_ptr[i];
     }
     __syncthreads();
     Ctx c;
     c.s_lvl = s_lv; c.s_ftl = s_lv + P.nlevels + 1; c.s_scl = s_lv + 2 * (P.nlevels + 1);
-    c.G = D.G; c.tid = threadIdx.x; c.sg = c.tid % c.G; c.slot = c.tid / c.G; c.nslots = IPM_NT / c.G;
+    c.G = D.G; c.tid = threadIdx.x; c.sg = c.tid % c.G; c.slot = c.tid / c.G; c.nslots = NT / c.G; c.nwarps = NT / 32;
+    c.flag = &s_flag; c.reftol = O.reftol;
     c.R = D.R; c.rr = c.slot % c.R; c.isl = c.slot / c.R; c.nisl = c.nslots / c.R;
     c.red = s_red; c.out = s_out;
     const int G = c.G, sg = c.sg;
@@ -751,7 +776,7 @@ __global__ void __launch_bounds__(IPM_NT) k_ipm_solve(const IpmProgram P, const 
         for (int i = c.slot; i < P.p; i += c.nslots) r2[GI(i)] = -ry[GI(i)];
         for (int i = c.slot; i < P.m; i += c.nslots) ds[GI(i)] = -rz[GI(i)] + s[GI(i)];  // ds used as bz scratch
         __syncthreads();
-        kkt_solve(P, c, D, Av, Gv, wm, socw, soceta, r1, r2, ds, dx, dy, dza, tm, gm, e1, e2, rhs, Ls, invD, O.nref);
+        kkt_solve(P, c, D, Av, Gv, wm, socw, soceta, r1, r2, ds, dx, dy, dza, tm, gm, e1, e2, rhs, Ls, invD, O.nref_aff);
         // ds = tmp - W^2 dz with tmp = -s; W^2 dz == G dx - bz is left in gm by kkt_solve (no W^2 W^-2
         // round trip: keeps G dx + ds = -rz to rounding even when the scaling is ill-conditioned)
         for (int i = c.slot; i < P.m; i += c.nslots) dsa[GI(i)] = -s[GI(i)] - gm[GI(i)];

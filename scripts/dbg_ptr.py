@@ -19,10 +19,12 @@ sc = pbm.scale
 X0 = np.array([go[0] + (0.01*sc.Sx*rng.standard_normal(go[0].shape) if b else 0.0) for b in range(nb)])
 U0 = np.array([go[1] + (0.01*sc.Su*rng.standard_normal(go[1].shape) if b else 0.0) for b in range(nb)])
 P0 = np.array([go[2]*(1+(0.02*rng.uniform(-1,1,go[2].shape) if b else 0.0)) for b in range(nb)])
-sol = pkg.ptr.solve(pbm, (X0, U0, P0))
-print("status", sol.raw_status, "iters", sol.iterations, "J", sol.cost[:4], "dev", sol.deviation[:4], "feas", sol.feas[:8], flush=True)
+import os
+opts = eval(os.environ.get('CONE_OPTS', '{}'))
+sol = pkg.ptr.solve(pbm, (X0, U0, P0), **opts)
+print("opts", opts, "status", np.unique(sol.raw_status, return_counts=True), "iters", np.unique(sol.iterations, return_counts=True), "J", sol.cost[:4], "dev", sol.deviation[:4], "feas", sol.feas[:8], flush=True)
 print("timing", sol.timing, flush=True)
-sol = pkg.ptr.solve(pbm, (X0, U0, P0))
+sol = pkg.ptr.solve(pbm, (X0, U0, P0), **opts)
 print("timing2", sol.timing, "SCP it/s", sol.iterations.sum()/sol.timing["total"], flush=True)
 if nb <= 8:
     opars = optr.Parameters(N=N, Nsub=Nsub, iter_max=15, wvc=1e3, wtr=0.1, eps_abs=1e-5, eps_rel=0.01/100, feas_tol=5e-3, solver_tol=1e-9)
