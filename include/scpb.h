@@ -98,7 +98,7 @@ typedef struct {
     int32_t verbose;                /* accepted, ignored ("verbose" of solver_opts)      */
     int32_t group;                  /* seeds per CTA (power of two <= 32); 0 = automatic */
     int32_t equil;                  /* Ruiz equilibration passes; <0: default 5, 0: off    */
-    int32_t threads;                /* threads per CTA: 512 (default) or 1024              */
+    int32_t threads;                /* threads per CTA: 1024 (default) or 512              */
 } scpb_cone_opts;
 
 /* per-seed status (termination_status, program.jl:427-428): */

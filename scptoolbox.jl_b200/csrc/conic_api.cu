@@ -87,7 +87,7 @@ static int cone_reserve(scpb_cone_s *c, int B, int G)
     D.soceta = al(S.nsoc + 1);
     D.dx = al(n); D.dy = al(p); D.dz = al(m); D.ds = al(m); D.dsa = al(m); D.dza = al(m); D.tm = al(m); D.gm = al(m);
     D.r1 = al(n); D.r2 = al(p); D.e1 = al(nm); D.e2 = al(p); D.rhs = al(nk);
-    D.Y = al(S.nnzL + nk); D.Ls = al(S.nnzL + 1); D.invD = al(nk);
+    D.Y = al(S.nnzL + nk); D.Ls = al(S.nnzL + 1); D.Lrow = al(S.nnzL + 1); D.invD = al(nk);
     for (double *q : c->bufs)
         if (!q) return set_err(h, SCPB_ERR_CUDA, "cone solver: device allocation failed (B=%d)", B);
     if (cudaMalloc((void **)&c->d_status, sizeof(int) * Bpad) != cudaSuccess ||
@@ -106,9 +106,19 @@ int scpb_internal_cone_run(scpb_cone_s *c, const IpmOpts &o)
 {
     scpb_handle_s *h = c->h;
     const int ng = (c->D.B + c->D.G - 1) / c->D.G;
-    const size_t smem = sizeof(int) * 3 * (size_t)(c->S.nlevels + 1);
-    if (o.threads >= 1024) k_ipm_solve<1024><<<ng, 1024, smem, h->stream>>>(c->P, c->D, o);
-    else k_ipm_solve<512><<<ng, 512, smem, h->stream>>>(c->P, c->D, o);
+    // dynamic shared memory: level pointers (+ the substitution vector when nk*G doubles fit next to the
+    // ~20 KB of static shared memory; B200 allows 227 KB per CTA)
+    size_t smem = sizeof(int) * ((3 * (size_t)(c->S.nlevels + 1) + 3) & ~(size_t)3);
+    const size_t vbytes = sizeof(double) * (size_t)c->S.nk * c->D.G;
+    c->D.vsmem = (smem + vbytes <= 200 * 1024) ? 1 : 0;
+    if (c->D.vsmem) smem += vbytes;
+    if (o.threads >= 1024) {
+        SCPB_CUDA(h, cudaFuncSetAttribute(k_ipm_solve<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_ipm_solve<1024><<<ng, 1024, smem, h->stream>>>(c->P, c->D, o);
+    } else {
+        SCPB_CUDA(h, cudaFuncSetAttribute(k_ipm_solve<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_ipm_solve<512><<<ng, 512, smem, h->stream>>>(c->P, c->D, o);
+    }
     h->launches++;
     SCPB_CUDA(h, cudaGetLastError());
     return SCPB_OK;
@@ -125,7 +135,7 @@ IpmOpts scpb_internal_make_opts(const scpb_cone_opts *o)
     r.maxit = (o && o->maxit > 0) ? o->maxit : 100;
     r.nref = (o && o->nref >= 0) ? o->nref : 2;
     r.equil = (o && o->equil >= 0) ? o->equil : 5;
-    r.threads = (o && o->threads > 0) ? o->threads : 512;
+    r.threads = (o && o->threads > 0) ? o->threads : 1024;
     r.nref_aff = 0;
     r.reftol = 1e-13;
     return r;
@@ -169,7 +179,7 @@ int32_t scpb_cone_setup(scpb_handle h, int32_t n, int32_t p, int32_t m, const in
     UP(sc_lvl_ptr); UP(sc_pos); UP(sc_col); UP(as_ptr); UP(as_a); UP(as_b); UP(as_c); UP(as_src); UP(as_sign);
 #undef UP
     P.fw_item = (const int4 *)upload_ints(c, S.fw_item); P.bw_item = (const int4 *)upload_ints(c, S.bw_item);
-    P.ft_item = (const int4 *)upload_ints(c, S.ft_item);
+    P.ft_item = (const int4 *)upload_ints(c, S.ft_item); P.sc_item = (const int4 *)upload_ints(c, S.sc_item);
     P.Lr_pc = (const int2 *)upload_ints(c, S.Lr_pc); P.ft_op = (const int2 *)upload_ints(c, S.ft_op);
     for (void *d : c->dev_ints)
         if (!d) {

@@ -28,7 +28,7 @@ struct IpmProgram {  // device copies of ConeSymbolic index arrays
     const int *ft_lvl_ptr, *ft_target, *ft_op_ptr, *ft_op_a, *ft_op_b;
     const int *sc_lvl_ptr, *sc_pos, *sc_col;
     const int *as_ptr, *as_a, *as_b, *as_c, *as_src, *as_sign;
-    const int4 *fw_item, *bw_item, *ft_item;
+    const int4 *fw_item, *bw_item, *ft_item, *sc_item;
     const int2 *Lr_pc, *ft_op;
 };
 
@@ -52,7 +52,8 @@ struct IpmData {  // group-blocked device arrays, all for B seeds
     double *xb, *yb, *zb, *sb;   // best iterate so far (restored when the run ends without reaching the tolerances)
     // work
     double *rx, *ry, *rz, *lam, *wm, *socw, *soceta;
-    double *dx, *dy, *dz, *ds, *dsa, *dza, *tm, *gm, *r1, *r2, *e1, *e2, *rhs, *Y, *Ls, *invD;
+    double *dx, *dy, *dz, *ds, *dsa, *dza, *tm, *gm, *r1, *r2, *e1, *e2, *rhs, *Y, *Ls, *Lrow, *invD;
+    int vsmem;   // 1: the substitution vector of kkt_ldl_solve lives in shared memory (nk*G doubles fit)
     // per-seed outputs
     double *pobj, *dobj, *res;   // res: [3][B] pres, dres, gap
     int *status, *iters;
@@ -72,6 +73,8 @@ struct Ctx {
     int R, rr, isl, nisl;
     const int *s_lvl, *s_ftl, *s_scl;   // level pointers staged in shared memory
     int *flag;                          // shared scratch word for CTA-uniform decisions
+    double *vs;                         // shared-memory substitution vector (nullptr: use global memory)
+    double *Lrow;                       // row-ordered copy of the scaled factor (forward substitution)
     double reftol;                      // iterative refinement stops once |residual|_inf <= reftol*(1+|rhs|_inf)
     double *red;   // shared: [8][IPM_NT_MAX/32][IPM_MAXG]
     double *out;   // shared: [8][IPM_MAXG]
@@ -225,16 +228,103 @@ __device__ void kkt_factor(const IpmProgram &P, const Ctx &c, double *Y, double 
         }
         __syncthreads();
         for (int w = c.s_scl[lv] + c.slot; w < c.s_scl[lv + 1]; w += c.nslots) {
-            const int q = P.sc_pos[w];
-            Ls[GI(q)] = Y[GI(q)] * invD[GI(P.sc_col[w])];
+            const int4 it = P.sc_item[w];
+            const double lv_ = Y[GI(it.x)] * invD[GI(it.y)];
+            Ls[GI(it.x)] = lv_;
+            c.Lrow[GI(it.z)] = lv_;
         }
         __syncthreads();
     }
 }
 
+// ---- shared-memory, prefetching substitution ------------------------------------------------------------
+// The vector lives in shared memory; L values are read in the order each sweep consumes them (row-ordered copy
+// Lrow forward, column-ordered Ls backward) and the NEXT level's item, indices and values are loaded before the
+// barrier of the current level, so that after a barrier only shared-memory traffic is on the critical path.
+#define IPM_PF 2
+struct SolvePre {
+    int node, k0, k1;
+    int idx[IPM_PF];
+    double val[IPM_PF];
+};
+
+__device__ __forceinline__ void solve_prefetch(const Ctx &c, const int4 *items, const int *idxarr, const double *vals,
+                                               int w, int wend, SolvePre &q)
+{
+    const int G = c.G, sg = c.sg;
+    q.node = -1;
+    if (w < wend) {
+        const int4 it = items[w];
+        q.node = it.x; q.k0 = it.y + c.rr; q.k1 = it.z;
+#pragma unroll
+        for (int j = 0; j < IPM_PF; j++) {
+            const int k = q.k0 + j * c.R;
+            if (k < q.k1) { q.idx[j] = idxarr[k]; q.val[j] = vals[GI(k)]; }
+        }
+    }
+}
+
+__device__ __forceinline__ void solve_consume(const Ctx &c, const int *idxarr, const double *vals, double *vs,
+                                              const SolvePre &q)
+{
+    const int G = c.G, sg = c.sg;
+    double part = 0.0;
+    if (q.node >= 0) {
+#pragma unroll
+        for (int j = 0; j < IPM_PF; j++)
+            if (q.k0 + j * c.R < q.k1) part = fma(q.val[j], vs[q.idx[j] * G + sg], part);
+        for (int k = q.k0 + IPM_PF * c.R; k < q.k1; k += c.R) part = fma(vals[GI(k)], vs[idxarr[k] * G + sg], part);
+    }
+    part = lanes_sum(c, part);
+    if (q.node >= 0 && c.rr == 0) vs[q.node * G + sg] -= part;
+}
+
+__device__ void kkt_ldl_solve_smem(const IpmProgram &P, const Ctx &c, const double *Ls, const double *invD, double *v)
+{
+    const int G = c.G, sg = c.sg;
+    double *vs = c.vs;
+    for (int i = c.slot; i < P.nk; i += c.nslots) vs[i * G + sg] = v[GI(i)];
+    SolvePre cur, nxt;
+    // forward: level 0 rows are empty (leaves have no dependencies)
+    solve_prefetch(c, P.fw_item, P.Lr_col, c.Lrow, c.s_lvl[1] + c.isl, P.nlevels > 1 ? c.s_lvl[2] : 0, cur);
+    __syncthreads();
+    for (int lv = 1; lv < P.nlevels; lv++) {
+        const int wend = c.s_lvl[lv + 1];
+        if (lv + 1 < P.nlevels) solve_prefetch(c, P.fw_item, P.Lr_col, c.Lrow, c.s_lvl[lv + 1] + c.isl, c.s_lvl[lv + 2], nxt);
+        else nxt.node = -1;
+        solve_consume(c, P.Lr_col, c.Lrow, vs, cur);
+        for (int w0 = c.s_lvl[lv] + c.nisl; w0 < wend; w0 += c.nisl) {   // wide levels: further passes
+            SolvePre q;
+            solve_prefetch(c, P.fw_item, P.Lr_col, c.Lrow, w0 + c.isl, wend, q);
+            solve_consume(c, P.Lr_col, c.Lrow, vs, q);
+        }
+        __syncthreads();
+        cur = nxt;
+    }
+    for (int i = c.slot; i < P.nk; i += c.nslots) vs[i * G + sg] *= invD[GI(i)];
+    solve_prefetch(c, P.bw_item, P.L_ri, Ls, c.s_lvl[P.nlevels - 1] + c.isl, c.s_lvl[P.nlevels], cur);
+    __syncthreads();
+    for (int lv = P.nlevels - 1; lv >= 0; lv--) {
+        const int wend = c.s_lvl[lv + 1];
+        if (lv > 0) solve_prefetch(c, P.bw_item, P.L_ri, Ls, c.s_lvl[lv - 1] + c.isl, c.s_lvl[lv], nxt);
+        else nxt.node = -1;
+        solve_consume(c, P.L_ri, Ls, vs, cur);
+        for (int w0 = c.s_lvl[lv] + c.nisl; w0 < wend; w0 += c.nisl) {
+            SolvePre q;
+            solve_prefetch(c, P.bw_item, P.L_ri, Ls, w0 + c.isl, wend, q);
+            solve_consume(c, P.L_ri, Ls, vs, q);
+        }
+        __syncthreads();
+        cur = nxt;
+    }
+    for (int i = c.slot; i < P.nk; i += c.nslots) v[GI(i)] = vs[i * G + sg];
+    __syncthreads();
+}
+
 // in-place solve of (L D L') v = rhs on the permuted vector v
 __device__ void kkt_ldl_solve(const IpmProgram &P, const Ctx &c, const double *Ls, const double *invD, double *v)
 {
+    if (c.vs) { kkt_ldl_solve_smem(P, c, Ls, invD, v); return; }
     const int G = c.G, sg = c.sg;
     for (int lv = 0; lv < P.nlevels; lv++) {   // forward, rows of L
         const int wend = c.s_lvl[lv + 1];
@@ -610,6 +700,7 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
     __syncthreads();
     Ctx c;
     c.s_lvl = s_lv; c.s_ftl = s_lv + P.nlevels + 1; c.s_scl = s_lv + 2 * (P.nlevels + 1);
+    c.vs = D.vsmem ? (double *)(s_lv + ((3 * (P.nlevels + 1) + 3) & ~3)) : nullptr;
     c.G = D.G; c.tid = threadIdx.x; c.sg = c.tid % c.G; c.slot = c.tid / c.G; c.nslots = NT / c.G; c.nwarps = NT / 32;
     c.flag = &s_flag; c.reftol = O.reftol;
     c.R = D.R; c.rr = c.slot % c.R; c.isl = c.slot / c.R; c.nisl = c.nslots / c.R;
@@ -633,6 +724,7 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
     const int nm = (P.n > P.m ? P.n : P.m);
     double *e1 = GP(D.e1, nm), *e2 = GP(D.e2, P.p), *rhs = GP(D.rhs, P.nk);
     double *Y = GP(D.Y, P.nnzL + P.nk), *Ls = GP(D.Ls, P.nnzL + 1), *invD = GP(D.invD, P.nk);
+    c.Lrow = GP(D.Lrow, P.nnzL + 1);
 #undef GP
 
     if (c.tid < G) { s_done[c.tid] = 0; s_status[c.tid] = IPM_MAXIT; s_iters[c.tid] = 0; s_best[c.tid] = CUDART_INF; s_save[c.tid] = 0; s_stall[c.tid] = 0; }

@@ -53,6 +53,7 @@ struct ConeSymbolic {
     std::vector<int> Lr_pc;              // int2 per L entry in row order: {position, column}
     std::vector<int> ft_item;            // int4 per factor target: {target id, op start, op end, sign}
     std::vector<int> ft_op;              // int2 per op: {a, b}
+    std::vector<int> sc_item;            // int4 per scaled entry: {position, column, row-order position, 0}
     long long factor_ops = 0;
     std::string err;
 };
@@ -307,6 +308,15 @@ inline bool cone_symbolic_build(ConeSymbolic &S, int n, int p, int m, const int 
         const int t = S.ft_target[w];
         S.ft_item[4 * w] = t; S.ft_item[4 * w + 1] = S.ft_op_ptr[w]; S.ft_item[4 * w + 2] = S.ft_op_ptr[w + 1];
         S.ft_item[4 * w + 3] = S.as_sign[t];
+    }
+    {
+        std::vector<int> rowpos(S.nnzL);
+        for (int w = 0; w < S.nnzL; w++) rowpos[S.Lr_pos[w]] = w;
+        S.sc_item.resize(4 * S.sc_pos.size());
+        for (size_t w = 0; w < S.sc_pos.size(); w++) {
+            S.sc_item[4 * w] = S.sc_pos[w]; S.sc_item[4 * w + 1] = S.sc_col[w];
+            S.sc_item[4 * w + 2] = rowpos[S.sc_pos[w]]; S.sc_item[4 * w + 3] = 0;
+        }
     }
     S.ft_op.resize(2 * S.ft_op_a.size());
     for (size_t k = 0; k < S.ft_op_a.size(); k++) { S.ft_op[2 * k] = S.ft_op_a[k]; S.ft_op[2 * k + 1] = S.ft_op_b[k]; }
