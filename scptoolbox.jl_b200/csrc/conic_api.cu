@@ -10,7 +10,7 @@ struct scpb_cone_s {
     IpmProgram P{};
     std::vector<void *> dev_ints;
     // data buffers (grow-only), sized for (ngroups*G) seeds
-    int capB = 0, capG = 0;
+    int capB = 0, capG = 0, lanes = 0;
     std::vector<double *> bufs;
     IpmData D{};
     double *stage = nullptr;  // seed-major staging on device
@@ -62,7 +62,7 @@ static int cone_reserve(scpb_cone_s *c, int B, int G)
 {
     scpb_handle_s *h = c->h;
     const int ng = (B + G - 1) / G, Bpad = ng * G;
-    c->D.R = std::max(1, std::min(8, 32 / G));
+    c->D.R = std::max(1, std::min(c->lanes > 0 ? c->lanes : 2, 32 / G));
     if (c->capB >= Bpad && c->capG == G) { c->D.B = B; c->D.G = G; return SCPB_OK; }
     for (double *p : c->bufs) cudaFree(p);
     c->bufs.clear();
@@ -141,7 +141,7 @@ IpmOpts scpb_internal_make_opts(const scpb_cone_opts *o)
     return r;
 }
 
-int scpb_internal_cone_reserve(scpb_cone_s *c, int B, int G) { return cone_reserve(c, B, G); }
+int scpb_internal_cone_reserve(scpb_cone_s *c, int B, int G, int lanes) { c->lanes = lanes; return cone_reserve(c, B, G); }
 IpmData *scpb_internal_cone_data(scpb_cone_s *c) { return &c->D; }
 const ConeSymbolic *scpb_internal_cone_sym(scpb_cone_s *c) { return &c->S; }
 scpb_handle_s *scpb_internal_cone_handle(scpb_cone_s *c) { return c->h; }
@@ -225,6 +225,7 @@ int32_t scpb_cone_solve(scpb_cone c, int32_t B, const double *Avals, const doubl
     if (B <= 0 || !cvec || (c->S.p > 0 && !bvec) || (c->S.m > 0 && !hvec)) return set_err(h, SCPB_ERR_ARG, "cone_solve: bad arguments");
     SCPB_CUDA(h, cudaSetDevice(h->device));
     const int G = scpb_internal_pick_group(B, opts ? opts->group : 0);
+    c->lanes = opts ? opts->lanes : 0;
     int rc = cone_reserve(c, B, G);
     if (rc) return rc;
     const ConeSymbolic &S = c->S;

@@ -206,13 +206,16 @@ __device__ void kkt_factor(const IpmProgram &P, const Ctx &c, double *Y, double 
                 if (c.rr == 0) y0t = Y[GI(item.x)];
                 const int k1 = item.z;
                 int k = item.y + c.rr;
-                for (; k + c.R < k1; k += 2 * c.R) {   // two independent gathers in flight
-                    const int2 o0 = P.ft_op[k], o1 = P.ft_op[k + c.R];
+                for (; k + 3 * c.R < k1; k += 4 * c.R) {   // four independent gathers in flight
+                    const int2 o0 = P.ft_op[k], o1 = P.ft_op[k + c.R], o2 = P.ft_op[k + 2 * c.R], o3 = P.ft_op[k + 3 * c.R];
                     const double ya = Y[GI(o0.x)], la = Ls[GI(o0.y)], yb = Y[GI(o1.x)], lb = Ls[GI(o1.y)];
+                    const double yc = Y[GI(o2.x)], lc = Ls[GI(o2.y)], yd = Y[GI(o3.x)], ld = Ls[GI(o3.y)];
                     part = fma(ya, la, part);
                     part = fma(yb, lb, part);
+                    part = fma(yc, lc, part);
+                    part = fma(yd, ld, part);
                 }
-                if (k < k1) { const int2 o0 = P.ft_op[k]; part = fma(Y[GI(o0.x)], Ls[GI(o0.y)], part); }
+                for (; k < k1; k += c.R) { const int2 o0 = P.ft_op[k]; part = fma(Y[GI(o0.x)], Ls[GI(o0.y)], part); }
             }
             part = lanes_sum(c, part);
             if (on && c.rr == 0) {
@@ -241,7 +244,7 @@ __device__ void kkt_factor(const IpmProgram &P, const Ctx &c, double *Y, double 
 // The vector lives in shared memory; L values are read in the order each sweep consumes them (row-ordered copy
 // Lrow forward, column-ordered Ls backward) and the NEXT level's item, indices and values are loaded before the
 // barrier of the current level, so that after a barrier only shared-memory traffic is on the critical path.
-#define IPM_PF 2
+#define IPM_PF 4
 struct SolvePre {
     int node, k0, k1;
     int idx[IPM_PF];

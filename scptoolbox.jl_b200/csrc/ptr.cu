@@ -17,7 +17,7 @@
 // pieces of conic_api.cu used here
 struct scpb_cone_s;
 int scpb_internal_cone_run(scpb_cone_s *c, const IpmOpts &o);
-int scpb_internal_cone_reserve(scpb_cone_s *c, int B, int G);
+int scpb_internal_cone_reserve(scpb_cone_s *c, int B, int G, int lanes);
 IpmData *scpb_internal_cone_data(scpb_cone_s *c);
 const ConeSymbolic *scpb_internal_cone_sym(scpb_cone_s *c);
 scpb_handle_s *scpb_internal_cone_handle(scpb_cone_s *c);
@@ -323,7 +323,7 @@ int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *u
     SCPB_CUDA(h, cudaSetDevice(h->device));
     const scpb_ptr_desc &d = s->d;
     const int G = scpb_internal_pick_group(B, opts ? opts->group : 0);
-    int rc = scpb_internal_cone_reserve(s->cone, B, G);
+    int rc = scpb_internal_cone_reserve(s->cone, B, G, opts ? opts->lanes : 0);
     if (rc) return rc;
     if ((rc = ptr_reserve(s, B, G))) return rc;
     IpmData *D = scpb_internal_cone_data(s->cone);

@@ -57,7 +57,7 @@ SIGNATURES = {
 class ConeOpts(C.Structure):
     _fields_ = [("feastol", C.c_double), ("abstol", C.c_double), ("reltol", C.c_double),
                 ("delta", C.c_double), ("delta_dyn", C.c_double), ("maxit", C.c_int32), ("nref", C.c_int32),
-                ("verbose", C.c_int32), ("group", C.c_int32), ("equil", C.c_int32), ("threads", C.c_int32)]
+                ("verbose", C.c_int32), ("group", C.c_int32), ("equil", C.c_int32), ("threads", C.c_int32), ("lanes", C.c_int32)]
 
 
 class PtrDesc(C.Structure):
