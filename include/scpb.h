@@ -99,7 +99,7 @@ typedef struct {
     int32_t group;                  /* seeds per CTA (power of two <= 32); 0 = automatic */
     int32_t equil;                  /* Ruiz equilibration passes; <0: default 5, 0: off    */
     int32_t threads;                /* threads per CTA: 1024 (default) or 512              */
-    int32_t lanes;                  /* lanes cooperating on one sparse row (1,2,4,8); 0: 2 */
+    int32_t lanes;                  /* lanes cooperating on one sparse row (1,2,4,8); 0: 8 */
 } scpb_cone_opts;
 
 /* per-seed status (termination_status, program.jl:427-428): */

@@ -62,7 +62,7 @@ static int cone_reserve(scpb_cone_s *c, int B, int G)
 {
     scpb_handle_s *h = c->h;
     const int ng = (B + G - 1) / G, Bpad = ng * G;
-    c->D.R = std::max(1, std::min(c->lanes > 0 ? c->lanes : 2, 32 / G));
+    c->D.R = std::max(1, std::min(c->lanes > 0 ? c->lanes : 8, 32 / G));
     if (c->capB >= Bpad && c->capG == G) { c->D.B = B; c->D.G = G; return SCPB_OK; }
     for (double *p : c->bufs) cudaFree(p);
     c->bufs.clear();
@@ -137,7 +137,7 @@ IpmOpts scpb_internal_make_opts(const scpb_cone_opts *o)
     r.equil = (o && o->equil >= 0) ? o->equil : 5;
     r.threads = (o && o->threads > 0) ? o->threads : 1024;
     r.nref_aff = 0;
-    r.reftol = 1e-13;
+    r.reftol = 1e-12;
     return r;
 }
 

@@ -841,7 +841,7 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
                 if (!(isfinite(pres) && isfinite(dres) && isfinite(gap))) { s_done[q] = 1; s_status[q] = IPM_NUMERICAL; }
                 else if (pres <= O.feastol && dres <= O.feastol && (gap <= O.abstol || relgap <= O.reltol)) {
                     s_done[q] = 1; s_status[q] = IPM_OPTIMAL;
-                } else if (s_stall[q] >= 4 && s_best[q] <= 1e-6) { s_done[q] = 1; s_status[q] = IPM_NUMERICAL; }  // numerical floor
+                } else if (s_stall[q] >= 2 && s_best[q] <= 1e-6) { s_done[q] = 1; s_status[q] = IPM_NUMERICAL; }  // numerical floor
                 else if (it == O.maxit) { s_done[q] = 1; s_status[q] = IPM_MAXIT; }
             }
         }
