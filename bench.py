@@ -87,6 +87,18 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def effective_cores():
+    """Host cores this container may actually use: min(visible CPUs, cgroup cpu.max quota)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(round(int(q) / int(per)))))
+    except Exception:
+        pass
+    return n
+
+
 def measured_peak():
     try:
         return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
@@ -154,11 +166,11 @@ def run_reference(args, rank):
     threads, one seed per process, on a bounded sample of the same workload."""
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = effective_cores()
     pb, g = oracle_base_guess(args.N)
     from oracle import ptr as optr
     sc = optr.Scaling(pb)
-    nseeds = args.cpu_seeds or min(args.batch, cores)
+    nseeds = args.cpu_seeds or min(args.batch, 2 * cores)
     X, U, P = make_seeds(g, sc.Sx, sc.Su, nseeds, 0)
     vals, walls = [], []
     cpu_run(args.N, args.Nsub, pb.hs, X[:min(8, nseeds)], U[:min(8, nseeds)], P[:min(8, nseeds)], min(cores, 8))  # warm-up
@@ -173,8 +185,9 @@ def run_reference(args, rank):
             "config": {"workload": f"starship_flip PTR N={args.N} Nsub={args.Nsub}", "batch_per_gpu": args.batch,
                        "ptr": PTR},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{nseeds} of {args.batch} seeds per step, one process per seed "
-                                       f"(oracle: C discretize + Python formulate + HiGHS LP)",
+                             "sample": f"{nseeds} of {args.batch} seeds per step, one single-threaded process per core "
+                                       f"(oracle: C discretize + Python formulate + HiGHS LP); cores = "
+                                       f"min(visible CPUs {os.cpu_count()}, cgroup cpu.max quota)",
                              "phase_cpu_seconds": ph},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -270,14 +283,15 @@ def run_ours(args, rank, local_rank, world):
         # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ----
         cpu = None
         if world == 1:
-            cores = os.cpu_count() or 1
-            nseeds = args.cpu_seeds or min(B, cores)
+            cores = effective_cores()
+            nseeds = args.cpu_seeds or min(B, 2 * cores)
             from oracle import ptr as optr, problems
             pbo = problems.StarshipProblem(N); pbo.hs = mdl.hs
             cits, cwall, cph, _ = cpu_run(N, Nsub, mdl.hs, X[:nseeds], U[:nseeds], P[:nseeds], min(cores, nseeds))
             cpu = {"value": cits / cwall, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{nseeds} of {B} seeds, full PTR solve each, one process per seed "
-                             f"(oracle: C discretize + Python formulate + HiGHS LP)",
+                   "sample": f"{nseeds} of {B} seeds, full PTR solve each, one single-threaded process per core "
+                             f"(oracle: C discretize + Python formulate + HiGHS LP); cores = min(visible CPUs "
+                             f"{os.cpu_count()}, cgroup cpu.max quota)",
                    "phase_cpu_seconds": cph}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
                 "ms_per_step": 1e3 * dev_t / args.steps, "higher_is_better": True, "scaling": "weak",
