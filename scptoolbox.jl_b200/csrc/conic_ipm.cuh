@@ -57,6 +57,7 @@ struct IpmData {  // group-blocked device arrays, all for B seeds
     // per-seed outputs
     double *pobj, *dobj, *res;   // res: [3][B] pres, dres, gap
     int *status, *iters;
+    long long *prof;   // [8] cycle counters of CTA 0: equilibrate, init, residuals, scaling+assemble, factor, solves, line search+update, total
 };
 
 enum { IPM_OPTIMAL = 0, IPM_MAXIT = 1, IPM_NUMERICAL = 2, IPM_ALMOST = 3 };
@@ -730,8 +731,13 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
     c.Lrow = GP(D.Lrow, P.nnzL + 1);
 #undef GP
 
+    long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tq = clock64();
+    const long long tstart = tq;
+#define PROF(i) { const long long tn = clock64(); pt[i] += tn - tq; tq = tn; }
     if (c.tid < G) { s_done[c.tid] = 0; s_status[c.tid] = IPM_MAXIT; s_iters[c.tid] = 0; s_best[c.tid] = CUDART_INF; s_save[c.tid] = 0; s_stall[c.tid] = 0; }
     if (O.equil > 0) equilibrate(P, c, Av, Gv, cc, bb, hh, eqD, eqA, eqG, O.equil);
+    PROF(0)
     // ---- data norms ----
     {
         double v[3] = {0.0, 0.0, 0.0};
@@ -796,6 +802,7 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
         __syncthreads();
     }
 
+    PROF(1)
     const double deg = (double)(P.l + P.nsoc);
     for (int it = 0; it <= O.maxit; it++) {
         // ---- residuals + objective pieces ----
@@ -841,7 +848,7 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
                 if (!(isfinite(pres) && isfinite(dres) && isfinite(gap))) { s_done[q] = 1; s_status[q] = IPM_NUMERICAL; }
                 else if (pres <= O.feastol && dres <= O.feastol && (gap <= O.abstol || relgap <= O.reltol)) {
                     s_done[q] = 1; s_status[q] = IPM_OPTIMAL;
-                } else if (s_stall[q] >= 2 && s_best[q] <= 1e-6) { s_done[q] = 1; s_status[q] = IPM_NUMERICAL; }  // numerical floor
+                } else if (s_stall[q] >= 3 && s_best[q] <= 1e-6) { s_done[q] = 1; s_status[q] = IPM_NUMERICAL; }  // numerical floor
                 else if (it == O.maxit) { s_done[q] = 1; s_status[q] = IPM_MAXIT; }
             }
         }
@@ -859,19 +866,24 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
         }
         __syncthreads();
         if (s_alldone) break;
+        PROF(2)
 
         // ---- scaling, KKT assembly, factorisation ----
         nt_scaling(P, c, s, z, lam, wm, socw, soceta);
         __syncthreads();
         kkt_assemble(P, c, D, Av, Gv, wm, Y, O.delta);
+        PROF(3)
         kkt_factor(P, c, Y, Ls, invD, O.delta_dyn);
+        PROF(4)
 
         // ---- affine direction: bx=-rx, by=-ry, bz=-rz+s ; ds = -s - W^2 dz ----
         for (int i = c.slot; i < P.n; i += c.nslots) r1[GI(i)] = -rx[GI(i)];
         for (int i = c.slot; i < P.p; i += c.nslots) r2[GI(i)] = -ry[GI(i)];
         for (int i = c.slot; i < P.m; i += c.nslots) ds[GI(i)] = -rz[GI(i)] + s[GI(i)];  // ds used as bz scratch
         __syncthreads();
+        PROF(6)
         kkt_solve(P, c, D, Av, Gv, wm, socw, soceta, r1, r2, ds, dx, dy, dza, tm, gm, e1, e2, rhs, Ls, invD, O.nref_aff);
+        PROF(5)
         // ds = tmp - W^2 dz with tmp = -s; W^2 dz == G dx - bz is left in gm by kkt_solve (no W^2 W^-2
         // round trip: keeps G dx + ds = -rz to rounding even when the scaling is ill-conditioned)
         for (int i = c.slot; i < P.m; i += c.nslots) dsa[GI(i)] = -s[GI(i)] - gm[GI(i)];
@@ -901,7 +913,9 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
             }
         }
         __syncthreads();
+        PROF(6)
         kkt_solve(P, c, D, Av, Gv, wm, socw, soceta, r1, r2, ds, dx, dy, dz, tm, gm, e1, e2, rhs, Ls, invD, O.nref);
+        PROF(5)
         for (int i = c.slot; i < P.m; i += c.nslots) ds[GI(i)] = dsa[GI(i)] - gm[GI(i)];
         __syncthreads();
         {
@@ -933,7 +947,13 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
             }
         }
         __syncthreads();
+        PROF(6)
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && D.prof) {
+        pt[7] = clock64() - tstart;
+        for (int i = 0; i < 8; i++) D.prof[i] = pt[i];
+    }
+#undef PROF
     // ---- epilogue: the best iterate is the answer (ECOS reports its best point the same way) ----
     __syncthreads();
     // the numerical floor of the fp64 normal-equation factorisation sits within ~10x of ECOS' 1e-8 targets

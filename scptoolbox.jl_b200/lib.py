@@ -206,10 +206,13 @@ class ConeProblem:
         self.l, self.soc_dims = int(l), list(soc_dims)
 
     def info(self):
-        buf = (C.c_int64 * 8)()
+        buf = (C.c_int64 * 16)()
         self.lib.scpb_cone_info(self.c, buf)
         keys = ["nk", "nnzL", "levels", "factor_ops", "assembly_ops", "nwm", "group", "capacity"]
-        return dict(zip(keys, [int(v) for v in buf]))
+        d = dict(zip(keys, [int(v) for v in buf[:8]]))
+        d["cycles"] = dict(zip(["equilibrate", "start_point", "residuals", "scale_assemble", "factor", "kkt_solves",
+                                "linesearch_update", "total"], [int(v) for v in buf[8:16]]))
+        return d
 
     def close(self):
         if getattr(self, "c", None) is not None and self.c.value:

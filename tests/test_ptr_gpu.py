@@ -2,9 +2,10 @@
 PTR loop (oracle/ptr.py with the oracle IPM standing in for ECOS) on the same initial guesses.
 
 Stated tolerance (measured floor of round 1): final augmented cost 1e-6 relative,
-iteration counts equal (+-1), states/parameters 2e-3 and thrust/gimbal inputs 2e-2 of their ranges (the LP
-subproblem has flat directions, so two interior-point codes that stop at different duality gaps agree on the cost
-far better than on the minimiser); both must report SCP_SOLVED.  North-star target is 1e-6 on the trajectory."""
+iteration counts equal (+-1), physical states / thrust / gimbal angle / parameters within 1e-4 of their ranges
+(measured: 4e-7 .. 1e-5); the auxiliary gimbal-rate pair (x[7], u[2]) is a flat direction of the LP subproblem (two
+interior-point codes agree on it only to ~1e-2) and is reported, not asserted.  Both must report SCP_SOLVED.
+North-star target is 1e-6 on the trajectory."""
 import numpy as np
 import pytest
 
@@ -24,18 +25,22 @@ def _setup(pkg, handle, N, Nsub, iter_max=15):
     return mdl, traj, pars
 
 
-def test_initial_guess_matches_oracle(pkg, handle):
+def test_initial_guess_generator(pkg, handle):
+    """starship_initial_guess (definition.jl:97-445) with the terminal-descent SOCPs solved as one batch on the GPU
+    cone solver: the flip phase must equal the oracle's, the descent phase must be a valid descent."""
     N = 12
     mdl, traj, pars = _setup(pkg, handle, N, 40)
-    xg, ug, pg = traj.guess(N)          # phase-2 SOCPs solved as one batch on the GPU cone solver
+    xg, ug, pg = traj.guess(N)
     pbo = problems.StarshipProblem(N)
     xo, uo, po = pbo.guess(N)
-    assert abs(pg[1] - po[1]) <= 1.0 and abs(pg[0] - po[0]) < 1e-9      # same flip time; descent time within one 1-s candidate step
-    assert abs(mdl.hs - pbo.hs) < 1e-9
-    sx = np.array([r[1] - r[0] for r in pbo.ranges()[0]])
-    # the terminal-descent SOCP has flat directions: two interior-point codes agree to ~3e-3 of the ranges
-    assert np.abs((xg - xo) / sx).max() < 1e-2
-    assert np.abs((ug[:, 0] - uo[:, 0]) / 1e6).max() < 5e-2
+    assert abs(pg[0] - po[0]) < 1e-9 and abs(mdl.hs - pbo.hs) < 1e-9      # same flip time and switch altitude
+    assert abs(pg[1] - po[1]) <= 1.0                                       # descent time within one 1-s candidate step
+    k1 = int(np.sum(np.arange(N) / (N - 1) <= mdl.tau_s))
+    assert np.abs(xg[:k1, :6] - xo[:k1, :6]).max() < 1e-9 and np.abs(ug[:k1] - uo[:k1]).max() < 1e-6
+    # descent phase: ends at rest on the pad, stays above ground, thrust within the single-engine bounds
+    assert np.abs(xg[-1, 0:2]).max() < 1e-3 and np.abs(xg[-1, 2:4] - mdl.vf).max() < 1e-3
+    assert xg[k1:, 1].min() > -1e-6
+    assert (ug[k1:, 0] <= mdl.T_max1 * (1 + 1e-6)).all() and (ug[k1:, 0] >= mdl.T_min1 * (1 - 1e-6)).all()
 
 
 @pytest.mark.parametrize("N,Nsub,nb", [(12, 60, 4), (31, 100, 3)])
@@ -63,11 +68,13 @@ def test_batched_ptr_matches_oracle_ptr(pkg, handle, N, Nsub, nb):
         ex = np.abs((sol.xd[b] - rs.xd) / sc.Sx).max()
         eu = np.abs((sol.ud[b] - rs.ud) / sc.Su).max()
         ep = np.abs((sol.p[b] - rs.p) / sc.Sp).max()
-        # states and parameters are pinned by the dynamics; the gimbal-rate input has flat directions in this LP
-        # (it only enters two-sided rate constraints), so inputs are compared on thrust and gimbal angle
+        # physical states, thrust, gimbal angle and parameters are pinned by the dynamics; the auxiliary pair
+        # (delayed gimbal angle x[7], gimbal rate u[2]) of the rate-limit approximation (definition.jl:544,740-743)
+        # is a flat direction of the LP subproblem and is reported but not asserted
+        ex7 = np.abs((sol.xd[b][:, :7] - rs.xd[:, :7]) / sc.Sx[:7]).max()
         eu2 = np.abs((sol.ud[b][:, :2] - rs.ud[:, :2]) / sc.Su[:2]).max()
-        print("parity seed", b, "ex", ex, "eu(T,delta)", eu2, "eu(all)", eu, "ep", ep)
-        assert max(ex, ep) <= 2e-3 and eu2 <= 2e-2, (b, ex, eu, ep, sol.iterations[b], ref["iterations"])
+        print("parity seed", b, "ex(phys)", ex7, "eu(T,delta)", eu2, "ex(all)", ex, "eu(all)", eu, "ep", ep)
+        assert max(ex7, eu2, ep) <= 1e-4, (b, ex7, eu2, ep, sol.iterations[b], ref["iterations"])
         assert abs(sol.cost[b] - rs.J_aug) <= 1e-6 * max(1.0, abs(rs.J_aug))
         assert abs(int(sol.iterations[b]) - ref["iterations"]) <= 1
         assert bool(sol.feas[b]) == rs.feas
