@@ -111,7 +111,7 @@ int scpb_internal_cone_run(scpb_cone_s *c, const IpmOpts &o)
     const int ng = (c->D.B + c->D.G - 1) / c->D.G;
     // dynamic shared memory: level pointers (+ the substitution vector when nk*G doubles fit next to the
     // ~20 KB of static shared memory; B200 allows 227 KB per CTA)
-    size_t smem = sizeof(int) * ((3 * (size_t)(c->S.nlevels + 1) + 3) & ~(size_t)3);
+    size_t smem = sizeof(int) * ((5 * (size_t)(c->S.nlevels + 1) + 3) & ~(size_t)3);
     const size_t vbytes = sizeof(double) * (size_t)c->S.nk * c->D.G;
     c->D.vsmem = (smem + vbytes <= 200 * 1024) ? 1 : 0;
     if (c->D.vsmem) smem += vbytes;

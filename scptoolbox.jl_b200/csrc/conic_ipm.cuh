@@ -71,8 +71,10 @@ struct Ctx {
     int G, sg, slot, nslots, tid, nwarps;
     // row-type work (sparse dot products): R lanes cooperate on one row for the G seeds of the group;
     // lane layout inside a warp: tid = (item*R + rr)*G + sg, reduced with xor-shuffles over rr
-    int R, rr, isl, nisl;
+    int R, rr, isl, nisl;               // current per-level values, see set_lanes()
+    const int *s_Rs, *s_Rf;             // per-level lanes-per-row for the substitutions / the factorisation
     const int *s_lvl, *s_ftl, *s_scl;   // level pointers staged in shared memory
+    int Rmax;
     int *flag;                          // shared scratch word for CTA-uniform decisions
     double *vs;                         // shared-memory substitution vector (nullptr: use global memory)
     double *Lrow;                       // row-ordered copy of the scaled factor (forward substitution)
@@ -117,6 +119,21 @@ __device__ __forceinline__ void seed_reduce(const Ctx &c, double (&v)[K], int op
 }
 
 #define GI(e) ((size_t)(e) * G + sg)
+
+// choose how many lanes cooperate on one row for a level: as many as keep the level within the minimum
+// number of passes over the CTA (wide leaf levels -> 1 lane per row, narrow separator levels -> 8)
+__device__ __forceinline__ int level_lanes(int width, int nslots, int rmax)
+{
+    if (width <= 0) return rmax;
+    const int passes = (width + nslots - 1) / nslots;
+    int r = 1;
+    while (2 * r <= rmax && (long long)width * (2 * r) <= (long long)nslots * passes) r *= 2;
+    return r;
+}
+__device__ __forceinline__ void set_lanes(Ctx &c, int R)
+{
+    c.R = R; c.rr = c.slot % R; c.isl = c.slot / R; c.nisl = c.nslots / R;
+}
 
 // sum over the R lanes that share a row (offsets G, 2G, .. (R/2)G inside the warp)
 __device__ __forceinline__ double lanes_sum(const Ctx &c, double a)
@@ -192,10 +209,11 @@ __device__ void kkt_assemble(const IpmProgram &P, const Ctx &c, const IpmData &D
     __syncthreads();
 }
 
-__device__ void kkt_factor(const IpmProgram &P, const Ctx &c, double *Y, double *Ls, double *invD, double delta_dyn)
+__device__ void kkt_factor(const IpmProgram &P, Ctx &c, double *Y, double *Ls, double *invD, double delta_dyn)
 {
     const int G = c.G, sg = c.sg;
     for (int lv = 0; lv < P.nlevels; lv++) {
+        set_lanes(c, c.s_Rf[lv]);
         const int wend = c.s_ftl[lv + 1];
         for (int w0 = c.s_ftl[lv]; w0 < wend; w0 += c.nisl) {   // uniform trip count: shuffles inside
             const int w = w0 + c.isl;
@@ -283,19 +301,23 @@ __device__ __forceinline__ void solve_consume(const Ctx &c, const int *idxarr, c
     if (q.node >= 0 && c.rr == 0) vs[q.node * G + sg] -= part;
 }
 
-__device__ void kkt_ldl_solve_smem(const IpmProgram &P, const Ctx &c, const double *Ls, const double *invD, double *v)
+__device__ void kkt_ldl_solve_smem(const IpmProgram &P, Ctx &c, const double *Ls, const double *invD, double *v)
 {
     const int G = c.G, sg = c.sg;
     double *vs = c.vs;
     for (int i = c.slot; i < P.nk; i += c.nslots) vs[i * G + sg] = v[GI(i)];
     SolvePre cur, nxt;
     // forward: level 0 rows are empty (leaves have no dependencies)
+    if (P.nlevels > 1) set_lanes(c, c.s_Rs[1]);
     solve_prefetch(c, P.fw_item, P.Lr_col, c.Lrow, c.s_lvl[1] + c.isl, P.nlevels > 1 ? c.s_lvl[2] : 0, cur);
     __syncthreads();
     for (int lv = 1; lv < P.nlevels; lv++) {
         const int wend = c.s_lvl[lv + 1];
-        if (lv + 1 < P.nlevels) solve_prefetch(c, P.fw_item, P.Lr_col, c.Lrow, c.s_lvl[lv + 1] + c.isl, c.s_lvl[lv + 2], nxt);
-        else nxt.node = -1;
+        if (lv + 1 < P.nlevels) {
+            set_lanes(c, c.s_Rs[lv + 1]);
+            solve_prefetch(c, P.fw_item, P.Lr_col, c.Lrow, c.s_lvl[lv + 1] + c.isl, c.s_lvl[lv + 2], nxt);
+        } else nxt.node = -1;
+        set_lanes(c, c.s_Rs[lv]);
         solve_consume(c, P.Lr_col, c.Lrow, vs, cur);
         for (int w0 = c.s_lvl[lv] + c.nisl; w0 < wend; w0 += c.nisl) {   // wide levels: further passes
             SolvePre q;
@@ -306,12 +328,16 @@ __device__ void kkt_ldl_solve_smem(const IpmProgram &P, const Ctx &c, const doub
         cur = nxt;
     }
     for (int i = c.slot; i < P.nk; i += c.nslots) vs[i * G + sg] *= invD[GI(i)];
+    set_lanes(c, c.s_Rs[P.nlevels - 1]);
     solve_prefetch(c, P.bw_item, P.L_ri, Ls, c.s_lvl[P.nlevels - 1] + c.isl, c.s_lvl[P.nlevels], cur);
     __syncthreads();
     for (int lv = P.nlevels - 1; lv >= 0; lv--) {
         const int wend = c.s_lvl[lv + 1];
-        if (lv > 0) solve_prefetch(c, P.bw_item, P.L_ri, Ls, c.s_lvl[lv - 1] + c.isl, c.s_lvl[lv], nxt);
-        else nxt.node = -1;
+        if (lv > 0) {
+            set_lanes(c, c.s_Rs[lv - 1]);
+            solve_prefetch(c, P.bw_item, P.L_ri, Ls, c.s_lvl[lv - 1] + c.isl, c.s_lvl[lv], nxt);
+        } else nxt.node = -1;
+        set_lanes(c, c.s_Rs[lv]);
         solve_consume(c, P.L_ri, Ls, vs, cur);
         for (int w0 = c.s_lvl[lv] + c.nisl; w0 < wend; w0 += c.nisl) {
             SolvePre q;
@@ -326,9 +352,10 @@ __device__ void kkt_ldl_solve_smem(const IpmProgram &P, const Ctx &c, const doub
 }
 
 // in-place solve of (L D L') v = rhs on the permuted vector v
-__device__ void kkt_ldl_solve(const IpmProgram &P, const Ctx &c, const double *Ls, const double *invD, double *v)
+__device__ void kkt_ldl_solve(const IpmProgram &P, Ctx &c, const double *Ls, const double *invD, double *v)
 {
     if (c.vs) { kkt_ldl_solve_smem(P, c, Ls, invD, v); return; }
+    set_lanes(c, c.Rmax);
     const int G = c.G, sg = c.sg;
     for (int lv = 0; lv < P.nlevels; lv++) {   // forward, rows of L
         const int wend = c.s_lvl[lv + 1];
@@ -388,7 +415,7 @@ __device__ void kkt_ldl_solve(const IpmProgram &P, const Ctx &c, const double *L
 //   (G' W^-2 G) dx + A' dy = bx + G' W^-2 bz ,  A dx = by ,  dz = W^-2 (G dx - bz)
 // with nref steps of iterative refinement against the unregularised reduced operator.
 // bx,by,bz are overwritten/consumed: bx -> r1 (in place), by -> r2 (kept), bz kept.
-__device__ void kkt_solve(const IpmProgram &P, const Ctx &c, const IpmData &D, const double *Av, const double *Gv,
+__device__ void kkt_solve(const IpmProgram &P, Ctx &c, const IpmData &D, const double *Av, const double *Gv,
                           const double *wm, const double *socw, const double *soceta, double *bx, const double *by,
                           const double *bz, double *dx, double *dy, double *dz, double *tm, double *gm, double *e1,
                           double *e2, double *rhs, const double *Ls, const double *invD, int nref)
@@ -704,10 +731,18 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
     __syncthreads();
     Ctx c;
     c.s_lvl = s_lv; c.s_ftl = s_lv + P.nlevels + 1; c.s_scl = s_lv + 2 * (P.nlevels + 1);
-    c.vs = D.vsmem ? (double *)(s_lv + ((3 * (P.nlevels + 1) + 3) & ~3)) : nullptr;
+    int *s_R = s_lv + 3 * (P.nlevels + 1);
+    c.s_Rs = s_R; c.s_Rf = s_R + P.nlevels;
+    c.vs = D.vsmem ? (double *)(s_lv + ((5 * (P.nlevels + 1) + 3) & ~3)) : nullptr;
     c.G = D.G; c.tid = threadIdx.x; c.sg = c.tid % c.G; c.slot = c.tid / c.G; c.nslots = NT / c.G; c.nwarps = NT / 32;
     c.flag = &s_flag; c.reftol = O.reftol;
-    c.R = D.R; c.rr = c.slot % c.R; c.isl = c.slot / c.R; c.nisl = c.nslots / c.R;
+    c.Rmax = D.R;
+    set_lanes(c, c.Rmax);
+    for (int i = threadIdx.x; i < P.nlevels; i += NT) {
+        s_R[i] = level_lanes(s_lv[i + 1] - s_lv[i], c.nslots, c.Rmax);
+        s_R[P.nlevels + i] = level_lanes(s_lv[P.nlevels + 1 + i + 1] - s_lv[P.nlevels + 1 + i], c.nslots, c.Rmax);
+    }
+    __syncthreads();
     c.red = s_red; c.out = s_out;
     const int G = c.G, sg = c.sg;
     const size_t g = blockIdx.x;
