@@ -183,6 +183,7 @@ int32_t scpb_cone_setup(scpb_handle h, int32_t n, int32_t p, int32_t m, const in
 #undef UP
     P.fw_item = (const int4 *)upload_ints(c, S.fw_item); P.bw_item = (const int4 *)upload_ints(c, S.bw_item);
     P.ft_item = (const int4 *)upload_ints(c, S.ft_item); P.sc_item = (const int4 *)upload_ints(c, S.sc_item);
+    P.lvl_maxlen = upload_ints(c, S.lvl_maxlen);
     P.Lr_pc = (const int2 *)upload_ints(c, S.Lr_pc); P.ft_op = (const int2 *)upload_ints(c, S.ft_op);
     for (void *d : c->dev_ints)
         if (!d) {

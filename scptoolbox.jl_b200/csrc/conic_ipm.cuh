@@ -30,6 +30,7 @@ struct IpmProgram {  // device copies of ConeSymbolic index arrays
     const int *as_ptr, *as_a, *as_b, *as_c, *as_src, *as_sign;
     const int4 *fw_item, *bw_item, *ft_item, *sc_item;
     const int2 *Lr_pc, *ft_op;
+    const int *lvl_maxlen;   // [3][nlevels]
 };
 
 struct IpmOpts {
@@ -122,13 +123,19 @@ __device__ __forceinline__ void seed_reduce(const Ctx &c, double (&v)[K], int op
 
 // choose how many lanes cooperate on one row for a level: as many as keep the level within the minimum
 // number of passes over the CTA (wide leaf levels -> 1 lane per row, narrow separator levels -> 8)
-__device__ __forceinline__ int level_lanes(int width, int nslots, int rmax)
+__device__ __forceinline__ int level_lanes(int width, int maxlen, int nslots, int rmax, int inflight)
 {
-    if (width <= 0) return rmax;
-    const int passes = (width + nslots - 1) / nslots;
-    int r = 1;
-    while (2 * r <= rmax && (long long)width * (2 * r) <= (long long)nslots * passes) r *= 2;
-    return r;
+    // cost model in units of one memory latency: passes over the CTA, each followed by the sequential part of the
+    // longest row that is not covered by the `inflight` loads a lane keeps in flight
+    int best = 1, bc = 0x7fffffff;
+    for (int r = 1; r <= rmax; r *= 2) {
+        const int passes = (int)(((long long)width * r + nslots - 1) / nslots);
+        const int per_lane = (maxlen + r - 1) / r;
+        const int seq = (per_lane + inflight - 1) / inflight;
+        const int cost = (passes > 0 ? passes : 1) * (seq > 0 ? seq : 1);
+        if (cost < bc || (cost == bc && r < best)) { bc = cost; best = r; }
+    }
+    return best;
 }
 __device__ __forceinline__ void set_lanes(Ctx &c, int R)
 {
@@ -739,8 +746,9 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
     c.Rmax = D.R;
     set_lanes(c, c.Rmax);
     for (int i = threadIdx.x; i < P.nlevels; i += NT) {
-        s_R[i] = level_lanes(s_lv[i + 1] - s_lv[i], c.nslots, c.Rmax);
-        s_R[P.nlevels + i] = level_lanes(s_lv[P.nlevels + 1 + i + 1] - s_lv[P.nlevels + 1 + i], c.nslots, c.Rmax);
+        const int ml = max(P.lvl_maxlen[i], P.lvl_maxlen[P.nlevels + i]);
+        s_R[i] = level_lanes(s_lv[i + 1] - s_lv[i], ml, c.nslots, c.Rmax, IPM_PF);
+        s_R[P.nlevels + i] = level_lanes(s_lv[P.nlevels + 1 + i + 1] - s_lv[P.nlevels + 1 + i], P.lvl_maxlen[2 * P.nlevels + i], c.nslots, c.Rmax, 4);
     }
     __syncthreads();
     c.red = s_red; c.out = s_out;

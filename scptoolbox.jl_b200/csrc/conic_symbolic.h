@@ -54,6 +54,7 @@ struct ConeSymbolic {
     std::vector<int> ft_item;            // int4 per factor target: {target id, op start, op end, sign}
     std::vector<int> ft_op;              // int2 per op: {a, b}
     std::vector<int> sc_item;            // int4 per scaled entry: {position, column, row-order position, 0}
+    std::vector<int> lvl_maxlen;         // [3][nlevels]: longest L row / L column / factor op list of each level
     long long factor_ops = 0;
     std::string err;
 };
@@ -317,6 +318,16 @@ inline bool cone_symbolic_build(ConeSymbolic &S, int n, int p, int m, const int 
             S.sc_item[4 * w] = S.sc_pos[w]; S.sc_item[4 * w + 1] = S.sc_col[w];
             S.sc_item[4 * w + 2] = rowpos[S.sc_pos[w]]; S.sc_item[4 * w + 3] = 0;
         }
+    }
+    S.lvl_maxlen.assign(3 * (size_t)S.nlevels, 0);
+    for (int lv = 0; lv < S.nlevels; lv++) {
+        for (int w = S.lvl_ptr[lv]; w < S.lvl_ptr[lv + 1]; w++) {
+            const int i = S.lvl_nodes[w];
+            S.lvl_maxlen[lv] = std::max(S.lvl_maxlen[lv], S.Lr_rp[i + 1] - S.Lr_rp[i]);
+            S.lvl_maxlen[S.nlevels + lv] = std::max(S.lvl_maxlen[S.nlevels + lv], S.L_cp[i + 1] - S.L_cp[i]);
+        }
+        for (int w = S.ft_lvl_ptr[lv]; w < S.ft_lvl_ptr[lv + 1]; w++)
+            S.lvl_maxlen[2 * S.nlevels + lv] = std::max(S.lvl_maxlen[2 * S.nlevels + lv], S.ft_op_ptr[w + 1] - S.ft_op_ptr[w]);
     }
     S.ft_op.resize(2 * S.ft_op_a.size());
     for (size_t k = 0; k < S.ft_op_a.size(); k++) { S.ft_op[2 * k] = S.ft_op_a[k]; S.ft_op[2 * k + 1] = S.ft_op_b[k]; }
