@@ -111,9 +111,10 @@ int32_t scpb_cone_setup(scpb_handle h, int32_t n, int32_t p, int32_t m,
                         const int32_t *G_rowptr, const int32_t *G_colind,
                         int32_t l, int32_t nsoc, const int32_t *soc_dims, const int32_t *perm,
                         scpb_cone *out);
-/* info[16] = {n+p, nnz(L), elimination-tree levels, factor ops, assembly ops, |W^-2|, group, capacity,
+/* info[20] = {n+p, nnz(L), elimination-tree levels, factor ops, assembly ops, |W^-2|, group, capacity,
  *             8 SM-cycle counters of the last launch (CTA 0): equilibrate, start point, residuals,
- *             scaling+assembly, factorisation, KKT solves, line search+update, total} */
+ *             scaling+assembly, factorisation, KKT solves, line search+update, total;
+ *             forward-substitution cycles, backward-substitution cycles, number of LDL' solves, 0} */
 int32_t scpb_cone_info(scpb_cone c, int64_t *info);
 int32_t scpb_cone_free(scpb_cone c);
 /* host arrays, seed-major: Avals[B][nnzA], Gvals[B][nnzG], c[B][n], b[B][p], h[B][m];

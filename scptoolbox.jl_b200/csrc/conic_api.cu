@@ -97,7 +97,7 @@ static int cone_reserve(scpb_cone_s *c, int B, int G)
         return set_err(h, SCPB_ERR_CUDA, "cone solver: device allocation failed");
     D.status = c->d_status; D.iters = c->d_iters;
     D.pobj = c->d_scal; D.dobj = c->d_scal + Bpad; D.res = c->d_scal + 2 * (size_t)Bpad;
-    if (!c->d_prof && cudaMalloc((void **)&c->d_prof, sizeof(long long) * 8) != cudaSuccess) c->d_prof = nullptr;
+    if (!c->d_prof && cudaMalloc((void **)&c->d_prof, sizeof(long long) * 12) != cudaSuccess) c->d_prof = nullptr;
     D.prof = c->d_prof;
     c->capB = Bpad; c->capG = G;
     D.B = B; D.G = G;
@@ -200,9 +200,9 @@ int32_t scpb_cone_info(scpb_cone c, int64_t *info)
     info[0] = c->S.nk; info[1] = c->S.nnzL; info[2] = c->S.nlevels; info[3] = c->S.factor_ops;
     info[4] = (int64_t)c->S.as_a.size(); info[5] = c->S.nwm; info[6] = c->capG; info[7] = c->capB;
     if (c->d_prof) {   // info[8..15]: cycle counters of the last launch (CTA 0)
-        long long hp[8];
+        long long hp[12];
         if (cudaMemcpy(hp, c->d_prof, sizeof hp, cudaMemcpyDeviceToHost) == cudaSuccess)
-            for (int i = 0; i < 8; i++) info[8 + i] = hp[i];
+            for (int i = 0; i < 12; i++) info[8 + i] = hp[i];
     }
     return SCPB_OK;
 }

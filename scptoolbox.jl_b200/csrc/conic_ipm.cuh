@@ -77,6 +77,7 @@ struct Ctx {
     const int *s_lvl, *s_ftl, *s_scl;   // level pointers staged in shared memory
     int Rmax;
     int *flag;                          // shared scratch word for CTA-uniform decisions
+    long long t_fw, t_bw, t_ldl_n;      // cycle counters (CTA-local copies, meaningful on thread 0)
     double *vs;                         // shared-memory substitution vector (nullptr: use global memory)
     double *Lrow;                       // row-ordered copy of the scaled factor (forward substitution)
     double reftol;                      // iterative refinement stops once |residual|_inf <= reftol*(1+|rhs|_inf)
@@ -312,6 +313,7 @@ __device__ void kkt_ldl_solve_smem(const IpmProgram &P, Ctx &c, const double *Ls
 {
     const int G = c.G, sg = c.sg;
     double *vs = c.vs;
+    const long long t0_ = clock64();
     for (int i = c.slot; i < P.nk; i += c.nslots) vs[i * G + sg] = v[GI(i)];
     SolvePre cur, nxt;
     // forward: level 0 rows are empty (leaves have no dependencies)
@@ -334,6 +336,7 @@ __device__ void kkt_ldl_solve_smem(const IpmProgram &P, Ctx &c, const double *Ls
         __syncthreads();
         cur = nxt;
     }
+    const long long t1_ = clock64();
     for (int i = c.slot; i < P.nk; i += c.nslots) vs[i * G + sg] *= invD[GI(i)];
     set_lanes(c, c.s_Rs[P.nlevels - 1]);
     solve_prefetch(c, P.bw_item, P.L_ri, Ls, c.s_lvl[P.nlevels - 1] + c.isl, c.s_lvl[P.nlevels], cur);
@@ -356,6 +359,8 @@ __device__ void kkt_ldl_solve_smem(const IpmProgram &P, Ctx &c, const double *Ls
     }
     for (int i = c.slot; i < P.nk; i += c.nslots) v[GI(i)] = vs[i * G + sg];
     __syncthreads();
+    const long long t2_ = clock64();
+    c.t_fw += t1_ - t0_; c.t_bw += t2_ - t1_; c.t_ldl_n += 1;
 }
 
 // in-place solve of (L D L') v = rhs on the permuted vector v
@@ -744,6 +749,7 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
     c.G = D.G; c.tid = threadIdx.x; c.sg = c.tid % c.G; c.slot = c.tid / c.G; c.nslots = NT / c.G; c.nwarps = NT / 32;
     c.flag = &s_flag; c.reftol = O.reftol;
     c.Rmax = D.R;
+    c.t_fw = c.t_bw = c.t_ldl_n = 0;
     set_lanes(c, c.Rmax);
     for (int i = threadIdx.x; i < P.nlevels; i += NT) {
         const int ml = max(P.lvl_maxlen[i], P.lvl_maxlen[P.nlevels + i]);
@@ -995,6 +1001,7 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
     if (blockIdx.x == 0 && threadIdx.x == 0 && D.prof) {
         pt[7] = clock64() - tstart;
         for (int i = 0; i < 8; i++) D.prof[i] = pt[i];
+        D.prof[8] = c.t_fw; D.prof[9] = c.t_bw; D.prof[10] = c.t_ldl_n; D.prof[11] = 0;
     }
 #undef PROF
     // ---- epilogue: the best iterate is the answer (ECOS reports its best point the same way) ----

@@ -206,12 +206,13 @@ class ConeProblem:
         self.l, self.soc_dims = int(l), list(soc_dims)
 
     def info(self):
-        buf = (C.c_int64 * 16)()
+        buf = (C.c_int64 * 20)()
         self.lib.scpb_cone_info(self.c, buf)
         keys = ["nk", "nnzL", "levels", "factor_ops", "assembly_ops", "nwm", "group", "capacity"]
         d = dict(zip(keys, [int(v) for v in buf[:8]]))
         d["cycles"] = dict(zip(["equilibrate", "start_point", "residuals", "scale_assemble", "factor", "kkt_solves",
-                                "linesearch_update", "total"], [int(v) for v in buf[8:16]]))
+                                "linesearch_update", "total", "ldl_forward", "ldl_backward", "ldl_count"],
+                               [int(v) for v in buf[8:19]]))
         return d
 
     def close(self):

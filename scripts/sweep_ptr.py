@@ -20,4 +20,4 @@ for opts in eval(sys.argv[4]):
     print(opts, "solved", sum(s == "SCP_SOLVED" for s in sol.status), "iters", int(sol.iterations.sum()), "ipm", t["ipm_iterations"],
           f"solve {t['solve']:.3f}s total {t['total']:.3f}s  it/s {sol.iterations.sum()/t['total']:.0f}  J0 {sol.cost[0]:.9f}", flush=True)
     cy = pbm.cone.info()["cycles"]; tot = max(cy["total"], 1)
-    print("   last-launch cycle shares:", {k: round(100 * v / tot, 1) for k, v in cy.items()}, "total Mcyc", round(tot / 1e6, 1), flush=True)
+    print("   last-launch cycle shares:", {k: round(100 * v / tot, 1) for k, v in cy.items() if k != "ldl_count"}, "total Mcyc", round(tot / 1e6, 1), "ldl solves", cy["ldl_count"], flush=True)
