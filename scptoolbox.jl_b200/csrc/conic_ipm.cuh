@@ -64,6 +64,7 @@ struct IpmData {  // group-blocked device arrays, all for B seeds
 enum { IPM_OPTIMAL = 0, IPM_MAXIT = 1, IPM_NUMERICAL = 2, IPM_ALMOST = 3 };
 
 #define IPM_MAXG 8
+#define IPM_LONG 96   // rows / op lists longer than this are reduced by the whole CTA (arrow rows of global variables)
 #define IPM_NT_MAX 1024
 
 #ifdef CONIC_IPM_IMPL   // the kernel itself is compiled in conic_api.cu only
@@ -225,11 +226,14 @@ __device__ void kkt_factor(const IpmProgram &P, Ctx &c, double *Y, double *Ls, d
         const int wend = c.s_ftl[lv + 1];
         for (int w0 = c.s_ftl[lv]; w0 < wend; w0 += c.nisl) {   // uniform trip count: shuffles inside
             const int w = w0 + c.isl;
-            const bool on = w < wend;
+            bool on = w < wend;
             int4 item = make_int4(0, 0, 0, 0);
             double part = 0.0, y0t = 0.0;
             if (on) {
                 item = P.ft_item[w];
+                if (item.z - item.y > IPM_LONG) { on = false; }
+            }
+            if (on) {
                 if (c.rr == 0) y0t = Y[GI(item.x)];
                 const int k1 = item.z;
                 int k = item.y + c.rr;
@@ -254,6 +258,25 @@ __device__ void kkt_factor(const IpmProgram &P, Ctx &c, double *Y, double *Ls, d
                     invD[GI(t - P.nnzL)] = 1.0 / acc;
                 }
                 Y[GI(t)] = acc;
+            }
+        }
+        if (P.lvl_maxlen[2 * P.nlevels + lv] > IPM_LONG) {   // long op lists: one target at a time, whole CTA
+            for (int w = c.s_ftl[lv]; w < wend; w++) {
+                const int4 item = P.ft_item[w];
+                if (item.z - item.y <= IPM_LONG) continue;
+                double a[1] = {0.0};
+                for (int k = item.y + c.slot; k < item.z; k += c.nslots) { const int2 o0 = P.ft_op[k]; a[0] = fma(Y[GI(o0.x)], Ls[GI(o0.y)], a[0]); }
+                seed_reduce<1>(c, a, 0);
+                if (c.tid < G) {
+                    const int t = item.x;
+                    double acc = Y[(size_t)t * G + c.tid] - c.out[c.tid];
+                    if (t >= P.nnzL) {
+                        const double sgn = (double)item.w;
+                        if (!(sgn * acc > delta_dyn)) acc = sgn * delta_dyn;
+                        invD[(size_t)(t - P.nnzL) * G + c.tid] = 1.0 / acc;
+                    }
+                    Y[(size_t)t * G + c.tid] = acc;
+                }
             }
         }
         __syncthreads();
@@ -327,11 +350,21 @@ __device__ void kkt_ldl_solve_smem(const IpmProgram &P, Ctx &c, const double *Ls
             solve_prefetch(c, P.fw_item, P.Lr_col, c.Lrow, c.s_lvl[lv + 1] + c.isl, c.s_lvl[lv + 2], nxt);
         } else nxt.node = -1;
         set_lanes(c, c.s_Rs[lv]);
-        solve_consume(c, P.Lr_col, c.Lrow, vs, cur);
-        for (int w0 = c.s_lvl[lv] + c.nisl; w0 < wend; w0 += c.nisl) {   // wide levels: further passes
-            SolvePre q;
-            solve_prefetch(c, P.fw_item, P.Lr_col, c.Lrow, w0 + c.isl, wend, q);
-            solve_consume(c, P.Lr_col, c.Lrow, vs, q);
+        if (P.lvl_maxlen[lv] > IPM_LONG) {   // arrow rows: one row at a time, reduced by the whole CTA
+            for (int w = c.s_lvl[lv]; w < wend; w++) {
+                const int4 it = P.fw_item[w];
+                double a[1] = {0.0};
+                for (int k = it.y + c.slot; k < it.z; k += c.nslots) a[0] = fma(c.Lrow[GI(k)], vs[P.Lr_col[k] * G + sg], a[0]);
+                seed_reduce<1>(c, a, 0);
+                if (c.tid < G) vs[it.x * G + c.tid] -= c.out[c.tid];
+            }
+        } else {
+            solve_consume(c, P.Lr_col, c.Lrow, vs, cur);
+            for (int w0 = c.s_lvl[lv] + c.nisl; w0 < wend; w0 += c.nisl) {   // wide levels: further passes
+                SolvePre q;
+                solve_prefetch(c, P.fw_item, P.Lr_col, c.Lrow, w0 + c.isl, wend, q);
+                solve_consume(c, P.Lr_col, c.Lrow, vs, q);
+            }
         }
         __syncthreads();
         cur = nxt;
@@ -752,9 +785,9 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
     c.t_fw = c.t_bw = c.t_ldl_n = 0;
     set_lanes(c, c.Rmax);
     for (int i = threadIdx.x; i < P.nlevels; i += NT) {
-        const int ml = max(P.lvl_maxlen[i], P.lvl_maxlen[P.nlevels + i]);
+        const int ml = min(IPM_LONG, max(P.lvl_maxlen[i], P.lvl_maxlen[P.nlevels + i]));
         s_R[i] = level_lanes(s_lv[i + 1] - s_lv[i], ml, c.nslots, c.Rmax, IPM_PF);
-        s_R[P.nlevels + i] = level_lanes(s_lv[P.nlevels + 1 + i + 1] - s_lv[P.nlevels + 1 + i], P.lvl_maxlen[2 * P.nlevels + i], c.nslots, c.Rmax, 4);
+        s_R[P.nlevels + i] = level_lanes(s_lv[P.nlevels + 1 + i + 1] - s_lv[P.nlevels + 1 + i], min(IPM_LONG, P.lvl_maxlen[2 * P.nlevels + i]), c.nslots, c.Rmax, 4);
     }
     __syncthreads();
     c.red = s_red; c.out = s_out;
