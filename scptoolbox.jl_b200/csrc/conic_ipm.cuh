@@ -141,7 +141,8 @@ __device__ __forceinline__ int level_lanes(int width, int maxlen, int nslots, in
 }
 __device__ __forceinline__ void set_lanes(Ctx &c, int R)
 {
-    c.R = R; c.rr = c.slot % R; c.isl = c.slot / R; c.nisl = c.nslots / R;
+    const int sh = 31 - __clz(R);   // R is a power of two: shifts instead of integer division
+    c.R = R; c.rr = c.slot & (R - 1); c.isl = c.slot >> sh; c.nisl = c.nslots >> sh;
 }
 
 // sum over the R lanes that share a row (offsets G, 2G, .. (R/2)G inside the warp)
