@@ -78,3 +78,37 @@ def test_batched_ptr_matches_oracle_ptr(pkg, handle, N, Nsub, nb):
         assert abs(sol.cost[b] - rs.J_aug) <= 1e-6 * max(1.0, abs(rs.J_aug))
         assert abs(int(sol.iterations[b]) - ref["iterations"]) <= 1
         assert bool(sol.feas[b]) == rs.feas
+
+
+def test_fixed_iteration_ptr_parity(pkg, handle):
+    """Both loops run exactly 10 PTR iterations (eps_abs = eps_rel = 0, like the reference's quadrotor / freeflyer
+    tests, quadrotor/tests.jl:35,46-47), which removes the sensitivity to *when* the stopping rule fires: what is
+    left is the agreement of the SCP fixed point reached through two different interior-point implementations."""
+    N, Nsub, nb, K = 31, 100, 2, 10
+    mdl, traj, pars = _setup(pkg, handle, N, Nsub, iter_max=K)
+    pars.eps_abs = 0.0
+    pars.eps_rel = 0.0
+    pbo = problems.StarshipProblem(N)
+    g = pbo.guess(N)
+    mdl.hs = pbo.hs
+    opars = optr.Parameters(N=N, Nsub=Nsub, iter_max=K, wvc=1e3, wtr=0.1, eps_abs=0.0, eps_rel=0.0, feas_tol=5e-3,
+                            solver_tol=1e-9)
+    P = optr.PTR(pbo, opars)
+    rng = np.random.default_rng(5)
+    sc = P.scale
+    X0 = np.array([g[0] + (0.01 * sc.Sx * rng.standard_normal(g[0].shape) if b else 0.0) for b in range(nb)])
+    U0 = np.array([g[1] + (0.01 * sc.Su * rng.standard_normal(g[1].shape) if b else 0.0) for b in range(nb)])
+    P0 = np.array([g[2] * (1 + (0.02 * rng.uniform(-1, 1, g[2].shape) if b else 0.0)) for b in range(nb)])
+    pbm = pkg.ptr.create(pars, traj, handle)
+    sol = pkg.ptr.solve(pbm, (X0, U0, P0))
+    pbm.close()
+    for b in range(nb):
+        ref = P.solve((X0[b], U0[b], P0[b]), prefer="ipm")
+        rs = ref["sol"]
+        assert int(sol.iterations[b]) == ref["iterations"] == K
+        ex7 = np.abs((sol.xd[b][:, :7] - rs.xd[:, :7]) / sc.Sx[:7]).max()
+        eu2 = np.abs((sol.ud[b][:, :2] - rs.ud[:, :2]) / sc.Su[:2]).max()
+        ep = np.abs((sol.p[b] - rs.p) / sc.Sp).max()
+        dJ = abs(sol.cost[b] - rs.J_aug) / max(1.0, abs(rs.J_aug))
+        print("fixed-iteration parity seed", b, "ex(phys)", ex7, "eu(T,delta)", eu2, "ep", ep, "dJ", dJ)
+        assert max(ex7, eu2, ep) <= 1e-4 and dJ <= 1e-6
