@@ -267,10 +267,13 @@ def run_ours(args, rank, local_rank, world):
         nnzK = pbm.cp["nnzA"] + pbm.cp["nnzG"]
         n_, p_, m_ = pbm.cp["n"], pbm.cp["p"], pbm.cp["m"]
         nnzL, nk = info["nnzL"], info["nk"]
-        nsolve = 2 * (1 + 2)                               # 2 directions x (1 + nref) triangular solve pairs
+        # LDL' solve pairs per interior-point iteration (2 directions + the refinement steps the adaptive rule took):
+        # counted by the kernel itself (CTA 0 of the last launch)
+        cyc = pbm.cone.info()["cycles"]
+        nsolve = cyc["ldl_count"] / max(cyc["factor_count"], 1)
         q_it = 8 * (nnzK + 3 * (nnzL + nk)                 # KKT assembly (read K, write Y) + factor (rw Y, write L)
                     + nsolve * (2 * nnzL + 4 * nk)         # forward+backward substitutions
-                    + (2 + 2 * 2 * 2) * nnzK               # residual / refinement SpMVs (K and K')
+                    + (2 + 2 * nsolve) * nnzK              # residual / refinement SpMVs (K and K')
                     + 12 * (n_ + p_ + 2 * m_))             # vector updates
         k_ms = 1e3 * phases["solve"] / max(lock, 1)
         ach = q_it * ipm / max(phases["solve"], 1e-12) / 1e9
@@ -308,7 +311,10 @@ def run_ours(args, rank, local_rank, world):
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                              "traffic": traffic, "peak_source": peak_src, "kernel": "k_ipm_solve",
                              "kernel_ms": k_ms, "algorithmic_bytes_per_ipm_iteration_per_seed": q_it,
-                             "ipm_iterations_per_launch": ipm / max(lock, 1)},
+                             "ipm_iterations_per_launch": ipm / max(lock, 1), "ldl_solves_per_ipm_iteration": nsolve,
+                             "kernel_share_of_step": phases["solve"] / max(dev_t, 1e-12),
+                             "kernel_cycle_shares": {k: v / max(cyc["total"], 1) for k, v in cyc.items()
+                                                     if k not in ("total", "ldl_count", "factor_count")}},
                 "cpu_baseline": cpu, "clocks": clocks}
         print(json.dumps(line))
     pbm.close()

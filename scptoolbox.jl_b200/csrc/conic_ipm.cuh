@@ -815,6 +815,7 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
 #undef GP
 
     long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long n_fact = 0;   // factorisations (= interior-point iterations) of this CTA
     long long tq = clock64();
     const long long tstart = tq;
 #define PROF(i) { const long long tn = clock64(); pt[i] += tn - tq; tq = tn; }
@@ -958,6 +959,7 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
         PROF(3)
         kkt_factor(P, c, Y, Ls, invD, O.delta_dyn);
         PROF(4)
+        n_fact++;
 
         // ---- affine direction: bx=-rx, by=-ry, bz=-rz+s ; ds = -s - W^2 dz ----
         for (int i = c.slot; i < P.n; i += c.nslots) r1[GI(i)] = -rx[GI(i)];
@@ -1035,7 +1037,7 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
     if (blockIdx.x == 0 && threadIdx.x == 0 && D.prof) {
         pt[7] = clock64() - tstart;
         for (int i = 0; i < 8; i++) D.prof[i] = pt[i];
-        D.prof[8] = c.t_fw; D.prof[9] = c.t_bw; D.prof[10] = c.t_ldl_n; D.prof[11] = 0;
+        D.prof[8] = c.t_fw; D.prof[9] = c.t_bw; D.prof[10] = c.t_ldl_n; D.prof[11] = n_fact;
     }
 #undef PROF
     // ---- epilogue: the best iterate is the answer (ECOS reports its best point the same way) ----

@@ -211,8 +211,8 @@ class ConeProblem:
         keys = ["nk", "nnzL", "levels", "factor_ops", "assembly_ops", "nwm", "group", "capacity"]
         d = dict(zip(keys, [int(v) for v in buf[:8]]))
         d["cycles"] = dict(zip(["equilibrate", "start_point", "residuals", "scale_assemble", "factor", "kkt_solves",
-                                "linesearch_update", "total", "ldl_forward", "ldl_backward", "ldl_count"],
-                               [int(v) for v in buf[8:19]]))
+                                "linesearch_update", "total", "ldl_forward", "ldl_backward", "ldl_count",
+                                "factor_count"], [int(v) for v in buf[8:20]]))
         return d
 
     def close(self):
