@@ -157,6 +157,11 @@ int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *u
                        const scpb_cone_opts *opts, double *xd, double *ud, double *p, int32_t *status,
                        int32_t *iters, double *J, double *deviation, int32_t *feas, double *timing);
 
+/* Diagnostic: per-level cycle counters of CTA 0 in the last scpb_cone_solve / scpb_ptr_solve launch, recorded
+ * only when the environment variable SCPB_LEVEL_PROFILE is set: out[0..L) numeric factorisation, out[L..2L)
+ * forward substitution, out[2L..3L) backward substitution (L = info[2] levels); cap >= 3L. */
+int32_t scpb_debug_level_profile(scpb_cone cone, int64_t *out, int32_t cap);
+
 /* ---- test hook: CPU interpreter of the solver's index programs for ONE seed (no GPU needed) ----
  * Assembles M = [dI + G'W^-2 G, A'; A, -dI] from (Av, Gv, wm), factors it with the level-scheduled
  * LDL' program and solves M sol = rhs (natural node order: n variables then p equality rows).

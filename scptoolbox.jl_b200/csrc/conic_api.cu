@@ -1,4 +1,5 @@
 // conic_api.cu -- C ABI of the batched cone solver (scpb_cone_*), host orchestration.
+#include <cstdlib>
 #include "handle.cuh"
 #include "conic_symbolic.h"
 #define CONIC_IPM_IMPL
@@ -97,7 +98,7 @@ static int cone_reserve(scpb_cone_s *c, int B, int G)
         return set_err(h, SCPB_ERR_CUDA, "cone solver: device allocation failed");
     D.status = c->d_status; D.iters = c->d_iters;
     D.pobj = c->d_scal; D.dobj = c->d_scal + Bpad; D.res = c->d_scal + 2 * (size_t)Bpad;
-    if (!c->d_prof && cudaMalloc((void **)&c->d_prof, sizeof(long long) * 12) != cudaSuccess) c->d_prof = nullptr;
+    if (!c->d_prof && cudaMalloc((void **)&c->d_prof, sizeof(long long) * (12 + 3 * (size_t)c->S.nlevels)) != cudaSuccess) c->d_prof = nullptr;
     D.prof = c->d_prof;
     c->capB = Bpad; c->capG = G;
     D.B = B; D.G = G;
@@ -115,6 +116,7 @@ int scpb_internal_cone_run(scpb_cone_s *c, const IpmOpts &o)
     const size_t vbytes = sizeof(double) * (size_t)c->S.nk * c->D.G;
     c->D.vsmem = (smem + vbytes <= 200 * 1024) ? 1 : 0;
     if (c->D.vsmem) smem += vbytes;
+    c->D.lvl_prof = (c->d_prof && getenv("SCPB_LEVEL_PROFILE")) ? 1 : 0;   // diagnostic: per-level cycle counters of CTA 0
     if (o.threads >= 1024) {
         SCPB_CUDA(h, cudaFuncSetAttribute(k_ipm_solve<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_ipm_solve<1024><<<ng, 1024, smem, h->stream>>>(c->P, c->D, o);
@@ -204,6 +206,18 @@ int32_t scpb_cone_info(scpb_cone c, int64_t *info)
         if (cudaMemcpy(hp, c->d_prof, sizeof hp, cudaMemcpyDeviceToHost) == cudaSuccess)
             for (int i = 0; i < 12; i++) info[8 + i] = hp[i];
     }
+    return SCPB_OK;
+}
+
+int32_t scpb_debug_level_profile(scpb_cone c, int64_t *out, int32_t cap)
+{
+    if (!c || !out) return SCPB_ERR_ARG;
+    const int nl = c->S.nlevels;
+    if (cap < 3 * nl || !c->d_prof) return SCPB_ERR_ARG;
+    std::vector<long long> hp(3 * (size_t)nl);
+    if (cudaMemcpy(hp.data(), c->d_prof + 12, sizeof(long long) * hp.size(), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return SCPB_ERR_CUDA;
+    for (size_t i = 0; i < hp.size(); i++) out[i] = hp[i];
     return SCPB_OK;
 }
 

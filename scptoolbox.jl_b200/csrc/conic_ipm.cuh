@@ -58,6 +58,7 @@ struct IpmData {  // group-blocked device arrays, all for B seeds
     // per-seed outputs
     double *pobj, *dobj, *res;   // res: [3][B] pres, dres, gap
     int *status, *iters;
+    int lvl_prof;      // 1: also record per-level cycles behind prof[12..]
     long long *prof;   // [8] cycle counters of CTA 0: equilibrate, init, residuals, scaling+assemble, factor, solves, line search+update, total
 };
 
@@ -79,6 +80,7 @@ struct Ctx {
     int Rmax;
     int *flag;                          // shared scratch word for CTA-uniform decisions
     long long t_fw, t_bw, t_ldl_n;      // cycle counters (CTA-local copies, meaningful on thread 0)
+    long long *lprof;                   // thread 0 of CTA 0: per-level cycles [factor | forward | backward][nlevels]
     double *vs;                         // shared-memory substitution vector (nullptr: use global memory)
     double *Lrow;                       // row-ordered copy of the scaled factor (forward substitution)
     double reftol;                      // iterative refinement stops once |residual|_inf <= reftol*(1+|rhs|_inf)
@@ -222,6 +224,7 @@ __device__ void kkt_assemble(const IpmProgram &P, const Ctx &c, const IpmData &D
 __device__ void kkt_factor(const IpmProgram &P, Ctx &c, double *Y, double *Ls, double *invD, double delta_dyn)
 {
     const int G = c.G, sg = c.sg;
+    long long tl_ = c.lprof ? clock64() : 0;
     for (int lv = 0; lv < P.nlevels; lv++) {
         set_lanes(c, c.s_Rf[lv]);
         const int wend = c.s_ftl[lv + 1];
@@ -288,6 +291,7 @@ __device__ void kkt_factor(const IpmProgram &P, Ctx &c, double *Y, double *Ls, d
             c.Lrow[GI(it.z)] = lv_;
         }
         __syncthreads();
+        if (c.lprof) { const long long tn = clock64(); c.lprof[lv] += tn - tl_; tl_ = tn; }
     }
 }
 
@@ -344,6 +348,7 @@ __device__ void kkt_ldl_solve_smem(const IpmProgram &P, Ctx &c, const double *Ls
     if (P.nlevels > 1) set_lanes(c, c.s_Rs[1]);
     solve_prefetch(c, P.fw_item, P.Lr_col, c.Lrow, c.s_lvl[1] + c.isl, P.nlevels > 1 ? c.s_lvl[2] : 0, cur);
     __syncthreads();
+    long long tl_ = c.lprof ? clock64() : 0;
     for (int lv = 1; lv < P.nlevels; lv++) {
         const int wend = c.s_lvl[lv + 1];
         if (lv + 1 < P.nlevels) {
@@ -369,12 +374,14 @@ __device__ void kkt_ldl_solve_smem(const IpmProgram &P, Ctx &c, const double *Ls
         }
         __syncthreads();
         cur = nxt;
+        if (c.lprof) { const long long tn = clock64(); c.lprof[P.nlevels + lv] += tn - tl_; tl_ = tn; }
     }
     const long long t1_ = clock64();
     for (int i = c.slot; i < P.nk; i += c.nslots) vs[i * G + sg] *= invD[GI(i)];
     set_lanes(c, c.s_Rs[P.nlevels - 1]);
     solve_prefetch(c, P.bw_item, P.L_ri, Ls, c.s_lvl[P.nlevels - 1] + c.isl, c.s_lvl[P.nlevels], cur);
     __syncthreads();
+    if (c.lprof) tl_ = clock64();
     for (int lv = P.nlevels - 1; lv >= 0; lv--) {
         const int wend = c.s_lvl[lv + 1];
         if (lv > 0) {
@@ -390,6 +397,7 @@ __device__ void kkt_ldl_solve_smem(const IpmProgram &P, Ctx &c, const double *Ls
         }
         __syncthreads();
         cur = nxt;
+        if (c.lprof) { const long long tn = clock64(); c.lprof[2 * P.nlevels + lv] += tn - tl_; tl_ = tn; }
     }
     for (int i = c.slot; i < P.nk; i += c.nslots) v[GI(i)] = vs[i * G + sg];
     __syncthreads();
@@ -784,6 +792,8 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
     c.flag = &s_flag; c.reftol = O.reftol;
     c.Rmax = D.R;
     c.t_fw = c.t_bw = c.t_ldl_n = 0;
+    c.lprof = (blockIdx.x == 0 && threadIdx.x == 0 && D.prof && D.lvl_prof) ? D.prof + 12 : nullptr;
+    if (c.lprof) for (int i = 0; i < 3 * P.nlevels; i++) c.lprof[i] = 0;
     set_lanes(c, c.Rmax);
     for (int i = threadIdx.x; i < P.nlevels; i += NT) {
         const int ml = min(IPM_LONG, max(P.lvl_maxlen[i], P.lvl_maxlen[P.nlevels + i]));

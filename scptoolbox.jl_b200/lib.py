@@ -49,6 +49,7 @@ SIGNATURES = {
     "scpb_ptr_free": (C.c_int32, [C.c_void_p]),
     "scpb_ptr_solve": (C.c_int32, [C.c_void_p, C.c_int32, _dp, _dp, _dp, C.c_void_p, _dp, _dp, _dp, _ip, _ip,
                                    _dp, _dp, _ip, _dp]),
+    "scpb_debug_level_profile": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
     "scpb_debug_kkt_solve": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _ip, _ip, _ip, _ip, C.c_int32, C.c_int32,
                                          _ip, _ip, _dp, _dp, _dp, C.c_double, C.c_double, _dp, _dp, C.POINTER(C.c_int64)]),
 }
@@ -214,6 +215,15 @@ class ConeProblem:
                                 "linesearch_update", "total", "ldl_forward", "ldl_backward", "ldl_count",
                                 "factor_count"], [int(v) for v in buf[8:20]]))
         return d
+
+    def level_profile(self):
+        """(3, levels) cycle counters [factor, forward, backward] of CTA 0 (needs SCPB_LEVEL_PROFILE=1)."""
+        nl = self.info()["levels"]
+        buf = (C.c_int64 * (3 * nl))()
+        rc = self.lib.scpb_debug_level_profile(self.c, buf, 3 * nl)
+        if rc != 0:
+            raise ScpbError(f"scpb_debug_level_profile failed ({rc})")
+        return np.array(buf[:], dtype=np.int64).reshape(3, nl)
 
     def close(self):
         if getattr(self, "c", None) is not None and self.c.value:
