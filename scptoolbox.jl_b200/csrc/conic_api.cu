@@ -112,7 +112,7 @@ int scpb_internal_cone_run(scpb_cone_s *c, const IpmOpts &o)
     const int ng = (c->D.B + c->D.G - 1) / c->D.G;
     // dynamic shared memory: level pointers (+ the substitution vector when nk*G doubles fit next to the
     // ~20 KB of static shared memory; B200 allows 227 KB per CTA)
-    size_t smem = sizeof(int) * ((5 * (size_t)(c->S.nlevels + 1) + 3) & ~(size_t)3);
+    size_t smem = sizeof(int) * ((9 * (size_t)(c->S.nlevels + 1) + 3) & ~(size_t)3);
     const size_t vbytes = sizeof(double) * (size_t)c->S.nk * c->D.G;
     c->D.vsmem = (smem + vbytes <= 200 * 1024) ? 1 : 0;
     if (c->D.vsmem) smem += vbytes;
@@ -186,6 +186,9 @@ int32_t scpb_cone_setup(scpb_handle h, int32_t n, int32_t p, int32_t m, const in
     P.fw_item = (const int4 *)upload_ints(c, S.fw_item); P.bw_item = (const int4 *)upload_ints(c, S.bw_item);
     P.ft_item = (const int4 *)upload_ints(c, S.ft_item); P.sc_item = (const int4 *)upload_ints(c, S.sc_item);
     P.lvl_maxlen = upload_ints(c, S.lvl_maxlen);
+    P.fwp_item = (const int4 *)upload_ints(c, S.fwp_item); P.bwp_item = (const int4 *)upload_ints(c, S.bwp_item);
+    P.fwp_lvl = upload_ints(c, S.fwp_lvl); P.bwp_lvl = upload_ints(c, S.bwp_lvl);
+    P.fwp_R = upload_ints(c, S.fwp_R); P.bwp_R = upload_ints(c, S.bwp_R);
     P.Lr_pc = (const int2 *)upload_ints(c, S.Lr_pc); P.ft_op = (const int2 *)upload_ints(c, S.ft_op);
     for (void *d : c->dev_ints)
         if (!d) {

@@ -38,21 +38,31 @@ extern "C" int32_t scpb_debug_kkt_solve(int32_t n, int32_t p, int32_t m, const i
         for (int w = S.sc_lvl_ptr[lv]; w < S.sc_lvl_ptr[lv + 1]; w++) Ls[S.sc_pos[w]] = Y[S.sc_pos[w]] * invD[S.sc_col[w]];
     }
     for (int i = 0; i < nk; i++) v[S.iperm[i]] = rhs[i];
-    for (int lv = 0; lv < S.nlevels; lv++)  // kkt_ldl_solve
-        for (int w = S.lvl_ptr[lv]; w < S.lvl_ptr[lv + 1]; w++) {
-            const int i = S.lvl_nodes[w];
-            double acc = v[i];
-            for (int k = S.Lr_rp[i]; k < S.Lr_rp[i + 1]; k++) acc -= Ls[S.Lr_pos[k]] * v[S.Lr_col[k]];
-            v[i] = acc;
+    // kkt_ldl_solve_smem: the balanced (split-item) substitution programs, level by level; within a level every
+    // item reads v as it was when the level started, except for the target it accumulates into
+    std::vector<double> Lrow(S.nnzL + 1);
+    for (int k = 0; k < S.nnzL; k++) Lrow[k] = Ls[S.Lr_pos[k]];
+    for (int lv = 0; lv < S.nlevels; lv++) {
+        const int R = S.fwp_R[lv];
+        for (int w = S.fwp_lvl[lv]; w < S.fwp_lvl[lv + 1]; w++) {
+            const int *it = &S.fwp_item[4 * (size_t)w];
+            if (it[2] - it[1] > R * CONIC_SOLVE_PF) return SCPB_ERR_ARG;
+            double part = 0.0;
+            for (int k = it[1]; k < it[2]; k++) part += Lrow[k] * v[S.Lr_col[k]];
+            v[it[0]] -= part;
         }
+    }
     for (int i = 0; i < nk; i++) v[i] *= invD[i];
-    for (int lv = S.nlevels - 1; lv >= 0; lv--)
-        for (int w = S.lvl_ptr[lv]; w < S.lvl_ptr[lv + 1]; w++) {
-            const int j = S.lvl_nodes[w];
-            double acc = v[j];
-            for (int k = S.L_cp[j]; k < S.L_cp[j + 1]; k++) acc -= Ls[k] * v[S.L_ri[k]];
-            v[j] = acc;
+    for (int lv = S.nlevels - 1; lv >= 0; lv--) {
+        const int R = S.bwp_R[lv];
+        for (int w = S.bwp_lvl[lv]; w < S.bwp_lvl[lv + 1]; w++) {
+            const int *it = &S.bwp_item[4 * (size_t)w];
+            if (it[2] - it[1] > R * CONIC_SOLVE_PF) return SCPB_ERR_ARG;
+            double part = 0.0;
+            for (int k = it[1]; k < it[2]; k++) part += Ls[k] * v[S.L_ri[k]];
+            v[it[0]] -= part;
         }
+    }
     for (int i = 0; i < nk; i++) sol[i] = v[S.iperm[i]];
     if (info) { info[0] = S.nnzL; info[1] = S.nlevels; info[2] = S.factor_ops; info[3] = (int64_t)S.as_a.size(); }
     return SCPB_OK;

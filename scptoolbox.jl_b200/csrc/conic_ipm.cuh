@@ -29,6 +29,8 @@ struct IpmProgram {  // device copies of ConeSymbolic index arrays
     const int *sc_lvl_ptr, *sc_pos, *sc_col;
     const int *as_ptr, *as_a, *as_b, *as_c, *as_src, *as_sign;
     const int4 *fw_item, *bw_item, *ft_item, *sc_item;
+    const int4 *fwp_item, *bwp_item;
+    const int *fwp_lvl, *bwp_lvl, *fwp_R, *bwp_R;
     const int2 *Lr_pc, *ft_op;
     const int *lvl_maxlen;   // [3][nlevels]
 };
@@ -77,6 +79,8 @@ struct Ctx {
     int R, rr, isl, nisl;               // current per-level values, see set_lanes()
     const int *s_Rs, *s_Rf;             // per-level lanes-per-row for the substitutions / the factorisation
     const int *s_lvl, *s_ftl, *s_scl;   // level pointers staged in shared memory
+    int o_fwl, o_bwl, o_fwR, o_bwR, o_vs;   // balanced substitution programs (item pointers, lanes per level) and
+                                            // the substitution vector: int offsets into the dynamic shared window
     int Rmax;
     int *flag;                          // shared scratch word for CTA-uniform decisions
     long long t_fw, t_bw, t_ldl_n;      // cycle counters (CTA-local copies, meaningful on thread 0)
@@ -296,45 +300,101 @@ __device__ void kkt_factor(const IpmProgram &P, Ctx &c, double *Y, double *Ls, d
 }
 
 // ---- shared-memory, prefetching substitution ------------------------------------------------------------
-// The vector lives in shared memory; L values are read in the order each sweep consumes them (row-ordered copy
-// Lrow forward, column-ordered Ls backward) and the NEXT level's item, indices and values are loaded before the
-// barrier of the current level, so that after a barrier only shared-memory traffic is on the critical path.
-#define IPM_PF 4
-struct SolvePre {
-    int node, k0, k1;
-    int idx[IPM_PF];
-    double val[IPM_PF];
+// The vector lives in shared memory.  The host splits every L row (forward) / column (backward) into items of at most
+// R*IPM_PF entries (conic_symbolic.h, "balanced substitution programs"), so a lane never owns more than IPM_PF
+// entries of an item: right after a level's items are consumed the lane issues ALL global loads of the next level
+// (indices + values, through an item descriptor fetched one level earlier) and only then waits at the barrier.
+// Items of a split row combine their partial sums with shared-memory atomics.
+// The sweep is a separate (noinline) function with by-value arguments and shared-window pointers: its register
+// allocation is independent of the 60+ live pointers of the solver body, so the prefetch registers are not spilled
+// (a spilled prefetch is a synchronous load).
+#define IPM_PF CONIC_SOLVE_PF
+struct SweepArgs {
+    const int4 *items;      // balanced items {node, start, end, split}
+    const int *idxarr;      // entry -> vector index (column of the row entry / row of the column entry)
+    const double *vals;     // group-blocked L values in the same entry order
+    int o_lvl, o_R, o_vs;   // offsets (ints) into the dynamic shared memory window
+    int nl, lv0, G, sg, slot, nslots;
+    long long *lprof;       // per-level cycle counters (CTA 0, thread 0) or nullptr
 };
+extern __shared__ int ipm_smem[];
 
-__device__ __forceinline__ void solve_prefetch(const Ctx &c, const int4 *items, const int *idxarr, const double *vals,
-                                               int w, int wend, SolvePre &q)
+__device__ __forceinline__ double smem_atomic_add(double *addr, double v)
 {
-    const int G = c.G, sg = c.sg;
-    q.node = -1;
-    if (w < wend) {
-        const int4 it = items[w];
-        q.node = it.x; q.k0 = it.y + c.rr; q.k1 = it.z;
-#pragma unroll
-        for (int j = 0; j < IPM_PF; j++) {
-            const int k = q.k0 + j * c.R;
-            if (k < q.k1) { q.idx[j] = idxarr[k]; q.val[j] = vals[GI(k)]; }
-        }
-    }
+    return atomicAdd(addr, v);   // addr is derived from ipm_smem: the compiler emits the shared-space form
 }
 
-__device__ __forceinline__ void solve_consume(const Ctx &c, const int *idxarr, const double *vals, double *vs,
-                                              const SolvePre &q)
+template <int DIR>
+__device__ __noinline__ void solve_sweep(const SweepArgs a)
 {
-    const int G = c.G, sg = c.sg;
-    double part = 0.0;
-    if (q.node >= 0) {
-#pragma unroll
-        for (int j = 0; j < IPM_PF; j++)
-            if (q.k0 + j * c.R < q.k1) part = fma(q.val[j], vs[q.idx[j] * G + sg], part);
-        for (int k = q.k0 + IPM_PF * c.R; k < q.k1; k += c.R) part = fma(vals[GI(k)], vs[idxarr[k] * G + sg], part);
+    __builtin_assume(__isGlobal(a.items)); __builtin_assume(__isGlobal(a.idxarr)); __builtin_assume(__isGlobal(a.vals));
+    const int *lvl = ipm_smem + a.o_lvl, *Rl = ipm_smem + a.o_R;
+    double *vs = (double *)(ipm_smem + a.o_vs);
+    const int G = a.G, sg = a.sg, slot = a.slot;
+    const int nsteps = DIR > 0 ? a.nl - a.lv0 : a.lv0 + 1;
+    if (nsteps <= 0) return;
+    // item descriptor of this lane for the level after next; (node | split << 30), first entry, end
+    int i_node, i_k0, i_k1, i_R;
+    int q_node;                    // current item: node | split << 30, or -1
+    int q_idx[IPM_PF];
+    double q_val[IPM_PF];
+#define IPM_ITEM_LOAD(LV, OFF)                                                            \
+    {                                                                                     \
+        const int R_ = Rl[LV], sh_ = 31 - __clz(R_);                                      \
+        const int w_ = lvl[LV] + (OFF) + (slot >> sh_);                                   \
+        i_node = -1; i_R = R_; i_k0 = 0; i_k1 = 0;                                        \
+        if (w_ < lvl[(LV) + 1]) {                                                         \
+            const int4 it_ = a.items[w_];                                                 \
+            i_node = it_.x | (it_.w << 30); i_k0 = it_.y + (slot & (R_ - 1)); i_k1 = it_.z; \
+        }                                                                                 \
     }
-    part = lanes_sum(c, part);
-    if (q.node >= 0 && c.rr == 0) vs[q.node * G + sg] -= part;
+#define IPM_VALS_LOAD()                                                                   \
+    {                                                                                     \
+        q_node = i_node;                                                                  \
+        _Pragma("unroll") for (int j = 0; j < IPM_PF; j++) {                              \
+            const int k_ = i_k0 + j * i_R;                                                \
+            const bool on_ = i_node >= 0 && k_ < i_k1;                                    \
+            q_idx[j] = on_ ? a.idxarr[k_] : 0;                                            \
+            q_val[j] = on_ ? a.vals[(size_t)k_ * G + sg] : 0.0;                           \
+        }                                                                                 \
+    }
+#define IPM_CONSUME(R)                                                                    \
+    {                                                                                     \
+        double part_ = 0.0;                                                               \
+        _Pragma("unroll") for (int j = 0; j < IPM_PF; j++) part_ = fma(q_val[j], vs[q_idx[j] * G + sg], part_); \
+        for (int o_ = G; o_ < G * (R); o_ <<= 1) part_ += __shfl_xor_sync(0xffffffffu, part_, o_); \
+        if (q_node >= 0 && (slot & ((R) - 1)) == 0) {                                     \
+            double *t_ = &vs[(q_node & 0x3fffffff) * G + sg];                             \
+            if (q_node >> 30) smem_atomic_add(t_, -part_); else *t_ -= part_;             \
+        }                                                                                 \
+    }
+    IPM_ITEM_LOAD(a.lv0, 0)
+    IPM_VALS_LOAD()
+    if (nsteps > 1) IPM_ITEM_LOAD(a.lv0 + DIR, 0) else i_node = -1;
+    __syncthreads();
+    long long tl_ = a.lprof ? clock64() : 0;
+    for (int st = 0, lv = a.lv0; st < nsteps; st++, lv += DIR) {
+        const int R = Rl[lv], nisl = a.nslots >> (31 - __clz(R));
+        IPM_CONSUME(R)
+        const int nit = lvl[lv + 1] - lvl[lv];
+        if (nit > nisl) {   // wide levels: further passes (not prefetched); rare above the leaf levels
+            const int sn = i_node, s0 = i_k0, s1 = i_k1, sR = i_R;
+            for (int off = nisl; off < nit; off += nisl) {
+                IPM_ITEM_LOAD(lv, off)
+                IPM_VALS_LOAD()
+                IPM_CONSUME(R)
+            }
+            i_node = sn; i_k0 = s0; i_k1 = s1; i_R = sR;
+        }
+        // prefetch: values of the next level (descriptor already here), descriptor of the level after it
+        IPM_VALS_LOAD()
+        if (st + 2 < nsteps) IPM_ITEM_LOAD(lv + 2 * DIR, 0) else i_node = -1;
+        __syncthreads();
+        if (a.lprof) { const long long tn = clock64(); a.lprof[lv] += tn - tl_; tl_ = tn; }
+    }
+#undef IPM_ITEM_LOAD
+#undef IPM_VALS_LOAD
+#undef IPM_CONSUME
 }
 
 __device__ void kkt_ldl_solve_smem(const IpmProgram &P, Ctx &c, const double *Ls, const double *invD, double *v)
@@ -343,62 +403,20 @@ __device__ void kkt_ldl_solve_smem(const IpmProgram &P, Ctx &c, const double *Ls
     double *vs = c.vs;
     const long long t0_ = clock64();
     for (int i = c.slot; i < P.nk; i += c.nslots) vs[i * G + sg] = v[GI(i)];
-    SolvePre cur, nxt;
-    // forward: level 0 rows are empty (leaves have no dependencies)
-    if (P.nlevels > 1) set_lanes(c, c.s_Rs[1]);
-    solve_prefetch(c, P.fw_item, P.Lr_col, c.Lrow, c.s_lvl[1] + c.isl, P.nlevels > 1 ? c.s_lvl[2] : 0, cur);
-    __syncthreads();
-    long long tl_ = c.lprof ? clock64() : 0;
-    for (int lv = 1; lv < P.nlevels; lv++) {
-        const int wend = c.s_lvl[lv + 1];
-        if (lv + 1 < P.nlevels) {
-            set_lanes(c, c.s_Rs[lv + 1]);
-            solve_prefetch(c, P.fw_item, P.Lr_col, c.Lrow, c.s_lvl[lv + 1] + c.isl, c.s_lvl[lv + 2], nxt);
-        } else nxt.node = -1;
-        set_lanes(c, c.s_Rs[lv]);
-        if (P.lvl_maxlen[lv] > IPM_LONG) {   // arrow rows: one row at a time, reduced by the whole CTA
-            for (int w = c.s_lvl[lv]; w < wend; w++) {
-                const int4 it = P.fw_item[w];
-                double a[1] = {0.0};
-                for (int k = it.y + c.slot; k < it.z; k += c.nslots) a[0] = fma(c.Lrow[GI(k)], vs[P.Lr_col[k] * G + sg], a[0]);
-                seed_reduce<1>(c, a, 0);
-                if (c.tid < G) vs[it.x * G + c.tid] -= c.out[c.tid];
-            }
-        } else {
-            solve_consume(c, P.Lr_col, c.Lrow, vs, cur);
-            for (int w0 = c.s_lvl[lv] + c.nisl; w0 < wend; w0 += c.nisl) {   // wide levels: further passes
-                SolvePre q;
-                solve_prefetch(c, P.fw_item, P.Lr_col, c.Lrow, w0 + c.isl, wend, q);
-                solve_consume(c, P.Lr_col, c.Lrow, vs, q);
-            }
-        }
-        __syncthreads();
-        cur = nxt;
-        if (c.lprof) { const long long tn = clock64(); c.lprof[P.nlevels + lv] += tn - tl_; tl_ = tn; }
-    }
+    SweepArgs a;
+    a.nl = P.nlevels; a.G = G; a.sg = sg; a.slot = c.slot; a.nslots = c.nslots; a.o_vs = c.o_vs;
+    // forward: level 0 rows are empty (leaves have no dependencies); the barrier inside the sweep publishes vs
+    a.items = P.fwp_item; a.idxarr = P.Lr_col; a.vals = c.Lrow; a.o_lvl = c.o_fwl; a.o_R = c.o_fwR; a.lv0 = 1;
+    a.lprof = c.lprof ? c.lprof + P.nlevels : nullptr;
+    solve_sweep<1>(a);
+    if (P.nlevels <= 1) __syncthreads();
     const long long t1_ = clock64();
     for (int i = c.slot; i < P.nk; i += c.nslots) vs[i * G + sg] *= invD[GI(i)];
-    set_lanes(c, c.s_Rs[P.nlevels - 1]);
-    solve_prefetch(c, P.bw_item, P.L_ri, Ls, c.s_lvl[P.nlevels - 1] + c.isl, c.s_lvl[P.nlevels], cur);
-    __syncthreads();
-    if (c.lprof) tl_ = clock64();
-    for (int lv = P.nlevels - 1; lv >= 0; lv--) {
-        const int wend = c.s_lvl[lv + 1];
-        if (lv > 0) {
-            set_lanes(c, c.s_Rs[lv - 1]);
-            solve_prefetch(c, P.bw_item, P.L_ri, Ls, c.s_lvl[lv - 1] + c.isl, c.s_lvl[lv], nxt);
-        } else nxt.node = -1;
-        set_lanes(c, c.s_Rs[lv]);
-        solve_consume(c, P.L_ri, Ls, vs, cur);
-        for (int w0 = c.s_lvl[lv] + c.nisl; w0 < wend; w0 += c.nisl) {
-            SolvePre q;
-            solve_prefetch(c, P.bw_item, P.L_ri, Ls, w0 + c.isl, wend, q);
-            solve_consume(c, P.L_ri, Ls, vs, q);
-        }
-        __syncthreads();
-        cur = nxt;
-        if (c.lprof) { const long long tn = clock64(); c.lprof[2 * P.nlevels + lv] += tn - tl_; tl_ = tn; }
-    }
+    // backward: the top level holds roots only (empty columns)
+    a.items = P.bwp_item; a.idxarr = P.L_ri; a.vals = Ls; a.o_lvl = c.o_bwl; a.o_R = c.o_bwR; a.lv0 = P.nlevels - 2;
+    a.lprof = c.lprof ? c.lprof + 2 * P.nlevels : nullptr;
+    solve_sweep<-1>(a);
+    if (P.nlevels <= 1) __syncthreads();
     for (int i = c.slot; i < P.nk; i += c.nslots) v[GI(i)] = vs[i * G + sg];
     __syncthreads();
     const long long t2_ = clock64();
@@ -778,7 +796,7 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
     __shared__ int s_done[IPM_MAXG], s_status[IPM_MAXG], s_iters[IPM_MAXG], s_alldone, s_save[IPM_MAXG], s_stall[IPM_MAXG];
     __shared__ double s_best[IPM_MAXG], s_bp[IPM_MAXG], s_bd[IPM_MAXG], s_br[3 * IPM_MAXG];
 
-    extern __shared__ int s_lv[];   // [3][nlevels+1]: lvl_ptr, ft_lvl_ptr, sc_lvl_ptr
+    int *s_lv = ipm_smem;   // [9][nlevels+1]: lvl_ptr, ft_lvl_ptr, sc_lvl_ptr, lanes (2), balanced programs (4)
     for (int i = threadIdx.x; i <= P.nlevels; i += NT) {
         s_lv[i] = P.lvl_ptr[i]; s_lv[P.nlevels + 1 + i] = P.ft_lvl_ptr[i]; s_lv[2 * (P.nlevels + 1) + i] = P.sc_lvl_ptr[i];
     }
@@ -786,8 +804,17 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
     Ctx c;
     c.s_lvl = s_lv; c.s_ftl = s_lv + P.nlevels + 1; c.s_scl = s_lv + 2 * (P.nlevels + 1);
     int *s_R = s_lv + 3 * (P.nlevels + 1);
+    {
+        int *s_p = s_lv + 5 * (P.nlevels + 1);   // [fwp_lvl | bwp_lvl | fwp_R | bwp_R]
+        for (int i = threadIdx.x; i <= P.nlevels; i += NT) { s_p[i] = P.fwp_lvl[i]; s_p[P.nlevels + 1 + i] = P.bwp_lvl[i]; }
+        for (int i = threadIdx.x; i < P.nlevels; i += NT) {
+            s_p[2 * (P.nlevels + 1) + i] = P.fwp_R[i]; s_p[3 * (P.nlevels + 1) + i] = P.bwp_R[i];
+        }
+        c.o_fwl = 5 * (P.nlevels + 1); c.o_bwl = 6 * (P.nlevels + 1); c.o_fwR = 7 * (P.nlevels + 1); c.o_bwR = 8 * (P.nlevels + 1);
+    }
     c.s_Rs = s_R; c.s_Rf = s_R + P.nlevels;
-    c.vs = D.vsmem ? (double *)(s_lv + ((5 * (P.nlevels + 1) + 3) & ~3)) : nullptr;
+    c.o_vs = (9 * (P.nlevels + 1) + 3) & ~3;
+    c.vs = D.vsmem ? (double *)(s_lv + c.o_vs) : nullptr;
     c.G = D.G; c.tid = threadIdx.x; c.sg = c.tid % c.G; c.slot = c.tid / c.G; c.nslots = NT / c.G; c.nwarps = NT / 32;
     c.flag = &s_flag; c.reftol = O.reftol;
     c.Rmax = D.R;

@@ -16,6 +16,10 @@
 #include <string>
 #include <vector>
 
+#ifndef CONIC_SOLVE_PF
+#define CONIC_SOLVE_PF 4   // L entries a lane keeps in flight per substitution item
+#endif
+
 struct ConeSymbolic {
     int n = 0, p = 0, m = 0, l = 0, nsoc = 0;
     int nk = 0;                       // n + p  (KKT dimension)
@@ -55,6 +59,12 @@ struct ConeSymbolic {
     std::vector<int> ft_op;              // int2 per op: {a, b}
     std::vector<int> sc_item;            // int4 per scaled entry: {position, column, row-order position, 0}
     std::vector<int> lvl_maxlen;         // [3][nlevels]: longest L row / L column / factor op list of each level
+    // balanced substitution programs: every item covers at most R*SOLVE_PF entries of one row (forward) / column
+    // (backward), R = lanes per item of that level; rows longer than that are split into several items whose partial
+    // sums are combined with atomics (flag in .w).  All loads of an item fit the per-lane register prefetch.
+    std::vector<int> fwp_item, bwp_item; // int4 {node, start, end, split}
+    std::vector<int> fwp_lvl, bwp_lvl;   // nlevels+1 -> index into the item lists
+    std::vector<int> fwp_R, bwp_R;       // lanes per item of each level
     long long factor_ops = 0;
     std::string err;
 };
@@ -331,5 +341,37 @@ inline bool cone_symbolic_build(ConeSymbolic &S, int n, int p, int m, const int 
     }
     S.ft_op.resize(2 * S.ft_op_a.size());
     for (size_t k = 0; k < S.ft_op_a.size(); k++) { S.ft_op[2 * k] = S.ft_op_a[k]; S.ft_op[2 * k + 1] = S.ft_op_b[k]; }
+    // ---- balanced substitution programs ----
+    {
+        const int PF = CONIC_SOLVE_PF, SLOTS = 512, RMAX = 4;   // RMAX*IPM_MAXG <= 32 lanes of one warp
+        auto build = [&](const std::vector<int> &ptr, std::vector<int> &item, std::vector<int> &lvl, std::vector<int> &Rl) {
+            item.clear(); lvl.assign(S.nlevels + 1, 0); Rl.assign(S.nlevels, 1);
+            for (int lv = 0; lv < S.nlevels; lv++) {
+                int bestR = 1; long long bestp = -1, bestw = -1;
+                for (int R = 1; R <= RMAX; R *= 2) {
+                    long long items = 0;
+                    for (int w = S.lvl_ptr[lv]; w < S.lvl_ptr[lv + 1]; w++) {
+                        const int i = S.lvl_nodes[w], len = ptr[i + 1] - ptr[i];
+                        items += (len + R * PF - 1) / (R * PF);
+                    }
+                    const long long passes = (items * R + SLOTS - 1) / SLOTS, waste = items * R;
+                    if (bestp < 0 || passes < bestp || (passes == bestp && waste < bestw)) { bestp = passes; bestw = waste; bestR = R; }
+                }
+                Rl[lv] = bestR;
+                const int cap = bestR * PF;
+                for (int w = S.lvl_ptr[lv]; w < S.lvl_ptr[lv + 1]; w++) {
+                    const int i = S.lvl_nodes[w], k0 = ptr[i], k1 = ptr[i + 1];
+                    const int split = (k1 - k0 > cap) ? 1 : 0;
+                    for (int k = k0; k < k1; k += cap) {
+                        item.push_back(i); item.push_back(k); item.push_back(std::min(k + cap, k1)); item.push_back(split);
+                    }
+                }
+                lvl[lv + 1] = (int)(item.size() / 4);
+            }
+            if (item.empty()) item.assign(4, 0);
+        };
+        build(S.Lr_rp, S.fwp_item, S.fwp_lvl, S.fwp_R);
+        build(S.L_cp, S.bwp_item, S.bwp_lvl, S.bwp_R);
+    }
     return true;
 }

@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, "libscpb.so")
+SO = os.environ.get("SCPB_LIBRARY") or os.path.join(HERE, "libscpb.so")   # override: A/B runs of kernel variants
 
 MODEL_DBLINT, MODEL_ROCKET, MODEL_STARSHIP, MODEL_QUADROTOR, MODEL_FREEFLYER = 1, 2, 3, 4, 5
 FOH, IMPULSE = 0, 1
