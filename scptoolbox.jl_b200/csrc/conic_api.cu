@@ -180,12 +180,11 @@ int32_t scpb_cone_setup(scpb_handle h, int32_t n, int32_t p, int32_t m, const in
     UP(soc_dim); UP(soc_off); UP(soc_woff); UP(A_rp); UP(A_ci); UP(G_rp); UP(G_ci);
     UP(At_rp); UP(At_ri); UP(At_vi); UP(Gt_rp); UP(Gt_ri); UP(Gt_vi); UP(iperm);
     UP(L_cp); UP(L_ri); UP(Lr_rp); UP(Lr_pos); UP(Lr_col); UP(lvl_ptr); UP(lvl_nodes);
-    UP(ft_lvl_ptr); UP(ft_target); UP(ft_op_ptr); UP(ft_op_a); UP(ft_op_b);
-    UP(sc_lvl_ptr); UP(sc_pos); UP(sc_col); UP(as_ptr); UP(as_a); UP(as_b); UP(as_c); UP(as_src); UP(as_sign);
+    UP(as_ptr); UP(as_a); UP(as_b); UP(as_c); UP(as_src); UP(as_sign);
 #undef UP
     P.fw_item = (const int4 *)upload_ints(c, S.fw_item); P.bw_item = (const int4 *)upload_ints(c, S.bw_item);
-    P.ft_item = (const int4 *)upload_ints(c, S.ft_item); P.sc_item = (const int4 *)upload_ints(c, S.sc_item);
-    P.lvl_maxlen = upload_ints(c, S.lvl_maxlen);
+    P.fa_item = (const int4 *)upload_ints(c, S.fa_item); P.fb_item = (const int4 *)upload_ints(c, S.fb_item);
+    P.fa_lvl = upload_ints(c, S.fa_lvl); P.fa_R = upload_ints(c, S.fa_R); P.fb_lvl = upload_ints(c, S.fb_lvl);
     P.fwp_item = (const int4 *)upload_ints(c, S.fwp_item); P.bwp_item = (const int4 *)upload_ints(c, S.bwp_item);
     P.fwp_lvl = upload_ints(c, S.fwp_lvl); P.bwp_lvl = upload_ints(c, S.bwp_lvl);
     P.fwp_R = upload_ints(c, S.fwp_R); P.bwp_R = upload_ints(c, S.bwp_R);

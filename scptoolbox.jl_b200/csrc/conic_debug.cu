@@ -23,19 +23,23 @@ extern "C" int32_t scpb_debug_kkt_solve(int32_t n, int32_t p, int32_t m, const i
         for (int k = S.as_ptr[t]; k < S.as_ptr[t + 1]; k++) acc += Gv[S.as_a[k]] * Gv[S.as_b[k]] * wm[S.as_c[k]];
         Y[t] = acc;
     }
-    for (int lv = 0; lv < S.nlevels; lv++) {  // kkt_factor
-        for (int w = S.ft_lvl_ptr[lv]; w < S.ft_lvl_ptr[lv + 1]; w++) {
-            const int t = S.ft_target[w];
-            double acc = Y[t];
-            for (int k = S.ft_op_ptr[w]; k < S.ft_op_ptr[w + 1]; k++) acc -= Y[S.ft_op_a[k]] * Ls[S.ft_op_b[k]];
-            if (t >= S.nnzL) {  // same dynamic regularisation rule as kkt_factor (conic_ipm.cuh)
-                const double sgn = (double)S.as_sign[t];
-                if (!(sgn * acc > delta_dyn)) acc = sgn * delta_dyn;
-                invD[t - S.nnzL] = 1.0 / acc;
-            }
-            Y[t] = acc;
+    for (int lv = 0; lv < S.nlevels; lv++) {  // kkt_factor: balanced program (phase A items, then phase B items)
+        const int R = S.fa_R[lv];
+        for (int w = S.fa_lvl[lv]; w < S.fa_lvl[lv + 1]; w++) {
+            const int *it = &S.fa_item[4 * (size_t)w];
+            if (it[2] - it[1] > R * CONIC_FACTOR_PF) return SCPB_ERR_ARG;
+            double part = 0.0;
+            for (int k = it[1]; k < it[2]; k++) part += Y[S.ft_op[2 * (size_t)k]] * Ls[S.ft_op[2 * (size_t)k + 1]];
+            Y[it[0]] -= part;
         }
-        for (int w = S.sc_lvl_ptr[lv]; w < S.sc_lvl_ptr[lv + 1]; w++) Ls[S.sc_pos[w]] = Y[S.sc_pos[w]] * invD[S.sc_col[w]];
+        for (int w = S.fb_lvl[lv]; w < S.fb_lvl[lv + 1]; w++) {   // every item regularises its own copy of the pivot
+            const int *it = &S.fb_item[4 * (size_t)w];
+            const double sgn = (it[3] & 1) ? 1.0 : -1.0;
+            double d = Y[S.nnzL + it[1]];
+            if (!(sgn * d > delta_dyn)) d = sgn * delta_dyn;
+            if (it[3] & 2) invD[it[1]] = 1.0 / d;
+            else Ls[it[0]] = Y[it[0]] * (1.0 / d);
+        }
     }
     for (int i = 0; i < nk; i++) v[S.iperm[i]] = rhs[i];
     // kkt_ldl_solve_smem: the balanced (split-item) substitution programs, level by level; within a level every

@@ -25,14 +25,12 @@ struct IpmProgram {  // device copies of ConeSymbolic index arrays
     const int *iperm;
     const int *L_cp, *L_ri, *Lr_rp, *Lr_pos, *Lr_col;
     const int *lvl_ptr, *lvl_nodes;
-    const int *ft_lvl_ptr, *ft_target, *ft_op_ptr, *ft_op_a, *ft_op_b;
-    const int *sc_lvl_ptr, *sc_pos, *sc_col;
     const int *as_ptr, *as_a, *as_b, *as_c, *as_src, *as_sign;
-    const int4 *fw_item, *bw_item, *ft_item, *sc_item;
-    const int4 *fwp_item, *bwp_item;
+    const int4 *fw_item, *bw_item;
+    const int4 *fwp_item, *bwp_item, *fa_item, *fb_item;
+    const int *fa_lvl, *fa_R, *fb_lvl;
     const int *fwp_lvl, *bwp_lvl, *fwp_R, *bwp_R;
     const int2 *Lr_pc, *ft_op;
-    const int *lvl_maxlen;   // [3][nlevels]
 };
 
 struct IpmOpts {
@@ -67,7 +65,6 @@ struct IpmData {  // group-blocked device arrays, all for B seeds
 enum { IPM_OPTIMAL = 0, IPM_MAXIT = 1, IPM_NUMERICAL = 2, IPM_ALMOST = 3 };
 
 #define IPM_MAXG 8
-#define IPM_LONG 96   // rows / op lists longer than this are reduced by the whole CTA (arrow rows of global variables)
 #define IPM_NT_MAX 1024
 
 #ifdef CONIC_IPM_IMPL   // the kernel itself is compiled in conic_api.cu only
@@ -77,8 +74,8 @@ struct Ctx {
     // row-type work (sparse dot products): R lanes cooperate on one row for the G seeds of the group;
     // lane layout inside a warp: tid = (item*R + rr)*G + sg, reduced with xor-shuffles over rr
     int R, rr, isl, nisl;               // current per-level values, see set_lanes()
-    const int *s_Rs, *s_Rf;             // per-level lanes-per-row for the substitutions / the factorisation
-    const int *s_lvl, *s_ftl, *s_scl;   // level pointers staged in shared memory
+    const int *s_lvl;                   // level pointers (nodes per level) staged in shared memory
+    int o_fal, o_faR, o_fbl;                // balanced factorisation program: phase A item pointers / lanes, phase B pointers
     int o_fwl, o_bwl, o_fwR, o_bwR, o_vs;   // balanced substitution programs (item pointers, lanes per level) and
                                             // the substitution vector: int offsets into the dynamic shared window
     int Rmax;
@@ -129,22 +126,6 @@ __device__ __forceinline__ void seed_reduce(const Ctx &c, double (&v)[K], int op
 
 #define GI(e) ((size_t)(e) * G + sg)
 
-// choose how many lanes cooperate on one row for a level: as many as keep the level within the minimum
-// number of passes over the CTA (wide leaf levels -> 1 lane per row, narrow separator levels -> 8)
-__device__ __forceinline__ int level_lanes(int width, int maxlen, int nslots, int rmax, int inflight)
-{
-    // cost model in units of one memory latency: passes over the CTA, each followed by the sequential part of the
-    // longest row that is not covered by the `inflight` loads a lane keeps in flight
-    int best = 1, bc = 0x7fffffff;
-    for (int r = 1; r <= rmax; r *= 2) {
-        const int passes = (int)(((long long)width * r + nslots - 1) / nslots);
-        const int per_lane = (maxlen + r - 1) / r;
-        const int seq = (per_lane + inflight - 1) / inflight;
-        const int cost = (passes > 0 ? passes : 1) * (seq > 0 ? seq : 1);
-        if (cost < bc || (cost == bc && r < best)) { bc = cost; best = r; }
-    }
-    return best;
-}
 __device__ __forceinline__ void set_lanes(Ctx &c, int R)
 {
     const int sh = 31 - __clz(R);   // R is a power of two: shifts instead of integer division
@@ -225,78 +206,116 @@ __device__ void kkt_assemble(const IpmProgram &P, const Ctx &c, const IpmData &D
     __syncthreads();
 }
 
+// ---- numeric LDL' : balanced, level-scheduled gather program (conic_symbolic.h, "balanced factorisation program") ----
+// Phase A of a level: an item subtracts at most R*IPM_FPF products Y[a]*Ls[b] from one target; a lane owns at most
+// IPM_FPF of them, so all its op indices and then all its gathers are in flight together.  Targets whose op list was
+// split receive their partial sums through global atomics (hence every read of Y goes to L2, ld.cg).  Phase B finishes
+// the level's columns: each item regularises its own copy of the pivot, the diagonal item stores 1/d, the others
+// scale their entry and store it twice (column order for the backward sweep, row order for the forward sweep).
+// The program data of the next phase (item descriptors, op indices) is requested one phase early.
+// Separate (noinline) function with by-value arguments: see solve_sweep.
+#define IPM_FPF CONIC_FACTOR_PF
+struct FactorArgs {
+    const int4 *fa_item, *fb_item;
+    const int2 *ft_op;
+    double *Y, *Ls, *Lrow, *invD;   // group-blocked, already offset to this CTA's group
+    double delta_dyn;
+    int o_fal, o_faR, o_fbl;        // offsets (ints) into the dynamic shared memory window
+    int nl, nnzLd, G, sg, slot, nslots;
+    long long *lprof;
+};
+extern __shared__ int ipm_smem[];
+
+__device__ __noinline__ void kkt_factor_levels(const FactorArgs a)
+{
+    __builtin_assume(__isGlobal(a.fa_item)); __builtin_assume(__isGlobal(a.fb_item)); __builtin_assume(__isGlobal(a.ft_op));
+    __builtin_assume(__isGlobal(a.Y)); __builtin_assume(__isGlobal(a.Ls)); __builtin_assume(__isGlobal(a.Lrow));
+    __builtin_assume(__isGlobal(a.invD));
+    const int *fal = ipm_smem + a.o_fal, *faR = ipm_smem + a.o_faR, *fbl = ipm_smem + a.o_fbl;
+    const int G = a.G, sg = a.sg, slot = a.slot, nslots = a.nslots;
+    int t_tgt;                 // target | split << 30, or -1
+    int2 t_op[IPM_FPF];        // op indices of this lane (x < 0: none)
+#define IPM_FA_LOAD(LV, OFF)                                                              \
+    {                                                                                     \
+        const int R_ = faR[LV], sh_ = 31 - __clz(R_);                                     \
+        const int w_ = fal[LV] + (OFF) + (slot >> sh_);                                   \
+        t_tgt = -1;                                                                       \
+        _Pragma("unroll") for (int j = 0; j < IPM_FPF; j++) t_op[j] = make_int2(-1, 0);   \
+        if (w_ < fal[(LV) + 1]) {                                                         \
+            const int4 it_ = a.fa_item[w_];                                               \
+            t_tgt = it_.x | (it_.w << 30);                                                \
+            _Pragma("unroll") for (int j = 0; j < IPM_FPF; j++) {                         \
+                const int k_ = it_.y + (slot & (R_ - 1)) + j * R_;                        \
+                if (k_ < it_.z) t_op[j] = a.ft_op[k_];                                    \
+            }                                                                             \
+        }                                                                                 \
+    }
+#define IPM_FA_CONSUME(R)                                                                 \
+    {                                                                                     \
+        double ya_[IPM_FPF], la_[IPM_FPF];                                                \
+        _Pragma("unroll") for (int j = 0; j < IPM_FPF; j++) {                             \
+            const bool on_ = t_op[j].x >= 0;                                              \
+            ya_[j] = on_ ? __ldcg(&a.Y[(size_t)t_op[j].x * G + sg]) : 0.0;                \
+            la_[j] = on_ ? a.Ls[(size_t)t_op[j].y * G + sg] : 0.0;                        \
+        }                                                                                 \
+        double part_ = 0.0;                                                               \
+        _Pragma("unroll") for (int j = 0; j < IPM_FPF; j++) part_ = fma(ya_[j], la_[j], part_); \
+        for (int o_ = G; o_ < G * (R); o_ <<= 1) part_ += __shfl_xor_sync(0xffffffffu, part_, o_); \
+        if (t_tgt >= 0 && (slot & ((R) - 1)) == 0) {                                      \
+            double *p_ = &a.Y[(size_t)(t_tgt & 0x3fffffff) * G + sg];                     \
+            if (t_tgt >> 30) atomicAdd(p_, -part_); else *p_ = __ldcg(p_) - part_;        \
+        }                                                                                 \
+    }
+    IPM_FA_LOAD(0, 0)
+    long long tl_ = a.lprof ? clock64() : 0;
+    for (int lv = 0; lv < a.nl; lv++) {
+        // ---- phase A ----
+        const int R = faR[lv], nisl = nslots >> (31 - __clz(R));
+        const int nA = fal[lv + 1] - fal[lv];
+        const int b0 = fbl[lv], b1 = fbl[lv + 1];
+        int4 sc = make_int4(-1, 0, 0, 0);                    // first phase-B item of this lane, requested early
+        if (b0 + slot < b1) sc = a.fb_item[b0 + slot];
+        if (nA > 0) {
+            IPM_FA_CONSUME(R)
+            for (int off = nisl; off < nA; off += nisl) {    // wide levels: further passes
+                IPM_FA_LOAD(lv, off)
+                IPM_FA_CONSUME(R)
+            }
+        }
+        __syncthreads();
+        // ---- phase B (program data of the next level's phase A requested first) ----
+        if (lv + 1 < a.nl) IPM_FA_LOAD(lv + 1, 0)
+        for (int w = b0 + slot; w < b1; w += nslots) {
+            if (w != b0 + slot) sc = a.fb_item[w];
+            const double sgn = (sc.w & 1) ? 1.0 : -1.0;
+            double d = __ldcg(&a.Y[(size_t)sc.x * G + sg]);   // diagonal item: its own target; others: see below
+            double e = 0.0;
+            if (!(sc.w & 2)) { e = d; d = __ldcg(&a.Y[(size_t)(a.nnzLd + sc.y) * G + sg]); }
+            if (!(sgn * d > a.delta_dyn)) d = sgn * a.delta_dyn;   // dynamic regularisation keeps the expected inertia
+            const double inv = 1.0 / d;
+            if (sc.w & 2) a.invD[(size_t)sc.y * G + sg] = inv;
+            else {
+                const double lv_ = e * inv;
+                a.Ls[(size_t)sc.x * G + sg] = lv_;
+                a.Lrow[(size_t)sc.z * G + sg] = lv_;
+            }
+        }
+        __syncthreads();
+        if (a.lprof) { const long long tn = clock64(); a.lprof[lv] += tn - tl_; tl_ = tn; }
+    }
+#undef IPM_FA_LOAD
+#undef IPM_FA_CONSUME
+}
+
 __device__ void kkt_factor(const IpmProgram &P, Ctx &c, double *Y, double *Ls, double *invD, double delta_dyn)
 {
-    const int G = c.G, sg = c.sg;
-    long long tl_ = c.lprof ? clock64() : 0;
-    for (int lv = 0; lv < P.nlevels; lv++) {
-        set_lanes(c, c.s_Rf[lv]);
-        const int wend = c.s_ftl[lv + 1];
-        for (int w0 = c.s_ftl[lv]; w0 < wend; w0 += c.nisl) {   // uniform trip count: shuffles inside
-            const int w = w0 + c.isl;
-            bool on = w < wend;
-            int4 item = make_int4(0, 0, 0, 0);
-            double part = 0.0, y0t = 0.0;
-            if (on) {
-                item = P.ft_item[w];
-                if (item.z - item.y > IPM_LONG) { on = false; }
-            }
-            if (on) {
-                if (c.rr == 0) y0t = Y[GI(item.x)];
-                const int k1 = item.z;
-                int k = item.y + c.rr;
-                for (; k + 3 * c.R < k1; k += 4 * c.R) {   // four independent gathers in flight
-                    const int2 o0 = P.ft_op[k], o1 = P.ft_op[k + c.R], o2 = P.ft_op[k + 2 * c.R], o3 = P.ft_op[k + 3 * c.R];
-                    const double ya = Y[GI(o0.x)], la = Ls[GI(o0.y)], yb = Y[GI(o1.x)], lb = Ls[GI(o1.y)];
-                    const double yc = Y[GI(o2.x)], lc = Ls[GI(o2.y)], yd = Y[GI(o3.x)], ld = Ls[GI(o3.y)];
-                    part = fma(ya, la, part);
-                    part = fma(yb, lb, part);
-                    part = fma(yc, lc, part);
-                    part = fma(yd, ld, part);
-                }
-                for (; k < k1; k += c.R) { const int2 o0 = P.ft_op[k]; part = fma(Y[GI(o0.x)], Ls[GI(o0.y)], part); }
-            }
-            part = lanes_sum(c, part);
-            if (on && c.rr == 0) {
-                const int t = item.x;
-                double acc = y0t - part;
-                if (t >= P.nnzL) {  // diagonal: dynamic regularisation keeps the expected inertia
-                    const double sgn = (double)item.w;
-                    if (!(sgn * acc > delta_dyn)) acc = sgn * delta_dyn;
-                    invD[GI(t - P.nnzL)] = 1.0 / acc;
-                }
-                Y[GI(t)] = acc;
-            }
-        }
-        if (P.lvl_maxlen[2 * P.nlevels + lv] > IPM_LONG) {   // long op lists: one target at a time, whole CTA
-            for (int w = c.s_ftl[lv]; w < wend; w++) {
-                const int4 item = P.ft_item[w];
-                if (item.z - item.y <= IPM_LONG) continue;
-                double a[1] = {0.0};
-                for (int k = item.y + c.slot; k < item.z; k += c.nslots) { const int2 o0 = P.ft_op[k]; a[0] = fma(Y[GI(o0.x)], Ls[GI(o0.y)], a[0]); }
-                seed_reduce<1>(c, a, 0);
-                if (c.tid < G) {
-                    const int t = item.x;
-                    double acc = Y[(size_t)t * G + c.tid] - c.out[c.tid];
-                    if (t >= P.nnzL) {
-                        const double sgn = (double)item.w;
-                        if (!(sgn * acc > delta_dyn)) acc = sgn * delta_dyn;
-                        invD[(size_t)(t - P.nnzL) * G + c.tid] = 1.0 / acc;
-                    }
-                    Y[(size_t)t * G + c.tid] = acc;
-                }
-            }
-        }
-        __syncthreads();
-        for (int w = c.s_scl[lv] + c.slot; w < c.s_scl[lv + 1]; w += c.nslots) {
-            const int4 it = P.sc_item[w];
-            const double lv_ = Y[GI(it.x)] * invD[GI(it.y)];
-            Ls[GI(it.x)] = lv_;
-            c.Lrow[GI(it.z)] = lv_;
-        }
-        __syncthreads();
-        if (c.lprof) { const long long tn = clock64(); c.lprof[lv] += tn - tl_; tl_ = tn; }
-    }
+    FactorArgs a;
+    a.fa_item = P.fa_item; a.fb_item = P.fb_item; a.ft_op = P.ft_op;
+    a.Y = Y; a.Ls = Ls; a.Lrow = c.Lrow; a.invD = invD; a.delta_dyn = delta_dyn;
+    a.o_fal = c.o_fal; a.o_faR = c.o_faR; a.o_fbl = c.o_fbl;
+    a.nl = P.nlevels; a.nnzLd = P.nnzL; a.G = c.G; a.sg = c.sg; a.slot = c.slot; a.nslots = c.nslots;
+    a.lprof = c.lprof;
+    kkt_factor_levels(a);
 }
 
 // ---- shared-memory, prefetching substitution ------------------------------------------------------------
@@ -317,7 +336,6 @@ struct SweepArgs {
     int nl, lv0, G, sg, slot, nslots;
     long long *lprof;       // per-level cycle counters (CTA 0, thread 0) or nullptr
 };
-extern __shared__ int ipm_smem[];
 
 __device__ __forceinline__ double smem_atomic_add(double *addr, double v)
 {
@@ -796,23 +814,19 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
     __shared__ int s_done[IPM_MAXG], s_status[IPM_MAXG], s_iters[IPM_MAXG], s_alldone, s_save[IPM_MAXG], s_stall[IPM_MAXG];
     __shared__ double s_best[IPM_MAXG], s_bp[IPM_MAXG], s_bd[IPM_MAXG], s_br[3 * IPM_MAXG];
 
-    int *s_lv = ipm_smem;   // [9][nlevels+1]: lvl_ptr, ft_lvl_ptr, sc_lvl_ptr, lanes (2), balanced programs (4)
+    int *s_lv = ipm_smem;   // [9][nlevels+1]: lvl_ptr | fa_lvl | fb_lvl | - | fa_R | fwp_lvl | bwp_lvl | fwp_R | bwp_R
+    const int nl1 = P.nlevels + 1;
     for (int i = threadIdx.x; i <= P.nlevels; i += NT) {
-        s_lv[i] = P.lvl_ptr[i]; s_lv[P.nlevels + 1 + i] = P.ft_lvl_ptr[i]; s_lv[2 * (P.nlevels + 1) + i] = P.sc_lvl_ptr[i];
+        s_lv[i] = P.lvl_ptr[i]; s_lv[nl1 + i] = P.fa_lvl[i]; s_lv[2 * nl1 + i] = P.fb_lvl[i];
+        s_lv[5 * nl1 + i] = P.fwp_lvl[i]; s_lv[6 * nl1 + i] = P.bwp_lvl[i];
     }
-    __syncthreads();
+    for (int i = threadIdx.x; i < P.nlevels; i += NT) {
+        s_lv[4 * nl1 + i] = P.fa_R[i]; s_lv[7 * nl1 + i] = P.fwp_R[i]; s_lv[8 * nl1 + i] = P.bwp_R[i];
+    }
     Ctx c;
-    c.s_lvl = s_lv; c.s_ftl = s_lv + P.nlevels + 1; c.s_scl = s_lv + 2 * (P.nlevels + 1);
-    int *s_R = s_lv + 3 * (P.nlevels + 1);
-    {
-        int *s_p = s_lv + 5 * (P.nlevels + 1);   // [fwp_lvl | bwp_lvl | fwp_R | bwp_R]
-        for (int i = threadIdx.x; i <= P.nlevels; i += NT) { s_p[i] = P.fwp_lvl[i]; s_p[P.nlevels + 1 + i] = P.bwp_lvl[i]; }
-        for (int i = threadIdx.x; i < P.nlevels; i += NT) {
-            s_p[2 * (P.nlevels + 1) + i] = P.fwp_R[i]; s_p[3 * (P.nlevels + 1) + i] = P.bwp_R[i];
-        }
-        c.o_fwl = 5 * (P.nlevels + 1); c.o_bwl = 6 * (P.nlevels + 1); c.o_fwR = 7 * (P.nlevels + 1); c.o_bwR = 8 * (P.nlevels + 1);
-    }
-    c.s_Rs = s_R; c.s_Rf = s_R + P.nlevels;
+    c.s_lvl = s_lv;
+    c.o_fal = nl1; c.o_fbl = 2 * nl1; c.o_faR = 4 * nl1;
+    c.o_fwl = 5 * nl1; c.o_bwl = 6 * nl1; c.o_fwR = 7 * nl1; c.o_bwR = 8 * nl1;
     c.o_vs = (9 * (P.nlevels + 1) + 3) & ~3;
     c.vs = D.vsmem ? (double *)(s_lv + c.o_vs) : nullptr;
     c.G = D.G; c.tid = threadIdx.x; c.sg = c.tid % c.G; c.slot = c.tid / c.G; c.nslots = NT / c.G; c.nwarps = NT / 32;
@@ -822,11 +836,6 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
     c.lprof = (blockIdx.x == 0 && threadIdx.x == 0 && D.prof && D.lvl_prof) ? D.prof + 12 : nullptr;
     if (c.lprof) for (int i = 0; i < 3 * P.nlevels; i++) c.lprof[i] = 0;
     set_lanes(c, c.Rmax);
-    for (int i = threadIdx.x; i < P.nlevels; i += NT) {
-        const int ml = min(IPM_LONG, max(P.lvl_maxlen[i], P.lvl_maxlen[P.nlevels + i]));
-        s_R[i] = level_lanes(s_lv[i + 1] - s_lv[i], ml, c.nslots, c.Rmax, IPM_PF);
-        s_R[P.nlevels + i] = level_lanes(s_lv[P.nlevels + 1 + i + 1] - s_lv[P.nlevels + 1 + i], min(IPM_LONG, P.lvl_maxlen[2 * P.nlevels + i]), c.nslots, c.Rmax, 4);
-    }
     __syncthreads();
     c.red = s_red; c.out = s_out;
     const int G = c.G, sg = c.sg;

@@ -16,6 +16,9 @@
 #include <string>
 #include <vector>
 
+#ifndef CONIC_FACTOR_PF
+#define CONIC_FACTOR_PF 4  // factor ops (gather pairs) a lane keeps in flight per item
+#endif
 #ifndef CONIC_SOLVE_PF
 #define CONIC_SOLVE_PF 4   // L entries a lane keeps in flight per substitution item
 #endif
@@ -65,6 +68,12 @@ struct ConeSymbolic {
     std::vector<int> fwp_item, bwp_item; // int4 {node, start, end, split}
     std::vector<int> fwp_lvl, bwp_lvl;   // nlevels+1 -> index into the item lists
     std::vector<int> fwp_R, bwp_R;       // lanes per item of each level
+    // balanced factorisation program, same idea: phase A items cover at most R*CONIC_FACTOR_PF ops of one target
+    // (Y[target] -= sum Y[a]*Ls[b]; split targets use atomics; targets without ops have no item), phase B items
+    // finish a column: {Y position, column, row-order position, flags}; flags bit0 = expected pivot sign is +,
+    // bit1 = the item is the diagonal itself (regularise, write 1/d), otherwise scale the entry by 1/d.
+    std::vector<int> fa_item, fa_lvl, fa_R;
+    std::vector<int> fb_item, fb_lvl;
     long long factor_ops = 0;
     std::string err;
 };
@@ -341,6 +350,43 @@ inline bool cone_symbolic_build(ConeSymbolic &S, int n, int p, int m, const int 
     }
     S.ft_op.resize(2 * S.ft_op_a.size());
     for (size_t k = 0; k < S.ft_op_a.size(); k++) { S.ft_op[2 * k] = S.ft_op_a[k]; S.ft_op[2 * k + 1] = S.ft_op_b[k]; }
+    // ---- balanced factorisation program ----
+    {
+        const int PF = CONIC_FACTOR_PF, SLOTS = 512, RMAX = 4;
+        S.fa_item.clear(); S.fa_lvl.assign(S.nlevels + 1, 0); S.fa_R.assign(S.nlevels, 1);
+        S.fb_item.clear(); S.fb_lvl.assign(S.nlevels + 1, 0);
+        std::vector<int> rowpos(S.nnzL);
+        for (int w = 0; w < S.nnzL; w++) rowpos[S.Lr_pos[w]] = w;
+        for (int lv = 0; lv < S.nlevels; lv++) {
+            const int w0 = S.ft_lvl_ptr[lv], w1 = S.ft_lvl_ptr[lv + 1];
+            int bestR = 1; long long bestp = -1, bestw = -1;
+            for (int R = 1; R <= RMAX; R *= 2) {
+                long long items = 0;
+                for (int w = w0; w < w1; w++) items += (S.ft_op_ptr[w + 1] - S.ft_op_ptr[w] + R * PF - 1) / (R * PF);
+                const long long passes = (items * R + SLOTS - 1) / SLOTS, waste = items * R;
+                if (bestp < 0 || passes < bestp || (passes == bestp && waste < bestw)) { bestp = passes; bestw = waste; bestR = R; }
+            }
+            S.fa_R[lv] = bestR;
+            const int cap = bestR * PF;
+            for (int w = w0; w < w1; w++) {
+                const int k0 = S.ft_op_ptr[w], k1 = S.ft_op_ptr[w + 1], split = (k1 - k0 > cap) ? 1 : 0;
+                for (int k = k0; k < k1; k += cap) {
+                    S.fa_item.push_back(S.ft_target[w]); S.fa_item.push_back(k);
+                    S.fa_item.push_back(std::min(k + cap, k1)); S.fa_item.push_back(split);
+                }
+            }
+            S.fa_lvl[lv + 1] = (int)(S.fa_item.size() / 4);
+            for (int w = S.lvl_ptr[lv]; w < S.lvl_ptr[lv + 1]; w++) {
+                const int j = S.lvl_nodes[w], pos = (S.as_sign[S.nnzL + j] > 0) ? 1 : 0;
+                S.fb_item.push_back(S.nnzL + j); S.fb_item.push_back(j); S.fb_item.push_back(0); S.fb_item.push_back(pos | 2);
+                for (int q = S.L_cp[j]; q < S.L_cp[j + 1]; q++) {
+                    S.fb_item.push_back(q); S.fb_item.push_back(j); S.fb_item.push_back(rowpos[q]); S.fb_item.push_back(pos);
+                }
+            }
+            S.fb_lvl[lv + 1] = (int)(S.fb_item.size() / 4);
+        }
+        if (S.fa_item.empty()) S.fa_item.assign(4, 0);
+    }
     // ---- balanced substitution programs ----
     {
         const int PF = CONIC_SOLVE_PF, SLOTS = 512, RMAX = 4;   // RMAX*IPM_MAXG <= 32 lanes of one warp
