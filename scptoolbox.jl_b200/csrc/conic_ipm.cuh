@@ -233,40 +233,32 @@ __device__ __noinline__ void kkt_factor_levels(const FactorArgs a)
     __builtin_assume(__isGlobal(a.invD));
     const int *fal = ipm_smem + a.o_fal, *faR = ipm_smem + a.o_faR, *fbl = ipm_smem + a.o_fbl;
     const int G = a.G, sg = a.sg, slot = a.slot, nslots = a.nslots;
-    int t_tgt;                 // target | split << 30, or -1
-    int2 t_op[IPM_FPF];        // op indices of this lane (x < 0: none)
-#define IPM_FA_LOAD(LV, OFF)                                                              \
+    // three-stage software pipeline over the passes of phase A: the item descriptor of pass p+2 and the op indices of
+    // pass p+1 are requested while the gathers of pass p are in flight, so a pass costs one memory latency
+    int t_tgt;                 // current pass: target | split << 30, or -1
+    int2 t_op[IPM_FPF];        // current pass: op indices of this lane (x < 0: none)
+    int i_tgt, i_k0, i_k1;     // next pass: item descriptor (k0 already offset to this lane)
+#define IPM_FA_ITEM(LV, OFF)                                                              \
     {                                                                                     \
         const int R_ = faR[LV], sh_ = 31 - __clz(R_);                                     \
         const int w_ = fal[LV] + (OFF) + (slot >> sh_);                                   \
-        t_tgt = -1;                                                                       \
-        _Pragma("unroll") for (int j = 0; j < IPM_FPF; j++) t_op[j] = make_int2(-1, 0);   \
-        if (w_ < fal[(LV) + 1]) {                                                         \
+        i_tgt = -1; i_k0 = 0; i_k1 = 0;                                                   \
+        if ((OFF) < fal[(LV) + 1] - fal[LV] && w_ < fal[(LV) + 1]) {                      \
             const int4 it_ = a.fa_item[w_];                                               \
-            t_tgt = it_.x | (it_.w << 30);                                                \
-            _Pragma("unroll") for (int j = 0; j < IPM_FPF; j++) {                         \
-                const int k_ = it_.y + (slot & (R_ - 1)) + j * R_;                        \
-                if (k_ < it_.z) t_op[j] = a.ft_op[k_];                                    \
-            }                                                                             \
+            i_tgt = it_.x | (it_.w << 30); i_k0 = it_.y + (slot & (R_ - 1)); i_k1 = it_.z; \
         }                                                                                 \
     }
-#define IPM_FA_CONSUME(R)                                                                 \
+#define IPM_FA_OPS(TGT, OP, R_)                                                           \
     {                                                                                     \
-        double ya_[IPM_FPF], la_[IPM_FPF];                                                \
+        TGT = i_tgt;                                                                      \
         _Pragma("unroll") for (int j = 0; j < IPM_FPF; j++) {                             \
-            const bool on_ = t_op[j].x >= 0;                                              \
-            ya_[j] = on_ ? __ldcg(&a.Y[(size_t)t_op[j].x * G + sg]) : 0.0;                \
-            la_[j] = on_ ? a.Ls[(size_t)t_op[j].y * G + sg] : 0.0;                        \
-        }                                                                                 \
-        double part_ = 0.0;                                                               \
-        _Pragma("unroll") for (int j = 0; j < IPM_FPF; j++) part_ = fma(ya_[j], la_[j], part_); \
-        for (int o_ = G; o_ < G * (R); o_ <<= 1) part_ += __shfl_xor_sync(0xffffffffu, part_, o_); \
-        if (t_tgt >= 0 && (slot & ((R) - 1)) == 0) {                                      \
-            double *p_ = &a.Y[(size_t)(t_tgt & 0x3fffffff) * G + sg];                     \
-            if (t_tgt >> 30) atomicAdd(p_, -part_); else *p_ = __ldcg(p_) - part_;        \
+            const int k_ = i_k0 + j * (R_);                                               \
+            OP[j] = (i_tgt >= 0 && k_ < i_k1) ? a.ft_op[k_] : make_int2(-1, 0);           \
         }                                                                                 \
     }
-    IPM_FA_LOAD(0, 0)
+    IPM_FA_ITEM(0, 0)
+    IPM_FA_OPS(t_tgt, t_op, faR[0])
+    IPM_FA_ITEM(0, (nslots >> (31 - __clz(faR[0]))))
     long long tl_ = a.lprof ? clock64() : 0;
     for (int lv = 0; lv < a.nl; lv++) {
         // ---- phase A ----
@@ -275,36 +267,59 @@ __device__ __noinline__ void kkt_factor_levels(const FactorArgs a)
         const int b0 = fbl[lv], b1 = fbl[lv + 1];
         int4 sc = make_int4(-1, 0, 0, 0);                    // first phase-B item of this lane, requested early
         if (b0 + slot < b1) sc = a.fb_item[b0 + slot];
-        if (nA > 0) {
-            IPM_FA_CONSUME(R)
-            for (int off = nisl; off < nA; off += nisl) {    // wide levels: further passes
-                IPM_FA_LOAD(lv, off)
-                IPM_FA_CONSUME(R)
+        for (int off = 0; off < nA; off += nisl) {
+            double ya_[IPM_FPF], la_[IPM_FPF];
+#pragma unroll
+            for (int j = 0; j < IPM_FPF; j++) {
+                const bool on_ = t_op[j].x >= 0;
+                ya_[j] = on_ ? __ldcg(&a.Y[(size_t)t_op[j].x * G + sg]) : 0.0;
+                la_[j] = on_ ? a.Ls[(size_t)t_op[j].y * G + sg] : 0.0;
             }
+            int n_tgt; int2 n_op[IPM_FPF];
+            IPM_FA_OPS(n_tgt, n_op, R)                       // pass p+1 (descriptor requested one pass ago)
+            IPM_FA_ITEM(lv, off + 2 * nisl)                  // pass p+2
+            double part_ = 0.0;
+#pragma unroll
+            for (int j = 0; j < IPM_FPF; j++) part_ = fma(ya_[j], la_[j], part_);
+            for (int o_ = G; o_ < G * R; o_ <<= 1) part_ += __shfl_xor_sync(0xffffffffu, part_, o_);
+            if (t_tgt >= 0 && (slot & (R - 1)) == 0) {
+                double *p_ = &a.Y[(size_t)(t_tgt & 0x3fffffff) * G + sg];
+                if (t_tgt >> 30) atomicAdd(p_, -part_); else *p_ = __ldcg(p_) - part_;
+            }
+            t_tgt = n_tgt;
+#pragma unroll
+            for (int j = 0; j < IPM_FPF; j++) t_op[j] = n_op[j];
         }
+        // descriptor of the next level's first pass: in flight across the barrier and phase B
+        if (lv + 1 < a.nl) IPM_FA_ITEM(lv + 1, 0)
         __syncthreads();
-        // ---- phase B (program data of the next level's phase A requested first) ----
-        if (lv + 1 < a.nl) IPM_FA_LOAD(lv + 1, 0)
+        // ---- phase B: one latency per pass (the next item is requested while the current loads are in flight) ----
         for (int w = b0 + slot; w < b1; w += nslots) {
-            if (w != b0 + slot) sc = a.fb_item[w];
             const double sgn = (sc.w & 1) ? 1.0 : -1.0;
-            double d = __ldcg(&a.Y[(size_t)sc.x * G + sg]);   // diagonal item: its own target; others: see below
-            double e = 0.0;
-            if (!(sc.w & 2)) { e = d; d = __ldcg(&a.Y[(size_t)(a.nnzLd + sc.y) * G + sg]); }
+            const bool isd = (sc.w & 2) != 0;
+            const double e = __ldcg(&a.Y[(size_t)sc.x * G + sg]);
+            double d = isd ? e : __ldcg(&a.Y[(size_t)(a.nnzLd + sc.y) * G + sg]);
+            const int4 cur = sc;
+            if (w + nslots < b1) sc = a.fb_item[w + nslots];
             if (!(sgn * d > a.delta_dyn)) d = sgn * a.delta_dyn;   // dynamic regularisation keeps the expected inertia
             const double inv = 1.0 / d;
-            if (sc.w & 2) a.invD[(size_t)sc.y * G + sg] = inv;
+            if (isd) a.invD[(size_t)cur.y * G + sg] = inv;
             else {
                 const double lv_ = e * inv;
-                a.Ls[(size_t)sc.x * G + sg] = lv_;
-                a.Lrow[(size_t)sc.z * G + sg] = lv_;
+                a.Ls[(size_t)cur.x * G + sg] = lv_;
+                a.Lrow[(size_t)cur.z * G + sg] = lv_;
             }
+        }
+        if (lv + 1 < a.nl) {   // op indices of the next level's first pass, descriptor of its second pass
+            const int Rn = faR[lv + 1];
+            IPM_FA_OPS(t_tgt, t_op, Rn)
+            IPM_FA_ITEM(lv + 1, (nslots >> (31 - __clz(Rn))))
         }
         __syncthreads();
         if (a.lprof) { const long long tn = clock64(); a.lprof[lv] += tn - tl_; tl_ = tn; }
     }
-#undef IPM_FA_LOAD
-#undef IPM_FA_CONSUME
+#undef IPM_FA_ITEM
+#undef IPM_FA_OPS
 }
 
 __device__ void kkt_factor(const IpmProgram &P, Ctx &c, double *Y, double *Ls, double *invD, double delta_dyn)
