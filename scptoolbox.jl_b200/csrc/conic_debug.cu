@@ -29,7 +29,7 @@ extern "C" int32_t scpb_debug_kkt_solve(int32_t n, int32_t p, int32_t m, const i
             const int *it = &S.fa_item[4 * (size_t)w];
             if (it[2] - it[1] > R * CONIC_FACTOR_PF) return SCPB_ERR_ARG;
             double part = 0.0;
-            for (int k = it[1]; k < it[2]; k++) part += Y[S.ft_op[2 * (size_t)k]] * Ls[S.ft_op[2 * (size_t)k + 1]];
+            for (int k = it[1]; k < it[2]; k++) part += Y[S.ft_op[2 * (size_t)k]] * Ls[S.Lr_pos[S.ft_op[2 * (size_t)k + 1]]];
             Y[it[0]] -= part;
         }
         for (int w = S.fb_lvl[lv]; w < S.fb_lvl[lv + 1]; w++) {   // every item regularises its own copy of the pivot

@@ -273,7 +273,7 @@ __device__ __noinline__ void kkt_factor_levels(const FactorArgs a)
             for (int j = 0; j < IPM_FPF; j++) {
                 const bool on_ = t_op[j].x >= 0;
                 ya_[j] = on_ ? __ldcg(&a.Y[(size_t)t_op[j].x * G + sg]) : 0.0;
-                la_[j] = on_ ? a.Ls[(size_t)t_op[j].y * G + sg] : 0.0;
+                la_[j] = on_ ? a.Lrow[(size_t)t_op[j].y * G + sg] : 0.0;   // row order: consecutive within an item
             }
             int n_tgt; int2 n_op[IPM_FPF];
             IPM_FA_OPS(n_tgt, n_op, R)                       // pass p+1 (descriptor requested one pass ago)

@@ -348,8 +348,16 @@ inline bool cone_symbolic_build(ConeSymbolic &S, int n, int p, int m, const int 
         for (int w = S.ft_lvl_ptr[lv]; w < S.ft_lvl_ptr[lv + 1]; w++)
             S.lvl_maxlen[2 * S.nlevels + lv] = std::max(S.lvl_maxlen[2 * S.nlevels + lv], S.ft_op_ptr[w + 1] - S.ft_op_ptr[w]);
     }
-    S.ft_op.resize(2 * S.ft_op_a.size());
-    for (size_t k = 0; k < S.ft_op_a.size(); k++) { S.ft_op[2 * k] = S.ft_op_a[k]; S.ft_op[2 * k + 1] = S.ft_op_b[k]; }
+    // op pairs for the kernel: {Y operand (column-order position), L operand as ROW-order position}.  The ops of a
+    // target (i,j) run over all of row j (pattern(row j) is contained in pattern(row i) by the fill rule), so in row
+    // order the L operands of an item are consecutive doubles: full 32-byte sectors instead of scattered gathers.
+    // (Storing Y in row order as well was measured and is slower: the assembly then scatters its writes.)
+    {
+        std::vector<int> rowpos(S.nnzL);
+        for (int w = 0; w < S.nnzL; w++) rowpos[S.Lr_pos[w]] = w;
+        S.ft_op.resize(2 * S.ft_op_a.size());
+        for (size_t k = 0; k < S.ft_op_a.size(); k++) { S.ft_op[2 * k] = S.ft_op_a[k]; S.ft_op[2 * k + 1] = rowpos[S.ft_op_b[k]]; }
+    }
     // ---- balanced factorisation program ----
     {
         const int PF = CONIC_FACTOR_PF, SLOTS = 512, RMAX = 4;
