@@ -99,7 +99,8 @@ typedef struct {
     int32_t group;                  /* seeds per CTA (power of two <= 32); 0 = automatic */
     int32_t equil;                  /* Ruiz equilibration passes; <0: default 5, 0: off    */
     int32_t threads;                /* threads per CTA: 1024 (default) or 512              */
-    int32_t lanes;                  /* lanes cooperating on one sparse row (1,2,4,8); 0: 8 */
+    int32_t lanes;                  /* lanes per sparse row in the fallback substitution that is used when the
+                                     * vector does not fit shared memory (1,2,4,8); 0: 8   */
 } scpb_cone_opts;
 
 /* per-seed status (termination_status, program.jl:427-428): */
@@ -114,7 +115,8 @@ int32_t scpb_cone_setup(scpb_handle h, int32_t n, int32_t p, int32_t m,
 /* info[20] = {n+p, nnz(L), elimination-tree levels, factor ops, assembly ops, |W^-2|, group, capacity,
  *             8 SM-cycle counters of the last launch (CTA 0): equilibrate, start point, residuals,
  *             scaling+assembly, factorisation, KKT solves, line search+update, total;
- *             forward-substitution cycles, backward-substitution cycles, number of LDL' solves, 0} */
+ *             forward-substitution cycles, backward-substitution cycles, number of LDL' solves,
+ *             number of factorisations (= interior-point iterations of CTA 0)} */
 int32_t scpb_cone_info(scpb_cone c, int64_t *info);
 int32_t scpb_cone_free(scpb_cone c);
 /* host arrays, seed-major: Avals[B][nnzA], Gvals[B][nnzG], c[B][n], b[B][p], h[B][m];

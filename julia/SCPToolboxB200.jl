@@ -44,9 +44,9 @@ end
 
 struct ConeOpts
     feastol::Float64; abstol::Float64; reltol::Float64; delta::Float64; delta_dyn::Float64
-    maxit::Int32; nref::Int32; verbose::Int32; group::Int32; equil::Int32
-end
-ConeOpts(; maxit = 0, verbose = 0) = ConeOpts(0, 0, 0, 0, 0, maxit, -1, verbose, 0, -1)
+    maxit::Int32; nref::Int32; verbose::Int32; group::Int32; equil::Int32; threads::Int32; lanes::Int32
+end   # field order and types mirror scpb_cone_opts (include/scpb.h)
+ConeOpts(; maxit = 0, verbose = 0) = ConeOpts(0, 0, 0, 0, 0, maxit, -1, verbose, 0, -1, 0, 0)
 
 function cone_setup(h::Handle, n, p, m, A_rp, A_ci, G_rp, G_ci, l, soc_dims::Vector{Int32}, perm)
     out = Ref{Ptr{Cvoid}}(C_NULL)
