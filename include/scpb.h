@@ -82,6 +82,14 @@ int32_t scpb_discretize_dev(scpb_handle h, int32_t method, int32_t B, int32_t N,
                             double *A, double *Bm, double *Bp, double *F, double *r, double *E,
                             double *defect, int32_t *feas);
 
+/* ---- propagate(sol, pbm; res): final continuous-time state trajectory of B converged solutions ----
+ * replaces src/solvers/discretization.jl:515-562 (FOH branch), called by SCPSolution (src/solvers/scp.jl:231-232,
+ * res = 2*Nsub*(N-1)).  RK4 of the nonlinear dynamics over LinRange(0,1,res) from xd[:,1], the input linearly
+ * interpolated over the whole grid, integration actions after every step.
+ * xc[B][res][nx]: per seed Julia's column-major nx x res matrix (values of the Trajectory xc). */
+int32_t scpb_propagate(scpb_handle h, int32_t method, int32_t B, int32_t N, int32_t res, const double *t_grid,
+                       const double *xd, const double *ud, const double *p, double *xc, double *seconds);
+
 /* ---- batched cone solver: replaces solve!(prg) -> JuMP.optimize! -> ECOS (program.jl:419-424) ----
  *   min c'x  s.t.  A x = b,  G x + s = h,  s in K = R+^l x SOC(q_1) x ... x SOC(q_nsoc)
  * (the standard form MathOptInterface hands to ECOS).  The sparsity pattern and the cone partition are

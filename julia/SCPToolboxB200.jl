@@ -42,6 +42,16 @@ function discretize!(h::Handle, t_grid, xd, ud, p, iSx, feas_tol, Nsub, A, Bm, B
     return secs[]
 end
 
+# propagate(sol, pbm; res) (src/solvers/discretization.jl:515-562, FOH): returns the nx x res matrix of xc values
+function propagate(h::Handle, N, res, t_grid, xd, ud, p)
+    xc = Matrix{Float64}(undef, size(xd, 1), res)
+    secs = Ref{Float64}(0.0)
+    check(h, ccall((:scpb_propagate, libscpb), Int32,
+        (Ptr{Cvoid}, Int32, Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+         Ptr{Float64}), h.ptr, 0, 1, N, res, t_grid, xd, ud, p, xc, secs), "scpb_propagate")
+    return xc
+end
+
 struct ConeOpts
     feastol::Float64; abstol::Float64; reltol::Float64; delta::Float64; delta_dyn::Float64
     maxit::Int32; nref::Int32; verbose::Int32; group::Int32; equil::Int32; threads::Int32; lanes::Int32

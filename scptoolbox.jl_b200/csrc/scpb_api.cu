@@ -1,6 +1,7 @@
 // scpb_api.cu -- C ABI entry points (include/scpb.h): lifetime, model selection, discretize.
 #include "handle.cuh"
 #include "discretize.cuh"
+#include "propagate.cuh"
 
 static int check_model(scpb_handle_s *h)
 {
@@ -232,3 +233,57 @@ int32_t scpb_discretize(scpb_handle h, int32_t method, int32_t B, int32_t N, int
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// scpb_propagate: final continuous-time trajectory (discretization.jl:515-562, FOH branch)
+template <class M>
+static void launch_prop(scpb_handle_s *h, const PropArgs &a)
+{
+    k_propagate_foh<M><<<(a.B + 31) / 32, 32, 0, h->stream>>>(a);
+    h->launches++;
+}
+
+int32_t scpb_propagate(scpb_handle h, int32_t method, int32_t B, int32_t N, int32_t res, const double *t_grid,
+                       const double *xd, const double *ud, const double *p, double *xc, double *seconds)
+{
+    int rc = check_model(h);
+    if (rc) return rc;
+    if (method != SCPB_FOH) return set_err(h, SCPB_ERR_UNSUPPORTED, "only FOH propagation is implemented");
+    if (!t_grid || !xd || !ud || !p || !xc) return set_err(h, SCPB_ERR_ARG, "null pointer");
+    if (B <= 0 || N < 2 || res < 2) return set_err(h, SCPB_ERR_ARG, "bad sizes B=%d N=%d res=%d", B, N, res);
+    SCPB_CUDA(h, cudaSetDevice(h->device));
+    const size_t nx = h->nx, nu = h->nu, np = h->np, nb = B;
+    const size_t s_t = N, s_x = nb * N * nx, s_u = nb * N * nu, s_p = nb * np, s_c = nb * (size_t)res * nx;
+    double *din = (double *)h->scratch(1, sizeof(double) * (s_t + s_x + s_u + s_p));
+    double *dout = (double *)h->scratch(2, sizeof(double) * s_c);
+    if (!din || !dout) return set_err(h, SCPB_ERR_CUDA, "device allocation failed");
+    double *d_t = din, *d_x = d_t + s_t, *d_u = d_x + s_x, *d_p = d_u + s_u;
+    cudaStream_t st = h->stream;
+    SCPB_CUDA(h, cudaMemcpyAsync(d_t, t_grid, sizeof(double) * s_t, cudaMemcpyHostToDevice, st));
+    SCPB_CUDA(h, cudaMemcpyAsync(d_x, xd, sizeof(double) * s_x, cudaMemcpyHostToDevice, st));
+    SCPB_CUDA(h, cudaMemcpyAsync(d_u, ud, sizeof(double) * s_u, cudaMemcpyHostToDevice, st));
+    SCPB_CUDA(h, cudaMemcpyAsync(d_p, p, sizeof(double) * s_p, cudaMemcpyHostToDevice, st));
+    PropArgs a{};
+    a.B = B; a.N = N; a.res = res; a.t_grid = d_t; a.xd = d_x; a.ud = d_u; a.p = d_p; a.np = (int)np; a.xc = dout;
+    a.par = h->par;
+    cudaEvent_t e0, e1;
+    SCPB_CUDA(h, cudaEventCreate(&e0)); SCPB_CUDA(h, cudaEventCreate(&e1));
+    SCPB_CUDA(h, cudaEventRecord(e0, st));
+    switch (h->model_id) {
+    case SCPB_MODEL_DBLINT: launch_prop<Model<SCPB_MODEL_DBLINT>>(h, a); break;
+    case SCPB_MODEL_ROCKET: launch_prop<Model<SCPB_MODEL_ROCKET>>(h, a); break;
+    case SCPB_MODEL_STARSHIP: launch_prop<Model<SCPB_MODEL_STARSHIP>>(h, a); break;
+    case SCPB_MODEL_QUADROTOR: launch_prop<Model<SCPB_MODEL_QUADROTOR>>(h, a); break;
+    case SCPB_MODEL_FREEFLYER: launch_prop<Model<SCPB_MODEL_FREEFLYER>>(h, a); break;
+    default: cudaEventDestroy(e0); cudaEventDestroy(e1); return set_err(h, SCPB_ERR_MODEL, "unknown model id %d", h->model_id);
+    }
+    SCPB_CUDA(h, cudaEventRecord(e1, st));
+    SCPB_CUDA(h, cudaGetLastError());
+    SCPB_CUDA(h, cudaMemcpyAsync(xc, dout, sizeof(double) * s_c, cudaMemcpyDeviceToHost, st));
+    SCPB_CUDA(h, cudaStreamSynchronize(st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (seconds) *seconds = 1e-3 * ms;
+    return SCPB_OK;
+}

@@ -39,6 +39,7 @@ SIGNATURES = {
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p]),
+    "scpb_propagate": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _dp, _dp, _dp, _dp]),
     "scpb_cone_setup": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _ip, _ip, _ip, _ip, C.c_int32,
                                     C.c_int32, _ip, _ip, C.POINTER(C.c_void_p)]),
     "scpb_cone_info": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64)]),
@@ -169,6 +170,25 @@ class Handle:
         self._check(rc, "scpb_discretize")
         out["seconds"] = sec.value
         return out
+
+    def propagate(self, t_grid, xd, ud, p, res, method=FOH):
+        """propagate(sol, pbm; res) for a batch (discretization.jl:515-562): xd (B, N, nx), ud (B, N, nu), p (B, np).
+
+        Returns (tc (res,), xc (B, res, nx), seconds): per seed xc[b].T is the reference's nx x res matrix."""
+        xd, pxd = _f64(xd)
+        ud, pud = _f64(ud)
+        p, pp = _f64(p)
+        tg, ptg = _f64(t_grid)
+        B, N = xd.shape[0], xd.shape[1]
+        assert xd.shape == (B, N, self.nx) and ud.shape == (B, N, self.nu) and p.shape == (B, self.np)
+        xc = np.empty((B, int(res), self.nx))
+        sec = C.c_double(0.0)
+        rc = self.lib.scpb_propagate(self.h, method, B, N, int(res), ptg, pxd, pud, pp, xc.ctypes.data_as(_dp),
+                                     C.byref(sec))
+        self._check(rc, "scpb_propagate")
+        d = res - 1
+        tc = np.array([(1.0 - j / d) * 0.0 + (j / d) * 1.0 for j in range(res)])
+        return tc, xc, sec.value
 
     def discretize_dev(self, t_grid, xd, ud, p, iSx_diag, feas_tol, Nsub, A, Bm, Bp, F, r, E, defect, feas,
                        B, N, method=FOH):

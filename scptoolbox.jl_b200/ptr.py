@@ -286,6 +286,8 @@ class SCPBatchSolution:      # batched SCPSolution (scp.jl:105-119)
     feas: np.ndarray
     timing: dict
     raw_status: np.ndarray
+    tc: np.ndarray = None       # continuous-time grid and state trajectory xc (B, res, nx): filled by propagate()
+    xc: np.ndarray = None
 
 
 def create(pars: Parameters, traj, handle, l1_block=4) -> SCPProblem:
@@ -330,3 +332,15 @@ def solve(pbm: SCPProblem, guesses=None, **cone_opts) -> SCPBatchSolution:
     tm = dict(discretize=timing[0], formulate=timing[1], solve=timing[2], overhead=timing[3], total=timing[4],
               lockstep_iterations=int(timing[5]), ipm_iterations=int(timing[6]))
     return SCPBatchSolution(names, iters, J, pbm.t, xd, ud, p, dev, feas, tm, status)
+
+
+def propagate(pbm: SCPProblem, sol: SCPBatchSolution, res=None) -> SCPBatchSolution:
+    """The continuous-time part of SCPSolution (scp.jl:228-236): xc = propagate(last_sol, pbm; res = 2*Nsub*(N-1))
+    (discretization.jl:515-562) for every seed of the batch, on the device.  The reference only propagates solved
+    trajectories; here failed seeds are propagated as well (their xc is simply not meaningful)."""
+    pars = pbm.pars
+    res = int(res) if res is not None else 2 * pars.Nsub * (pars.N - 1)
+    pbm.handle.model_set(pbm.traj.model_id, pbm.traj.model_par, pbm.traj.nx, pbm.traj.nu, pbm.traj.np)
+    sol.tc, sol.xc, sec = pbm.handle.propagate(pbm.t, sol.xd, sol.ud, sol.p, res)
+    sol.timing["propagate"] = sec
+    return sol

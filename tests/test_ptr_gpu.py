@@ -9,7 +9,7 @@ North-star target is 1e-6 on the trajectory."""
 import numpy as np
 import pytest
 
-from oracle import problems, ptr as optr
+from oracle import orc, problems, ptr as optr
 
 pytestmark = pytest.mark.gpu
 
@@ -104,8 +104,15 @@ def test_fixed_iteration_ptr_parity(pkg, handle):
     P0 = np.array([g[2] * (1 + (0.02 * rng.uniform(-1, 1, g[2].shape) if b else 0.0)) for b in range(nb)])
     pbm = pkg.ptr.create(pars, traj, handle)
     sol = pkg.ptr.solve(pbm, (X0, U0, P0))
+    pkg.ptr.propagate(pbm, sol)            # SCPSolution's continuous-time trajectory (scp.jl:231-232)
     pbm.close()
+    assert sol.xc.shape == (nb, 2 * Nsub * (N - 1), 8)
     for b in range(nb):
+        # the propagated trajectory of the product's own solution: oracle propagate on the same (xd, ud, p)
+        xco = orc.propagate(pbo.orc_model(), sol.xd[b], sol.ud[b], sol.p[b], sol.xc.shape[1])
+        assert np.abs(sol.xc[b] - xco).max() <= 1e-9 * max(1.0, np.abs(xco).max())
+        # a converged solution is dynamically feasible: the roll-out from node 0 ends near the last node
+        assert np.abs((sol.xc[b][-1, :7] - sol.xd[b][-1, :7]) / sc.Sx[:7]).max() <= 0.1
         ref = P.solve((X0[b], U0[b], P0[b]), prefer="ipm")
         rs = ref["sol"]
         assert int(sol.iterations[b]) == ref["iterations"] == K
