@@ -240,10 +240,18 @@ class DoubleIntegratorProblem(_DynOnly):
 
 
 class RocketProblem(_DynOnly):
-    """rocket_landing/parameters.jl:78-150 (Mars powered descent), free-final-time variant."""
+    """Mars powered-descent guidance as a free-final-time PTR problem (BASELINE config C2).
+
+    The reference ships this vehicle only as a single-shot LCvx program (rocket_landing/definition.jl:33-140); the
+    SCP form below is a NEW definition on the same data (parameters.jl:78-150): state x = [r(3) v(3) z = ln m],
+    input u = [a(3) xi] (thrust acceleration and its slack), parameter p = [tf], dynamics f = tf (A_c x + B_c u + p_c)
+    (parameters.jl:110-121), constraints of definition.jl:93-131 with the mass profile z0 evaluated on a NOMINAL
+    flight time (so that every constraint stays convex in (x, u, p): thrust-magnitude bounds mu = rho exp(-z0) are
+    node constants), terminal cost -z_N (maximum final mass).  There is no nonconvex path constraint."""
     name = "rocket"
     model_id = orc.MODEL_ROCKET
     nx, nu, np = 7, 4, 1
+    ns = 0
 
     def __init__(self, N: int):
         self.N = N
@@ -264,9 +272,84 @@ class RocketProblem(_DynOnly):
         self.r0 = (2 * ex + 0 * ey + 1.5 * ez) * 1e3
         self.v0 = 80 * ex + 30 * ey - 75 * ez
         self.alpha = 1 / (self.Isp * 9.807 * math.cos(self.phi))
+        self.tf_min, self.tf_max, self.tf_nom = 50.0, 110.0, 75.0
+        cg, sg = math.cos(self.gamma_gs), math.sin(self.gamma_gs)
+        self.H_gs = np.array([[cg, 0, -sg], [-cg, 0, -sg], [0, cg, -sg], [0, -cg, -sg]])
 
     def par(self):
         return np.concatenate([self.g, self.omega, [self.alpha]])
+
+    # node constants of the thrust / mass bounds (definition.jl:93-104) on the nominal time grid
+    def z0(self, tau):
+        return math.log(self.m_wet - self.alpha * self.rho_max * tau * self.tf_nom)
+
+    def z1(self, tau):
+        return math.log(self.m_wet - self.alpha * self.rho_min * tau * self.tf_nom)
+
+    def ranges(self):
+        amax = self.rho_max / self.m_dry
+        xrg = [(-500.0, 2500.0), (-500.0, 500.0), (0.0, 1600.0), (-100.0, 100.0), (-100.0, 100.0), (-100.0, 100.0),
+               (math.log(self.m_dry), math.log(self.m_wet))]
+        urg = [(-amax * math.sin(self.gamma_p), amax * math.sin(self.gamma_p))] * 2 + [(0.0, amax), (0.0, amax)]
+        prg = [(self.tf_min, self.tf_max)]
+        return xrg, urg, prg
+
+    has_running_cost = False
+
+    def cost_aff(self, x, u, p, t):
+        dz = math.log(self.m_wet) - math.log(self.m_dry)
+        return (x[6, -1] - math.log(self.m_wet)) * (-1.0 / dz)      # fraction of the propellant budget spent
+
+    def guess(self, N):
+        tau = np.arange(N) / (N - 1)
+        xg = np.zeros((N, 7)); ug = np.zeros((N, 4))
+        for k in range(N):
+            xg[k, 0:3] = (1 - tau[k]) * self.r0
+            xg[k, 3:6] = (1 - tau[k]) * self.v0
+            xg[k, 6] = (1 - tau[k]) * math.log(self.m_wet) + tau[k] * math.log(0.5 * (self.m_dry + self.m_wet))
+            ug[k, 0:3] = -self.g
+            ug[k, 3] = np.linalg.norm(self.g)
+        return xg, ug, np.array([self.tf_nom])
+
+    # boundary conditions (definition.jl:124-131); the final-mass inequality is a state constraint at node N
+    def gic(self, x, p):
+        rhs = np.concatenate([self.r0, self.v0, [math.log(self.m_wet)]])
+        return x[0:7] - rhs
+
+    def H0(self, x, p):
+        return np.eye(7)
+
+    K0 = None
+
+    def gtc(self, x, p):
+        return x[0:6] - np.zeros(6)
+
+    def Hf(self, x, p):
+        H = np.zeros((6, 7)); H[np.arange(6), np.arange(6)] = 1.0
+        return H
+
+    Kf = None
+
+    def emit_X(self, prg, t, k, x, p):
+        r, v, z = x[0:3], x[3:6], x[6]
+        prg.nonpos([self.z0(t) - z], "mass_lower")
+        prg.nonpos([z - self.z1(t)], "mass_upper")
+        for i in range(4):
+            prg.nonpos([r[0] * self.H_gs[i, 0] + r[1] * self.H_gs[i, 1] + r[2] * self.H_gs[i, 2]], "glide_slope")
+        prg.soc([self.v_max + 0.0 * v[0], v[0], v[1], v[2]], "max_speed")
+        if k == self.N:
+            prg.nonpos([math.log(self.m_dry) - z], "dry_mass")
+        prg.nonpos([p[0] - self.tf_max], "max_time")
+        prg.nonpos([self.tf_min - p[0]], "min_time")
+
+    def emit_U(self, prg, t, k, u, p):
+        a, xi = u[0:3], u[3]
+        prg.soc([xi, a[0], a[1], a[2]], "lcvx_equality")
+        prg.nonpos([xi * math.cos(self.gamma_p) - a[2]], "pointing")
+        # thrust magnitude bounds: the mass entering mu = rho/m is the node constant exp(z0) (nominal profile)
+        mu_min, mu_max = self.rho_min * math.exp(-self.z0(t)), self.rho_max * math.exp(-self.z0(t))
+        prg.nonpos([mu_min - xi], "min_thrust")
+        prg.nonpos([xi - mu_max], "max_thrust")
 
 
 class QuadrotorProblem(_DynOnly):

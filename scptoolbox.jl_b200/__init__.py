@@ -6,4 +6,5 @@ The directory name carries a dot, so the package is imported under the alias
 from . import lib, ordering, parser, problem, ptr  # noqa: F401
 from . import examples  # noqa: F401
 from .examples import starship as _starship  # noqa: F401
+from .examples import rocket_landing as _rocket_landing  # noqa: F401
 from .lib import Handle, ScpbError  # noqa: F401

@@ -122,3 +122,72 @@ def test_fixed_iteration_ptr_parity(pkg, handle):
         dJ = abs(sol.cost[b] - rs.J_aug) / max(1.0, abs(rs.J_aug))
         print("fixed-iteration parity seed", b, "ex(phys)", ex7, "eu(T,delta)", eu2, "ep", ep, "dJ", dJ)
         assert max(ex7, eu2, ep) <= 1e-4 and dJ <= 1e-6
+
+
+def _rocket_setup(pkg, handle, N, Nsub, iter_max=20):
+    ex = pkg.examples.rocket_landing
+    mdl = ex.RocketProblem()
+    traj = pkg.problem.TrajectoryProblem(mdl)
+    ex.define_problem(traj, "ptr", handle=handle)
+    pars = pkg.ptr.Parameters(N=N, Nsub=Nsub, iter_max=iter_max, disc_method=pkg.ptr.FOH, wvc=1e3, wtr=0.1,
+                              eps_abs=1e-5, eps_rel=0.01 / 100, feas_tol=1e-3, q_tr=np.inf, q_exit=np.inf,
+                              solver_opts={"verbose": 0, "maxit": 100})
+    return mdl, traj, pars
+
+
+def test_rocket_landing_ptr_matches_oracle_ptr(pkg, handle):
+    """BASELINE config C2 (rocket_landing PTR, a new definition on the reference's vehicle data): second-order cones
+    inside the SCP loop (thrust slack and speed limit at every node).  Same tolerances as the starship case."""
+    N, Nsub, nb = 12, 15, 3
+    mdl, traj, pars = _rocket_setup(pkg, handle, N, Nsub)
+    pbo = problems.RocketProblem(N)
+    g = pbo.guess(N)
+    opars = optr.Parameters(N=N, Nsub=Nsub, iter_max=20, wvc=1e3, wtr=0.1, eps_abs=1e-5, eps_rel=0.01 / 100,
+                            feas_tol=1e-3, solver_tol=1e-9)
+    P = optr.PTR(pbo, opars)
+    sc = P.scale
+    rng = np.random.default_rng(21)
+    X0 = np.array([g[0] + (0.01 * sc.Sx * rng.standard_normal(g[0].shape) if b else 0.0) for b in range(nb)])
+    U0 = np.array([g[1] + (0.01 * sc.Su * rng.standard_normal(g[1].shape) if b else 0.0) for b in range(nb)])
+    P0 = np.array([g[2] * (1 + (0.02 * rng.uniform(-1, 1, g[2].shape) if b else 0.0)) for b in range(nb)])
+    pbm = pkg.ptr.create(pars, traj, handle)
+    assert list(pbm.cp["soc_dims"]) == [4] * (2 * N)
+    sol = pkg.ptr.solve(pbm, (X0, U0, P0))
+    pbm.close()
+    for b in range(nb):
+        ref = P.solve((X0[b], U0[b], P0[b]), prefer="ipm")
+        rs = ref["sol"]
+        assert sol.status[b] == ref["status"] == "SCP_SOLVED", (sol.status, sol.raw_status, ref["status"])
+        assert abs(int(sol.iterations[b]) - ref["iterations"]) <= 1
+        ex = np.abs((sol.xd[b] - rs.xd) / sc.Sx).max()
+        eu = np.abs((sol.ud[b] - rs.ud) / sc.Su).max()
+        ep = np.abs((sol.p[b] - rs.p) / sc.Sp).max()
+        dJ = abs(sol.cost[b] - rs.J_aug) / max(1.0, abs(rs.J_aug))
+        print("rocket parity seed", b, "ex", ex, "eu", eu, "ep", ep, "dJ", dJ, "iters", sol.iterations[b], ref["iterations"])
+        assert dJ <= 1e-6 and max(ex, eu, ep) <= 1e-4
+        assert bool(sol.feas[b])
+        # the converged landing is physical: thrust slack tight (LCvx), final mass above dry mass
+        a, xi = sol.ud[b][:, 0:3], sol.ud[b][:, 3]
+        assert (np.linalg.norm(a, axis=1) <= xi * (1 + 1e-6) + 1e-9).all()
+        assert np.exp(sol.xd[b][-1, 6]) >= mdl.m_dry * (1 - 1e-9)
+
+
+def test_rocket_landing_batch_c2_size(pkg, handle):
+    """C2 at its node count (N = 50) on a 64-seed batch: every seed must reach SCP_SOLVED, dynamically feasible."""
+    N, Nsub, nb = 50, 15, 64
+    mdl, traj, pars = _rocket_setup(pkg, handle, N, Nsub)
+    pbm = pkg.ptr.create(pars, traj, handle)
+    g = traj.guess(N)
+    rng = np.random.default_rng(5)
+    X0 = np.array([g[0] + 0.01 * pbm.scale.Sx * rng.standard_normal(g[0].shape) for _ in range(nb)])
+    U0 = np.array([g[1] + 0.01 * pbm.scale.Su * rng.standard_normal(g[1].shape) for _ in range(nb)])
+    P0 = np.array([g[2] * (1 + 0.02 * rng.uniform(-1, 1, g[2].shape)) for _ in range(nb)])
+    sol = pkg.ptr.solve(pbm, (X0, U0, P0))
+    info = pbm.cone.info()
+    pbm.close()
+    print("rocket C2: iterations", sol.iterations.min(), sol.iterations.max(), "solve s", sol.timing["solve"],
+          "total s", sol.timing["total"], "nk", info["nk"], "nnzL", info["nnzL"], "levels", info["levels"])
+    assert all(s == "SCP_SOLVED" for s in sol.status), (sol.status, sol.raw_status)
+    assert sol.feas.all()
+    mf = np.exp(sol.xd[:, -1, 6])
+    assert (mf >= mdl.m_dry * (1 - 1e-9)).all() and np.ptp(mf) <= 1e-2 * mf.mean()   # all seeds find the same landing

@@ -22,12 +22,13 @@ def _sources(sm, pbo, P, ref):
         src[sm.oE + k * nx * nx: sm.oE + (k + 1) * nx * nx] = d.E[k].flatten(order="F")
     t = P.t
     for k in range(N):
-        a = (t[k], k + 1, ref.xd[k], ref.ud[k], ref.p)
-        Cm, Dm, Gm, s = pbo.C(*a), pbo.D(*a), pbo.G(*a), pbo.s(*a)
-        src[sm.oC + k * ns * nx: sm.oC + (k + 1) * ns * nx] = Cm.flatten()
-        src[sm.oD + k * ns * nu: sm.oD + (k + 1) * ns * nu] = Dm.flatten()
-        src[sm.oG + k * ns * np_: sm.oG + (k + 1) * ns * np_] = Gm.flatten()
-        src[sm.ors + k * ns: sm.ors + (k + 1) * ns] = s - Cm @ ref.xd[k] - Dm @ ref.ud[k] - Gm @ ref.p
+        if ns:
+            a = (t[k], k + 1, ref.xd[k], ref.ud[k], ref.p)
+            Cm, Dm, Gm, s = pbo.C(*a), pbo.D(*a), pbo.G(*a), pbo.s(*a)
+            src[sm.oC + k * ns * nx: sm.oC + (k + 1) * ns * nx] = Cm.flatten()
+            src[sm.oD + k * ns * nu: sm.oD + (k + 1) * ns * nu] = Dm.flatten()
+            src[sm.oG + k * ns * np_: sm.oG + (k + 1) * ns * np_] = Gm.flatten()
+            src[sm.ors + k * ns: sm.ors + (k + 1) * ns] = s - Cm @ ref.xd[k] - Dm @ ref.ud[k] - Gm @ ref.p
         src[sm.oxh + k * nx: sm.oxh + (k + 1) * nx] = (ref.xd[k] - P.scale.cx) * P.scale.iSx
         src[sm.ouh + k * nu: sm.ouh + (k + 1) * nu] = (ref.ud[k] - P.scale.cu) * P.scale.iSu
     src[sm.oph: sm.oph + np_] = (ref.p - P.scale.cp) * P.scale.iSp
@@ -82,3 +83,43 @@ def test_template_matches_oracle_subproblem(pkg, N, monkeypatch):
     # stage ordering covers every KKT node exactly once
     perm = pbm.perm
     assert sorted(perm.tolist()) == list(range(n + p_))
+
+
+def test_rocket_template_matches_oracle_subproblem(pkg, monkeypatch):
+    """Same check for the SOC-constrained PTR case (rocket landing, BASELINE config C2): two SOC(4) cones per node."""
+    N = 10
+    pbo = problems.RocketProblem(N)
+    xd, ud, p = problems.test_trajectory(pbo, 1, N, seed=3)
+    opars = optr.Parameters(N=N, Nsub=15, iter_max=5, wvc=1e3, wtr=0.1, eps_abs=1e-5, eps_rel=1e-4, feas_tol=1e-3)
+    P = optr.PTR(pbo, opars)
+    ref = P.make_solution(xd[0], ud[0], p[0])
+    prg, _ = P.build(ref)
+    ocp = prg.compile()
+    ex = pkg.examples.rocket_landing
+    mdl = ex.RocketProblem()
+    traj = pkg.problem.TrajectoryProblem(mdl)
+    ex.define_problem(traj, "ptr", handle=None)
+    pars = pkg.ptr.Parameters(N=N, Nsub=15, iter_max=5, disc_method=pkg.ptr.FOH, wvc=1e3, wtr=0.1, eps_abs=1e-5,
+                              eps_rel=1e-4, feas_tol=1e-3, q_tr=np.inf, q_exit=np.inf)
+
+    class FakeHandle:
+        def model_set(self, *a): pass
+    monkeypatch.setattr(pkg.lib, "ConeProblem", lambda *a, **k: type("C", (), {"c": None, "close": lambda s: None})())
+    fake = FakeHandle(); fake.lib = type("L", (), {"scpb_ptr_setup": staticmethod(lambda *a: 0)})(); fake.h = None
+    fake._check = lambda rc, what: None
+    pbm = pkg.ptr.SCPProblem(pars, traj, fake, l1_block=0)
+    cp, sm = pbm.cp, pbm.sm
+    vals = pbm.W @ _sources(sm, pbo, P, ref)
+    n, p_, m = cp["n"], cp["p"], cp["m"]
+    assert (n, p_, m, cp["l"]) == (ocp["c"].size, ocp["A"].shape[0], ocp["G"].shape[0], ocp["l"])
+    assert list(cp["soc_dims"]) == list(ocp["q"]) == [4] * (2 * N)
+    A = sp.csr_matrix((vals[:cp["nnzA"]], cp["A"].indices, cp["A"].indptr), shape=(p_, n))
+    G = sp.csr_matrix((vals[cp["nnzA"]:cp["nnzA"] + cp["nnzG"]], cp["G"].indices, cp["G"].indptr), shape=(m, n))
+    tol = 1e-12
+    assert abs(A - ocp["A"]).max() <= tol * max(1.0, abs(ocp["A"]).max())
+    assert abs(G - ocp["G"]).max() <= tol * max(1.0, abs(ocp["G"]).max())
+    c = vals[cp["off_c"]:cp["off_c"] + n]; b = vals[cp["off_b"]:cp["off_b"] + p_]; h = vals[cp["off_h"]:cp["off_h"] + m]
+    assert np.abs(c - ocp["c"]).max() <= tol * max(1.0, np.abs(ocp["c"]).max())
+    assert np.abs(b - ocp["b"]).max() <= 1e-11 * max(1.0, np.abs(ocp["b"]).max())
+    assert np.abs(h - ocp["h"]).max() <= 1e-11 * max(1.0, np.abs(ocp["h"]).max())
+    assert abs(vals[-1] - ocp["c0"]) <= 1e-12
