@@ -224,19 +224,74 @@ class _DynOnly:
 
 
 class DoubleIntegratorProblem(_DynOnly):
-    """double_integrator/parameters.jl:50-64 (friction g), free-final-time variant."""
+    """Double integrator with friction as a free-final-time, minimum-time PTR problem (BASELINE config C1).
+
+    The reference ships this plant only as a fixed-time LCvx program (double_integrator/definition.jl:38-118 on
+    parameters.jl:50-64: f = [x2; u - g], travel distance s, two parameter choices); the SCP form is a NEW definition
+    on the same data: x = [position, velocity], |u| <= u_max = 2 (the outer bound of definition.jl:60-65),
+    p = [tf], f = tf [x2; u - g], rest-to-rest over the distance s, cost tf.  Its continuous-time optimum is the
+    bang-bang law of the maximum principle (cf. solve_mp, definition.jl:137-294), available in closed form:
+    see t_opt()."""
     name = "dblint"
     model_id = orc.MODEL_DBLINT
     nx, nu, np = 2, 1, 1
+    ns = 0
 
     def __init__(self, N: int, choice: int = 1):
         self.N = N
         self.g = 0.1 if choice == 1 else 0.6
         self.s = 47.0 if choice == 1 else 30.0
         self.T = 10.0
+        self.u_max = 2.0
+        self.tf_min, self.tf_max = 1.0, 30.0
 
     def par(self):
         return np.array([self.g])
+
+    def t_opt(self):
+        """minimum time: accelerate with a1 = u_max - g until t1, brake with a2 = u_max + g"""
+        a1, a2 = self.u_max - self.g, self.u_max + self.g
+        t1 = math.sqrt(2 * self.s * a2 / (a1 * (a1 + a2)))
+        return t1 * (1 + a1 / a2), t1
+
+    def ranges(self):
+        vmax = 2.0 * self.s / 8.0
+        return [(0.0, self.s), (0.0, vmax)], [(-self.u_max, self.u_max)], [(self.tf_min, self.tf_max)]
+
+    has_running_cost = False
+
+    def cost_aff(self, x, u, p, t):
+        return p[0] * (1.0 / self.T)
+
+    def guess(self, N):
+        tau = np.arange(N) / (N - 1)
+        xg = np.zeros((N, 2)); ug = np.zeros((N, 1))
+        xg[:, 0] = tau * self.s
+        xg[:, 1] = self.s / self.T
+        return xg, ug, np.array([self.T])
+
+    def gic(self, x, p):
+        return x[0:2] - np.zeros(2)
+
+    def H0(self, x, p):
+        return np.eye(2)
+
+    K0 = None
+
+    def gtc(self, x, p):
+        return x[0:2] - np.array([self.s, 0.0])
+
+    def Hf(self, x, p):
+        return np.eye(2)
+
+    Kf = None
+
+    def emit_X(self, prg, t, k, x, p):
+        prg.nonpos([p[0] - self.tf_max], "max_time")
+        prg.nonpos([self.tf_min - p[0]], "min_time")
+
+    def emit_U(self, prg, t, k, u, p):
+        prg.l1([self.u_max + 0.0 * u[0], u[0]], "input_bound")
 
 
 class RocketProblem(_DynOnly):

@@ -7,4 +7,5 @@ from . import lib, ordering, parser, problem, ptr  # noqa: F401
 from . import examples  # noqa: F401
 from .examples import starship as _starship  # noqa: F401
 from .examples import rocket_landing as _rocket_landing  # noqa: F401
+from .examples import double_integrator as _double_integrator  # noqa: F401
 from .lib import Handle, ScpbError  # noqa: F401

@@ -191,3 +191,32 @@ def test_rocket_landing_batch_c2_size(pkg, handle):
     assert sol.feas.all()
     mf = np.exp(sol.xd[:, -1, 6])
     assert (mf >= mdl.m_dry * (1 - 1e-9)).all() and np.ptp(mf) <= 1e-2 * mf.mean()   # all seeds find the same landing
+
+
+def test_double_integrator_min_time_known_answer(pkg, handle):
+    """BASELINE config C1 (double integrator PTR, N = 30, one seed): the CUDA path against the oracle PTR AND against the
+    closed-form maximum-principle optimum (minimum time of the bang-bang law)."""
+    N, Nsub = 30, 10
+    for choice in (1, 2):
+        ex = pkg.examples.double_integrator
+        mdl = ex.DoubleIntegratorProblem(choice)
+        traj = pkg.problem.TrajectoryProblem(mdl)
+        ex.define_problem(traj, "ptr", handle=handle)
+        pars = pkg.ptr.Parameters(N=N, Nsub=Nsub, iter_max=30, disc_method=pkg.ptr.FOH, wvc=1e3, wtr=0.1, eps_abs=1e-5,
+                                  eps_rel=1e-4, feas_tol=1e-3, q_tr=np.inf, q_exit=np.inf)
+        pbm = pkg.ptr.create(pars, traj, handle)
+        sol = pkg.ptr.solve(pbm)                    # the problem's own guess, one seed
+        pbm.close()
+        pbo = problems.DoubleIntegratorProblem(N, choice)
+        opars = optr.Parameters(N=N, Nsub=Nsub, iter_max=30, wvc=1e3, wtr=0.1, eps_abs=1e-5, eps_rel=1e-4,
+                                feas_tol=1e-3, solver_tol=1e-9)
+        ref = optr.PTR(pbo, opars).solve(pbo.guess(N))
+        T, _ = mdl.t_opt()
+        print("dblint choice", choice, "tf", sol.p[0, 0], "oracle", ref["sol"].p[0], "analytic", T, "iters",
+              sol.iterations[0], ref["iterations"])
+        assert sol.status[0] == ref["status"] == "SCP_SOLVED"
+        assert abs(int(sol.iterations[0]) - ref["iterations"]) <= 1
+        assert T * (1 - 1e-6) <= sol.p[0, 0] <= T * (1 + 5e-3)
+        assert abs(sol.p[0, 0] - ref["sol"].p[0]) <= 1e-5 * T
+        assert np.abs(sol.xd[0] - ref["sol"].xd).max() <= 1e-4 * mdl.s
+        assert abs(sol.cost[0] - ref["sol"].J_aug) <= 1e-6 * max(1.0, abs(ref["sol"].J_aug))
