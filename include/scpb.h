@@ -167,6 +167,26 @@ int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *u
                        const scpb_cone_opts *opts, double *xd, double *ud, double *p, int32_t *status,
                        int32_t *iters, double *J, double *deviation, int32_t *feas, double *timing);
 
+/* ---- batched SCvx loop: replaces the body of SCvx.solve (src/solvers/scvx.jl:460-546) for B seeds ----
+ * Same template machinery as PTR: scpb_ptr_setup with the SCvx flavour of the subproblem (scptoolbox.jl_b200/scvx.py,
+ * mirror of scvx.jl:225-303, 578-701, 804-901): no trust-region variables, the radius eta is the per-seed source
+ * `oeta`.  scpb_scvx_attach adds what the ratio test needs: the algorithm constants (scvx.jl:57-81) and the sparse
+ * rows Q (over the scaled solver variables of the x, u, p blocks, constants Q_const) of
+ *   row 0: original cost L(x,u,p);  rows 1..n_ic: g_ic(x_1,p);  rows n_ic+1..n_ic+n_tc: g_tc(x_N,p)
+ * which, with the defects of discretize! and the constraint pack's s, give the nonlinear augmented cost
+ * (actual_cost_penalty!, scvx.jl:919-951).  scpb_scvx_solve returns what SCPSolution keeps of the last subproblem
+ * (scp.jl:205-236): trajectory, status (0/1 solved, 2+16*cone status failed), iterations, J_aug, deviation, feas,
+ * and the final trust-region radius per seed. */
+typedef struct {
+    double lam, rho_0, rho_1, rho_2, beta_sh, beta_gr, eta_init, eta_lb, eta_ub;
+    int32_t oeta, n_ic, n_tc, reserved;
+} scpb_scvx_desc;
+int32_t scpb_scvx_attach(scpb_ptr ptr, const scpb_scvx_desc *desc, const int32_t *Q_rowptr, const int32_t *Q_colind,
+                         const double *Q_vals, const double *Q_const);
+int32_t scpb_scvx_solve(scpb_ptr ptr, int32_t B, const double *xd0, const double *ud0, const double *p0,
+                        const scpb_cone_opts *opts, double *xd, double *ud, double *p, int32_t *status,
+                        int32_t *iters, double *J, double *deviation, int32_t *feas, double *eta, double *timing);
+
 /* Diagnostic: per-level cycle counters of CTA 0 in the last scpb_cone_solve / scpb_ptr_solve launch, recorded
  * only when the environment variable SCPB_LEVEL_PROFILE is set: out[0..L) numeric factorisation, out[L..2L)
  * forward substitution, out[2L..3L) backward substitution (L = info[2] levels); cap >= 3L. */

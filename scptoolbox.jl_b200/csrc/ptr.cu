@@ -31,6 +31,8 @@ struct PtrDev {
     const double *t_grid, *Sx, *cx, *Su, *cu, *Sp, *cp;
     double *src;
     ModelPar par;
+    const double *eta = nullptr;   // SCvx: per-seed trust-region radius written to source oeta (scvx.jl:245)
+    int oeta = 0;
 };
 
 __device__ __forceinline__ size_t gaddr(int b, int G, long long E, long long e)
@@ -65,6 +67,7 @@ __global__ void k_linearize(const PtrDev d, const double *xd, const double *ud, 
     if (k == 0) {
         for (int j = 0; j < d.np; j++) d.src[gaddr(b, G, E, d.oph + j)] = (pp[j] - d.cp[j]) / d.Sp[j];
         d.src[gaddr(b, G, E, 0)] = 1.0;
+        if (d.eta) d.src[gaddr(b, G, E, d.oeta)] = d.eta[b];
     }
 }
 
@@ -200,6 +203,13 @@ struct scpb_ptr_s {
     double *src = nullptr, *xd = nullptr, *ud = nullptr, *p = nullptr, *xn = nullptr, *un = nullptr, *pn = nullptr;
     double *defect = nullptr, *J_ref = nullptr, *J_new = nullptr, *devi = nullptr, *imp = nullptr, *c0 = nullptr;
     int *feas = nullptr, *done = nullptr, *status = nullptr, *iters = nullptr, *nactive = nullptr;
+    // SCvx (scpb_scvx_attach)
+    bool scvx = false;
+    scpb_scvx_desc sv{};
+    int *Q_rp = nullptr, *Q_ci = nullptr;
+    double *Q_v = nullptr, *Q_c = nullptr;
+    double *src2 = nullptr, *eta = nullptr, *L_new = nullptr, *J_out = nullptr;
+    int *accept = nullptr;
 };
 
 template <class T>
@@ -234,6 +244,11 @@ static int ptr_reserve(scpb_ptr_s *s, int B, int G)
     s->feas = (int *)al(sizeof(int) * Bpad); s->done = (int *)al(sizeof(int) * Bpad);
     s->status = (int *)al(sizeof(int) * Bpad); s->iters = (int *)al(sizeof(int) * Bpad);
     s->nactive = (int *)al(sizeof(int));
+    if (s->scvx) {
+        s->src2 = (double *)al(sizeof(double) * (size_t)d.nsrc * Bpad);
+        s->eta = (double *)al(sizeof(double) * Bpad); s->L_new = (double *)al(sizeof(double) * Bpad);
+        s->J_out = (double *)al(sizeof(double) * Bpad); s->accept = (int *)al(sizeof(int) * Bpad);
+    }
     if (!ok) return set_err(h, SCPB_ERR_CUDA, "ptr: device allocation failed (B=%d)", B);
     s->capB = Bpad; s->capG = G;
     return SCPB_OK;
@@ -246,8 +261,10 @@ static OutView grouped(double *src, int G, long long nsrc, long long off, long l
     return v;
 }
 
-static int run_discretize(scpb_ptr_s *s, int B, int G, const double *xd, const double *ud, const double *p)
+static int run_discretize(scpb_ptr_s *s, int B, int G, const double *xd, const double *ud, const double *p,
+                          double *srcbuf = nullptr)
 {
+    double *sb = srcbuf ? srcbuf : s->src;
     const scpb_ptr_desc &d = s->d;
     DiscArgs a{};
     a.B = B; a.N = d.N; a.Nsub = d.Nsub;
@@ -258,15 +275,154 @@ static int run_discretize(scpb_ptr_s *s, int B, int G, const double *xd, const d
     a.psB = d.np; a.psE = 1;
     a.f_packed = 1;
     const long long nx = d.nx, nu = d.nu;
-    a.A = grouped(s->src, G, d.nsrc, d.oA, nx * nx);
-    a.Bm = grouped(s->src, G, d.nsrc, d.oBm, nx * nu);
-    a.Bp = grouped(s->src, G, d.nsrc, d.oBp, nx * nu);
-    a.F = grouped(s->src, G, d.nsrc, d.oF, nx * d.nf);
-    a.r = grouped(s->src, G, d.nsrc, d.or_, nx);
-    a.E = grouped(s->src, G, d.nsrc, d.oE, nx * nx);
+    a.A = grouped(sb, G, d.nsrc, d.oA, nx * nx);
+    a.Bm = grouped(sb, G, d.nsrc, d.oBm, nx * nu);
+    a.Bp = grouped(sb, G, d.nsrc, d.oBp, nx * nu);
+    a.F = grouped(sb, G, d.nsrc, d.oF, nx * d.nf);
+    a.r = grouped(sb, G, d.nsrc, d.or_, nx);
+    a.E = grouped(sb, G, d.nsrc, d.oE, nx * nx);
     OutView df{}; df.ptr = s->defect; df.Gq = 1; df.sGrp = (long long)(d.N - 1) * nx; df.sB = 0; df.sK = nx; df.sE = 1;
     a.defect = df;
     return scpb_internal_discretize(s->h, a, d.feas_tol, s->feas);
+}
+
+
+// ----------------------------------------------------------------------------------------------
+// SCvx (src/solvers/scvx.jl): nonlinear augmented cost, ratio test, accept / reject, radius update
+struct ScvxDev {
+    int B, G, N, nx, nu, np, n_ic, n_tc, vx, vu, vp, q_exit, iter, iter_max, nsrc, dltv_lo, dltv_hi;
+    double lam, rho_0, rho_1, rho_2, beta_sh, beta_gr, eta_lb, eta_ub, eps_abs, eps_rel;
+    const int *Q_rp, *Q_ci;
+    const double *Q_v, *Q_c;
+    const double *Sx, *cx, *Su, *cu, *Sp, *cp, *t_grid, *defect;
+    ModelPar par;
+    double *xd, *ud, *p, *xn, *un, *pn;
+    double *J_ref, *J_new, *L_new, *J_out, *eta, *dev;
+    const int *cone_status, *feas_new;
+    int *done, *status, *iters, *nactive, *accept;
+    double *src, *src2;
+};
+
+// value of solver variable v (scaled) at the physical trajectory (x, u, p): only x, u, p blocks may appear in Q
+__device__ __forceinline__ double scvx_var(const ScvxDev &d, const double *x, const double *u, const double *p, int v)
+{
+    if (v >= d.vx && v < d.vx + d.N * d.nx) { const int e = v - d.vx, i = e % d.nx; return (x[e] - d.cx[i]) / d.Sx[i]; }
+    if (v >= d.vu && v < d.vu + d.N * d.nu) { const int e = v - d.vu, i = e % d.nu; return (u[e] - d.cu[i]) / d.Su[i]; }
+    const int j = v - d.vp;
+    return (p[j] - d.cp[j]) / d.Sp[j];
+}
+
+// one thread per seed: J = L + lambda (trapz_k(|defect_k|_1 + |max(s_k, 0)|_1) + |g_ic|_1 + |g_tc|_1)
+// (solution_cost! / actual_cost_penalty!, scvx.jl:919-988) of the trajectory (x, u, p) whose defects are in d.defect
+template <class CP>
+__global__ void k_scvx_cost(const ScvxDev d, const double *xall, const double *uall, const double *pall, double *J, double *L)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= d.B) return;
+    if (d.done[b]) return;
+    const double *x = xall + (size_t)b * d.N * d.nx, *u = uall + (size_t)b * d.N * d.nu, *p = pall + (size_t)b * d.np;
+    double q0 = 0.0, gsum = 0.0;
+    for (int r = 0; r < 1 + d.n_ic + d.n_tc; r++) {
+        double acc = d.Q_c[r];
+        for (int k = d.Q_rp[r]; k < d.Q_rp[r + 1]; k++) acc = fma(d.Q_v[k], scvx_var(d, x, u, p, d.Q_ci[k]), acc);
+        if (r == 0) q0 = acc; else gsum += fabs(acc);
+    }
+    double pen = 0.0, Pprev = 0.0;
+    for (int k = 0; k < d.N; k++) {
+        double Pk = 0.0;
+        if (k < d.N - 1)
+            for (int i = 0; i < d.nx; i++) Pk += fabs(d.defect[((size_t)b * (d.N - 1) + k) * d.nx + i]);
+        if constexpr (CP::NS > 0) {
+            constexpr int NS = CP::NS, NX = CP::NX, NU = CP::NU, NP = CP::NP;
+            double s[NS], C[NS * NX], D[NS * NU], Gm[NS * NP];
+            CP::eval(d.par, d.t_grid[k], d.N, x + (size_t)k * d.nx, u + (size_t)k * d.nu, p, s, C, D, Gm);
+            for (int r = 0; r < NS; r++) Pk += fmax(s[r], 0.0);
+        }
+        Pk *= d.lam;
+        if (k > 0) pen += (Pk + Pprev) * (0.5 * (d.t_grid[k] - d.t_grid[k - 1]));   // trapz, helper.jl:560-568
+        Pprev = Pk;
+    }
+    L[b] = q0;
+    J[b] = q0 + (pen + d.lam * gsum);
+}
+
+// one thread per seed: check_stopping_criterion! (scvx.jl:711-733), update_trust_region! / update_rule (:745-770,
+// 1000-1045).  The candidate (xn, un, pn) becomes the reference when accepted; it is also what the loop returns when
+// it stops or runs out of iterations (SCPSolution takes the last subproblem's solution, scp.jl:205-236).
+__global__ void k_scvx_step(const ScvxDev d)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= d.B) return;
+    d.accept[b] = 0;
+    if (d.done[b]) return;
+    const int cs = d.cone_status[b];
+    if (!(cs == IPM_OPTIMAL || cs == IPM_ALMOST)) {  // unsafe_solution, scp.jl:965-980
+        d.done[b] = 1; d.status[b] = 2 + 16 * cs; d.iters[b] = d.iter;
+        return;
+    }
+    const int q = d.q_exit;
+    double dp = 0.0;
+    for (int j = 0; j < d.np; j++) dp = qnorm_acc(dp, (d.pn[(size_t)b * d.np + j] - d.p[(size_t)b * d.np + j]) / d.Sp[j], q);
+    if (q == 2) dp = sqrt(dp);
+    double dx = 0.0;
+    for (int k = 0; k < d.N; k++) {
+        double a = 0.0;
+        for (int j = 0; j < d.nx; j++) {
+            const size_t o = ((size_t)b * d.N + k) * d.nx + j;
+            a = qnorm_acc(a, (d.xn[o] - d.xd[o]) / d.Sx[j], q);
+        }
+        if (q == 2) a = sqrt(a);
+        dx = fmax(dx, a);
+    }
+    const double deviation = dp + dx;
+    d.dev[b] = deviation;
+    const double Jr = d.J_ref[b], Jn = d.J_new[b], Ln = d.L_new[b];
+    const double pre = Jr - Ln;                        // pre_improv = J_ref - L(sol)  (scvx.jl:724-726)
+    const double pre_rel = pre / fabs(Jr);
+    const bool stop = d.iter > 1 && d.feas_new[b] && (pre_rel <= d.eps_rel || deviation <= d.eps_abs);
+    bool acc = true;
+    double eta = d.eta[b];
+    if (!stop) {
+        const double rho = (Jr - Jn) / pre;
+        if (rho < d.rho_0) { eta = fmax(d.eta_lb, eta / d.beta_sh); acc = false; }
+        else if (d.rho_0 <= rho && rho < d.rho_1) eta = fmax(d.eta_lb, eta / d.beta_sh);
+        else if (d.rho_1 <= rho && rho < d.rho_2) {}
+        else eta = fmin(d.eta_ub, d.beta_gr * eta);
+        d.eta[b] = eta;
+    }
+    const bool last = stop || d.iter >= d.iter_max;
+    if (acc || last) {
+        for (int k = 0; k < d.N; k++) {
+            for (int j = 0; j < d.nx; j++) { const size_t o = ((size_t)b * d.N + k) * d.nx + j; d.xd[o] = d.xn[o]; }
+            for (int j = 0; j < d.nu; j++) { const size_t o = ((size_t)b * d.N + k) * d.nu + j; d.ud[o] = d.un[o]; }
+        }
+        for (int j = 0; j < d.np; j++) d.p[(size_t)b * d.np + j] = d.pn[(size_t)b * d.np + j];
+        d.J_ref[b] = Jn;
+    }
+    d.accept[b] = (acc && !last) ? 1 : 0;
+    d.J_out[b] = Jn;
+    d.iters[b] = d.iter;
+    if (stop) { d.done[b] = 1; d.status[b] = 0; }
+    else atomicAdd(d.nactive, 1);
+}
+
+// accepted seeds: the candidate's DLTV blocks (written by discretize! into src2) become the reference linearisation
+__global__ void k_scvx_take_dltv(const ScvxDev d)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long span = d.dltv_hi - d.dltv_lo;
+    if (i >= span * d.B) return;
+    const int b = (int)(i % d.B);
+    if (!d.accept[b]) return;
+    const long long e = d.dltv_lo + i / d.B;
+    const size_t a = gaddr(b, d.G, d.nsrc, e);
+    d.src[a] = d.src2[a];
+}
+
+__global__ void k_fill(double *v, double a, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = a;
 }
 
 extern "C" {
@@ -412,6 +568,179 @@ int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *u
     if (J) SCPB_CUDA(h, cudaMemcpyAsync(J, s->J_ref, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
     if (deviation) SCPB_CUDA(h, cudaMemcpyAsync(deviation, s->devi, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
     if (feas) SCPB_CUDA(h, cudaMemcpyAsync(feas, s->feas, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    SCPB_CUDA(h, cudaStreamSynchronize(st));
+    double acc[4] = {0, 0, 0, 0};
+    for (size_t i = 1; i < ev.size(); i++) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+        if (phase[i] >= 0) acc[phase[i]] += ms * 1e-3;
+    }
+    float tot_ms = 0.f;
+    cudaEventElapsedTime(&tot_ms, ev.front(), ev.back());
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    if (timing) {
+        timing[0] = acc[0]; timing[1] = acc[1]; timing[2] = acc[2]; timing[3] = acc[3];
+        timing[4] = tot_ms * 1e-3; timing[5] = (double)total_it; timing[6] = (double)ipm_iters; timing[7] = 0.0;
+    }
+    return SCPB_OK;
+}
+
+int32_t scpb_scvx_attach(scpb_ptr s, const scpb_scvx_desc *desc, const int32_t *Q_rowptr, const int32_t *Q_colind,
+                         const double *Q_vals, const double *Q_const)
+{
+    if (!s) return SCPB_ERR_ARG;
+    scpb_handle_s *h = s->h;
+    if (!desc || !Q_rowptr || !Q_colind || !Q_vals || !Q_const) return set_err(h, SCPB_ERR_ARG, "scvx_attach: null pointer");
+    const scpb_ptr_desc &d = s->d;
+    if (desc->oeta <= 0 || desc->oeta >= d.nsrc || desc->n_ic < 0 || desc->n_tc < 0)
+        return set_err(h, SCPB_ERR_ARG, "scvx_attach: bad descriptor (oeta=%d)", desc->oeta);
+    const int nq = 1 + desc->n_ic + desc->n_tc, nnz = Q_rowptr[nq];
+    for (int k = 0; k < nnz; k++) {
+        const int v = Q_colind[k];
+        const bool ok = (v >= d.vx && v < d.vx + d.N * d.nx) || (v >= d.vu && v < d.vu + d.N * d.nu) ||
+                        (v >= d.vp && v < d.vp + d.np);
+        if (!ok) return set_err(h, SCPB_ERR_ARG, "scvx_attach: Q references solver variable %d outside x, u, p", v);
+    }
+    SCPB_CUDA(h, cudaSetDevice(h->device));
+    s->sv = *desc;
+    s->Q_rp = up(s, Q_rowptr, (size_t)nq + 1);
+    s->Q_ci = up(s, Q_colind, (size_t)nnz);
+    s->Q_v = up(s, Q_vals, (size_t)nnz);
+    s->Q_c = up(s, Q_const, (size_t)nq);
+    if (!s->Q_rp || !s->Q_ci || !s->Q_v || !s->Q_c) return set_err(h, SCPB_ERR_CUDA, "scvx_attach: device allocation failed");
+    s->scvx = true;
+    s->capB = 0;   // batch buffers are re-reserved with the SCvx extras
+    return SCPB_OK;
+}
+
+int32_t scpb_scvx_solve(scpb_ptr s, int32_t B, const double *xd0, const double *ud0, const double *p0,
+                        const scpb_cone_opts *opts, double *xd, double *ud, double *p, int32_t *status,
+                        int32_t *iters, double *J, double *deviation, int32_t *feas, double *eta, double *timing)
+{
+    if (!s) return SCPB_ERR_ARG;
+    scpb_handle_s *h = s->h;
+    if (!s->scvx) return set_err(h, SCPB_ERR_STATE, "scvx_solve: call scpb_scvx_attach first");
+    if (B <= 0 || !xd0 || !ud0 || !p0) return set_err(h, SCPB_ERR_ARG, "scvx_solve: bad arguments");
+    SCPB_CUDA(h, cudaSetDevice(h->device));
+    const scpb_ptr_desc &d = s->d;
+    const scpb_scvx_desc &v = s->sv;
+    const int G = scpb_internal_pick_group(B, opts ? opts->group : 0);
+    int rc = scpb_internal_cone_reserve(s->cone, B, G, opts ? opts->lanes : 0);
+    if (rc) return rc;
+    if ((rc = ptr_reserve(s, B, G))) return rc;
+    IpmData *D = scpb_internal_cone_data(s->cone);
+    const ConeSymbolic *S = scpb_internal_cone_sym(s->cone);
+    const IpmOpts o = scpb_internal_make_opts(opts);
+    cudaStream_t st = h->stream;
+    const size_t nX = (size_t)B * d.N * d.nx, nU = (size_t)B * d.N * d.nu, nP = (size_t)B * d.np;
+    SCPB_CUDA(h, cudaMemcpyAsync(s->xd, xd0, sizeof(double) * nX, cudaMemcpyHostToDevice, st));
+    SCPB_CUDA(h, cudaMemcpyAsync(s->ud, ud0, sizeof(double) * nU, cudaMemcpyHostToDevice, st));
+    SCPB_CUDA(h, cudaMemcpyAsync(s->p, p0, sizeof(double) * nP, cudaMemcpyHostToDevice, st));
+    SCPB_CUDA(h, cudaMemsetAsync(s->src, 0, sizeof(double) * (size_t)d.nsrc * s->capB, st));
+    SCPB_CUDA(h, cudaMemsetAsync(s->src2, 0, sizeof(double) * (size_t)d.nsrc * s->capB, st));
+    SCPB_CUDA(h, cudaMemsetAsync(s->done, 0, sizeof(int) * s->capB, st));
+    SCPB_CUDA(h, cudaMemsetAsync(s->iters, 0, sizeof(int) * s->capB, st));
+    std::vector<int> init_status(s->capB, 1);
+    SCPB_CUDA(h, cudaMemcpyAsync(s->status, init_status.data(), sizeof(int) * s->capB, cudaMemcpyHostToDevice, st));
+    std::vector<double> nanv(s->capB, nan(""));
+    SCPB_CUDA(h, cudaMemcpyAsync(s->devi, nanv.data(), sizeof(double) * s->capB, cudaMemcpyHostToDevice, st));
+    SCPB_CUDA(h, cudaMemcpyAsync(s->J_out, nanv.data(), sizeof(double) * s->capB, cudaMemcpyHostToDevice, st));
+    k_fill<<<(s->capB + 127) / 128, 128, 0, st>>>(s->eta, v.eta_init, s->capB);
+    h->launches++;
+
+    const size_t nsc = (size_t)(d.nx + d.nu + d.np);
+    const double *Sx = s->scale, *Su = Sx + d.nx, *Sp = Su + d.nu, *cx = s->scale + nsc, *cu = cx + d.nx, *cp = cu + d.nu;
+    PtrDev pd{};
+    pd.B = B; pd.G = G; pd.N = d.N; pd.nx = d.nx; pd.nu = d.nu; pd.np = d.np; pd.ns = d.ns;
+    pd.nsrc = d.nsrc; pd.oC = d.oC; pd.oD = d.oD; pd.oG = d.oG; pd.ors = d.ors; pd.oxh = d.oxh; pd.ouh = d.ouh; pd.oph = d.oph;
+    pd.t_grid = s->tgrid; pd.Sx = Sx; pd.cx = cx; pd.Su = Su; pd.cu = cu; pd.Sp = Sp; pd.cp = cp;
+    pd.src = s->src; pd.par = h->par; pd.eta = s->eta; pd.oeta = v.oeta;
+    AsmDev ad{};
+    ad.B = B; ad.G = G; ad.nsrc = d.nsrc; ad.nval = d.nval; ad.nnzA = (int)S->A_ci.size(); ad.nnzG = (int)S->G_ci.size();
+    ad.n = S->n; ad.p = S->p; ad.m = S->m; ad.W_rp = s->W_rp; ad.W_ci = s->W_ci; ad.W_v = s->W_v; ad.src = s->src;
+    ad.Av = D->Av; ad.Gv = D->Gv; ad.c = D->c; ad.b = D->b; ad.h = D->h; ad.c0 = s->c0;
+    StepDev sd{};   // k_extract only
+    sd.B = B; sd.G = G; sd.N = d.N; sd.nx = d.nx; sd.nu = d.nu; sd.np = d.np; sd.n = S->n; sd.vx = d.vx; sd.vu = d.vu; sd.vp = d.vp;
+    sd.q_exit = d.q_exit; sd.eps_abs = d.eps_abs; sd.eps_rel = d.eps_rel;
+    sd.Sx = Sx; sd.cx = cx; sd.Su = Su; sd.cu = cu; sd.Sp = Sp; sd.cp = cp;
+    sd.xsol = D->x; sd.pobj = D->pobj; sd.c0 = s->c0; sd.cone_status = D->status;
+    sd.xd = s->xd; sd.ud = s->ud; sd.p = s->p; sd.xn = s->xn; sd.un = s->un; sd.pn = s->pn;
+    sd.J_ref = s->J_ref; sd.J_new = s->J_new; sd.dev = s->devi; sd.imp = s->imp; sd.feas_new = s->feas;
+    sd.done = s->done; sd.status = s->status; sd.iters = s->iters; sd.nactive = s->nactive;
+    ScvxDev cv{};
+    cv.B = B; cv.G = G; cv.N = d.N; cv.nx = d.nx; cv.nu = d.nu; cv.np = d.np; cv.n_ic = v.n_ic; cv.n_tc = v.n_tc;
+    cv.vx = d.vx; cv.vu = d.vu; cv.vp = d.vp; cv.q_exit = d.q_exit; cv.iter_max = d.iter_max; cv.nsrc = d.nsrc;
+    cv.dltv_lo = d.oA; cv.dltv_hi = d.oC;
+    cv.lam = v.lam; cv.rho_0 = v.rho_0; cv.rho_1 = v.rho_1; cv.rho_2 = v.rho_2; cv.beta_sh = v.beta_sh; cv.beta_gr = v.beta_gr;
+    cv.eta_lb = v.eta_lb; cv.eta_ub = v.eta_ub; cv.eps_abs = d.eps_abs; cv.eps_rel = d.eps_rel;
+    cv.Q_rp = s->Q_rp; cv.Q_ci = s->Q_ci; cv.Q_v = s->Q_v; cv.Q_c = s->Q_c;
+    cv.Sx = Sx; cv.cx = cx; cv.Su = Su; cv.cu = cu; cv.Sp = Sp; cv.cp = cp; cv.t_grid = s->tgrid; cv.defect = s->defect;
+    cv.par = h->par;
+    cv.xd = s->xd; cv.ud = s->ud; cv.p = s->p; cv.xn = s->xn; cv.un = s->un; cv.pn = s->pn;
+    cv.J_ref = s->J_ref; cv.J_new = s->J_new; cv.L_new = s->L_new; cv.J_out = s->J_out; cv.eta = s->eta; cv.dev = s->devi;
+    cv.cone_status = D->status; cv.feas_new = s->feas;
+    cv.done = s->done; cv.status = s->status; cv.iters = s->iters; cv.nactive = s->nactive; cv.accept = s->accept;
+    cv.src = s->src; cv.src2 = s->src2;
+    const bool pack = (h->model_id == SCPB_MODEL_STARSHIP && d.ns > 0);
+    auto cost = [&](const double *X, const double *U, const double *P, double *Jd, double *Ld) {
+        if (pack) k_scvx_cost<Constr<SCPB_MODEL_STARSHIP>><<<(B + 63) / 64, 64, 0, st>>>(cv, X, U, P, Jd, Ld);
+        else k_scvx_cost<Constr<0>><<<(B + 63) / 64, 64, 0, st>>>(cv, X, U, P, Jd, Ld);
+        h->launches++;
+    };
+
+    std::vector<cudaEvent_t> ev;
+    auto mark = [&]() { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev.push_back(e); };
+    std::vector<int> phase;
+    mark(); phase.push_back(-1);
+    // generate_initial_guess: SubproblemSolution(x, u, p, 0, pbm) = discretize! + nonlinear cost (scvx.jl:560-568, 392-394)
+    if ((rc = run_discretize(s, B, G, s->xd, s->ud, s->p))) return rc;
+    cost(s->xd, s->ud, s->p, s->J_ref, s->L_new);
+    mark(); phase.push_back(0);
+    const int nbn = (int)(((long long)B * d.N + 127) / 128);
+    const int Bpad = s->capB;
+    int it = 1, nact = B, total_it = 0;
+    long long ipm_iters = 0;
+    std::vector<int> hit(B);
+    const long long span = (long long)(d.oC - d.oA) * B;
+    for (; it <= d.iter_max; it++) {
+        if (pack) k_linearize<Constr<SCPB_MODEL_STARSHIP>><<<nbn, 128, 0, st>>>(pd, s->xd, s->ud, s->p);
+        else k_linearize<Constr<0>><<<nbn, 128, 0, st>>>(pd, s->xd, s->ud, s->p);
+        const long long tot = (long long)d.nval * Bpad;
+        k_assemble<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ad);
+        h->launches += 2;
+        mark(); phase.push_back(1);
+        if ((rc = scpb_internal_cone_run(s->cone, o))) return rc;
+        mark(); phase.push_back(2);
+        SCPB_CUDA(h, cudaMemcpyAsync(hit.data(), D->iters, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+        sd.iter = it;
+        k_extract<<<nbn, 128, 0, st>>>(sd);
+        h->launches++;
+        mark(); phase.push_back(3);
+        if ((rc = run_discretize(s, B, G, s->xn, s->un, s->pn, s->src2))) return rc;   // candidate: DLTV into src2
+        cost(s->xn, s->un, s->pn, s->J_new, s->L_new);
+        mark(); phase.push_back(0);
+        SCPB_CUDA(h, cudaMemsetAsync(s->nactive, 0, sizeof(int), st));
+        cv.iter = it;
+        k_scvx_step<<<(B + 127) / 128, 128, 0, st>>>(cv);
+        k_scvx_take_dltv<<<(unsigned)((span + 255) / 256), 256, 0, st>>>(cv);
+        h->launches += 2;
+        SCPB_CUDA(h, cudaMemcpyAsync(&nact, s->nactive, sizeof(int), cudaMemcpyDeviceToHost, st));
+        mark(); phase.push_back(3);
+        SCPB_CUDA(h, cudaStreamSynchronize(st));
+        for (int b = 0; b < B; b++) ipm_iters += hit[b];
+        total_it++;
+        if (nact == 0) break;
+    }
+    SCPB_CUDA(h, cudaGetLastError());
+    if (xd) SCPB_CUDA(h, cudaMemcpyAsync(xd, s->xd, sizeof(double) * nX, cudaMemcpyDeviceToHost, st));
+    if (ud) SCPB_CUDA(h, cudaMemcpyAsync(ud, s->ud, sizeof(double) * nU, cudaMemcpyDeviceToHost, st));
+    if (p) SCPB_CUDA(h, cudaMemcpyAsync(p, s->p, sizeof(double) * nP, cudaMemcpyDeviceToHost, st));
+    if (status) SCPB_CUDA(h, cudaMemcpyAsync(status, s->status, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    if (iters) SCPB_CUDA(h, cudaMemcpyAsync(iters, s->iters, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    if (J) SCPB_CUDA(h, cudaMemcpyAsync(J, s->J_out, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+    if (deviation) SCPB_CUDA(h, cudaMemcpyAsync(deviation, s->devi, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+    if (feas) SCPB_CUDA(h, cudaMemcpyAsync(feas, s->feas, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    if (eta) SCPB_CUDA(h, cudaMemcpyAsync(eta, s->eta, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
     SCPB_CUDA(h, cudaStreamSynchronize(st));
     double acc[4] = {0, 0, 0, 0};
     for (size_t i = 1; i < ev.size(); i++) {

@@ -50,6 +50,9 @@ SIGNATURES = {
     "scpb_ptr_free": (C.c_int32, [C.c_void_p]),
     "scpb_ptr_solve": (C.c_int32, [C.c_void_p, C.c_int32, _dp, _dp, _dp, C.c_void_p, _dp, _dp, _dp, _ip, _ip,
                                    _dp, _dp, _ip, _dp]),
+    "scpb_scvx_attach": (C.c_int32, [C.c_void_p, C.c_void_p, _ip, _ip, _dp, _dp]),
+    "scpb_scvx_solve": (C.c_int32, [C.c_void_p, C.c_int32, _dp, _dp, _dp, C.c_void_p, _dp, _dp, _dp, _ip, _ip,
+                                    _dp, _dp, _ip, _dp, _dp]),
     "scpb_debug_level_profile": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
     "scpb_debug_kkt_solve": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _ip, _ip, _ip, _ip, C.c_int32, C.c_int32,
                                          _ip, _ip, _dp, _dp, _dp, C.c_double, C.c_double, _dp, _dp, C.POINTER(C.c_int64)]),
@@ -67,6 +70,11 @@ class PtrDesc(C.Structure):
                 ("N", "Nsub", "nx", "nu", "np", "ns", "nf", "nsrc", "oA", "oBm", "oBp", "oF", "or_", "oE", "oC", "oD",
                  "oG", "ors", "oxh", "ouh", "oph", "nval", "vx", "vu", "vp", "q_exit", "iter_max")] + \
                [(k, C.c_double) for k in ("eps_abs", "eps_rel", "feas_tol")]
+
+
+class ScvxDesc(C.Structure):        # scpb_scvx_desc (include/scpb.h)
+    _fields_ = [(k, C.c_double) for k in ("lam", "rho_0", "rho_1", "rho_2", "beta_sh", "beta_gr", "eta_init", "eta_lb",
+                                           "eta_ub")] + [(k, C.c_int32) for k in ("oeta", "n_ic", "n_tc", "reserved")]
 
 
 CONE_STATUS = {0: "OPTIMAL", 1: "ITERATION_LIMIT", 2: "NUMERICAL_ERROR", 3: "ALMOST_OPTIMAL"}

@@ -91,6 +91,7 @@ class SourceMap:
         self.oxh = o; o += N * nx
         self.ouh = o; o += N * nu
         self.oph = o; o += np_
+        self.oeta = o; o += 1          # SCvx trust-region radius (scvx.jl:245); unused by PTR
         self.nsrc = o
         self.N, self.nx, self.nu, self.np, self.ns, self.nf = N, nx, nu, np_, ns, nf
 
@@ -112,9 +113,10 @@ class SourceMap:
 class SCPProblem:
     """pbm returned by create(): template, device objects, scaling."""
 
-    def __init__(self, pars, traj, handle, l1_block=4):
+    def __init__(self, pars, traj, handle, l1_block=4, algo="ptr"):
         self.pars, self.traj, self.handle = pars, traj, handle
         self.l1_block = l1_block
+        self.algo = algo
         self.scale = SCPScaling(traj)
         self.t = t_grid(pars.N)
         traj.scp = pars
@@ -134,9 +136,14 @@ class SCPProblem:
         u = prg.new_variable((nu, N), "u", sc.Su, sc.cu, stage="col")
         p = prg.new_variable(np_, "p", sc.Sp, sc.cp, stage=(traj.p_stage(N) if traj.p_stage else None))
         vd = prg.new_variable((nx, N - 1), "vd", stage="col")
-        eta_x = prg.new_variable(N, "eta_x", stage="idx")
-        eta_u = prg.new_variable(N, "eta_u", stage="idx")
-        eta_p = prg.new_variable(1, "eta_p", stage=None)
+        scvx = self.algo == "scvx"
+        if not scvx:            # PTR: the trust-region radii are variables (ptr.jl:246-249); SCvx: eta is data
+            eta_x = prg.new_variable(N, "eta_x", stage="idx")
+            eta_u = prg.new_variable(N, "eta_u", stage="idx")
+            eta_p = prg.new_variable(1, "eta_p", stage=None)
+        else:                   # scvx.jl:263-264: the penalty epigraph variables are created with the subproblem
+            P = prg.new_variable(N, "P", stage="idx")
+            Pf = prg.new_variable(2, "Pf", stage=None)
         # add_dynamics! / state_update! (discretization.jl:424-497)
         from .problem import dltv_masks
         mA, mB, mE = dltv_masks(traj)
@@ -172,12 +179,13 @@ class SCPProblem:
                 prg.nonpos([lhs[i] + Expr(None, rs[i]) - vs[i, k] for i in range(ns)], "path_ncvx")
         # boundary conditions, relaxed (scp.jl:808-895); affine g => exact linearisation
         vic = vtc = None
+        g_ic, g_tc = [], []
         if traj.gic is not None:
-            g = traj.gic(x[:, 0], p)
+            g_ic = g = traj.gic(x[:, 0], p)
             vic = prg.new_variable(len(g), "vic", stage=0)
             prg.zero([g[i] + vic[i] for i in range(len(g))], "initial_condition")
         if traj.gtc is not None:
-            g = traj.gtc(x[:, N - 1], p)
+            g_tc = g = traj.gtc(x[:, N - 1], p)
             vtc = prg.new_variable(len(g), "vtc", stage=N - 1)
             prg.zero([g[i] + vtc[i] for i in range(len(g))], "terminal_condition")
         # trust region (ptr.jl:565-743)
@@ -187,19 +195,26 @@ class SCPProblem:
         ph_ref = sm.vec(sm.oph, 0, np_)
         cone([dp_lq[0]] + [(p[i] - sc.cp[i]) * (1.0 / sc.Sp[i]) - Expr(None, ph_ref[i]) for i in range(np_)],
              "parameter_trust_region")
-        prg.nonpos([dp_lq[0] - eta_p[0]])
+        if not scvx:
+            prg.nonpos([dp_lq[0] - eta_p[0]])
         dx_lq = prg.new_variable(N, "dx_lq", stage="idx")
         for k in range(N):
             xr = sm.vec(sm.oxh, k, nx)
             cone([dx_lq[k]] + [(x[i, k] - sc.cx[i]) * (1.0 / sc.Sx[i]) - Expr(None, xr[i]) for i in range(nx)],
                  "state_trust_region")
-            prg.nonpos([dx_lq[k] - eta_x[k]])
+            if not scvx:
+                prg.nonpos([dx_lq[k] - eta_x[k]])
         du_lq = prg.new_variable(N, "du_lq", stage="idx")
         for k in range(N):
             ur = sm.vec(sm.ouh, k, nu)
             cone([du_lq[k]] + [(u[i, k] - sc.cu[i]) * (1.0 / sc.Su[i]) - Expr(None, ur[i]) for i in range(nu)],
                  "input_trust_region")
-            prg.nonpos([du_lq[k] - eta_u[k]])
+            if not scvx:
+                prg.nonpos([du_lq[k] - eta_u[k]])
+        if scvx:                # trust_region_bound (scvx.jl:649-674): dx_lq[k] + du_lq[k] + dp_lq <= eta
+            eta_src = Expr(None, Lin.src(sm.oeta))
+            for k in range(N):
+                prg.nonpos([dx_lq[k] + du_lq[k] + dp_lq[0] - eta_src], "trust_region_bound")
         # cost (ptr.jl:753-895, scp.jl:552-601)
         J = Expr()
         if traj.phi is not None:
@@ -207,9 +222,12 @@ class SCPProblem:
         if traj.Gamma is not None:
             J = J + trapz([traj.Gamma(t[k], k + 1, x[:, k], u[:, k], p) for k in range(N)], t)
         prg.add_cost(J)
-        prg.add_cost((trapz(list(eta_x), t) + trapz(list(eta_u), t) + eta_p[0]) * pars.wtr)
-        P = prg.new_variable(N, "P", stage="idx")
-        Pf = prg.new_variable(2, "Pf", stage=None)
+        self.J_orig, self.g_ic, self.g_tc = J, list(g_ic), list(g_tc)     # rows re-evaluated by SCvx (nonlinear cost)
+        if not scvx:
+            prg.add_cost((trapz(list(eta_x), t) + trapz(list(eta_u), t) + eta_p[0]) * pars.wtr)
+        if not scvx:
+            P = prg.new_variable(N, "P", stage="idx")
+            Pf = prg.new_variable(2, "Pf", stage=None)
         for k in range(N):
             if k < N - 1:
                 E = sm.mat(sm.oE, k, nx, nx, mask=mE)
@@ -227,7 +245,7 @@ class SCPProblem:
             prg.l1([Pf[1]] + list(vtc), "vtc_penalty", stage=N - 1)
         else:
             prg.zero([Pf[1]])
-        prg.add_cost((trapz(list(P), t) + Pf[0] + Pf[1]) * pars.wvc)
+        prg.add_cost((trapz(list(P), t) + Pf[0] + Pf[1]) * (pars.lam if scvx else pars.wvc))
         self.template = prg
         self.cp = cp = prg.compile()
         # one extra W row for the cost constant c0

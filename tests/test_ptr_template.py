@@ -123,3 +123,60 @@ def test_rocket_template_matches_oracle_subproblem(pkg, monkeypatch):
     assert np.abs(b - ocp["b"]).max() <= 1e-11 * max(1.0, np.abs(ocp["b"]).max())
     assert np.abs(h - ocp["h"]).max() <= 1e-11 * max(1.0, np.abs(ocp["h"]).max())
     assert abs(vals[-1] - ocp["c0"]) <= 1e-12
+
+
+def test_scvx_template_matches_oracle_subproblem(pkg, monkeypatch):
+    """SCvx flavour of the template (trust-region radius as a device source, lambda penalty, no eta variables) against
+    the oracle's numeric SCvx subproblem (oracle/scvx.py restating scvx.jl:225-303, 578-701, 804-901)."""
+    from oracle import scvx as oscvx
+    N = 9
+    pbo = problems.StarshipProblem(N)
+    xd, ud, p = problems.test_trajectory(pbo, 1, N, seed=5)
+    pbo.hs = 77.0
+    kw = dict(lam=5e2, rho_0=0.0, rho_1=0.1, rho_2=0.7, beta_sh=2.0, beta_gr=2.0, eta_init=1.0, eta_lb=1e-8, eta_ub=10.0,
+              eps_abs=1e-5, eps_rel=1e-4, feas_tol=5e-3)
+    S = oscvx.SCvx(pbo, oscvx.Parameters(N=N, Nsub=60, iter_max=5, **kw))
+    ref = S.make_solution(xd[0], ud[0], p[0])
+    eta = 0.37
+    prg, _ = S.build(ref, eta)
+    ocp = prg.compile()
+    ex = pkg.examples.starship
+    mdl = ex.StarshipProblem(); mdl.hs = 77.0
+    traj = pkg.problem.TrajectoryProblem(mdl)
+    ex.define_problem(traj, "scvx", handle=None)
+    pars = pkg.scvx.Parameters(N=N, Nsub=60, iter_max=5, disc_method=pkg.ptr.FOH, q_tr=np.inf, q_exit=np.inf, **kw)
+
+    class FakeHandle:
+        def model_set(self, *a): pass
+    monkeypatch.setattr(pkg.lib, "ConeProblem", lambda *a, **k: type("C", (), {"c": None, "close": lambda s: None})())
+    fake = FakeHandle(); fake.lib = type("L", (), {"scpb_ptr_setup": staticmethod(lambda *a: 0)})(); fake.h = None
+    fake._check = lambda rc, what: None
+    pbm = pkg.ptr.SCPProblem(pars, traj, fake, l1_block=0, algo="scvx")
+    cp, sm = pbm.cp, pbm.sm
+    src = _sources(sm, pbo, S, ref)
+    src[sm.oeta] = eta
+    vals = pbm.W @ src
+    n, p_, m = cp["n"], cp["p"], cp["m"]
+    assert (n, p_, m, cp["l"]) == (ocp["c"].size, ocp["A"].shape[0], ocp["G"].shape[0], ocp["l"])
+    A = sp.csr_matrix((vals[:cp["nnzA"]], cp["A"].indices, cp["A"].indptr), shape=(p_, n))
+    G = sp.csr_matrix((vals[cp["nnzA"]:cp["nnzA"] + cp["nnzG"]], cp["G"].indices, cp["G"].indptr), shape=(m, n))
+    tol = 1e-12
+    assert abs(A - ocp["A"]).max() <= tol * max(1.0, abs(ocp["A"]).max())
+    assert abs(G - ocp["G"]).max() <= tol * max(1.0, abs(ocp["G"]).max())
+    c = vals[cp["off_c"]:cp["off_c"] + n]; b = vals[cp["off_b"]:cp["off_b"] + p_]; h = vals[cp["off_h"]:cp["off_h"] + m]
+    assert np.abs(c - ocp["c"]).max() <= tol * max(1.0, np.abs(ocp["c"]).max())
+    assert np.abs(b - ocp["b"]).max() <= 1e-11 * max(1.0, np.abs(ocp["b"]).max())
+    assert np.abs(h - ocp["h"]).max() <= 1e-11 * max(1.0, np.abs(ocp["h"]).max())
+    assert abs(vals[-1] - ocp["c0"]) <= 1e-12
+    # Q rows (original cost, boundary conditions) evaluated at the scaled reference = the oracle's numeric values
+    rp, ci, v, c0 = pkg.scvx._rows_matrix([pkg.parser.Expr.lift(pbm.J_orig)] + pbm.g_ic + pbm.g_tc, n)
+    z = np.zeros(n)
+    sc = pbm.scale
+    ox, ou, op = pbm.template.blocks["x"][0], pbm.template.blocks["u"][0], pbm.template.blocks["p"][0]
+    z[ox:ox + N * 8] = ((ref.xd - sc.cx) / sc.Sx).ravel()
+    z[ou:ou + N * 3] = ((ref.ud - sc.cu) / sc.Su).ravel()
+    z[op:op + 10] = (ref.p - sc.cp) / sc.Sp
+    Q = sp.csr_matrix((v, ci, rp), shape=(len(c0), n))
+    q = Q @ z + c0
+    want = np.concatenate([[S.original_cost(ref)], pbo.gic(ref.xd[0], ref.p), pbo.gtc(ref.xd[-1], ref.p)])
+    assert np.abs(q - want).max() <= 1e-10 * max(1.0, np.abs(want).max())
