@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--N", type=int, default=100)
     ap.add_argument("--Nsub", type=int, default=100)
     ap.add_argument("--cpu-seeds", type=int, default=0, help="seeds in the CPU sample (0 = one per host thread)")
+    ap.add_argument("--algo", default="ptr", choices=["ptr", "scvx"],
+                    help="ptr: the north-star workload (default); scvx: BASELINE configs[2], starship SCvx")
     return ap.parse_args()
 
 
@@ -108,6 +110,10 @@ def measured_peak():
 
 # PTR constants of the reference test (starship_flip/tests.jl:33-47)
 PTR = dict(iter_max=15, wvc=1e3, wtr=0.1, eps_abs=1e-5, eps_rel=0.01 / 100, feas_tol=5e-3)
+# SCvx constants of the reference test (starship_flip/tests.jl:69-121)
+SCVX = dict(iter_max=100, lam=5e2, rho_0=0.0, rho_1=0.1, rho_2=0.7, beta_sh=2.0, beta_gr=2.0, eta_init=1.0, eta_lb=1e-8,
+            eta_ub=10.0, eps_abs=1e-5, eps_rel=0.01 / 100, feas_tol=5e-3)
+ALGO = "ptr"
 
 
 def make_seeds(base, Sx, Su, nb, seed):
@@ -124,12 +130,15 @@ def make_seeds(base, Sx, Su, nb, seed):
 # ----------------------------------------------------------------------------------------------
 def oracle_worker(args):
     """One seed through the oracle PTR (C discretize + HiGHS LP); returns (iterations, phase seconds)."""
-    N, Nsub, hs, xd, ud, p = args
-    from oracle import problems, ptr as optr
+    N, Nsub, hs, xd, ud, p = args[:6]
+    algo = args[6] if len(args) > 6 else "ptr"
+    from oracle import problems, ptr as optr, scvx as oscvx
     pb = problems.StarshipProblem(N)
     pb.hs = hs
-    pars = optr.Parameters(N=N, Nsub=Nsub, solver_tol=1e-9, **PTR)
-    P = optr.PTR(pb, pars)
+    if algo == "scvx":
+        P = oscvx.SCvx(pb, oscvx.Parameters(N=N, Nsub=Nsub, solver_tol=1e-9, **SCVX))
+    else:
+        P = optr.PTR(pb, optr.Parameters(N=N, Nsub=Nsub, solver_tol=1e-9, **PTR))
     out = P.solve((xd, ud, p))
     tm = {"discretize": 0.0, "formulate": 0.0, "solve": 0.0}
     for s in out["history"]:
@@ -144,7 +153,7 @@ def cpu_run(N, Nsub, hs, X, U, P, nproc):
     # over the cores): the reference is a single-threaded Julia process per trajectory
     for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "HIGHS_NUM_THREADS"):
         os.environ[v] = "1"
-    jobs = [(N, Nsub, hs, X[b], U[b], P[b]) for b in range(X.shape[0])]
+    jobs = [(N, Nsub, hs, X[b], U[b], P[b], ALGO) for b in range(X.shape[0])]
     t0 = time.perf_counter()
     with mp.get_context("fork").Pool(nproc) as pool:
         res = pool.map(oracle_worker, jobs, chunksize=1)
@@ -182,8 +191,8 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"starship_flip PTR N={args.N} Nsub={args.Nsub}", "batch_per_gpu": args.batch,
-                       "ptr": PTR},
+            "config": {"workload": f"starship_flip {args.algo.upper()} N={args.N} Nsub={args.Nsub}",
+                       "batch_per_gpu": args.batch, "algorithm_constants": (SCVX if args.algo == "scvx" else PTR)},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{nseeds} of {args.batch} seeds per step, one single-threaded process per core "
                                        f"(oracle: C discretize + Python formulate + HiGHS LP); cores = "
@@ -210,10 +219,15 @@ def run_ours(args, rank, local_rank, world):
     mdl = ex.StarshipProblem()
     traj = pkg.problem.TrajectoryProblem(mdl)
     ex.define_problem(traj, "ptr", handle=h)
-    pars = pkg.ptr.Parameters(N=N, Nsub=Nsub, disc_method=pkg.ptr.FOH, q_tr=np.inf, q_exit=np.inf,
-                              solver_opts={"verbose": 0, "maxit": 100}, **PTR)
+    algo = pkg.scvx if args.algo == "scvx" else pkg.ptr
+    if args.algo == "scvx":
+        pars = pkg.scvx.Parameters(N=N, Nsub=Nsub, disc_method=pkg.ptr.FOH, q_tr=np.inf, q_exit=np.inf,
+                                   solver_opts={"verbose": 0, "maxit": 100}, **SCVX)
+    else:
+        pars = pkg.ptr.Parameters(N=N, Nsub=Nsub, disc_method=pkg.ptr.FOH, q_tr=np.inf, q_exit=np.inf,
+                                  solver_opts={"verbose": 0, "maxit": 100}, **PTR)
     base = traj.guess(N)                     # nominal guess (GPU SOCP batch); outside the timed region
-    pbm = pkg.ptr.create(pars, traj, h)
+    pbm = algo.create(pars, traj, h)
     X, U, P = make_seeds(base, pbm.scale.Sx, pbm.scale.Su, B, rank)
     info = pbm.cone.info()
 
@@ -226,7 +240,7 @@ def run_ours(args, rank, local_rank, world):
     W = max(args.warmup, 3)
     for _ in range(W):
         l2_flush.zero_()
-        sol = pkg.ptr.solve(pbm, (X, U, P))
+        sol = algo.solve(pbm, (X, U, P))
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -238,7 +252,7 @@ def run_ours(args, rank, local_rank, world):
     for _ in range(args.steps):
         l2_flush.zero_(); tc.synchronize()
         t0 = time.perf_counter()
-        sol = pkg.ptr.solve(pbm, (X, U, P))   # host buffers in, host buffers out: the reference-facing call
+        sol = algo.solve(pbm, (X, U, P))      # host buffers in, host buffers out: the reference-facing call
         wall_t += time.perf_counter() - t0
         dev_t += sol.timing["total"]          # CUDA events on the library's stream, H2D/D2H copies excluded
         its += int(sol.iterations.sum())
@@ -299,7 +313,8 @@ def run_ours(args, rank, local_rank, world):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
                 "ms_per_step": 1e3 * dev_t / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"starship_flip PTR N={N} Nsub={Nsub}", "batch_per_gpu": B, "ptr": PTR,
+                "config": {"workload": f"starship_flip {args.algo.upper()} N={N} Nsub={Nsub}", "batch_per_gpu": B,
+                           "algorithm_constants": (SCVX if args.algo == "scvx" else PTR),
                            "seeds_solved": int(solved[0]), "seeds_total": B * world,
                            "scp_iterations_per_step": float(cnt[0]) / args.steps,
                            "l2": "256 MiB buffer written between timed steps; per-seed working set (1.4 GB) >> L2"},
@@ -323,7 +338,9 @@ def run_ours(args, rank, local_rank, world):
 
 
 def main():
+    global ALGO
     args = parse()
+    ALGO = args.algo
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
