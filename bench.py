@@ -306,7 +306,7 @@ def run_ours(args, rank, local_rank, world):
             pbo = problems.StarshipProblem(N); pbo.hs = mdl.hs
             cits, cwall, cph, _ = cpu_run(N, Nsub, mdl.hs, X[:nseeds], U[:nseeds], P[:nseeds], min(cores, nseeds))
             cpu = {"value": cits / cwall, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{nseeds} of {B} seeds, full PTR solve each, one single-threaded process per core "
+                   "sample": f"{nseeds} of {B} seeds, full {args.algo.upper()} solve each, one single-threaded process per core "
                              f"(oracle: C discretize + Python formulate + HiGHS LP); cores = min(visible CPUs "
                              f"{os.cpu_count()}, cgroup cpu.max quota)",
                    "phase_cpu_seconds": cph}

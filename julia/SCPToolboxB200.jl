@@ -78,6 +78,28 @@ end
 
 cone_free(cone) = ccall((:scpb_cone_free, libscpb), Int32, (Ptr{Cvoid},), cone)
 
+# scpb_scvx_attach / scpb_scvx_solve (SCvx.solve for a batch, src/solvers/scvx.jl:460-546): the descriptor mirrors
+# scpb_scvx_desc; Q holds the rows of the original cost and of g_ic / g_tc over the scaled solver variables
+struct ScvxDesc
+    lam::Float64; rho_0::Float64; rho_1::Float64; rho_2::Float64; beta_sh::Float64; beta_gr::Float64
+    eta_init::Float64; eta_lb::Float64; eta_ub::Float64
+    oeta::Int32; n_ic::Int32; n_tc::Int32; reserved::Int32
+end
+
+function scvx_attach(h::Handle, ptr, desc::ScvxDesc, Q_rp::Vector{Int32}, Q_ci::Vector{Int32}, Q_v::Vector{Float64},
+                     Q_c::Vector{Float64})
+    check(h, ccall((:scpb_scvx_attach, libscpb), Int32,
+        (Ptr{Cvoid}, Ref{ScvxDesc}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}), ptr, desc, Q_rp, Q_ci, Q_v, Q_c),
+        "scpb_scvx_attach")
+end
+
+function scvx_solve(h::Handle, ptr, B, xd0, ud0, p0, opts::ConeOpts, xd, ud, p, status, iters, J, dev, feas, eta, timing)
+    check(h, ccall((:scpb_scvx_solve, libscpb), Int32,
+        (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{ConeOpts}, Ptr{Float64}, Ptr{Float64},
+         Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}),
+        ptr, B, xd0, ud0, p0, opts, xd, ud, p, status, iters, J, dev, feas, eta, timing), "scpb_scvx_solve")
+end
+
 # scpb_ptr_setup / scpb_ptr_solve / scpb_ptr_free: same pattern; the descriptor struct mirrors scpb_ptr_desc
 # field by field (27 Int32 + 3 Float64).  See INTEGRATION.md section 3.
 

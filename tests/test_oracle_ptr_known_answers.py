@@ -43,3 +43,20 @@ def test_rocket_landing_ptr_converges_and_is_physical():
     assert (np.linalg.norm(a, axis=1) <= xi * (1 + 1e-6) + 1e-9).all()           # SOC slack holds
     assert pb.m_dry <= np.exp(s.xd[-1, 6]) <= pb.m_wet
     assert pb.tf_min <= s.p[0] <= pb.tf_max and np.abs(s.xd[-1, 0:6]).max() <= 1e-5
+
+
+def test_oracle_scvx_solves_the_reference_starship_configuration():
+    """starship_flip/tests.jl:69-121: SCvx must end SCP_SOLVED within iter_max = 100 (the reference's own assertion),
+    with a dynamically feasible trajectory; the trust region only ever shrinks by beta_sh or grows by beta_gr."""
+    from oracle import scvx as oscvx
+    N = 31
+    pb = problems.StarshipProblem(N)
+    pars = oscvx.Parameters(N=N, Nsub=100, iter_max=100, lam=5e2, rho_0=0.0, rho_1=0.1, rho_2=0.7, beta_sh=2.0,
+                            beta_gr=2.0, eta_init=1.0, eta_lb=1e-8, eta_ub=10.0, eps_abs=1e-5, eps_rel=1e-4, feas_tol=5e-3)
+    out = oscvx.SCvx(pb, pars).solve(pb.guess(N))
+    assert out["status"] == "SCP_SOLVED" and out["iterations"] < 100 and out["sol"].feas
+    etas = [h.eta for h in out["history"]]
+    for a, b in zip(etas[:-1], etas[1:]):
+        assert b in (a, a / 2.0, min(10.0, 2.0 * a))
+    J = [h.J_aug for h in out["history"]]
+    assert J[-1] < 1e-3 * J[0]                     # the penalised cost drops by three orders of magnitude
