@@ -114,7 +114,7 @@ int scpb_internal_cone_run(scpb_cone_s *c, const IpmOpts &o)
     // ~20 KB of static shared memory; B200 allows 227 KB per CTA)
     size_t smem = sizeof(int) * ((9 * (size_t)(c->S.nlevels + 1) + 3) & ~(size_t)3);
     const size_t vbytes = sizeof(double) * (size_t)c->S.nk * c->D.G;
-    c->D.vsmem = (smem + vbytes <= 200 * 1024) ? 1 : 0;
+    c->D.vsmem = (smem + vbytes <= 200 * 1024 && !getenv("SCPB_NO_VSMEM")) ? 1 : 0;   // env: force the global-memory sweep (tests)
     if (c->D.vsmem) smem += vbytes;
     c->D.lvl_prof = (c->d_prof && getenv("SCPB_LEVEL_PROFILE")) ? 1 : 0;   // diagnostic: per-level cycle counters of CTA 0
     if (o.threads >= 1024) {

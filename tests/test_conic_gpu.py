@@ -132,3 +132,11 @@ def test_cone_error_paths(handle, pkg):
     assert out["status"][0] == 0 and abs(out["pobj"][0] - 1.0) < 1e-7
     assert np.abs(out["x"][0] - [1.0, 0.0]).max() < 1e-6
     cone.close()
+
+
+def test_global_memory_sweep_fallback(handle, pkg, monkeypatch):
+    """Problems whose substitution vector does not fit shared memory take the global-memory sweeps (kkt_ldl_solve);
+    SCPB_NO_VSMEM forces that path on a small problem so that it stays covered."""
+    monkeypatch.setenv("SCPB_NO_VSMEM", "1")
+    test_starship_ptr_subproblem_matches_highs(handle, pkg, 12, 0)
+    test_random_programs_match_oracle(handle, pkg, 1, 16, 5, 10, [3, 4])
