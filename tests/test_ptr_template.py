@@ -180,3 +180,46 @@ def test_scvx_template_matches_oracle_subproblem(pkg, monkeypatch):
     q = Q @ z + c0
     want = np.concatenate([[S.original_cost(ref)], pbo.gic(ref.xd[0], ref.p), pbo.gtc(ref.xd[-1], ref.p)])
     assert np.abs(q - want).max() <= 1e-10 * max(1.0, np.abs(want).max())
+
+
+@pytest.mark.parametrize("q_tr", [1, 2])
+def test_template_other_trust_region_norms(pkg, monkeypatch, q_tr):
+    """q_tr in {1, 2} (ptr.jl:582: L1 / SOC trust-region cones instead of LINF): template == oracle subproblem."""
+    N = 7
+    pbo = problems.StarshipProblem(N)
+    xd, ud, p = problems.test_trajectory(pbo, 1, N, seed=q_tr)
+    pbo.hs = 50.0
+    opars = optr.Parameters(N=N, Nsub=40, iter_max=5, wvc=1e3, wtr=0.1, eps_abs=1e-5, eps_rel=1e-4, feas_tol=5e-3, q_tr=q_tr)
+    P = optr.PTR(pbo, opars)
+    ref = P.make_solution(xd[0], ud[0], p[0])
+    prg, _ = P.build(ref)
+    ocp = prg.compile()
+    ex = pkg.examples.starship
+    mdl = ex.StarshipProblem(); mdl.hs = 50.0
+    traj = pkg.problem.TrajectoryProblem(mdl)
+    ex.define_problem(traj, "ptr", handle=None)
+    pars = pkg.ptr.Parameters(N=N, Nsub=40, iter_max=5, disc_method=pkg.ptr.FOH, wvc=1e3, wtr=0.1, eps_abs=1e-5,
+                              eps_rel=1e-4, feas_tol=5e-3, q_tr=q_tr, q_exit=np.inf)
+
+    class FakeHandle:
+        def model_set(self, *a): pass
+    monkeypatch.setattr(pkg.lib, "ConeProblem", lambda *a, **k: type("C", (), {"c": None, "close": lambda s: None})())
+    fake = FakeHandle(); fake.lib = type("L", (), {"scpb_ptr_setup": staticmethod(lambda *a: 0)})(); fake.h = None
+    fake._check = lambda rc, what: None
+    pbm = pkg.ptr.SCPProblem(pars, traj, fake, l1_block=0)
+    cp, sm = pbm.cp, pbm.sm
+    vals = pbm.W @ _sources(sm, pbo, P, ref)
+    n, p_, m = cp["n"], cp["p"], cp["m"]
+    assert (n, p_, m, cp["l"]) == (ocp["c"].size, ocp["A"].shape[0], ocp["G"].shape[0], ocp["l"])
+    assert list(cp["soc_dims"]) == list(ocp["q"])
+    if q_tr == 2:
+        assert sorted(set(cp["soc_dims"])) == [4, 9, 11]      # input, state and parameter trust regions
+    A = sp.csr_matrix((vals[:cp["nnzA"]], cp["A"].indices, cp["A"].indptr), shape=(p_, n))
+    G = sp.csr_matrix((vals[cp["nnzA"]:cp["nnzA"] + cp["nnzG"]], cp["G"].indices, cp["G"].indptr), shape=(m, n))
+    tol = 1e-12
+    assert abs(A - ocp["A"]).max() <= tol * max(1.0, abs(ocp["A"]).max())
+    assert abs(G - ocp["G"]).max() <= tol * max(1.0, abs(ocp["G"]).max())
+    c = vals[cp["off_c"]:cp["off_c"] + n]; b = vals[cp["off_b"]:cp["off_b"] + p_]; h = vals[cp["off_h"]:cp["off_h"] + m]
+    assert np.abs(c - ocp["c"]).max() <= tol * max(1.0, np.abs(ocp["c"]).max())
+    assert np.abs(b - ocp["b"]).max() <= 1e-11 * max(1.0, np.abs(ocp["b"]).max())
+    assert np.abs(h - ocp["h"]).max() <= 1e-11 * max(1.0, np.abs(ocp["h"]).max())
