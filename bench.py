@@ -317,7 +317,7 @@ def run_ours(args, rank, local_rank, world):
                            "algorithm_constants": (SCVX if args.algo == "scvx" else PTR),
                            "seeds_solved": int(solved[0]), "seeds_total": B * world,
                            "scp_iterations_per_step": float(cnt[0]) / args.steps,
-                           "l2": "256 MiB buffer written between timed steps; per-seed working set (1.4 GB) >> L2"},
+                           "l2": "256 MiB buffer written between timed steps; solver working set (1.1 GB for 256 seeds) >> L2"},
                 "gpu_launches": int(launches),
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(X.nbytes + U.nbytes + P.nbytes),
                         "d2h_bytes_per_step": int(X.nbytes + U.nbytes + P.nbytes + B * (4 * 3 + 8 * 2))},
