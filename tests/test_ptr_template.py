@@ -223,3 +223,47 @@ def test_template_other_trust_region_norms(pkg, monkeypatch, q_tr):
     assert np.abs(c - ocp["c"]).max() <= tol * max(1.0, np.abs(ocp["c"]).max())
     assert np.abs(b - ocp["b"]).max() <= 1e-11 * max(1.0, np.abs(ocp["b"]).max())
     assert np.abs(h - ocp["h"]).max() <= 1e-11 * max(1.0, np.abs(ocp["h"]).max())
+
+
+def test_l1_block_lowering_is_an_equivalent_program(pkg, monkeypatch):
+    """The product lowers wide L1 cones through partial sums (l1_block = 4, keeps the KKT factor sparse); the reference's
+    NormOneBridge form is l1_block = 0.  Both must be the same optimisation problem: equal optimal value and equal
+    (x, u, p) minimiser on the oracle's data (HiGHS on both compiled programs)."""
+    from oracle import conic
+    N = 8
+    pbo = problems.StarshipProblem(N)
+    xd, ud, p = problems.test_trajectory(pbo, 1, N, seed=2)
+    pbo.hs = 60.0
+    opars = optr.Parameters(N=N, Nsub=40, iter_max=5, wvc=1e3, wtr=0.1, eps_abs=1e-5, eps_rel=1e-4, feas_tol=5e-3)
+    P = optr.PTR(pbo, opars)
+    ref = P.make_solution(xd[0], ud[0], p[0])
+    ex = pkg.examples.starship
+    mdl = ex.StarshipProblem(); mdl.hs = 60.0
+    traj = pkg.problem.TrajectoryProblem(mdl)
+    ex.define_problem(traj, "ptr", handle=None)
+    pars = pkg.ptr.Parameters(N=N, Nsub=40, iter_max=5, disc_method=pkg.ptr.FOH, wvc=1e3, wtr=0.1, eps_abs=1e-5,
+                              eps_rel=1e-4, feas_tol=5e-3, q_tr=np.inf, q_exit=np.inf)
+
+    class FakeHandle:
+        def model_set(self, *a): pass
+    monkeypatch.setattr(pkg.lib, "ConeProblem", lambda *a, **k: type("C", (), {"c": None, "close": lambda s: None})())
+    fake = FakeHandle(); fake.lib = type("L", (), {"scpb_ptr_setup": staticmethod(lambda *a: 0)})(); fake.h = None
+    fake._check = lambda rc, what: None
+    res = {}
+    for blk in (0, 4):
+        pbm = pkg.ptr.SCPProblem(pars, traj, fake, l1_block=blk)
+        cp, sm = pbm.cp, pbm.sm
+        vals = pbm.W @ _sources(sm, pbo, P, ref)
+        n, p_, m = cp["n"], cp["p"], cp["m"]
+        A = sp.csr_matrix((vals[:cp["nnzA"]], cp["A"].indices, cp["A"].indptr), shape=(p_, n))
+        G = sp.csr_matrix((vals[cp["nnzA"]:cp["nnzA"] + cp["nnzG"]], cp["G"].indices, cp["G"].indptr), shape=(m, n))
+        prog = dict(c=vals[cp["off_c"]:cp["off_c"] + n], c0=vals[-1], A=A, b=vals[cp["off_b"]:cp["off_b"] + p_], G=G,
+                    h=vals[cp["off_h"]:cp["off_h"] + m], l=cp["l"], q=[])
+        out = conic.solve_highs(prog, tol=1e-9)
+        assert out["status"] == "OPTIMAL"
+        nxu = N * (8 + 3) + 10                      # x, u, p blocks come first in both programs
+        res[blk] = (out["obj"], out["z"][:nxu], n)
+    assert res[4][2] > res[0][2]                    # the lowering adds partial-sum variables ...
+    assert abs(res[0][0] - res[4][0]) <= 1e-8 * max(1.0, abs(res[0][0]))          # ... and changes nothing else
+    d = np.abs(res[0][1] - res[4][1])
+    assert np.median(d) <= 1e-7                     # (flat directions may differ between two LP vertices)
