@@ -202,6 +202,14 @@ int32_t scpb_debug_kkt_solve(int32_t n, int32_t p, int32_t m, const int32_t *A_r
                              const int32_t *soc_dims, const int32_t *perm, const double *Avals,
                              const double *Gvals, const double *wm, double delta, double delta_dyn,
                              const double *rhs, double *sol, int64_t *info);
+/* The same hook for the supernodal program (dense panels, one barrier per supernodal level) that the next kernel
+ * generation executes; info[8] = {supernodes, supernodal levels, panel doubles per seed, update scatter entries,
+ * max width, max panel rows, scalar levels, nnz(L)}. */
+int32_t scpb_debug_kkt_solve_sn(int32_t n, int32_t p, int32_t m, const int32_t *A_rowptr, const int32_t *A_colind,
+                             const int32_t *G_rowptr, const int32_t *G_colind, int32_t l, int32_t nsoc,
+                             const int32_t *soc_dims, const int32_t *perm, const double *Avals,
+                             const double *Gvals, const double *wm, double delta, double delta_dyn,
+                             const double *rhs, double *sol, int64_t *info);
 
 #ifdef __cplusplus
 }

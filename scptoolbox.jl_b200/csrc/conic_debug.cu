@@ -71,3 +71,82 @@ extern "C" int32_t scpb_debug_kkt_solve(int32_t n, int32_t p, int32_t m, const i
     if (info) { info[0] = S.nnzL; info[1] = S.nlevels; info[2] = S.factor_ops; info[3] = (int64_t)S.as_a.size(); }
     return SCPB_OK;
 }
+
+// Same test hook for the SUPERNODAL program (conic_symbolic.h, "supernodal program"): dense panels, one supernodal
+// level at a time, right-looking updates scattered through the precomputed maps.  This is the executable specification
+// of the round-2 device kernels; nothing on the product path calls it.
+extern "C" int32_t scpb_debug_kkt_solve_sn(int32_t n, int32_t p, int32_t m, const int32_t *A_rp, const int32_t *A_ci,
+                                           const int32_t *G_rp, const int32_t *G_ci, int32_t l, int32_t nsoc,
+                                           const int32_t *soc_dims, const int32_t *perm, const double *Av,
+                                           const double *Gv, const double *wm, double delta, double delta_dyn,
+                                           const double *rhs, double *sol, int64_t *info)
+{
+    ConeSymbolic S;
+    static const int zero = 0;
+    if (!cone_symbolic_build(S, n, p, m, A_rp, A_ci ? A_ci : &zero, G_rp, G_ci ? G_ci : &zero, l, nsoc, soc_dims, perm))
+        return SCPB_ERR_ARG;
+    const int nk = S.nk, ntgt = S.nnzL + nk, ns = (int)S.sn_first.size();
+    std::vector<double> P((size_t)S.sn_panel_size, 0.0), invD(nk), v(nk);
+    for (int t = 0; t < ntgt; t++) {  // assembly straight into the panels
+        double acc = delta * S.as_sign[t];
+        if (S.as_src[t] >= 0) acc += Av[S.as_src[t]];
+        for (int k = S.as_ptr[t]; k < S.as_ptr[t + 1]; k++) acc += Gv[S.as_a[k]] * Gv[S.as_b[k]] * wm[S.as_c[k]];
+        P[(size_t)S.sn_pos_of_target[t]] = acc;
+    }
+    for (int lv = 0; lv < S.sn_nlevels; lv++)
+        for (int w_ = S.sn_lvl_ptr[lv]; w_ < S.sn_lvl_ptr[lv + 1]; w_++) {
+            const int s = S.sn_lvl_nodes[w_], a = S.sn_first[s], w = S.sn_width[s], R = S.sn_nrows[s];
+            double *Q = &P[(size_t)S.sn_panel_off[s]];
+            for (int c = 0; c < w; c++) {   // dense LDL' of the panel, right-looking inside the supernode
+                double d = Q[c + (size_t)R * c];
+                const double sgn = (double)S.as_sign[S.nnzL + a + c];
+                if (!(sgn * d > delta_dyn)) d = sgn * delta_dyn;
+                Q[c + (size_t)R * c] = d;
+                invD[a + c] = 1.0 / d;
+                for (int r = c + 1; r < R; r++) Q[r + (size_t)R * c] /= d;
+                for (int c2 = c + 1; c2 < w; c2++) {
+                    const double f = Q[c2 + (size_t)R * c] * d;
+                    for (int r = c2; r < R; r++) Q[r + (size_t)R * c2] -= Q[r + (size_t)R * c] * f;
+                }
+            }
+            long long k = S.sn_upd_ptr[s];   // Schur update of the ancestors' panels
+            for (int y = 0; y < R - w; y++)
+                for (int x = y; x < R - w; x++) {
+                    double u = 0.0;
+                    for (int c = 0; c < w; c++) u += Q[w + x + (size_t)R * c] * Q[c + (size_t)R * c] * Q[w + y + (size_t)R * c];
+                    P[(size_t)S.sn_upd_dst[k++]] -= u;
+                }
+        }
+    for (int i = 0; i < nk; i++) v[S.iperm[i]] = rhs[i];
+    for (int lv = 0; lv < S.sn_nlevels; lv++)   // forward: column oriented, updates scattered to the rows below
+        for (int w_ = S.sn_lvl_ptr[lv]; w_ < S.sn_lvl_ptr[lv + 1]; w_++) {
+            const int s = S.sn_lvl_nodes[w_], w = S.sn_width[s], R = S.sn_nrows[s];
+            const double *Q = &P[(size_t)S.sn_panel_off[s]];
+            const int *rows = &S.sn_rows[S.sn_rows_ptr[s]];
+            for (int c = 0; c < w; c++) {
+                const double xc = v[rows[c]];
+                for (int r = c + 1; r < R; r++) v[rows[r]] -= Q[r + (size_t)R * c] * xc;
+            }
+        }
+    for (int i = 0; i < nk; i++) v[i] *= invD[i];
+    for (int lv = S.sn_nlevels - 1; lv >= 0; lv--)   // backward: gathers from the rows below
+        for (int w_ = S.sn_lvl_ptr[lv]; w_ < S.sn_lvl_ptr[lv + 1]; w_++) {
+            const int s = S.sn_lvl_nodes[w_], w = S.sn_width[s], R = S.sn_nrows[s];
+            const double *Q = &P[(size_t)S.sn_panel_off[s]];
+            const int *rows = &S.sn_rows[S.sn_rows_ptr[s]];
+            for (int c = w - 1; c >= 0; c--) {
+                double acc = v[rows[c]];
+                for (int r = c + 1; r < R; r++) acc -= Q[r + (size_t)R * c] * v[rows[r]];
+                v[rows[c]] = acc;
+            }
+        }
+    for (int i = 0; i < nk; i++) sol[i] = v[S.iperm[i]];
+    if (info) {
+        info[0] = ns; info[1] = S.sn_nlevels; info[2] = S.sn_panel_size; info[3] = (int64_t)S.sn_upd_dst.size();
+        int wmax = 0, rmax = 0;
+        for (int s = 0; s < ns; s++) { wmax = std::max(wmax, S.sn_width[s]); rmax = std::max(rmax, S.sn_nrows[s]); }
+        info[4] = wmax; info[5] = rmax; info[6] = S.nlevels; info[7] = S.nnzL;
+    }
+    (void)ns;
+    return SCPB_OK;
+}

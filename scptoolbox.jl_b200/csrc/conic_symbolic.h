@@ -74,6 +74,21 @@ struct ConeSymbolic {
     // bit1 = the item is the diagonal itself (regularise, write 1/d), otherwise scale the entry by 1/d.
     std::vector<int> fa_item, fa_lvl, fa_R;
     std::vector<int> fb_item, fb_lvl;
+    // ---- supernodal program (host side of the round-2 kernels; executed today only by the CPU interpreter
+    // scpb_debug_kkt_solve_sn, tests/test_conic_symbolic.py) ----
+    // Maximal supernodes: consecutive columns a..b with parent(j) = j+1 and struct(L[:,j]) = {j+1} + struct(L[:,j+1]);
+    // each owns a dense column-major R x w panel (rows = its own w columns, then the rows below), D on the panel
+    // diagonal, unit-lower L below it.  A supernodal level needs ONE barrier; the bench KKT has 22 such levels
+    // against 88 scalar ones (profiles/r1_supernode_study.txt).
+    std::vector<int> sn_first, sn_width, sn_nrows;   // per supernode
+    std::vector<int> sn_rows_ptr, sn_rows;           // row (node) indices of each panel
+    std::vector<long long> sn_panel_off;             // offset of each panel in the per-seed panel array
+    std::vector<int> sn_lvl_ptr, sn_lvl_nodes;       // supernodal level schedule (children before parents)
+    std::vector<long long> sn_pos_of_target;         // target id (L position | nnzL + column) -> panel offset
+    std::vector<long long> sn_upd_ptr;               // per supernode: range of its update scatter list
+    std::vector<long long> sn_upd_dst;               // lower-triangle pairs (x >= y) of the below rows -> panel offset
+    long long sn_panel_size = 0;
+    int sn_nlevels = 0;
     long long factor_ops = 0;
     std::string err;
 };
@@ -394,6 +409,93 @@ inline bool cone_symbolic_build(ConeSymbolic &S, int n, int p, int m, const int 
             S.fb_lvl[lv + 1] = (int)(S.fb_item.size() / 4);
         }
         if (S.fa_item.empty()) S.fa_item.assign(4, 0);
+    }
+    // ---- supernodal program ----
+    {
+        const int ns_max = nk;
+        std::vector<int> sn_of(nk, 0);
+        S.sn_first.clear(); S.sn_width.clear(); S.sn_nrows.clear();
+        for (int j = 0; j < nk;) {
+            int k = j;
+            while (k + 1 < nk && S.L_cp[k + 1] > S.L_cp[k] && S.L_ri[S.L_cp[k]] == k + 1 &&
+                   (S.L_cp[k + 1] - S.L_cp[k]) == (S.L_cp[k + 2] - S.L_cp[k + 1]) + 1)
+                k++;
+            const int sid = (int)S.sn_first.size();
+            for (int c = j; c <= k; c++) sn_of[c] = sid;
+            S.sn_first.push_back(j); S.sn_width.push_back(k - j + 1);
+            S.sn_nrows.push_back((k - j + 1) + (S.L_cp[k + 1] - S.L_cp[k]));
+            j = k + 1;
+        }
+        (void)ns_max;
+        const int ns = (int)S.sn_first.size();
+        S.sn_rows_ptr.assign(ns + 1, 0); S.sn_panel_off.assign(ns + 1, 0);
+        for (int s = 0; s < ns; s++) {
+            S.sn_rows_ptr[s + 1] = S.sn_rows_ptr[s] + S.sn_nrows[s];
+            S.sn_panel_off[s + 1] = S.sn_panel_off[s] + (long long)S.sn_nrows[s] * S.sn_width[s];
+        }
+        S.sn_panel_size = S.sn_panel_off[ns];
+        S.sn_rows.resize(S.sn_rows_ptr[ns]);
+        for (int s = 0; s < ns; s++) {
+            const int a = S.sn_first[s], w = S.sn_width[s], b = a + w - 1;
+            int o = S.sn_rows_ptr[s];
+            for (int c = 0; c < w; c++) S.sn_rows[o++] = a + c;
+            for (int q = S.L_cp[b]; q < S.L_cp[b + 1]; q++) S.sn_rows[o++] = S.L_ri[q];
+        }
+        // panel position of entry (row i, column j)
+        auto panel_pos = [&](int i, int j) -> long long {
+            const int s = sn_of[j], a = S.sn_first[s], w = S.sn_width[s], R = S.sn_nrows[s], c = j - a;
+            int r;
+            if (i < a + w) r = i - a;
+            else {
+                const int *lo = &S.sn_rows[S.sn_rows_ptr[s] + w], *hi = &S.sn_rows[S.sn_rows_ptr[s] + R];
+                const int *it = std::lower_bound(lo, hi, i);
+                if (it == hi || *it != i) return -1;
+                r = w + (int)(it - lo);
+            }
+            return S.sn_panel_off[s] + r + (long long)R * c;
+        };
+        S.sn_pos_of_target.assign((size_t)S.nnzL + nk, -1);
+        for (int j = 0; j < nk; j++) {
+            S.sn_pos_of_target[(size_t)S.nnzL + j] = panel_pos(j, j);
+            for (int q = S.L_cp[j]; q < S.L_cp[j + 1]; q++) {
+                const long long pp = panel_pos(S.L_ri[q], j);
+                if (pp < 0) { S.err = "internal: supernode panel does not cover an L entry"; return false; }
+                S.sn_pos_of_target[q] = pp;
+            }
+        }
+        // update scatter lists
+        S.sn_upd_ptr.assign(ns + 1, 0);
+        S.sn_upd_dst.clear();
+        for (int s = 0; s < ns; s++) {
+            const int w = S.sn_width[s], R = S.sn_nrows[s];
+            const int *below = &S.sn_rows[S.sn_rows_ptr[s] + w];
+            for (int y = 0; y < R - w; y++)
+                for (int x = y; x < R - w; x++) {
+                    const long long pp = panel_pos(below[x], below[y]);
+                    if (pp < 0) { S.err = "internal: supernodal update falls outside the L pattern"; return false; }
+                    S.sn_upd_dst.push_back(pp);
+                }
+            S.sn_upd_ptr[s + 1] = (long long)S.sn_upd_dst.size();
+        }
+        // level schedule: a supernode follows every supernode whose last column's parent lies inside it
+        std::vector<int> slev(ns, 0);
+        for (int s = 0; s < ns; s++) {
+            const int b = S.sn_first[s] + S.sn_width[s] - 1;
+            if (S.L_cp[b + 1] > S.L_cp[b]) {
+                const int ps = sn_of[S.L_ri[S.L_cp[b]]];
+                slev[ps] = std::max(slev[ps], slev[s] + 1);
+            }
+        }
+        S.sn_nlevels = 0;
+        for (int s = 0; s < ns; s++) S.sn_nlevels = std::max(S.sn_nlevels, slev[s] + 1);
+        S.sn_lvl_ptr.assign(S.sn_nlevels + 1, 0);
+        for (int s = 0; s < ns; s++) S.sn_lvl_ptr[slev[s] + 1]++;
+        for (int l2 = 0; l2 < S.sn_nlevels; l2++) S.sn_lvl_ptr[l2 + 1] += S.sn_lvl_ptr[l2];
+        S.sn_lvl_nodes.resize(ns);
+        {
+            std::vector<int> nxt(S.sn_lvl_ptr.begin(), S.sn_lvl_ptr.end() - 1);
+            for (int s = 0; s < ns; s++) S.sn_lvl_nodes[nxt[slev[s]]++] = s;
+        }
     }
     // ---- balanced substitution programs ----
     {

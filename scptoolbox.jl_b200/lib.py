@@ -56,6 +56,8 @@ SIGNATURES = {
     "scpb_debug_level_profile": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
     "scpb_debug_kkt_solve": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _ip, _ip, _ip, _ip, C.c_int32, C.c_int32,
                                          _ip, _ip, _dp, _dp, _dp, C.c_double, C.c_double, _dp, _dp, C.POINTER(C.c_int64)]),
+    "scpb_debug_kkt_solve_sn": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _ip, _ip, _ip, _ip, C.c_int32, C.c_int32,
+                                         _ip, _ip, _dp, _dp, _dp, C.c_double, C.c_double, _dp, _dp, C.POINTER(C.c_int64)]),
 }
 
 
@@ -283,8 +285,9 @@ class ConeProblem:
         return out
 
 
-def debug_kkt_solve(A, G, l, soc_dims, perm, Avals, Gvals, wm, delta, rhs, delta_dyn=0.0):
-    """CPU interpreter of the index programs for one seed (test hook, see include/scpb.h)."""
+def debug_kkt_solve(A, G, l, soc_dims, perm, Avals, Gvals, wm, delta, rhs, delta_dyn=0.0, supernodal=False):
+    """CPU interpreter of the index programs for one seed (test hook, see include/scpb.h); supernodal=True runs the
+    dense-panel program of the next kernel generation instead of the scalar level-scheduled one."""
     lib = load()
     A = A.tocsr(); G = G.tocsr(); A.sort_indices(); G.sort_indices()
     n, p, m = A.shape[1], A.shape[0], G.shape[0]
@@ -293,7 +296,14 @@ def debug_kkt_solve(A, G, l, soc_dims, perm, Avals, Gvals, wm, delta, rhs, delta
     pm = _i32(perm) if perm is not None else (None, None)
     Av, pAv = _f64(Avals); Gv, pGv = _f64(Gvals); wmv, pwm = _f64(wm); r, pr = _f64(rhs)
     sol = np.zeros(n + p)
-    info = (C.c_int64 * 4)()
+    info = (C.c_int64 * 8)()
+    if supernodal:
+        rc = lib.scpb_debug_kkt_solve_sn(n, p, m, a0[1], a1[1], g0[1], g1[1], int(l), len(soc_dims), sd[1], pm[1],
+                                         pAv, pGv, pwm, float(delta), float(delta_dyn), pr, sol.ctypes.data_as(_dp), info)
+        if rc != 0:
+            raise ScpbError(f"scpb_debug_kkt_solve_sn failed ({rc})")
+        keys = ("supernodes", "sn_levels", "panel_doubles", "update_entries", "max_width", "max_rows", "levels", "nnzL")
+        return sol, dict(zip(keys, [int(v) for v in info]))
     rc = lib.scpb_debug_kkt_solve(n, p, m, a0[1], a1[1], g0[1], g1[1], int(l), len(soc_dims), sd[1], pm[1],
                                   pAv, pGv, pwm, float(delta), float(delta_dyn), pr, sol.ctypes.data_as(_dp), info)
     if rc != 0:

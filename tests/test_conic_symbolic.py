@@ -47,6 +47,11 @@ def test_kkt_programs_match_dense_solve(pkg, seed, n, p, l, soc):
         sol, info = pkg.lib.debug_kkt_solve(A, G, l, soc, perm, A.data, G.data, wm, delta, rhs)
         assert np.abs(sol - want).max() <= 1e-7 * max(1.0, np.abs(want).max()), info   # cond(K) ~ 1/delta
         assert info["levels"] >= 1 and info["nnzL"] >= A.nnz
+        # the supernodal program (dense panels; the next kernel generation) solves the same system
+        sol2, info2 = pkg.lib.debug_kkt_solve(A, G, l, soc, perm, A.data, G.data, wm, delta, rhs, supernodal=True)
+        assert np.abs(sol2 - want).max() <= 1e-7 * max(1.0, np.abs(want).max()), info2
+        assert info2["nnzL"] == info["nnzL"] and info2["sn_levels"] <= info["levels"]
+        assert info2["supernodes"] <= n + p and info2["panel_doubles"] >= info["nnzL"] + n + p
 
 
 def test_stage_order_keeps_fill_small(pkg):
@@ -83,3 +88,24 @@ def test_stage_order_keeps_fill_small(pkg):
     # natural order (variables first, then rows) is far worse on the same pattern
     _, info_nat = pkg.lib.debug_kkt_solve(A, G, l, [], None, A.data, G.data, wm, 1e-8, rhs)
     assert info_nat["nnzL"] > 2 * info["nnzL"]
+
+
+def test_supernodal_program_on_the_starship_kkt(pkg):
+    """The reference's starship PTR subproblem under the product's stage ordering: the supernodal schedule must need far
+    fewer dependent steps than the scalar one (22 vs 88 at N = 100, profiles/r1_supernode_study.txt) with small panels,
+    and solve the KKT system like the scalar program does."""
+    from tests import helpers
+    N = 16
+    pb, P, subs = helpers.starship_subproblems(N, 1, seed=3)
+    cp = subs[0]["cp"]
+    A, G, l = cp["A"].tocsr(), cp["G"].tocsr(), cp["l"]
+    lab = helpers.labels_from_program(subs[0]["prg"], N)
+    perm = pkg.ordering.stage_order(A, G, lab, N)
+    rng = np.random.default_rng(0)
+    wm = rng.uniform(0.5, 2.0, l)
+    rhs = rng.standard_normal(A.shape[1] + A.shape[0])
+    s1, i1 = pkg.lib.debug_kkt_solve(A, G, l, [], perm, A.data, G.data, wm, 1e-9, rhs, delta_dyn=1e-7)
+    s2, i2 = pkg.lib.debug_kkt_solve(A, G, l, [], perm, A.data, G.data, wm, 1e-9, rhs, delta_dyn=1e-7, supernodal=True)
+    assert np.abs(s1 - s2).max() <= 1e-8 * max(1.0, np.abs(s1).max())
+    # (this is the reference's NormOneBridge form, whose dense L1 blocks give wider supernodes than the product's lowering)
+    assert i2["sn_levels"] * 2 <= i1["levels"] and i2["max_rows"] <= 64 and i2["max_width"] <= 32, (i1, i2)
