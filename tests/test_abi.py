@@ -50,3 +50,15 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no CPU fallback", ""), f"{f} references the oracle"
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/scpb.h is the drop-in boundary: it must compile as C99 (what ccall / cgo / ctypes bind), not only as C++."""
+    import subprocess
+    src = tmp_path / "use_scpb.c"
+    src.write_text('#include "scpb.h"\n'
+                   'int use(void) { scpb_handle h = 0; scpb_cone_opts o; scpb_ptr_desc d; scpb_scvx_desc v;\n'
+                   '  (void)o; (void)d; (void)v; return scpb_create(0, &h) == SCPB_OK ? (int)sizeof(o) : (int)sizeof(d); }\n')
+    r = subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only",
+                        "-I", os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
