@@ -210,6 +210,13 @@ int32_t scpb_debug_kkt_solve_sn(int32_t n, int32_t p, int32_t m, const int32_t *
                              const int32_t *soc_dims, const int32_t *perm, const double *Avals,
                              const double *Gvals, const double *wm, double delta, double delta_dyn,
                              const double *rhs, double *sol, int64_t *info);
+/* ... and through the per-panel warp routines of csrc/conic_sn.cuh compiled in lane-emulation mode (the code the
+ * supernodal kernel path runs per (supernode, seed) item); SCPB_ERR_UNSUPPORTED if a panel exceeds the warp scratch. */
+int32_t scpb_debug_kkt_solve_sn_emu(int32_t n, int32_t p, int32_t m, const int32_t *A_rowptr, const int32_t *A_colind,
+                             const int32_t *G_rowptr, const int32_t *G_colind, int32_t l, int32_t nsoc,
+                             const int32_t *soc_dims, const int32_t *perm, const double *Avals,
+                             const double *Gvals, const double *wm, double delta, double delta_dyn,
+                             const double *rhs, double *sol, int64_t *info);
 
 #ifdef __cplusplus
 }

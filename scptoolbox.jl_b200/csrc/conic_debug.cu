@@ -4,6 +4,8 @@
 // It is not reachable from any product entry point (scpb_cone_solve always launches k_ipm_solve).
 #include "../../include/scpb.h"
 #include "conic_symbolic.h"
+#define SN_EMULATE
+#include "conic_sn.cuh"
 
 extern "C" int32_t scpb_debug_kkt_solve(int32_t n, int32_t p, int32_t m, const int32_t *A_rp, const int32_t *A_ci,
                                         const int32_t *G_rp, const int32_t *G_ci, int32_t l, int32_t nsoc,
@@ -148,5 +150,49 @@ extern "C" int32_t scpb_debug_kkt_solve_sn(int32_t n, int32_t p, int32_t m, cons
         info[4] = wmax; info[5] = rmax; info[6] = S.nlevels; info[7] = S.nnzL;
     }
     (void)ns;
+    return SCPB_OK;
+}
+
+// The same system once more, this time through the WARP routines of conic_sn.cuh compiled in lane-emulation mode
+// (SN_EMULATE): the code that k_ipm_solve runs per (supernode, seed) item, executed here one item at a time.
+extern "C" int32_t scpb_debug_kkt_solve_sn_emu(int32_t n, int32_t p, int32_t m, const int32_t *A_rp, const int32_t *A_ci,
+                                               const int32_t *G_rp, const int32_t *G_ci, int32_t l, int32_t nsoc,
+                                               const int32_t *soc_dims, const int32_t *perm, const double *Av,
+                                               const double *Gv, const double *wm, double delta, double delta_dyn,
+                                               const double *rhs, double *sol, int64_t *info)
+{
+    ConeSymbolic S;
+    static const int zero = 0;
+    if (!cone_symbolic_build(S, n, p, m, A_rp, A_ci ? A_ci : &zero, G_rp, G_ci ? G_ci : &zero, l, nsoc, soc_dims, perm))
+        return SCPB_ERR_ARG;
+    const int nk = S.nk, ntgt = S.nnzL + nk, ns = (int)S.sn_first.size();
+    for (int s = 0; s < ns; s++)
+        if (S.sn_nrows[s] > SN_MAXROWS || S.sn_nrows[s] * S.sn_width[s] > SN_SCRATCH) return SCPB_ERR_UNSUPPORTED;
+    SnProgram Q{};
+    Q.first = S.sn_first.data(); Q.width = S.sn_width.data(); Q.nrows = S.sn_nrows.data();
+    Q.rows_ptr = S.sn_rows_ptr.data(); Q.rows = S.sn_rows.data(); Q.lvl_ptr = S.sn_lvl_ptr.data();
+    Q.lvl_nodes = S.sn_lvl_nodes.data(); Q.upd_xy = S.sn_upd_xy.data(); Q.sign = S.sn_sign.data();
+    Q.panel_off = S.sn_panel_off.data(); Q.upd_ptr = S.sn_upd_ptr.data(); Q.upd_dst = S.sn_upd_dst.data();
+    Q.nlevels = S.sn_nlevels;
+    std::vector<double> P((size_t)S.sn_panel_size, 0.0), invD(nk), v(nk), scr(SN_SCRATCH), xs(SN_MAXROWS + 32);
+    for (int t = 0; t < ntgt; t++) {
+        double acc = delta * S.as_sign[t];
+        if (S.as_src[t] >= 0) acc += Av[S.as_src[t]];
+        for (int k = S.as_ptr[t]; k < S.as_ptr[t + 1]; k++) acc += Gv[S.as_a[k]] * Gv[S.as_b[k]] * wm[S.as_c[k]];
+        P[(size_t)S.sn_pos_of_target[t]] = acc;
+    }
+    for (int lv = 0; lv < S.sn_nlevels; lv++)
+        for (int w_ = S.sn_lvl_ptr[lv]; w_ < S.sn_lvl_ptr[lv + 1]; w_++)
+            sn_factor_item(Q, S.sn_lvl_nodes[w_], P.data(), invD.data(), 1, 0, delta_dyn, scr.data());
+    for (int i = 0; i < nk; i++) v[S.iperm[i]] = rhs[i];
+    for (int lv = 0; lv < S.sn_nlevels; lv++)
+        for (int w_ = S.sn_lvl_ptr[lv]; w_ < S.sn_lvl_ptr[lv + 1]; w_++)
+            sn_forward_item(Q, S.sn_lvl_nodes[w_], P.data(), v.data(), 1, 0, xs.data());
+    for (int i = 0; i < nk; i++) v[i] *= invD[i];
+    for (int lv = S.sn_nlevels - 1; lv >= 0; lv--)
+        for (int w_ = S.sn_lvl_ptr[lv]; w_ < S.sn_lvl_ptr[lv + 1]; w_++)
+            sn_backward_item(Q, S.sn_lvl_nodes[w_], P.data(), v.data(), 1, 0, xs.data());
+    for (int i = 0; i < nk; i++) sol[i] = v[S.iperm[i]];
+    if (info) { info[0] = ns; info[1] = S.sn_nlevels; info[2] = S.sn_panel_size; info[3] = (int64_t)S.sn_upd_dst.size(); }
     return SCPB_OK;
 }

@@ -87,6 +87,8 @@ struct ConeSymbolic {
     std::vector<long long> sn_pos_of_target;         // target id (L position | nnzL + column) -> panel offset
     std::vector<long long> sn_upd_ptr;               // per supernode: range of its update scatter list
     std::vector<long long> sn_upd_dst;               // lower-triangle pairs (x >= y) of the below rows -> panel offset
+    std::vector<int> sn_upd_xy;                      // the pair itself, packed x | y << 16 (indices into the below rows)
+    std::vector<int> sn_sign;                        // expected pivot sign of each column (+1 / -1)
     long long sn_panel_size = 0;
     int sn_nlevels = 0;
     long long factor_ops = 0;
@@ -465,7 +467,9 @@ inline bool cone_symbolic_build(ConeSymbolic &S, int n, int p, int m, const int 
         }
         // update scatter lists
         S.sn_upd_ptr.assign(ns + 1, 0);
-        S.sn_upd_dst.clear();
+        S.sn_upd_dst.clear(); S.sn_upd_xy.clear();
+        S.sn_sign.resize(nk);
+        for (int j = 0; j < nk; j++) S.sn_sign[j] = S.as_sign[(size_t)S.nnzL + j];
         for (int s = 0; s < ns; s++) {
             const int w = S.sn_width[s], R = S.sn_nrows[s];
             const int *below = &S.sn_rows[S.sn_rows_ptr[s] + w];
@@ -474,6 +478,7 @@ inline bool cone_symbolic_build(ConeSymbolic &S, int n, int p, int m, const int 
                     const long long pp = panel_pos(below[x], below[y]);
                     if (pp < 0) { S.err = "internal: supernodal update falls outside the L pattern"; return false; }
                     S.sn_upd_dst.push_back(pp);
+                    S.sn_upd_xy.push_back(x | (y << 16));
                 }
             S.sn_upd_ptr[s + 1] = (long long)S.sn_upd_dst.size();
         }

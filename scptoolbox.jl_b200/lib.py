@@ -58,6 +58,8 @@ SIGNATURES = {
                                          _ip, _ip, _dp, _dp, _dp, C.c_double, C.c_double, _dp, _dp, C.POINTER(C.c_int64)]),
     "scpb_debug_kkt_solve_sn": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _ip, _ip, _ip, _ip, C.c_int32, C.c_int32,
                                          _ip, _ip, _dp, _dp, _dp, C.c_double, C.c_double, _dp, _dp, C.POINTER(C.c_int64)]),
+    "scpb_debug_kkt_solve_sn_emu": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _ip, _ip, _ip, _ip, C.c_int32, C.c_int32,
+                                         _ip, _ip, _dp, _dp, _dp, C.c_double, C.c_double, _dp, _dp, C.POINTER(C.c_int64)]),
 }
 
 
@@ -297,6 +299,12 @@ def debug_kkt_solve(A, G, l, soc_dims, perm, Avals, Gvals, wm, delta, rhs, delta
     Av, pAv = _f64(Avals); Gv, pGv = _f64(Gvals); wmv, pwm = _f64(wm); r, pr = _f64(rhs)
     sol = np.zeros(n + p)
     info = (C.c_int64 * 8)()
+    if supernodal == "emu":
+        rc = lib.scpb_debug_kkt_solve_sn_emu(n, p, m, a0[1], a1[1], g0[1], g1[1], int(l), len(soc_dims), sd[1], pm[1],
+                                             pAv, pGv, pwm, float(delta), float(delta_dyn), pr, sol.ctypes.data_as(_dp), info)
+        if rc != 0:
+            raise ScpbError(f"scpb_debug_kkt_solve_sn_emu failed ({rc})")
+        return sol, dict(zip(("supernodes", "sn_levels", "panel_doubles", "update_entries"), [int(v) for v in info[:4]]))
     if supernodal:
         rc = lib.scpb_debug_kkt_solve_sn(n, p, m, a0[1], a1[1], g0[1], g1[1], int(l), len(soc_dims), sd[1], pm[1],
                                          pAv, pGv, pwm, float(delta), float(delta_dyn), pr, sol.ctypes.data_as(_dp), info)

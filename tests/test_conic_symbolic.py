@@ -52,6 +52,12 @@ def test_kkt_programs_match_dense_solve(pkg, seed, n, p, l, soc):
         assert np.abs(sol2 - want).max() <= 1e-7 * max(1.0, np.abs(want).max()), info2
         assert info2["nnzL"] == info["nnzL"] and info2["sn_levels"] <= info["levels"]
         assert info2["supernodes"] <= n + p and info2["panel_doubles"] >= info["nnzL"] + n + p
+        # ... and so do the per-panel warp routines of csrc/conic_sn.cuh in lane-emulation mode
+        try:
+            sol3, info3 = pkg.lib.debug_kkt_solve(A, G, l, soc, perm, A.data, G.data, wm, delta, rhs, supernodal="emu")
+        except pkg.ScpbError:
+            continue                      # a panel larger than the warp scratch (random orderings of dense programs)
+        assert np.abs(sol3 - want).max() <= 1e-7 * max(1.0, np.abs(want).max()), info3
 
 
 def test_stage_order_keeps_fill_small(pkg):
@@ -109,3 +115,34 @@ def test_supernodal_program_on_the_starship_kkt(pkg):
     assert np.abs(s1 - s2).max() <= 1e-8 * max(1.0, np.abs(s1).max())
     # (this is the reference's NormOneBridge form, whose dense L1 blocks give wider supernodes than the product's lowering)
     assert i2["sn_levels"] * 2 <= i1["levels"] and i2["max_rows"] <= 64 and i2["max_width"] <= 32, (i1, i2)
+
+
+def test_supernodal_warp_routines_on_the_product_template(pkg, monkeypatch):
+    """The bench-shaped KKT (product template with the L1 lowering, stage ordering, N = 24): scalar program, supernodal
+    interpreter and the lane-emulated warp routines give the same solution."""
+    ex = pkg.examples.starship
+    mdl = ex.StarshipProblem(); mdl.hs = 100.0
+    traj = pkg.problem.TrajectoryProblem(mdl)
+    ex.define_problem(traj, "ptr", handle=None)
+    N = 24
+    pars = pkg.ptr.Parameters(N=N, Nsub=20, iter_max=5, disc_method=pkg.ptr.FOH, wvc=1e3, wtr=0.1, eps_abs=1e-5,
+                              eps_rel=1e-4, feas_tol=5e-3, q_tr=np.inf, q_exit=np.inf)
+
+    class FakeHandle:
+        def model_set(self, *a): pass
+    monkeypatch.setattr(pkg.lib, "ConeProblem", lambda *a, **k: type("C", (), {"c": None, "close": lambda s: None})())
+    fake = FakeHandle(); fake.lib = type("L", (), {"scpb_ptr_setup": staticmethod(lambda *a: 0)})(); fake.h = None
+    fake._check = lambda rc, what: None
+    pbm = pkg.ptr.SCPProblem(pars, traj, fake, l1_block=4)
+    cp = pbm.cp
+    rng = np.random.default_rng(1)
+    A, G = cp["A"], cp["G"]
+    Av = rng.uniform(0.5, 1.5, A.nnz); Gv = rng.uniform(0.5, 1.5, G.nnz); wm = rng.uniform(0.5, 2.0, cp["l"])
+    rhs = rng.standard_normal(cp["n"] + cp["p"])
+    args = (A, G, cp["l"], [], pbm.perm, Av, Gv, wm, 1e-9, rhs)
+    s1, i1 = pkg.lib.debug_kkt_solve(*args, delta_dyn=1e-7)
+    s2, i2 = pkg.lib.debug_kkt_solve(*args, delta_dyn=1e-7, supernodal=True)
+    s3, i3 = pkg.lib.debug_kkt_solve(*args, delta_dyn=1e-7, supernodal="emu")
+    scale = max(1.0, np.abs(s1).max())
+    assert np.abs(s1 - s2).max() <= 1e-8 * scale and np.abs(s2 - s3).max() <= 1e-9 * scale
+    assert i2["sn_levels"] * 3 <= i1["levels"] and i2["max_rows"] <= 32 and i2["max_width"] <= 10, (i1, i2)
