@@ -12,6 +12,7 @@ struct scpb_cone_s {
     std::vector<void *> dev_ints;
     // data buffers (grow-only), sized for (ngroups*G) seeds
     int capB = 0, capG = 0, lanes = 0;
+    bool sn_ok = false;   // every supernodal panel fits the warp scratch
     std::vector<double *> bufs;
     IpmData D{};
     double *stage = nullptr;  // seed-major staging on device
@@ -89,7 +90,7 @@ static int cone_reserve(scpb_cone_s *c, int B, int G)
     D.soceta = al(S.nsoc + 1);
     D.dx = al(n); D.dy = al(p); D.dz = al(m); D.ds = al(m); D.dsa = al(m); D.dza = al(m); D.tm = al(m); D.gm = al(m);
     D.r1 = al(n); D.r2 = al(p); D.e1 = al(nm); D.e2 = al(p); D.rhs = al(nk);
-    D.Y = al(S.nnzL + nk); D.Ls = al(S.nnzL + 1); D.Lrow = al(S.nnzL + 1); D.invD = al(nk);
+    D.Y = al(std::max<size_t>((size_t)S.nnzL + nk, (size_t)S.sn_panel_size)); D.Ls = al(S.nnzL + 1); D.Lrow = al(S.nnzL + 1); D.invD = al(nk);
     for (double *q : c->bufs)
         if (!q) return set_err(h, SCPB_ERR_CUDA, "cone solver: device allocation failed (B=%d)", B);
     if (cudaMalloc((void **)&c->d_status, sizeof(int) * Bpad) != cudaSuccess ||
@@ -116,6 +117,18 @@ int scpb_internal_cone_run(scpb_cone_s *c, const IpmOpts &o)
     const size_t vbytes = sizeof(double) * (size_t)c->S.nk * c->D.G;
     c->D.vsmem = (smem + vbytes <= 200 * 1024 && !getenv("SCPB_NO_VSMEM")) ? 1 : 0;   // env: force the global-memory sweep (tests)
     if (c->D.vsmem) smem += vbytes;
+    // experimental supernodal path (csrc/conic_sn.cuh; CPU-checked, not yet run on a GPU): needs the shared-memory
+    // vector (its window doubles as the factorisation's panel scratch) and a per-warp sweep scratch behind it
+    c->D.sn = 0;
+    if (getenv("SCPB_SUPERNODAL") && c->sn_ok && c->D.vsmem) {
+        const size_t nw = (o.threads >= 1024 ? 1024 : 512) / 32;
+        const size_t xbytes = sizeof(double) * nw * (SN_MAXROWS + 32);
+        if (vbytes >= sizeof(double) * nw * SN_SCRATCH && smem + xbytes <= 205 * 1024) {
+            c->D.sn = 1;
+            c->D.o_snx = (int)(smem / sizeof(int));
+            smem += xbytes;
+        }
+    }
     c->D.lvl_prof = (c->d_prof && getenv("SCPB_LEVEL_PROFILE")) ? 1 : 0;   // diagnostic: per-level cycle counters of CTA 0
     if (o.threads >= 1024) {
         SCPB_CUDA(h, cudaFuncSetAttribute(k_ipm_solve<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -184,6 +197,17 @@ int32_t scpb_cone_setup(scpb_handle h, int32_t n, int32_t p, int32_t m, const in
 #undef UP
     P.fw_item = (const int4 *)upload_ints(c, S.fw_item); P.bw_item = (const int4 *)upload_ints(c, S.bw_item);
     P.fa_item = (const int4 *)upload_ints(c, S.fa_item); P.fb_item = (const int4 *)upload_ints(c, S.fb_item);
+    P.ysize = (int)std::max<long long>((long long)S.nnzL + S.nk, S.sn_panel_size);
+    P.sn.first = upload_ints(c, S.sn_first); P.sn.width = upload_ints(c, S.sn_width); P.sn.nrows = upload_ints(c, S.sn_nrows);
+    P.sn.rows_ptr = upload_ints(c, S.sn_rows_ptr); P.sn.rows = upload_ints(c, S.sn_rows);
+    P.sn.lvl_ptr = upload_ints(c, S.sn_lvl_ptr); P.sn.lvl_nodes = upload_ints(c, S.sn_lvl_nodes);
+    P.sn.upd_xy = upload_ints(c, S.sn_upd_xy); P.sn.sign = upload_ints(c, S.sn_sign);
+    P.sn.panel_off = upload_ints(c, S.sn_panel_off); P.sn.upd_ptr = upload_ints(c, S.sn_upd_ptr);
+    P.sn.upd_dst = upload_ints(c, S.sn_upd_dst); P.sn.nlevels = S.sn_nlevels;
+    P.sn_pos = upload_ints(c, S.sn_pos_of_target);
+    c->sn_ok = true;
+    for (size_t s_ = 0; s_ < S.sn_first.size(); s_++)
+        if (S.sn_nrows[s_] > SN_MAXROWS || S.sn_nrows[s_] * S.sn_width[s_] > SN_SCRATCH) c->sn_ok = false;
     P.fa_lvl = upload_ints(c, S.fa_lvl); P.fa_R = upload_ints(c, S.fa_R); P.fb_lvl = upload_ints(c, S.fb_lvl);
     P.fwp_item = (const int4 *)upload_ints(c, S.fwp_item); P.bwp_item = (const int4 *)upload_ints(c, S.bwp_item);
     P.fwp_lvl = upload_ints(c, S.fwp_lvl); P.bwp_lvl = upload_ints(c, S.bwp_lvl);

@@ -111,7 +111,7 @@ extern "C" int32_t scpb_debug_kkt_solve_sn(int32_t n, int32_t p, int32_t m, cons
                     for (int r = c2; r < R; r++) Q[r + (size_t)R * c2] -= Q[r + (size_t)R * c] * f;
                 }
             }
-            long long k = S.sn_upd_ptr[s];   // Schur update of the ancestors' panels
+            int k = S.sn_upd_ptr[s];   // Schur update of the ancestors' panels
             for (int y = 0; y < R - w; y++)
                 for (int x = y; x < R - w; x++) {
                     double u = 0.0;

@@ -17,6 +17,8 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
+#include "conic_sn.cuh"
+
 struct IpmProgram {  // device copies of ConeSymbolic index arrays
     int n, p, m, l, nsoc, nk, nnzL, nlevels, nwm, nnzA, nnzG;
     const int *soc_dim, *soc_off, *soc_woff;
@@ -28,6 +30,9 @@ struct IpmProgram {  // device copies of ConeSymbolic index arrays
     const int *as_ptr, *as_a, *as_b, *as_c, *as_src, *as_sign;
     const int4 *fw_item, *bw_item;
     const int4 *fwp_item, *bwp_item, *fa_item, *fb_item;
+    SnProgram sn;            // supernodal program (used when IpmData.sn is set)
+    int ysize;               // doubles per seed of the Y array: max(nnzL + nk, supernodal panels)
+    const int *sn_pos;       // target id -> panel offset
     const int *fa_lvl, *fa_R, *fb_lvl;
     const int *fwp_lvl, *bwp_lvl, *fwp_R, *bwp_R;
     const int2 *Lr_pc, *ft_op;
@@ -59,6 +64,8 @@ struct IpmData {  // group-blocked device arrays, all for B seeds
     double *pobj, *dobj, *res;   // res: [3][B] pres, dres, gap
     int *status, *iters;
     int lvl_prof;      // 1: also record per-level cycles behind prof[12..]
+    int sn;            // 1: supernodal factorisation / sweeps (SCPB_SUPERNODAL=1; experimental, see conic_sn.cuh)
+    int o_snx;         // offset (ints) of the per-warp sweep scratch in the dynamic shared window
     long long *prof;   // [8] cycle counters of CTA 0: equilibrate, init, residuals, scaling+assemble, factor, solves, line search+update, total
 };
 
@@ -82,6 +89,8 @@ struct Ctx {
     int *flag;                          // shared scratch word for CTA-uniform decisions
     long long t_fw, t_bw, t_ldl_n;      // cycle counters (CTA-local copies, meaningful on thread 0)
     long long *lprof;                   // thread 0 of CTA 0: per-level cycles [factor | forward | backward][nlevels]
+    int sn, o_snx;                      // supernodal mode, offset of the per-warp sweep scratch
+    const double *Ypanels;              // supernodal mode: this group's panels (the Y array)
     double *vs;                         // shared-memory substitution vector (nullptr: use global memory)
     double *Lrow;                       // row-ordered copy of the scaled factor (forward substitution)
     double reftol;                      // iterative refinement stops once |residual|_inf <= reftol*(1+|rhs|_inf)
@@ -201,7 +210,7 @@ __device__ void kkt_assemble(const IpmProgram &P, const Ctx &c, const IpmData &D
         if (src >= 0) acc += Av[GI(src)];
         for (int k = P.as_ptr[t]; k < P.as_ptr[t + 1]; k++)
             acc = fma(Gv[GI(P.as_a[k])] * Gv[GI(P.as_b[k])], wmx[GI(P.as_c[k])], acc);
-        Y[GI(t)] = acc;
+        Y[GI(D.sn ? P.sn_pos[t] : t)] = acc;   // supernodal mode: straight into the dense panels
     }
     __syncthreads();
 }
@@ -322,8 +331,53 @@ __device__ __noinline__ void kkt_factor_levels(const FactorArgs a)
 #undef IPM_FA_OPS
 }
 
+// supernodal numeric factorisation: one warp per (supernode, seed) item, one barrier per supernodal level; the warp
+// scratch (panel copies) borrows the shared-memory window of the substitution vector, which is idle here
+__device__ void kkt_factor_sn(const IpmProgram &P, Ctx &c, double *Y, double *invD, double delta_dyn)
+{
+    const int warp = c.tid >> 5, G = c.G;
+    double *scr = c.vs + (size_t)warp * SN_SCRATCH;
+    for (int lv = 0; lv < P.sn.nlevels; lv++) {
+        const int i0 = P.sn.lvl_ptr[lv], nit = (P.sn.lvl_ptr[lv + 1] - i0) * G;
+        for (int it = warp; it < nit; it += c.nwarps)
+            sn_factor_item(P.sn, P.sn.lvl_nodes[i0 + it / G], Y, invD, G, it % G, delta_dyn, scr);
+        __syncthreads();
+    }
+}
+
+// supernodal substitutions on the shared-memory vector
+__device__ void kkt_ldl_solve_sn(const IpmProgram &P, Ctx &c, const double *Y, const double *invD, double *v)
+{
+    const int warp = c.tid >> 5, G = c.G, sg = c.sg;
+    double *vs = c.vs;
+    double *xs = (double *)(ipm_smem + c.o_snx) + (size_t)warp * (SN_MAXROWS + 32);
+    const long long t0_ = clock64();
+    for (int i = c.slot; i < P.nk; i += c.nslots) vs[i * G + sg] = v[GI(i)];
+    __syncthreads();
+    for (int lv = 0; lv < P.sn.nlevels; lv++) {
+        const int i0 = P.sn.lvl_ptr[lv], nit = (P.sn.lvl_ptr[lv + 1] - i0) * G;
+        for (int it = warp; it < nit; it += c.nwarps)
+            sn_forward_item(P.sn, P.sn.lvl_nodes[i0 + it / G], Y, vs, G, it % G, xs);
+        __syncthreads();
+    }
+    const long long t1_ = clock64();
+    for (int i = c.slot; i < P.nk; i += c.nslots) vs[i * G + sg] *= invD[GI(i)];
+    __syncthreads();
+    for (int lv = P.sn.nlevels - 1; lv >= 0; lv--) {
+        const int i0 = P.sn.lvl_ptr[lv], nit = (P.sn.lvl_ptr[lv + 1] - i0) * G;
+        for (int it = warp; it < nit; it += c.nwarps)
+            sn_backward_item(P.sn, P.sn.lvl_nodes[i0 + it / G], Y, vs, G, it % G, xs);
+        __syncthreads();
+    }
+    for (int i = c.slot; i < P.nk; i += c.nslots) v[GI(i)] = vs[i * G + sg];
+    __syncthreads();
+    const long long t2_ = clock64();
+    c.t_fw += t1_ - t0_; c.t_bw += t2_ - t1_; c.t_ldl_n += 1;
+}
+
 __device__ void kkt_factor(const IpmProgram &P, Ctx &c, double *Y, double *Ls, double *invD, double delta_dyn)
 {
+    if (c.sn) { kkt_factor_sn(P, c, Y, invD, delta_dyn); return; }
     FactorArgs a;
     a.fa_item = P.fa_item; a.fb_item = P.fb_item; a.ft_op = P.ft_op;
     a.Y = Y; a.Ls = Ls; a.Lrow = c.Lrow; a.invD = invD; a.delta_dyn = delta_dyn;
@@ -459,6 +513,7 @@ __device__ void kkt_ldl_solve_smem(const IpmProgram &P, Ctx &c, const double *Ls
 // in-place solve of (L D L') v = rhs on the permuted vector v
 __device__ void kkt_ldl_solve(const IpmProgram &P, Ctx &c, const double *Ls, const double *invD, double *v)
 {
+    if (c.sn) { kkt_ldl_solve_sn(P, c, c.Ypanels, invD, v); return; }
     if (c.vs) { kkt_ldl_solve_smem(P, c, Ls, invD, v); return; }
     set_lanes(c, c.Rmax);
     const int G = c.G, sg = c.sg;
@@ -871,7 +926,8 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
     double *r1 = GP(D.r1, P.n), *r2 = GP(D.r2, P.p);
     const int nm = (P.n > P.m ? P.n : P.m);
     double *e1 = GP(D.e1, nm), *e2 = GP(D.e2, P.p), *rhs = GP(D.rhs, P.nk);
-    double *Y = GP(D.Y, P.nnzL + P.nk), *Ls = GP(D.Ls, P.nnzL + 1), *invD = GP(D.invD, P.nk);
+    double *Y = GP(D.Y, P.ysize), *Ls = GP(D.Ls, P.nnzL + 1), *invD = GP(D.invD, P.nk);
+    c.sn = D.sn; c.o_snx = D.o_snx; c.Ypanels = Y;
     c.Lrow = GP(D.Lrow, P.nnzL + 1);
 #undef GP
 

@@ -31,7 +31,7 @@
 
 struct SnProgram {          // device view of the supernodal program (all arrays shared by the batch)
     const int *first, *width, *nrows, *rows_ptr, *rows, *lvl_ptr, *lvl_nodes, *upd_xy, *sign;
-    const long long *panel_off, *upd_ptr, *upd_dst;
+    const int *panel_off, *upd_ptr, *upd_dst;
     int nlevels;
 };
 
@@ -41,8 +41,8 @@ SN_FN void sn_factor_item(const SnProgram &S, int s, double *P, double *invD, in
                           double *scr)
 {
     const int a = S.first[s], w = S.width[s], R = S.nrows[s];
-    const long long off = S.panel_off[s];
-    SN_LANES(l) { for (int e = l; e < R * w; e += 32) scr[e] = SN_LDCG(&P[(off + e) * G + sg]); }
+    const int off = S.panel_off[s];
+    SN_LANES(l) { for (int e = l; e < R * w; e += 32) scr[e] = SN_LDCG(&P[(size_t)(off + e) * G + sg]); }
     SN_SYNC();
     for (int c = 0; c < w; c++) {
         double d = scr[c + R * c];
@@ -62,14 +62,14 @@ SN_FN void sn_factor_item(const SnProgram &S, int s, double *P, double *invD, in
         }
         SN_SYNC();
     }
-    SN_LANES(l) { for (int e = l; e < R * w; e += 32) P[(off + e) * G + sg] = scr[e]; }
-    const long long k0 = S.upd_ptr[s], k1 = S.upd_ptr[s + 1];
+    SN_LANES(l) { for (int e = l; e < R * w; e += 32) P[(size_t)(off + e) * G + sg] = scr[e]; }
+    const int k0 = S.upd_ptr[s], k1 = S.upd_ptr[s + 1];
     SN_LANES(l) {
-        for (long long k = k0 + l; k < k1; k += 32) {
+        for (int k = k0 + l; k < k1; k += 32) {
             const int xy = S.upd_xy[k], x = xy & 0xffff, y = xy >> 16;
             double u = 0.0;
             for (int c = 0; c < w; c++) u += scr[w + x + R * c] * scr[c + R * c] * scr[w + y + R * c];
-            SN_ATOMIC_SUB(&P[S.upd_dst[k] * G + sg], u);
+            SN_ATOMIC_SUB(&P[(size_t)S.upd_dst[k] * G + sg], u);
         }
     }
     SN_SYNC();
@@ -80,14 +80,14 @@ SN_FN void sn_factor_item(const SnProgram &S, int s, double *P, double *invD, in
 SN_FN void sn_forward_item(const SnProgram &S, int s, const double *P, double *v, int G, int sg, double *xs)
 {
     const int w = S.width[s], R = S.nrows[s];
-    const long long off = S.panel_off[s];
+    const int off = S.panel_off[s];
     const int *rows = S.rows + S.rows_ptr[s];
     SN_LANES(l) { for (int r = l; r < R; r += 32) xs[r] = (r < w) ? v[(size_t)rows[r] * G + sg] : 0.0; }
     SN_SYNC();
     for (int c = 0; c < w; c++) {
         SN_LANES(l) {
             const double xc = xs[c];
-            for (int r = c + 1 + l; r < R; r += 32) xs[r] -= P[(off + r + (long long)R * c) * G + sg] * xc;
+            for (int r = c + 1 + l; r < R; r += 32) xs[r] -= P[(size_t)(off + r + R * c) * G + sg] * xc;
         }
         SN_SYNC();
     }
@@ -105,7 +105,7 @@ SN_FN void sn_forward_item(const SnProgram &S, int s, const double *P, double *v
 SN_FN void sn_backward_item(const SnProgram &S, int s, const double *P, double *v, int G, int sg, double *xs)
 {
     const int w = S.width[s], R = S.nrows[s];
-    const long long off = S.panel_off[s];
+    const int off = S.panel_off[s];
     const int *rows = S.rows + S.rows_ptr[s];
     double *ps = xs + SN_MAXROWS;
     SN_LANES(l) { for (int r = l; r < R; r += 32) xs[r] = v[(size_t)rows[r] * G + sg]; }
@@ -113,7 +113,7 @@ SN_FN void sn_backward_item(const SnProgram &S, int s, const double *P, double *
     for (int c = w - 1; c >= 0; c--) {
         SN_LANES(l) {
             double acc = 0.0;
-            for (int r = c + 1 + l; r < R; r += 32) acc += P[(off + r + (long long)R * c) * G + sg] * xs[r];
+            for (int r = c + 1 + l; r < R; r += 32) acc += P[(size_t)(off + r + R * c) * G + sg] * xs[r];
             ps[l] = acc;
         }
         SN_SYNC();

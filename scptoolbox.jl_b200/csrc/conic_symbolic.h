@@ -82,11 +82,11 @@ struct ConeSymbolic {
     // against 88 scalar ones (profiles/r1_supernode_study.txt).
     std::vector<int> sn_first, sn_width, sn_nrows;   // per supernode
     std::vector<int> sn_rows_ptr, sn_rows;           // row (node) indices of each panel
-    std::vector<long long> sn_panel_off;             // offset of each panel in the per-seed panel array
+    std::vector<int> sn_panel_off;                   // offset of each panel in the per-seed panel array
     std::vector<int> sn_lvl_ptr, sn_lvl_nodes;       // supernodal level schedule (children before parents)
-    std::vector<long long> sn_pos_of_target;         // target id (L position | nnzL + column) -> panel offset
-    std::vector<long long> sn_upd_ptr;               // per supernode: range of its update scatter list
-    std::vector<long long> sn_upd_dst;               // lower-triangle pairs (x >= y) of the below rows -> panel offset
+    std::vector<int> sn_pos_of_target;               // target id (L position | nnzL + column) -> panel offset
+    std::vector<int> sn_upd_ptr;                     // per supernode: range of its update scatter list
+    std::vector<int> sn_upd_dst;                     // lower-triangle pairs (x >= y) of the below rows -> panel offset
     std::vector<int> sn_upd_xy;                      // the pair itself, packed x | y << 16 (indices into the below rows)
     std::vector<int> sn_sign;                        // expected pivot sign of each column (+1 / -1)
     long long sn_panel_size = 0;
@@ -433,7 +433,9 @@ inline bool cone_symbolic_build(ConeSymbolic &S, int n, int p, int m, const int 
         S.sn_rows_ptr.assign(ns + 1, 0); S.sn_panel_off.assign(ns + 1, 0);
         for (int s = 0; s < ns; s++) {
             S.sn_rows_ptr[s + 1] = S.sn_rows_ptr[s] + S.sn_nrows[s];
-            S.sn_panel_off[s + 1] = S.sn_panel_off[s] + (long long)S.sn_nrows[s] * S.sn_width[s];
+            const long long nxt_ = (long long)S.sn_panel_off[s] + (long long)S.sn_nrows[s] * S.sn_width[s];
+            if (nxt_ > 2000000000LL) { S.err = "supernodal panels too large"; return false; }
+            S.sn_panel_off[s + 1] = (int)nxt_;
         }
         S.sn_panel_size = S.sn_panel_off[ns];
         S.sn_rows.resize(S.sn_rows_ptr[ns]);
@@ -444,7 +446,7 @@ inline bool cone_symbolic_build(ConeSymbolic &S, int n, int p, int m, const int 
             for (int q = S.L_cp[b]; q < S.L_cp[b + 1]; q++) S.sn_rows[o++] = S.L_ri[q];
         }
         // panel position of entry (row i, column j)
-        auto panel_pos = [&](int i, int j) -> long long {
+        auto panel_pos = [&](int i, int j) -> int {
             const int s = sn_of[j], a = S.sn_first[s], w = S.sn_width[s], R = S.sn_nrows[s], c = j - a;
             int r;
             if (i < a + w) r = i - a;
@@ -454,13 +456,13 @@ inline bool cone_symbolic_build(ConeSymbolic &S, int n, int p, int m, const int 
                 if (it == hi || *it != i) return -1;
                 r = w + (int)(it - lo);
             }
-            return S.sn_panel_off[s] + r + (long long)R * c;
+            return S.sn_panel_off[s] + r + R * c;
         };
         S.sn_pos_of_target.assign((size_t)S.nnzL + nk, -1);
         for (int j = 0; j < nk; j++) {
             S.sn_pos_of_target[(size_t)S.nnzL + j] = panel_pos(j, j);
             for (int q = S.L_cp[j]; q < S.L_cp[j + 1]; q++) {
-                const long long pp = panel_pos(S.L_ri[q], j);
+                const int pp = panel_pos(S.L_ri[q], j);
                 if (pp < 0) { S.err = "internal: supernode panel does not cover an L entry"; return false; }
                 S.sn_pos_of_target[q] = pp;
             }
@@ -475,12 +477,13 @@ inline bool cone_symbolic_build(ConeSymbolic &S, int n, int p, int m, const int 
             const int *below = &S.sn_rows[S.sn_rows_ptr[s] + w];
             for (int y = 0; y < R - w; y++)
                 for (int x = y; x < R - w; x++) {
-                    const long long pp = panel_pos(below[x], below[y]);
+                    const int pp = panel_pos(below[x], below[y]);
                     if (pp < 0) { S.err = "internal: supernodal update falls outside the L pattern"; return false; }
                     S.sn_upd_dst.push_back(pp);
                     S.sn_upd_xy.push_back(x | (y << 16));
                 }
-            S.sn_upd_ptr[s + 1] = (long long)S.sn_upd_dst.size();
+            if (S.sn_upd_dst.size() > 2000000000ULL) { S.err = "supernodal update lists too large"; return false; }
+            S.sn_upd_ptr[s + 1] = (int)S.sn_upd_dst.size();
         }
         // level schedule: a supernode follows every supernode whose last column's parent lies inside it
         std::vector<int> slev(ns, 0);
