@@ -205,9 +205,9 @@ int32_t scpb_cone_setup(scpb_handle h, int32_t n, int32_t p, int32_t m, const in
     P.sn.panel_off = upload_ints(c, S.sn_panel_off); P.sn.upd_ptr = upload_ints(c, S.sn_upd_ptr);
     P.sn.upd_dst = upload_ints(c, S.sn_upd_dst); P.sn.nlevels = S.sn_nlevels;
     P.sn_pos = upload_ints(c, S.sn_pos_of_target);
-    c->sn_ok = true;
-    for (size_t s_ = 0; s_ < S.sn_first.size(); s_++)
-        if (S.sn_nrows[s_] > SN_MAXROWS || S.sn_nrows[s_] * S.sn_width[s_] > SN_SCRATCH) c->sn_ok = false;
+    P.sn.cls_ptr = upload_ints(c, S.sn_cls_ptr);
+    static_assert(SN_SCRATCH == 384 && SN_MAXROWS == 64, "conic_symbolic.h (cls_of) assumes these scratch sizes");
+    c->sn_ok = S.sn_fits;
     P.fa_lvl = upload_ints(c, S.fa_lvl); P.fa_R = upload_ints(c, S.fa_R); P.fb_lvl = upload_ints(c, S.fb_lvl);
     P.fwp_item = (const int4 *)upload_ints(c, S.fwp_item); P.bwp_item = (const int4 *)upload_ints(c, S.bwp_item);
     P.fwp_lvl = upload_ints(c, S.fwp_lvl); P.bwp_lvl = upload_ints(c, S.bwp_lvl);

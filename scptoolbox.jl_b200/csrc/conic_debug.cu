@@ -166,15 +166,22 @@ extern "C" int32_t scpb_debug_kkt_solve_sn_emu(int32_t n, int32_t p, int32_t m, 
     if (!cone_symbolic_build(S, n, p, m, A_rp, A_ci ? A_ci : &zero, G_rp, G_ci ? G_ci : &zero, l, nsoc, soc_dims, perm))
         return SCPB_ERR_ARG;
     const int nk = S.nk, ntgt = S.nnzL + nk, ns = (int)S.sn_first.size();
-    for (int s = 0; s < ns; s++)
-        if (S.sn_nrows[s] > SN_MAXROWS || S.sn_nrows[s] * S.sn_width[s] > SN_SCRATCH) return SCPB_ERR_UNSUPPORTED;
+    static_assert(SN_SCRATCH == 384 && SN_MAXROWS == 64, "conic_symbolic.h (cls_of) assumes these scratch sizes");
+    if (!S.sn_fits) return SCPB_ERR_UNSUPPORTED;
     SnProgram Q{};
     Q.first = S.sn_first.data(); Q.width = S.sn_width.data(); Q.nrows = S.sn_nrows.data();
     Q.rows_ptr = S.sn_rows_ptr.data(); Q.rows = S.sn_rows.data(); Q.lvl_ptr = S.sn_lvl_ptr.data();
     Q.lvl_nodes = S.sn_lvl_nodes.data(); Q.upd_xy = S.sn_upd_xy.data(); Q.sign = S.sn_sign.data();
     Q.panel_off = S.sn_panel_off.data(); Q.upd_ptr = S.sn_upd_ptr.data(); Q.upd_dst = S.sn_upd_dst.data();
-    Q.nlevels = S.sn_nlevels;
+    Q.nlevels = S.sn_nlevels; Q.cls_ptr = S.sn_cls_ptr.data();
     std::vector<double> P((size_t)S.sn_panel_size, 0.0), invD(nk), v(nk), scr(SN_SCRATCH), xs(SN_MAXROWS + 32);
+    // per level the three lane-group classes, exactly as the kernel walks them (each group with its share of the scratch)
+    auto each = [&](int lv, auto &&f8, auto &&f16, auto &&f32) {
+        const int *cp_ = &S.sn_cls_ptr[4 * (size_t)lv];
+        for (int w_ = cp_[0]; w_ < cp_[1]; w_++) f8(S.sn_lvl_nodes[w_]);
+        for (int w_ = cp_[1]; w_ < cp_[2]; w_++) f16(S.sn_lvl_nodes[w_]);
+        for (int w_ = cp_[2]; w_ < cp_[3]; w_++) f32(S.sn_lvl_nodes[w_]);
+    };
     for (int t = 0; t < ntgt; t++) {
         double acc = delta * S.as_sign[t];
         if (S.as_src[t] >= 0) acc += Av[S.as_src[t]];
@@ -182,16 +189,20 @@ extern "C" int32_t scpb_debug_kkt_solve_sn_emu(int32_t n, int32_t p, int32_t m, 
         P[(size_t)S.sn_pos_of_target[t]] = acc;
     }
     for (int lv = 0; lv < S.sn_nlevels; lv++)
-        for (int w_ = S.sn_lvl_ptr[lv]; w_ < S.sn_lvl_ptr[lv + 1]; w_++)
-            sn_factor_item(Q, S.sn_lvl_nodes[w_], P.data(), invD.data(), 1, 0, delta_dyn, scr.data());
+        each(lv, [&](int s) { sn_factor_item<8>(Q, s, P.data(), invD.data(), 1, 0, delta_dyn, scr.data() + 3 * (SN_SCRATCH / 4)); },
+             [&](int s) { sn_factor_item<16>(Q, s, P.data(), invD.data(), 1, 0, delta_dyn, scr.data() + SN_SCRATCH / 2); },
+             [&](int s) { sn_factor_item<32>(Q, s, P.data(), invD.data(), 1, 0, delta_dyn, scr.data()); });
     for (int i = 0; i < nk; i++) v[S.iperm[i]] = rhs[i];
+    const int XS = SN_MAXROWS + 32;
     for (int lv = 0; lv < S.sn_nlevels; lv++)
-        for (int w_ = S.sn_lvl_ptr[lv]; w_ < S.sn_lvl_ptr[lv + 1]; w_++)
-            sn_forward_item(Q, S.sn_lvl_nodes[w_], P.data(), v.data(), 1, 0, xs.data());
+        each(lv, [&](int s) { sn_forward_item<8>(Q, s, P.data(), v.data(), 1, 0, xs.data() + 3 * (XS / 4)); },
+             [&](int s) { sn_forward_item<16>(Q, s, P.data(), v.data(), 1, 0, xs.data() + XS / 2); },
+             [&](int s) { sn_forward_item<32>(Q, s, P.data(), v.data(), 1, 0, xs.data()); });
     for (int i = 0; i < nk; i++) v[i] *= invD[i];
     for (int lv = S.sn_nlevels - 1; lv >= 0; lv--)
-        for (int w_ = S.sn_lvl_ptr[lv]; w_ < S.sn_lvl_ptr[lv + 1]; w_++)
-            sn_backward_item(Q, S.sn_lvl_nodes[w_], P.data(), v.data(), 1, 0, xs.data());
+        each(lv, [&](int s) { sn_backward_item<8>(Q, s, P.data(), v.data(), 1, 0, xs.data() + 3 * (XS / 4)); },
+             [&](int s) { sn_backward_item<16>(Q, s, P.data(), v.data(), 1, 0, xs.data() + XS / 2); },
+             [&](int s) { sn_backward_item<32>(Q, s, P.data(), v.data(), 1, 0, xs.data()); });
     for (int i = 0; i < nk; i++) sol[i] = v[S.iperm[i]];
     if (info) { info[0] = ns; info[1] = S.sn_nlevels; info[2] = S.sn_panel_size; info[3] = (int64_t)S.sn_upd_dst.size(); }
     return SCPB_OK;

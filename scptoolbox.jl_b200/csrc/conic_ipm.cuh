@@ -331,16 +331,29 @@ __device__ __noinline__ void kkt_factor_levels(const FactorArgs a)
 #undef IPM_FA_OPS
 }
 
-// supernodal numeric factorisation: one warp per (supernode, seed) item, one barrier per supernodal level; the warp
-// scratch (panel copies) borrows the shared-memory window of the substitution vector, which is idle here
+// supernodal numeric factorisation: one lane group (8, 16 or 32 lanes, by panel size) per (supernode, seed) item, one
+// barrier per supernodal level; the scratch (panel copies) borrows the shared-memory window of the substitution
+// vector, which is idle here
+template <int GS, class F>
+__device__ __forceinline__ void sn_for_items(const IpmProgram &P, const Ctx &c, int lv, int cls, F &&f)
+{
+    constexpr int GPW = 32 / GS;                       // lane groups per warp
+    const int i0 = P.sn.cls_ptr[4 * lv + cls], nit = (P.sn.cls_ptr[4 * lv + cls + 1] - i0) * c.G;
+    const int unit = (c.tid >> 5) * GPW + ((c.tid & 31) / GS), nunits = c.nwarps * GPW;
+    for (int it = unit; it < nit; it += nunits) f(P.sn.lvl_nodes[i0 + it / c.G], it % c.G, (c.tid & 31) / GS);
+}
+
 __device__ void kkt_factor_sn(const IpmProgram &P, Ctx &c, double *Y, double *invD, double delta_dyn)
 {
-    const int warp = c.tid >> 5, G = c.G;
-    double *scr = c.vs + (size_t)warp * SN_SCRATCH;
+    const int G = c.G;
+    double *scr = c.vs + (size_t)(c.tid >> 5) * SN_SCRATCH;
     for (int lv = 0; lv < P.sn.nlevels; lv++) {
-        const int i0 = P.sn.lvl_ptr[lv], nit = (P.sn.lvl_ptr[lv + 1] - i0) * G;
-        for (int it = warp; it < nit; it += c.nwarps)
-            sn_factor_item(P.sn, P.sn.lvl_nodes[i0 + it / G], Y, invD, G, it % G, delta_dyn, scr);
+        sn_for_items<8>(P, c, lv, 0, [&](int s, int sgi, int sub) {
+            sn_factor_item<8>(P.sn, s, Y, invD, G, sgi, delta_dyn, scr + sub * (SN_SCRATCH / 4)); });
+        sn_for_items<16>(P, c, lv, 1, [&](int s, int sgi, int sub) {
+            sn_factor_item<16>(P.sn, s, Y, invD, G, sgi, delta_dyn, scr + sub * (SN_SCRATCH / 2)); });
+        sn_for_items<32>(P, c, lv, 2, [&](int s, int sgi, int) {
+            sn_factor_item<32>(P.sn, s, Y, invD, G, sgi, delta_dyn, scr); });
         __syncthreads();
     }
 }
@@ -348,25 +361,26 @@ __device__ void kkt_factor_sn(const IpmProgram &P, Ctx &c, double *Y, double *in
 // supernodal substitutions on the shared-memory vector
 __device__ void kkt_ldl_solve_sn(const IpmProgram &P, Ctx &c, const double *Y, const double *invD, double *v)
 {
-    const int warp = c.tid >> 5, G = c.G, sg = c.sg;
+    const int G = c.G, sg = c.sg;
+    constexpr int XS = SN_MAXROWS + 32;
     double *vs = c.vs;
-    double *xs = (double *)(ipm_smem + c.o_snx) + (size_t)warp * (SN_MAXROWS + 32);
+    double *xs = (double *)(ipm_smem + c.o_snx) + (size_t)(c.tid >> 5) * XS;
     const long long t0_ = clock64();
     for (int i = c.slot; i < P.nk; i += c.nslots) vs[i * G + sg] = v[GI(i)];
     __syncthreads();
     for (int lv = 0; lv < P.sn.nlevels; lv++) {
-        const int i0 = P.sn.lvl_ptr[lv], nit = (P.sn.lvl_ptr[lv + 1] - i0) * G;
-        for (int it = warp; it < nit; it += c.nwarps)
-            sn_forward_item(P.sn, P.sn.lvl_nodes[i0 + it / G], Y, vs, G, it % G, xs);
+        sn_for_items<8>(P, c, lv, 0, [&](int s, int sgi, int sub) { sn_forward_item<8>(P.sn, s, Y, vs, G, sgi, xs + sub * (XS / 4)); });
+        sn_for_items<16>(P, c, lv, 1, [&](int s, int sgi, int sub) { sn_forward_item<16>(P.sn, s, Y, vs, G, sgi, xs + sub * (XS / 2)); });
+        sn_for_items<32>(P, c, lv, 2, [&](int s, int sgi, int) { sn_forward_item<32>(P.sn, s, Y, vs, G, sgi, xs); });
         __syncthreads();
     }
     const long long t1_ = clock64();
     for (int i = c.slot; i < P.nk; i += c.nslots) vs[i * G + sg] *= invD[GI(i)];
     __syncthreads();
     for (int lv = P.sn.nlevels - 1; lv >= 0; lv--) {
-        const int i0 = P.sn.lvl_ptr[lv], nit = (P.sn.lvl_ptr[lv + 1] - i0) * G;
-        for (int it = warp; it < nit; it += c.nwarps)
-            sn_backward_item(P.sn, P.sn.lvl_nodes[i0 + it / G], Y, vs, G, it % G, xs);
+        sn_for_items<8>(P, c, lv, 0, [&](int s, int sgi, int sub) { sn_backward_item<8>(P.sn, s, Y, vs, G, sgi, xs + sub * (XS / 4)); });
+        sn_for_items<16>(P, c, lv, 1, [&](int s, int sgi, int sub) { sn_backward_item<16>(P.sn, s, Y, vs, G, sgi, xs + sub * (XS / 2)); });
+        sn_for_items<32>(P, c, lv, 2, [&](int s, int sgi, int) { sn_backward_item<32>(P.sn, s, Y, vs, G, sgi, xs); });
         __syncthreads();
     }
     for (int i = c.slot; i < P.nk; i += c.nslots) v[GI(i)] = vs[i * G + sg];

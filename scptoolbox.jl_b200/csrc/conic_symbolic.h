@@ -89,6 +89,8 @@ struct ConeSymbolic {
     std::vector<int> sn_upd_dst;                     // lower-triangle pairs (x >= y) of the below rows -> panel offset
     std::vector<int> sn_upd_xy;                      // the pair itself, packed x | y << 16 (indices into the below rows)
     std::vector<int> sn_sign;                        // expected pivot sign of each column (+1 / -1)
+    std::vector<int> sn_cls_ptr;                     // [nlevels][4]: level nodes sorted by lane-group size 8 | 16 | 32 (conic_sn.cuh)
+    bool sn_fits = true;                             // every panel fits a warp's scratch
     long long sn_panel_size = 0;
     int sn_nlevels = 0;
     long long factor_ops = 0;
@@ -503,6 +505,24 @@ inline bool cone_symbolic_build(ConeSymbolic &S, int n, int p, int m, const int 
         {
             std::vector<int> nxt(S.sn_lvl_ptr.begin(), S.sn_lvl_ptr.end() - 1);
             for (int s = 0; s < ns; s++) S.sn_lvl_nodes[nxt[slev[s]]++] = s;
+        }
+        // inside a level: small panels first (lane groups of 8, then 16, then 32 lanes)
+        auto cls_of = [&](int s) { int R = S.sn_nrows[s], w = S.sn_width[s];
+                                   for (int gs = 8; gs <= 32; gs *= 2)
+                                       if (R <= gs && R * w <= 384 * gs / 32 && R + gs <= 96 * gs / 32) return gs;
+                                   return (R <= 64 && R * w <= 384) ? 32 : 0; };
+        S.sn_cls_ptr.assign(4 * (size_t)S.sn_nlevels, 0);
+        S.sn_fits = true;
+        for (int lv = 0; lv < S.sn_nlevels; lv++) {
+            int *b = &S.sn_lvl_nodes[S.sn_lvl_ptr[lv]], *e = &S.sn_lvl_nodes[S.sn_lvl_ptr[lv + 1]];
+            std::stable_sort(b, e, [&](int x, int y) { int cx = cls_of(x), cy = cls_of(y); return (cx ? cx : 64) < (cy ? cy : 64); });
+            int o = S.sn_lvl_ptr[lv];
+            S.sn_cls_ptr[4 * lv] = o;
+            for (int gs = 8, q = 1; gs <= 32; gs *= 2, q++) {
+                while (o < S.sn_lvl_ptr[lv + 1] && cls_of(S.sn_lvl_nodes[o]) == gs) o++;
+                S.sn_cls_ptr[4 * lv + q] = o;
+            }
+            if (o != S.sn_lvl_ptr[lv + 1]) S.sn_fits = false;   // a panel too large for the warp scratch
         }
     }
     // ---- balanced substitution programs ----
