@@ -100,9 +100,11 @@ typedef struct scpb_cone_s *scpb_cone;
 
 typedef struct {
     double feastol, abstol, reltol; /* <=0: ECOS defaults 1e-8                          */
-    double delta, delta_dyn;        /* <=0: static 1e-9 / dynamic 1e-7 regularisation    */
+    double delta, delta_dyn;        /* static regularisation of the KKT system: every seed starts from `delta`
+                                     * (<=0: 1e-12) and is escalated x1000, up to `delta_dyn` (<=0: 1e-6), whenever a
+                                     * factorisation loses its inertia to cancellation (last iterations only)  */
     int32_t maxit;                  /* <=0: 100 ("maxit" of solver_opts)                 */
-    int32_t nref;                   /* <0: 2 iterative-refinement steps                  */
+    int32_t nref;                   /* <0: at most 3 iterative-refinement steps          */
     int32_t verbose;                /* accepted, ignored ("verbose" of solver_opts)      */
     int32_t group;                  /* seeds per CTA (power of two <= 32); 0 = automatic */
     int32_t equil;                  /* Ruiz equilibration passes; <0: default 5, 0: off    */
@@ -204,19 +206,30 @@ int32_t scpb_debug_kkt_solve(int32_t n, int32_t p, int32_t m, const int32_t *A_r
                              const double *rhs, double *sol, int64_t *info);
 /* The same hook for the supernodal program (dense panels, one barrier per supernodal level) that the next kernel
  * generation executes; info[8] = {supernodes, supernodal levels, panel doubles per seed, update scatter entries,
- * max width, max panel rows, scalar levels, nnz(L)}. */
+ * max width, max panel rows, scalar levels, nnz(L)}.  The kernels of csrc/conic_sn.cuh execute this program. */
 int32_t scpb_debug_kkt_solve_sn(int32_t n, int32_t p, int32_t m, const int32_t *A_rowptr, const int32_t *A_colind,
                              const int32_t *G_rowptr, const int32_t *G_colind, int32_t l, int32_t nsoc,
                              const int32_t *soc_dims, const int32_t *perm, const double *Avals,
                              const double *Gvals, const double *wm, double delta, double delta_dyn,
                              const double *rhs, double *sol, int64_t *info);
-/* ... and through the per-panel warp routines of csrc/conic_sn.cuh compiled in lane-emulation mode (the code the
- * supernodal kernel path runs per (supernode, seed) item); SCPB_ERR_UNSUPPORTED if a panel exceeds the warp scratch. */
-int32_t scpb_debug_kkt_solve_sn_emu(int32_t n, int32_t p, int32_t m, const int32_t *A_rowptr, const int32_t *A_colind,
-                             const int32_t *G_rowptr, const int32_t *G_colind, int32_t l, int32_t nsoc,
-                             const int32_t *soc_dims, const int32_t *perm, const double *Avals,
-                             const double *Gvals, const double *wm, double delta, double delta_dyn,
-                             const double *rhs, double *sol, int64_t *info);
+/* The same single KKT solve executed ON THE DEVICE by the code path of the solver kernel (supernodal panels, or the
+ * scalar programs with SCPB_SUPERNODAL=0) for B seeds: Avals[B][nnzA], Gvals[B][nnzG], wm[B][|W^-2|] (LP rows one
+ * weight, SOC cones dense q x q blocks), rhs / sol [B][n+p] in natural node order; bad[B] (nullable) = 1 when the
+ * factorisation flagged lost inertia.  GPU tests compare it with scpb_debug_kkt_solve. */
+int32_t scpb_debug_kkt_solve_dev(scpb_cone cone, int32_t B, const double *Avals, const double *Gvals, const double *wm,
+                                 double delta, const double *rhs, double *sol, int32_t *bad);
+/* Stateful variant of the scalar interpreter for numerics studies on the CPU (scripts/emu_ipm.py): symbolic analysis
+ * once (scpb_debug_kkt_new), then any number of factorisations and solves.  scpb_debug_kkt_factor applies the kernel's
+ * dynamic regularisation (a pivot with sgn*d <= tau becomes sgn*rho) and returns the number of rejected pivots that
+ * were NOT small (|d| > bad_abs or non-finite: the inertia was lost to cancellation), or a negative error code;
+ * stats[3] = {regularised pivots, max |L|, min |D|}.  info[4] = {nnz(L), levels, factor ops, supernodal levels}. */
+int32_t scpb_debug_kkt_new(int32_t n, int32_t p, int32_t m, const int32_t *A_rowptr, const int32_t *A_colind,
+                           const int32_t *G_rowptr, const int32_t *G_colind, int32_t l, int32_t nsoc,
+                           const int32_t *soc_dims, const int32_t *perm, void **out, int64_t *info);
+int32_t scpb_debug_kkt_factor(void *kkt, const double *Avals, const double *Gvals, const double *wm, double delta,
+                              double tau, double rho, double bad_abs, double *stats);
+int32_t scpb_debug_kkt_resolve(void *kkt, const double *rhs, double *sol);
+int32_t scpb_debug_kkt_free(void *kkt);
 
 #ifdef __cplusplus
 }

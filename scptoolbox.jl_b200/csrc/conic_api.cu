@@ -67,15 +67,24 @@ static int cone_reserve(scpb_cone_s *c, int B, int G)
     const int ng = (B + G - 1) / G, Bpad = ng * G;
     c->D.R = std::max(1, std::min(c->lanes > 0 ? c->lanes : 8, 32 / G));
     if (c->capB >= Bpad && c->capG == G) { c->D.B = B; c->D.G = G; return SCPB_OK; }
-    for (double *p : c->bufs) cudaFree(p);
+    // release the old set and forget it BEFORE allocating: if an allocation below fails, the problem is left with
+    // capacity zero and null pointers (the next call re-reserves) instead of stale pointers to freed memory
+    for (double *p : c->bufs) if (p) cudaFree(p);
     c->bufs.clear();
     if (c->d_status) cudaFree(c->d_status);
     if (c->d_iters) cudaFree(c->d_iters);
     if (c->d_scal) cudaFree(c->d_scal);
+    c->d_status = nullptr; c->d_iters = nullptr; c->d_scal = nullptr;
+    c->capB = 0; c->capG = 0;
+    {
+        IpmData z{};
+        z.R = c->D.R; z.prof = c->D.prof;
+        c->D = z;
+    }
     const ConeSymbolic &S = c->S;
     auto al = [&](size_t E) -> double * {
         double *p = nullptr;
-        if (cudaMalloc((void **)&p, sizeof(double) * (E + 1) * Bpad) != cudaSuccess) return nullptr;
+        if (cudaMalloc((void **)&p, sizeof(double) * (E + 1) * Bpad) != cudaSuccess) p = nullptr;
         c->bufs.push_back(p);
         return p;
     };
@@ -91,12 +100,24 @@ static int cone_reserve(scpb_cone_s *c, int B, int G)
     D.dx = al(n); D.dy = al(p); D.dz = al(m); D.ds = al(m); D.dsa = al(m); D.dza = al(m); D.tm = al(m); D.gm = al(m);
     D.r1 = al(n); D.r2 = al(p); D.e1 = al(nm); D.e2 = al(p); D.rhs = al(nk);
     D.Y = al(std::max<size_t>((size_t)S.nnzL + nk, (size_t)S.sn_panel_size)); D.Ls = al(S.nnzL + 1); D.Lrow = al(S.nnzL + 1); D.invD = al(nk);
-    for (double *q : c->bufs)
-        if (!q) return set_err(h, SCPB_ERR_CUDA, "cone solver: device allocation failed (B=%d)", B);
-    if (cudaMalloc((void **)&c->d_status, sizeof(int) * Bpad) != cudaSuccess ||
-        cudaMalloc((void **)&c->d_iters, sizeof(int) * Bpad) != cudaSuccess ||
-        cudaMalloc((void **)&c->d_scal, sizeof(double) * 5 * Bpad) != cudaSuccess)
-        return set_err(h, SCPB_ERR_CUDA, "cone solver: device allocation failed");
+    bool ok = true;
+    for (double *q : c->bufs) ok = ok && q != nullptr;
+    ok = ok && cudaMalloc((void **)&c->d_status, sizeof(int) * Bpad) == cudaSuccess &&
+         cudaMalloc((void **)&c->d_iters, sizeof(int) * Bpad) == cudaSuccess &&
+         cudaMalloc((void **)&c->d_scal, sizeof(double) * 5 * Bpad) == cudaSuccess;
+    if (!ok) {
+        cudaGetLastError();
+        for (double *q : c->bufs) if (q) cudaFree(q);
+        c->bufs.clear();
+        if (c->d_status) cudaFree(c->d_status);
+        if (c->d_iters) cudaFree(c->d_iters);
+        if (c->d_scal) cudaFree(c->d_scal);
+        c->d_status = nullptr; c->d_iters = nullptr; c->d_scal = nullptr;
+        IpmData z{};
+        z.R = c->D.R; z.prof = c->D.prof;
+        c->D = z;
+        return set_err(h, SCPB_ERR_CUDA, "cone solver: device allocation failed (B=%d)", B);
+    }
     D.status = c->d_status; D.iters = c->d_iters;
     D.pobj = c->d_scal; D.dobj = c->d_scal + Bpad; D.res = c->d_scal + 2 * (size_t)Bpad;
     if (!c->d_prof && cudaMalloc((void **)&c->d_prof, sizeof(long long) * (12 + 3 * (size_t)c->S.nlevels)) != cudaSuccess) c->d_prof = nullptr;
@@ -107,8 +128,9 @@ static int cone_reserve(scpb_cone_s *c, int B, int G)
 }
 
 // run the solver on the data currently in the grouped buffers (device-resident entry, internal API)
-int scpb_internal_cone_run(scpb_cone_s *c, const IpmOpts &o)
+int scpb_internal_cone_run(scpb_cone_s *c, const IpmOpts &o, const int *skip)
 {
+    c->D.skip = skip;
     scpb_handle_s *h = c->h;
     const int ng = (c->D.B + c->D.G - 1) / c->D.G;
     // dynamic shared memory: level pointers (+ the substitution vector when nk*G doubles fit next to the
@@ -117,17 +139,11 @@ int scpb_internal_cone_run(scpb_cone_s *c, const IpmOpts &o)
     const size_t vbytes = sizeof(double) * (size_t)c->S.nk * c->D.G;
     c->D.vsmem = (smem + vbytes <= 200 * 1024 && !getenv("SCPB_NO_VSMEM")) ? 1 : 0;   // env: force the global-memory sweep (tests)
     if (c->D.vsmem) smem += vbytes;
-    // experimental supernodal path (csrc/conic_sn.cuh; CPU-checked, not yet run on a GPU): needs the shared-memory
-    // vector (its window doubles as the factorisation's panel scratch) and a per-warp sweep scratch behind it
-    c->D.sn = 0;
-    if (getenv("SCPB_SUPERNODAL") && c->sn_ok && c->D.vsmem) {
-        const size_t nw = (o.threads >= 1024 ? 1024 : 512) / 32;
-        const size_t xbytes = sizeof(double) * nw * (SN_MAXROWS + 32);
-        if (vbytes >= sizeof(double) * nw * SN_SCRATCH && smem + xbytes <= 205 * 1024) {
-            c->D.sn = 1;
-            c->D.o_snx = (int)(smem / sizeof(int));
-            smem += xbytes;
-        }
+    // supernodal factorisation / substitutions (csrc/conic_sn.cuh): every panel must fit a lane group and the
+    // substitution vector must live in shared memory; SCPB_SUPERNODAL=0 selects the scalar level-scheduled programs
+    {
+        const char *e = getenv("SCPB_SUPERNODAL");
+        c->D.sn = (c->sn_ok && c->D.vsmem && !(e && e[0] == '0')) ? 1 : 0;
     }
     c->D.lvl_prof = (c->d_prof && getenv("SCPB_LEVEL_PROFILE")) ? 1 : 0;   // diagnostic: per-level cycle counters of CTA 0
     if (o.threads >= 1024) {
@@ -148,14 +164,18 @@ IpmOpts scpb_internal_make_opts(const scpb_cone_opts *o)
     r.feastol = (o && o->feastol > 0) ? o->feastol : 1e-8;
     r.abstol = (o && o->abstol > 0) ? o->abstol : 1e-8;
     r.reltol = (o && o->reltol > 0) ? o->reltol : 1e-8;
-    r.delta = (o && o->delta > 0) ? o->delta : 1e-9;
-    r.delta_dyn = (o && o->delta_dyn > 0) ? o->delta_dyn : 1e-7;
+    r.delta = (o && o->delta > 0) ? o->delta : 1e-12;
+    r.delta_max = (o && o->delta_dyn > 0) ? o->delta_dyn : 1e-6;
+    if (r.delta_max < r.delta) r.delta_max = r.delta;
+    r.delta_esc = 1e3;
+    r.rho_min = 1e-9;
+    r.bad_abs = 1e-6;
     r.maxit = (o && o->maxit > 0) ? o->maxit : 100;
-    r.nref = (o && o->nref >= 0) ? o->nref : 2;
+    r.nref = (o && o->nref >= 0) ? o->nref : 3;
     r.equil = (o && o->equil >= 0) ? o->equil : 5;
     r.threads = (o && o->threads > 0) ? o->threads : 1024;
     r.nref_aff = 0;
-    r.reftol = 1e-12;
+    r.reftol = 1e-13;
     return r;
 }
 
@@ -206,7 +226,15 @@ int32_t scpb_cone_setup(scpb_handle h, int32_t n, int32_t p, int32_t m, const in
     P.sn.upd_dst = upload_ints(c, S.sn_upd_dst); P.sn.nlevels = S.sn_nlevels;
     P.sn_pos = upload_ints(c, S.sn_pos_of_target);
     P.sn.cls_ptr = upload_ints(c, S.sn_cls_ptr);
-    static_assert(SN_SCRATCH == 384 && SN_MAXROWS == 64, "conic_symbolic.h (cls_of) assumes these scratch sizes");
+    {
+        std::vector<int> desc(8 * S.sn_first.size() + 8, 0);   // in level order: item i of lvl_nodes
+        for (size_t i = 0; i < S.sn_lvl_nodes.size(); i++) {
+            const int q = S.sn_lvl_nodes[i];
+            desc[8 * i] = S.sn_first[q]; desc[8 * i + 1] = S.sn_width[q]; desc[8 * i + 2] = S.sn_nrows[q];
+            desc[8 * i + 3] = S.sn_panel_off[q]; desc[8 * i + 4] = S.sn_rows_ptr[q]; desc[8 * i + 5] = S.sn_upd_ptr[q];
+        }
+        P.sn.desc = (const int4 *)upload_ints(c, desc);
+    }
     c->sn_ok = S.sn_fits;
     P.fa_lvl = upload_ints(c, S.fa_lvl); P.fa_R = upload_ints(c, S.fa_R); P.fb_lvl = upload_ints(c, S.fb_lvl);
     P.fwp_item = (const int4 *)upload_ints(c, S.fwp_item); P.bwp_item = (const int4 *)upload_ints(c, S.bwp_item);
@@ -244,6 +272,62 @@ int32_t scpb_debug_level_profile(scpb_cone c, int64_t *out, int32_t cap)
     if (cudaMemcpy(hp.data(), c->d_prof + 12, sizeof(long long) * hp.size(), cudaMemcpyDeviceToHost) != cudaSuccess)
         return SCPB_ERR_CUDA;
     for (size_t i = 0; i < hp.size(); i++) out[i] = hp[i];
+    return SCPB_OK;
+}
+
+/* test hook: one assemble + factor + solve of the reduced KKT system ON THE DEVICE (the code path of k_ipm_solve,
+ * supernodal or scalar by SCPB_SUPERNODAL) for B seeds; rhs / sol in natural node order [B][n+p]; wm[B][nwm] is W^-2
+ * (LP rows: one weight; SOC: dense q x q blocks); bad[B] = 1 when the factorisation flagged lost inertia. */
+int32_t scpb_debug_kkt_solve_dev(scpb_cone c, int32_t B, const double *Avals, const double *Gvals, const double *wm,
+                                 double delta, const double *rhs, double *sol, int32_t *bad)
+{
+    if (!c || B <= 0 || !wm || !rhs || !sol) return SCPB_ERR_ARG;
+    scpb_handle_s *h = c->h;
+    SCPB_CUDA(h, cudaSetDevice(h->device));
+    const int G = scpb_internal_pick_group(B, 0);
+    int rc = cone_reserve(c, B, G);
+    if (rc) return rc;
+    const ConeSymbolic &S = c->S;
+    const int Bpad = c->capB, nk = S.nk;
+    const size_t maxE = std::max<size_t>({S.A_ci.size(), S.G_ci.size(), (size_t)S.nwm, (size_t)nk, 1});
+    if (c->stage_cap < maxE * B) {
+        if (c->stage) cudaFree(c->stage);
+        c->stage = nullptr; c->stage_cap = 0;
+        SCPB_CUDA(h, cudaMalloc((void **)&c->stage, sizeof(double) * maxE * B));
+        c->stage_cap = maxE * B;
+    }
+    cudaStream_t st = h->stream;
+    auto put = [&](const double *src, double *dst, size_t E) -> int {
+        if (E == 0) return SCPB_OK;
+        if (!src) { SCPB_CUDA(h, cudaMemsetAsync(dst, 0, sizeof(double) * E * Bpad, st)); return SCPB_OK; }
+        SCPB_CUDA(h, cudaMemcpyAsync(c->stage, src, sizeof(double) * E * B, cudaMemcpyHostToDevice, st));
+        const long long tot = (long long)E * Bpad;
+        k_to_grouped<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(c->stage, dst, (int)E, B, G, Bpad);
+        SCPB_CUDA(h, cudaStreamSynchronize(st));   // the staging buffer is reused by the next array
+        return SCPB_OK;
+    };
+    std::vector<double> rp((size_t)B * nk);
+    for (int b = 0; b < B; b++)
+        for (int i = 0; i < nk; i++) rp[(size_t)b * nk + S.iperm[i]] = rhs[(size_t)b * nk + i];
+    if ((rc = put(Avals, c->D.Av, S.A_ci.size())) || (rc = put(Gvals, c->D.Gv, S.G_ci.size())) ||
+        (rc = put(wm, c->D.wm, (size_t)S.nwm)) || (rc = put(rp.data(), c->D.rhs, (size_t)nk)))
+        return rc;
+    scpb_cone_opts oo{};
+    oo.delta = delta;
+    IpmOpts o = scpb_internal_make_opts(&oo);
+    c->D.debug_kkt = 1;
+    rc = scpb_internal_cone_run(c, o, nullptr);
+    c->D.debug_kkt = 0;
+    if (rc) return rc;
+    k_from_grouped<<<(unsigned)(((long long)nk * B + 255) / 256), 256, 0, st>>>(c->D.rhs, c->stage, nk, B, G);
+    SCPB_CUDA(h, cudaMemcpyAsync(rp.data(), c->stage, sizeof(double) * nk * B, cudaMemcpyDeviceToHost, st));
+    std::vector<int> hb(B, 0);
+    SCPB_CUDA(h, cudaMemcpyAsync(hb.data(), c->D.status, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    SCPB_CUDA(h, cudaStreamSynchronize(st));
+    for (int b = 0; b < B; b++) {
+        for (int i = 0; i < nk; i++) sol[(size_t)b * nk + i] = rp[(size_t)b * nk + S.iperm[i]];
+        if (bad) bad[b] = hb[b];
+    }
     return SCPB_OK;
 }
 
@@ -302,7 +386,7 @@ int32_t scpb_cone_solve(scpb_cone c, int32_t B, const double *Avals, const doubl
         return rc;
     IpmOpts o = scpb_internal_make_opts(opts);
     SCPB_CUDA(h, cudaEventRecord(h->ev0, st));
-    rc = scpb_internal_cone_run(c, o);
+    rc = scpb_internal_cone_run(c, o, nullptr);
     if (rc) return rc;
     SCPB_CUDA(h, cudaEventRecord(h->ev1, st));
     auto get = [&](double *dst, const double *src, size_t E) -> int {

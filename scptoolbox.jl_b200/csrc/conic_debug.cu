@@ -4,8 +4,6 @@
 // It is not reachable from any product entry point (scpb_cone_solve always launches k_ipm_solve).
 #include "../../include/scpb.h"
 #include "conic_symbolic.h"
-#define SN_EMULATE
-#include "conic_sn.cuh"
 
 extern "C" int32_t scpb_debug_kkt_solve(int32_t n, int32_t p, int32_t m, const int32_t *A_rp, const int32_t *A_ci,
                                         const int32_t *G_rp, const int32_t *G_ci, int32_t l, int32_t nsoc,
@@ -153,57 +151,101 @@ extern "C" int32_t scpb_debug_kkt_solve_sn(int32_t n, int32_t p, int32_t m, cons
     return SCPB_OK;
 }
 
-// The same system once more, this time through the WARP routines of conic_sn.cuh compiled in lane-emulation mode
-// (SN_EMULATE): the code that k_ipm_solve runs per (supernode, seed) item, executed here one item at a time.
-extern "C" int32_t scpb_debug_kkt_solve_sn_emu(int32_t n, int32_t p, int32_t m, const int32_t *A_rp, const int32_t *A_ci,
-                                               const int32_t *G_rp, const int32_t *G_ci, int32_t l, int32_t nsoc,
-                                               const int32_t *soc_dims, const int32_t *perm, const double *Av,
-                                               const double *Gv, const double *wm, double delta, double delta_dyn,
-                                               const double *rhs, double *sol, int64_t *info)
-{
+// ---- stateful variant of the scalar interpreter (numerics studies on the CPU: symbolic analysis once, then any number
+// of factor / solve calls).  Dynamic regularisation as in the kernel: a pivot with sgn*d <= tau is replaced by sgn*rho;
+// a replaced pivot that is NOT small (|d| > bad_abs, or non-finite) means the inertia was lost to cancellation and is
+// counted in the return value of the factor call (the kernel escalates the static regularisation on that signal).
+struct scpb_debug_kkt_s {
     ConeSymbolic S;
+    std::vector<double> Y, Ls, Lrow, invD, v;
+};
+
+extern "C" int32_t scpb_debug_kkt_new(int32_t n, int32_t p, int32_t m, const int32_t *A_rp, const int32_t *A_ci,
+                                      const int32_t *G_rp, const int32_t *G_ci, int32_t l, int32_t nsoc,
+                                      const int32_t *soc_dims, const int32_t *perm, void **out, int64_t *info)
+{
+    if (!out) return SCPB_ERR_ARG;
+    scpb_debug_kkt_s *k = new scpb_debug_kkt_s();
     static const int zero = 0;
-    if (!cone_symbolic_build(S, n, p, m, A_rp, A_ci ? A_ci : &zero, G_rp, G_ci ? G_ci : &zero, l, nsoc, soc_dims, perm))
+    if (!cone_symbolic_build(k->S, n, p, m, A_rp, A_ci ? A_ci : &zero, G_rp, G_ci ? G_ci : &zero, l, nsoc, soc_dims, perm)) {
+        delete k;
         return SCPB_ERR_ARG;
-    const int nk = S.nk, ntgt = S.nnzL + nk, ns = (int)S.sn_first.size();
-    static_assert(SN_SCRATCH == 384 && SN_MAXROWS == 64, "conic_symbolic.h (cls_of) assumes these scratch sizes");
-    if (!S.sn_fits) return SCPB_ERR_UNSUPPORTED;
-    SnProgram Q{};
-    Q.first = S.sn_first.data(); Q.width = S.sn_width.data(); Q.nrows = S.sn_nrows.data();
-    Q.rows_ptr = S.sn_rows_ptr.data(); Q.rows = S.sn_rows.data(); Q.lvl_ptr = S.sn_lvl_ptr.data();
-    Q.lvl_nodes = S.sn_lvl_nodes.data(); Q.upd_xy = S.sn_upd_xy.data(); Q.sign = S.sn_sign.data();
-    Q.panel_off = S.sn_panel_off.data(); Q.upd_ptr = S.sn_upd_ptr.data(); Q.upd_dst = S.sn_upd_dst.data();
-    Q.nlevels = S.sn_nlevels; Q.cls_ptr = S.sn_cls_ptr.data();
-    std::vector<double> P((size_t)S.sn_panel_size, 0.0), invD(nk), v(nk), scr(SN_SCRATCH), xs(SN_MAXROWS + 32);
-    // per level the three lane-group classes, exactly as the kernel walks them (each group with its share of the scratch)
-    auto each = [&](int lv, auto &&f8, auto &&f16, auto &&f32) {
-        const int *cp_ = &S.sn_cls_ptr[4 * (size_t)lv];
-        for (int w_ = cp_[0]; w_ < cp_[1]; w_++) f8(S.sn_lvl_nodes[w_]);
-        for (int w_ = cp_[1]; w_ < cp_[2]; w_++) f16(S.sn_lvl_nodes[w_]);
-        for (int w_ = cp_[2]; w_ < cp_[3]; w_++) f32(S.sn_lvl_nodes[w_]);
-    };
+    }
+    const ConeSymbolic &S = k->S;
+    k->Y.resize((size_t)S.nnzL + S.nk); k->Ls.resize((size_t)S.nnzL + 1); k->Lrow.resize((size_t)S.nnzL + 1);
+    k->invD.resize(S.nk); k->v.resize(S.nk);
+    if (info) { info[0] = S.nnzL; info[1] = S.nlevels; info[2] = S.factor_ops; info[3] = S.sn_nlevels; }
+    *out = k;
+    return SCPB_OK;
+}
+
+extern "C" int32_t scpb_debug_kkt_free(void *h)
+{
+    delete (scpb_debug_kkt_s *)h;
+    return SCPB_OK;
+}
+
+// returns the number of "bad" (large wrong-sign or non-finite) pivots, or a negative error code
+extern "C" int32_t scpb_debug_kkt_factor(void *h, const double *Av, const double *Gv, const double *wm, double delta,
+                                         double tau, double rho, double bad_abs, double *stats)
+{
+    scpb_debug_kkt_s *k = (scpb_debug_kkt_s *)h;
+    if (!k) return -1;
+    const ConeSymbolic &S = k->S;
+    const int nk = S.nk, ntgt = S.nnzL + nk;
+    std::vector<double> &Y = k->Y, &Ls = k->Ls, &invD = k->invD;
     for (int t = 0; t < ntgt; t++) {
         double acc = delta * S.as_sign[t];
         if (S.as_src[t] >= 0) acc += Av[S.as_src[t]];
-        for (int k = S.as_ptr[t]; k < S.as_ptr[t + 1]; k++) acc += Gv[S.as_a[k]] * Gv[S.as_b[k]] * wm[S.as_c[k]];
-        P[(size_t)S.sn_pos_of_target[t]] = acc;
+        for (int q = S.as_ptr[t]; q < S.as_ptr[t + 1]; q++) acc += Gv[S.as_a[q]] * Gv[S.as_b[q]] * wm[S.as_c[q]];
+        Y[t] = acc;
     }
-    for (int lv = 0; lv < S.sn_nlevels; lv++)
-        each(lv, [&](int s) { sn_factor_item<8>(Q, s, P.data(), invD.data(), 1, 0, delta_dyn, scr.data() + 3 * (SN_SCRATCH / 4)); },
-             [&](int s) { sn_factor_item<16>(Q, s, P.data(), invD.data(), 1, 0, delta_dyn, scr.data() + SN_SCRATCH / 2); },
-             [&](int s) { sn_factor_item<32>(Q, s, P.data(), invD.data(), 1, 0, delta_dyn, scr.data()); });
+    int nbad = 0, nreg = 0;
+    double lmax = 0.0, dmin = 1e300;
+    for (int lv = 0; lv < S.nlevels; lv++) {
+        for (int w = S.fa_lvl[lv]; w < S.fa_lvl[lv + 1]; w++) {
+            const int *it = &S.fa_item[4 * (size_t)w];
+            double part = 0.0;
+            for (int q = it[1]; q < it[2]; q++) part += Y[S.ft_op[2 * (size_t)q]] * Ls[S.Lr_pos[S.ft_op[2 * (size_t)q + 1]]];
+            Y[it[0]] -= part;
+        }
+        for (int w = S.fb_lvl[lv]; w < S.fb_lvl[lv + 1]; w++) {
+            const int *it = &S.fb_item[4 * (size_t)w];
+            const double sgn = (it[3] & 1) ? 1.0 : -1.0;
+            double d = Y[S.nnzL + it[1]];
+            if (!(sgn * d > tau)) {
+                if (it[3] & 2) { nreg++; if (!(std::abs(d) <= bad_abs)) nbad++; }
+                d = sgn * rho;
+            }
+            if (it[3] & 2) { invD[it[1]] = 1.0 / d; dmin = std::min(dmin, std::abs(d)); }
+            else { Ls[it[0]] = Y[it[0]] * (1.0 / d); lmax = std::max(lmax, std::abs(Ls[it[0]])); }
+        }
+    }
+    for (int q = 0; q < S.nnzL; q++) k->Lrow[q] = Ls[S.Lr_pos[q]];
+    if (!(lmax < 1e300)) nbad++;
+    if (stats) { stats[0] = nreg; stats[1] = lmax; stats[2] = dmin; }
+    return nbad;
+}
+
+extern "C" int32_t scpb_debug_kkt_resolve(void *h, const double *rhs, double *sol)
+{
+    scpb_debug_kkt_s *k = (scpb_debug_kkt_s *)h;
+    if (!k) return SCPB_ERR_ARG;
+    const ConeSymbolic &S = k->S;
+    const int nk = S.nk;
+    std::vector<double> &v = k->v;
     for (int i = 0; i < nk; i++) v[S.iperm[i]] = rhs[i];
-    const int XS = SN_MAXROWS + 32;
-    for (int lv = 0; lv < S.sn_nlevels; lv++)
-        each(lv, [&](int s) { sn_forward_item<8>(Q, s, P.data(), v.data(), 1, 0, xs.data() + 3 * (XS / 4)); },
-             [&](int s) { sn_forward_item<16>(Q, s, P.data(), v.data(), 1, 0, xs.data() + XS / 2); },
-             [&](int s) { sn_forward_item<32>(Q, s, P.data(), v.data(), 1, 0, xs.data()); });
-    for (int i = 0; i < nk; i++) v[i] *= invD[i];
-    for (int lv = S.sn_nlevels - 1; lv >= 0; lv--)
-        each(lv, [&](int s) { sn_backward_item<8>(Q, s, P.data(), v.data(), 1, 0, xs.data() + 3 * (XS / 4)); },
-             [&](int s) { sn_backward_item<16>(Q, s, P.data(), v.data(), 1, 0, xs.data() + XS / 2); },
-             [&](int s) { sn_backward_item<32>(Q, s, P.data(), v.data(), 1, 0, xs.data()); });
+    for (int i = 0; i < nk; i++) {     // forward, rows in elimination order
+        double part = 0.0;
+        for (int q = S.Lr_rp[i]; q < S.Lr_rp[i + 1]; q++) part += k->Lrow[q] * v[S.Lr_col[q]];
+        v[i] -= part;
+    }
+    for (int i = 0; i < nk; i++) v[i] *= k->invD[i];
+    for (int j = nk - 1; j >= 0; j--) {
+        double part = 0.0;
+        for (int q = S.L_cp[j]; q < S.L_cp[j + 1]; q++) part += k->Ls[q] * v[S.L_ri[q]];
+        v[j] -= part;
+    }
     for (int i = 0; i < nk; i++) sol[i] = v[S.iperm[i]];
-    if (info) { info[0] = ns; info[1] = S.sn_nlevels; info[2] = S.sn_panel_size; info[3] = (int64_t)S.sn_upd_dst.size(); }
     return SCPB_OK;
 }

@@ -40,8 +40,11 @@ struct IpmProgram {  // device copies of ConeSymbolic index arrays
 
 struct IpmOpts {
     double feastol, abstol, reltol;   // ECOS defaults 1e-8
-    double delta;                     // static regularisation
-    double delta_dyn;                 // dynamic regularisation threshold / value
+    double delta;                     // static regularisation each seed starts from (tiny: 1e-12)
+    double delta_max;                 // ... and the ceiling it may be escalated to when a factorisation loses its inertia
+    double delta_esc;                 // escalation factor
+    double rho_min;                   // a rejected pivot (sgn*d <= delta/2) is replaced by sgn*max(delta, rho_min)
+    double bad_abs;                   // a rejected pivot larger than this (or NaN) counts as lost inertia
     int maxit, nref, equil;   // equil: Ruiz iterations (0 = off)
     int threads;              // CTA size: 512 or 1024
     int nref_aff;             // refinement steps for the predictor (affine) direction
@@ -63,9 +66,10 @@ struct IpmData {  // group-blocked device arrays, all for B seeds
     // per-seed outputs
     double *pobj, *dobj, *res;   // res: [3][B] pres, dres, gap
     int *status, *iters;
+    const int *skip;   // nullable [B]: seeds marked non-zero are not solved (their outputs are left untouched)
+    int debug_kkt;     // test hook (scpb_debug_kkt_solve_dev): assemble + factor with the caller's wm, solve rhs in place, return
     int lvl_prof;      // 1: also record per-level cycles behind prof[12..]
-    int sn;            // 1: supernodal factorisation / sweeps (SCPB_SUPERNODAL=1; experimental, see conic_sn.cuh)
-    int o_snx;         // offset (ints) of the per-warp sweep scratch in the dynamic shared window
+    int sn;            // 1: supernodal factorisation / sweeps (conic_sn.cuh); 0: scalar level-scheduled programs
     long long *prof;   // [8] cycle counters of CTA 0: equilibrate, init, residuals, scaling+assemble, factor, solves, line search+update, total
 };
 
@@ -89,8 +93,13 @@ struct Ctx {
     int *flag;                          // shared scratch word for CTA-uniform decisions
     long long t_fw, t_bw, t_ldl_n;      // cycle counters (CTA-local copies, meaningful on thread 0)
     long long *lprof;                   // thread 0 of CTA 0: per-level cycles [factor | forward | backward][nlevels]
-    int sn, o_snx;                      // supernodal mode, offset of the per-warp sweep scratch
-    const double *Ypanels;              // supernodal mode: this group's panels (the Y array)
+    int sn;                             // supernodal mode
+    double *Ypanels;                    // supernodal mode: this group's panels (the Y array, one seed after the other)
+    size_t ysize;                       // doubles per seed of the Y array
+    const int *s_done;                  // shared: per-seed "finished" flags (finished seeds skip the per-seed panel work)
+    double *s_delta;                    // shared: per-seed static regularisation
+    int *s_bad;                         // shared: per-seed "inertia lost" flag raised by the factorisation
+    double rho_min, bad_abs;
     double *vs;                         // shared-memory substitution vector (nullptr: use global memory)
     double *Lrow;                       // row-ordered copy of the scaled factor (forward substitution)
     double reftol;                      // iterative refinement stops once |residual|_inf <= reftol*(1+|rhs|_inf)
@@ -148,20 +157,73 @@ __device__ __forceinline__ double lanes_sum(const Ctx &c, double a)
     return a;
 }
 
-// y = alpha * (M x) [+ y0]  row-wise CSR; M values Mv group-blocked
-__device__ __forceinline__ double row_dot(const int *rp, const int *ci, const double *Mv, const double *x, int r,
-                                          int G, int sg)
+// Sparse dot products of the residual / refinement SpMVs.  Rows are short (2-10 entries) and every entry costs two
+// dependent loads (index, then operand), so a row is consumed in chunks of four entries whose loads are all issued
+// before the first use (clamped indices instead of branches); the first chunk is straight-line code, which lets the
+// compiler overlap it with the neighbouring dot product of the same loop body.  Summation order = storage order.
+#define IPM_CHUNK4(K, N_, IDX0, IDX1, IDX2, IDX3)                                                 \
+    const int j0_ = (K), j1_ = (N_) > 1 ? (K) + 1 : (K), j2_ = (N_) > 2 ? (K) + 2 : (K), j3_ = (N_) > 3 ? (K) + 3 : (K);
+// (M x)_r, M in CSR with group-blocked values
+__device__ __forceinline__ double row_dot(const int *__restrict__ rp, const int *__restrict__ ci,
+                                          const double *__restrict__ Mv, const double *__restrict__ x, int r, int G, int sg)
 {
+    const int k0 = rp[r], k1 = rp[r + 1];
     double acc = 0.0;
-    for (int k = rp[r]; k < rp[r + 1]; k++) acc = fma(Mv[GI(k)], x[GI(ci[k])], acc);
+    {
+        const int n_ = k1 - k0;
+        IPM_CHUNK4(k0, n_, 0, 0, 0, 0)
+        const int c0 = ci[j0_], c1 = ci[j1_], c2 = ci[j2_], c3 = ci[j3_];
+        const double m0 = Mv[GI(j0_)], m1 = Mv[GI(j1_)], m2 = Mv[GI(j2_)], m3 = Mv[GI(j3_)];
+        const double x0 = x[GI(c0)], x1 = x[GI(c1)], x2 = x[GI(c2)], x3 = x[GI(c3)];
+        if (n_ > 0) acc = m0 * x0;
+        if (n_ > 1) acc = fma(m1, x1, acc);
+        if (n_ > 2) acc = fma(m2, x2, acc);
+        if (n_ > 3) acc = fma(m3, x3, acc);
+    }
+    for (int k = k0 + 4; k < k1; k += 4) {
+        const int n_ = k1 - k;
+        IPM_CHUNK4(k, n_, 0, 0, 0, 0)
+        const int c0 = ci[j0_], c1 = ci[j1_], c2 = ci[j2_], c3 = ci[j3_];
+        const double m0 = Mv[GI(j0_)], m1 = Mv[GI(j1_)], m2 = Mv[GI(j2_)], m3 = Mv[GI(j3_)];
+        const double x0 = x[GI(c0)], x1 = x[GI(c1)], x2 = x[GI(c2)], x3 = x[GI(c3)];
+        acc = fma(m0, x0, acc);
+        if (n_ > 1) acc = fma(m1, x1, acc);
+        if (n_ > 2) acc = fma(m2, x2, acc);
+        if (n_ > 3) acc = fma(m3, x3, acc);
+    }
     return acc;
 }
 // (M' y)_v via the transposed pattern with value map
-__device__ __forceinline__ double col_dot(const int *trp, const int *tri, const int *tvi, const double *Mv,
-                                          const double *y, int v, int G, int sg)
+__device__ __forceinline__ double col_dot(const int *__restrict__ trp, const int *__restrict__ tri,
+                                          const int *__restrict__ tvi, const double *__restrict__ Mv,
+                                          const double *__restrict__ y, int v, int G, int sg)
 {
+    const int k0 = trp[v], k1 = trp[v + 1];
     double acc = 0.0;
-    for (int k = trp[v]; k < trp[v + 1]; k++) acc = fma(Mv[GI(tvi[k])], y[GI(tri[k])], acc);
+    {
+        const int n_ = k1 - k0;
+        IPM_CHUNK4(k0, n_, 0, 0, 0, 0)
+        const int r0 = tri[j0_], r1 = tri[j1_], r2 = tri[j2_], r3 = tri[j3_];
+        const int v0 = tvi[j0_], v1 = tvi[j1_], v2 = tvi[j2_], v3 = tvi[j3_];
+        const double m0 = Mv[GI(v0)], m1 = Mv[GI(v1)], m2 = Mv[GI(v2)], m3 = Mv[GI(v3)];
+        const double y0 = y[GI(r0)], y1 = y[GI(r1)], y2 = y[GI(r2)], y3 = y[GI(r3)];
+        if (n_ > 0) acc = m0 * y0;
+        if (n_ > 1) acc = fma(m1, y1, acc);
+        if (n_ > 2) acc = fma(m2, y2, acc);
+        if (n_ > 3) acc = fma(m3, y3, acc);
+    }
+    for (int k = k0 + 4; k < k1; k += 4) {
+        const int n_ = k1 - k;
+        IPM_CHUNK4(k, n_, 0, 0, 0, 0)
+        const int r0 = tri[j0_], r1 = tri[j1_], r2 = tri[j2_], r3 = tri[j3_];
+        const int v0 = tvi[j0_], v1 = tvi[j1_], v2 = tvi[j2_], v3 = tvi[j3_];
+        const double m0 = Mv[GI(v0)], m1 = Mv[GI(v1)], m2 = Mv[GI(v2)], m3 = Mv[GI(v3)];
+        const double y0 = y[GI(r0)], y1 = y[GI(r1)], y2 = y[GI(r2)], y3 = y[GI(r3)];
+        acc = fma(m0, y0, acc);
+        if (n_ > 1) acc = fma(m1, y1, acc);
+        if (n_ > 2) acc = fma(m2, y2, acc);
+        if (n_ > 3) acc = fma(m3, y3, acc);
+    }
     return acc;
 }
 
@@ -204,13 +266,24 @@ __device__ void kkt_assemble(const IpmProgram &P, const Ctx &c, const IpmData &D
 {
     const int G = c.G, sg = c.sg;
     const int ntgt = P.nnzL + P.nk;
+    (void)delta;
+    const double dl = c.s_delta[sg];
     for (int t = c.slot; t < ntgt; t += c.nslots) {
-        double acc = delta * (double)P.as_sign[t];
+        double acc = dl * (double)P.as_sign[t];
         const int src = P.as_src[t];
+        const int k0 = P.as_ptr[t], k1 = P.as_ptr[t + 1];
         if (src >= 0) acc += Av[GI(src)];
-        for (int k = P.as_ptr[t]; k < P.as_ptr[t + 1]; k++)
-            acc = fma(Gv[GI(P.as_a[k])] * Gv[GI(P.as_b[k])], wmx[GI(P.as_c[k])], acc);
-        Y[GI(D.sn ? P.sn_pos[t] : t)] = acc;   // supernodal mode: straight into the dense panels
+        for (int k = k0; k < k1; k += 2) {   // two triples in flight
+            const bool two = k + 1 < k1;
+            const int a0 = P.as_a[k], b0 = P.as_b[k], c0 = P.as_c[k];
+            const int a1 = two ? P.as_a[k + 1] : a0, b1 = two ? P.as_b[k + 1] : b0, c1 = two ? P.as_c[k + 1] : c0;
+            const double g0 = Gv[GI(a0)], h0 = Gv[GI(b0)], w0 = wmx[GI(c0)];
+            const double g1 = Gv[GI(a1)], h1 = Gv[GI(b1)], w1 = wmx[GI(c1)];
+            acc = fma(g0 * h0, w0, acc);
+            if (two) acc = fma(g1 * h1, w1, acc);
+        }
+        if (D.sn) Y[(size_t)sg * c.ysize + P.sn_pos[t]] = acc;   // supernodal mode: straight into this seed's dense panels
+        else Y[GI(t)] = acc;
     }
     __syncthreads();
 }
@@ -228,7 +301,9 @@ struct FactorArgs {
     const int4 *fa_item, *fb_item;
     const int2 *ft_op;
     double *Y, *Ls, *Lrow, *invD;   // group-blocked, already offset to this CTA's group
-    double delta_dyn;
+    const double *s_delta;          // shared: per-seed static regularisation (pivot threshold delta/2)
+    int *s_bad;                     // shared: per-seed "inertia lost" flags
+    double rho_min, bad_abs;
     int o_fal, o_faR, o_fbl;        // offsets (ints) into the dynamic shared memory window
     int nl, nnzLd, G, sg, slot, nslots;
     long long *lprof;
@@ -310,7 +385,11 @@ __device__ __noinline__ void kkt_factor_levels(const FactorArgs a)
             double d = isd ? e : __ldcg(&a.Y[(size_t)(a.nnzLd + sc.y) * G + sg]);
             const int4 cur = sc;
             if (w + nslots < b1) sc = a.fb_item[w + nslots];
-            if (!(sgn * d > a.delta_dyn)) d = sgn * a.delta_dyn;   // dynamic regularisation keeps the expected inertia
+            const double dl_ = a.s_delta[sg];
+            if (!(sgn * d > 0.5 * dl_)) {   // dynamic regularisation keeps the expected inertia
+                if (isd && !(fabs(d) <= a.bad_abs)) a.s_bad[sg] = 1;   // not a small pivot: cancellation destroyed it
+                d = sgn * fmax(dl_, a.rho_min);
+            }
             const double inv = 1.0 / d;
             if (isd) a.invD[(size_t)cur.y * G + sg] = inv;
             else {
@@ -331,57 +410,80 @@ __device__ __noinline__ void kkt_factor_levels(const FactorArgs a)
 #undef IPM_FA_OPS
 }
 
-// supernodal numeric factorisation: one lane group (8, 16 or 32 lanes, by panel size) per (supernode, seed) item, one
-// barrier per supernodal level; the scratch (panel copies) borrows the shared-memory window of the substitution
-// vector, which is idle here
+// supernodal numeric factorisation: one thread (small leaves) or one lane group (8, 16 or 32 lanes, by panel height)
+// per (supernode, seed) item, one barrier per supernodal level; panels live in registers (conic_sn.cuh).  The
+// descriptor of a unit's next item is requested before the current item is worked on.
 template <int GS, class F>
 __device__ __forceinline__ void sn_for_items(const IpmProgram &P, const Ctx &c, int lv, int cls, F &&f)
 {
-    constexpr int GPW = 32 / GS;                       // lane groups per warp
-    const int i0 = P.sn.cls_ptr[4 * lv + cls], nit = (P.sn.cls_ptr[4 * lv + cls + 1] - i0) * c.G;
-    const int unit = (c.tid >> 5) * GPW + ((c.tid & 31) / GS), nunits = c.nwarps * GPW;
-    for (int it = unit; it < nit; it += nunits) f(P.sn.lvl_nodes[i0 + it / c.G], it % c.G, (c.tid & 31) / GS);
+    const int i0 = P.sn.cls_ptr[5 * lv + cls], nit = (P.sn.cls_ptr[5 * lv + cls + 1] - i0) * c.G;
+    const int gsh = 31 - __clz(c.G);
+    int unit, nunits;
+    if (GS == 1) { unit = c.tid; nunits = c.nwarps * 32; }
+    else { constexpr int GPW = 32 / (GS == 1 ? 32 : GS); unit = (c.tid >> 5) * GPW + ((c.tid & 31) / (GS == 1 ? 32 : GS)); nunits = c.nwarps * GPW; }
+    int it = unit;
+    int4 d0 = make_int4(0, 0, 0, 0), d1 = d0;
+    if (it < nit) { const int q = 2 * (i0 + (it >> gsh)); d0 = P.sn.desc[q]; d1 = P.sn.desc[q + 1]; }
+    while (it < nit) {
+        const int sgi = it & (c.G - 1);
+        const int4 c0 = d0, c1 = d1;
+        const int nx = it + nunits;
+        if (nx < nit) { const int q = 2 * (i0 + (nx >> gsh)); d0 = P.sn.desc[q]; d1 = P.sn.desc[q + 1]; }
+        if (!c.s_done[sgi]) f(c0, c1, sgi);    // lane groups: uniform within the group
+        it = nx;
+    }
 }
 
-__device__ void kkt_factor_sn(const IpmProgram &P, Ctx &c, double *Y, double *invD, double delta_dyn)
+__device__ __noinline__ void kkt_factor_sn(const IpmProgram &P, const Ctx &c, double *Y, double *invD)
 {
     const int G = c.G;
-    double *scr = c.vs + (size_t)(c.tid >> 5) * SN_SCRATCH;
+    long long tl_ = c.lprof ? clock64() : 0;
     for (int lv = 0; lv < P.sn.nlevels; lv++) {
-        sn_for_items<8>(P, c, lv, 0, [&](int s, int sgi, int sub) {
-            sn_factor_item<8>(P.sn, s, Y, invD, G, sgi, delta_dyn, scr + sub * (SN_SCRATCH / 4)); });
-        sn_for_items<16>(P, c, lv, 1, [&](int s, int sgi, int sub) {
-            sn_factor_item<16>(P.sn, s, Y, invD, G, sgi, delta_dyn, scr + sub * (SN_SCRATCH / 2)); });
-        sn_for_items<32>(P, c, lv, 2, [&](int s, int sgi, int) {
-            sn_factor_item<32>(P.sn, s, Y, invD, G, sgi, delta_dyn, scr); });
+        sn_for_items<1>(P, c, lv, 0, [&](const int4 d0, const int4 d1, int sgi) {
+            const double dl = c.s_delta[sgi];
+            sn1_factor_panel(P.sn, d0, d1, Y + (size_t)sgi * c.ysize, invD, G, sgi, 0.5 * dl, fmax(dl, c.rho_min), c.bad_abs, &c.s_bad[sgi]); });
+        sn_for_items<8>(P, c, lv, 1, [&](const int4 d0, const int4 d1, int sgi) {
+            const double dl = c.s_delta[sgi];
+            sn_factor_panel<8>(P.sn, d0, d1, Y + (size_t)sgi * c.ysize, invD, G, sgi, 0.5 * dl, fmax(dl, c.rho_min), c.bad_abs, &c.s_bad[sgi]); });
+        sn_for_items<16>(P, c, lv, 2, [&](const int4 d0, const int4 d1, int sgi) {
+            const double dl = c.s_delta[sgi];
+            sn_factor_panel<16>(P.sn, d0, d1, Y + (size_t)sgi * c.ysize, invD, G, sgi, 0.5 * dl, fmax(dl, c.rho_min), c.bad_abs, &c.s_bad[sgi]); });
+        sn_for_items<32>(P, c, lv, 3, [&](const int4 d0, const int4 d1, int sgi) {
+            const double dl = c.s_delta[sgi];
+            sn_factor_panel<32>(P.sn, d0, d1, Y + (size_t)sgi * c.ysize, invD, G, sgi, 0.5 * dl, fmax(dl, c.rho_min), c.bad_abs, &c.s_bad[sgi]); });
         __syncthreads();
+        if (c.lprof) { const long long tn = clock64(); c.lprof[lv] += tn - tl_; tl_ = tn; }
     }
 }
 
 // supernodal substitutions on the shared-memory vector
-__device__ void kkt_ldl_solve_sn(const IpmProgram &P, Ctx &c, const double *Y, const double *invD, double *v)
+__device__ __noinline__ void kkt_ldl_solve_sn(const IpmProgram &P, Ctx &c, const double *Y, const double *invD, double *v)
 {
     const int G = c.G, sg = c.sg;
-    constexpr int XS = SN_MAXROWS + 32;
     double *vs = c.vs;
-    double *xs = (double *)(ipm_smem + c.o_snx) + (size_t)(c.tid >> 5) * XS;
     const long long t0_ = clock64();
     for (int i = c.slot; i < P.nk; i += c.nslots) vs[i * G + sg] = v[GI(i)];
     __syncthreads();
+    long long tlp_ = c.lprof ? clock64() : 0;
     for (int lv = 0; lv < P.sn.nlevels; lv++) {
-        sn_for_items<8>(P, c, lv, 0, [&](int s, int sgi, int sub) { sn_forward_item<8>(P.sn, s, Y, vs, G, sgi, xs + sub * (XS / 4)); });
-        sn_for_items<16>(P, c, lv, 1, [&](int s, int sgi, int sub) { sn_forward_item<16>(P.sn, s, Y, vs, G, sgi, xs + sub * (XS / 2)); });
-        sn_for_items<32>(P, c, lv, 2, [&](int s, int sgi, int) { sn_forward_item<32>(P.sn, s, Y, vs, G, sgi, xs); });
+        sn_for_items<1>(P, c, lv, 0, [&](const int4 d0, const int4 d1, int sgi) { sn1_forward_panel(P.sn, d0, d1, Y + (size_t)sgi * c.ysize, vs, G, sgi); });
+        sn_for_items<8>(P, c, lv, 1, [&](const int4 d0, const int4 d1, int sgi) { sn_forward_panel<8>(P.sn, d0, d1, Y + (size_t)sgi * c.ysize, vs, G, sgi); });
+        sn_for_items<16>(P, c, lv, 2, [&](const int4 d0, const int4 d1, int sgi) { sn_forward_panel<16>(P.sn, d0, d1, Y + (size_t)sgi * c.ysize, vs, G, sgi); });
+        sn_for_items<32>(P, c, lv, 3, [&](const int4 d0, const int4 d1, int sgi) { sn_forward_panel<32>(P.sn, d0, d1, Y + (size_t)sgi * c.ysize, vs, G, sgi); });
         __syncthreads();
+        if (c.lprof) { const long long tn = clock64(); c.lprof[P.nlevels + lv] += tn - tlp_; tlp_ = tn; }
     }
     const long long t1_ = clock64();
     for (int i = c.slot; i < P.nk; i += c.nslots) vs[i * G + sg] *= invD[GI(i)];
     __syncthreads();
+    tlp_ = c.lprof ? clock64() : 0;
     for (int lv = P.sn.nlevels - 1; lv >= 0; lv--) {
-        sn_for_items<8>(P, c, lv, 0, [&](int s, int sgi, int sub) { sn_backward_item<8>(P.sn, s, Y, vs, G, sgi, xs + sub * (XS / 4)); });
-        sn_for_items<16>(P, c, lv, 1, [&](int s, int sgi, int sub) { sn_backward_item<16>(P.sn, s, Y, vs, G, sgi, xs + sub * (XS / 2)); });
-        sn_for_items<32>(P, c, lv, 2, [&](int s, int sgi, int) { sn_backward_item<32>(P.sn, s, Y, vs, G, sgi, xs); });
+        sn_for_items<1>(P, c, lv, 0, [&](const int4 d0, const int4 d1, int sgi) { sn1_backward_panel(P.sn, d0, d1, Y + (size_t)sgi * c.ysize, vs, G, sgi); });
+        sn_for_items<8>(P, c, lv, 1, [&](const int4 d0, const int4 d1, int sgi) { sn_backward_panel<8>(P.sn, d0, d1, Y + (size_t)sgi * c.ysize, vs, G, sgi); });
+        sn_for_items<16>(P, c, lv, 2, [&](const int4 d0, const int4 d1, int sgi) { sn_backward_panel<16>(P.sn, d0, d1, Y + (size_t)sgi * c.ysize, vs, G, sgi); });
+        sn_for_items<32>(P, c, lv, 3, [&](const int4 d0, const int4 d1, int sgi) { sn_backward_panel<32>(P.sn, d0, d1, Y + (size_t)sgi * c.ysize, vs, G, sgi); });
         __syncthreads();
+        if (c.lprof) { const long long tn = clock64(); c.lprof[2 * P.nlevels + lv] += tn - tlp_; tlp_ = tn; }
     }
     for (int i = c.slot; i < P.nk; i += c.nslots) v[GI(i)] = vs[i * G + sg];
     __syncthreads();
@@ -389,12 +491,13 @@ __device__ void kkt_ldl_solve_sn(const IpmProgram &P, Ctx &c, const double *Y, c
     c.t_fw += t1_ - t0_; c.t_bw += t2_ - t1_; c.t_ldl_n += 1;
 }
 
-__device__ void kkt_factor(const IpmProgram &P, Ctx &c, double *Y, double *Ls, double *invD, double delta_dyn)
+__device__ void kkt_factor(const IpmProgram &P, Ctx &c, double *Y, double *Ls, double *invD)
 {
-    if (c.sn) { kkt_factor_sn(P, c, Y, invD, delta_dyn); return; }
+    if (c.sn) { kkt_factor_sn(P, c, Y, invD); return; }
     FactorArgs a;
     a.fa_item = P.fa_item; a.fb_item = P.fb_item; a.ft_op = P.ft_op;
-    a.Y = Y; a.Ls = Ls; a.Lrow = c.Lrow; a.invD = invD; a.delta_dyn = delta_dyn;
+    a.Y = Y; a.Ls = Ls; a.Lrow = c.Lrow; a.invD = invD;
+    a.s_delta = c.s_delta; a.s_bad = c.s_bad; a.rho_min = c.rho_min; a.bad_abs = c.bad_abs;
     a.o_fal = c.o_fal; a.o_faR = c.o_faR; a.o_fbl = c.o_fbl;
     a.nl = P.nlevels; a.nnzLd = P.nnzL; a.G = c.G; a.sg = c.sg; a.slot = c.slot; a.nslots = c.nslots;
     a.lprof = c.lprof;
@@ -897,6 +1000,8 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
     __shared__ int s_flag;
     __shared__ int s_done[IPM_MAXG], s_status[IPM_MAXG], s_iters[IPM_MAXG], s_alldone, s_save[IPM_MAXG], s_stall[IPM_MAXG];
     __shared__ double s_best[IPM_MAXG], s_bp[IPM_MAXG], s_bd[IPM_MAXG], s_br[3 * IPM_MAXG];
+    __shared__ double s_delta[IPM_MAXG], s_alpha_d[IPM_MAXG];
+    __shared__ int s_bad[IPM_MAXG], s_skip[IPM_MAXG];
 
     int *s_lv = ipm_smem;   // [9][nlevels+1]: lvl_ptr | fa_lvl | fb_lvl | - | fa_R | fwp_lvl | bwp_lvl | fwp_R | bwp_R
     const int nl1 = P.nlevels + 1;
@@ -941,16 +1046,59 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
     const int nm = (P.n > P.m ? P.n : P.m);
     double *e1 = GP(D.e1, nm), *e2 = GP(D.e2, P.p), *rhs = GP(D.rhs, P.nk);
     double *Y = GP(D.Y, P.ysize), *Ls = GP(D.Ls, P.nnzL + 1), *invD = GP(D.invD, P.nk);
-    c.sn = D.sn; c.o_snx = D.o_snx; c.Ypanels = Y;
+    c.sn = D.sn; c.Ypanels = Y; c.ysize = (size_t)P.ysize;
+    c.s_done = s_done; c.s_delta = s_delta; c.s_bad = s_bad; c.rho_min = O.rho_min; c.bad_abs = O.bad_abs;
     c.Lrow = GP(D.Lrow, P.nnzL + 1);
 #undef GP
 
     long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long n_fact = 0;   // factorisations (= interior-point iterations) of this CTA
+    long long n_retry = 0;  // ... and the repeated ones (static regularisation escalated)
     long long tq = clock64();
     const long long tstart = tq;
 #define PROF(i) { const long long tn = clock64(); pt[i] += tn - tq; tq = tn; }
-    if (c.tid < G) { s_done[c.tid] = 0; s_status[c.tid] = IPM_MAXIT; s_iters[c.tid] = 0; s_best[c.tid] = CUDART_INF; s_save[c.tid] = 0; s_stall[c.tid] = 0; }
+    if (c.tid < G) {
+        const int sd = (int)g * G + c.tid;
+        // padded seeds and seeds the caller marked (SCP seeds that have already stopped) are not solved
+        const int sk = (sd >= D.B) || (D.skip && D.skip[sd]);
+        s_skip[c.tid] = sk; s_done[c.tid] = sk;
+        s_status[c.tid] = IPM_MAXIT; s_iters[c.tid] = 0; s_best[c.tid] = CUDART_INF; s_save[c.tid] = 0; s_stall[c.tid] = 0;
+        s_delta[c.tid] = O.delta; s_bad[c.tid] = 0;
+    }
+    __syncthreads();
+    {
+        int all = 1;
+        for (int q = 0; q < G; q++) all &= s_skip[q];
+        if (all) return;   // CTA-uniform: nothing to solve in this group
+    }
+    if (D.debug_kkt) {   // test hook: one KKT solve on the device with the caller's scaling and right-hand side
+        kkt_assemble(P, c, D, Av, Gv, wm, Y, 0.0);
+        kkt_factor(P, c, Y, Ls, invD);
+        kkt_ldl_solve(P, c, Ls, invD, rhs);
+        if (c.tid < G && (int)g * G + c.tid < D.B) D.status[(int)g * G + c.tid] = s_bad[c.tid];
+        return;
+    }
+    // (re)assemble and factor; a seed whose factorisation lost its inertia to cancellation (the scaling matrix spans
+    // > 25 orders of magnitude in the last iterations) gets a larger static regularisation and the group factors again
+#define IPM_FACTOR()                                                                               \
+    for (int tr_ = 0;; tr_++) {                                                                    \
+        if (c.tid < G) s_bad[c.tid] = 0;                                                           \
+        kkt_assemble(P, c, D, Av, Gv, wm, Y, 0.0);                                                 \
+        kkt_factor(P, c, Y, Ls, invD);                                                             \
+        if (c.tid == 0) {                                                                          \
+            int again_ = 0;                                                                        \
+            for (int q = 0; q < G; q++)                                                            \
+                if (s_bad[q] && !s_done[q] && s_delta[q] < O.delta_max) {                          \
+                    s_delta[q] = fmin(s_delta[q] * O.delta_esc, O.delta_max); again_ = 1;          \
+                }                                                                                  \
+            s_flag = again_;                                                                       \
+        }                                                                                          \
+        __syncthreads();                                                                           \
+        const int again_ = s_flag;                                                                 \
+        __syncthreads();                                                                           \
+        if (!again_ || tr_ >= 4) break;                                                            \
+        n_retry++;                                                                                 \
+    }
     if (O.equil > 0) equilibrate(P, c, Av, Gv, cc, bb, hh, eqD, eqA, eqG, O.equil);
     PROF(0)
     // ---- data norms ----
@@ -970,8 +1118,7 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
     // ---- starting point (CVXOPT conelp 7.1 / ECOS init): factor with W = I ----
     set_identity_scaling(P, c, wm, socw, soceta);
     __syncthreads();
-    kkt_assemble(P, c, D, Av, Gv, wm, Y, O.delta);
-    kkt_factor(P, c, Y, Ls, invD, O.delta_dyn);
+    IPM_FACTOR()
     // solve 1: [0;b;h] -> x, s = h - G x
     for (int v = c.slot; v < P.n; v += c.nslots) r1[GI(v)] = 0.0;
     __syncthreads();
@@ -1086,9 +1233,8 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
         // ---- scaling, KKT assembly, factorisation ----
         nt_scaling(P, c, s, z, lam, wm, socw, soceta);
         __syncthreads();
-        kkt_assemble(P, c, D, Av, Gv, wm, Y, O.delta);
         PROF(3)
-        kkt_factor(P, c, Y, Ls, invD, O.delta_dyn);
+        IPM_FACTOR()
         PROF(4)
         n_fact++;
 
@@ -1104,12 +1250,19 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
         // round trip: keeps G dx + ds = -rz to rounding even when the scaling is ill-conditioned)
         for (int i = c.slot; i < P.m; i += c.nslots) dsa[GI(i)] = -s[GI(i)] - gm[GI(i)];
         __syncthreads();
-        {
-            double a[1] = {fmin(cone_alpha_partial(P, c, s, dsa), cone_alpha_partial(P, c, z, dza))};
-            seed_reduce<1>(c, a, 1);
+        {   // separate primal / dual step lengths (the primal and dual residuals shrink independently); centring
+            // parameter from the predicted complementarity, sigma = (mu_aff / mu)^3 (Mehrotra)
+            double a[2] = {cone_alpha_partial(P, c, s, dsa), cone_alpha_partial(P, c, z, dza)};
+            seed_reduce<2>(c, a, 1);
+            const double ap = fmin(1.0, s_out[sg]), ad = fmin(1.0, s_out[IPM_MAXG + sg]);
+            double ma[1] = {0.0};
+            for (int i = c.slot; i < P.m; i += c.nslots) ma[0] = fma(s[GI(i)] + ap * dsa[GI(i)], z[GI(i)] + ad * dza[GI(i)], ma[0]);
+            seed_reduce<1>(c, ma, 0);
             if (c.tid < G) {
-                const double al = fmin(1.0, s_out[c.tid]);
-                const double sig = (1.0 - al) * (1.0 - al) * (1.0 - al);
+                double r = s_out[c.tid] / (deg * s_mu[c.tid]);
+                r = fmin(1.0, fmax(0.0, r));
+                if (!(r == r)) r = 1.0;
+                const double sig = r * r * r;
                 s_sigmu[c.tid] = sig * s_mu[c.tid];
                 s_scale[c.tid] = 1.0 - sig;
             }
@@ -1135,31 +1288,39 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
         for (int i = c.slot; i < P.m; i += c.nslots) ds[GI(i)] = dsa[GI(i)] - gm[GI(i)];
         __syncthreads();
         {
-            double a[1] = {fmin(cone_alpha_partial(P, c, s, ds), cone_alpha_partial(P, c, z, dz))};
-            seed_reduce<1>(c, a, 1);
-            if (c.tid < G) s_alpha[c.tid] = s_done[c.tid] ? 0.0 : fmin(1.0, 0.99 * s_out[c.tid]);
+            double a[2] = {cone_alpha_partial(P, c, s, ds), cone_alpha_partial(P, c, z, dz)};
+            seed_reduce<2>(c, a, 1);
+            if (c.tid < G) {
+                s_alpha[c.tid] = s_done[c.tid] ? 0.0 : fmin(1.0, 0.99 * s_out[c.tid]);                 // primal: x, s
+                s_alpha_d[c.tid] = s_done[c.tid] ? 0.0 : fmin(1.0, 0.99 * s_out[IPM_MAXG + c.tid]);   // dual: y, z
+            }
             __syncthreads();
         }
         // safeguard: make sure the new point is strictly interior (halve the step otherwise) so that the
         // next NT scaling is well defined
         for (int bt = 0; bt < 12; bt++) {
-            const double al = s_alpha[sg];
-            double mg[1] = {fmin(cone_margin_partial(P, c, s, ds, al), cone_margin_partial(P, c, z, dz, al))};
-            seed_reduce<1>(c, mg, 1);
+            double mg[2] = {cone_margin_partial(P, c, s, ds, s_alpha[sg]), cone_margin_partial(P, c, z, dz, s_alpha_d[sg])};
+            seed_reduce<2>(c, mg, 1);
             if (c.tid == 0) s_alldone = 1;
             __syncthreads();
-            if (c.tid < G && s_alpha[c.tid] > 0.0 && !(s_out[c.tid] > 0.0)) { s_alpha[c.tid] *= 0.5; s_alldone = 0; }
+            if (c.tid < G) {
+                if (s_alpha[c.tid] > 0.0 && !(s_out[c.tid] > 0.0)) { s_alpha[c.tid] *= 0.5; s_alldone = 0; }
+                if (s_alpha_d[c.tid] > 0.0 && !(s_out[IPM_MAXG + c.tid] > 0.0)) { s_alpha_d[c.tid] *= 0.5; s_alldone = 0; }
+            }
             __syncthreads();
             const int okall = s_alldone;
             __syncthreads();
             if (okall) break;
         }
         {
-            const double al = s_alpha[sg];
-            if (al > 0.0) {
-                for (int i = c.slot; i < P.n; i += c.nslots) x[GI(i)] += al * dx[GI(i)];
-                for (int i = c.slot; i < P.p; i += c.nslots) y[GI(i)] += al * dy[GI(i)];
-                for (int i = c.slot; i < P.m; i += c.nslots) { z[GI(i)] += al * dz[GI(i)]; s[GI(i)] += al * ds[GI(i)]; }
+            const double ap = s_alpha[sg], ad = s_alpha_d[sg];
+            if (ap > 0.0) {
+                for (int i = c.slot; i < P.n; i += c.nslots) x[GI(i)] += ap * dx[GI(i)];
+                for (int i = c.slot; i < P.m; i += c.nslots) s[GI(i)] += ap * ds[GI(i)];
+            }
+            if (ad > 0.0) {
+                for (int i = c.slot; i < P.p; i += c.nslots) y[GI(i)] += ad * dy[GI(i)];
+                for (int i = c.slot; i < P.m; i += c.nslots) z[GI(i)] += ad * dz[GI(i)];
             }
         }
         __syncthreads();
@@ -1168,7 +1329,7 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
     if (blockIdx.x == 0 && threadIdx.x == 0 && D.prof) {
         pt[7] = clock64() - tstart;
         for (int i = 0; i < 8; i++) D.prof[i] = pt[i];
-        D.prof[8] = c.t_fw; D.prof[9] = c.t_bw; D.prof[10] = c.t_ldl_n; D.prof[11] = n_fact;
+        D.prof[8] = c.t_fw; D.prof[9] = c.t_bw; D.prof[10] = c.t_ldl_n; D.prof[11] = n_fact | (n_retry << 32);
     }
 #undef PROF
     // ---- epilogue: the best iterate is the answer (ECOS reports its best point the same way) ----
@@ -1192,7 +1353,7 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
     }
     if (c.tid < G) {
         const int sd = (int)g * G + c.tid;
-        if (sd < D.B) {
+        if (sd < D.B && !s_skip[c.tid]) {
             D.status[sd] = s_status[c.tid]; D.iters[sd] = s_iters[c.tid];
             D.pobj[sd] = s_bp[c.tid]; D.dobj[sd] = s_bd[c.tid];
             D.res[sd] = s_br[c.tid]; D.res[D.B + sd] = s_br[IPM_MAXG + c.tid]; D.res[2 * D.B + sd] = s_br[2 * IPM_MAXG + c.tid];

@@ -1,145 +1,239 @@
-// conic_sn.cuh -- supernodal LDL' : the per-panel routines of the next kernel generation.
+// conic_sn.cuh -- supernodal LDL' : warp-synchronous per-panel routines.
 //
-// STATUS: executed and checked on the CPU (lane emulation, scpb_debug_kkt_solve_sn with mode 1,
-// tests/test_conic_symbolic.py); wired into k_ipm_solve behind SCPB_SUPERNODAL=1 but NOT yet run on a GPU -- the
-// default path is the scalar level-scheduled one.
-//
-// One warp owns one (supernode, seed) item of a supernodal level (conic_symbolic.h, "supernodal program"): a dense
-// column-major R x w panel, D on its diagonal, unit-lower L below.  The routines are written as a sequence of lane
-// phases -- SN_LANES(l) { ... } SN_SYNC() -- whose bodies only read what earlier phases wrote: on the device a phase is
-// the warp's 32 lanes followed by __syncwarp(), in the CPU build it is a plain loop over 32 lanes.  Per-lane state that
-// crosses a phase lives in the warp's scratch (shared memory on the device), never in registers, which is what makes
-// the two builds the same program.
+// One lane GROUP (8, 16 or 32 lanes of a warp, by panel height) owns one (supernode, seed) item of a supernodal
+// level (conic_symbolic.h, "supernodal program"): a dense column-major R x w panel, D on its diagonal, unit-lower L
+// below.  Lane r of the group holds ROW r of the panel in registers (w <= CONIC_SN_WMAX doubles), so the panel is read
+// from HBM/L2 exactly once per use, fully coalesced (the panels of ONE seed are contiguous), and the elimination of
+// its w columns costs no memory round trip and no CTA barrier -- only warp shuffles:
+//   factor   : pivot broadcast from lane c, rank-1 update of the columns to the right, then the Schur complement
+//              of the rows below is scattered into the ancestors' panels with fire-and-forget atomics;
+//   forward  : x_S = L_SS^-1 x_S by shuffles, the rows below receive -L_below,S x_S (shared-memory atomics);
+//   backward : x_S = L_SS^-T (x_S - L_below,S' x_below), one group reduction per column.
+// Single-column panels of at most CONIC_SN_R1MAX rows (the thousands of leaves of the elimination tree) are worked on
+// by ONE thread each (sn1_* below): no shuffles, all loads of an item issued together.
+// The scalar level-scheduled programs of conic_ipm.cuh need one barrier and two memory round trips per COLUMN of a
+// dense separator block; here a block of w columns is one level (bench KKT: 22 levels instead of 88).
+// The executable specification of the panel program is the CPU interpreter scpb_debug_kkt_solve_sn (conic_debug.cu).
 #pragma once
+#include "conic_symbolic.h"
 
-// A panel is worked on by a GROUP of GS = 8, 16 or 32 lanes (small leaf panels would waste a whole warp): SN_LANES
-// runs l over the lanes of the group, SN_SYNC synchronises the group only (groups of one warp may take different trip
-// counts, so the mask matters).
-#ifdef SN_EMULATE
-#define SN_FN template <int GS> static inline
-#define SN_LANES(l) for (int l = 0; l < GS; l++)
-#define SN_SYNC() ((void)0)
-#define SN_ATOMIC_SUB(p, v) (*(p) -= (v))
-#define SN_LDCG(p) (*(p))
-#else
-#define SN_FN template <int GS> __device__ __forceinline__
-#define SN_LANES(l) for (int l = (int)(threadIdx.x & (GS - 1)), l##_go = 1; l##_go; l##_go = 0)
-#define SN_SYNC() __syncwarp(GS == 32 ? 0xffffffffu : (((1u << GS) - 1u) << ((threadIdx.x & 31) & ~(GS - 1))))
-#define SN_ATOMIC_SUB(p, v) atomicAdd((p), -(v))
-#define SN_LDCG(p) __ldcg(p)
-#endif
-
-#define SN_MAXROWS 64      // panel rows a 32-lane group can hold in its sweep scratch
-#define SN_SCRATCH 384     // doubles of factor scratch per warp (panel copies of its groups): see sn_class()
-
-// lane-group size of a panel: the smallest of 8 / 16 / 32 lanes that covers its rows and whose share of the warp's
-// scratch (SN_SCRATCH * GS / 32 for the panel copy, (SN_MAXROWS + 32) * GS / 32 for the sweeps) holds it; 0 = too large
-static inline int sn_class(int R, int w)
-{
-    for (int gs = 8; gs <= 32; gs *= 2)
-        if (R <= gs && R * w <= SN_SCRATCH * gs / 32 && R + gs <= (SN_MAXROWS + 32) * gs / 32) return gs;
-    if (R <= SN_MAXROWS && R * w <= SN_SCRATCH) return 32;
-    return 0;
-}
+#define SN_WMAX CONIC_SN_WMAX
 
 struct SnProgram {          // device view of the supernodal program (all arrays shared by the batch)
     const int *first, *width, *nrows, *rows_ptr, *rows, *lvl_ptr, *lvl_nodes, *upd_xy, *sign;
-    const int *cls_ptr;     // [nlevels][4]: inside a level the supernodes are sorted by lane-group size 8 | 16 | 32
+    const int *cls_ptr;     // [nlevels][5]: inside a level the supernodes are sorted by lane-group size 1 | 8 | 16 | 32
     const int *panel_off, *upd_ptr, *upd_dst;
+    const int4 *desc;       // two int4 per supernode IN LEVEL ORDER (the order of lvl_nodes): {first, width, nrows,
+                            // panel_off}, {rows_ptr, upd_ptr, -, -}; an item costs two loads, requested one item ahead
     int nlevels;
 };
 
-// ---- numeric factorisation of one panel + Schur update of the ancestors ------------------------------------
-// P: this seed group's panels (entry e of seed sg at P[e*G + sg]); scr: >= R*w doubles of warp scratch
-SN_FN void sn_factor_item(const SnProgram &S, int s, double *P, double *invD, int G, int sg, double delta_dyn,
-                          double *scr)
+#ifdef __CUDACC__
+#define SN_R1 CONIC_SN_R1MAX
+
+template <int GS>
+__device__ __forceinline__ unsigned sn_group_mask()
 {
-    const int a = S.first[s], w = S.width[s], R = S.nrows[s];
-    const int off = S.panel_off[s];
-    SN_LANES(l) { for (int e = l; e < R * w; e += GS) scr[e] = SN_LDCG(&P[(size_t)(off + e) * G + sg]); }
-    SN_SYNC();
-    for (int c = 0; c < w; c++) {
-        double d = scr[c + R * c];
-        const double sgn = (double)S.sign[a + c];
-        if (!(sgn * d > delta_dyn)) d = sgn * delta_dyn;   // dynamic regularisation keeps the expected inertia
-        SN_LANES(l) {
-            for (int r = c + 1 + l; r < R; r += GS) scr[r + R * c] /= d;
+    return GS == 32 ? 0xffffffffu : (((1u << GS) - 1u) << ((threadIdx.x & 31) & ~(GS - 1)));
+}
+
+// ---- numeric factorisation of one panel + Schur update of the ancestors ------------------------------------
+// P: the panels of THIS seed (entry e at P[e]); invD group-blocked (entry i of seed sg at invD[i*G + sg]).
+// A pivot with sgn*d <= tau is replaced by sgn*rho (dynamic regularisation); when the rejected value is not small
+// (|d| > bad_abs or NaN) the inertia was lost to cancellation and *bad is raised: the caller escalates the static
+// regularisation of that seed and factors again.
+template <int GS>
+__device__ __forceinline__ void sn_factor_panel(const SnProgram &S, const int4 d0, const int4 d1, double *P, double *invD,
+                                                int G, int sg, double tau, double rho, double bad_abs, int *bad)
+{
+    const unsigned gm = sn_group_mask<GS>();
+    const int lg = (int)(threadIdx.x & (GS - 1));
+    const int a = d0.x, w = d0.y, R = d0.z, off = d0.w;
+    const int sgn_l = (lg < w) ? S.sign[a + lg] : 1;
+    double prow[SN_WMAX];
+#pragma unroll
+    for (int c = 0; c < SN_WMAX; c++)
+        prow[c] = (c < w && lg < R && lg >= c) ? __ldcg(&P[(size_t)off + lg + (size_t)R * c]) : 0.0;
+#pragma unroll
+    for (int c = 0; c < SN_WMAX; c++) {
+        if (c < w) {
+            double d = __shfl_sync(gm, prow[c], c, GS);
+            const double sgn = (double)__shfl_sync(gm, sgn_l, c, GS);
+            if (!(sgn * d > tau)) {
+                if (lg == 0 && !(fabs(d) <= bad_abs)) *bad = 1;
+                d = sgn * rho;
+            }
+            const double inv = 1.0 / d;
+            const double l = (lg > c && lg < R) ? prow[c] * inv : 0.0;
+            const double ld = l * d;
+#pragma unroll
+            for (int c2 = c + 1; c2 < SN_WMAX; c2++) {
+                if (c2 < w) {
+                    const double lc2 = __shfl_sync(gm, l, c2, GS);
+                    if (lg >= c2) prow[c2] = fma(-ld, lc2, prow[c2]);
+                }
+            }
+            if (lg == c) { prow[c] = d; invD[(size_t)(a + c) * G + sg] = inv; }
+            else if (lg > c) prow[c] = l;
         }
-        SN_SYNC();
-        SN_LANES(l) {
-            if (l == 0) { scr[c + R * c] = d; invD[(size_t)(a + c) * G + sg] = 1.0 / d; }
-            const int span = (w - c - 1) * R;
-            for (int idx = l; idx < span; idx += GS) {
-                const int c2 = c + 1 + idx / R, r = idx % R;
-                if (r >= c2) scr[r + R * c2] -= scr[r + R * c] * d * scr[c2 + R * c];
+    }
+#pragma unroll
+    for (int c = 0; c < SN_WMAX; c++)
+        if (c < w && lg < R && lg >= c) P[(size_t)off + lg + (size_t)R * c] = prow[c];
+    // Schur complement of the rows below: entry (x, y), x >= y, receives -sum_c L[x,c] d_c L[y,c];
+    // four rows y per round: their scatter indices are requested before the shuffles of the round
+    const int nb = R - w;
+    if (nb > 0) {
+        double ldv[SN_WMAX];
+#pragma unroll
+        for (int c = 0; c < SN_WMAX; c++) {
+            const double dc = (c < w) ? __shfl_sync(gm, prow[c], c, GS) : 0.0;
+            ldv[c] = (lg >= w) ? prow[c] * dc : 0.0;
+        }
+        const int x = lg - w;
+        const int k0 = d1.y;
+        for (int y0 = 0; y0 < nb; y0 += 4) {
+            int kk[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int y = y0 + j;
+                kk[j] = (y < nb && x >= y && x < nb) ? S.upd_dst[k0 + y * nb - (y * (y - 1)) / 2 + (x - y)] : -1;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int y = y0 + j;
+                if (y < nb) {
+                    double u = 0.0;
+#pragma unroll
+                    for (int c = 0; c < SN_WMAX; c++) {
+                        if (c < w) {
+                            const double pv = __shfl_sync(gm, prow[c], w + y, GS);
+                            u = fma(ldv[c], pv, u);
+                        }
+                    }
+                    if (kk[j] >= 0) atomicAdd(&P[kk[j]], -u);
+                }
             }
         }
-        SN_SYNC();
     }
-    SN_LANES(l) { for (int e = l; e < R * w; e += GS) P[(size_t)(off + e) * G + sg] = scr[e]; }
-    const int k0 = S.upd_ptr[s], k1 = S.upd_ptr[s + 1];
-    SN_LANES(l) {
-        for (int k = k0 + l; k < k1; k += GS) {
-            const int xy = S.upd_xy[k], x = xy & 0xffff, y = xy >> 16;
-            double u = 0.0;
-            for (int c = 0; c < w; c++) u += scr[w + x + R * c] * scr[c + R * c] * scr[w + y + R * c];
-            SN_ATOMIC_SUB(&P[(size_t)S.upd_dst[k] * G + sg], u);
+}
+
+// one thread, one single-column panel of at most SN_R1 rows
+__device__ __forceinline__ void sn1_factor_panel(const SnProgram &S, const int4 d0, const int4 d1, double *P, double *invD,
+                                                 int G, int sg, double tau, double rho, double bad_abs, int *bad)
+{
+    const int a = d0.x, R = d0.z, off = d0.w, nb = R - 1;
+    double v[SN_R1];
+#pragma unroll
+    for (int r = 0; r < SN_R1; r++) v[r] = (r < R) ? __ldcg(&P[(size_t)off + r]) : 0.0;
+    const double sgn = (double)S.sign[a];
+    double d = v[0];
+    if (!(sgn * d > tau)) {
+        if (!(fabs(d) <= bad_abs)) *bad = 1;
+        d = sgn * rho;
+    }
+    const double inv = 1.0 / d;
+    invD[(size_t)a * G + sg] = inv;
+    P[off] = d;
+#pragma unroll
+    for (int r = 1; r < SN_R1; r++)
+        if (r < R) { v[r] *= inv; P[(size_t)off + r] = v[r]; }
+    int k = d1.y;
+#pragma unroll
+    for (int y = 0; y < SN_R1 - 1; y++) {
+        if (y < nb) {
+            const double ly = v[1 + y] * d;
+#pragma unroll
+            for (int x = y; x < SN_R1 - 1; x++)
+                if (x < nb) { atomicAdd(&P[S.upd_dst[k]], -(v[1 + x] * ly)); k++; }
         }
     }
-    SN_SYNC();
 }
 
 // ---- forward substitution of one panel: x_S = L_SS^-1 x_S, then the rows below receive -L_below,S x_S ---------
-// v: the substitution vector of this seed group (entry i of seed sg at v[i*G + sg]); xs: >= R doubles of warp scratch
-SN_FN void sn_forward_item(const SnProgram &S, int s, const double *P, double *v, int G, int sg, double *xs)
+// v: the substitution vector of this seed group in shared memory (entry i of seed sg at v[i*G + sg])
+template <int GS>
+__device__ __forceinline__ void sn_forward_panel(const SnProgram &S, const int4 d0, const int4 d1, const double *P,
+                                                 double *v, int G, int sg)
 {
-    const int w = S.width[s], R = S.nrows[s];
-    const int off = S.panel_off[s];
-    const int *rows = S.rows + S.rows_ptr[s];
-    SN_LANES(l) { for (int r = l; r < R; r += GS) xs[r] = (r < w) ? v[(size_t)rows[r] * G + sg] : 0.0; }
-    SN_SYNC();
-    for (int c = 0; c < w; c++) {
-        SN_LANES(l) {
-            const double xc = xs[c];
-            for (int r = c + 1 + l; r < R; r += GS) xs[r] -= P[(size_t)(off + r + R * c) * G + sg] * xc;
-        }
-        SN_SYNC();
-    }
-    SN_LANES(l) {
-        for (int r = l; r < R; r += GS) {
-            double *t = &v[(size_t)rows[r] * G + sg];
-            if (r < w) *t = xs[r]; else SN_ATOMIC_SUB(t, -xs[r]);   // siblings update common ancestors: atomic
+    const unsigned gm = sn_group_mask<GS>();
+    const int lg = (int)(threadIdx.x & (GS - 1));
+    const int w = d0.y, R = d0.z, off = d0.w;
+    const int ri = (lg < R) ? S.rows[d1.x + lg] : 0;
+    double prow[SN_WMAX];
+#pragma unroll
+    for (int c = 0; c < SN_WMAX; c++)
+        prow[c] = (c < w && lg < R && lg > c) ? __ldcg(&P[(size_t)off + lg + (size_t)R * c]) : 0.0;
+    double x = (lg < w) ? v[(size_t)ri * G + sg] : 0.0;
+#pragma unroll
+    for (int c = 0; c < SN_WMAX; c++) {
+        if (c < w) {
+            const double xc = __shfl_sync(gm, x, c, GS);
+            x = fma(-prow[c], xc, x);      // prow[c] is zero for lanes <= c
         }
     }
-    SN_SYNC();
+    if (lg < w) v[(size_t)ri * G + sg] = x;
+    else if (lg < R) atomicAdd(&v[(size_t)ri * G + sg], x);   // siblings update common ancestors
+}
+
+__device__ __forceinline__ void sn1_forward_panel(const SnProgram &S, const int4 d0, const int4 d1, const double *P,
+                                                  double *v, int G, int sg)
+{
+    const int R = d0.z, off = d0.w;
+    int ri[SN_R1];
+    double l[SN_R1];
+#pragma unroll
+    for (int r = 0; r < SN_R1; r++) {
+        ri[r] = (r < R) ? S.rows[d1.x + r] : 0;
+        l[r] = (r > 0 && r < R) ? __ldcg(&P[(size_t)off + r]) : 0.0;
+    }
+    const double xc = v[(size_t)ri[0] * G + sg];
+#pragma unroll
+    for (int r = 1; r < SN_R1; r++)
+        if (r < R) atomicAdd(&v[(size_t)ri[r] * G + sg], -l[r] * xc);
 }
 
 // ---- backward substitution of one panel: x_S = L_SS^-T (x_S - L_below,S^T x_below) -----------------------------
-// xs: >= SN_MAXROWS + GS doubles of group scratch (rows, then the partial sums)
-SN_FN void sn_backward_item(const SnProgram &S, int s, const double *P, double *v, int G, int sg, double *xs)
+template <int GS>
+__device__ __forceinline__ void sn_backward_panel(const SnProgram &S, const int4 d0, const int4 d1, const double *P,
+                                                  double *v, int G, int sg)
 {
-    const int w = S.width[s], R = S.nrows[s];
-    const int off = S.panel_off[s];
-    const int *rows = S.rows + S.rows_ptr[s];
-    double *ps = xs + (GS == 32 ? SN_MAXROWS : GS);
-    SN_LANES(l) { for (int r = l; r < R; r += GS) xs[r] = v[(size_t)rows[r] * G + sg]; }
-    SN_SYNC();
-    for (int c = w - 1; c >= 0; c--) {
-        SN_LANES(l) {
-            double acc = 0.0;
-            for (int r = c + 1 + l; r < R; r += GS) acc += P[(size_t)(off + r + R * c) * G + sg] * xs[r];
-            ps[l] = acc;
+    const unsigned gm = sn_group_mask<GS>();
+    const int lg = (int)(threadIdx.x & (GS - 1));
+    const int w = d0.y, R = d0.z, off = d0.w;
+    const int ri = (lg < R) ? S.rows[d1.x + lg] : 0;
+    double prow[SN_WMAX];
+#pragma unroll
+    for (int c = 0; c < SN_WMAX; c++)
+        prow[c] = (c < w && lg < R && lg > c) ? __ldcg(&P[(size_t)off + lg + (size_t)R * c]) : 0.0;
+    double x = (lg < R) ? v[(size_t)ri * G + sg] : 0.0;
+#pragma unroll
+    for (int c = SN_WMAX - 1; c >= 0; c--) {
+        if (c < w) {
+            double t = prow[c] * x;
+#pragma unroll
+            for (int o = GS / 2; o > 0; o >>= 1) t += __shfl_xor_sync(gm, t, o, GS);
+            if (lg == c) x -= t;
         }
-        SN_SYNC();
-        SN_LANES(l) {
-            if (l == 0) {
-                double t = 0.0;
-                for (int j = 0; j < GS; j++) t += ps[j];
-                xs[c] -= t;
-            }
-        }
-        SN_SYNC();
     }
-    SN_LANES(l) { for (int r = l; r < w; r += GS) v[(size_t)rows[r] * G + sg] = xs[r]; }
-    SN_SYNC();
+    if (lg < w) v[(size_t)ri * G + sg] = x;
 }
+
+__device__ __forceinline__ void sn1_backward_panel(const SnProgram &S, const int4 d0, const int4 d1, const double *P,
+                                                   double *v, int G, int sg)
+{
+    const int R = d0.z, off = d0.w;
+    int ri[SN_R1];
+    double l[SN_R1];
+#pragma unroll
+    for (int r = 0; r < SN_R1; r++) {
+        ri[r] = (r < R) ? S.rows[d1.x + r] : 0;
+        l[r] = (r > 0 && r < R) ? __ldcg(&P[(size_t)off + r]) : 0.0;
+    }
+    double x = v[(size_t)ri[0] * G + sg];
+#pragma unroll
+    for (int r = 1; r < SN_R1; r++)
+        if (r < R) x = fma(-l[r], v[(size_t)ri[r] * G + sg], x);
+    v[(size_t)ri[0] * G + sg] = x;
+}
+#endif  // __CUDACC__

@@ -22,6 +22,18 @@
 #ifndef CONIC_SOLVE_PF
 #define CONIC_SOLVE_PF 4   // L entries a lane keeps in flight per substitution item
 #endif
+// supernodal panels (conic_sn.cuh): a panel is held by a lane group, one lane per row, at most CONIC_SN_WMAX columns
+// in registers; wider runs of columns are cut into several supernodes
+#define CONIC_SN_WMAX 12
+#define CONIC_SN_RMAX 32
+#define CONIC_SN_R1MAX 10   // single-column panels up to this height are handled by ONE thread (leaf levels)
+// lane-group size of an R x w panel (1, 8, 16 or 32 lanes; 0: the panel does not fit a warp -> scalar programs only)
+inline int conic_sn_class(int R, int w)
+{
+    if (w > CONIC_SN_WMAX || R > CONIC_SN_RMAX) return 0;
+    if (w == 1 && R <= CONIC_SN_R1MAX) return 1;
+    return R <= 8 ? 8 : (R <= 16 ? 16 : 32);
+}
 
 struct ConeSymbolic {
     int n = 0, p = 0, m = 0, l = 0, nsoc = 0;
@@ -74,12 +86,12 @@ struct ConeSymbolic {
     // bit1 = the item is the diagonal itself (regularise, write 1/d), otherwise scale the entry by 1/d.
     std::vector<int> fa_item, fa_lvl, fa_R;
     std::vector<int> fb_item, fb_lvl;
-    // ---- supernodal program (host side of the round-2 kernels; executed today only by the CPU interpreter
-    // scpb_debug_kkt_solve_sn, tests/test_conic_symbolic.py) ----
+    // ---- supernodal program (executed by the kernels of conic_sn.cuh; CPU interpreter scpb_debug_kkt_solve_sn,
+    // tests/test_conic_symbolic.py) ----
     // Maximal supernodes: consecutive columns a..b with parent(j) = j+1 and struct(L[:,j]) = {j+1} + struct(L[:,j+1]);
     // each owns a dense column-major R x w panel (rows = its own w columns, then the rows below), D on the panel
-    // diagonal, unit-lower L below it.  A supernodal level needs ONE barrier; the bench KKT has 22 such levels
-    // against 88 scalar ones (profiles/r1_supernode_study.txt).
+    // diagonal, unit-lower L below it (at most CONIC_SN_WMAX columns per supernode).  A supernodal level needs ONE
+    // barrier; the bench KKT has 22 such levels against 88 scalar ones (profiles/r1_supernode_study.txt).
     std::vector<int> sn_first, sn_width, sn_nrows;   // per supernode
     std::vector<int> sn_rows_ptr, sn_rows;           // row (node) indices of each panel
     std::vector<int> sn_panel_off;                   // offset of each panel in the per-seed panel array
@@ -89,7 +101,7 @@ struct ConeSymbolic {
     std::vector<int> sn_upd_dst;                     // lower-triangle pairs (x >= y) of the below rows -> panel offset
     std::vector<int> sn_upd_xy;                      // the pair itself, packed x | y << 16 (indices into the below rows)
     std::vector<int> sn_sign;                        // expected pivot sign of each column (+1 / -1)
-    std::vector<int> sn_cls_ptr;                     // [nlevels][4]: level nodes sorted by lane-group size 8 | 16 | 32 (conic_sn.cuh)
+    std::vector<int> sn_cls_ptr;                     // [nlevels][5]: level nodes sorted by lane-group size 1 | 8 | 16 | 32 (conic_sn.cuh)
     bool sn_fits = true;                             // every panel fits a warp's scratch
     long long sn_panel_size = 0;
     int sn_nlevels = 0;
@@ -421,7 +433,7 @@ inline bool cone_symbolic_build(ConeSymbolic &S, int n, int p, int m, const int 
         S.sn_first.clear(); S.sn_width.clear(); S.sn_nrows.clear();
         for (int j = 0; j < nk;) {
             int k = j;
-            while (k + 1 < nk && S.L_cp[k + 1] > S.L_cp[k] && S.L_ri[S.L_cp[k]] == k + 1 &&
+            while (k + 1 < nk && (k - j + 1) < CONIC_SN_WMAX && S.L_cp[k + 1] > S.L_cp[k] && S.L_ri[S.L_cp[k]] == k + 1 &&
                    (S.L_cp[k + 1] - S.L_cp[k]) == (S.L_cp[k + 2] - S.L_cp[k + 1]) + 1)
                 k++;
             const int sid = (int)S.sn_first.size();
@@ -506,21 +518,19 @@ inline bool cone_symbolic_build(ConeSymbolic &S, int n, int p, int m, const int 
             std::vector<int> nxt(S.sn_lvl_ptr.begin(), S.sn_lvl_ptr.end() - 1);
             for (int s = 0; s < ns; s++) S.sn_lvl_nodes[nxt[slev[s]]++] = s;
         }
-        // inside a level: small panels first (lane groups of 8, then 16, then 32 lanes)
-        auto cls_of = [&](int s) { int R = S.sn_nrows[s], w = S.sn_width[s];
-                                   for (int gs = 8; gs <= 32; gs *= 2)
-                                       if (R <= gs && R * w <= 384 * gs / 32 && R + gs <= 96 * gs / 32) return gs;
-                                   return (R <= 64 && R * w <= 384) ? 32 : 0; };
-        S.sn_cls_ptr.assign(4 * (size_t)S.sn_nlevels, 0);
+        // inside a level: small panels first (single threads, then lane groups of 8, 16 and 32 lanes)
+        auto cls_of = [&](int s) { return conic_sn_class(S.sn_nrows[s], S.sn_width[s]); };
+        S.sn_cls_ptr.assign(5 * (size_t)S.sn_nlevels, 0);
         S.sn_fits = true;
         for (int lv = 0; lv < S.sn_nlevels; lv++) {
             int *b = &S.sn_lvl_nodes[S.sn_lvl_ptr[lv]], *e = &S.sn_lvl_nodes[S.sn_lvl_ptr[lv + 1]];
             std::stable_sort(b, e, [&](int x, int y) { int cx = cls_of(x), cy = cls_of(y); return (cx ? cx : 64) < (cy ? cy : 64); });
             int o = S.sn_lvl_ptr[lv];
-            S.sn_cls_ptr[4 * lv] = o;
-            for (int gs = 8, q = 1; gs <= 32; gs *= 2, q++) {
-                while (o < S.sn_lvl_ptr[lv + 1] && cls_of(S.sn_lvl_nodes[o]) == gs) o++;
-                S.sn_cls_ptr[4 * lv + q] = o;
+            S.sn_cls_ptr[5 * lv] = o;
+            const int gss[4] = {1, 8, 16, 32};
+            for (int q = 0; q < 4; q++) {
+                while (o < S.sn_lvl_ptr[lv + 1] && cls_of(S.sn_lvl_nodes[o]) == gss[q]) o++;
+                S.sn_cls_ptr[5 * lv + q + 1] = o;
             }
             if (o != S.sn_lvl_ptr[lv + 1]) S.sn_fits = false;   // a panel too large for the warp scratch
         }

@@ -16,7 +16,7 @@
 
 // pieces of conic_api.cu used here
 struct scpb_cone_s;
-int scpb_internal_cone_run(scpb_cone_s *c, const IpmOpts &o);
+int scpb_internal_cone_run(scpb_cone_s *c, const IpmOpts &o, const int *skip);
 int scpb_internal_cone_reserve(scpb_cone_s *c, int B, int G, int lanes);
 IpmData *scpb_internal_cone_data(scpb_cone_s *c);
 const ConeSymbolic *scpb_internal_cone_sym(scpb_cone_s *c);
@@ -192,6 +192,8 @@ __global__ void k_ptr_step(const StepDev d)
 struct scpb_ptr_s {
     scpb_handle_s *h = nullptr;
     scpb_cone_s *cone = nullptr;
+    int model_id = 0;            // dynamics pack and parameters captured at setup: a later scpb_model_set on the same
+    ModelPar par{};              // handle (another problem sharing it) must not change what THIS problem solves
     scpb_ptr_desc d{};
     std::vector<void *> dev;
     int *W_rp = nullptr, *W_ci = nullptr;
@@ -212,6 +214,33 @@ struct scpb_ptr_s {
     int *accept = nullptr;
 };
 
+// the handle may have been pointed at another model pack since scpb_ptr_setup (several problems can share one handle):
+// every solve re-selects the pack and parameters this problem was set up with
+static void ptr_select_model(scpb_ptr_s *s)
+{
+    scpb_handle_s *h = s->h;
+    h->model_id = s->model_id; h->par = s->par;
+    h->nx = s->d.nx; h->nu = s->d.nu; h->np = s->d.np;
+}
+
+// events of the phase timers: destroyed on every exit path
+struct EventList {
+    std::vector<cudaEvent_t> ev;
+    ~EventList() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
+};
+
+// singular-transition-matrix flag raised by k_discretize_foh during the loop: report it and clear it
+static int ptr_check_disc_status(scpb_handle_s *h, const char *who)
+{
+    int hstat = 0;
+    SCPB_CUDA(h, cudaMemcpy(&hstat, h->d_status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (hstat & 1) {
+        cudaMemset(h->d_status, 0, sizeof(int));
+        return set_err(h, SCPB_ERR_STATE, "%s: singular transition matrix during discretization", who);
+    }
+    return SCPB_OK;
+}
+
 template <class T>
 static T *up(scpb_ptr_s *s, const T *src, size_t n)
 {
@@ -227,8 +256,17 @@ static int ptr_reserve(scpb_ptr_s *s, int B, int G)
     scpb_handle_s *h = s->h;
     const int Bpad = ((B + G - 1) / G) * G;
     if (s->capB >= Bpad && s->capG == G) return SCPB_OK;
-    for (void *q : s->bb) cudaFree(q);
-    s->bb.clear();
+    // forget the old set before allocating the new one: a failed allocation must not leave stale pointers behind
+    auto drop = [&]() {
+        for (void *q : s->bb) if (q) cudaFree(q);
+        s->bb.clear();
+        s->capB = 0; s->capG = 0;
+        s->src = s->xd = s->ud = s->p = s->xn = s->un = s->pn = nullptr;
+        s->defect = s->J_ref = s->J_new = s->devi = s->imp = s->c0 = nullptr;
+        s->feas = s->done = s->status = s->iters = s->nactive = nullptr;
+        s->src2 = s->eta = s->L_new = s->J_out = nullptr; s->accept = nullptr;
+    };
+    drop();
     const scpb_ptr_desc &d = s->d;
     bool ok = true;
     auto al = [&](size_t bytes) { void *q = nullptr; if (cudaMalloc(&q, bytes + 64) != cudaSuccess) { ok = false; return (void *)nullptr; } s->bb.push_back(q); return q; };
@@ -249,7 +287,7 @@ static int ptr_reserve(scpb_ptr_s *s, int B, int G)
         s->eta = (double *)al(sizeof(double) * Bpad); s->L_new = (double *)al(sizeof(double) * Bpad);
         s->J_out = (double *)al(sizeof(double) * Bpad); s->accept = (int *)al(sizeof(int) * Bpad);
     }
-    if (!ok) return set_err(h, SCPB_ERR_CUDA, "ptr: device allocation failed (B=%d)", B);
+    if (!ok) { cudaGetLastError(); drop(); return set_err(h, SCPB_ERR_CUDA, "ptr: device allocation failed (B=%d)", B); }
     s->capB = Bpad; s->capG = G;
     return SCPB_OK;
 }
@@ -445,6 +483,7 @@ int32_t scpb_ptr_setup(scpb_handle h, scpb_cone cone, const scpb_ptr_desc *desc,
     scpb_ptr_s *s = new (std::nothrow) scpb_ptr_s();
     if (!s) return SCPB_ERR_CUDA;
     s->h = h; s->cone = cone; s->d = *desc;
+    s->model_id = h->model_id; s->par = h->par;
     const int nnzW = W_rowptr[desc->nval];
     s->W_rp = up(s, W_rowptr, (size_t)desc->nval + 1);
     s->W_ci = up(s, W_colind, (size_t)nnzW);
@@ -477,6 +516,8 @@ int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *u
     scpb_handle_s *h = s->h;
     if (B <= 0 || !xd0 || !ud0 || !p0) return set_err(h, SCPB_ERR_ARG, "ptr_solve: bad arguments");
     SCPB_CUDA(h, cudaSetDevice(h->device));
+    ptr_select_model(s);
+    SCPB_CUDA(h, cudaMemsetAsync(h->d_status, 0, sizeof(int), h->stream));
     const scpb_ptr_desc &d = s->d;
     const int G = scpb_internal_pick_group(B, opts ? opts->group : 0);
     int rc = scpb_internal_cone_reserve(s->cone, B, G, opts ? opts->lanes : 0);
@@ -505,7 +546,7 @@ int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *u
     pd.B = B; pd.G = G; pd.N = d.N; pd.nx = d.nx; pd.nu = d.nu; pd.np = d.np; pd.ns = d.ns;
     pd.nsrc = d.nsrc; pd.oC = d.oC; pd.oD = d.oD; pd.oG = d.oG; pd.ors = d.ors; pd.oxh = d.oxh; pd.ouh = d.ouh; pd.oph = d.oph;
     pd.t_grid = s->tgrid; pd.Sx = Sx; pd.cx = cx; pd.Su = Su; pd.cu = cu; pd.Sp = Sp; pd.cp = cp;
-    pd.src = s->src; pd.par = h->par;
+    pd.src = s->src; pd.par = s->par;
     AsmDev ad{};
     ad.B = B; ad.G = G; ad.nsrc = d.nsrc; ad.nval = d.nval; ad.nnzA = (int)S->A_ci.size(); ad.nnzG = (int)S->G_ci.size();
     ad.n = S->n; ad.p = S->p; ad.m = S->m; ad.W_rp = s->W_rp; ad.W_ci = s->W_ci; ad.W_v = s->W_v; ad.src = s->src;
@@ -520,7 +561,8 @@ int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *u
     sd.done = s->done; sd.status = s->status; sd.iters = s->iters; sd.nactive = s->nactive;
 
     // phase timers (the reference's keys: discretize / formulate / solve / overhead, scp.jl:177-178,990-995)
-    std::vector<cudaEvent_t> ev;
+    EventList evl;
+    std::vector<cudaEvent_t> &ev = evl.ev;
     auto mark = [&]() { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev.push_back(e); };
     std::vector<int> phase;   // phase id of the interval that ENDS at event i
     mark(); phase.push_back(-1);
@@ -532,7 +574,7 @@ int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *u
     long long ipm_iters = 0;
     std::vector<int> hit(B);
     for (; it <= d.iter_max; it++) {
-        if (h->model_id == SCPB_MODEL_STARSHIP && d.ns > 0)
+        if (s->model_id == SCPB_MODEL_STARSHIP && d.ns > 0)
             k_linearize<Constr<SCPB_MODEL_STARSHIP>><<<nbn, 128, 0, st>>>(pd, s->xd, s->ud, s->p);
         else
             k_linearize<Constr<0>><<<nbn, 128, 0, st>>>(pd, s->xd, s->ud, s->p);
@@ -540,7 +582,7 @@ int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *u
         k_assemble<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ad);
         h->launches += 2;
         mark(); phase.push_back(1);
-        if ((rc = scpb_internal_cone_run(s->cone, o))) return rc;
+        if ((rc = scpb_internal_cone_run(s->cone, o, s->done))) return rc;
         mark(); phase.push_back(2);
         SCPB_CUDA(h, cudaMemcpyAsync(hit.data(), D->iters, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
         sd.iter = it;
@@ -577,12 +619,11 @@ int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *u
     }
     float tot_ms = 0.f;
     cudaEventElapsedTime(&tot_ms, ev.front(), ev.back());
-    for (cudaEvent_t e : ev) cudaEventDestroy(e);
     if (timing) {
         timing[0] = acc[0]; timing[1] = acc[1]; timing[2] = acc[2]; timing[3] = acc[3];
         timing[4] = tot_ms * 1e-3; timing[5] = (double)total_it; timing[6] = (double)ipm_iters; timing[7] = 0.0;
     }
-    return SCPB_OK;
+    return ptr_check_disc_status(h, "ptr_solve");
 }
 
 int32_t scpb_scvx_attach(scpb_ptr s, const scpb_scvx_desc *desc, const int32_t *Q_rowptr, const int32_t *Q_colind,
@@ -622,6 +663,8 @@ int32_t scpb_scvx_solve(scpb_ptr s, int32_t B, const double *xd0, const double *
     if (!s->scvx) return set_err(h, SCPB_ERR_STATE, "scvx_solve: call scpb_scvx_attach first");
     if (B <= 0 || !xd0 || !ud0 || !p0) return set_err(h, SCPB_ERR_ARG, "scvx_solve: bad arguments");
     SCPB_CUDA(h, cudaSetDevice(h->device));
+    ptr_select_model(s);
+    SCPB_CUDA(h, cudaMemsetAsync(h->d_status, 0, sizeof(int), h->stream));
     const scpb_ptr_desc &d = s->d;
     const scpb_scvx_desc &v = s->sv;
     const int G = scpb_internal_pick_group(B, opts ? opts->group : 0);
@@ -654,7 +697,7 @@ int32_t scpb_scvx_solve(scpb_ptr s, int32_t B, const double *xd0, const double *
     pd.B = B; pd.G = G; pd.N = d.N; pd.nx = d.nx; pd.nu = d.nu; pd.np = d.np; pd.ns = d.ns;
     pd.nsrc = d.nsrc; pd.oC = d.oC; pd.oD = d.oD; pd.oG = d.oG; pd.ors = d.ors; pd.oxh = d.oxh; pd.ouh = d.ouh; pd.oph = d.oph;
     pd.t_grid = s->tgrid; pd.Sx = Sx; pd.cx = cx; pd.Su = Su; pd.cu = cu; pd.Sp = Sp; pd.cp = cp;
-    pd.src = s->src; pd.par = h->par; pd.eta = s->eta; pd.oeta = v.oeta;
+    pd.src = s->src; pd.par = s->par; pd.eta = s->eta; pd.oeta = v.oeta;
     AsmDev ad{};
     ad.B = B; ad.G = G; ad.nsrc = d.nsrc; ad.nval = d.nval; ad.nnzA = (int)S->A_ci.size(); ad.nnzG = (int)S->G_ci.size();
     ad.n = S->n; ad.p = S->p; ad.m = S->m; ad.W_rp = s->W_rp; ad.W_ci = s->W_ci; ad.W_v = s->W_v; ad.src = s->src;
@@ -675,20 +718,21 @@ int32_t scpb_scvx_solve(scpb_ptr s, int32_t B, const double *xd0, const double *
     cv.eta_lb = v.eta_lb; cv.eta_ub = v.eta_ub; cv.eps_abs = d.eps_abs; cv.eps_rel = d.eps_rel;
     cv.Q_rp = s->Q_rp; cv.Q_ci = s->Q_ci; cv.Q_v = s->Q_v; cv.Q_c = s->Q_c;
     cv.Sx = Sx; cv.cx = cx; cv.Su = Su; cv.cu = cu; cv.Sp = Sp; cv.cp = cp; cv.t_grid = s->tgrid; cv.defect = s->defect;
-    cv.par = h->par;
+    cv.par = s->par;
     cv.xd = s->xd; cv.ud = s->ud; cv.p = s->p; cv.xn = s->xn; cv.un = s->un; cv.pn = s->pn;
     cv.J_ref = s->J_ref; cv.J_new = s->J_new; cv.L_new = s->L_new; cv.J_out = s->J_out; cv.eta = s->eta; cv.dev = s->devi;
     cv.cone_status = D->status; cv.feas_new = s->feas;
     cv.done = s->done; cv.status = s->status; cv.iters = s->iters; cv.nactive = s->nactive; cv.accept = s->accept;
     cv.src = s->src; cv.src2 = s->src2;
-    const bool pack = (h->model_id == SCPB_MODEL_STARSHIP && d.ns > 0);
+    const bool pack = (s->model_id == SCPB_MODEL_STARSHIP && d.ns > 0);
     auto cost = [&](const double *X, const double *U, const double *P, double *Jd, double *Ld) {
         if (pack) k_scvx_cost<Constr<SCPB_MODEL_STARSHIP>><<<(B + 63) / 64, 64, 0, st>>>(cv, X, U, P, Jd, Ld);
         else k_scvx_cost<Constr<0>><<<(B + 63) / 64, 64, 0, st>>>(cv, X, U, P, Jd, Ld);
         h->launches++;
     };
 
-    std::vector<cudaEvent_t> ev;
+    EventList evl;
+    std::vector<cudaEvent_t> &ev = evl.ev;
     auto mark = [&]() { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev.push_back(e); };
     std::vector<int> phase;
     mark(); phase.push_back(-1);
@@ -709,7 +753,7 @@ int32_t scpb_scvx_solve(scpb_ptr s, int32_t B, const double *xd0, const double *
         k_assemble<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ad);
         h->launches += 2;
         mark(); phase.push_back(1);
-        if ((rc = scpb_internal_cone_run(s->cone, o))) return rc;
+        if ((rc = scpb_internal_cone_run(s->cone, o, s->done))) return rc;
         mark(); phase.push_back(2);
         SCPB_CUDA(h, cudaMemcpyAsync(hit.data(), D->iters, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
         sd.iter = it;
@@ -750,12 +794,11 @@ int32_t scpb_scvx_solve(scpb_ptr s, int32_t B, const double *xd0, const double *
     }
     float tot_ms = 0.f;
     cudaEventElapsedTime(&tot_ms, ev.front(), ev.back());
-    for (cudaEvent_t e : ev) cudaEventDestroy(e);
     if (timing) {
         timing[0] = acc[0]; timing[1] = acc[1]; timing[2] = acc[2]; timing[3] = acc[3];
         timing[4] = tot_ms * 1e-3; timing[5] = (double)total_it; timing[6] = (double)ipm_iters; timing[7] = 0.0;
     }
-    return SCPB_OK;
+    return ptr_check_disc_status(h, "scvx_solve");
 }
 
 }  // extern "C"

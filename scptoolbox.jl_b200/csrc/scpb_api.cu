@@ -194,6 +194,7 @@ int32_t scpb_discretize(scpb_handle h, int32_t method, int32_t B, int32_t N, int
     double *d_A = dout, *d_E = d_A + s_A, *d_Bm = d_E + s_A, *d_Bp = d_Bm + s_B, *d_F = d_Bp + s_B,
            *d_r = d_F + s_F, *d_df = d_r + s_r;
     cudaStream_t st = h->stream;
+    SCPB_CUDA(h, cudaMemsetAsync(h->d_status, 0, sizeof(int), st));   // a stale flag of an earlier call is not this call's error
     SCPB_CUDA(h, cudaMemcpyAsync(d_t, t_grid, sizeof(double) * s_t, cudaMemcpyHostToDevice, st));
     SCPB_CUDA(h, cudaMemcpyAsync(d_x, xd, sizeof(double) * s_x, cudaMemcpyHostToDevice, st));
     SCPB_CUDA(h, cudaMemcpyAsync(d_u, ud, sizeof(double) * s_u, cudaMemcpyHostToDevice, st));
@@ -266,8 +267,7 @@ int32_t scpb_propagate(scpb_handle h, int32_t method, int32_t B, int32_t N, int3
     PropArgs a{};
     a.B = B; a.N = N; a.res = res; a.t_grid = d_t; a.xd = d_x; a.ud = d_u; a.p = d_p; a.np = (int)np; a.xc = dout;
     a.par = h->par;
-    cudaEvent_t e0, e1;
-    SCPB_CUDA(h, cudaEventCreate(&e0)); SCPB_CUDA(h, cudaEventCreate(&e1));
+    cudaEvent_t e0 = h->ev0, e1 = h->ev1;   // the handle's own pair: nothing to leak on an error path
     SCPB_CUDA(h, cudaEventRecord(e0, st));
     switch (h->model_id) {
     case SCPB_MODEL_DBLINT: launch_prop<Model<SCPB_MODEL_DBLINT>>(h, a); break;
@@ -275,7 +275,7 @@ int32_t scpb_propagate(scpb_handle h, int32_t method, int32_t B, int32_t N, int3
     case SCPB_MODEL_STARSHIP: launch_prop<Model<SCPB_MODEL_STARSHIP>>(h, a); break;
     case SCPB_MODEL_QUADROTOR: launch_prop<Model<SCPB_MODEL_QUADROTOR>>(h, a); break;
     case SCPB_MODEL_FREEFLYER: launch_prop<Model<SCPB_MODEL_FREEFLYER>>(h, a); break;
-    default: cudaEventDestroy(e0); cudaEventDestroy(e1); return set_err(h, SCPB_ERR_MODEL, "unknown model id %d", h->model_id);
+    default: return set_err(h, SCPB_ERR_MODEL, "unknown model id %d", h->model_id);
     }
     SCPB_CUDA(h, cudaEventRecord(e1, st));
     SCPB_CUDA(h, cudaGetLastError());
@@ -283,7 +283,6 @@ int32_t scpb_propagate(scpb_handle h, int32_t method, int32_t B, int32_t N, int3
     SCPB_CUDA(h, cudaStreamSynchronize(st));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (seconds) *seconds = 1e-3 * ms;
     return SCPB_OK;
 }

@@ -58,8 +58,12 @@ SIGNATURES = {
                                          _ip, _ip, _dp, _dp, _dp, C.c_double, C.c_double, _dp, _dp, C.POINTER(C.c_int64)]),
     "scpb_debug_kkt_solve_sn": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _ip, _ip, _ip, _ip, C.c_int32, C.c_int32,
                                          _ip, _ip, _dp, _dp, _dp, C.c_double, C.c_double, _dp, _dp, C.POINTER(C.c_int64)]),
-    "scpb_debug_kkt_solve_sn_emu": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _ip, _ip, _ip, _ip, C.c_int32, C.c_int32,
-                                         _ip, _ip, _dp, _dp, _dp, C.c_double, C.c_double, _dp, _dp, C.POINTER(C.c_int64)]),
+    "scpb_debug_kkt_solve_dev": (C.c_int32, [C.c_void_p, C.c_int32, _dp, _dp, _dp, C.c_double, _dp, _dp, _ip]),
+    "scpb_debug_kkt_new": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _ip, _ip, _ip, _ip, C.c_int32, C.c_int32, _ip, _ip,
+                                       C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "scpb_debug_kkt_factor": (C.c_int32, [C.c_void_p, _dp, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_double, _dp]),
+    "scpb_debug_kkt_resolve": (C.c_int32, [C.c_void_p, _dp, _dp]),
+    "scpb_debug_kkt_free": (C.c_int32, [C.c_void_p]),
 }
 
 
@@ -246,6 +250,9 @@ class ConeProblem:
         d["cycles"] = dict(zip(["equilibrate", "start_point", "residuals", "scale_assemble", "factor", "kkt_solves",
                                 "linesearch_update", "total", "ldl_forward", "ldl_backward", "ldl_count",
                                 "factor_count"], [int(v) for v in buf[8:20]]))
+        fc = d["cycles"]["factor_count"]
+        d["cycles"]["factor_count"] = fc & 0xffffffff      # interior-point iterations of CTA 0
+        d["cycles"]["factor_retries"] = fc >> 32           # factorisations repeated with a larger static regularisation
         return d
 
     def level_profile(self):
@@ -261,6 +268,18 @@ class ConeProblem:
         if getattr(self, "c", None) is not None and self.c.value:
             self.lib.scpb_cone_free(self.c)
             self.c = C.c_void_p()
+
+    def debug_kkt_solve_dev(self, Avals, Gvals, wm, delta, rhs):
+        """Test hook: one reduced-KKT assemble + factor + solve on the device for a batch (see include/scpb.h)."""
+        Avals, pA = _f64(Avals); Gvals, pG = _f64(Gvals); wm, pw = _f64(wm); rhs, pr = _f64(rhs)
+        B = rhs.shape[0]
+        assert rhs.shape == (B, self.n + self.p)
+        sol = np.zeros_like(rhs)
+        bad = np.zeros(B, dtype=np.int32)
+        rc = self.lib.scpb_debug_kkt_solve_dev(self.c, B, pA, pG, pw, float(delta), pr, sol.ctypes.data_as(_dp),
+                                               bad.ctypes.data_as(_ip))
+        self.hd._check(rc, "scpb_debug_kkt_solve_dev")
+        return sol, bad
 
     def solve(self, Avals, Gvals, c, b, h, **opts):
         """Batched solve; arrays are (B, nnzA), (B, nnzG), (B, n), (B, p), (B, m)."""
@@ -299,12 +318,6 @@ def debug_kkt_solve(A, G, l, soc_dims, perm, Avals, Gvals, wm, delta, rhs, delta
     Av, pAv = _f64(Avals); Gv, pGv = _f64(Gvals); wmv, pwm = _f64(wm); r, pr = _f64(rhs)
     sol = np.zeros(n + p)
     info = (C.c_int64 * 8)()
-    if supernodal == "emu":
-        rc = lib.scpb_debug_kkt_solve_sn_emu(n, p, m, a0[1], a1[1], g0[1], g1[1], int(l), len(soc_dims), sd[1], pm[1],
-                                             pAv, pGv, pwm, float(delta), float(delta_dyn), pr, sol.ctypes.data_as(_dp), info)
-        if rc != 0:
-            raise ScpbError(f"scpb_debug_kkt_solve_sn_emu failed ({rc})")
-        return sol, dict(zip(("supernodes", "sn_levels", "panel_doubles", "update_entries"), [int(v) for v in info[:4]]))
     if supernodal:
         rc = lib.scpb_debug_kkt_solve_sn(n, p, m, a0[1], a1[1], g0[1], g1[1], int(l), len(soc_dims), sd[1], pm[1],
                                          pAv, pGv, pwm, float(delta), float(delta_dyn), pr, sol.ctypes.data_as(_dp), info)
