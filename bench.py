@@ -5,11 +5,12 @@
   python bench.py --impl reference --gpus N --steps K ...   reference arm (CPU oracle port, all host threads)
 
 Workload (config.workload): BASELINE.json's north-star case -- starship_flip PTR, N=100 nodes, Nsub=100,
-256 randomly perturbed initial guesses ("seeds") per GPU, fp64.  One "step" = one complete batched PTR solve
+256 randomly perturbed initial guesses ("seeds"), fp64.  One "step" = one complete batched PTR solve
 of those seeds (discretize! + formulate + conic solve + discretize! + stopping test, in lock step until every
-seed stops); the metric is SCP iterations per second = sum over seeds of PTR iterations / time.
-Seeds are independent, so N GPUs each take their own 256 seeds ("scaling": "weak"); the only collective
-is the final NCCL all_gather of the per-seed results.
+seed stops) INCLUDING the final gather; the metric is SCP iterations per second = sum over seeds of PTR iterations / time.
+Seeds are independent: with N GPUs the 256 seeds are cut into blocks of ceil(256/N) per rank (SURVEY 8(e);
+"scaling": "strong"), no collective on the data path, one NCCL all_gather of the per-seed results at the end, inside
+the timed region (scptoolbox.jl_b200/sharded.py).  --weak keeps 256 seeds per GPU instead ("scaling": "weak").
 """
 from __future__ import annotations
 
@@ -37,7 +38,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="seeds per GPU")
+    ap.add_argument("--batch", type=int, default=256, help="seeds in the batch (per GPU with --weak)")
+    ap.add_argument("--weak", action="store_true", help="weak scaling: --batch seeds on EVERY GPU (default: strong, "
+                                                        "the batch is cut into ceil(batch/N) seeds per GPU)")
     ap.add_argument("--N", type=int, default=100)
     ap.add_argument("--Nsub", type=int, default=100)
     ap.add_argument("--cpu-seeds", type=int, default=0, help="seeds in the CPU sample (0 = one per host thread)")
@@ -116,15 +119,26 @@ SCVX = dict(iter_max=100, lam=5e2, rho_0=0.0, rho_1=0.1, rho_2=0.7, beta_sh=2.0,
 ALGO = "ptr"
 
 
-def make_seeds(base, Sx, Su, nb, seed):
-    """Synthetic seeds: the nominal guess plus N(0, 0.01*range) perturbations of states and inputs
-    and +-2 % of the parameters; seed 0 of rank 0 is the unperturbed nominal guess."""
-    rng = np.random.default_rng(seed)
+def make_seeds(base, Sx, Su, nb, seed, cx=None, cu=None):
+    """Synthetic seeds as SURVEY 8(d) specifies them for C3: the nominal guess with x += 0.05*Sx*N(0,1),
+    u += 0.05*Su*N(0,1) clipped to the advised ranges [c, c+S], and the two time-dilation parameters (t1, t2) drawn from
+    U[0.8, 1.2] x nominal (the switch state xs stays nominal); seed 0 of stream 0 is the unperturbed nominal guess."""
+    rng = np.random.default_rng(0x5C90 + seed)
     x, u, p = base
-    X = np.array([x + (0.01 * Sx * rng.standard_normal(x.shape) if (b or seed) else 0.0) for b in range(nb)])
-    U = np.array([u + (0.01 * Su * rng.standard_normal(u.shape) if (b or seed) else 0.0) for b in range(nb)])
-    P = np.array([p * (1 + (0.02 * rng.uniform(-1, 1, p.shape) if (b or seed) else 0.0)) for b in range(nb)])
-    return X, U, P
+    X, U, P = [], [], []
+    for b in range(nb):
+        pert = bool(b or seed)
+        xb = x + (0.05 * Sx * rng.standard_normal(x.shape) if pert else 0.0)
+        ub = u + (0.05 * Su * rng.standard_normal(u.shape) if pert else 0.0)
+        if pert and cx is not None:
+            xb = np.clip(xb, cx, cx + Sx)
+        if pert and cu is not None:
+            ub = np.clip(ub, cu, cu + Su)
+        pb = np.array(p, dtype=float)
+        if pert:
+            pb[:2] = pb[:2] * rng.uniform(0.8, 1.2, 2)
+        X.append(xb); U.append(ub); P.append(pb)
+    return np.array(X), np.array(U), np.array(P)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -180,7 +194,7 @@ def run_reference(args, rank):
     from oracle import ptr as optr
     sc = optr.Scaling(pb)
     nseeds = args.cpu_seeds or min(args.batch, 2 * cores)
-    X, U, P = make_seeds(g, sc.Sx, sc.Su, nseeds, 0)
+    X, U, P = make_seeds(g, sc.Sx, sc.Su, nseeds, 0, sc.cx, sc.cu)      # the first seeds of the GPU arm's batch
     vals, walls = [], []
     cpu_run(args.N, args.Nsub, pb.hs, X[:min(8, nseeds)], U[:min(8, nseeds)], P[:min(8, nseeds)], min(cores, 8))  # warm-up
     for _ in range(args.steps):
@@ -190,9 +204,11 @@ def run_reference(args, rank):
     val = sum(vals) / tot
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
             "config": {"workload": f"starship_flip {args.algo.upper()} N={args.N} Nsub={args.Nsub}",
-                       "batch_per_gpu": args.batch, "algorithm_constants": (SCVX if args.algo == "scvx" else PTR)},
+                       "batch_total": args.batch * (args.gpus if args.weak else 1),
+                       "algorithm_constants": (SCVX if args.algo == "scvx" else PTR)},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{nseeds} of {args.batch} seeds per step, one single-threaded process per core "
                                        f"(oracle: C discretize + Python formulate + HiGHS LP); cores = "
@@ -200,6 +216,13 @@ def run_reference(args, rank):
                              "phase_cpu_seconds": ph},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def k1_flops_per_seed(N, Nsub, nx, nu, np_):
+    """algorithmic fp64 work of one discretize! call for one seed."""
+    V = nx * (2 + 2 * nx + 2 * nu + np_)
+    per = 2 * nx ** 3 + (8.0 / 3.0) * nx ** 3 + 2 * nx ** 2 * (2 * nu + np_ + 1 + nx) + 2 * nx * (nx + nu + np_) + 8 * V
+    return (N - 1) * (Nsub - 1) * 4 * per
 
 
 def run_ours(args, rank, local_rank, world):
@@ -213,7 +236,9 @@ def run_ours(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     tc = torch.cuda
-    N, Nsub, B = args.N, args.Nsub, args.batch
+    dev = torch.device("cuda", local_rank)
+    N, Nsub = args.N, args.Nsub
+    Btot = args.batch * world if args.weak else args.batch      # seeds in the whole job
     h = pkg.Handle(local_rank)
     ex = pkg.examples.starship
     mdl = ex.StarshipProblem()
@@ -228,7 +253,10 @@ def run_ours(args, rank, local_rank, world):
                                   solver_opts={"verbose": 0, "maxit": 100}, **PTR)
     base = traj.guess(N)                     # nominal guess (GPU SOCP batch); outside the timed region
     pbm = algo.create(pars, traj, h)
-    X, U, P = make_seeds(base, pbm.scale.Sx, pbm.scale.Su, B, rank)
+    sc = pbm.scale
+    X, U, P = make_seeds(base, sc.Sx, sc.Su, Btot, 0, sc.cx, sc.cu)      # the whole batch, identical on every rank
+    lo, hi = pkg.sharded.shard_bounds(Btot, world, rank)
+    Bloc = hi - lo
     info = pbm.cone.info()
 
     def barrier():
@@ -240,43 +268,43 @@ def run_ours(args, rank, local_rank, world):
     W = max(args.warmup, 3)
     for _ in range(W):
         l2_flush.zero_()
-        sol = algo.solve(pbm, (X, U, P))
+        sol, loc = pkg.sharded.solve_sharded(algo, pbm, (X, U, P), dist=dist, device=dev)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     n0 = h.launches
-    dev_t, wall_t, its, ipm, phases = 0.0, 0.0, 0, 0, {"discretize": 0.0, "formulate": 0.0, "solve": 0.0, "overhead": 0.0}
-    lock = 0
+    dev_t, wall_t, ipm, phases = 0.0, 0.0, 0, {"discretize": 0.0, "formulate": 0.0, "solve": 0.0, "overhead": 0.0}
+    its, lock = 0, 0
     barrier()
     for _ in range(args.steps):
         l2_flush.zero_(); tc.synchronize()
+        if dist is not None:
+            dist.barrier()
         t0 = time.perf_counter()
-        sol = algo.solve(pbm, (X, U, P))      # host buffers in, host buffers out: the reference-facing call
+        # the reference-facing call: host buffers in, host buffers out; shard -> device loop -> NCCL all_gather
+        sol, loc = pkg.sharded.solve_sharded(algo, pbm, (X, U, P), dist=dist, device=dev)
         wall_t += time.perf_counter() - t0
-        dev_t += sol.timing["total"]          # CUDA events on the library's stream, H2D/D2H copies excluded
-        its += int(sol.iterations.sum())
-        ipm += sol.timing["ipm_iterations"]; lock += sol.timing["lockstep_iterations"]
-        for k in phases:
-            phases[k] += sol.timing[k]
+        its += int(sol.iterations.sum())     # every rank holds the gathered whole-job result
+        if loc is not None:
+            dev_t += loc.timing["total"]     # CUDA events on the library's stream, H2D/D2H copies and the gather excluded
+            ipm += loc.timing["ipm_iterations"]; lock += loc.timing["lockstep_iterations"]
+            for k in phases:
+                phases[k] += loc.timing[k]
     barrier()
     launches = h.launches - n0
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([dev_t, wall_t], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([float(its)], dtype=torch.float64, device="cuda")
-    solved = torch.tensor([float(sum(s == "SCP_SOLVED" for s in sol.status))], dtype=torch.float64, device="cuda")
+    ln = torch.tensor([float(launches)], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        dist.all_reduce(solved, op=dist.ReduceOp.SUM)
-        # the path's only collective: gather the converged trajectories on every rank (K7)
-        res = torch.from_numpy(np.concatenate([sol.xd.reshape(B, -1), sol.ud.reshape(B, -1), sol.p], axis=1)).cuda()
-        allres = [torch.empty_like(res) for _ in range(world)]
-        dist.all_gather(allres, res)
+        dist.all_reduce(ln, op=dist.ReduceOp.SUM)
     dev_t, wall_t = float(t[0]), float(t[1])
     if rank == 0:
-        value = float(cnt[0]) / dev_t
-        e2e = float(cnt[0]) / wall_t
+        value = its / dev_t
+        e2e = its / wall_t
+        solved = sum(s_ == "SCP_SOLVED" for s_ in sol.status)
+        itv = sol.iterations
         # ---- roofline of the dominant kernel (k_ipm_solve): algorithmic bytes per interior-point iteration ----
         nnzK = pbm.cp["nnzA"] + pbm.cp["nnzG"]
         n_, p_, m_ = pbm.cp["n"], pbm.cp["p"], pbm.cp["m"]
@@ -293,34 +321,57 @@ def run_ours(args, rank, local_rank, world):
         ach = q_it * ipm / max(phases["solve"], 1e-12) / 1e9
         peak, peak_src = measured_peak()
         traffic = None
+        for fn in ("r2_ipm_ncu_summary.json", "r1_ipm_ncu_summary.json"):
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", fn)))["dram_bytes_per_launch"]
+                break
+            except Exception:
+                pass
+        # ---- roofline of K1 (k_discretize_foh): fp64-FMA bound; W from SURVEY 8(d), peak measured here ----
+        ncalls = lock + args.steps                           # one discretize! per lock-step iteration + the initial guess
+        w_seed = k1_flops_per_seed(N, Nsub, traj.nx, traj.nu, traj.np)
+        k1_s = phases["discretize"] / max(ncalls, 1)
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_ipm_ncu_summary.json")))["dram_bytes_per_launch"]
+            fp64_peak = h.fp64_peak()
         except Exception:
-            pass
+            fp64_peak = None
+        k1_ach = w_seed * Bloc / max(k1_s, 1e-12) / 1e12
+        roof_k1 = {"bound": "fp64", "achieved": k1_ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                   "frac": (k1_ach / fp64_peak) if fp64_peak else None, "traffic": None, "kernel": "k_discretize_foh",
+                   "kernel_ms": 1e3 * k1_s, "algorithmic_flops_per_seed_per_call": w_seed, "seeds_per_launch": Bloc,
+                   "peak_source": "measured in this run (scpb_debug_fp64_peak: register-resident fp64 FMA microkernel)",
+                   "kernel_share_of_step": phases["discretize"] / max(dev_t, 1e-12)}
         # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ----
         cpu = None
         if world == 1:
             cores = effective_cores()
-            nseeds = args.cpu_seeds or min(B, 2 * cores)
-            from oracle import ptr as optr, problems
-            pbo = problems.StarshipProblem(N); pbo.hs = mdl.hs
+            nseeds = args.cpu_seeds or min(Btot, 2 * cores)
             cits, cwall, cph, _ = cpu_run(N, Nsub, mdl.hs, X[:nseeds], U[:nseeds], P[:nseeds], min(cores, nseeds))
             cpu = {"value": cits / cwall, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{nseeds} of {B} seeds, full {args.algo.upper()} solve each, one single-threaded process per core "
+                   "sample": f"{nseeds} of {Btot} seeds, full {args.algo.upper()} solve each, one single-threaded process per core "
                              f"(oracle: C discretize + Python formulate + HiGHS LP); cores = min(visible CPUs "
                              f"{os.cpu_count()}, cgroup cpu.max quota)",
                    "phase_cpu_seconds": cph}
+        nb_in = int(X.nbytes + U.nbytes + P.nbytes)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
-                "ms_per_step": 1e3 * dev_t / args.steps, "higher_is_better": True, "scaling": "weak",
+                "ms_per_step": 1e3 * dev_t / args.steps, "higher_is_better": True,
+                "scaling": "weak" if args.weak else "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"starship_flip {args.algo.upper()} N={N} Nsub={Nsub}", "batch_per_gpu": B,
+                "config": {"workload": f"starship_flip {args.algo.upper()} N={N} Nsub={Nsub}", "batch_total": Btot,
+                           "batch_per_gpu": -(-Btot // world), "partition": "contiguous blocks of ceil(batch_total / n_gpus) seeds",
                            "algorithm_constants": (SCVX if args.algo == "scvx" else PTR),
-                           "seeds_solved": int(solved[0]), "seeds_total": B * world,
-                           "scp_iterations_per_step": float(cnt[0]) / args.steps,
+                           "seeds": "SURVEY 8(d): x += 0.05*Sx*N(0,1), u += 0.05*Su*N(0,1) clipped to the advised ranges, "
+                                    "(t1, t2) x U[0.8, 1.2]",
+                           "seeds_solved": int(solved), "seeds_total": Btot,
+                           "scp_iterations_per_step": its / args.steps,
+                           "scp_iterations_min_median_max": [int(itv.min()), float(np.median(itv)), int(itv.max())],
+                           "lockstep_iterations_per_step_rank0": lock / args.steps,
+                           "frozen_seed_fraction_rank0": 1.0 - (float(loc.iterations.sum()) / max(1, Bloc * (lock / args.steps))),
                            "l2": "256 MiB buffer written between timed steps; solver working set (1.1 GB for 256 seeds) >> L2"},
-                "gpu_launches": int(launches),
-                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(X.nbytes + U.nbytes + P.nbytes),
-                        "d2h_bytes_per_step": int(X.nbytes + U.nbytes + P.nbytes + B * (4 * 3 + 8 * 2))},
+                "gpu_launches": int(ln[0]),
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": nb_in,
+                        "d2h_bytes_per_step": int(nb_in + Btot * (4 * 3 + 8 * 2)),
+                        "includes": "H2D of the guesses, device loop, D2H of the results and the all_gather over NCCL"},
                 "ms_per_socp_solve": k_ms,
                 "phase_seconds_per_step": {k: v / args.steps for k, v in phases.items()},
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
@@ -329,7 +380,8 @@ def run_ours(args, rank, local_rank, world):
                              "ipm_iterations_per_launch": ipm / max(lock, 1), "ldl_solves_per_ipm_iteration": nsolve,
                              "kernel_share_of_step": phases["solve"] / max(dev_t, 1e-12),
                              "kernel_cycle_shares": {k: v / max(cyc["total"], 1) for k, v in cyc.items()
-                                                     if k not in ("total", "ldl_count", "factor_count")}},
+                                                     if k not in ("total", "ldl_count", "factor_count", "factor_retries")}},
+                "roofline_k1": roof_k1,
                 "cpu_baseline": cpu, "clocks": clocks}
         print(json.dumps(line))
     pbm.close()

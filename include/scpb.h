@@ -33,7 +33,10 @@ enum {
     SCPB_MODEL_STARSHIP = 3,  /* starship_flip/definition.jl:498-637;
                                  par: m, J, lcg, lcp, CD, alpha_e, rate_delay, g0, tau_s           */
     SCPB_MODEL_QUADROTOR = 4, /* quadrotor/definition.jl:140-186; par: g[3]                        */
-    SCPB_MODEL_FREEFLYER = 5  /* freeflyer/definition.jl:224-284; par: mass, J[9], Jinv[9] (col-major) */
+    SCPB_MODEL_FREEFLYER = 5, /* freeflyer/definition.jl:224-284; par: mass, J[9], Jinv[9] (col-major) */
+    SCPB_MODEL_RENDEZVOUS2D = 6 /* rendezvous_planar/definition.jl:147-243 (impulsive RCS thrust): x=[r2,v2,theta,omega],
+                                 u[0..2]=(f-,f+,f0) of 12 inputs, p=[tdil]; par: m, J, lu, lv, n.  The only pack with
+                                 impulse semantics (the reference's f/B called with a negative segment index) */
 };
 #define SCPB_MAX_PAR 64
 
@@ -65,6 +68,9 @@ int32_t scpb_model_set(scpb_handle h, int32_t model_id, const double *par, int32
                        int32_t nx, int32_t nu, int32_t np);
 
 /* ---- discretize!  (host buffers; H2D + kernel + D2H inside) ----
+ * method: SCPB_FOH (discretization.jl:235-286) or SCPB_IMPULSE (:186-193 jump, :304-340 derivs_impulse, :384-390
+ * B_k = A_k B(t_k, -k); needs a model pack with impulse semantics).  For IMPULSE dyn.B has ONE block: Bm; Bp (if
+ * given) is written as zeros.
  * t_grid[N]; xd[B][N][nx]; ud[B][N][nu]; p[B][np]; iSx_diag[nx];
  * A[B][N-1][nx*nx], Bm/Bp[B][N-1][nx*nu], F[B][N-1][nx*np], r[B][N-1][nx], E[B][N-1][nx*nx],
  * defect[B][N-1][nx], feas[B] (1 = dynamically feasible); *seconds = device time of the kernel. */
@@ -86,7 +92,10 @@ int32_t scpb_discretize_dev(scpb_handle h, int32_t method, int32_t B, int32_t N,
  * replaces src/solvers/discretization.jl:515-562 (FOH branch), called by SCPSolution (src/solvers/scp.jl:231-232,
  * res = 2*Nsub*(N-1)).  RK4 of the nonlinear dynamics over LinRange(0,1,res) from xd[:,1], the input linearly
  * interpolated over the whole grid, integration actions after every step.
- * xc[B][res][nx]: per seed Julia's column-major nx x res matrix (values of the Trajectory xc). */
+ * xc[B][res][nx]: per seed Julia's column-major nx x res matrix (values of the Trajectory xc).
+ * method SCPB_IMPULSE (:539-558): every interval restarts from the impulse-updated node state and coasts; the output
+ * has 1 + (N-1)*ceil(res/(N-1)) columns per seed (xd[:,1], then ceil(res/(N-1)) columns per interval), which is what xc
+ * must hold. */
 int32_t scpb_propagate(scpb_handle h, int32_t method, int32_t B, int32_t N, int32_t res, const double *t_grid,
                        const double *xd, const double *ud, const double *p, double *xc, double *seconds);
 
@@ -115,7 +124,10 @@ typedef struct {
 
 /* per-seed status (termination_status, program.jl:427-428): */
 enum { SCPB_CONE_OPTIMAL = 0, SCPB_CONE_ITERATION_LIMIT = 1, SCPB_CONE_NUMERICAL_ERROR = 2,
-       SCPB_CONE_ALMOST_OPTIMAL = 3 /* best iterate meets ECOS' reduced tolerances (5e-5) */ };
+       SCPB_CONE_ALMOST_OPTIMAL = 3, /* best iterate meets ECOS' reduced tolerances (5e-5) */
+       SCPB_CONE_INFEASIBLE = 4,      /* certificate (y, z): A'y + G'z ~ 0, b'y + h'z < 0  (MOI INFEASIBLE)          */
+       SCPB_CONE_DUAL_INFEASIBLE = 5  /* certificate x: Ax ~ 0, Gx + s ~ 0, c'x < 0, i.e. unbounded (MOI DUAL_INFEASIBLE,
+                                         the status compute_scaling tests for, src/solvers/scp.jl:470-473) */ };
 
 int32_t scpb_cone_setup(scpb_handle h, int32_t n, int32_t p, int32_t m,
                         const int32_t *A_rowptr, const int32_t *A_colind,
@@ -188,6 +200,10 @@ int32_t scpb_scvx_attach(scpb_ptr ptr, const scpb_scvx_desc *desc, const int32_t
 int32_t scpb_scvx_solve(scpb_ptr ptr, int32_t B, const double *xd0, const double *ud0, const double *p0,
                         const scpb_cone_opts *opts, double *xd, double *ud, double *p, int32_t *status,
                         int32_t *iters, double *J, double *deviation, int32_t *feas, double *eta, double *timing);
+
+/* Measured fp64 FMA throughput of the handle's device in TFLOP/s (a register-resident FMA microkernel, best of 3
+ * timed launches): the denominator of the discretization kernel's roofline in bench.py. */
+int32_t scpb_debug_fp64_peak(scpb_handle h, double *tflops);
 
 /* Diagnostic: per-level cycle counters of CTA 0 in the last scpb_cone_solve / scpb_ptr_solve launch, recorded
  * only when the environment variable SCPB_LEVEL_PROFILE is set: out[0..L) numeric factorisation, out[L..2L)

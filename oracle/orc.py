@@ -17,7 +17,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-MODEL_DBLINT, MODEL_ROCKET, MODEL_STARSHIP, MODEL_QUADROTOR, MODEL_FREEFLYER = 1, 2, 3, 4, 5
+MODEL_DBLINT, MODEL_ROCKET, MODEL_STARSHIP, MODEL_QUADROTOR, MODEL_FREEFLYER, MODEL_RENDEZVOUS2D = 1, 2, 3, 4, 5, 6
 MAX_PAR = 64
 
 
@@ -53,6 +53,11 @@ def lib():
         _LIB.orc_discretize_foh_batch.restype = C.c_int
         _LIB.orc_propagate_foh.argtypes = [mp, C.c_int, C.c_int, dp, dp, dp, dp, dp]
         _LIB.orc_propagate_foh.restype = C.c_int
+        _LIB.orc_discretize_impulse.argtypes = [mp, C.c_int, C.c_int, dp, dp, dp, dp, dp, C.c_double,
+                                                dp, dp, dp, dp, dp, dp, C.POINTER(C.c_int)]
+        _LIB.orc_discretize_impulse.restype = C.c_int
+        _LIB.orc_propagate_impulse.argtypes = [mp, C.c_int, C.c_int, dp, dp, dp, dp, dp]
+        _LIB.orc_propagate_impulse.restype = C.c_int
     return _LIB
 
 
@@ -153,4 +158,38 @@ def propagate(m: OrcModel, xd, ud, p, res):
     tg = t_grid(N)
     xc = np.zeros((res, m.nx))
     lib().orc_propagate_foh(C.byref(m), N, res, _p(tg), _p(xd), _p(ud), _p(p), _p(xc))
+    return xc
+
+
+def discretize_impulse(m: OrcModel, xd, ud, p, Nsub, iSx_diag, feas_tol, tg=None) -> DLTV:
+    """discretize! (IMPULSE, discretization.jl:186-193, 304-340, 384-390) for one trajectory; Bp is None."""
+    xd = np.ascontiguousarray(xd, dtype=np.float64)
+    ud = np.ascontiguousarray(ud, dtype=np.float64)
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    N = xd.shape[0]
+    nx, nu, np_ = m.nx, m.nu, m.np
+    tg = t_grid(N) if tg is None else np.ascontiguousarray(tg, dtype=np.float64)
+    iS = np.ascontiguousarray(iSx_diag, dtype=np.float64)
+    A = np.zeros((N - 1, nx * nx)); Bm = np.zeros((N - 1, nx * nu))
+    F = np.zeros((N - 1, nx * np_)); r = np.zeros((N - 1, nx)); E = np.zeros((N - 1, nx * nx))
+    dfc = np.zeros((N - 1, nx))
+    feas = C.c_int(0)
+    rc = lib().orc_discretize_impulse(C.byref(m), N, Nsub, _p(tg), _p(xd), _p(ud), _p(p), _p(iS), feas_tol,
+                                      _p(A), _p(Bm), _p(F), _p(r), _p(E), _p(dfc), C.byref(feas))
+    if rc != 0:
+        raise RuntimeError("oracle discretize failed (singular Phi)")
+    col = lambda a, rr, cc: a.reshape(N - 1, cc, rr).transpose(0, 2, 1)
+    return DLTV(col(A, nx, nx), col(Bm, nx, nu), None, col(F, nx, np_), r, col(E, nx, nx), dfc, bool(feas.value))
+
+
+def propagate_impulse(m: OrcModel, xd, ud, p, res):
+    """propagate, IMPULSE branch (discretization.jl:539-558): (1 + (N-1)*ceil(res/(N-1)), nx)."""
+    xd = np.ascontiguousarray(xd, dtype=np.float64)
+    ud = np.ascontiguousarray(ud, dtype=np.float64)
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    N = xd.shape[0]
+    tg = t_grid(N)
+    sub = -(-res // (N - 1))
+    xc = np.zeros((1 + (N - 1) * sub, m.nx))
+    lib().orc_propagate_impulse(C.byref(m), N, res, _p(tg), _p(xd), _p(ud), _p(p), _p(xc))
     return xc

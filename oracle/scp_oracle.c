@@ -310,10 +310,60 @@ static void ff_B(const orc_model *m, const double *p, double *B)
 }
 
 /* ------------------------------------------------------------------ */
+/* ---------------------------------------------------------------- planar rendezvous (impulsive RCS)
+ * rendezvous_planar/definition.jl:147-243, parameters.jl:87-111: x = [r(2) v(2) theta omega], u[0..2] = (f-, f+, f0)
+ * (the other 9 inputs are references / absolute values and do not enter the dynamics), p = [tdil];
+ * par: m, J, lu, lv, n.  xh = (1,0), yh = (0,1); uh = (-cos th, sin th), vh = (-sin th, -cos th).
+ * k < 0 selects the impulse: f returns the jump of (v, omega) only and is NOT scaled by tdil. */
+static void rdv_f(const orc_model *m, int k, const double *x, const double *u, const double *p, double *f)
+{
+    const double ms = m->par[0], J = m->par[1], lu = m->par[2], lv = m->par[3], n = m->par[4];
+    const double th = x[4], fm = u[0], fp = u[1], f0 = u[2], tdil = p[0];
+    const double uh0 = -cos(th), uh1 = sin(th), vh0 = -sin(th), vh1 = -cos(th);
+    for (int i = 0; i < 6; i++) f[i] = 0.0;
+    f[2] = ((fm + fp) * uh0 + f0 * vh0) / ms;
+    f[3] = ((fm + fp) * uh1 + f0 * vh1) / ms;
+    f[5] = ((fp - fm) * lv - f0 * lu) / J;
+    if (k >= 0) {
+        f[0] = x[2]; f[1] = x[3];
+        f[2] += 2.0 * n * x[3];                        /* (2 n yh.v) xh */
+        f[3] += 3.0 * n * n * x[1] - 2.0 * n * x[2];   /* (3 n^2 yh.r - 2 n xh.v) yh */
+        f[4] = x[5];
+        for (int i = 0; i < 6; i++) f[i] *= tdil;
+    }
+}
+static void rdv_A(const orc_model *m, const double *x, const double *u, const double *p, double *A)
+{
+    const double ms = m->par[0], n = m->par[4];
+    const double th = x[4], fm = u[0], fp = u[1], f0 = u[2], tdil = p[0];
+    /* d uh / d th = -vh = (sin th, cos th); d vh / d th = uh = (-cos th, sin th) */
+    const double duh0 = sin(th), duh1 = cos(th), dvh0 = -cos(th), dvh1 = sin(th);
+    for (int i = 0; i < 36; i++) A[i] = 0.0;
+    A[IDX(0, 2, 6)] = 1.0; A[IDX(1, 3, 6)] = 1.0;
+    A[IDX(3, 1, 6)] = 3.0 * n * n;                         /* 3 n^2 yh yh' */
+    A[IDX(2, 3, 6)] = 2.0 * n; A[IDX(3, 2, 6)] = -2.0 * n; /* 2 n (xh yh' - yh xh') */
+    A[IDX(2, 4, 6)] = ((fm + fp) * duh0 + f0 * dvh0) / ms;
+    A[IDX(3, 4, 6)] = ((fm + fp) * duh1 + f0 * dvh1) / ms;
+    A[IDX(4, 5, 6)] = 1.0;
+    for (int i = 0; i < 36; i++) A[i] *= tdil;
+}
+static void rdv_B(const orc_model *m, int k, const double *x, const double *p, double *B)
+{
+    const double ms = m->par[0], J = m->par[1], lu = m->par[2], lv = m->par[3];
+    const double th = x[4], tdil = p[0];
+    const double uh0 = -cos(th), uh1 = sin(th), vh0 = -sin(th), vh1 = -cos(th);
+    for (int i = 0; i < 6 * m->nu; i++) B[i] = 0.0;
+    B[IDX(2, 0, 6)] = uh0 / ms; B[IDX(3, 0, 6)] = uh1 / ms; B[IDX(5, 0, 6)] = -lv / J;
+    B[IDX(2, 1, 6)] = uh0 / ms; B[IDX(3, 1, 6)] = uh1 / ms; B[IDX(5, 1, 6)] = lv / J;
+    B[IDX(2, 2, 6)] = vh0 / ms; B[IDX(3, 2, 6)] = vh1 / ms; B[IDX(5, 2, 6)] = -lu / J;
+    if (k >= 0)
+        for (int i = 0; i < 6 * m->nu; i++) B[i] *= tdil;
+}
+
 void orc_f(const orc_model *m, double t, int k, const double *x, const double *u, const double *p, double *f)
 {
-    (void)k;
     switch (m->model_id) {
+    case ORC_MODEL_RENDEZVOUS2D: rdv_f(m, k, x, u, p, f); break;
     case ORC_MODEL_DBLINT: dblint_f(m, x, u, p, f); break;
     case ORC_MODEL_ROCKET: rocket_f(m, x, u, p, f); break;
     case ORC_MODEL_STARSHIP: starship_f(m, t, x, u, p, f); break;
@@ -326,6 +376,7 @@ void orc_A(const orc_model *m, double t, int k, const double *x, const double *u
 {
     (void)k;
     switch (m->model_id) {
+    case ORC_MODEL_RENDEZVOUS2D: rdv_A(m, x, u, p, A); break;
     case ORC_MODEL_DBLINT: dblint_A(m, p, A); break;
     case ORC_MODEL_ROCKET: {
         double Bc[28], pc[7];
@@ -344,8 +395,8 @@ void orc_A(const orc_model *m, double t, int k, const double *x, const double *u
 }
 void orc_B(const orc_model *m, double t, int k, const double *x, const double *u, const double *p, double *B)
 {
-    (void)k;
     switch (m->model_id) {
+    case ORC_MODEL_RENDEZVOUS2D: rdv_B(m, k, x, p, B); break;
     case ORC_MODEL_DBLINT: dblint_B(m, p, B); break;
     case ORC_MODEL_ROCKET: {
         double Ac[49], pc[7];
@@ -622,6 +673,151 @@ int orc_discretize_foh_batch(const orc_model *m, int nb, int N, int Nsub, const 
         err |= (e != 0);
     }
     return err ? -1 : 0;
+}
+
+/* ------------------------------------------------------------------ */
+/* IMPULSE discretization.  V = [x; vec(Phi); vec(PF); Pr; vec(PE)]  (DiscretizationIndices without B blocks,
+ * discretization.jl:113-144); derivs_impulse (discretization.jl:304-340): u = 0 during the coast. */
+typedef struct {
+    const orc_model *m;
+    int k, ox, oA, oF, or_, oE, len;
+    const double *p;
+    double *wk;
+    int err;
+} imp_ctx;
+
+static void derivs_impulse(imp_ctx *c, double t, const double *V, double *dV)
+{
+    const orc_model *m = c->m;
+    int nx = m->nx, nu = m->nu, np = m->np;
+    double *w = c->wk;
+    double *u0 = w;            w += nu;
+    double *f = w;             w += nx;
+    double *A = w;             w += nx * nx;
+    double *F = w;             w += nx * np;
+    double *r = w;             w += nx;
+    double *iPhi = w;          w += nx * nx;
+    double *lu = w;            w += nx * nx;
+    const double *x = &V[c->ox];
+    const double *Phi = &V[c->oA];
+    for (int i = 0; i < nu; i++) u0[i] = 0.0;
+    orc_f(m, t, c->k, x, u0, c->p, f);
+    orc_A(m, t, c->k, x, u0, c->p, A);
+    orc_F(m, t, c->k, x, u0, c->p, F);
+    for (int i = 0; i < nx; i++) {   /* r = f - A x - F p */
+        double ax = 0.0, fp = 0.0;
+        for (int j = 0; j < nx; j++) ax += A[IDX(i, j, nx)] * x[j];
+        for (int j = 0; j < np; j++) fp += F[IDX(i, j, nx)] * c->p[j];
+        r[i] = f[i] - ax - fp;
+    }
+    if (dense_inverse(nx, Phi, iPhi, lu) != 0) c->err = -1;
+    memcpy(&dV[c->ox], f, sizeof(double) * nx);
+    matmul(nx, nx, nx, A, Phi, &dV[c->oA]);
+    matmul(nx, nx, np, iPhi, F, &dV[c->oF]);
+    matmul(nx, nx, 1, iPhi, r, &dV[c->or_]);
+    memcpy(&dV[c->oE], iPhi, sizeof(double) * nx * nx);
+}
+
+static void rk4_step_imp(imp_ctx *c, double *X, double t, double tp, double *k1, double *k2, double *k3,
+                         double *k4, double *xt)
+{
+    int n = c->len;
+    double h = tp - t;
+    derivs_impulse(c, t, X, k1);
+    for (int i = 0; i < n; i++) xt[i] = X[i] + h / 2 * k1[i];
+    derivs_impulse(c, t + h / 2, xt, k2);
+    for (int i = 0; i < n; i++) xt[i] = X[i] + h / 2 * k2[i];
+    derivs_impulse(c, t + h / 2, xt, k3);
+    for (int i = 0; i < n; i++) xt[i] = X[i] + h * k3[i];
+    derivs_impulse(c, t + h, xt, k4);
+    for (int i = 0; i < n; i++) X[i] = X[i] + h / 6 * (k1[i] + 2 * k2[i] + 2 * k3[i] + k4[i]);
+}
+
+int orc_discretize_impulse(const orc_model *m, int N, int Nsub, const double *t_grid,
+                           const double *xd, const double *ud, const double *p,
+                           const double *iSx_diag, double feas_tol,
+                           double *A, double *Bm, double *F, double *r, double *E,
+                           double *defect, int *feas)
+{
+    int nx = m->nx, nu = m->nu, np = m->np;
+    imp_ctx c;
+    c.m = m; c.p = p; c.err = 0;
+    c.ox = 0; c.oA = nx; c.oF = c.oA + nx * nx; c.or_ = c.oF + nx * np; c.oE = c.or_ + nx; c.len = c.oE + nx * nx;
+    int n = c.len;
+    size_t wk_sz = (size_t)nu + nx + nx * nx + (size_t)nx * np + nx + 2 * nx * nx + 16;
+    double *buf = (double *)malloc(sizeof(double) * (6 * (size_t)n + wk_sz + nx + (size_t)nx * nu));
+    if (!buf) return -2;
+    double *V = buf, *k1 = V + n, *k2 = k1 + n, *k3 = k2 + n, *k4 = k3 + n, *xt = k4 + n;
+    c.wk = xt + n;
+    double *jump = c.wk + wk_sz, *Btk = jump + nx;
+    *feas = 1;
+    for (int k = 1; k <= N - 1; k++) {
+        const double *xk = &xd[(size_t)(k - 1) * nx], *uk = &ud[(size_t)(k - 1) * nu];
+        memset(V, 0, sizeof(double) * n);
+        for (int i = 0; i < nx; i++) V[c.oA + IDX(i, i, nx)] = 1.0;
+        /* impulse-update the state: xk_plus = xk + f(tk, -k, xk, uk, p)  (discretization.jl:186-193) */
+        orc_f(m, t_grid[k - 1], -k, xk, uk, p, jump);
+        for (int i = 0; i < nx; i++) V[c.ox + i] = xk[i] + jump[i];
+        c.k = k;
+        for (int j = 1; j < Nsub; j++) {
+            double t = linrange_at(t_grid[k - 1], t_grid[k], j - 1, Nsub - 1);
+            double tp = linrange_at(t_grid[k - 1], t_grid[k], j, Nsub - 1);
+            rk4_step_imp(&c, V, t, tp, k1, k2, k3, k4, xt);
+            integ_actions(m, V);
+        }
+        const double *Ak = &V[c.oA];
+        size_t s = (size_t)(k - 1);
+        memcpy(&A[s * nx * nx], Ak, sizeof(double) * nx * nx);
+        orc_B(m, t_grid[k - 1], -k, xk, uk, p, Btk);      /* B_k = A_k * B(tk, -k, xk, uk, p)  (:384-390) */
+        matmul(nx, nx, nu, Ak, Btk, &Bm[s * nx * nu]);
+        matmul(nx, nx, np, Ak, &V[c.oF], &F[s * nx * np]);
+        matmul(nx, nx, 1, Ak, &V[c.or_], &r[s * nx]);
+        matmul(nx, nx, nx, Ak, &V[c.oE], &E[s * nx * nx]);
+        double nrm = 0.0;
+        for (int i = 0; i < nx; i++) {
+            double d = xd[(size_t)k * nx + i] - V[c.ox + i];
+            defect[s * nx + i] = d;
+            double a = fabs(iSx_diag[i] * d);
+            if (a > nrm || a != a) nrm = a;
+        }
+        if (nrm > feas_tol) *feas = 0;
+    }
+    int err = c.err;
+    free(buf);
+    return err;
+}
+
+int orc_propagate_impulse(const orc_model *m, int N, int res, const double *t_grid,
+                          const double *xd, const double *ud, const double *p, double *xc)
+{
+    int nx = m->nx, nu = m->nu;
+    int subres = (res + (N - 1) - 1) / (N - 1);      /* ceil(Int, res / (N - 1)) */
+    double X[32], k1[32], k2[32], k3[32], k4[32], xt[32], u0[64], jump[32];
+    for (int i = 0; i < nu; i++) u0[i] = 0.0;
+    memcpy(xc, xd, sizeof(double) * nx);             /* xc_intvl[1] = xd[:, 1] */
+    size_t col = 1;
+    for (int k = 1; k <= N - 1; k++) {
+        const double *xk = &xd[(size_t)(k - 1) * nx], *uk = &ud[(size_t)(k - 1) * nu];
+        orc_f(m, t_grid[k - 1], -k, xk, uk, p, jump);
+        for (int i = 0; i < nx; i++) X[i] = xk[i] + jump[i];
+        memcpy(&xc[col * nx], X, sizeof(double) * nx); col++;
+        for (int j = 1; j < subres; j++) {
+            double t = linrange_at(t_grid[k - 1], t_grid[k], j - 1, subres - 1);
+            double tp = linrange_at(t_grid[k - 1], t_grid[k], j, subres - 1);
+            double h = tp - t;
+            orc_f(m, t, N, X, u0, p, k1);
+            for (int i = 0; i < nx; i++) xt[i] = X[i] + h / 2 * k1[i];
+            orc_f(m, t + h / 2, N, xt, u0, p, k2);
+            for (int i = 0; i < nx; i++) xt[i] = X[i] + h / 2 * k2[i];
+            orc_f(m, t + h / 2, N, xt, u0, p, k3);
+            for (int i = 0; i < nx; i++) xt[i] = X[i] + h * k3[i];
+            orc_f(m, t + h, N, xt, u0, p, k4);
+            for (int i = 0; i < nx; i++) X[i] = X[i] + h / 6 * (k1[i] + 2 * k2[i] + 2 * k3[i] + k4[i]);
+            integ_actions(m, X);
+            memcpy(&xc[col * nx], X, sizeof(double) * nx); col++;
+        }
+    }
+    return 0;
 }
 
 /* propagate, FOH branch (discretization.jl:533-538): RK4 of f over LinRange(0,1,res)

@@ -25,7 +25,8 @@ enum {
     ORC_MODEL_ROCKET = 2,   /* Mars powered-descent LTI rocket  (rocket_landing/parameters.jl:110) */
     ORC_MODEL_STARSHIP = 3, /* starship_flip/definition.jl:498-637                                 */
     ORC_MODEL_QUADROTOR = 4,/* quadrotor/definition.jl:140-186                                     */
-    ORC_MODEL_FREEFLYER = 5 /* freeflyer/definition.jl:224-284                                     */
+    ORC_MODEL_FREEFLYER = 5,/* freeflyer/definition.jl:224-284                                     */
+    ORC_MODEL_RENDEZVOUS2D = 6 /* rendezvous_planar/definition.jl:147-243: impulsive RCS thrust (k < 0 = the jump) */
 };
 
 #define ORC_MAX_PAR 64
@@ -63,6 +64,19 @@ int orc_discretize_foh_batch(const orc_model *m, int nb, int N, int Nsub, const 
 /* propagate (discretization.jl:515-562, FOH branch): full RK4 roll-out on res points */
 int orc_propagate_foh(const orc_model *m, int N, int res, const double *t_grid,
                       const double *xd, const double *ud, const double *p, double *xc);
+
+/* discretize! with IMPULSE (discretization.jl:186-193 jump, :304-340 derivs_impulse, :384-390 B_k = A_k B(t_k,-k)):
+ * same arrays as the FOH variant; Bp is not written (dyn.B has one block for IMPULSE). */
+int orc_discretize_impulse(const orc_model *m, int N, int Nsub, const double *t_grid,
+                           const double *xd, const double *ud, const double *p,
+                           const double *iSx_diag, double feas_tol,
+                           double *A, double *Bm, double *F, double *r, double *E,
+                           double *defect, int *feas);
+
+/* propagate, IMPULSE branch (discretization.jl:539-558): per interval RK4 of the coasting dynamics from the
+ * impulse-updated state on LinRange(t_k, t_k+1, subres), subres = ceil(res/(N-1)); xc is nx*(1+(N-1)*subres). */
+int orc_propagate_impulse(const orc_model *m, int N, int res, const double *t_grid,
+                          const double *xd, const double *ud, const double *p, double *xc);
 
 #ifdef __cplusplus
 }

@@ -139,20 +139,23 @@ int scpb_internal_cone_run(scpb_cone_s *c, const IpmOpts &o, const int *skip)
     const size_t vbytes = sizeof(double) * (size_t)c->S.nk * c->D.G;
     c->D.vsmem = (smem + vbytes <= 200 * 1024 && !getenv("SCPB_NO_VSMEM")) ? 1 : 0;   // env: force the global-memory sweep (tests)
     if (c->D.vsmem) smem += vbytes;
-    // supernodal factorisation / substitutions (csrc/conic_sn.cuh): every panel must fit a lane group and the
-    // substitution vector must live in shared memory; SCPB_SUPERNODAL=0 selects the scalar level-scheduled programs
+    // supernodal factorisation / substitutions (csrc/conic_sn.cuh), SCPB_SUPERNODAL=1: every panel must fit a lane
+    // group and the substitution vector must live in shared memory.  Correct on the device (tests/test_conic_gpu.py)
+    // but measured slower than the scalar level-scheduled programs on the bench KKT (profiles/r2_experiments.md), so
+    // the scalar programs stay the default.
     {
         const char *e = getenv("SCPB_SUPERNODAL");
-        c->D.sn = (c->sn_ok && c->D.vsmem && !(e && e[0] == '0')) ? 1 : 0;
+        c->D.sn = (c->sn_ok && c->D.vsmem && e && e[0] == '1') ? 1 : 0;
     }
     c->D.lvl_prof = (c->d_prof && getenv("SCPB_LEVEL_PROFILE")) ? 1 : 0;   // diagnostic: per-level cycle counters of CTA 0
-    if (o.threads >= 1024) {
-        SCPB_CUDA(h, cudaFuncSetAttribute(k_ipm_solve<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_ipm_solve<1024><<<ng, 1024, smem, h->stream>>>(c->P, c->D, o);
-    } else {
-        SCPB_CUDA(h, cudaFuncSetAttribute(k_ipm_solve<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_ipm_solve<512><<<ng, 512, smem, h->stream>>>(c->P, c->D, o);
+#define SCPB_LAUNCH_IPM(NT_, SN_)                                                                                        \
+    {                                                                                                                    \
+        SCPB_CUDA(h, cudaFuncSetAttribute(k_ipm_solve<NT_, SN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_ipm_solve<NT_, SN_><<<ng, NT_, smem, h->stream>>>(c->P, c->D, o);                                              \
     }
+    if (o.threads >= 1024) { if (c->D.sn) SCPB_LAUNCH_IPM(1024, 1) else SCPB_LAUNCH_IPM(1024, 0) }
+    else { if (c->D.sn) SCPB_LAUNCH_IPM(512, 1) else SCPB_LAUNCH_IPM(512, 0) }
+#undef SCPB_LAUNCH_IPM
     h->launches++;
     SCPB_CUDA(h, cudaGetLastError());
     return SCPB_OK;

@@ -73,7 +73,7 @@ struct IpmData {  // group-blocked device arrays, all for B seeds
     long long *prof;   // [8] cycle counters of CTA 0: equilibrate, init, residuals, scaling+assemble, factor, solves, line search+update, total
 };
 
-enum { IPM_OPTIMAL = 0, IPM_MAXIT = 1, IPM_NUMERICAL = 2, IPM_ALMOST = 3 };
+enum { IPM_OPTIMAL = 0, IPM_MAXIT = 1, IPM_NUMERICAL = 2, IPM_ALMOST = 3, IPM_PINF = 4, IPM_DINF = 5 };
 
 #define IPM_MAXG 8
 #define IPM_NT_MAX 1024
@@ -95,6 +95,7 @@ struct Ctx {
     long long *lprof;                   // thread 0 of CTA 0: per-level cycles [factor | forward | backward][nlevels]
     int sn;                             // supernodal mode
     double *Ypanels;                    // supernodal mode: this group's panels (the Y array, one seed after the other)
+    const struct SnArgs *s_sn;          // supernodal mode: argument block of the panel kernels, in shared memory
     size_t ysize;                       // doubles per seed of the Y array
     const int *s_done;                  // shared: per-seed "finished" flags (finished seeds skip the per-seed panel work)
     double *s_delta;                    // shared: per-seed static regularisation
@@ -103,8 +104,8 @@ struct Ctx {
     double *vs;                         // shared-memory substitution vector (nullptr: use global memory)
     double *Lrow;                       // row-ordered copy of the scaled factor (forward substitution)
     double reftol;                      // iterative refinement stops once |residual|_inf <= reftol*(1+|rhs|_inf)
-    double *red;   // shared: [8][IPM_NT_MAX/32][IPM_MAXG]
-    double *out;   // shared: [8][IPM_MAXG]
+    double *red;   // shared: [10][IPM_NT_MAX/32][IPM_MAXG]
+    double *out;   // shared: [10][IPM_MAXG]
 };
 
 // per-seed reduction of up to K values; op 0 = sum, 1 = min, 2 = max. Result in c.out[k*MAXG + sg].
@@ -157,73 +158,22 @@ __device__ __forceinline__ double lanes_sum(const Ctx &c, double a)
     return a;
 }
 
-// Sparse dot products of the residual / refinement SpMVs.  Rows are short (2-10 entries) and every entry costs two
-// dependent loads (index, then operand), so a row is consumed in chunks of four entries whose loads are all issued
-// before the first use (clamped indices instead of branches); the first chunk is straight-line code, which lets the
-// compiler overlap it with the neighbouring dot product of the same loop body.  Summation order = storage order.
-#define IPM_CHUNK4(K, N_, IDX0, IDX1, IDX2, IDX3)                                                 \
-    const int j0_ = (K), j1_ = (N_) > 1 ? (K) + 1 : (K), j2_ = (N_) > 2 ? (K) + 2 : (K), j3_ = (N_) > 3 ? (K) + 3 : (K);
-// (M x)_r, M in CSR with group-blocked values
-__device__ __forceinline__ double row_dot(const int *__restrict__ rp, const int *__restrict__ ci,
-                                          const double *__restrict__ Mv, const double *__restrict__ x, int r, int G, int sg)
+// y = alpha * (M x) [+ y0]  row-wise CSR; M values Mv group-blocked
+// (chunked variants with four entries in flight were measured and are slower: inside the solver body the 64-register
+// budget of a 1024-thread CTA spills them, profiles/r2_experiments.md)
+__device__ __forceinline__ double row_dot(const int *rp, const int *ci, const double *Mv, const double *x, int r,
+                                          int G, int sg)
 {
-    const int k0 = rp[r], k1 = rp[r + 1];
     double acc = 0.0;
-    {
-        const int n_ = k1 - k0;
-        IPM_CHUNK4(k0, n_, 0, 0, 0, 0)
-        const int c0 = ci[j0_], c1 = ci[j1_], c2 = ci[j2_], c3 = ci[j3_];
-        const double m0 = Mv[GI(j0_)], m1 = Mv[GI(j1_)], m2 = Mv[GI(j2_)], m3 = Mv[GI(j3_)];
-        const double x0 = x[GI(c0)], x1 = x[GI(c1)], x2 = x[GI(c2)], x3 = x[GI(c3)];
-        if (n_ > 0) acc = m0 * x0;
-        if (n_ > 1) acc = fma(m1, x1, acc);
-        if (n_ > 2) acc = fma(m2, x2, acc);
-        if (n_ > 3) acc = fma(m3, x3, acc);
-    }
-    for (int k = k0 + 4; k < k1; k += 4) {
-        const int n_ = k1 - k;
-        IPM_CHUNK4(k, n_, 0, 0, 0, 0)
-        const int c0 = ci[j0_], c1 = ci[j1_], c2 = ci[j2_], c3 = ci[j3_];
-        const double m0 = Mv[GI(j0_)], m1 = Mv[GI(j1_)], m2 = Mv[GI(j2_)], m3 = Mv[GI(j3_)];
-        const double x0 = x[GI(c0)], x1 = x[GI(c1)], x2 = x[GI(c2)], x3 = x[GI(c3)];
-        acc = fma(m0, x0, acc);
-        if (n_ > 1) acc = fma(m1, x1, acc);
-        if (n_ > 2) acc = fma(m2, x2, acc);
-        if (n_ > 3) acc = fma(m3, x3, acc);
-    }
+    for (int k = rp[r]; k < rp[r + 1]; k++) acc = fma(Mv[GI(k)], x[GI(ci[k])], acc);
     return acc;
 }
 // (M' y)_v via the transposed pattern with value map
-__device__ __forceinline__ double col_dot(const int *__restrict__ trp, const int *__restrict__ tri,
-                                          const int *__restrict__ tvi, const double *__restrict__ Mv,
-                                          const double *__restrict__ y, int v, int G, int sg)
+__device__ __forceinline__ double col_dot(const int *trp, const int *tri, const int *tvi, const double *Mv,
+                                          const double *y, int v, int G, int sg)
 {
-    const int k0 = trp[v], k1 = trp[v + 1];
     double acc = 0.0;
-    {
-        const int n_ = k1 - k0;
-        IPM_CHUNK4(k0, n_, 0, 0, 0, 0)
-        const int r0 = tri[j0_], r1 = tri[j1_], r2 = tri[j2_], r3 = tri[j3_];
-        const int v0 = tvi[j0_], v1 = tvi[j1_], v2 = tvi[j2_], v3 = tvi[j3_];
-        const double m0 = Mv[GI(v0)], m1 = Mv[GI(v1)], m2 = Mv[GI(v2)], m3 = Mv[GI(v3)];
-        const double y0 = y[GI(r0)], y1 = y[GI(r1)], y2 = y[GI(r2)], y3 = y[GI(r3)];
-        if (n_ > 0) acc = m0 * y0;
-        if (n_ > 1) acc = fma(m1, y1, acc);
-        if (n_ > 2) acc = fma(m2, y2, acc);
-        if (n_ > 3) acc = fma(m3, y3, acc);
-    }
-    for (int k = k0 + 4; k < k1; k += 4) {
-        const int n_ = k1 - k;
-        IPM_CHUNK4(k, n_, 0, 0, 0, 0)
-        const int r0 = tri[j0_], r1 = tri[j1_], r2 = tri[j2_], r3 = tri[j3_];
-        const int v0 = tvi[j0_], v1 = tvi[j1_], v2 = tvi[j2_], v3 = tvi[j3_];
-        const double m0 = Mv[GI(v0)], m1 = Mv[GI(v1)], m2 = Mv[GI(v2)], m3 = Mv[GI(v3)];
-        const double y0 = y[GI(r0)], y1 = y[GI(r1)], y2 = y[GI(r2)], y3 = y[GI(r3)];
-        acc = fma(m0, y0, acc);
-        if (n_ > 1) acc = fma(m1, y1, acc);
-        if (n_ > 2) acc = fma(m2, y2, acc);
-        if (n_ > 3) acc = fma(m3, y3, acc);
-    }
+    for (int k = trp[v]; k < trp[v + 1]; k++) acc = fma(Mv[GI(tvi[k])], y[GI(tri[k])], acc);
     return acc;
 }
 
@@ -261,7 +211,7 @@ __device__ void apply_w2(const IpmProgram &P, const Ctx &c, const double *wm, co
 }
 
 // ---- LDL' : assemble, factor, solve ----
-__device__ void kkt_assemble(const IpmProgram &P, const Ctx &c, const IpmData &D, const double *Av, const double *Gv,
+__device__ __forceinline__ void kkt_assemble(const IpmProgram &P, const Ctx &c, const IpmData &D, const double *Av, const double *Gv,
                              const double *wmx, double *Y, double delta)
 {
     const int G = c.G, sg = c.sg;
@@ -271,17 +221,9 @@ __device__ void kkt_assemble(const IpmProgram &P, const Ctx &c, const IpmData &D
     for (int t = c.slot; t < ntgt; t += c.nslots) {
         double acc = dl * (double)P.as_sign[t];
         const int src = P.as_src[t];
-        const int k0 = P.as_ptr[t], k1 = P.as_ptr[t + 1];
         if (src >= 0) acc += Av[GI(src)];
-        for (int k = k0; k < k1; k += 2) {   // two triples in flight
-            const bool two = k + 1 < k1;
-            const int a0 = P.as_a[k], b0 = P.as_b[k], c0 = P.as_c[k];
-            const int a1 = two ? P.as_a[k + 1] : a0, b1 = two ? P.as_b[k + 1] : b0, c1 = two ? P.as_c[k + 1] : c0;
-            const double g0 = Gv[GI(a0)], h0 = Gv[GI(b0)], w0 = wmx[GI(c0)];
-            const double g1 = Gv[GI(a1)], h1 = Gv[GI(b1)], w1 = wmx[GI(c1)];
-            acc = fma(g0 * h0, w0, acc);
-            if (two) acc = fma(g1 * h1, w1, acc);
-        }
+        for (int k = P.as_ptr[t]; k < P.as_ptr[t + 1]; k++)
+            acc = fma(Gv[GI(P.as_a[k])] * Gv[GI(P.as_b[k])], wmx[GI(P.as_c[k])], acc);
         if (D.sn) Y[(size_t)sg * c.ysize + P.sn_pos[t]] = acc;   // supernodal mode: straight into this seed's dense panels
         else Y[GI(t)] = acc;
     }
@@ -301,14 +243,16 @@ struct FactorArgs {
     const int4 *fa_item, *fb_item;
     const int2 *ft_op;
     double *Y, *Ls, *Lrow, *invD;   // group-blocked, already offset to this CTA's group
-    const double *s_delta;          // shared: per-seed static regularisation (pivot threshold delta/2)
-    int *s_bad;                     // shared: per-seed "inertia lost" flags
-    double rho_min, bad_abs;
     int o_fal, o_faR, o_fbl;        // offsets (ints) into the dynamic shared memory window
     int nl, nnzLd, G, sg, slot, nslots;
     long long *lprof;
 };
 extern __shared__ int ipm_smem[];
+// per-seed regularisation state of the factorisation, file-scope shared so that the noinline level programs reach it
+// without widening their by-value argument blocks (a block above 128 bytes is passed through local memory)
+__shared__ double ipm_s_delta[IPM_MAXG];   // static regularisation of each seed of the group
+__shared__ int ipm_s_bad[IPM_MAXG];        // "inertia lost" flags raised by the factorisation
+__shared__ double ipm_s_reg[2];            // rho_min, bad_abs
 
 __device__ __noinline__ void kkt_factor_levels(const FactorArgs a)
 {
@@ -385,10 +329,10 @@ __device__ __noinline__ void kkt_factor_levels(const FactorArgs a)
             double d = isd ? e : __ldcg(&a.Y[(size_t)(a.nnzLd + sc.y) * G + sg]);
             const int4 cur = sc;
             if (w + nslots < b1) sc = a.fb_item[w + nslots];
-            const double dl_ = a.s_delta[sg];
+            const double dl_ = ipm_s_delta[sg];
             if (!(sgn * d > 0.5 * dl_)) {   // dynamic regularisation keeps the expected inertia
-                if (isd && !(fabs(d) <= a.bad_abs)) a.s_bad[sg] = 1;   // not a small pivot: cancellation destroyed it
-                d = sgn * fmax(dl_, a.rho_min);
+                if (isd && !(fabs(d) <= ipm_s_reg[1])) ipm_s_bad[sg] = 1;   // not a small pivot: cancellation destroyed it
+                d = sgn * fmax(dl_, ipm_s_reg[0]);
             }
             const double inv = 1.0 / d;
             if (isd) a.invD[(size_t)cur.y * G + sg] = inv;
@@ -413,91 +357,121 @@ __device__ __noinline__ void kkt_factor_levels(const FactorArgs a)
 // supernodal numeric factorisation: one thread (small leaves) or one lane group (8, 16 or 32 lanes, by panel height)
 // per (supernode, seed) item, one barrier per supernodal level; panels live in registers (conic_sn.cuh).  The
 // descriptor of a unit's next item is requested before the current item is worked on.
+// Like the scalar programs these are separate (noinline) functions with BY-VALUE arguments: passing the solver's
+// context or the kernel parameters by reference would force them into local memory for the whole kernel.
+struct SnArgs {
+    SnProgram sn;
+    double *Y, *invD, *vs;          // this group's panels (one seed after the other), 1/D (group-blocked), shared vector
+    const int *s_done;              // shared: finished seeds are skipped
+    const double *s_delta;          // shared: per-seed static regularisation
+    int *s_bad;                     // shared: per-seed "inertia lost" flags
+    double rho_min, bad_abs;
+    size_t ysize;
+    int G, tid, nwarps, nls;        // nls: scalar level count (stride of the profile arrays)
+    long long *lprof;
+};
+
 template <int GS, class F>
-__device__ __forceinline__ void sn_for_items(const IpmProgram &P, const Ctx &c, int lv, int cls, F &&f)
+__device__ __forceinline__ void sn_for_items(const SnArgs &a, int lv, int cls, F &&f)
 {
-    const int i0 = P.sn.cls_ptr[5 * lv + cls], nit = (P.sn.cls_ptr[5 * lv + cls + 1] - i0) * c.G;
-    const int gsh = 31 - __clz(c.G);
+    const int i0 = a.sn.cls_ptr[5 * lv + cls], nit = (a.sn.cls_ptr[5 * lv + cls + 1] - i0) * a.G;
+    const int gsh = 31 - __clz(a.G);
     int unit, nunits;
-    if (GS == 1) { unit = c.tid; nunits = c.nwarps * 32; }
-    else { constexpr int GPW = 32 / (GS == 1 ? 32 : GS); unit = (c.tid >> 5) * GPW + ((c.tid & 31) / (GS == 1 ? 32 : GS)); nunits = c.nwarps * GPW; }
+    if (GS == 1) { unit = a.tid; nunits = a.nwarps * 32; }
+    else { constexpr int GPW = 32 / (GS == 1 ? 32 : GS); unit = (a.tid >> 5) * GPW + ((a.tid & 31) / (GS == 1 ? 32 : GS)); nunits = a.nwarps * GPW; }
     int it = unit;
     int4 d0 = make_int4(0, 0, 0, 0), d1 = d0;
-    if (it < nit) { const int q = 2 * (i0 + (it >> gsh)); d0 = P.sn.desc[q]; d1 = P.sn.desc[q + 1]; }
+    if (it < nit) { const int q = 2 * (i0 + (it >> gsh)); d0 = a.sn.desc[q]; d1 = a.sn.desc[q + 1]; }
     while (it < nit) {
-        const int sgi = it & (c.G - 1);
+        const int sgi = it & (a.G - 1);
         const int4 c0 = d0, c1 = d1;
         const int nx = it + nunits;
-        if (nx < nit) { const int q = 2 * (i0 + (nx >> gsh)); d0 = P.sn.desc[q]; d1 = P.sn.desc[q + 1]; }
-        if (!c.s_done[sgi]) f(c0, c1, sgi);    // lane groups: uniform within the group
+        if (nx < nit) { const int q = 2 * (i0 + (nx >> gsh)); d0 = a.sn.desc[q]; d1 = a.sn.desc[q + 1]; }
+        if (!a.s_done[sgi]) f(c0, c1, sgi);    // lane groups: uniform within the group
         it = nx;
     }
 }
 
-__device__ __noinline__ void kkt_factor_sn(const IpmProgram &P, const Ctx &c, double *Y, double *invD)
+__device__ __noinline__ void kkt_factor_sn(const SnArgs *ap, int tid)
 {
-    const int G = c.G;
-    long long tl_ = c.lprof ? clock64() : 0;
-    for (int lv = 0; lv < P.sn.nlevels; lv++) {
-        sn_for_items<1>(P, c, lv, 0, [&](const int4 d0, const int4 d1, int sgi) {
-            const double dl = c.s_delta[sgi];
-            sn1_factor_panel(P.sn, d0, d1, Y + (size_t)sgi * c.ysize, invD, G, sgi, 0.5 * dl, fmax(dl, c.rho_min), c.bad_abs, &c.s_bad[sgi]); });
-        sn_for_items<8>(P, c, lv, 1, [&](const int4 d0, const int4 d1, int sgi) {
-            const double dl = c.s_delta[sgi];
-            sn_factor_panel<8>(P.sn, d0, d1, Y + (size_t)sgi * c.ysize, invD, G, sgi, 0.5 * dl, fmax(dl, c.rho_min), c.bad_abs, &c.s_bad[sgi]); });
-        sn_for_items<16>(P, c, lv, 2, [&](const int4 d0, const int4 d1, int sgi) {
-            const double dl = c.s_delta[sgi];
-            sn_factor_panel<16>(P.sn, d0, d1, Y + (size_t)sgi * c.ysize, invD, G, sgi, 0.5 * dl, fmax(dl, c.rho_min), c.bad_abs, &c.s_bad[sgi]); });
-        sn_for_items<32>(P, c, lv, 3, [&](const int4 d0, const int4 d1, int sgi) {
-            const double dl = c.s_delta[sgi];
-            sn_factor_panel<32>(P.sn, d0, d1, Y + (size_t)sgi * c.ysize, invD, G, sgi, 0.5 * dl, fmax(dl, c.rho_min), c.bad_abs, &c.s_bad[sgi]); });
+    SnArgs a = *ap;       // from shared memory (filled once per launch): nothing of the caller's goes to the stack
+    a.tid = tid;
+    if (tid != 0) a.lprof = nullptr;
+    const int G = a.G;
+    long long tl_ = a.lprof ? clock64() : 0;
+    for (int lv = 0; lv < a.sn.nlevels; lv++) {
+        sn_for_items<1>(a, lv, 0, [&](const int4 d0, const int4 d1, int sgi) {
+            const double dl = a.s_delta[sgi];
+            sn1_factor_panel(a.sn, d0, d1, a.Y + (size_t)sgi * a.ysize, a.invD, G, sgi, 0.5 * dl, fmax(dl, a.rho_min), a.bad_abs, &a.s_bad[sgi]); });
+        sn_for_items<8>(a, lv, 1, [&](const int4 d0, const int4 d1, int sgi) {
+            const double dl = a.s_delta[sgi];
+            sn_factor_panel<8>(a.sn, d0, d1, a.Y + (size_t)sgi * a.ysize, a.invD, G, sgi, 0.5 * dl, fmax(dl, a.rho_min), a.bad_abs, &a.s_bad[sgi]); });
+        sn_for_items<16>(a, lv, 2, [&](const int4 d0, const int4 d1, int sgi) {
+            const double dl = a.s_delta[sgi];
+            sn_factor_panel<16>(a.sn, d0, d1, a.Y + (size_t)sgi * a.ysize, a.invD, G, sgi, 0.5 * dl, fmax(dl, a.rho_min), a.bad_abs, &a.s_bad[sgi]); });
+        sn_for_items<32>(a, lv, 3, [&](const int4 d0, const int4 d1, int sgi) {
+            const double dl = a.s_delta[sgi];
+            sn_factor_panel<32>(a.sn, d0, d1, a.Y + (size_t)sgi * a.ysize, a.invD, G, sgi, 0.5 * dl, fmax(dl, a.rho_min), a.bad_abs, &a.s_bad[sgi]); });
         __syncthreads();
-        if (c.lprof) { const long long tn = clock64(); c.lprof[lv] += tn - tl_; tl_ = tn; }
+        if (a.lprof) { const long long tn = clock64(); a.lprof[lv] += tn - tl_; tl_ = tn; }
     }
 }
 
-// supernodal substitutions on the shared-memory vector
-__device__ __noinline__ void kkt_ldl_solve_sn(const IpmProgram &P, Ctx &c, const double *Y, const double *invD, double *v)
+// supernodal substitutions on the shared-memory vector: DIR > 0 forward (levels ascending), DIR < 0 backward
+template <int DIR>
+__device__ __noinline__ void kkt_sweep_sn(const SnArgs *ap, int tid)
+{
+    SnArgs a = *ap;
+    a.tid = tid;
+    if (tid != 0) a.lprof = nullptr;
+    const int G = a.G;
+    double *vs = a.vs;
+    long long tlp_ = a.lprof ? clock64() : 0;
+    for (int st = 0; st < a.sn.nlevels; st++) {
+        const int lv = DIR > 0 ? st : a.sn.nlevels - 1 - st;
+        if (DIR > 0) {
+            sn_for_items<1>(a, lv, 0, [&](const int4 d0, const int4 d1, int sgi) { sn1_forward_panel(a.sn, d0, d1, a.Y + (size_t)sgi * a.ysize, vs, G, sgi); });
+            sn_for_items<8>(a, lv, 1, [&](const int4 d0, const int4 d1, int sgi) { sn_forward_panel<8>(a.sn, d0, d1, a.Y + (size_t)sgi * a.ysize, vs, G, sgi); });
+            sn_for_items<16>(a, lv, 2, [&](const int4 d0, const int4 d1, int sgi) { sn_forward_panel<16>(a.sn, d0, d1, a.Y + (size_t)sgi * a.ysize, vs, G, sgi); });
+            sn_for_items<32>(a, lv, 3, [&](const int4 d0, const int4 d1, int sgi) { sn_forward_panel<32>(a.sn, d0, d1, a.Y + (size_t)sgi * a.ysize, vs, G, sgi); });
+        } else {
+            sn_for_items<1>(a, lv, 0, [&](const int4 d0, const int4 d1, int sgi) { sn1_backward_panel(a.sn, d0, d1, a.Y + (size_t)sgi * a.ysize, vs, G, sgi); });
+            sn_for_items<8>(a, lv, 1, [&](const int4 d0, const int4 d1, int sgi) { sn_backward_panel<8>(a.sn, d0, d1, a.Y + (size_t)sgi * a.ysize, vs, G, sgi); });
+            sn_for_items<16>(a, lv, 2, [&](const int4 d0, const int4 d1, int sgi) { sn_backward_panel<16>(a.sn, d0, d1, a.Y + (size_t)sgi * a.ysize, vs, G, sgi); });
+            sn_for_items<32>(a, lv, 3, [&](const int4 d0, const int4 d1, int sgi) { sn_backward_panel<32>(a.sn, d0, d1, a.Y + (size_t)sgi * a.ysize, vs, G, sgi); });
+        }
+        __syncthreads();
+        if (a.lprof) { const long long tn = clock64(); a.lprof[(DIR > 0 ? 1 : 2) * a.nls + lv] += tn - tlp_; tlp_ = tn; }
+    }
+}
+
+__device__ __forceinline__ void kkt_ldl_solve_sn(const IpmProgram &P, Ctx &c, const double *invD, double *v)
 {
     const int G = c.G, sg = c.sg;
     double *vs = c.vs;
     const long long t0_ = clock64();
     for (int i = c.slot; i < P.nk; i += c.nslots) vs[i * G + sg] = v[GI(i)];
     __syncthreads();
-    long long tlp_ = c.lprof ? clock64() : 0;
-    for (int lv = 0; lv < P.sn.nlevels; lv++) {
-        sn_for_items<1>(P, c, lv, 0, [&](const int4 d0, const int4 d1, int sgi) { sn1_forward_panel(P.sn, d0, d1, Y + (size_t)sgi * c.ysize, vs, G, sgi); });
-        sn_for_items<8>(P, c, lv, 1, [&](const int4 d0, const int4 d1, int sgi) { sn_forward_panel<8>(P.sn, d0, d1, Y + (size_t)sgi * c.ysize, vs, G, sgi); });
-        sn_for_items<16>(P, c, lv, 2, [&](const int4 d0, const int4 d1, int sgi) { sn_forward_panel<16>(P.sn, d0, d1, Y + (size_t)sgi * c.ysize, vs, G, sgi); });
-        sn_for_items<32>(P, c, lv, 3, [&](const int4 d0, const int4 d1, int sgi) { sn_forward_panel<32>(P.sn, d0, d1, Y + (size_t)sgi * c.ysize, vs, G, sgi); });
-        __syncthreads();
-        if (c.lprof) { const long long tn = clock64(); c.lprof[P.nlevels + lv] += tn - tlp_; tlp_ = tn; }
-    }
+    kkt_sweep_sn<1>(c.s_sn, c.tid);
     const long long t1_ = clock64();
     for (int i = c.slot; i < P.nk; i += c.nslots) vs[i * G + sg] *= invD[GI(i)];
     __syncthreads();
-    tlp_ = c.lprof ? clock64() : 0;
-    for (int lv = P.sn.nlevels - 1; lv >= 0; lv--) {
-        sn_for_items<1>(P, c, lv, 0, [&](const int4 d0, const int4 d1, int sgi) { sn1_backward_panel(P.sn, d0, d1, Y + (size_t)sgi * c.ysize, vs, G, sgi); });
-        sn_for_items<8>(P, c, lv, 1, [&](const int4 d0, const int4 d1, int sgi) { sn_backward_panel<8>(P.sn, d0, d1, Y + (size_t)sgi * c.ysize, vs, G, sgi); });
-        sn_for_items<16>(P, c, lv, 2, [&](const int4 d0, const int4 d1, int sgi) { sn_backward_panel<16>(P.sn, d0, d1, Y + (size_t)sgi * c.ysize, vs, G, sgi); });
-        sn_for_items<32>(P, c, lv, 3, [&](const int4 d0, const int4 d1, int sgi) { sn_backward_panel<32>(P.sn, d0, d1, Y + (size_t)sgi * c.ysize, vs, G, sgi); });
-        __syncthreads();
-        if (c.lprof) { const long long tn = clock64(); c.lprof[2 * P.nlevels + lv] += tn - tlp_; tlp_ = tn; }
-    }
+    kkt_sweep_sn<-1>(c.s_sn, c.tid);
     for (int i = c.slot; i < P.nk; i += c.nslots) v[GI(i)] = vs[i * G + sg];
     __syncthreads();
     const long long t2_ = clock64();
     c.t_fw += t1_ - t0_; c.t_bw += t2_ - t1_; c.t_ldl_n += 1;
 }
 
-__device__ void kkt_factor(const IpmProgram &P, Ctx &c, double *Y, double *Ls, double *invD)
+// SN (compile time): the supernodal kernels are instantiated only in the kernel variant that uses them -- their mere
+// presence as call sites costs the default (scalar) variant ~3 KB of spill traffic per thread (ptxas -v)
+template <int SN>
+__device__ __forceinline__ void kkt_factor(const IpmProgram &P, Ctx &c, double *Y, double *Ls, double *invD)
 {
-    if (c.sn) { kkt_factor_sn(P, c, Y, invD); return; }
+    if constexpr (SN) { kkt_factor_sn(c.s_sn, c.tid); return; }
     FactorArgs a;
     a.fa_item = P.fa_item; a.fb_item = P.fb_item; a.ft_op = P.ft_op;
     a.Y = Y; a.Ls = Ls; a.Lrow = c.Lrow; a.invD = invD;
-    a.s_delta = c.s_delta; a.s_bad = c.s_bad; a.rho_min = c.rho_min; a.bad_abs = c.bad_abs;
     a.o_fal = c.o_fal; a.o_faR = c.o_faR; a.o_fbl = c.o_fbl;
     a.nl = P.nlevels; a.nnzLd = P.nnzL; a.G = c.G; a.sg = c.sg; a.slot = c.slot; a.nslots = c.nslots;
     a.lprof = c.lprof;
@@ -601,7 +575,7 @@ __device__ __noinline__ void solve_sweep(const SweepArgs a)
 #undef IPM_CONSUME
 }
 
-__device__ void kkt_ldl_solve_smem(const IpmProgram &P, Ctx &c, const double *Ls, const double *invD, double *v)
+__device__ __forceinline__ void kkt_ldl_solve_smem(const IpmProgram &P, Ctx &c, const double *Ls, const double *invD, double *v)
 {
     const int G = c.G, sg = c.sg;
     double *vs = c.vs;
@@ -628,9 +602,10 @@ __device__ void kkt_ldl_solve_smem(const IpmProgram &P, Ctx &c, const double *Ls
 }
 
 // in-place solve of (L D L') v = rhs on the permuted vector v
-__device__ void kkt_ldl_solve(const IpmProgram &P, Ctx &c, const double *Ls, const double *invD, double *v)
+template <int SN>
+__device__ __forceinline__ void kkt_ldl_solve(const IpmProgram &P, Ctx &c, const double *Ls, const double *invD, double *v)
 {
-    if (c.sn) { kkt_ldl_solve_sn(P, c, c.Ypanels, invD, v); return; }
+    if constexpr (SN) { kkt_ldl_solve_sn(P, c, invD, v); return; }
     if (c.vs) { kkt_ldl_solve_smem(P, c, Ls, invD, v); return; }
     set_lanes(c, c.Rmax);
     const int G = c.G, sg = c.sg;
@@ -692,7 +667,8 @@ __device__ void kkt_ldl_solve(const IpmProgram &P, Ctx &c, const double *Ls, con
 //   (G' W^-2 G) dx + A' dy = bx + G' W^-2 bz ,  A dx = by ,  dz = W^-2 (G dx - bz)
 // with nref steps of iterative refinement against the unregularised reduced operator.
 // bx,by,bz are overwritten/consumed: bx -> r1 (in place), by -> r2 (kept), bz kept.
-__device__ void kkt_solve(const IpmProgram &P, Ctx &c, const IpmData &D, const double *Av, const double *Gv,
+template <int SN>
+__device__ __forceinline__ void kkt_solve(const IpmProgram &P, Ctx &c, const IpmData &D, const double *Av, const double *Gv,
                           const double *wm, const double *socw, const double *soceta, double *bx, const double *by,
                           const double *bz, double *dx, double *dy, double *dz, double *tm, double *gm, double *e1,
                           double *e2, double *rhs, const double *Ls, const double *invD, int nref)
@@ -710,7 +686,7 @@ __device__ void kkt_solve(const IpmProgram &P, Ctx &c, const IpmData &D, const d
     for (int r = c.slot; r < P.p; r += c.nslots) { rhs[GI(P.iperm[P.n + r])] = by[GI(r)]; dy[GI(r)] = 0.0; }
     __syncthreads();
     for (int it = 0;; it++) {
-        kkt_ldl_solve(P, c, Ls, invD, rhs);
+        kkt_ldl_solve<SN>(P, c, Ls, invD, rhs);
         for (int v = c.slot; v < P.n; v += c.nslots) dx[GI(v)] += rhs[GI(P.iperm[v])];
         for (int r = c.slot; r < P.p; r += c.nslots) dy[GI(r)] += rhs[GI(P.iperm[P.n + r])];
         __syncthreads();
@@ -990,18 +966,21 @@ __device__ void equilibrate(const IpmProgram &P, const Ctx &c, double *Av, doubl
 }
 
 // =============================================================================================
-template <int NT>
+template <int NT, int SN>
 __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmData D, const IpmOpts O)
 {
-    __shared__ double s_red[8 * (IPM_NT_MAX / 32) * IPM_MAXG];
-    __shared__ double s_out[8 * IPM_MAXG];
+    __shared__ double s_red[10 * (IPM_NT_MAX / 32) * IPM_MAXG];
+    __shared__ double s_out[10 * IPM_MAXG];
     __shared__ double s_nb[IPM_MAXG], s_nh[IPM_MAXG], s_nc[IPM_MAXG];
     __shared__ double s_mu[IPM_MAXG], s_sigmu[IPM_MAXG], s_alpha[IPM_MAXG], s_scale[IPM_MAXG];
     __shared__ int s_flag;
     __shared__ int s_done[IPM_MAXG], s_status[IPM_MAXG], s_iters[IPM_MAXG], s_alldone, s_save[IPM_MAXG], s_stall[IPM_MAXG];
     __shared__ double s_best[IPM_MAXG], s_bp[IPM_MAXG], s_bd[IPM_MAXG], s_br[3 * IPM_MAXG];
-    __shared__ double s_delta[IPM_MAXG], s_alpha_d[IPM_MAXG];
-    __shared__ int s_bad[IPM_MAXG], s_skip[IPM_MAXG];
+    __shared__ double s_alpha_d[IPM_MAXG];
+    __shared__ int s_skip[IPM_MAXG];
+    double *const s_delta = ipm_s_delta;
+    int *const s_bad = ipm_s_bad;
+    __shared__ SnArgs s_snargs;
 
     int *s_lv = ipm_smem;   // [9][nlevels+1]: lvl_ptr | fa_lvl | fb_lvl | - | fa_R | fwp_lvl | bwp_lvl | fwp_R | bwp_R
     const int nl1 = P.nlevels + 1;
@@ -1048,6 +1027,15 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
     double *Y = GP(D.Y, P.ysize), *Ls = GP(D.Ls, P.nnzL + 1), *invD = GP(D.invD, P.nk);
     c.sn = D.sn; c.Ypanels = Y; c.ysize = (size_t)P.ysize;
     c.s_done = s_done; c.s_delta = s_delta; c.s_bad = s_bad; c.rho_min = O.rho_min; c.bad_abs = O.bad_abs;
+    if (threadIdx.x == 0) { ipm_s_reg[0] = O.rho_min; ipm_s_reg[1] = O.bad_abs; }
+    c.s_sn = &s_snargs;
+    if (SN && threadIdx.x == 0) {
+        SnArgs a;
+        a.sn = P.sn; a.Y = Y; a.invD = invD; a.vs = c.vs; a.s_done = s_done; a.s_delta = s_delta; a.s_bad = s_bad;
+        a.rho_min = O.rho_min; a.bad_abs = O.bad_abs; a.ysize = (size_t)P.ysize; a.G = D.G; a.tid = 0; a.nwarps = NT / 32;
+        a.nls = P.nlevels; a.lprof = (blockIdx.x == 0 && D.prof && D.lvl_prof) ? D.prof + 12 : nullptr;
+        s_snargs = a;
+    }
     c.Lrow = GP(D.Lrow, P.nnzL + 1);
 #undef GP
 
@@ -1073,8 +1061,8 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
     }
     if (D.debug_kkt) {   // test hook: one KKT solve on the device with the caller's scaling and right-hand side
         kkt_assemble(P, c, D, Av, Gv, wm, Y, 0.0);
-        kkt_factor(P, c, Y, Ls, invD);
-        kkt_ldl_solve(P, c, Ls, invD, rhs);
+        kkt_factor<SN>(P, c, Y, Ls, invD);
+        kkt_ldl_solve<SN>(P, c, Ls, invD, rhs);
         if (c.tid < G && (int)g * G + c.tid < D.B) D.status[(int)g * G + c.tid] = s_bad[c.tid];
         return;
     }
@@ -1084,7 +1072,7 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
     for (int tr_ = 0;; tr_++) {                                                                    \
         if (c.tid < G) s_bad[c.tid] = 0;                                                           \
         kkt_assemble(P, c, D, Av, Gv, wm, Y, 0.0);                                                 \
-        kkt_factor(P, c, Y, Ls, invD);                                                             \
+        kkt_factor<SN>(P, c, Y, Ls, invD);                                                             \
         if (c.tid == 0) {                                                                          \
             int again_ = 0;                                                                        \
             for (int q = 0; q < G; q++)                                                            \
@@ -1122,7 +1110,7 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
     // solve 1: [0;b;h] -> x, s = h - G x
     for (int v = c.slot; v < P.n; v += c.nslots) r1[GI(v)] = 0.0;
     __syncthreads();
-    kkt_solve(P, c, D, Av, Gv, wm, socw, soceta, r1, bb, hh, x, dy, dz, tm, gm, e1, e2, rhs, Ls, invD, O.nref);
+    kkt_solve<SN>(P, c, D, Av, Gv, wm, socw, soceta, r1, bb, hh, x, dy, dz, tm, gm, e1, e2, rhs, Ls, invD, O.nref);
     for (int r = c.slot; r < P.m; r += c.nslots) s[GI(r)] = -dz[GI(r)];
     __syncthreads();
     {
@@ -1146,7 +1134,7 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
     for (int r = c.slot; r < P.p; r += c.nslots) r2[GI(r)] = 0.0;
     for (int r = c.slot; r < P.m; r += c.nslots) rz[GI(r)] = 0.0;
     __syncthreads();
-    kkt_solve(P, c, D, Av, Gv, wm, socw, soceta, r1, r2, rz, dx, y, z, tm, gm, e1, e2, rhs, Ls, invD, O.nref);
+    kkt_solve<SN>(P, c, D, Av, Gv, wm, socw, soceta, r1, r2, rz, dx, y, z, tm, gm, e1, e2, rhs, Ls, invD, O.nref);
     {
         double vv[1] = {cone_shift_partial(P, c, z)};
         double w2[1] = {0.0};
@@ -1168,28 +1156,36 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
     const double deg = (double)(P.l + P.nsoc);
     for (int it = 0; it <= O.maxit; it++) {
         // ---- residuals + objective pieces ----
-        double v[7] = {0, 0, 0, 0, 0, 0, 0};
+        // v[7..9]: |A'y + G'z|^2, |Ax|^2, |Gx + s|^2 for the infeasibility certificates (ECOS reports INFEASIBLE /
+        // DUAL_INFEASIBLE the same way; src/solvers/scp.jl:470-473 and :975 branch on those statuses)
+        double v[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         for (int i = c.slot; i < P.n; i += c.nslots) {
-            const double r = cc[GI(i)] + col_dot(P.At_rp, P.At_ri, P.At_vi, Av, y, i, G, sg) +
+            const double ci_ = cc[GI(i)];
+            const double r = ci_ + col_dot(P.At_rp, P.At_ri, P.At_vi, Av, y, i, G, sg) +
                              col_dot(P.Gt_rp, P.Gt_ri, P.Gt_vi, Gv, z, i, G, sg);
             rx[GI(i)] = r;
             v[0] += r * r;
-            v[3] += cc[GI(i)] * x[GI(i)];
+            v[3] += ci_ * x[GI(i)];
+            v[7] += (r - ci_) * (r - ci_);
         }
         for (int i = c.slot; i < P.p; i += c.nslots) {
-            const double r = row_dot(P.A_rp, P.A_ci, Av, x, i, G, sg) - bb[GI(i)];
+            const double bi_ = bb[GI(i)];
+            const double r = row_dot(P.A_rp, P.A_ci, Av, x, i, G, sg) - bi_;
             ry[GI(i)] = r;
             v[1] += r * r;
-            v[4] += bb[GI(i)] * y[GI(i)];
+            v[4] += bi_ * y[GI(i)];
+            v[8] += (r + bi_) * (r + bi_);
         }
         for (int i = c.slot; i < P.m; i += c.nslots) {
-            const double r = row_dot(P.G_rp, P.G_ci, Gv, x, i, G, sg) + s[GI(i)] - hh[GI(i)];
+            const double hi_ = hh[GI(i)];
+            const double r = row_dot(P.G_rp, P.G_ci, Gv, x, i, G, sg) + s[GI(i)] - hi_;
             rz[GI(i)] = r;
             v[2] += r * r;
-            v[5] += hh[GI(i)] * z[GI(i)];
+            v[5] += hi_ * z[GI(i)];
             v[6] += s[GI(i)] * z[GI(i)];
+            v[9] += (r + hi_) * (r + hi_);
         }
-        seed_reduce<7>(c, v, 0);
+        seed_reduce<10>(c, v, 0);
         if (c.tid < G) {
             const int q = c.tid;
             const double nrx = sqrt(s_out[0 * IPM_MAXG + q]), nry = sqrt(s_out[1 * IPM_MAXG + q]),
@@ -1207,10 +1203,16 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
                     s_best[q] = acc; s_save[q] = 1; s_stall[q] = 0;
                     s_bp[q] = pcost; s_bd[q] = dcost; s_br[q] = pres; s_br[IPM_MAXG + q] = dres; s_br[2 * IPM_MAXG + q] = gap;
                 } else s_stall[q]++;
+                // certificates: (y, z) with A'y + G'z ~ 0 and b'y + h'z < 0 proves primal infeasibility; x with
+                // Ax ~ 0, Gx + s ~ 0 and c'x < 0 proves dual infeasibility (an unbounded program)
+                const double pinf = (dcost > 0.0) ? sqrt(s_out[7 * IPM_MAXG + q]) / dcost : CUDART_INF;
+                const double dinf = (pcost < 0.0) ? sqrt(fmax(s_out[8 * IPM_MAXG + q], s_out[9 * IPM_MAXG + q])) / (-pcost) : CUDART_INF;
                 if (!(isfinite(pres) && isfinite(dres) && isfinite(gap))) { s_done[q] = 1; s_status[q] = IPM_NUMERICAL; }
                 else if (pres <= O.feastol && dres <= O.feastol && (gap <= O.abstol || relgap <= O.reltol)) {
                     s_done[q] = 1; s_status[q] = IPM_OPTIMAL;
-                } else if (s_stall[q] >= 3 && s_best[q] <= 1e-6) { s_done[q] = 1; s_status[q] = IPM_NUMERICAL; }  // numerical floor
+                }
+                else if (it >= 2 && pinf <= O.feastol) { s_done[q] = 1; s_status[q] = IPM_PINF; s_save[q] = 1; }
+                else if (it >= 2 && dinf <= O.feastol) { s_done[q] = 1; s_status[q] = IPM_DINF; s_save[q] = 1; } else if (s_stall[q] >= 3 && s_best[q] <= 1e-6) { s_done[q] = 1; s_status[q] = IPM_NUMERICAL; }  // numerical floor
                 else if (it == O.maxit) { s_done[q] = 1; s_status[q] = IPM_MAXIT; }
             }
         }
@@ -1244,7 +1246,7 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
         for (int i = c.slot; i < P.m; i += c.nslots) ds[GI(i)] = -rz[GI(i)] + s[GI(i)];  // ds used as bz scratch
         __syncthreads();
         PROF(6)
-        kkt_solve(P, c, D, Av, Gv, wm, socw, soceta, r1, r2, ds, dx, dy, dza, tm, gm, e1, e2, rhs, Ls, invD, O.nref_aff);
+        kkt_solve<SN>(P, c, D, Av, Gv, wm, socw, soceta, r1, r2, ds, dx, dy, dza, tm, gm, e1, e2, rhs, Ls, invD, O.nref_aff);
         PROF(5)
         // ds = tmp - W^2 dz with tmp = -s; W^2 dz == G dx - bz is left in gm by kkt_solve (no W^2 W^-2
         // round trip: keeps G dx + ds = -rz to rounding even when the scaling is ill-conditioned)
@@ -1283,7 +1285,7 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
         }
         __syncthreads();
         PROF(6)
-        kkt_solve(P, c, D, Av, Gv, wm, socw, soceta, r1, r2, ds, dx, dy, dz, tm, gm, e1, e2, rhs, Ls, invD, O.nref);
+        kkt_solve<SN>(P, c, D, Av, Gv, wm, socw, soceta, r1, r2, ds, dx, dy, dz, tm, gm, e1, e2, rhs, Ls, invD, O.nref);
         PROF(5)
         for (int i = c.slot; i < P.m; i += c.nslots) ds[GI(i)] = dsa[GI(i)] - gm[GI(i)];
         __syncthreads();
@@ -1335,7 +1337,7 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
     // ---- epilogue: the best iterate is the answer (ECOS reports its best point the same way) ----
     __syncthreads();
     // the numerical floor of the fp64 normal-equation factorisation sits within ~10x of ECOS' 1e-8 targets
-    if (c.tid < G && s_status[c.tid] != IPM_OPTIMAL) {
+    if (c.tid < G && s_status[c.tid] != IPM_OPTIMAL && s_status[c.tid] != IPM_PINF && s_status[c.tid] != IPM_DINF) {
         if (s_best[c.tid] <= 10.0 * fmax(O.feastol, O.reltol)) s_status[c.tid] = IPM_OPTIMAL;
         else if (s_best[c.tid] <= 5e-5) s_status[c.tid] = IPM_ALMOST;
     }

@@ -49,6 +49,7 @@ struct DiscArgs {
     OutView A, Bm, Bp, F, r, E, defect;
     double *dnorm;          // [B][N-1]  ||iSx*defect||_inf per segment
     int *status;            // device word, OR-ed with 1 on a singular pivot
+    const int *skip;        // nullable [B]: seeds marked non-zero are left untouched (SCP seeds that have stopped)
     ModelPar par;
 };
 
@@ -57,7 +58,10 @@ __device__ __forceinline__ double shfl_d(double v, int src)
     return __shfl_sync(0xffffffffu, v, src);
 }
 
-template <class M>
+// IMP = 1: IMPULSE discretization (discretization.jl:186-193, 304-340, 384-390): the segment starts from the
+// impulse-updated state x_k + f(t_k, -k, x_k, u_k, p), coasts with u = 0, and B_k = A_k * B(t_k, -k, x_k, u_k, p) (one
+// input block: Bm; Bp is written as zero).  Phi, F, r and E columns are the FOH ones evaluated at u = 0.
+template <class M, int IMP>
 __global__ void __launch_bounds__(128) k_discretize_foh(const DiscArgs a)
 {
     constexpr int NX = M::NX, NU = M::NU, NF = M::NF, NPD = M::NPD;
@@ -72,6 +76,7 @@ __global__ void __launch_bounds__(128) k_discretize_foh(const DiscArgs a)
     const int nseg = a.N - 1;
     if (gw >= (long long)a.B * nseg) return;
     const int b = (int)(gw / nseg), k = (int)(gw % nseg);
+    if (a.skip && a.skip[b]) return;     // warp-uniform: the whole warp works on seed b
     double *Q = smem + wib * QSZ;
 
     // ---- column bookkeeping for this lane ----
@@ -103,6 +108,13 @@ __global__ void __launch_bounds__(128) k_discretize_foh(const DiscArgs a)
     }
 #pragma unroll
     for (int i = 0; i < NPD; i++) pp[i] = a.p[b * a.psB + i * a.psE];
+    if constexpr (IMP) {
+        static_assert(M::IMPULSE, "this model pack has no impulse semantics");
+        double jump[NX], Bj[NX * NU];
+        M::eval_impulse(a.par, t1, xv, uk, pp, jump, Bj);
+#pragma unroll
+        for (int i = 0; i < NX; i++) xv[i] += jump[i];
+    }
 
     // V0 = [x_k; vec(I); 0]  (discretization.jl:177-185)
     double colv[CPL][NX], phib[NX], phis[NX];
@@ -139,7 +151,7 @@ __global__ void __launch_bounds__(128) k_discretize_foh(const DiscArgs a)
             const double sgp = __ddiv_rn(__dsub_rn(t, t1), dts);
             double u[NU];
 #pragma unroll
-            for (int i = 0; i < NU; i++) u[i] = cc * uk[i] + omc * ukp1[i];
+            for (int i = 0; i < NU; i++) u[i] = IMP ? 0.0 : cc * uk[i] + omc * ukp1[i];
 
             double f[NX], A[NX * NX], Bu[NX * NU], Fc[NF * NX];
             M::eval(a.par, t, xs, u, pp, f, A, Bu, Fc);
@@ -244,6 +256,23 @@ __global__ void __launch_bounds__(128) k_discretize_foh(const DiscArgs a)
         M::post_step(xv);  // integration actions act on V[idx] after every step (helper.jl:492-496)
     }
 
+    if constexpr (IMP) {   // B_k = A_k * B(t_k, -k, x_k, u_k, p): the input columns carry the jump Jacobian into the product
+        double xk[NX], jump[NX], Bj[NX * NU];
+#pragma unroll
+        for (int i = 0; i < NX; i++) xk[i] = a.xd[b * a.xsB + k * a.xsK + i * a.xsE];
+        M::eval_impulse(a.par, t1, xk, uk, pp, jump, Bj);
+#pragma unroll
+        for (int s = 0; s < CPL; s++) {
+            const int c = lane + 32 * s;
+            if (scl[s] == 1) {
+#pragma unroll
+                for (int r = 0; r < NX; r++) colv[s][r] = Bj[(c - NX) * NX + r];
+            } else if (scl[s] == 2) {
+#pragma unroll
+                for (int r = 0; r < NX; r++) colv[s][r] = 0.0;
+            }
+        }
+    }
     // ---- set_update_matrices (discretization.jl:354-406): A_k = Phi, X_k = A_k * XV ----
     double outc[CPL][NX];
 #pragma unroll
@@ -299,10 +328,11 @@ __global__ void __launch_bounds__(128) k_discretize_foh(const DiscArgs a)
 }
 
 // feas[b] = all_k !(dnorm[b][k] > feas_tol)   (NaN compares false, as in the reference)
-static __global__ void k_feas_reduce(const double *dnorm, int B, int nseg, double feas_tol, int *feas)
+static __global__ void k_feas_reduce(const double *dnorm, int B, int nseg, double feas_tol, int *feas, const int *skip)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
+    if (skip && skip[b]) return;
     int ok = 1;
     for (int k = 0; k < nseg; k++)
         if (dnorm[(long long)b * nseg + k] > feas_tol) ok = 0;

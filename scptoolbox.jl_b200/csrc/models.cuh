@@ -36,6 +36,7 @@ struct Model<SCPB_MODEL_DBLINT> {
         B[0] = 0.0; B[1] = p[0];
         Fc[0] = f0; Fc[1] = f1;
     }
+    static constexpr bool IMPULSE = false;
     __device__ __forceinline__ static void post_step(double *) {}
 };
 
@@ -93,6 +94,7 @@ struct Model<SCPB_MODEL_ROCKET> {
         B[5 + 7 * 2] = td;
         B[6 + 7 * 3] = -alpha * td;
     }
+    static constexpr bool IMPULSE = false;
     __device__ __forceinline__ static void post_step(double *) {}
 };
 
@@ -177,6 +179,7 @@ struct Model<SCPB_MODEL_STARSHIP> {
         B[6 + 8 * 0] = tdil * ae;
         B[7 + 8 * 1] = tdil * (1.0 / rd);
     }
+    static constexpr bool IMPULSE = false;
     __device__ __forceinline__ static void post_step(double *) {}
 };
 
@@ -206,6 +209,7 @@ struct Model<SCPB_MODEL_QUADROTOR> {
 #pragma unroll
         for (int i = 0; i < 3; i++) B[(3 + i) + 6 * i] = td;
     }
+    static constexpr bool IMPULSE = false;
     __device__ __forceinline__ static void post_step(double *) {}
 };
 
@@ -282,10 +286,74 @@ struct Model<SCPB_MODEL_FREEFLYER> {
             for (int j = 0; j < 3; j++) B[(10 + i) + 13 * (3 + j)] = td * Ji[i + 3 * j];
         }
     }
+    static constexpr bool IMPULSE = false;
     __device__ __forceinline__ static void post_step(double *x)
     {
         const double n = sqrt(x[6] * x[6] + x[7] * x[7] + x[8] * x[8] + x[9] * x[9]);
 #pragma unroll
         for (int i = 0; i < 4; i++) x[6 + i] = x[6 + i] / n;
     }
+};
+
+// ---------------------------------------------------------------- planar rendezvous with impulsive RCS thrust
+// rendezvous_planar/definition.jl:147-243, parameters.jl:87-111.  x = [r(2) v(2) theta omega]; u[0..2] = (f-, f+, f0),
+// the other nine inputs (references, absolute values) do not enter the dynamics; p = [tdil]; par: m, J, lu, lv, n.
+// The reference calls f / B with a NEGATIVE segment index for the impulse (discretization.jl:191, 389): the jump of
+// (v, omega) and its input Jacobian, not scaled by the time dilation -> eval_impulse().
+template <>
+struct Model<SCPB_MODEL_RENDEZVOUS2D> {
+    static constexpr int NX = 6, NU = 12, NF = 1, NPD = 1;
+    static constexpr bool IMPULSE = true;
+    __device__ static constexpr int fcol(int) { return 0; }
+    __device__ __forceinline__ static void eval(const ModelPar &P, double, const double *x, const double *u,
+                                                const double *p, double *f, double *A, double *B, double *Fc)
+    {
+        const double ms = P.v[0], J = P.v[1], lu = P.v[2], lv = P.v[3], n = P.v[4];
+        const double th = x[4], fm = u[0], fp = u[1], f0 = u[2], tdil = p[0];
+        double sth, cth;
+        sincos(th, &sth, &cth);
+        const double uh0 = -cth, uh1 = sth, vh0 = -sth, vh1 = -cth;
+        double g[6];
+        g[0] = x[2]; g[1] = x[3];
+        g[2] = ((fm + fp) * uh0 + f0 * vh0) / ms + 2.0 * n * x[3];
+        g[3] = ((fm + fp) * uh1 + f0 * vh1) / ms + (3.0 * n * n * x[1] - 2.0 * n * x[2]);
+        g[4] = x[5];
+        g[5] = ((fp - fm) * lv - f0 * lu) / J;
+#pragma unroll
+        for (int i = 0; i < 6; i++) { Fc[i] = g[i]; f[i] = g[i] * tdil; }
+#pragma unroll
+        for (int i = 0; i < 36; i++) A[i] = 0.0;
+        A[0 + 6 * 2] = tdil; A[1 + 6 * 3] = tdil;
+        A[3 + 6 * 1] = 3.0 * n * n * tdil;
+        A[2 + 6 * 3] = 2.0 * n * tdil; A[3 + 6 * 2] = -2.0 * n * tdil;
+        A[2 + 6 * 4] = ((fm + fp) * sth + f0 * (-cth)) / ms * tdil;   // d uh/d th = (sin, cos), d vh/d th = (-cos, sin)
+        A[3 + 6 * 4] = ((fm + fp) * cth + f0 * sth) / ms * tdil;
+        A[4 + 6 * 5] = tdil;
+#pragma unroll
+        for (int i = 0; i < 72; i++) B[i] = 0.0;
+        B[2 + 6 * 0] = uh0 / ms * tdil; B[3 + 6 * 0] = uh1 / ms * tdil; B[5 + 6 * 0] = -lv / J * tdil;
+        B[2 + 6 * 1] = uh0 / ms * tdil; B[3 + 6 * 1] = uh1 / ms * tdil; B[5 + 6 * 1] = lv / J * tdil;
+        B[2 + 6 * 2] = vh0 / ms * tdil; B[3 + 6 * 2] = vh1 / ms * tdil; B[5 + 6 * 2] = -lu / J * tdil;
+    }
+    // the impulse at a node: jump[NX] = f(t, -k, x, u, p), Bj = B(t, -k, x, u, p) (col-major NX*NU)
+    __device__ __forceinline__ static void eval_impulse(const ModelPar &P, double, const double *x, const double *u,
+                                                        const double *, double *jump, double *Bj)
+    {
+        const double ms = P.v[0], J = P.v[1], lu = P.v[2], lv = P.v[3];
+        const double th = x[4], fm = u[0], fp = u[1], f0 = u[2];
+        double sth, cth;
+        sincos(th, &sth, &cth);
+        const double uh0 = -cth, uh1 = sth, vh0 = -sth, vh1 = -cth;
+#pragma unroll
+        for (int i = 0; i < 6; i++) jump[i] = 0.0;
+        jump[2] = ((fm + fp) * uh0 + f0 * vh0) / ms;
+        jump[3] = ((fm + fp) * uh1 + f0 * vh1) / ms;
+        jump[5] = ((fp - fm) * lv - f0 * lu) / J;
+#pragma unroll
+        for (int i = 0; i < 72; i++) Bj[i] = 0.0;
+        Bj[2 + 6 * 0] = uh0 / ms; Bj[3 + 6 * 0] = uh1 / ms; Bj[5 + 6 * 0] = -lv / J;
+        Bj[2 + 6 * 1] = uh0 / ms; Bj[3 + 6 * 1] = uh1 / ms; Bj[5 + 6 * 1] = lv / J;
+        Bj[2 + 6 * 2] = vh0 / ms; Bj[3 + 6 * 2] = vh1 / ms; Bj[5 + 6 * 2] = -lu / J;
+    }
+    __device__ __forceinline__ static void post_step(double *) {}
 };

@@ -91,3 +91,63 @@ __global__ void __launch_bounds__(32) k_propagate_foh(const PropArgs a)
         for (int i = 0; i < NX; i++) xc[(size_t)j * NX + i] = X[i];
     }
 }
+
+// IMPULSE branch (discretization.jl:539-558): every interval is integrated on its own from the impulse-updated state
+// x_k + f(t_k, -k, x_k, u_k, p) with the thrusters idle, on LinRange(t_k, t_k+1, subres), subres = ceil(res / (N - 1));
+// the output holds xd[:, 1] followed by the subres columns of every interval: 1 + (N - 1) * subres columns per seed.
+// One thread per (seed, interval): the intervals are independent initial-value problems.
+template <class M>
+__global__ void __launch_bounds__(64) k_propagate_impulse(const PropArgs a, int subres)
+{
+    constexpr int NX = M::NX, NU = M::NU, NF = M::NF, NPD = M::NPD;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int nseg = a.N - 1;
+    if (i >= (long long)a.B * nseg) return;
+    const int b = (int)(i / nseg), k = (int)(i % nseg);
+    const size_t ncol = 1 + (size_t)nseg * subres;
+    double *xc = a.xc + (size_t)b * ncol * NX;
+    double X[NX], uk[NU], u0[NU], pp[NPD], jump[NX], Bj[NX * NU];
+#pragma unroll
+    for (int j = 0; j < NX; j++) X[j] = a.xd[((size_t)b * a.N + k) * NX + j];
+#pragma unroll
+    for (int j = 0; j < NU; j++) { uk[j] = a.ud[((size_t)b * a.N + k) * NU + j]; u0[j] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < NPD; j++) pp[j] = a.p[(size_t)b * a.np + j];
+    if (k == 0) {
+#pragma unroll
+        for (int j = 0; j < NX; j++) xc[j] = X[j];
+    }
+    const double t1 = a.t_grid[k], t2 = a.t_grid[k + 1];
+    if constexpr (M::IMPULSE) {
+        M::eval_impulse(a.par, t1, X, uk, pp, jump, Bj);
+#pragma unroll
+        for (int j = 0; j < NX; j++) X[j] += jump[j];
+    }
+    double *out = xc + (1 + (size_t)k * subres) * NX;
+#pragma unroll
+    for (int j = 0; j < NX; j++) out[j] = X[j];
+    const int d = subres - 1;
+    for (int q = 1; q <= d; q++) {
+        const double f0 = __ddiv_rn((double)(q - 1), (double)d), f1 = __ddiv_rn((double)q, (double)d);
+        const double t = __dadd_rn(__dmul_rn(__dsub_rn(1.0, f0), t1), __dmul_rn(f0, t2));
+        const double tp = __dadd_rn(__dmul_rn(__dsub_rn(1.0, f1), t1), __dmul_rn(f1, t2));
+        const double h = __dsub_rn(tp, t), hh = __ddiv_rn(h, 2.0);
+        const double tm = __dadd_rn(t, hh), te = __dadd_rn(t, h);
+        double k1[NX], k2[NX], k3[NX], k4[NX], xt[NX], A[NX * NX], Bu[NX * NU], Fc[NF * NX];
+        M::eval(a.par, t, X, u0, pp, k1, A, Bu, Fc);
+#pragma unroll
+        for (int j = 0; j < NX; j++) xt[j] = X[j] + hh * k1[j];
+        M::eval(a.par, tm, xt, u0, pp, k2, A, Bu, Fc);
+#pragma unroll
+        for (int j = 0; j < NX; j++) xt[j] = X[j] + hh * k2[j];
+        M::eval(a.par, tm, xt, u0, pp, k3, A, Bu, Fc);
+#pragma unroll
+        for (int j = 0; j < NX; j++) xt[j] = X[j] + h * k3[j];
+        M::eval(a.par, te, xt, u0, pp, k4, A, Bu, Fc);
+#pragma unroll
+        for (int j = 0; j < NX; j++) X[j] = X[j] + h / 6.0 * (k1[j] + 2.0 * k2[j] + 2.0 * k3[j] + k4[j]);
+        M::post_step(X);
+#pragma unroll
+        for (int j = 0; j < NX; j++) out[(size_t)q * NX + j] = X[j];
+    }
+}

@@ -23,7 +23,7 @@ const ConeSymbolic *scpb_internal_cone_sym(scpb_cone_s *c);
 scpb_handle_s *scpb_internal_cone_handle(scpb_cone_s *c);
 IpmOpts scpb_internal_make_opts(const scpb_cone_opts *o);
 int scpb_internal_pick_group(int B, int want);
-int scpb_internal_discretize(scpb_handle_s *h, DiscArgs &a, double feas_tol, int *feas);
+int scpb_internal_discretize(scpb_handle_s *h, DiscArgs &a, double feas_tol, int *feas, int method);
 
 struct PtrDev {
     int B, G, N, nx, nu, np, ns;
@@ -300,7 +300,7 @@ static OutView grouped(double *src, int G, long long nsrc, long long off, long l
 }
 
 static int run_discretize(scpb_ptr_s *s, int B, int G, const double *xd, const double *ud, const double *p,
-                          double *srcbuf = nullptr)
+                          double *srcbuf = nullptr, const int *skip = nullptr)
 {
     double *sb = srcbuf ? srcbuf : s->src;
     const scpb_ptr_desc &d = s->d;
@@ -312,6 +312,7 @@ static int run_discretize(scpb_ptr_s *s, int B, int G, const double *xd, const d
     a.usB = (long long)d.N * d.nu; a.usK = d.nu; a.usE = 1;
     a.psB = d.np; a.psE = 1;
     a.f_packed = 1;
+    a.skip = skip;     // seeds that have stopped keep their DLTV blocks, defects and feasibility flag
     const long long nx = d.nx, nu = d.nu;
     a.A = grouped(sb, G, d.nsrc, d.oA, nx * nx);
     a.Bm = grouped(sb, G, d.nsrc, d.oBm, nx * nu);
@@ -321,7 +322,7 @@ static int run_discretize(scpb_ptr_s *s, int B, int G, const double *xd, const d
     a.E = grouped(sb, G, d.nsrc, d.oE, nx * nx);
     OutView df{}; df.ptr = s->defect; df.Gq = 1; df.sGrp = (long long)(d.N - 1) * nx; df.sB = 0; df.sK = nx; df.sE = 1;
     a.defect = df;
-    return scpb_internal_discretize(s->h, a, d.feas_tol, s->feas);
+    return scpb_internal_discretize(s->h, a, d.feas_tol, s->feas, SCPB_FOH);
 }
 
 
@@ -589,7 +590,7 @@ int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *u
         k_extract<<<nbn, 128, 0, st>>>(sd);
         h->launches++;
         mark(); phase.push_back(3);
-        if ((rc = run_discretize(s, B, G, s->xn, s->un, s->pn))) return rc;
+        if ((rc = run_discretize(s, B, G, s->xn, s->un, s->pn, nullptr, s->done))) return rc;
         mark(); phase.push_back(0);
         SCPB_CUDA(h, cudaMemsetAsync(s->nactive, 0, sizeof(int), st));
         k_ptr_step<<<(B + 127) / 128, 128, 0, st>>>(sd);
@@ -760,7 +761,7 @@ int32_t scpb_scvx_solve(scpb_ptr s, int32_t B, const double *xd0, const double *
         k_extract<<<nbn, 128, 0, st>>>(sd);
         h->launches++;
         mark(); phase.push_back(3);
-        if ((rc = run_discretize(s, B, G, s->xn, s->un, s->pn, s->src2))) return rc;   // candidate: DLTV into src2
+        if ((rc = run_discretize(s, B, G, s->xn, s->un, s->pn, s->src2, s->done))) return rc;   // candidate: DLTV into src2
         cost(s->xn, s->un, s->pn, s->J_new, s->L_new);
         mark(); phase.push_back(0);
         SCPB_CUDA(h, cudaMemsetAsync(s->nactive, 0, sizeof(int), st));

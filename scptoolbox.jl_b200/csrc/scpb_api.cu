@@ -11,23 +11,29 @@ static int check_model(scpb_handle_s *h)
 }
 
 template <class M>
-static int launch_disc(scpb_handle_s *h, DiscArgs &a)
+static int launch_disc(scpb_handle_s *h, DiscArgs &a, int method)
 {
     constexpr int QSZ = (M::NU + M::NF + 1) * M::NX;
     const int wpb = 4;
     const long long warps = (long long)a.B * (a.N - 1);
     const int blocks = (int)((warps + wpb - 1) / wpb);
     const size_t smem = sizeof(double) * QSZ * wpb;
-    k_discretize_foh<M><<<blocks, wpb * 32, smem, h->stream>>>(a);
+    if (method == SCPB_IMPULSE) {
+        if constexpr (M::IMPULSE) k_discretize_foh<M, 1><<<blocks, wpb * 32, smem, h->stream>>>(a);
+        else return set_err(h, SCPB_ERR_UNSUPPORTED, "model %d has no impulse semantics (IMPULSE discretization)", h->model_id);
+    } else {
+        k_discretize_foh<M, 0><<<blocks, wpb * 32, smem, h->stream>>>(a);
+    }
     h->launches++;
     return SCPB_OK;
 }
 
 // Launch K1 (+ the feasibility reduction when feas != nullptr). All pointers are device pointers.
-int scpb_internal_discretize(scpb_handle_s *h, DiscArgs &a, double feas_tol, int *feas)
+int scpb_internal_discretize(scpb_handle_s *h, DiscArgs &a, double feas_tol, int *feas, int method)
 {
     int rc = check_model(h);
     if (rc) return rc;
+    if (method != SCPB_FOH && method != SCPB_IMPULSE) return set_err(h, SCPB_ERR_ARG, "unknown discretization method %d", method);
     if (a.B <= 0 || a.N < 2 || a.Nsub < 2) return set_err(h, SCPB_ERR_ARG, "bad sizes B=%d N=%d Nsub=%d", a.B, a.N, a.Nsub);
     a.par = h->par;
     a.np = h->np;
@@ -36,15 +42,17 @@ int scpb_internal_discretize(scpb_handle_s *h, DiscArgs &a, double feas_tol, int
     if (!dn) return set_err(h, SCPB_ERR_CUDA, "scratch allocation failed");
     a.dnorm = dn;
     switch (h->model_id) {
-    case SCPB_MODEL_DBLINT: launch_disc<Model<SCPB_MODEL_DBLINT>>(h, a); break;
-    case SCPB_MODEL_ROCKET: launch_disc<Model<SCPB_MODEL_ROCKET>>(h, a); break;
-    case SCPB_MODEL_STARSHIP: launch_disc<Model<SCPB_MODEL_STARSHIP>>(h, a); break;
-    case SCPB_MODEL_QUADROTOR: launch_disc<Model<SCPB_MODEL_QUADROTOR>>(h, a); break;
-    case SCPB_MODEL_FREEFLYER: launch_disc<Model<SCPB_MODEL_FREEFLYER>>(h, a); break;
+    case SCPB_MODEL_DBLINT: rc = launch_disc<Model<SCPB_MODEL_DBLINT>>(h, a, method); break;
+    case SCPB_MODEL_ROCKET: rc = launch_disc<Model<SCPB_MODEL_ROCKET>>(h, a, method); break;
+    case SCPB_MODEL_STARSHIP: rc = launch_disc<Model<SCPB_MODEL_STARSHIP>>(h, a, method); break;
+    case SCPB_MODEL_QUADROTOR: rc = launch_disc<Model<SCPB_MODEL_QUADROTOR>>(h, a, method); break;
+    case SCPB_MODEL_FREEFLYER: rc = launch_disc<Model<SCPB_MODEL_FREEFLYER>>(h, a, method); break;
+    case SCPB_MODEL_RENDEZVOUS2D: rc = launch_disc<Model<SCPB_MODEL_RENDEZVOUS2D>>(h, a, method); break;
     default: return set_err(h, SCPB_ERR_MODEL, "unknown model id %d", h->model_id);
     }
+    if (rc) return rc;
     if (feas) {
-        k_feas_reduce<<<(a.B + 127) / 128, 128, 0, h->stream>>>(dn, a.B, a.N - 1, feas_tol, feas);
+        k_feas_reduce<<<(a.B + 127) / 128, 128, 0, h->stream>>>(dn, a.B, a.N - 1, feas_tol, feas, a.skip);
         h->launches++;
     }
     SCPB_CUDA(h, cudaGetLastError());
@@ -141,6 +149,7 @@ int32_t scpb_model_set(scpb_handle h, int32_t model_id, const double *par, int32
     case SCPB_MODEL_STARSHIP: enx = 8; enu = 3; enp_min = 2; break;
     case SCPB_MODEL_QUADROTOR: enx = 6; enu = 4; break;
     case SCPB_MODEL_FREEFLYER: enx = 13; enu = 6; break;
+    case SCPB_MODEL_RENDEZVOUS2D: enx = 6; enu = 12; break;
     default: return set_err(h, SCPB_ERR_MODEL, "unknown model id %d", model_id);
     }
     if (nx != enx || nu != enu || np < enp_min)
@@ -160,14 +169,13 @@ int32_t scpb_discretize_dev(scpb_handle h, int32_t method, int32_t B, int32_t N,
 {
     int rc = check_model(h);
     if (rc) return rc;
-    if (method != SCPB_FOH) return set_err(h, SCPB_ERR_UNSUPPORTED, "only FOH discretization is implemented");
     if (!t_grid || !xd || !ud || !p || !iSx_diag) return set_err(h, SCPB_ERR_ARG, "null input pointer");
     SCPB_CUDA(h, cudaSetDevice(h->device));
     DiscArgs a{};
     a.B = B; a.N = N; a.Nsub = Nsub;
     a.t_grid = t_grid; a.xd = xd; a.ud = ud; a.p = p; a.iSx = iSx_diag;
     julia_views(a, h->nx, h->nu, h->np, A, Bm, Bp, F, r, E, defect);
-    return scpb_internal_discretize(h, a, feas_tol, feas);
+    return scpb_internal_discretize(h, a, feas_tol, feas, method);
 }
 
 int32_t scpb_discretize(scpb_handle h, int32_t method, int32_t B, int32_t N, int32_t Nsub,
@@ -177,7 +185,7 @@ int32_t scpb_discretize(scpb_handle h, int32_t method, int32_t B, int32_t N, int
 {
     int rc = check_model(h);
     if (rc) return rc;
-    if (method != SCPB_FOH) return set_err(h, SCPB_ERR_UNSUPPORTED, "only FOH discretization is implemented");
+    if (method != SCPB_FOH && method != SCPB_IMPULSE) return set_err(h, SCPB_ERR_ARG, "unknown discretization method %d", method);
     if (!t_grid || !xd || !ud || !p || !iSx_diag) return set_err(h, SCPB_ERR_ARG, "null input pointer");
     if (B <= 0 || N < 2 || Nsub < 2) return set_err(h, SCPB_ERR_ARG, "bad sizes B=%d N=%d Nsub=%d", B, N, Nsub);
     SCPB_CUDA(h, cudaSetDevice(h->device));
@@ -207,7 +215,7 @@ int32_t scpb_discretize(scpb_handle h, int32_t method, int32_t B, int32_t N, int
     a.t_grid = d_t; a.xd = d_x; a.ud = d_u; a.p = d_p; a.iSx = d_s;
     julia_views(a, h->nx, h->nu, h->np, d_A, d_Bm, d_Bp, d_F, d_r, d_E, d_df);
     SCPB_CUDA(h, cudaEventRecord(h->ev0, st));
-    rc = scpb_internal_discretize(h, a, feas_tol, dfeas);
+    rc = scpb_internal_discretize(h, a, feas_tol, dfeas, method);
     if (rc) return rc;
     SCPB_CUDA(h, cudaEventRecord(h->ev1, st));
     if (A) SCPB_CUDA(h, cudaMemcpyAsync(A, d_A, sizeof(double) * s_A, cudaMemcpyDeviceToHost, st));
@@ -236,12 +244,66 @@ int32_t scpb_discretize(scpb_handle h, int32_t method, int32_t B, int32_t N, int
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------
+// fp64 FMA peak of this device, measured: the denominator of K1's roofline (bench.py, "roofline_k1").
+// 16 independent FMA chains per thread keep the fp64 pipe full; the result is stored so nothing is optimised away.
+__global__ void k_fp64_peak(double *out, int iters, double a, double b)
+{
+    double v[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) v[j] = (double)(threadIdx.x + j) * 1e-3;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[j] = fma(v[j], a, b);
+    }
+    double sacc = 0.0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) sacc += v[j];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = sacc;
+}
+
+extern "C" int32_t scpb_debug_fp64_peak(scpb_handle h, double *tflops)
+{
+    if (!h || !tflops) return SCPB_ERR_ARG;
+    SCPB_CUDA(h, cudaSetDevice(h->device));
+    cudaDeviceProp pr;
+    SCPB_CUDA(h, cudaGetDeviceProperties(&pr, h->device));
+    const int blocks = pr.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+    double *buf = (double *)h->scratch(4, sizeof(double) * (size_t)blocks * threads);
+    if (!buf) return set_err(h, SCPB_ERR_CUDA, "scratch allocation failed");
+    cudaStream_t st = h->stream;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) {
+        SCPB_CUDA(h, cudaEventRecord(h->ev0, st));
+        k_fp64_peak<<<blocks, threads, 0, st>>>(buf, iters, 0.999999, 1e-6);
+        h->launches++;
+        SCPB_CUDA(h, cudaEventRecord(h->ev1, st));
+        SCPB_CUDA(h, cudaStreamSynchronize(st));
+        float ms = 0.f;
+        SCPB_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        const double tf = 2.0 * 16.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    *tflops = best;
+    return SCPB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // scpb_propagate: final continuous-time trajectory (discretization.jl:515-562, FOH branch)
 template <class M>
-static void launch_prop(scpb_handle_s *h, const PropArgs &a)
+static int launch_prop(scpb_handle_s *h, const PropArgs &a, int method, int subres)
 {
-    k_propagate_foh<M><<<(a.B + 31) / 32, 32, 0, h->stream>>>(a);
+    if (method == SCPB_IMPULSE) {
+        if constexpr (M::IMPULSE) {
+            const long long items = (long long)a.B * (a.N - 1);
+            k_propagate_impulse<M><<<(unsigned)((items + 63) / 64), 64, 0, h->stream>>>(a, subres);
+        } else {
+            return set_err(h, SCPB_ERR_UNSUPPORTED, "model %d has no impulse semantics (IMPULSE propagation)", h->model_id);
+        }
+    } else {
+        k_propagate_foh<M><<<(a.B + 31) / 32, 32, 0, h->stream>>>(a);
+    }
     h->launches++;
+    return SCPB_OK;
 }
 
 int32_t scpb_propagate(scpb_handle h, int32_t method, int32_t B, int32_t N, int32_t res, const double *t_grid,
@@ -249,12 +311,16 @@ int32_t scpb_propagate(scpb_handle h, int32_t method, int32_t B, int32_t N, int3
 {
     int rc = check_model(h);
     if (rc) return rc;
-    if (method != SCPB_FOH) return set_err(h, SCPB_ERR_UNSUPPORTED, "only FOH propagation is implemented");
+    if (method != SCPB_FOH && method != SCPB_IMPULSE) return set_err(h, SCPB_ERR_ARG, "unknown discretization method %d", method);
     if (!t_grid || !xd || !ud || !p || !xc) return set_err(h, SCPB_ERR_ARG, "null pointer");
     if (B <= 0 || N < 2 || res < 2) return set_err(h, SCPB_ERR_ARG, "bad sizes B=%d N=%d res=%d", B, N, res);
     SCPB_CUDA(h, cudaSetDevice(h->device));
     const size_t nx = h->nx, nu = h->nu, np = h->np, nb = B;
-    const size_t s_t = N, s_x = nb * N * nx, s_u = nb * N * nu, s_p = nb * np, s_c = nb * (size_t)res * nx;
+    // IMPULSE: 1 + (N-1)*ceil(res/(N-1)) columns per seed (discretization.jl:541-556), FOH: res columns
+    const int subres = (res + (N - 1) - 1) / (N - 1);
+    const size_t ncol = (method == SCPB_IMPULSE) ? 1 + (size_t)(N - 1) * subres : (size_t)res;
+    if (method == SCPB_IMPULSE && subres < 2) return set_err(h, SCPB_ERR_ARG, "IMPULSE propagation needs res >= 2 (N-1)");
+    const size_t s_t = N, s_x = nb * N * nx, s_u = nb * N * nu, s_p = nb * np, s_c = nb * ncol * nx;
     double *din = (double *)h->scratch(1, sizeof(double) * (s_t + s_x + s_u + s_p));
     double *dout = (double *)h->scratch(2, sizeof(double) * s_c);
     if (!din || !dout) return set_err(h, SCPB_ERR_CUDA, "device allocation failed");
@@ -270,13 +336,15 @@ int32_t scpb_propagate(scpb_handle h, int32_t method, int32_t B, int32_t N, int3
     cudaEvent_t e0 = h->ev0, e1 = h->ev1;   // the handle's own pair: nothing to leak on an error path
     SCPB_CUDA(h, cudaEventRecord(e0, st));
     switch (h->model_id) {
-    case SCPB_MODEL_DBLINT: launch_prop<Model<SCPB_MODEL_DBLINT>>(h, a); break;
-    case SCPB_MODEL_ROCKET: launch_prop<Model<SCPB_MODEL_ROCKET>>(h, a); break;
-    case SCPB_MODEL_STARSHIP: launch_prop<Model<SCPB_MODEL_STARSHIP>>(h, a); break;
-    case SCPB_MODEL_QUADROTOR: launch_prop<Model<SCPB_MODEL_QUADROTOR>>(h, a); break;
-    case SCPB_MODEL_FREEFLYER: launch_prop<Model<SCPB_MODEL_FREEFLYER>>(h, a); break;
+    case SCPB_MODEL_DBLINT: rc = launch_prop<Model<SCPB_MODEL_DBLINT>>(h, a, method, subres); break;
+    case SCPB_MODEL_ROCKET: rc = launch_prop<Model<SCPB_MODEL_ROCKET>>(h, a, method, subres); break;
+    case SCPB_MODEL_STARSHIP: rc = launch_prop<Model<SCPB_MODEL_STARSHIP>>(h, a, method, subres); break;
+    case SCPB_MODEL_QUADROTOR: rc = launch_prop<Model<SCPB_MODEL_QUADROTOR>>(h, a, method, subres); break;
+    case SCPB_MODEL_FREEFLYER: rc = launch_prop<Model<SCPB_MODEL_FREEFLYER>>(h, a, method, subres); break;
+    case SCPB_MODEL_RENDEZVOUS2D: rc = launch_prop<Model<SCPB_MODEL_RENDEZVOUS2D>>(h, a, method, subres); break;
     default: return set_err(h, SCPB_ERR_MODEL, "unknown model id %d", h->model_id);
     }
+    if (rc) return rc;
     SCPB_CUDA(h, cudaEventRecord(e1, st));
     SCPB_CUDA(h, cudaGetLastError());
     SCPB_CUDA(h, cudaMemcpyAsync(xc, dout, sizeof(double) * s_c, cudaMemcpyDeviceToHost, st));

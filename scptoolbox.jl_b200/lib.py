@@ -14,7 +14,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.environ.get("SCPB_LIBRARY") or os.path.join(HERE, "libscpb.so")   # override: A/B runs of kernel variants
 
-MODEL_DBLINT, MODEL_ROCKET, MODEL_STARSHIP, MODEL_QUADROTOR, MODEL_FREEFLYER = 1, 2, 3, 4, 5
+MODEL_DBLINT, MODEL_ROCKET, MODEL_STARSHIP, MODEL_QUADROTOR, MODEL_FREEFLYER, MODEL_RENDEZVOUS2D = 1, 2, 3, 4, 5, 6
 FOH, IMPULSE = 0, 1
 
 _lib = None
@@ -58,6 +58,7 @@ SIGNATURES = {
                                          _ip, _ip, _dp, _dp, _dp, C.c_double, C.c_double, _dp, _dp, C.POINTER(C.c_int64)]),
     "scpb_debug_kkt_solve_sn": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _ip, _ip, _ip, _ip, C.c_int32, C.c_int32,
                                          _ip, _ip, _dp, _dp, _dp, C.c_double, C.c_double, _dp, _dp, C.POINTER(C.c_int64)]),
+    "scpb_debug_fp64_peak": (C.c_int32, [C.c_void_p, _dp]),
     "scpb_debug_kkt_solve_dev": (C.c_int32, [C.c_void_p, C.c_int32, _dp, _dp, _dp, C.c_double, _dp, _dp, _ip]),
     "scpb_debug_kkt_new": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _ip, _ip, _ip, _ip, C.c_int32, C.c_int32, _ip, _ip,
                                        C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
@@ -85,7 +86,8 @@ class ScvxDesc(C.Structure):        # scpb_scvx_desc (include/scpb.h)
                                            "eta_ub")] + [(k, C.c_int32) for k in ("oeta", "n_ic", "n_tc", "reserved")]
 
 
-CONE_STATUS = {0: "OPTIMAL", 1: "ITERATION_LIMIT", 2: "NUMERICAL_ERROR", 3: "ALMOST_OPTIMAL"}
+CONE_STATUS = {0: "OPTIMAL", 1: "ITERATION_LIMIT", 2: "NUMERICAL_ERROR", 3: "ALMOST_OPTIMAL", 4: "INFEASIBLE",
+               5: "DUAL_INFEASIBLE"}
 
 
 class ScpbError(RuntimeError):
@@ -197,14 +199,33 @@ class Handle:
         tg, ptg = _f64(t_grid)
         B, N = xd.shape[0], xd.shape[1]
         assert xd.shape == (B, N, self.nx) and ud.shape == (B, N, self.nu) and p.shape == (B, self.np)
-        xc = np.empty((B, int(res), self.nx))
+        if method == IMPULSE:     # discretization.jl:539-558: xd[:,1] + ceil(res/(N-1)) columns per interval
+            sub = -(-int(res) // (N - 1))
+            ncol = 1 + (N - 1) * sub
+        else:
+            ncol = int(res)
+        xc = np.empty((B, ncol, self.nx))
         sec = C.c_double(0.0)
         rc = self.lib.scpb_propagate(self.h, method, B, N, int(res), ptg, pxd, pud, pp, xc.ctypes.data_as(_dp),
                                      C.byref(sec))
         self._check(rc, "scpb_propagate")
+        if method == IMPULSE:
+            dt = float(np.sqrt(np.finfo(float).eps))          # the reference's tiny "impulse duration" offset
+            tc = [0.0]
+            for k in range(N - 1):
+                seg = [(1.0 - j / (sub - 1)) * tg[k] + (j / (sub - 1)) * tg[k + 1] for j in range(sub)]
+                seg[0] += dt
+                tc.extend(seg)
+            return np.array(tc), xc, sec.value
         d = res - 1
         tc = np.array([(1.0 - j / d) * 0.0 + (j / d) * 1.0 for j in range(res)])
         return tc, xc, sec.value
+
+    def fp64_peak(self):
+        """Measured fp64 FMA throughput of this device in TFLOP/s (scpb_debug_fp64_peak)."""
+        v = C.c_double(0.0)
+        self._check(self.lib.scpb_debug_fp64_peak(self.h, C.byref(v)), "scpb_debug_fp64_peak")
+        return v.value
 
     def discretize_dev(self, t_grid, xd, ud, p, iSx_diag, feas_tol, Nsub, A, Bm, Bp, F, r, E, defect, feas,
                        B, N, method=FOH):

@@ -16,10 +16,10 @@ P = dict(bench.PTR); P["iter_max"] = int(os.environ.get("ITER_MAX", str(P["iter_
 pars = pkg.ptr.Parameters(N=N, Nsub=Nsub, disc_method=pkg.ptr.FOH, q_tr=np.inf, q_exit=np.inf, **P)
 base = traj.guess(N)
 pbm = pkg.ptr.create(pars, traj, h)
-X, U, Pp = bench.make_seeds(base, pbm.scale.Sx, pbm.scale.Su, B, 0)
-variants = [("sn1 t1024", "1", dict()), ("sn0 t1024", "0", dict()), ("sn1 t512", "1", dict(threads=512)),
-            ("sn1 g1 t512", "1", dict(group=1, threads=512)), ("sn1 g4", "1", dict(group=4)),
-            ("sn1 tol1e-10", "1", dict(feastol=1e-10, abstol=1e-10, reltol=1e-10))]
+X, U, Pp = bench.make_seeds(base, pbm.scale.Sx, pbm.scale.Su, B, 0, pbm.scale.cx, pbm.scale.cu)
+variants = [("sn0 t1024", "0", dict()), ("sn1 t1024", "1", dict()), ("sn0 t512", "0", dict(threads=512)),
+            ("sn0 tol1e-10", "0", dict(feastol=1e-10, abstol=1e-10, reltol=1e-10)),
+            ("sn0 old-delta", "0", dict(delta=1e-9, delta_dyn=1e-9))]
 want = sys.argv[4:]
 ref = None
 for name, sn, opts in variants:

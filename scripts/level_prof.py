@@ -13,7 +13,7 @@ P = dict(bench.PTR); P["iter_max"] = 1
 pars = pkg.ptr.Parameters(N=N, Nsub=Nsub, disc_method=pkg.ptr.FOH, q_tr=np.inf, q_exit=np.inf, **P)
 base = traj.guess(N)
 pbm = pkg.ptr.create(pars, traj, h)
-X, U, Pp = bench.make_seeds(base, pbm.scale.Sx, pbm.scale.Su, B, 0)
+X, U, Pp = bench.make_seeds(base, pbm.scale.Sx, pbm.scale.Su, B, 0, pbm.scale.cx, pbm.scale.cu)
 opts = eval(os.environ.get('CONE_OPTS', '{}'))
 sol = pkg.ptr.solve(pbm, (X, U, Pp), **opts)
 info = pbm.cone.info()

@@ -196,6 +196,34 @@ def test_device_kkt_solve_on_the_product_template(handle, pkg, monkeypatch, sn):
     pbm.close()
 
 
+def test_infeasibility_certificates(handle, pkg):
+    """termination_status values the reference branches on (program.jl:427-428; scp.jl:470-473 DUAL_INFEASIBLE while
+    computing the scaling, :975 unsafe_solution): an infeasible and an unbounded program in the same batch as a solvable
+    one must come back INFEASIBLE / DUAL_INFEASIBLE / OPTIMAL, seed by seed."""
+    # variables (x1, x2); rows: -x1 <= h1, -x2 <= h2, x1 + x2 <= h3 ; equality x1 - x2 = b
+    A = sp.csr_matrix(np.array([[1.0, -1.0]]))
+    G = sp.csr_matrix(np.array([[-1.0, 0.0], [0.0, -1.0], [1.0, 1.0]]))
+    cone = pkg.lib.ConeProblem(handle, A, G, 3, [])
+    Av = np.tile(A.data, (3, 1)); Gv = np.tile(G.data, (3, 1))
+    c = np.array([[1.0, 1.0], [1.0, 1.0], [-1.0, -1.0]])
+    b = np.array([[0.0], [0.0], [0.0]])
+    h = np.array([[0.0, 0.0, 2.0],        # solvable: min x1+x2, x >= 0, x1 + x2 <= 2, x1 = x2 -> 0
+                  [-2.0, -2.0, 1.0],      # infeasible: x1 >= 2, x2 >= 2, x1 + x2 <= 1
+                  [0.0, 0.0, 2.0]])       # seed 2 becomes unbounded below by dropping the cap (huge h3 is not enough):
+    Gv[2, -2:] = 0.0                      # ... zero the row x1 + x2 <= h3 -> min -(x1+x2), x >= 0, x1 = x2: unbounded
+    out = cone.solve(Av, Gv, c, b, h)
+    assert list(out["status"]) == [0, 4, 5], (out["status"], out["iters"])
+    assert abs(out["pobj"][0]) < 1e-7
+    y, z = out["y"][1], out["z"][1]       # the returned (y, z) is the certificate, up to scale
+    Ad, Gd = A.toarray(), G.toarray()
+    nrm = -(b[1] @ y + h[1] @ z)
+    assert nrm > 0 and np.abs(Ad.T @ y + Gd.T @ z).max() <= 1e-6 * nrm and (z > -1e-9 * nrm).all()
+    x = out["x"][2]
+    G2 = Gd.copy(); G2[2] = 0.0
+    assert c[2] @ x < 0 and np.abs(Ad @ x).max() <= 1e-6 * abs(c[2] @ x) and (G2 @ x).max() <= 1e-6 * abs(c[2] @ x)
+    cone.close()
+
+
 def test_cone_error_paths(handle, pkg):
     A = sp.csr_matrix(np.array([[1.0, 1.0]])); G = sp.csr_matrix(-np.eye(2))
     with pytest.raises(pkg.ScpbError):

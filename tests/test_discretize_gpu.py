@@ -102,3 +102,64 @@ def test_launch_counter_and_error_paths(handle, pkg):
         handle.model_set(99, [0.0], 2, 1, 1)
     with pytest.raises(pkg.ScpbError):
         handle.model_set(pkg.lib.MODEL_STARSHIP, [0.0] * 9, 7, 3, 10)  # wrong nx
+
+
+def _rendezvous(pkg, handle):
+    """planar rendezvous pack (rendezvous_planar/parameters.jl:87-111): the only pack with impulse semantics"""
+    par = [30e3, 30e3 * 4.0, 0.6, 2.1, 2 * np.pi / 5400.0]
+    handle.model_set(pkg.lib.MODEL_RENDEZVOUS2D, par, 6, 12, 1)
+    return orc.make_model(orc.MODEL_RENDEZVOUS2D, 6, 12, 1, par)
+
+
+def test_impulse_discretization_matches_oracle(pkg, handle):
+    """IMPULSE discretize! (discretization.jl:186-193 jump, :304-340 derivs_impulse, :384-390 B_k = A_k B(t_k, -k)) on the
+    rendezvous pack, the reference's own IMPULSE configuration (rendezvous_planar/tests.jl:34, Nsub = 15)."""
+    m = _rendezvous(pkg, handle)
+    rng = np.random.default_rng(3)
+    nb, N, Nsub = 5, 9, 15
+    xd = rng.standard_normal((nb, N, 6)) * np.array([50, 50, 0.5, 0.5, 0.3, 0.01])
+    ud = np.zeros((nb, N, 12)); ud[:, :, :3] = rng.uniform(0, 400.0, (nb, N, 3)); ud[:, :, 3:] = rng.standard_normal((nb, N, 9))
+    p = rng.uniform(200.0, 600.0, (nb, 1))
+    iS = 1.0 / np.array([100.0, 100.0, 1.0, 1.0, 1.0, 0.1])
+    out = handle.discretize(orc.t_grid(N), xd, ud, p, iS, 1e-2, Nsub, method=pkg.lib.IMPULSE)
+    for b in range(nb):
+        ref = orc.discretize_impulse(m, xd[b], ud[b], p[b], Nsub, iS, 1e-2)
+        col = lambda a, rr, cc: a.reshape(N - 1, cc, rr).transpose(0, 2, 1)
+        for name, got, want in (("A", col(out["A"][b], 6, 6), ref.A), ("B", col(out["Bm"][b], 6, 12), ref.Bm),
+                                ("F", col(out["F"][b], 6, 1), ref.F), ("r", out["r"][b], ref.r),
+                                ("E", col(out["E"][b], 6, 6), ref.E), ("defect", out["defect"][b], ref.defect)):
+            assert np.abs(got - want).max() <= 1e-11 * max(1.0, np.abs(want).max()), (b, name)
+        assert np.abs(out["Bp"][b]).max() == 0.0            # dyn.B has a single block for IMPULSE
+        assert bool(out["feas"][b]) == ref.feas
+    # a trajectory that follows the impulsive dynamics has zero defect (size-independent property): roll it out
+    # interval by interval with the IMPULSE propagate on the same sub-grid (ceil(res/(N-1)) = Nsub)
+    xr = xd.copy()
+    for k in range(N - 1):
+        xc = handle.propagate(orc.t_grid(N), xr, ud, p, Nsub * (N - 1), method=pkg.lib.IMPULSE)[1]
+        xr[:, k + 1] = xc[:, 1 + k * Nsub + Nsub - 1]
+    out2 = handle.discretize(orc.t_grid(N), xr, ud, p, iS, 1e-9, Nsub, method=pkg.lib.IMPULSE)
+    assert out2["feas"].all() and np.abs(out2["defect"]).max() <= 1e-9
+
+
+def test_impulse_propagate_matches_oracle(pkg, handle):
+    """propagate, IMPULSE branch (discretization.jl:539-558)."""
+    m = _rendezvous(pkg, handle)
+    rng = np.random.default_rng(4)
+    nb, N, res = 3, 7, 60
+    xd = rng.standard_normal((nb, N, 6)) * np.array([50, 50, 0.5, 0.5, 0.3, 0.01])
+    ud = np.zeros((nb, N, 12)); ud[:, :, :3] = rng.uniform(0, 400.0, (nb, N, 3))
+    p = rng.uniform(200.0, 600.0, (nb, 1))
+    tc, xc, _ = handle.propagate(orc.t_grid(N), xd, ud, p, res, method=pkg.lib.IMPULSE)
+    sub = -(-res // (N - 1))
+    assert xc.shape == (nb, 1 + (N - 1) * sub, 6) and tc.shape == (1 + (N - 1) * sub,)
+    for b in range(nb):
+        want = orc.propagate_impulse(m, xd[b], ud[b], p[b], res)
+        assert np.abs(xc[b] - want).max() <= 1e-10 * max(1.0, np.abs(want).max())
+
+
+def test_impulse_needs_an_impulse_pack(pkg, handle):
+    pb = problems.QuadrotorProblem()
+    handle.model_set(pb.model_id, pb.par(), pb.nx, pb.nu, pb.np)
+    xd, ud, p = problems.test_trajectory(pb, 1, 5, seed=1)
+    with pytest.raises(pkg.ScpbError):
+        handle.discretize(orc.t_grid(5), xd, ud, p, np.ones(pb.nx), 1e-3, 10, method=pkg.lib.IMPULSE)

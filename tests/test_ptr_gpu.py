@@ -1,17 +1,23 @@
 """GPU parity of the whole SCP hot path: batched PTR (scpb_ptr_solve through the host API) vs the oracle's
 PTR loop (oracle/ptr.py with the oracle IPM standing in for ECOS) on the same initial guesses.
 
-Stated tolerance (measured floor of round 1): final augmented cost 1e-6 relative,
-iteration counts equal (+-1), physical states / thrust / gimbal angle / parameters within 1e-4 of their ranges
-(measured: 4e-7 .. 1e-5); the auxiliary gimbal-rate pair (x[7], u[2]) is a flat direction of the LP subproblem (two
-interior-point codes agree on it only to ~1e-2) and is reported, not asserted.  Both must report SCP_SOLVED.
-North-star target is 1e-6 on the trajectory."""
+Stated tolerance = the north-star target: converged physical trajectory (states, thrust, gimbal angle, parameters)
+within 1e-6 of the ranges, final augmented cost within 1e-7 relative, iteration counts equal, same feasibility flags,
+both SCP_SOLVED.  Both interior-point solvers run at 1e-11 (TOL below; ECOS' default is 1e-8): an SCP loop amplifies
+subproblem errors -- the oracle run at 1e-8 is 2.4e-4 away from the oracle run at 1e-11 after 15 iterations of a seed
+that does not converge (measured, profiles/r2_parity_vs_tolerance.txt) -- so a 1e-6 comparison of two loops needs
+subproblem solutions tighter than that, on both sides.  The auxiliary gimbal-rate pair (x[7], u[2]) only enters two-sided
+rate constraints (definition.jl:544,740-743), is not determined by the LP (two exact solvers differ by 0.4 of its range
+on the very first subproblem) and is reported, not asserted."""
 import numpy as np
 import pytest
 
 from oracle import orc, problems, ptr as optr
 
 pytestmark = pytest.mark.gpu
+
+TOL = dict(feastol=1e-11, abstol=1e-11, reltol=1e-11)      # cone-solver tolerances of the parity runs (see above)
+OTOL = 1e-11                                               # the oracle interior point's tolerance
 
 
 def _setup(pkg, handle, N, Nsub, iter_max=15):
@@ -53,7 +59,7 @@ def test_batched_ptr_matches_oracle_ptr(pkg, handle, N, Nsub, nb):
     g = pbo.guess(N)
     mdl.hs = pbo.hs                      # same cost normalisation on both sides
     opars = optr.Parameters(N=N, Nsub=Nsub, iter_max=15, wvc=1e3, wtr=0.1, eps_abs=1e-5, eps_rel=0.01 / 100,
-                            feas_tol=5e-3, solver_tol=1e-9)
+                            feas_tol=5e-3, solver_tol=OTOL)
     P = optr.PTR(pbo, opars)
     rng = np.random.default_rng(N)
     sc = P.scale
@@ -61,7 +67,7 @@ def test_batched_ptr_matches_oracle_ptr(pkg, handle, N, Nsub, nb):
     U0 = np.array([g[1] + (0.01 * sc.Su * rng.standard_normal(g[1].shape) if b else 0.0) for b in range(nb)])
     P0 = np.array([g[2] * (1 + (0.02 * rng.uniform(-1, 1, g[2].shape) if b else 0.0)) for b in range(nb)])
     pbm = pkg.ptr.create(pars, traj, handle)
-    sol = pkg.ptr.solve(pbm, (X0, U0, P0))
+    sol = pkg.ptr.solve(pbm, (X0, U0, P0), **TOL)
     pbm.close()
     assert all(s == "SCP_SOLVED" for s in sol.status), sol.status
     for b in range(nb):
@@ -77,9 +83,9 @@ def test_batched_ptr_matches_oracle_ptr(pkg, handle, N, Nsub, nb):
         ex7 = np.abs((sol.xd[b][:, :7] - rs.xd[:, :7]) / sc.Sx[:7]).max()
         eu2 = np.abs((sol.ud[b][:, :2] - rs.ud[:, :2]) / sc.Su[:2]).max()
         print("parity seed", b, "ex(phys)", ex7, "eu(T,delta)", eu2, "ex(all)", ex, "eu(all)", eu, "ep", ep)
-        assert max(ex7, eu2, ep) <= 1e-4, (b, ex7, eu2, ep, sol.iterations[b], ref["iterations"])
-        assert abs(sol.cost[b] - rs.J_aug) <= 1e-6 * max(1.0, abs(rs.J_aug))
-        assert abs(int(sol.iterations[b]) - ref["iterations"]) <= 1
+        assert max(ex7, eu2, ep) <= 1e-6, (b, ex7, eu2, ep, sol.iterations[b], ref["iterations"])
+        assert abs(sol.cost[b] - rs.J_aug) <= 1e-7 * max(1.0, abs(rs.J_aug))
+        assert int(sol.iterations[b]) == ref["iterations"]
         assert bool(sol.feas[b]) == rs.feas
 
 
@@ -95,7 +101,7 @@ def test_fixed_iteration_ptr_parity(pkg, handle):
     g = pbo.guess(N)
     mdl.hs = pbo.hs
     opars = optr.Parameters(N=N, Nsub=Nsub, iter_max=K, wvc=1e3, wtr=0.1, eps_abs=0.0, eps_rel=0.0, feas_tol=5e-3,
-                            solver_tol=1e-9)
+                            solver_tol=OTOL)
     P = optr.PTR(pbo, opars)
     rng = np.random.default_rng(5)
     sc = P.scale
@@ -103,7 +109,7 @@ def test_fixed_iteration_ptr_parity(pkg, handle):
     U0 = np.array([g[1] + (0.01 * sc.Su * rng.standard_normal(g[1].shape) if b else 0.0) for b in range(nb)])
     P0 = np.array([g[2] * (1 + (0.02 * rng.uniform(-1, 1, g[2].shape) if b else 0.0)) for b in range(nb)])
     pbm = pkg.ptr.create(pars, traj, handle)
-    sol = pkg.ptr.solve(pbm, (X0, U0, P0))
+    sol = pkg.ptr.solve(pbm, (X0, U0, P0), **TOL)
     pkg.ptr.propagate(pbm, sol)            # SCPSolution's continuous-time trajectory (scp.jl:231-232)
     pbm.close()
     assert sol.xc.shape == (nb, 2 * Nsub * (N - 1), 8)
@@ -121,7 +127,7 @@ def test_fixed_iteration_ptr_parity(pkg, handle):
         ep = np.abs((sol.p[b] - rs.p) / sc.Sp).max()
         dJ = abs(sol.cost[b] - rs.J_aug) / max(1.0, abs(rs.J_aug))
         print("fixed-iteration parity seed", b, "ex(phys)", ex7, "eu(T,delta)", eu2, "ep", ep, "dJ", dJ)
-        assert max(ex7, eu2, ep) <= 1e-4 and dJ <= 1e-6
+        assert max(ex7, eu2, ep) <= 1e-6 and dJ <= 1e-7
 
 
 def _rocket_setup(pkg, handle, N, Nsub, iter_max=20):
@@ -143,7 +149,7 @@ def test_rocket_landing_ptr_matches_oracle_ptr(pkg, handle):
     pbo = problems.RocketProblem(N)
     g = pbo.guess(N)
     opars = optr.Parameters(N=N, Nsub=Nsub, iter_max=20, wvc=1e3, wtr=0.1, eps_abs=1e-5, eps_rel=0.01 / 100,
-                            feas_tol=1e-3, solver_tol=1e-9)
+                            feas_tol=1e-3, solver_tol=OTOL)
     P = optr.PTR(pbo, opars)
     sc = P.scale
     rng = np.random.default_rng(21)
@@ -152,19 +158,19 @@ def test_rocket_landing_ptr_matches_oracle_ptr(pkg, handle):
     P0 = np.array([g[2] * (1 + (0.02 * rng.uniform(-1, 1, g[2].shape) if b else 0.0)) for b in range(nb)])
     pbm = pkg.ptr.create(pars, traj, handle)
     assert list(pbm.cp["soc_dims"]) == [4] * (2 * N)
-    sol = pkg.ptr.solve(pbm, (X0, U0, P0))
+    sol = pkg.ptr.solve(pbm, (X0, U0, P0), **TOL)
     pbm.close()
     for b in range(nb):
         ref = P.solve((X0[b], U0[b], P0[b]), prefer="ipm")
         rs = ref["sol"]
         assert sol.status[b] == ref["status"] == "SCP_SOLVED", (sol.status, sol.raw_status, ref["status"])
-        assert abs(int(sol.iterations[b]) - ref["iterations"]) <= 1
+        assert int(sol.iterations[b]) == ref["iterations"]
         ex = np.abs((sol.xd[b] - rs.xd) / sc.Sx).max()
         eu = np.abs((sol.ud[b] - rs.ud) / sc.Su).max()
         ep = np.abs((sol.p[b] - rs.p) / sc.Sp).max()
         dJ = abs(sol.cost[b] - rs.J_aug) / max(1.0, abs(rs.J_aug))
         print("rocket parity seed", b, "ex", ex, "eu", eu, "ep", ep, "dJ", dJ, "iters", sol.iterations[b], ref["iterations"])
-        assert dJ <= 1e-6 and max(ex, eu, ep) <= 1e-4
+        assert dJ <= 1e-7 and max(ex, eu, ep) <= 1e-6
         assert bool(sol.feas[b])
         # the converged landing is physical: thrust slack tight (LCvx), final mass above dry mass
         a, xi = sol.ud[b][:, 0:3], sol.ud[b][:, 3]
@@ -205,18 +211,18 @@ def test_double_integrator_min_time_known_answer(pkg, handle):
         pars = pkg.ptr.Parameters(N=N, Nsub=Nsub, iter_max=30, disc_method=pkg.ptr.FOH, wvc=1e3, wtr=0.1, eps_abs=1e-5,
                                   eps_rel=1e-4, feas_tol=1e-3, q_tr=np.inf, q_exit=np.inf)
         pbm = pkg.ptr.create(pars, traj, handle)
-        sol = pkg.ptr.solve(pbm)                    # the problem's own guess, one seed
+        sol = pkg.ptr.solve(pbm, **TOL)             # the problem's own guess, one seed
         pbm.close()
         pbo = problems.DoubleIntegratorProblem(N, choice)
         opars = optr.Parameters(N=N, Nsub=Nsub, iter_max=30, wvc=1e3, wtr=0.1, eps_abs=1e-5, eps_rel=1e-4,
-                                feas_tol=1e-3, solver_tol=1e-9)
+                                feas_tol=1e-3, solver_tol=OTOL)
         ref = optr.PTR(pbo, opars).solve(pbo.guess(N))
         T, _ = mdl.t_opt()
         print("dblint choice", choice, "tf", sol.p[0, 0], "oracle", ref["sol"].p[0], "analytic", T, "iters",
               sol.iterations[0], ref["iterations"])
         assert sol.status[0] == ref["status"] == "SCP_SOLVED"
-        assert abs(int(sol.iterations[0]) - ref["iterations"]) <= 1
+        assert int(sol.iterations[0]) == ref["iterations"]
         assert T * (1 - 1e-6) <= sol.p[0, 0] <= T * (1 + 5e-3)
-        assert abs(sol.p[0, 0] - ref["sol"].p[0]) <= 1e-5 * T
-        assert np.abs(sol.xd[0] - ref["sol"].xd).max() <= 1e-4 * mdl.s
-        assert abs(sol.cost[0] - ref["sol"].J_aug) <= 1e-6 * max(1.0, abs(ref["sol"].J_aug))
+        assert abs(sol.p[0, 0] - ref["sol"].p[0]) <= 1e-6 * T
+        assert np.abs(sol.xd[0] - ref["sol"].xd).max() <= 1e-6 * mdl.s
+        assert abs(sol.cost[0] - ref["sol"].J_aug) <= 1e-7 * max(1.0, abs(ref["sol"].J_aug))

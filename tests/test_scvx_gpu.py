@@ -16,6 +16,8 @@ from oracle import problems, scvx as oscvx
 
 pytestmark = pytest.mark.gpu
 
+TOL = dict(feastol=1e-11, abstol=1e-11, reltol=1e-11)      # cone-solver tolerances of the parity runs
+
 KW = dict(lam=5e2, rho_0=0.0, rho_1=0.1, rho_2=0.7, beta_sh=2.0, beta_gr=2.0, eta_init=1.0, eta_lb=1e-8, eta_ub=10.0,
           eps_abs=1e-5, eps_rel=0.01 / 100, feas_tol=5e-3)
 
@@ -36,17 +38,17 @@ def test_batched_scvx_matches_oracle_scvx(pkg, handle, N, Nsub, nb, iter_max):
     pbo = problems.StarshipProblem(N)
     g = pbo.guess(N)
     mdl.hs = pbo.hs
-    S = oscvx.SCvx(pbo, oscvx.Parameters(N=N, Nsub=Nsub, iter_max=iter_max, **KW))
+    S = oscvx.SCvx(pbo, oscvx.Parameters(N=N, Nsub=Nsub, iter_max=iter_max, solver_tol=1e-11, **KW))
     sc = S.scale
     rng = np.random.default_rng(N)
     X0 = np.array([g[0] + (0.01 * sc.Sx * rng.standard_normal(g[0].shape) if b else 0.0) for b in range(nb)])
     U0 = np.array([g[1] + (0.01 * sc.Su * rng.standard_normal(g[1].shape) if b else 0.0) for b in range(nb)])
     P0 = np.array([g[2] * (1 + (0.02 * rng.uniform(-1, 1, g[2].shape) if b else 0.0)) for b in range(nb)])
     pbm = pkg.scvx.create(pars, traj, handle)
-    sol = pkg.scvx.solve(pbm, (X0, U0, P0))
+    sol = pkg.scvx.solve(pbm, (X0, U0, P0), **TOL)
     pbm.close()
     for b in range(nb):
-        ref = S.solve((X0[b], U0[b], P0[b]))
+        ref = S.solve((X0[b], U0[b], P0[b]), prefer="ipm")
         rs = ref["sol"]
         ex7 = np.abs((sol.xd[b][:, :7] - rs.xd[:, :7]) / sc.Sx[:7]).max()
         eu2 = np.abs((sol.ud[b][:, :2] - rs.ud[:, :2]) / sc.Su[:2]).max()
@@ -72,12 +74,12 @@ def test_scvx_first_iterations_are_identical(pkg, handle):
     g = pbo.guess(N)
     mdl.hs = pbo.hs
     kw = dict(KW); kw["eps_abs"] = 0.0; kw["eps_rel"] = 0.0
-    S = oscvx.SCvx(pbo, oscvx.Parameters(N=N, Nsub=Nsub, iter_max=K, **kw))
+    S = oscvx.SCvx(pbo, oscvx.Parameters(N=N, Nsub=Nsub, iter_max=K, solver_tol=1e-11, **kw))
     sc = S.scale
     pbm = pkg.scvx.create(pars, traj, handle)
-    sol = pkg.scvx.solve(pbm, (g[0][None], g[1][None], g[2][None]))
+    sol = pkg.scvx.solve(pbm, (g[0][None], g[1][None], g[2][None]), **TOL)
     pbm.close()
-    ref = S.solve(g)
+    ref = S.solve(g, prefer="ipm")
     rs = ref["sol"]
     assert int(sol.iterations[0]) == ref["iterations"] == K
     assert sol.eta[0] == ref["eta"]
