@@ -153,7 +153,8 @@ int32_t scpb_cone_solve(scpb_cone c, int32_t B, const double *Avals, const doubl
  * the fill matrix W with [Avals; Gvals; c; b; h; c0] = W * src, where src is the per-seed vector of
  * device-computed quantities laid out by the offsets below (source 0 is the constant 1):
  *   oA,oBm,oBp,oF,or_,oE : DLTV blocks per segment (column-major nx*nx, nx*nu, nx*nf, nx) -- discretize!
- *   oC,oD,oG,ors         : ds/dx, ds/du, ds/dp (row-major) and r = s - Cx - Du - Gp per node (scp.jl:763-773)
+ *   oC,oD,oG,ors         : ds/dx, ds/du, ds/dp (row-major; ds/dp packed to ng columns, see csrc/constraints.cuh)
+ *                          and r = s - Cx - Du - Gp per node (scp.jl:763-773)
  *   oxh,ouh,oph          : scaled reference trajectory (ptr.jl:575-577)
  * vx,vu,vp are the offsets of the scaled x, u, p variable blocks inside the cone program's variables. */
 typedef struct scpb_ptr_s *scpb_ptr;
@@ -164,6 +165,7 @@ typedef struct {
     int32_t nval, vx, vu, vp;
     int32_t q_exit;          /* stopping-criterion norm: 0 = Inf, 1, 2 (pars.q_exit) */
     int32_t iter_max;
+    int32_t ng;              /* packed columns of ds/dp per node (the constraint pack's NG; = np for most packs) */
     double eps_abs, eps_rel, feas_tol;
 } scpb_ptr_desc;
 

@@ -424,23 +424,196 @@ class QuadrotorProblem(_DynOnly):
 
 
 class FreeFlyerProblem(_DynOnly):
-    """freeflyer/parameters.jl:105-190; np = 1 + 6N (room SDF slack per node)."""
+    """freeflyer/parameters.jl:105-190 and definition.jl (scaling advice :52-67, guess :84-167, cost :170-222, convex
+    sets :286-375, nonconvex constraints :376-442, boundary conditions :455-520); np = 1 + 6N (room SDF slack per node).
+    The PTR instance (BASELINE config C5) uses the SCvx flavour of the running cost (definition.jl:190-204)."""
     name = "freeflyer"
     model_id = orc.MODEL_FREEFLYER
     nx, nu = 13, 6
+    ns = 4
 
     def __init__(self, N: int):
         self.N = N
-        self.n_iss = 6
+        self.n_iss, self.n_obs = 6, 3
         self.np = 1 + self.n_iss * N
         self.mass = 7.2
         self.J = np.diag([0.1083, 0.1083, 0.1083])
         self.v_max, self.omega_max = 0.4, deg2rad(1)
         self.T_max, self.M_max = 20e-3, 1e-4
         self.tf_min, self.tf_max = 60.0, 200.0
+        self.gamma, self.hom, self.eps_sdf = 0.0, 50.0, 1e-4
+        z_iss = 4.75
+        self.obs_H = [np.diag([1.0, 1.0, 1.0]) / 0.3] * 3
+        self.obs_c = [np.array([8.5, -0.15, 5.0]), np.array([11.2, 1.84, 5.0]), np.array([11.3, 3.8, 4.8])]
+        self.rooms = [self._room([6.0, 0.0, z_iss], 1.0, 1.0, 1.5, 0.0, 90.0),
+                      self._room([7.5, 0.0, z_iss], 2.0, 2.0, 4.0, 0.0, 90.0),
+                      self._room([11.5, 0.0, z_iss], 1.25, 1.25, 0.5, 0.0, 90.0),
+                      self._room([10.75, -1.0, z_iss], 1.5, 1.5, 1.5, -90.0, 90.0),
+                      self._room([10.75, 1.0, z_iss], 1.5, 1.5, 1.5, 90.0, 90.0),
+                      self._room([10.75, 2.5, z_iss], 2.5, 2.5, 4.5, 90.0, 90.0)]
+        self.r0 = np.array([6.5, -0.2, 5.0]); self.v0 = np.array([0.035, 0.035, 0.0])
+        self.q0 = self._qaa(deg2rad(-40), [0.0, 1.0, 1.0]); self.w0 = np.zeros(3)
+        self.rf = np.array([11.3, 6.0, 4.5]); self.vf = np.zeros(3)
+        self.qf = self._qaa(0.0, [0.0, 0.0, 1.0]); self.wf = np.zeros(3)
+
+    # ---- geometry / quaternion helpers (src/utils/hyperrectangle.jl:85-138, quaternion.jl) ----
+    @staticmethod
+    def _room(offset, width, height, depth, yaw, pitch):
+        cd = lambda a: math.cos(math.radians(a)); sd = lambda a: math.sin(math.radians(a))
+        lo = np.array([-width / 2, -height / 2, 0.0]); hi = np.array([width / 2, height / 2, depth])
+        Rz = np.array([[cd(yaw), -sd(yaw), 0], [sd(yaw), cd(yaw), 0], [0, 0, 1]])
+        Ry = np.array([[cd(pitch), 0, sd(pitch)], [0, 1, 0], [-sd(pitch), 0, cd(pitch)]])
+        R = Rz @ Ry
+        lr, ur = R @ lo, R @ hi
+        l = np.minimum(lr, ur) + np.asarray(offset, float); u = np.maximum(lr, ur) + np.asarray(offset, float)
+        return (u + l) / 2, (u - l) / 2
+
+    @staticmethod
+    def _qaa(alpha, axis):
+        a = np.asarray(axis, float); a = a / np.linalg.norm(a)
+        return np.concatenate([a * math.sin(alpha / 2), [math.cos(alpha / 2)]])
+
+    @staticmethod
+    def _qmul(q, p):
+        return np.concatenate([q[3] * p[:3] + np.cross(q[:3], p[:3]) + q[:3] * p[3], [q[3] * p[3] - q[:3] @ p[:3]]])
+
+    @staticmethod
+    def _qlog(q):
+        nv = np.linalg.norm(q[:3])
+        return 2 * math.atan2(nv, q[3]), q[:3] / nv
+
+    def idd(self, i, k):
+        return 1 + i + self.n_iss * k
 
     def par(self):
-        return np.concatenate([[self.mass], self.J.flatten(order="F"), np.linalg.inv(self.J).flatten(order="F")])
+        ob = []
+        for H, c in zip(self.obs_H, self.obs_c):
+            ob += list(H.flatten(order="F")) + list(c)
+        return np.concatenate([[self.mass], self.J.flatten(order="F"), np.linalg.inv(self.J).flatten(order="F"),
+                               [self.hom], ob])
+
+    def ranges(self):
+        lo, hi = np.minimum(self.r0, self.rf), np.maximum(self.r0, self.rf)
+        xrg = [(lo[i], hi[i]) for i in range(3)] + [None] * 10
+        urg = [None] * 6
+        prg = [(self.tf_min, self.tf_max)] + [(-100.0, 1.0)] * (self.np - 1)
+        return xrg, urg, prg
+
+    def cost_emit(self, prg, x, u, p, t):
+        """terminal eps_sdf * sum(-delta) (+ gamma (tdil/tdil_max)^2) and the trapezoid rule of the convex running cost
+        (1 - gamma) (|T|^2 / T_max^2 + |M|^2 / M_max^2), one rotated second-order cone per node"""
+        from . import conic
+        from .ptr import trapz
+        J = conic.Aff()
+        for i in range(1, self.np):
+            J = J + p[i] * (-self.eps_sdf)
+        run = []
+        for k in range(self.N):
+            q = prg.new_variable(1, f"_q{k}")[0]
+            es = [u[i, k] * (1.0 / self.T_max) for i in range(3)] + [u[3 + i, k] * (1.0 / self.M_max) for i in range(3)]
+            prg.soc([q + 1.0] + [e * 2.0 for e in es] + [q - 1.0], "input_energy")
+            run.append(q * (1.0 - self.gamma))
+        return J + trapz(run, t)
+
+    def guess(self, N):
+        p = np.zeros(self.np)
+        ft = 0.5 * (self.tf_min + self.tf_max)
+        p[0] = ft
+        x = np.zeros((N, 13))
+        speed = np.abs(self.rf - self.r0).sum() / ft
+        times = np.array([(1 - k / (N - 1)) * 0.0 + (k / (N - 1)) * ft for k in range(N)])
+        cum = np.cumsum(np.abs(self.rf - self.r0) / speed)
+        for k in range(N):
+            tk = min(times[k], cum[2])
+            for i in range(3):
+                if tk <= cum[i]:
+                    t0 = cum[i - 1] if i > 0 else 0.0
+                    tf = cum[i]
+                    r0 = self.r0.copy(); r0[:i] = self.rf[:i]
+                    rf = r0.copy(); rf[i] = self.rf[i]
+                    c = (tf - tk) / (tf - t0)
+                    x[k, 0:3] = c * r0 + (1 - c) * rf
+                    d = rf - r0
+                    x[k, 3:6] = speed * d / np.linalg.norm(d)
+                    break
+        qc = np.concatenate([-self.q0[:3], [self.q0[3]]])
+        da, dax = self._qlog(self._qmul(qc, self.qf))
+        for k in range(N):
+            tau = max(0.0, min(1.0, k / (N - 1)))
+            x[k, 6:10] = self._qmul(self.q0, self._qaa(tau * da, dax))
+        ang, ax = self._qlog(self._qmul(self.qf, qc))
+        x[:, 10:13] = (ang / ft) * ax
+        for i in range(self.n_iss):
+            c, s_ = self.rooms[i]
+            for k in range(N):
+                p[self.idd(i, k)] = 1 - np.abs((x[k, 0:3] - c) / s_).max()
+        return x, np.zeros((N, 6)), p
+
+    # nonconvex path constraints (definition.jl:376-442); k is 1-based
+    def _ell(self, r):
+        s = np.zeros(self.n_obs); g = np.zeros((self.n_obs, 3))
+        for i in range(self.n_obs):
+            y = self.obs_H[i] @ (r - self.obs_c[i])
+            E = np.linalg.norm(y)
+            s[i] = 1 - E
+            g[i] = -(self.obs_H[i].T @ y) / E
+        return s, g
+
+    def _lse(self, d):
+        a = np.max(self.hom * d)
+        e = np.exp(self.hom * d - a)
+        return (a + math.log(e.sum())) / self.hom, e / e.sum()
+
+    def s(self, t, k, x, u, p):
+        s, _ = self._ell(x[0:3])
+        d, _ = self._lse(np.array([p[self.idd(i, k - 1)] for i in range(self.n_iss)]))
+        return np.concatenate([s, [-d]])
+
+    def C(self, t, k, x, u, p):
+        C = np.zeros((self.ns, 13))
+        C[:self.n_obs, 0:3] = self._ell(x[0:3])[1]
+        return C
+
+    def D(self, t, k, x, u, p):
+        return np.zeros((self.ns, 6))
+
+    def G(self, t, k, x, u, p):
+        G = np.zeros((self.ns, self.np))
+        _, w = self._lse(np.array([p[self.idd(i, k - 1)] for i in range(self.n_iss)]))
+        for i in range(self.n_iss):
+            G[self.ns - 1, self.idd(i, k - 1)] = -w[i]
+        return G
+
+    def gic(self, x, p):
+        return x[0:13] - np.concatenate([self.r0, self.v0, self.q0, self.w0])
+
+    def H0(self, x, p):
+        return np.eye(13)
+
+    K0 = None
+
+    def gtc(self, x, p):
+        return x[0:13] - np.concatenate([self.rf, self.vf, self.qf, self.wf])
+
+    def Hf(self, x, p):
+        return np.eye(13)
+
+    Kf = None
+
+    def emit_X(self, prg, t, k, x, p):
+        r, v, w = x[0:3], x[3:6], x[10:13]
+        prg.soc([self.v_max + 0.0 * v[0], v[0], v[1], v[2]], "max_lin_vel")
+        prg.soc([self.omega_max + 0.0 * w[0], w[0], w[1], w[2]], "max_ang_vel")
+        prg.nonpos([p[0] - self.tf_max], "max_duration")
+        prg.nonpos([self.tf_min - p[0]], "min_duration")
+        for i in range(self.n_iss):
+            c, s_ = self.rooms[i]
+            d = p[self.idd(i, k - 1)]
+            prg.linf([1.0 - d] + [(r[j] - c[j]) * (1.0 / s_[j]) for j in range(3)], f"room_sdf_{i + 1}")
+
+    def emit_U(self, prg, t, k, u, p):
+        prg.soc([self.T_max + 0.0 * u[0], u[0], u[1], u[2]], "max_thrust")
+        prg.soc([self.M_max + 0.0 * u[3], u[3], u[4], u[5]], "max_torque")
 
 
 def test_trajectory(pb, nb: int, N: int, seed: int = 0):

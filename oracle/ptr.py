@@ -37,9 +37,57 @@ class Parameters:           # ptr.jl:57-71
     solver_tol: float = 1e-9
 
 
+def compute_bbox(pb, N):
+    """compute_scaling's bounding boxes (scp.jl:376-481): advised ranges where given (entries of pb.ranges() that are
+    not None), otherwise min / max of the variable over the convex set X (states, parameters) or U (inputs, parameters)
+    imposed at every node on ONE (x, u, p); unbounded (DUAL_INFEASIBLE) or failed (NUMERICAL_ERROR) programs keep the
+    default box [0, 1].  HiGHS for polyhedral sets, the oracle IPM for sets with second-order cones."""
+    from . import orc
+    xrg, urg, prg_ = pb.ranges()
+    t = orc.t_grid(N)
+    box = {"x": [list(r) if r is not None else [0.0, 1.0] for r in xrg],
+           "u": [list(r) if r is not None else [0.0, 1.0] for r in urg],
+           "p": [list(r) if r is not None else [0.0, 1.0] for r in prg_]}
+    adv = {"x": xrg, "u": urg, "p": prg_}
+    passes = [("x", "emit_X"), ("u", "emit_U"), ("p", "emit_X"), ("p", "emit_U")]
+    for blk, emit in passes:
+        miss = [i for i, r in enumerate(adv[blk]) if r is None]
+        if not miss or not hasattr(pb, emit):
+            continue
+        for i in miss:
+            for j in (0, 1):
+                prg = conic.ConeProgram()
+                x = prg.new_variable(pb.nx, "x"); u = prg.new_variable(pb.nu, "u"); p = prg.new_variable(pb.np, "p")
+                for k in range(N):
+                    if emit == "emit_X":
+                        pb.emit_X(prg, t[k], k + 1, x, p)
+                    else:
+                        pb.emit_U(prg, t[k], k + 1, u, p)
+                z = {"x": x, "u": u, "p": p}[blk][i]
+                sgn = 1.0 if j == 0 else -1.0
+                prg.add_cost(z * sgn)
+                cp = prg.compile()
+                if cp["G"].shape[0] == 0 and cp["A"].shape[0] == 0:
+                    continue
+                if cp["q"]:
+                    with np.errstate(all="ignore"):
+                        res = conic.solve_ipm(cp, tol=1e-9, maxit=60)
+                    if res["status"] in ("OPTIMAL", "ALMOST_OPTIMAL") and np.isfinite(res["obj"]) and abs(res["obj"]) < 1e7:
+                        box[blk][i][j] = sgn * res["obj"]
+                else:
+                    res = conic.solve_highs(cp)
+                    if res["status"] == "OPTIMAL":
+                        box[blk][i][j] = sgn * res["obj"]
+                    elif res["status"] not in ("DUAL_INFEASIBLE", "NUMERICAL_ERROR", "INFEASIBLE"):
+                        raise RuntimeError(f"Solver failed during variable scaling ({res['status']})")
+    return box["x"], box["u"], box["p"]
+
+
 class Scaling:              # scp.jl:483-516
-    def __init__(self, pb):
+    def __init__(self, pb, N=None):
         xrg, urg, prg = pb.ranges()
+        if any(r is None for r in list(xrg) + list(urg) + list(prg)):
+            xrg, urg, prg = compute_bbox(pb, N if N is not None else pb.N)
         zero_tol = np.sqrt(np.finfo(float).eps)
 
         def mk(rg):
@@ -91,7 +139,7 @@ def trapz(f, grid):         # helper.jl:560-568
 class PTR:
     def __init__(self, pb, pars: Parameters):
         self.pb, self.pars = pb, pars
-        self.scale = Scaling(pb)
+        self.scale = Scaling(pb, pars.N)
         self.t = orc.t_grid(pars.N)
         self.model = pb.orc_model()
 
@@ -179,7 +227,10 @@ class PTR:
             cone([du_lq[k]] + [(u[i, k] - sc.cu[i]) * sc.iSu[i] - uh_ref[k, i] for i in range(nu)], "input_trust_region")
             prg.nonpos([du_lq[k] - eta_u[k]])
         # cost
-        J = pb.cost_aff(x, u, p, t) if hasattr(pb, "cost_aff") else conic.Aff()
+        if hasattr(pb, "cost_emit"):        # convex non-affine cost: the problem adds its epigraph cones to the program
+            J = pb.cost_emit(prg, x, u, p, t)
+        else:
+            J = pb.cost_aff(x, u, p, t) if hasattr(pb, "cost_aff") else conic.Aff()
         prg.add_cost(J)
         J_tr = (trapz(eta_x, t) + trapz(eta_u, t) + eta_p[0]) * pars.wtr
         prg.add_cost(J_tr)

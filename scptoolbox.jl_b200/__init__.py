@@ -8,4 +8,5 @@ from . import examples  # noqa: F401
 from .examples import starship as _starship  # noqa: F401
 from .examples import rocket_landing as _rocket_landing  # noqa: F401
 from .examples import double_integrator as _double_integrator  # noqa: F401
+from .examples import freeflyer as _freeflyer  # noqa: F401
 from .lib import Handle, ScpbError  # noqa: F401

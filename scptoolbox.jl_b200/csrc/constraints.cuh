@@ -1,9 +1,13 @@
 // constraints.cuh -- device packs for the nonconvex path constraints s(t,k,x,u,p) <= 0 and their Jacobians
 // C = ds/dx, D = ds/du, G = ds/dp  (the device twins of traj.s/C/D/G, src/parser/problem.jl:560-587,
 // consumed by add_nonconvex_constraints!, src/solvers/scp.jl:744-794).
-// Outputs are dense, row-major: s[NS], C[NS][NX], D[NS][NU], G[NS][NP]; entries that are structurally zero
-// for a pack are simply never referenced by the host template.
+// Outputs are dense, row-major: s[NS], C[NS][NX], D[NS][NU], G[NS][NG]; entries that are structurally zero
+// for a pack are simply never referenced by the host template.  G is PACKED: it holds NG columns and gcol(k, j) names
+// the parameter each one belongs to at node k (0-based).  For most packs NG = np and gcol(k, j) = j; the free-flyer
+// has np = 1 + 6N parameters of which only the six room-SDF slacks of node k enter s at that node
+// (freeflyer/definition.jl:398-424), so its G has six columns instead of 481.
 #pragma once
+#include <math_constants.h>
 #include "models.cuh"
 
 template <int ID>
@@ -15,8 +19,9 @@ struct Constr {
 // [8] tau_s (shared with the dynamics pack).
 template <>
 struct Constr<SCPB_MODEL_STARSHIP> {
-    static constexpr int NS = 23, NX = 8, NU = 3, NP = 10;
-    __device__ static void eval(const ModelPar &P, double t, int N, const double *x, const double *u, const double *p,
+    static constexpr int NS = 23, NX = 8, NU = 3, NP = 10, NG = 10;
+    __device__ static constexpr int gcol(int, int j) { return j; }
+    __device__ static void eval(const ModelPar &P, double t, int N, int, const double *x, const double *u, const double *p,
                                 double *s, double *C, double *D, double *G)
     {
         const double taus = P.v[8], rd = P.v[9], ddmax = P.v[10], cgs = cos(P.v[11]), thmax = P.v[12];
@@ -60,5 +65,63 @@ struct Constr<SCPB_MODEL_STARSHIP> {
             C[21 * NX + 4] = 1.0;
             C[22 * NX + 4] = -1.0;
         }
+    }
+};
+
+// shared helper: ellipsoidal keep-out zones  s_i = 1 - |H_i (r - c_i)|,  ds_i/dr = -(H_i' H_i)(r - c_i) / |H_i (r - c_i)|
+// (src/utils/ellipsoid.jl:99-118; quadrotor/definition.jl:237-262, freeflyer/definition.jl:380-404).
+// par block per obstacle: H (3x3 column-major), c (3).
+__device__ __forceinline__ void ellipsoid_rows(const double *ob, int nobs, const double *r, double *s, double *C, int NX)
+{
+    for (int i = 0; i < nobs; i++) {
+        const double *H = ob + 12 * i, *c = H + 9;
+        const double d0 = r[0] - c[0], d1 = r[1] - c[1], d2 = r[2] - c[2];
+        double y[3];
+        for (int a = 0; a < 3; a++) y[a] = H[a + 3 * 0] * d0 + H[a + 3 * 1] * d1 + H[a + 3 * 2] * d2;
+        const double E = sqrt(y[0] * y[0] + y[1] * y[1] + y[2] * y[2]);
+        s[i] = 1.0 - E;
+        for (int b = 0; b < 3; b++) {          // (H'H d)_b = sum_a H[a,b] y_a
+            const double g = H[0 + 3 * b] * y[0] + H[1 + 3 * b] * y[1] + H[2 + 3 * b] * y[2];
+            C[i * NX + b] = -g / E;
+        }
+    }
+}
+
+// quadrotor/definition.jl:237-262: two ellipsoidal obstacles.  par: g(3), then 2 x {H(9), c(3)} from [3].
+template <>
+struct Constr<SCPB_MODEL_QUADROTOR> {
+    static constexpr int NS = 2, NX = 6, NU = 4, NP = 1, NG = 1;
+    __device__ static constexpr int gcol(int, int j) { return j; }
+    __device__ static void eval(const ModelPar &P, double, int, int, const double *x, const double *, const double *,
+                                double *s, double *C, double *D, double *G)
+    {
+        for (int i = 0; i < NS * NX; i++) C[i] = 0.0;
+        for (int i = 0; i < NS * NU; i++) D[i] = 0.0;
+        for (int i = 0; i < NS * NG; i++) G[i] = 0.0;
+        ellipsoid_rows(&P.v[3], NS, x, s, C, NX);
+    }
+};
+
+// freeflyer/definition.jl:376-442: three ellipsoidal obstacles and the space-station flight-space SDF
+//   s_4 = -logsumexp(delta[:, k]; t = hom)  (src/utils/helper.jl:623-662), dG = -softmax weights on the six slacks of node k.
+// par: mass [0], J [1..9], Jinv [10..18] (dynamics pack), hom [19], then 3 x {H(9), c(3)} from [20].
+template <>
+struct Constr<SCPB_MODEL_FREEFLYER> {
+    static constexpr int NS = 4, NX = 13, NU = 6, NG = 6, NISS = 6, NOBS = 3;
+    __device__ static constexpr int gcol(int k, int j) { return 1 + NISS * k + j; }
+    __device__ static void eval(const ModelPar &P, double, int, int k, const double *x, const double *, const double *p,
+                                double *s, double *C, double *D, double *G)
+    {
+        for (int i = 0; i < NS * NX; i++) C[i] = 0.0;
+        for (int i = 0; i < NS * NU; i++) D[i] = 0.0;
+        for (int i = 0; i < NS * NG; i++) G[i] = 0.0;
+        ellipsoid_rows(&P.v[20], NOBS, x, s, C, NX);
+        const double hom = P.v[19];
+        double dl[NISS], a = -CUDART_INF;
+        for (int j = 0; j < NISS; j++) { dl[j] = p[gcol(k, j)]; a = fmax(a, hom * dl[j]); }
+        double E = 0.0;
+        for (int j = 0; j < NISS; j++) E += exp(hom * dl[j] - a);
+        s[3] = -((a + log(E)) / hom);
+        for (int j = 0; j < NISS; j++) G[3 * NG + j] = -(exp(hom * dl[j] - a) / E);
     }
 };

@@ -51,14 +51,14 @@ __global__ void k_linearize(const PtrDev d, const double *xd, const double *ud, 
     const int G = d.G;
     const long long E = d.nsrc;
     if constexpr (CP::NS > 0) {
-        constexpr int NS = CP::NS, NX = CP::NX, NU = CP::NU, NP = CP::NP;
-        double s[NS], C[NS * NX], D[NS * NU], Gm[NS * NP];
-        CP::eval(d.par, d.t_grid[k], d.N, x, u, pp, s, C, D, Gm);
+        constexpr int NS = CP::NS, NX = CP::NX, NU = CP::NU, NG = CP::NG;
+        double s[NS], C[NS * NX], D[NS * NU], Gm[NS * NG];
+        CP::eval(d.par, d.t_grid[k], d.N, k, x, u, pp, s, C, D, Gm);
         for (int r = 0; r < NS; r++) {
             double rs = s[r];
             for (int j = 0; j < NX; j++) { rs -= C[r * NX + j] * x[j]; d.src[gaddr(b, G, E, d.oC + ((long long)k * NS + r) * NX + j)] = C[r * NX + j]; }
             for (int j = 0; j < NU; j++) { rs -= D[r * NU + j] * u[j]; d.src[gaddr(b, G, E, d.oD + ((long long)k * NS + r) * NU + j)] = D[r * NU + j]; }
-            for (int j = 0; j < NP; j++) { rs -= Gm[r * NP + j] * pp[j]; d.src[gaddr(b, G, E, d.oG + ((long long)k * NS + r) * NP + j)] = Gm[r * NP + j]; }
+            for (int j = 0; j < NG; j++) { rs -= Gm[r * NG + j] * pp[CP::gcol(k, j)]; d.src[gaddr(b, G, E, d.oG + ((long long)k * NS + r) * NG + j)] = Gm[r * NG + j]; }
             d.src[gaddr(b, G, E, d.ors + (long long)k * NS + r)] = rs;
         }
     }
@@ -372,9 +372,9 @@ __global__ void k_scvx_cost(const ScvxDev d, const double *xall, const double *u
         if (k < d.N - 1)
             for (int i = 0; i < d.nx; i++) Pk += fabs(d.defect[((size_t)b * (d.N - 1) + k) * d.nx + i]);
         if constexpr (CP::NS > 0) {
-            constexpr int NS = CP::NS, NX = CP::NX, NU = CP::NU, NP = CP::NP;
-            double s[NS], C[NS * NX], D[NS * NU], Gm[NS * NP];
-            CP::eval(d.par, d.t_grid[k], d.N, x + (size_t)k * d.nx, u + (size_t)k * d.nu, p, s, C, D, Gm);
+            constexpr int NS = CP::NS, NX = CP::NX, NU = CP::NU, NG = CP::NG;
+            double s[NS], C[NS * NX], D[NS * NU], Gm[NS * NG];
+            CP::eval(d.par, d.t_grid[k], d.N, k, x + (size_t)k * d.nx, u + (size_t)k * d.nu, p, s, C, D, Gm);
             for (int r = 0; r < NS; r++) Pk += fmax(s[r], 0.0);
         }
         Pk *= d.lam;
@@ -478,8 +478,20 @@ int32_t scpb_ptr_setup(scpb_handle h, scpb_cone cone, const scpb_ptr_desc *desc,
     const ConeSymbolic *S = scpb_internal_cone_sym(cone);
     if (desc->nval != (int)(S->A_ci.size() + S->G_ci.size()) + S->n + S->p + S->m + 1)
         return set_err(h, SCPB_ERR_ARG, "ptr_setup: nval does not match the cone program (%d)", desc->nval);
-    if (desc->ns > 0 && !(h->model_id == SCPB_MODEL_STARSHIP && desc->ns == Constr<SCPB_MODEL_STARSHIP>::NS))
-        return set_err(h, SCPB_ERR_UNSUPPORTED, "ptr_setup: no constraint pack for model %d with ns=%d", h->model_id, desc->ns);
+    if (desc->ns > 0) {
+        int pns = 0, png = 0;
+        switch (h->model_id) {
+        case SCPB_MODEL_STARSHIP: pns = Constr<SCPB_MODEL_STARSHIP>::NS; png = Constr<SCPB_MODEL_STARSHIP>::NG; break;
+        case SCPB_MODEL_QUADROTOR: pns = Constr<SCPB_MODEL_QUADROTOR>::NS; png = Constr<SCPB_MODEL_QUADROTOR>::NG; break;
+        case SCPB_MODEL_FREEFLYER: pns = Constr<SCPB_MODEL_FREEFLYER>::NS; png = Constr<SCPB_MODEL_FREEFLYER>::NG; break;
+        default: break;
+        }
+        if (pns != desc->ns || png != desc->ng)
+            return set_err(h, SCPB_ERR_UNSUPPORTED, "ptr_setup: no constraint pack for model %d with ns=%d, ng=%d", h->model_id,
+                           desc->ns, desc->ng);
+        if (h->model_id == SCPB_MODEL_FREEFLYER && desc->np != 1 + Constr<SCPB_MODEL_FREEFLYER>::NISS * desc->N)
+            return set_err(h, SCPB_ERR_ARG, "ptr_setup: the free-flyer pack expects np = 1 + 6 N");
+    }
     SCPB_CUDA(h, cudaSetDevice(h->device));
     scpb_ptr_s *s = new (std::nothrow) scpb_ptr_s();
     if (!s) return SCPB_ERR_CUDA;
@@ -575,8 +587,12 @@ int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *u
     long long ipm_iters = 0;
     std::vector<int> hit(B);
     for (; it <= d.iter_max; it++) {
-        if (s->model_id == SCPB_MODEL_STARSHIP && d.ns > 0)
+        if (d.ns > 0 && s->model_id == SCPB_MODEL_STARSHIP)
             k_linearize<Constr<SCPB_MODEL_STARSHIP>><<<nbn, 128, 0, st>>>(pd, s->xd, s->ud, s->p);
+        else if (d.ns > 0 && s->model_id == SCPB_MODEL_FREEFLYER)
+            k_linearize<Constr<SCPB_MODEL_FREEFLYER>><<<nbn, 128, 0, st>>>(pd, s->xd, s->ud, s->p);
+        else if (d.ns > 0 && s->model_id == SCPB_MODEL_QUADROTOR)
+            k_linearize<Constr<SCPB_MODEL_QUADROTOR>><<<nbn, 128, 0, st>>>(pd, s->xd, s->ud, s->p);
         else
             k_linearize<Constr<0>><<<nbn, 128, 0, st>>>(pd, s->xd, s->ud, s->p);
         const long long tot = (long long)d.nval * Bpad;

@@ -77,7 +77,7 @@ class ConeOpts(C.Structure):
 class PtrDesc(C.Structure):
     _fields_ = [(k, C.c_int32) for k in
                 ("N", "Nsub", "nx", "nu", "np", "ns", "nf", "nsrc", "oA", "oBm", "oBp", "oF", "or_", "oE", "oC", "oD",
-                 "oG", "ors", "oxh", "ouh", "oph", "nval", "vx", "vu", "vp", "q_exit", "iter_max")] + \
+                 "oG", "ors", "oxh", "ouh", "oph", "nval", "vx", "vu", "vp", "q_exit", "iter_max", "ng")] + \
                [(k, C.c_double) for k in ("eps_abs", "eps_rel", "feas_tol")]
 
 

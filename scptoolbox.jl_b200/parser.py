@@ -228,6 +228,15 @@ class ConicTemplate:
     def soc(self, exprs, name=""):
         self.socs.append([Expr.lift(e) for e in exprs])
 
+    def sumsq(self, exprs, name="", stage=-2):
+        """epigraph of a sum of squares: returns q (a new variable, as Expr) with  sum_i e_i^2 <= q  imposed as the
+        rotated second-order cone |(2 e_1, ..., 2 e_n, q - 1)|_2 <= q + 1.  This is how a convex quadratic running cost
+        reaches a linear-objective cone solver (JuMP lowers quadratic objectives for ECOS the same way, through its
+        quadratic-to-SOC bridge; the minimiser is identical)."""
+        q = self._aux(1, stage)[0]
+        self.socs.append([q + 1.0] + [Expr.lift(e) * 2.0 for e in exprs] + [q - 1.0])
+        return q
+
     def add_cost(self, e):
         self.cost = self.cost + Expr.lift(e)
 

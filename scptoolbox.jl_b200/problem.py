@@ -30,6 +30,8 @@ class TrajectoryProblem:
         self.U = None            # U(t,k,u,p,pbm,ocp)                                  (problem.jl:534-543)
         self.ns = 0
         self.s_struct = None     # (Cmask, Dmask, Gmask) structural non-zeros of the constraint pack
+        self.gcols = None        # gcols(k) -> parameter indices of the pack's packed ds/dp columns at node k (None: all)
+        self.ocp = None          # the program under construction while the cost closures run (see ptr.SCPProblem._build)
         self.gic = None          # affine boundary conditions g(x_expr, p_expr, pbm) -> list[Expr]
         self.gtc = None
         self.scp = None
@@ -98,13 +100,14 @@ def problem_set_U(pbm, U):
     pbm.U = lambda ocp, t, k, u, p: U(t, k, u, p, pbm, ocp)
 
 
-def problem_set_s(pbm, ns, struct):
+def problem_set_s(pbm, ns, struct, gcols=None):
     """problem_set_s! (problem.jl:560-587): the constraint pack of the selected model evaluates s, C, D, G on the
     device; struct(t, k, pbm) -> (Cmask, Dmask, Gmask) gives their structural non-zeros at node k
     (row-major ns x nx / nu / np).  Node-dependent structure keeps e.g. phase-switch rows from coupling a
     parameter to every stage."""
     pbm.ns = int(ns)
     pbm.s_struct = lambda t, k: struct(t, k, pbm)
+    pbm.gcols = gcols        # packed ds/dp: gcols(k) lists the parameters the pack's NG columns refer to at node k
 
 
 def problem_advise_parameter_stage(pbm, stage_of):

@@ -40,22 +40,88 @@ class Parameters:            # ptr.jl:57-71
     solver_opts: dict = None         # {"verbose":.., "maxit":..} as in the reference tests
 
 
-class SCPScaling:            # scp.jl:39-49, 483-516 (user-advised ranges)
-    def __init__(self, traj):
+class SCPScaling:
+    """SCPScaling + compute_scaling (scp.jl:39-49, 376-517): x = S*xh + c maps the bounding box of every variable onto
+    [0, 1].  A variable with an advised range (problem_advise_scale!) uses it; for the others the reference solves
+    2*(nx + nu + 2*np) tiny cone programs  min / max z_i  over the convex sets X (states, parameters) and U (inputs,
+    parameters) imposed at every time node (scp.jl:439-481).  Here those programs share one sparsity pattern per set,
+    so they are ONE batched call of the GPU cone solver each (only the cost vector differs per seed); a program that
+    comes back DUAL_INFEASIBLE (unbounded variable) or NUMERICAL_ERROR keeps the default box [0, 1] (scp.jl:470-473)."""
+
+    def __init__(self, traj, handle=None, t=None):
         zero_tol = np.sqrt(np.finfo(float).eps)
+        nx, nu, np_ = traj.nx, traj.nu, traj.np
+        box = {"x": np.tile([0.0, 1.0], (nx, 1)), "u": np.tile([0.0, 1.0], (nu, 1)), "p": np.tile([0.0, 1.0], (np_, 1))}
+        adv = {"x": traj.xrg, "u": traj.urg, "p": traj.prg}
+        for k_ in box:
+            for i, r in enumerate(adv[k_]):
+                if r is not None:
+                    box[k_][i] = r
+        self.computed = {}        # (block, index, 0 = min / 1 = max) -> cone status name, for the boxes that were solved
+        missing = {k_: [i for i, r in enumerate(adv[k_]) if r is None] for k_ in box}
+        # the reference's four passes, in its order: x over X, u over U, p over X, p over U (a later pass overwrites)
+        passes = [("x", traj.X, "X"), ("u", traj.U, "U"), ("p", traj.X, "X"), ("p", traj.U, "U")]
+        cache = {}
+        for blk, cset, tag in passes:
+            if not missing[blk] or cset is None:
+                continue              # no set: every program is unbounded -> default box (what ECOS reports, :470)
+            if handle is None or t is None:
+                raise lib.ScpbError(f"no scaling advice for {blk}{missing[blk]}: the bounding-box solves need a device handle")
+            if tag not in cache:
+                cache[tag] = self._set_program(traj, cset, tag, t)
+            self._bbox_pass(handle, cache[tag], blk, missing[blk], box[blk])
 
-        def mk(rg, what):
-            if any(r is None for r in rg):
-                raise lib.ScpbError(f"advise a range for every {what} (automatic bounding-box solves are not implemented)")
-            lo = np.array([r[0] for r in rg], dtype=float)
-            hi = np.array([r[1] for r in rg], dtype=float)
-            S = hi - lo
-            S[S < zero_tol] = 1.0
-            return S, lo.copy()
+        def mk(b):
+            S = b[:, 1] - b[:, 0]
+            S = np.where(S < zero_tol, 1.0, S)
+            return S, b[:, 0].copy()
 
-        self.Sx, self.cx = mk(traj.xrg, "state")
-        self.Su, self.cu = mk(traj.urg, "input")
-        self.Sp, self.cp = mk(traj.prg, "parameter")
+        self.Sx, self.cx = mk(box["x"])
+        self.Su, self.cu = mk(box["u"])
+        self.Sp, self.cp = mk(box["p"])
+
+    @staticmethod
+    def _set_program(traj, cset, tag, t):
+        """plain (unscaled) variables x, u, p; the set imposed at every node k on the SAME variables (scp.jl:446-455)"""
+        prg = ConicTemplate(1)
+        x = prg.new_variable(traj.nx, "x")
+        u = prg.new_variable(traj.nu, "u")
+        p = prg.new_variable(traj.np, "p")
+        for k in range(len(t)):
+            if tag == "X":
+                cset(prg, t[k], k + 1, x, p)
+            else:
+                cset(prg, t[k], k + 1, u, p)
+        cp = prg.compile()
+        vals = np.asarray(cp["W"] @ np.ones(1)).ravel()
+        return dict(prg=prg, cp=cp, vals=vals)
+
+    def _bbox_pass(self, handle, prog, blk, idx, box):
+        cp, vals, prg = prog["cp"], prog["vals"], prog["prg"]
+        n, p_, m = cp["n"], cp["p"], cp["m"]
+        if m == 0 and p_ == 0:
+            return
+        off = prg.blocks[blk][0]
+        nb = 2 * len(idx)
+        Av = np.tile(vals[:cp["nnzA"]], (nb, 1)); Gv = np.tile(vals[cp["nnzA"]:cp["nnzA"] + cp["nnzG"]], (nb, 1))
+        b = np.tile(vals[cp["off_b"]:cp["off_b"] + p_], (nb, 1)); h = np.tile(vals[cp["off_h"]:cp["off_h"] + m], (nb, 1))
+        c = np.zeros((nb, n))
+        for q, i in enumerate(idx):
+            c[2 * q, off + i] = 1.0         # min z_i
+            c[2 * q + 1, off + i] = -1.0    # max z_i
+        cone = lib.ConeProblem(handle, cp["A"], cp["G"], cp["l"], cp["soc_dims"], perm=ordering.rcm_order(cp["A"], cp["G"]))
+        try:
+            out = cone.solve(Av, Gv, c, b, h)
+        finally:
+            cone.close()
+        for q, i in enumerate(idx):
+            for j in range(2):
+                st = int(out["status"][2 * q + j])
+                self.computed[(blk, i, j)] = lib.CONE_STATUS.get(st, "?")
+                if st in (0, 3):                                   # OPTIMAL / ALMOST_OPTIMAL
+                    box[i, j] = (1.0 if j == 0 else -1.0) * out["pobj"][2 * q + j]
+                elif st not in (5, 2):                             # DUAL_INFEASIBLE / NUMERICAL_ERROR keep the default
+                    raise lib.ScpbError(f"Solver failed during variable scaling ({lib.CONE_STATUS.get(st, st)})")
 
 
 def t_grid(N):
@@ -75,8 +141,9 @@ def trapz(f, grid):          # helper.jl:560-568
 class SourceMap:
     """Layout of the per-seed source vector (see include/scpb.h, scpb_ptr_desc)."""
 
-    def __init__(self, N, nx, nu, np_, ns, nf):
+    def __init__(self, N, nx, nu, np_, ns, nf, ng=None):
         M = N - 1
+        ng = np_ if ng is None else ng       # packed columns of ds/dp per node (csrc/constraints.cuh)
         o = 1
         self.oA = o; o += M * nx * nx
         self.oBm = o; o += M * nx * nu
@@ -86,14 +153,14 @@ class SourceMap:
         self.oE = o; o += M * nx * nx
         self.oC = o; o += N * ns * nx
         self.oD = o; o += N * ns * nu
-        self.oG = o; o += N * ns * np_
+        self.oG = o; o += N * ns * ng
         self.ors = o; o += N * ns
         self.oxh = o; o += N * nx
         self.ouh = o; o += N * nu
         self.oph = o; o += np_
         self.oeta = o; o += 1          # SCvx trust-region radius (scvx.jl:245); unused by PTR
         self.nsrc = o
-        self.N, self.nx, self.nu, self.np, self.ns, self.nf = N, nx, nu, np_, ns, nf
+        self.N, self.nx, self.nu, self.np, self.ns, self.nf, self.ng = N, nx, nu, np_, ns, nf, ng
 
     def mat(self, off, k, rows, cols, colmajor=True, mask=None):
         blk = rows * cols
@@ -117,9 +184,9 @@ class SCPProblem:
         self.pars, self.traj, self.handle = pars, traj, handle
         self.l1_block = l1_block
         self.algo = algo
-        self.scale = SCPScaling(traj)
         self.t = t_grid(pars.N)
         traj.scp = pars
+        self.scale = SCPScaling(traj, handle, self.t)
         if pars.disc_method != FOH:
             raise lib.ScpbError("only FOH discretization is implemented on the device")
         self._build()
@@ -129,7 +196,10 @@ class SCPProblem:
         pars, traj, sc, t = self.pars, self.traj, self.scale, self.t
         N, nx, nu, np_ = pars.N, traj.nx, traj.nu, traj.np
         ns, nf = traj.ns, len(traj.fcols)
-        sm = SourceMap(N, nx, nu, np_, ns, nf)
+        gcols = traj.gcols if getattr(traj, "gcols", None) else (lambda k: list(range(np_)))
+        ng = len(gcols(0)) if ns else np_
+        sm = SourceMap(N, nx, nu, np_, ns, nf, ng)
+        traj.ocp = None
         self.sm = sm
         prg = ConicTemplate(sm.nsrc, l1_block=self.l1_block)
         x = prg.new_variable((nx, N), "x", sc.Sx, sc.cx, stage="col")
@@ -173,9 +243,10 @@ class SCPProblem:
                 Cm, Dm, Gm = traj.s_struct(t[k], k + 1)
                 Cs = sm.mat(sm.oC, k, ns, nx, colmajor=False, mask=Cm)
                 Ds = sm.mat(sm.oD, k, ns, nu, colmajor=False, mask=Dm)
-                Gs = sm.mat(sm.oG, k, ns, np_, colmajor=False, mask=Gm)
+                Gs = sm.mat(sm.oG, k, ns, ng, colmajor=False, mask=Gm)
                 rs = sm.vec(sm.ors, k, ns)
-                lhs = [a + b + c for a, b, c in zip(matvec(Cs, x[:, k]), matvec(Ds, u[:, k]), matvec(Gs, p))]
+                lhs = [a + b + c for a, b, c in zip(matvec(Cs, x[:, k]), matvec(Ds, u[:, k]),
+                                                    matvec(Gs, [p[j] for j in gcols(k)]))]
                 prg.nonpos([lhs[i] + Expr(None, rs[i]) - vs[i, k] for i in range(ns)], "path_ncvx")
         # boundary conditions, relaxed (scp.jl:808-895); affine g => exact linearisation
         vic = vtc = None
@@ -217,10 +288,12 @@ class SCPProblem:
                 prg.nonpos([dx_lq[k] + du_lq[k] + dp_lq[0] - eta_src], "trust_region_bound")
         # cost (ptr.jl:753-895, scp.jl:552-601)
         J = Expr()
+        traj.ocp = prg          # a convex (non-affine) running cost adds its epigraph to the program (parser.sumsq)
         if traj.phi is not None:
             J = J + traj.phi(x[:, N - 1], p)
         if traj.Gamma is not None:
             J = J + trapz([traj.Gamma(t[k], k + 1, x[:, k], u[:, k], p) for k in range(N)], t)
+        traj.ocp = None
         prg.add_cost(J)
         self.J_orig, self.g_ic, self.g_tc = J, list(g_ic), list(g_tc)     # rows re-evaluated by SCvx (nonlinear cost)
         if not scvx:
@@ -265,6 +338,7 @@ class SCPProblem:
         for k_ in ("nsrc", "oA", "oBm", "oBp", "oF", "or_", "oE", "oC", "oD", "oG", "ors", "oxh", "ouh", "oph"):
             setattr(d, k_, getattr(sm, k_))
         d.nval = self.nval
+        d.ng = ng
         d.vx, d.vu, d.vp = prg.blocks["x"][0], prg.blocks["u"][0], prg.blocks["p"][0]
         d.q_exit = {np.inf: 0, 1: 1, 2: 2}[pars.q_exit]
         d.iter_max = pars.iter_max

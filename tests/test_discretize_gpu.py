@@ -158,7 +158,7 @@ def test_impulse_propagate_matches_oracle(pkg, handle):
 
 
 def test_impulse_needs_an_impulse_pack(pkg, handle):
-    pb = problems.QuadrotorProblem()
+    pb = problems.QuadrotorProblem(5)
     handle.model_set(pb.model_id, pb.par(), pb.nx, pb.nu, pb.np)
     xd, ud, p = problems.test_trajectory(pb, 1, 5, seed=1)
     with pytest.raises(pkg.ScpbError):

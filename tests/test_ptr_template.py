@@ -11,6 +11,8 @@ from oracle import orc, problems, ptr as optr
 def _sources(sm, pbo, P, ref):
     """Fill the source vector on the host from oracle quantities (what the device kernels compute)."""
     N, nx, nu, np_, ns, nf = sm.N, sm.nx, sm.nu, sm.np, sm.ns, sm.nf
+    ng = getattr(sm, "ng", np_)
+    gcols = getattr(pbo, "gcols", None) or (lambda k: list(range(np_)))
     src = np.zeros(sm.nsrc); src[0] = 1.0
     d = ref.dyn
     for k in range(N - 1):
@@ -27,7 +29,7 @@ def _sources(sm, pbo, P, ref):
             Cm, Dm, Gm, s = pbo.C(*a), pbo.D(*a), pbo.G(*a), pbo.s(*a)
             src[sm.oC + k * ns * nx: sm.oC + (k + 1) * ns * nx] = Cm.flatten()
             src[sm.oD + k * ns * nu: sm.oD + (k + 1) * ns * nu] = Dm.flatten()
-            src[sm.oG + k * ns * np_: sm.oG + (k + 1) * ns * np_] = Gm.flatten()
+            src[sm.oG + k * ns * ng: sm.oG + (k + 1) * ns * ng] = Gm[:, gcols(k)].flatten()
             src[sm.ors + k * ns: sm.ors + (k + 1) * ns] = s - Cm @ ref.xd[k] - Dm @ ref.ud[k] - Gm @ ref.p
         src[sm.oxh + k * nx: sm.oxh + (k + 1) * nx] = (ref.xd[k] - P.scale.cx) * P.scale.iSx
         src[sm.ouh + k * nu: sm.ouh + (k + 1) * nu] = (ref.ud[k] - P.scale.cu) * P.scale.iSu
@@ -267,3 +269,63 @@ def test_l1_block_lowering_is_an_equivalent_program(pkg, monkeypatch):
     assert abs(res[0][0] - res[4][0]) <= 1e-8 * max(1.0, abs(res[0][0]))          # ... and changes nothing else
     d = np.abs(res[0][1] - res[4][1])
     assert np.median(d) <= 1e-7                     # (flat directions may differ between two LP vertices)
+
+
+def test_freeflyer_template_matches_oracle_subproblem(pkg, monkeypatch):
+    """BASELINE config C5 (free-flyer PTR): SOC(4) velocity / rate / thrust / torque cones, LINF room SDF cones, the
+    log-sum-exp SDF row with its packed ds/dp columns (np = 1 + 6N), the quadratic running cost lowered to one rotated
+    cone per node.  The bounding boxes come from the oracle's compute_bbox (the product computes its own on the GPU,
+    tests/test_ptr_gpu.py compares the two)."""
+    N = 6
+    pbo = problems.FreeFlyerProblem(N)
+    pbo.gcols = lambda k: [pbo.idd(i, k) for i in range(pbo.n_iss)]
+    xd, ud, p = pbo.guess(N)
+    rng = np.random.default_rng(2)
+    xd = xd + 1e-3 * rng.standard_normal(xd.shape); ud = ud + 1e-4 * rng.standard_normal(ud.shape)
+    opars = optr.Parameters(N=N, Nsub=15, iter_max=5, wvc=1e3, wtr=0.1, eps_abs=1e-5, eps_rel=1e-4, feas_tol=1e-3)
+    P = optr.PTR(pbo, opars)
+    ref = P.make_solution(xd, ud, p)
+    prg, _ = P.build(ref)
+    ocp = prg.compile()
+    ex = pkg.examples.freeflyer
+    mdl = ex.FreeFlyerProblem(N)
+    traj = pkg.problem.TrajectoryProblem(mdl)
+    ex.define_problem(traj, "ptr", handle=None)
+    xb, ub, pb_ = optr.compute_bbox(pbo, N)           # advise every variable: no GPU on this box
+    for i, r in enumerate(xb): pkg.problem.problem_advise_scale(traj, "state", i, r)
+    for i, r in enumerate(ub): pkg.problem.problem_advise_scale(traj, "input", i, r)
+    pars = pkg.ptr.Parameters(N=N, Nsub=15, iter_max=5, disc_method=pkg.ptr.FOH, wvc=1e3, wtr=0.1, eps_abs=1e-5,
+                              eps_rel=1e-4, feas_tol=1e-3, q_tr=np.inf, q_exit=np.inf)
+
+    class FakeHandle:
+        def model_set(self, *a): pass
+    monkeypatch.setattr(pkg.lib, "ConeProblem", lambda *a, **k: type("C", (), {"c": None, "close": lambda s: None})())
+    fake = FakeHandle(); fake.lib = type("L", (), {"scpb_ptr_setup": staticmethod(lambda *a: 0)})(); fake.h = None
+    fake._check = lambda rc, what: None
+    pbm = pkg.ptr.SCPProblem(pars, traj, fake, l1_block=0)
+    cp, sm = pbm.cp, pbm.sm
+    assert sm.ng == 6 and pbm.desc.ng == 6
+    # same guess on both sides
+    xg, ug, pg = traj.guess(N)
+    x0, u0, p0 = pbo.guess(N)
+    assert np.abs(xg - x0).max() < 1e-12 and np.abs(pg - p0).max() < 1e-12
+    assert np.abs(pbm.scale.Sx - P.scale.Sx).max() < 1e-9 and np.abs(pbm.scale.Su - P.scale.Su).max() < 1e-9
+    vals = pbm.W @ _sources(sm, pbo, P, ref)
+    n, p_, m = cp["n"], cp["p"], cp["m"]
+    assert (n, p_, m, cp["l"]) == (ocp["c"].size, ocp["A"].shape[0], ocp["G"].shape[0], ocp["l"])
+    assert sorted(cp["soc_dims"]) == sorted(ocp["q"])
+    # variables and rows are emitted in a different order on the two sides (epigraph variables, cone order): compare
+    # the programs through their optimal values instead of entry by entry
+    from oracle import conic
+    A = sp.csr_matrix((vals[:cp["nnzA"]], cp["A"].indices, cp["A"].indptr), shape=(p_, n))
+    G = sp.csr_matrix((vals[cp["nnzA"]:cp["nnzA"] + cp["nnzG"]], cp["G"].indices, cp["G"].indptr), shape=(m, n))
+    mine = dict(c=vals[cp["off_c"]:cp["off_c"] + n], c0=vals[-1], A=A, b=vals[cp["off_b"]:cp["off_b"] + p_], G=G,
+                h=vals[cp["off_h"]:cp["off_h"] + m], l=cp["l"], q=list(cp["soc_dims"]))
+    r1 = conic.solve_ipm(mine, tol=1e-9)
+    r2 = conic.solve_ipm(ocp, tol=1e-9)
+    assert r1["status"] == r2["status"] == "OPTIMAL"
+    assert abs(r1["obj"] - r2["obj"]) <= 1e-7 * max(1.0, abs(r2["obj"]))
+    bx = pbm.template.blocks
+    ox, (nx_, _) = bx["x"][0], bx["x"][1]
+    oxo = prg.blocks["x"][0]
+    assert np.abs(r1["z"][ox:ox + nx_ * N] - r2["z"][oxo:oxo + nx_ * N]).max() <= 1e-5

@@ -5,10 +5,11 @@ configuration (starship_flip/tests.jl:69-121: N = 31, Nsub = 100, lambda = 5e2, 
 SCvx with the reference's predicted-improvement rule does not stop at a minimiser but when the trust region has
 collapsed (deviation <= eps_abs after ~40 accept / reject steps), and every LP subproblem has flat directions, so the
 end point depends on the whole path: two solvers that agree to 1e-7 per subproblem end 1e-3 apart.  Measured on B200:
-identical accept / reject sequence, identical iteration count and final radius; after 3 iterations the trajectories
-agree to 6e-7 and J_aug to 3e-6, after 40 iterations to 3e-3 and 2e-4.  Stated tolerance (with margin for a ratio test
-that lands next to a threshold): both SCP_SOLVED, iteration counts within +-4, final augmented cost within 2e-3
-relative, physical trajectory within 2e-2 of its ranges; the three-iteration test asserts 1e-5 / 1e-5."""
+identical accept / reject sequence, identical iteration count and final radius (asserted exactly); with both solvers
+at 1e-11 the trajectories agree to 2e-9 after 3 iterations and between 3e-9 and 8e-3 at the end, depending on the seed
+(the end point of a collapsed trust region is not a minimiser).  Stated tolerance: both SCP_SOLVED, iteration counts and
+final radius equal, final augmented cost within 2e-3 relative, physical trajectory within 2e-2 of its ranges; the
+three-iteration test asserts 1e-7 / 1e-7."""
 import numpy as np
 import pytest
 
@@ -57,7 +58,7 @@ def test_batched_scvx_matches_oracle_scvx(pkg, handle, N, Nsub, nb, iter_max):
         print("scvx parity seed", b, "iters", sol.iterations[b], ref["iterations"], "eta", sol.eta[b], ref["eta"],
               "ex(phys)", ex7, "eu", eu2, "ep", ep, "dJ", dJ, sol.status[b], ref["status"])
         assert sol.status[b] == ref["status"] == "SCP_SOLVED", (sol.status, sol.raw_status)
-        assert abs(int(sol.iterations[b]) - ref["iterations"]) <= 4
+        assert int(sol.iterations[b]) == ref["iterations"] and sol.eta[b] == ref["eta"]     # same accept / reject path
         assert dJ <= 2e-3 and max(ex7, eu2, ep) <= 2e-2
         dn = np.abs(rs.defect * sc.iSx).max()             # feasibility flag: compare unless it sits on the tolerance
         if abs(dn - KW["feas_tol"]) > 0.05 * KW["feas_tol"]:
@@ -86,4 +87,4 @@ def test_scvx_first_iterations_are_identical(pkg, handle):
     ex7 = np.abs((sol.xd[0][:, :7] - rs.xd[:, :7]) / sc.Sx[:7]).max()
     dJ = abs(sol.cost[0] - rs.J_aug) / max(1.0, abs(rs.J_aug))
     print("scvx 3 iterations: ex(phys)", ex7, "dJ", dJ, "J", sol.cost[0], rs.J_aug)
-    assert dJ <= 1e-5 and ex7 <= 1e-5
+    assert dJ <= 1e-7 and ex7 <= 1e-7
