@@ -203,6 +203,31 @@ int32_t scpb_scvx_solve(scpb_ptr ptr, int32_t B, const double *xd0, const double
                         const scpb_cone_opts *opts, double *xd, double *ud, double *p, int32_t *status,
                         int32_t *iters, double *J, double *deviation, int32_t *feas, double *eta, double *timing);
 
+/* ---- batched GuSTO loop: replaces the body of GuSTO.solve (src/solvers/gusto.jl:425-502, pen = :quad) for B seeds ----
+ * Same template machinery: scpb_ptr_setup with the GuSTO flavour of the subproblem (scptoolbox.jl_b200/gusto.py, mirror of
+ * gusto.jl:218-287, 534-1190): dynamics and boundary conditions un-relaxed, the nonconvex path constraints and the trust
+ * region enter through quadratic soft penalties lambda max(0, .)^2 lowered to rotated second-order cones, with the
+ * per-seed sources `oeta` (trust-region radius eta) and `osl` (sqrt(lambda)).  scpb_gusto_attach adds the algorithm
+ * constants (gusto.jl:58-85) and the sparse rows Q over the scaled solver variables (constants Q_const):
+ *   row 0            affine part of the original cost J(x,u,p)            (x, u, p blocks only)
+ *   rows 1..nsq      rows r_j whose weighted squares complete it: J = row0 + sum_j Q_weight[j-1] r_j^2   (x, u, p only)
+ *   row nsq+1        L_tr, the soft trust-region cost as the subproblem measures it (any solver variable)
+ * With the dynamics / constraint packs these give, per iteration and seed, J, J_st, J_tr, J_aug of the new iterate
+ * (gusto.jl:399-418), the convexification error rho (update_trust_region!, :1245-1293), the update rule for the
+ * reference, eta and lambda (update_rule!, :1310-1427, incl. the mu-shrink of :268) and the stopping rule (:1203-1231).
+ * scpb_gusto_solve returns what SCPSolution keeps of the LAST subproblem (scp.jl:205-236): trajectory, status
+ * (0/1 solved, 2+16*cone status failed), iterations, cost = J_aug, deviation, feas, and the final eta and lambda. */
+typedef struct {
+    double lam_init, lam_max, rho_0, rho_1, beta_sh, beta_gr, gamma_fail, eta_init, eta_lb, eta_ub, mu;
+    int32_t iter_mu, q_tr /* 0 = Inf, 1, 2 */, oeta, osl, nsq, reserved;
+} scpb_gusto_desc;
+int32_t scpb_gusto_attach(scpb_ptr ptr, const scpb_gusto_desc *desc, const int32_t *Q_rowptr, const int32_t *Q_colind,
+                          const double *Q_vals, const double *Q_const, const double *Q_weight);
+int32_t scpb_gusto_solve(scpb_ptr ptr, int32_t B, const double *xd0, const double *ud0, const double *p0,
+                         const scpb_cone_opts *opts, double *xd, double *ud, double *p, int32_t *status,
+                         int32_t *iters, double *J, double *deviation, int32_t *feas, double *eta, double *lam,
+                         double *timing);
+
 /* Measured fp64 FMA throughput of the handle's device in TFLOP/s (a register-resident FMA microkernel, best of 3
  * timed launches): the denominator of the discretization kernel's roofline in bench.py. */
 int32_t scpb_debug_fp64_peak(scpb_handle h, double *tflops);

@@ -408,19 +408,87 @@ class RocketProblem(_DynOnly):
 
 
 class QuadrotorProblem(_DynOnly):
-    """quadrotor/parameters.jl:96-135."""
+    """quadrotor/parameters.jl:96-135 and definition.jl (scaling advice :48-58, guess :61-91, cost :94-138, input set
+    :188-235, obstacles :237-270, boundary conditions :272-330) in their GuSTO flavour (BASELINE config C4)."""
     name = "quadrotor"
     model_id = orc.MODEL_QUADROTOR
     nx, nu, np = 6, 4, 1
+    ns = 2
 
     def __init__(self, N: int):
         self.N = N
         self.g = np.array([0.0, 0.0, -9.81])   # parameters.jl:83-84: g = -gnrm * e_z
         self.u_max, self.u_min, self.tilt_max = 23.2, 0.6, deg2rad(60)
         self.tf_min, self.tf_max = 0.0, 2.5
+        self.gamma = 0.0
+        self.obs_H = [np.diag([2.0, 2.0, 0.0]), np.diag([1.5, 1.5, 0.0])]
+        self.obs_c = [np.array([1.0, 2.0, 0.0]), np.array([2.0, 5.0, 0.0])]
+        self.r0, self.v0 = np.zeros(3), np.zeros(3)
+        self.rf, self.vf = np.array([2.5, 6.0, 0.0]), np.zeros(3)
 
     def par(self):
-        return self.g.copy()
+        ob = []
+        for H, c in zip(self.obs_H, self.obs_c):
+            ob += list(H.flatten(order="F")) + list(c)
+        return np.concatenate([self.g, ob])
+
+    def ranges(self):
+        return [None] * 6, [None] * 4, [(self.tf_min, self.tf_min + 1.0 * (self.tf_max - self.tf_min))]
+
+    def guess(self, N):
+        x0 = np.concatenate([self.r0, self.v0]); xf = np.concatenate([self.rf, self.vf])
+        x = np.array([(1 - k / (N - 1)) * x0 + (k / (N - 1)) * xf for k in range(N)])
+        hover = np.concatenate([-self.g, [np.linalg.norm(self.g)]])
+        return x, np.tile(hover, (N, 1)), np.array([0.5 * (self.tf_min + self.tf_max)])
+
+    def S(self, t, k, p):                       # definition.jl:122-133
+        S = np.zeros((4, 4))
+        S[3, 3] = (1 - self.gamma) / np.linalg.norm(self.g) ** 2
+        return S
+
+    def phi(self, x, p):                        # definition.jl:96-103
+        return self.gamma * (p[0] / self.tf_max) ** 2
+
+    def s(self, t, k, x, u, p):                 # definition.jl:240-250
+        return np.array([1 - np.linalg.norm(H @ (x[0:3] - c)) for H, c in zip(self.obs_H, self.obs_c)])
+
+    def C(self, t, k, x, u, p):                 # definition.jl:253-262
+        C = np.zeros((2, 6))
+        for i, (H, c) in enumerate(zip(self.obs_H, self.obs_c)):
+            y = H @ (x[0:3] - c)
+            C[i, 0:3] = -(H.T @ y) / np.linalg.norm(y)
+        return C
+
+    def D(self, t, k, x, u, p):
+        return np.zeros((2, 4))
+
+    def G(self, t, k, x, u, p):
+        return np.zeros((2, 1))
+
+    def gic(self, x, p):
+        return x[0:6] - np.concatenate([self.r0, self.v0])
+
+    def H0(self, x, p):
+        return np.eye(6)
+
+    K0 = None
+
+    def gtc(self, x, p):
+        return x[0:6] - np.concatenate([self.rf, self.vf])
+
+    def Hf(self, x, p):
+        return np.eye(6)
+
+    Kf = None
+
+    def emit_U(self, prg, t, k, u, p):          # definition.jl:188-235
+        a, sg = u[0:3], u[3]
+        prg.nonpos([self.u_min - sg], "min_accel")
+        prg.nonpos([sg - self.u_max], "max_accel")
+        prg.soc([sg, a[0], a[1], a[2]], "lcvx_equality")
+        prg.nonpos([sg * math.cos(self.tilt_max) - a[2]], "max_tilt")
+        prg.nonpos([p[0] - self.tf_max], "max_duration")
+        prg.nonpos([self.tf_min - p[0]], "min_duration")
 
 
 class FreeFlyerProblem(_DynOnly):

@@ -83,6 +83,37 @@ def compute_bbox(pb, N):
     return box["x"], box["u"], box["p"]
 
 
+def correct_convex(pb, sc, N, xd, ud, p, tol=1e-9):
+    """correct_convex! (scp.jl:275-361): the closest trajectory, in the scaled L1 sense, that satisfies the convex path
+    constraints X and U at every node.  Returns the projected (xd, ud, p)."""
+    from . import orc
+    t = orc.t_grid(N)
+    prg = conic.ConeProgram()
+    x = prg.new_variable((pb.nx, N), "x", sc.Sx, sc.cx)
+    u = prg.new_variable((pb.nu, N), "u", sc.Su, sc.cu)
+    pp = prg.new_variable(pb.np, "p", sc.Sp, sc.cp)
+    for k in range(N):
+        if hasattr(pb, "emit_X"):
+            pb.emit_X(prg, t[k], k + 1, x[:, k], pp)
+        if hasattr(pb, "emit_U"):
+            pb.emit_U(prg, t[k], k + 1, u[:, k], pp)
+    ex = prg.new_variable(N, "tau_x"); eu = prg.new_variable(N, "tau_u"); ep = prg.new_variable(1, "tau_p")
+    for k in range(N):
+        prg.l1([ex[k]] + [(x[i, k] - xd[k, i]) * sc.iSx[i] for i in range(pb.nx)], "x_variation")
+        prg.l1([eu[k]] + [(u[i, k] - ud[k, i]) * sc.iSu[i] for i in range(pb.nu)], "u_variation")
+    prg.l1([ep[0]] + [(pp[i] - p[i]) * sc.iSp[i] for i in range(pb.np)], "p_variation")
+    J = conic.Aff()
+    for k in range(N):
+        J = J + ex[k] + eu[k]
+    prg.add_cost(J + ep[0])
+    res = conic.solve(prg.compile(), tol=tol, prefer="ipm")
+    if res["status"] not in ("OPTIMAL", "ALMOST_OPTIMAL"):
+        raise RuntimeError(f"Solver failed to find the closest initial guess that satisfies the convex constraints ({res['status']})")
+    z = res["z"]
+    val = np.vectorize(lambda e: e.value(z), otypes=[float])
+    return val(x).T.copy(), val(u).T.copy(), val(pp)
+
+
 class Scaling:              # scp.jl:483-516
     def __init__(self, pb, N=None):
         xrg, urg, prg = pb.ranges()

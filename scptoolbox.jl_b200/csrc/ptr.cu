@@ -31,8 +31,10 @@ struct PtrDev {
     const double *t_grid, *Sx, *cx, *Su, *cu, *Sp, *cp;
     double *src;
     ModelPar par;
-    const double *eta = nullptr;   // SCvx: per-seed trust-region radius written to source oeta (scvx.jl:245)
+    const double *eta = nullptr;   // SCvx / GuSTO: per-seed trust-region radius written to source oeta (scvx.jl:245)
     int oeta = 0;
+    const double *lam = nullptr;   // GuSTO: per-seed soft-penalty weight; sqrt(lambda) is written to source osl (gusto.jl:228)
+    int osl = 0;
 };
 
 __device__ __forceinline__ size_t gaddr(int b, int G, long long E, long long e)
@@ -68,6 +70,7 @@ __global__ void k_linearize(const PtrDev d, const double *xd, const double *ud, 
         for (int j = 0; j < d.np; j++) d.src[gaddr(b, G, E, d.oph + j)] = (pp[j] - d.cp[j]) / d.Sp[j];
         d.src[gaddr(b, G, E, 0)] = 1.0;
         if (d.eta) d.src[gaddr(b, G, E, d.oeta)] = d.eta[b];
+        if (d.lam) d.src[gaddr(b, G, E, d.osl)] = sqrt(d.lam[b]);
     }
 }
 
@@ -212,6 +215,12 @@ struct scpb_ptr_s {
     double *Q_v = nullptr, *Q_c = nullptr;
     double *src2 = nullptr, *eta = nullptr, *L_new = nullptr, *J_out = nullptr;
     int *accept = nullptr;
+    // GuSTO (scpb_gusto_attach)
+    bool gusto = false;
+    scpb_gusto_desc gv{};
+    double *Q_w = nullptr;
+    double *lam = nullptr, *nodeq = nullptr;
+    int *nodef = nullptr;
 };
 
 // the handle may have been pointed at another model pack since scpb_ptr_setup (several problems can share one handle):
@@ -265,6 +274,7 @@ static int ptr_reserve(scpb_ptr_s *s, int B, int G)
         s->defect = s->J_ref = s->J_new = s->devi = s->imp = s->c0 = nullptr;
         s->feas = s->done = s->status = s->iters = s->nactive = nullptr;
         s->src2 = s->eta = s->L_new = s->J_out = nullptr; s->accept = nullptr;
+        s->lam = s->nodeq = nullptr; s->nodef = nullptr;
     };
     drop();
     const scpb_ptr_desc &d = s->d;
@@ -282,10 +292,14 @@ static int ptr_reserve(scpb_ptr_s *s, int B, int G)
     s->feas = (int *)al(sizeof(int) * Bpad); s->done = (int *)al(sizeof(int) * Bpad);
     s->status = (int *)al(sizeof(int) * Bpad); s->iters = (int *)al(sizeof(int) * Bpad);
     s->nactive = (int *)al(sizeof(int));
-    if (s->scvx) {
+    if (s->scvx || s->gusto) {
         s->src2 = (double *)al(sizeof(double) * (size_t)d.nsrc * Bpad);
         s->eta = (double *)al(sizeof(double) * Bpad); s->L_new = (double *)al(sizeof(double) * Bpad);
         s->J_out = (double *)al(sizeof(double) * Bpad); s->accept = (int *)al(sizeof(int) * Bpad);
+    }
+    if (s->gusto) {
+        s->lam = (double *)al(sizeof(double) * Bpad);
+        s->nodeq = (double *)al(sizeof(double) * 4 * NB); s->nodef = (int *)al(sizeof(int) * NB);
     }
     if (!ok) { cudaGetLastError(); drop(); return set_err(h, SCPB_ERR_CUDA, "ptr: device allocation failed (B=%d)", B); }
     s->capB = Bpad; s->capG = G;
@@ -458,10 +472,223 @@ __global__ void k_scvx_take_dltv(const ScvxDev d)
     d.src[a] = d.src2[a];
 }
 
+// ----------------------------------------------------------------------------------------------
+// GuSTO (src/solvers/gusto.jl, pen = :quad): nonconvex costs of the candidate, convexification error, update rule
+struct GustoDev {
+    int B, G, N, nx, nu, np, n, vx, vu, vp, q_exit, q_tr, iter, iter_max, iter_mu, nsq;
+    double lam_init, lam_max, rho_0, rho_1, beta_sh, beta_gr, gamma_fail, eta_lb, eta_ub, mu, eps_abs, eps_rel;
+    const int *Q_rp, *Q_ci;
+    const double *Q_v, *Q_c, *Q_w;
+    const double *Sx, *cx, *Su, *cu, *Sp, *cp, *t_grid;
+    const double *xsol;
+    ModelPar par;
+    double *xd, *ud, *p, *xn, *un, *pn;
+    double *J_ref, *L_aug, *J_out, *eta, *lam, *dev, *nodeq;
+    int *nodef;
+    const int *cone_status, *feas_new;
+    int *done, *status, *iters, *nactive, *accept;
+};
+
+// one thread per (seed, node): the per-node terms of
+//   * the convexification error of the dynamics (update_trust_region!, gusto.jl:1262-1283): |f(sol) - f_lin(sol)|_2 and
+//     |f_lin(sol)|_2 with f_lin the linearisation about the reference node;
+//   * the nonconvex state penalty of the candidate (state_penalty_cost, :nonconvex, gusto.jl:846-864):
+//     lambda sum_i max(0, s_i)^2, and the hard feasibility flag of update_rule! (s_i > 1e-3, gusto.jl:1345-1360);
+//   * the trust-region left-hand side |xh_k - xh_ref,k|_q (trust_region_cost, :nonconvex, gusto.jl:1167-1187).
+template <class M, class CP>
+__global__ void k_gusto_nodes(const GustoDev d)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)d.B * d.N) return;
+    const int b = (int)(i / d.N), k = (int)(i % d.N);
+    if (d.done[b]) return;
+    constexpr int NX = M::NX, NU = M::NU, NF = M::NF;
+    const double *xr = d.xd + ((size_t)b * d.N + k) * NX, *ur = d.ud + ((size_t)b * d.N + k) * NU, *pr = d.p + (size_t)b * d.np;
+    const double *xs = d.xn + ((size_t)b * d.N + k) * NX, *us = d.un + ((size_t)b * d.N + k) * NU, *ps = d.pn + (size_t)b * d.np;
+    const double t = d.t_grid[k];
+    double f[NX], A[NX * NX], Bm[NX * NU], F[NX * NF], fl[NX];
+    M::eval(d.par, t, xr, ur, pr, f, A, Bm, F);
+    for (int r = 0; r < NX; r++) {           // f_lin(sol) = f(ref) + A (xs - xr) + B (us - ur) + F (ps - pr)
+        double a = f[r];
+        for (int j = 0; j < NX; j++) a = fma(A[r + NX * j], xs[j] - xr[j], a);
+        for (int j = 0; j < NU; j++) a = fma(Bm[r + NX * j], us[j] - ur[j], a);
+        for (int j = 0; j < NF; j++) a = fma(F[r + NX * j], ps[M::fcol(j)] - pr[M::fcol(j)], a);
+        fl[r] = a;
+    }
+    M::eval(d.par, t, xs, us, ps, f, A, Bm, F);
+    double df = 0.0, dn = 0.0;
+    for (int r = 0; r < NX; r++) { df += (f[r] - fl[r]) * (f[r] - fl[r]); dn += fl[r] * fl[r]; }
+    double pen = 0.0;
+    int viol = 0;
+    if constexpr (CP::NS > 0) {
+        constexpr int NS = CP::NS, NG = CP::NG;
+        double s[NS], C[NS * NX], D[NS * NU], Gm[NS * NG];
+        CP::eval(d.par, t, d.N, k, xs, us, ps, s, C, D, Gm);
+        for (int r = 0; r < NS; r++) {
+            const double m = fmax(s[r], 0.0);
+            pen += m * m;
+            if (s[r] > 1e-3) viol = 1;
+        }
+        pen *= d.lam[b];
+    }
+    double tr = 0.0;
+    for (int j = 0; j < NX; j++) tr = qnorm_acc(tr, (xs[j] - d.cx[j]) / d.Sx[j] - (xr[j] - d.cx[j]) / d.Sx[j], d.q_tr);
+    if (d.q_tr == 2) tr = sqrt(tr);
+    double *o = d.nodeq + 4 * (size_t)i;
+    o[0] = sqrt(df); o[1] = sqrt(dn); o[2] = pen; o[3] = tr;
+    d.nodef[i] = viol;
+}
+
+// value of solver variable v (scaled) at the physical trajectory (x, u, p)
+__device__ __forceinline__ double gusto_var(const GustoDev &d, const double *x, const double *u, const double *p, int v)
+{
+    if (v >= d.vx && v < d.vx + d.N * d.nx) { const int e = v - d.vx, i = e % d.nx; return (x[e] - d.cx[i]) / d.Sx[i]; }
+    if (v >= d.vu && v < d.vu + d.N * d.nu) { const int e = v - d.vu, i = e % d.nu; return (u[e] - d.cu[i]) / d.Su[i]; }
+    const int j = v - d.vp;
+    return (p[j] - d.cp[j]) / d.Sp[j];
+}
+
+// one thread per seed: SubproblemSolution(spbm) costs (gusto.jl:399-418), check_stopping_criterion! (:1203-1231),
+// update_trust_region! (:1245-1293) and update_rule! (:1310-1427, with the mu-shrink of the next subproblem's eta, :268).
+__global__ void k_gusto_step(const GustoDev d)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= d.B) return;
+    d.accept[b] = 0;
+    if (d.done[b]) return;
+    const int cs = d.cone_status[b];
+    if (!(cs == IPM_OPTIMAL || cs == IPM_ALMOST)) {  // unsafe_solution, scp.jl:965-980
+        d.done[b] = 1; d.status[b] = 2 + 16 * cs; d.iters[b] = d.iter;
+        return;
+    }
+    const double *x = d.xn + (size_t)b * d.N * d.nx, *u = d.un + (size_t)b * d.N * d.nu, *p = d.pn + (size_t)b * d.np;
+    // original cost J of the candidate: affine row + weighted squares (original_cost, gusto.jl:680-707)
+    double J = 0.0;
+    for (int r = 0; r <= d.nsq; r++) {
+        double acc = d.Q_c[r];
+        for (int k = d.Q_rp[r]; k < d.Q_rp[r + 1]; k++) acc = fma(d.Q_v[k], gusto_var(d, x, u, p, d.Q_ci[k]), acc);
+        J += r == 0 ? acc : d.Q_w[r - 1] * acc * acc;
+    }
+    // soft trust-region cost as the subproblem measured it (J_tr = value(L_tr), gusto.jl:409)
+    double J_tr = d.Q_c[d.nsq + 1];
+    for (int k = d.Q_rp[d.nsq + 1]; k < d.Q_rp[d.nsq + 2]; k++) J_tr = fma(d.Q_v[k], d.xsol[gaddr(b, d.G, d.n, d.Q_ci[k])], J_tr);
+    // trapezoid sums of the node terms
+    const double *nq = d.nodeq + 4 * (size_t)b * d.N;
+    const int *nf = d.nodef + (size_t)b * d.N;
+    double dyn_err = 0.0, dyn_nrm = 0.0, J_st = 0.0, trmax = -1e300;
+    int viol = 0;
+    double dpn = 0.0;
+    for (int j = 0; j < d.np; j++) dpn = qnorm_acc(dpn, (p[j] - d.cp[j]) / d.Sp[j] - (d.p[(size_t)b * d.np + j] - d.cp[j]) / d.Sp[j], d.q_tr);
+    if (d.q_tr == 2) dpn = sqrt(dpn);
+    for (int k = 0; k < d.N; k++) {
+        if (k > 0) {
+            const double w = 0.5 * (d.t_grid[k] - d.t_grid[k - 1]);
+            dyn_err += (nq[4 * k] + nq[4 * (k - 1)]) * w;
+            dyn_nrm += (nq[4 * k + 1] + nq[4 * (k - 1) + 1]) * w;
+            J_st += (nq[4 * k + 2] + nq[4 * (k - 1) + 2]) * w;
+        }
+        trmax = fmax(trmax, nq[4 * k + 3]);
+        viol |= nf[k];
+    }
+    const double eta = d.eta[b], lam = d.lam[b];
+    const double J_aug = J + J_st + J_tr, L_aug = d.L_aug[b];
+    // deviation from the reference (solution_deviation, scp.jl:909-931)
+    const int q = d.q_exit;
+    double dp = 0.0;
+    for (int j = 0; j < d.np; j++) dp = qnorm_acc(dp, (p[j] - d.p[(size_t)b * d.np + j]) / d.Sp[j], q);
+    if (q == 2) dp = sqrt(dp);
+    double dx = 0.0;
+    for (int k = 0; k < d.N; k++) {
+        double a = 0.0;
+        for (int j = 0; j < d.nx; j++) {
+            const size_t o = ((size_t)b * d.N + k) * d.nx + j;
+            a = qnorm_acc(a, (d.xn[o] - d.xd[o]) / d.Sx[j], q);
+        }
+        if (q == 2) a = sqrt(a);
+        dx = fmax(dx, a);
+    }
+    const double deviation = dp + dx;
+    d.dev[b] = deviation;
+    const double Jr = d.J_ref[b];
+    const double dJ = fabs(Jr - J_aug) / fabs(Jr);
+    const bool infeas = lam > d.lam_max;
+    const bool stop = d.iter > 1 && ((d.feas_new[b] && (dJ <= d.eps_rel || deviation <= d.eps_abs)) || infeas);
+    bool acc = false;
+    if (!stop) {
+        const double cost_err = fabs(J_aug - L_aug), cost_nrm = fabs(L_aug);
+        const double rho = (cost_err + dyn_err) / (cost_nrm + dyn_nrm);
+        const bool trust_viol = (trmax + dpn - eta) > 1e-3;
+        double n_eta = eta, n_lam = lam;
+        if (trust_viol) n_lam = d.gamma_fail * lam;
+        else if (rho < d.rho_1) {
+            if (rho < d.rho_0) n_eta = fmin(d.eta_ub, d.beta_gr * eta);
+            n_lam = viol ? d.gamma_fail * lam : d.lam_init;
+            acc = true;
+        } else n_eta = fmax(d.eta_lb, eta / d.beta_sh);
+        const double kappa = d.iter < d.iter_mu ? 1.0 : pow(d.mu, (double)(1 + d.iter - d.iter_mu));
+        if (kappa < 1.0) n_eta *= kappa;
+        d.eta[b] = n_eta; d.lam[b] = n_lam;
+    }
+    const bool last = stop || d.iter >= d.iter_max;
+    if (acc || last) {   // the candidate becomes the reference; it is also what the loop returns when it ends (scp.jl:205-236)
+        for (int k = 0; k < d.N; k++) {
+            for (int j = 0; j < d.nx; j++) { const size_t o = ((size_t)b * d.N + k) * d.nx + j; d.xd[o] = d.xn[o]; }
+            for (int j = 0; j < d.nu; j++) { const size_t o = ((size_t)b * d.N + k) * d.nu + j; d.ud[o] = d.un[o]; }
+        }
+        for (int j = 0; j < d.np; j++) d.p[(size_t)b * d.np + j] = d.pn[(size_t)b * d.np + j];
+        d.J_ref[b] = J_aug;
+    }
+    d.accept[b] = (acc && !last) ? 1 : 0;
+    d.J_out[b] = J_aug;            // SCPSolution.cost = last_sol.J_aug (scp.jl:236)
+    d.iters[b] = d.iter;
+    if (stop) { d.done[b] = 1; d.status[b] = 0; }
+    else atomicAdd(d.nactive, 1);
+}
+
 __global__ void k_fill(double *v, double a, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) v[i] = a;
+}
+
+// nonconvex-constraint linearisation with the pack of the problem's model (none: only the scaled references)
+static void launch_linearize(scpb_ptr_s *s, const PtrDev &pd, int nbn, cudaStream_t st)
+{
+    const bool has = s->d.ns > 0;
+    if (has && s->model_id == SCPB_MODEL_STARSHIP) k_linearize<Constr<SCPB_MODEL_STARSHIP>><<<nbn, 128, 0, st>>>(pd, s->xd, s->ud, s->p);
+    else if (has && s->model_id == SCPB_MODEL_FREEFLYER) k_linearize<Constr<SCPB_MODEL_FREEFLYER>><<<nbn, 128, 0, st>>>(pd, s->xd, s->ud, s->p);
+    else if (has && s->model_id == SCPB_MODEL_QUADROTOR) k_linearize<Constr<SCPB_MODEL_QUADROTOR>><<<nbn, 128, 0, st>>>(pd, s->xd, s->ud, s->p);
+    else k_linearize<Constr<0>><<<nbn, 128, 0, st>>>(pd, s->xd, s->ud, s->p);
+}
+
+template <class M, class CP>
+static void launch_gusto_nodes_t(const GustoDev &gd, int nbn, cudaStream_t st)
+{
+    k_gusto_nodes<M, CP><<<nbn, 64, 0, st>>>(gd);
+}
+
+static int launch_gusto_nodes(scpb_ptr_s *s, const GustoDev &gd, cudaStream_t st)
+{
+    const int nbn = (int)(((long long)gd.B * gd.N + 63) / 64);
+    const bool has = s->d.ns > 0;
+    switch (s->model_id) {
+    case SCPB_MODEL_DBLINT: launch_gusto_nodes_t<Model<SCPB_MODEL_DBLINT>, Constr<0>>(gd, nbn, st); break;
+    case SCPB_MODEL_ROCKET: launch_gusto_nodes_t<Model<SCPB_MODEL_ROCKET>, Constr<0>>(gd, nbn, st); break;
+    case SCPB_MODEL_STARSHIP:
+        if (has) launch_gusto_nodes_t<Model<SCPB_MODEL_STARSHIP>, Constr<SCPB_MODEL_STARSHIP>>(gd, nbn, st);
+        else launch_gusto_nodes_t<Model<SCPB_MODEL_STARSHIP>, Constr<0>>(gd, nbn, st);
+        break;
+    case SCPB_MODEL_QUADROTOR:
+        if (has) launch_gusto_nodes_t<Model<SCPB_MODEL_QUADROTOR>, Constr<SCPB_MODEL_QUADROTOR>>(gd, nbn, st);
+        else launch_gusto_nodes_t<Model<SCPB_MODEL_QUADROTOR>, Constr<0>>(gd, nbn, st);
+        break;
+    case SCPB_MODEL_FREEFLYER:
+        if (has) launch_gusto_nodes_t<Model<SCPB_MODEL_FREEFLYER>, Constr<SCPB_MODEL_FREEFLYER>>(gd, nbn, st);
+        else launch_gusto_nodes_t<Model<SCPB_MODEL_FREEFLYER>, Constr<0>>(gd, nbn, st);
+        break;
+    default: return SCPB_ERR_UNSUPPORTED;
+    }
+    return SCPB_OK;
 }
 
 extern "C" {
@@ -587,14 +814,7 @@ int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *u
     long long ipm_iters = 0;
     std::vector<int> hit(B);
     for (; it <= d.iter_max; it++) {
-        if (d.ns > 0 && s->model_id == SCPB_MODEL_STARSHIP)
-            k_linearize<Constr<SCPB_MODEL_STARSHIP>><<<nbn, 128, 0, st>>>(pd, s->xd, s->ud, s->p);
-        else if (d.ns > 0 && s->model_id == SCPB_MODEL_FREEFLYER)
-            k_linearize<Constr<SCPB_MODEL_FREEFLYER>><<<nbn, 128, 0, st>>>(pd, s->xd, s->ud, s->p);
-        else if (d.ns > 0 && s->model_id == SCPB_MODEL_QUADROTOR)
-            k_linearize<Constr<SCPB_MODEL_QUADROTOR>><<<nbn, 128, 0, st>>>(pd, s->xd, s->ud, s->p);
-        else
-            k_linearize<Constr<0>><<<nbn, 128, 0, st>>>(pd, s->xd, s->ud, s->p);
+        launch_linearize(s, pd, nbn, st);
         const long long tot = (long long)d.nval * Bpad;
         k_assemble<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ad);
         h->launches += 2;
@@ -816,6 +1036,185 @@ int32_t scpb_scvx_solve(scpb_ptr s, int32_t B, const double *xd0, const double *
         timing[4] = tot_ms * 1e-3; timing[5] = (double)total_it; timing[6] = (double)ipm_iters; timing[7] = 0.0;
     }
     return ptr_check_disc_status(h, "scvx_solve");
+}
+
+int32_t scpb_gusto_attach(scpb_ptr s, const scpb_gusto_desc *desc, const int32_t *Q_rowptr, const int32_t *Q_colind,
+                          const double *Q_vals, const double *Q_const, const double *Q_weight)
+{
+    if (!s) return SCPB_ERR_ARG;
+    scpb_handle_s *h = s->h;
+    if (!desc || !Q_rowptr || !Q_colind || !Q_vals || !Q_const || (desc->nsq > 0 && !Q_weight))
+        return set_err(h, SCPB_ERR_ARG, "gusto_attach: null pointer");
+    const scpb_ptr_desc &d = s->d;
+    if (desc->oeta <= 0 || desc->oeta >= d.nsrc || desc->osl <= 0 || desc->osl >= d.nsrc || desc->osl == desc->oeta ||
+        desc->nsq < 0 || desc->q_tr < 0 || desc->q_tr > 2)
+        return set_err(h, SCPB_ERR_ARG, "gusto_attach: bad descriptor (oeta=%d, osl=%d, nsq=%d, q_tr=%d)", desc->oeta, desc->osl,
+                       desc->nsq, desc->q_tr);
+    if (s->scvx) return set_err(h, SCPB_ERR_STATE, "gusto_attach: the problem already carries the SCvx extras");
+    const ConeSymbolic *S = scpb_internal_cone_sym(s->cone);
+    const int nq = desc->nsq + 2, nnz = Q_rowptr[nq], nphys = Q_rowptr[desc->nsq + 1];
+    for (int k = 0; k < nnz; k++) {
+        const int v = Q_colind[k];
+        const bool phys = (v >= d.vx && v < d.vx + d.N * d.nx) || (v >= d.vu && v < d.vu + d.N * d.nu) ||
+                          (v >= d.vp && v < d.vp + d.np);
+        if (k < nphys ? !phys : (v < 0 || v >= S->n))
+            return set_err(h, SCPB_ERR_ARG, "gusto_attach: Q references solver variable %d outside its block", v);
+    }
+    SCPB_CUDA(h, cudaSetDevice(h->device));
+    s->gv = *desc;
+    s->Q_rp = up(s, Q_rowptr, (size_t)nq + 1);
+    s->Q_ci = up(s, Q_colind, (size_t)nnz);
+    s->Q_v = up(s, Q_vals, (size_t)nnz);
+    s->Q_c = up(s, Q_const, (size_t)nq);
+    s->Q_w = up(s, Q_weight, (size_t)desc->nsq);
+    if (!s->Q_rp || !s->Q_ci || !s->Q_v || !s->Q_c || !s->Q_w) return set_err(h, SCPB_ERR_CUDA, "gusto_attach: device allocation failed");
+    s->gusto = true;
+    s->capB = 0;   // batch buffers are re-reserved with the GuSTO extras
+    return SCPB_OK;
+}
+
+int32_t scpb_gusto_solve(scpb_ptr s, int32_t B, const double *xd0, const double *ud0, const double *p0,
+                         const scpb_cone_opts *opts, double *xd, double *ud, double *p, int32_t *status,
+                         int32_t *iters, double *J, double *deviation, int32_t *feas, double *eta, double *lam,
+                         double *timing)
+{
+    if (!s) return SCPB_ERR_ARG;
+    scpb_handle_s *h = s->h;
+    if (!s->gusto) return set_err(h, SCPB_ERR_STATE, "gusto_solve: call scpb_gusto_attach first");
+    if (B <= 0 || !xd0 || !ud0 || !p0) return set_err(h, SCPB_ERR_ARG, "gusto_solve: bad arguments");
+    SCPB_CUDA(h, cudaSetDevice(h->device));
+    ptr_select_model(s);
+    SCPB_CUDA(h, cudaMemsetAsync(h->d_status, 0, sizeof(int), h->stream));
+    const scpb_ptr_desc &d = s->d;
+    const scpb_gusto_desc &v = s->gv;
+    const int G = scpb_internal_pick_group(B, opts ? opts->group : 0);
+    int rc = scpb_internal_cone_reserve(s->cone, B, G, opts ? opts->lanes : 0);
+    if (rc) return rc;
+    if ((rc = ptr_reserve(s, B, G))) return rc;
+    IpmData *D = scpb_internal_cone_data(s->cone);
+    const ConeSymbolic *S = scpb_internal_cone_sym(s->cone);
+    const IpmOpts o = scpb_internal_make_opts(opts);
+    cudaStream_t st = h->stream;
+    const size_t nX = (size_t)B * d.N * d.nx, nU = (size_t)B * d.N * d.nu, nP = (size_t)B * d.np;
+    SCPB_CUDA(h, cudaMemcpyAsync(s->xd, xd0, sizeof(double) * nX, cudaMemcpyHostToDevice, st));
+    SCPB_CUDA(h, cudaMemcpyAsync(s->ud, ud0, sizeof(double) * nU, cudaMemcpyHostToDevice, st));
+    SCPB_CUDA(h, cudaMemcpyAsync(s->p, p0, sizeof(double) * nP, cudaMemcpyHostToDevice, st));
+    SCPB_CUDA(h, cudaMemsetAsync(s->src, 0, sizeof(double) * (size_t)d.nsrc * s->capB, st));
+    SCPB_CUDA(h, cudaMemsetAsync(s->src2, 0, sizeof(double) * (size_t)d.nsrc * s->capB, st));
+    SCPB_CUDA(h, cudaMemsetAsync(s->done, 0, sizeof(int) * s->capB, st));
+    SCPB_CUDA(h, cudaMemsetAsync(s->iters, 0, sizeof(int) * s->capB, st));
+    std::vector<int> init_status(s->capB, 1);
+    SCPB_CUDA(h, cudaMemcpyAsync(s->status, init_status.data(), sizeof(int) * s->capB, cudaMemcpyHostToDevice, st));
+    std::vector<double> nanv(s->capB, nan(""));
+    SCPB_CUDA(h, cudaMemcpyAsync(s->devi, nanv.data(), sizeof(double) * s->capB, cudaMemcpyHostToDevice, st));
+    SCPB_CUDA(h, cudaMemcpyAsync(s->J_out, nanv.data(), sizeof(double) * s->capB, cudaMemcpyHostToDevice, st));
+    SCPB_CUDA(h, cudaMemcpyAsync(s->J_ref, nanv.data(), sizeof(double) * s->capB, cudaMemcpyHostToDevice, st));  // the guess has no J_aug
+    k_fill<<<(s->capB + 127) / 128, 128, 0, st>>>(s->eta, v.eta_init, s->capB);
+    k_fill<<<(s->capB + 127) / 128, 128, 0, st>>>(s->lam, v.lam_init, s->capB);
+    h->launches += 2;
+
+    const size_t nsc = (size_t)(d.nx + d.nu + d.np);
+    const double *Sx = s->scale, *Su = Sx + d.nx, *Sp = Su + d.nu, *cx = s->scale + nsc, *cu = cx + d.nx, *cp = cu + d.nu;
+    PtrDev pd{};
+    pd.B = B; pd.G = G; pd.N = d.N; pd.nx = d.nx; pd.nu = d.nu; pd.np = d.np; pd.ns = d.ns;
+    pd.nsrc = d.nsrc; pd.oC = d.oC; pd.oD = d.oD; pd.oG = d.oG; pd.ors = d.ors; pd.oxh = d.oxh; pd.ouh = d.ouh; pd.oph = d.oph;
+    pd.t_grid = s->tgrid; pd.Sx = Sx; pd.cx = cx; pd.Su = Su; pd.cu = cu; pd.Sp = Sp; pd.cp = cp;
+    pd.src = s->src; pd.par = s->par; pd.eta = s->eta; pd.oeta = v.oeta; pd.lam = s->lam; pd.osl = v.osl;
+    AsmDev ad{};
+    ad.B = B; ad.G = G; ad.nsrc = d.nsrc; ad.nval = d.nval; ad.nnzA = (int)S->A_ci.size(); ad.nnzG = (int)S->G_ci.size();
+    ad.n = S->n; ad.p = S->p; ad.m = S->m; ad.W_rp = s->W_rp; ad.W_ci = s->W_ci; ad.W_v = s->W_v; ad.src = s->src;
+    ad.Av = D->Av; ad.Gv = D->Gv; ad.c = D->c; ad.b = D->b; ad.h = D->h; ad.c0 = s->c0;
+    StepDev sd{};   // k_extract only: J_new = pobj + c0 is the subproblem's L_aug
+    sd.B = B; sd.G = G; sd.N = d.N; sd.nx = d.nx; sd.nu = d.nu; sd.np = d.np; sd.n = S->n; sd.vx = d.vx; sd.vu = d.vu; sd.vp = d.vp;
+    sd.q_exit = d.q_exit; sd.eps_abs = d.eps_abs; sd.eps_rel = d.eps_rel;
+    sd.Sx = Sx; sd.cx = cx; sd.Su = Su; sd.cu = cu; sd.Sp = Sp; sd.cp = cp;
+    sd.xsol = D->x; sd.pobj = D->pobj; sd.c0 = s->c0; sd.cone_status = D->status;
+    sd.xd = s->xd; sd.ud = s->ud; sd.p = s->p; sd.xn = s->xn; sd.un = s->un; sd.pn = s->pn;
+    sd.J_ref = s->J_ref; sd.J_new = s->J_new; sd.dev = s->devi; sd.imp = s->imp; sd.feas_new = s->feas;
+    sd.done = s->done; sd.status = s->status; sd.iters = s->iters; sd.nactive = s->nactive;
+    GustoDev gd{};
+    gd.B = B; gd.G = G; gd.N = d.N; gd.nx = d.nx; gd.nu = d.nu; gd.np = d.np; gd.n = S->n; gd.vx = d.vx; gd.vu = d.vu; gd.vp = d.vp;
+    gd.q_exit = d.q_exit; gd.q_tr = v.q_tr; gd.iter_max = d.iter_max; gd.iter_mu = v.iter_mu; gd.nsq = v.nsq;
+    gd.lam_init = v.lam_init; gd.lam_max = v.lam_max; gd.rho_0 = v.rho_0; gd.rho_1 = v.rho_1; gd.beta_sh = v.beta_sh;
+    gd.beta_gr = v.beta_gr; gd.gamma_fail = v.gamma_fail; gd.eta_lb = v.eta_lb; gd.eta_ub = v.eta_ub; gd.mu = v.mu;
+    gd.eps_abs = d.eps_abs; gd.eps_rel = d.eps_rel;
+    gd.Q_rp = s->Q_rp; gd.Q_ci = s->Q_ci; gd.Q_v = s->Q_v; gd.Q_c = s->Q_c; gd.Q_w = s->Q_w;
+    gd.Sx = Sx; gd.cx = cx; gd.Su = Su; gd.cu = cu; gd.Sp = Sp; gd.cp = cp; gd.t_grid = s->tgrid; gd.xsol = D->x;
+    gd.par = s->par;
+    gd.xd = s->xd; gd.ud = s->ud; gd.p = s->p; gd.xn = s->xn; gd.un = s->un; gd.pn = s->pn;
+    gd.J_ref = s->J_ref; gd.L_aug = s->J_new; gd.J_out = s->J_out; gd.eta = s->eta; gd.lam = s->lam; gd.dev = s->devi;
+    gd.nodeq = s->nodeq; gd.nodef = s->nodef;
+    gd.cone_status = D->status; gd.feas_new = s->feas;
+    gd.done = s->done; gd.status = s->status; gd.iters = s->iters; gd.nactive = s->nactive; gd.accept = s->accept;
+    ScvxDev cv{};   // k_scvx_take_dltv only
+    cv.B = B; cv.G = G; cv.nsrc = d.nsrc; cv.dltv_lo = d.oA; cv.dltv_hi = d.oC; cv.accept = s->accept; cv.src = s->src; cv.src2 = s->src2;
+
+    EventList evl;
+    std::vector<cudaEvent_t> &ev = evl.ev;
+    auto mark = [&]() { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev.push_back(e); };
+    std::vector<int> phase;
+    mark(); phase.push_back(-1);
+    if ((rc = run_discretize(s, B, G, s->xd, s->ud, s->p))) return rc;   // generate_initial_guess -> discretize! (gusto.jl:517-526)
+    mark(); phase.push_back(0);
+    const int nbn = (int)(((long long)B * d.N + 127) / 128);
+    const int Bpad = s->capB;
+    int it = 1, nact = B, total_it = 0;
+    long long ipm_iters = 0;
+    std::vector<int> hit(B);
+    const long long span = (long long)(d.oC - d.oA) * B;
+    for (; it <= d.iter_max; it++) {
+        launch_linearize(s, pd, nbn, st);
+        const long long tot = (long long)d.nval * Bpad;
+        k_assemble<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ad);
+        h->launches += 2;
+        mark(); phase.push_back(1);
+        if ((rc = scpb_internal_cone_run(s->cone, o, s->done))) return rc;
+        mark(); phase.push_back(2);
+        SCPB_CUDA(h, cudaMemcpyAsync(hit.data(), D->iters, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+        sd.iter = it;
+        k_extract<<<nbn, 128, 0, st>>>(sd);
+        h->launches++;
+        mark(); phase.push_back(3);
+        if ((rc = run_discretize(s, B, G, s->xn, s->un, s->pn, s->src2, s->done))) return rc;   // candidate: DLTV into src2
+        mark(); phase.push_back(0);
+        SCPB_CUDA(h, cudaMemsetAsync(s->nactive, 0, sizeof(int), st));
+        gd.iter = it;
+        if (launch_gusto_nodes(s, gd, st)) return set_err(h, SCPB_ERR_UNSUPPORTED, "gusto_solve: no device pack for model %d", s->model_id);
+        k_gusto_step<<<(B + 63) / 64, 64, 0, st>>>(gd);
+        k_scvx_take_dltv<<<(unsigned)((span + 255) / 256), 256, 0, st>>>(cv);
+        h->launches += 3;
+        SCPB_CUDA(h, cudaMemcpyAsync(&nact, s->nactive, sizeof(int), cudaMemcpyDeviceToHost, st));
+        mark(); phase.push_back(3);
+        SCPB_CUDA(h, cudaStreamSynchronize(st));
+        for (int b = 0; b < B; b++) ipm_iters += hit[b];
+        total_it++;
+        if (nact == 0) break;
+    }
+    SCPB_CUDA(h, cudaGetLastError());
+    if (xd) SCPB_CUDA(h, cudaMemcpyAsync(xd, s->xd, sizeof(double) * nX, cudaMemcpyDeviceToHost, st));
+    if (ud) SCPB_CUDA(h, cudaMemcpyAsync(ud, s->ud, sizeof(double) * nU, cudaMemcpyDeviceToHost, st));
+    if (p) SCPB_CUDA(h, cudaMemcpyAsync(p, s->p, sizeof(double) * nP, cudaMemcpyDeviceToHost, st));
+    if (status) SCPB_CUDA(h, cudaMemcpyAsync(status, s->status, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    if (iters) SCPB_CUDA(h, cudaMemcpyAsync(iters, s->iters, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    if (J) SCPB_CUDA(h, cudaMemcpyAsync(J, s->J_out, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+    if (deviation) SCPB_CUDA(h, cudaMemcpyAsync(deviation, s->devi, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+    if (feas) SCPB_CUDA(h, cudaMemcpyAsync(feas, s->feas, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    if (eta) SCPB_CUDA(h, cudaMemcpyAsync(eta, s->eta, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+    if (lam) SCPB_CUDA(h, cudaMemcpyAsync(lam, s->lam, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+    SCPB_CUDA(h, cudaStreamSynchronize(st));
+    double acc[4] = {0, 0, 0, 0};
+    for (size_t i = 1; i < ev.size(); i++) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+        if (phase[i] >= 0) acc[phase[i]] += ms * 1e-3;
+    }
+    float tot_ms = 0.f;
+    cudaEventElapsedTime(&tot_ms, ev.front(), ev.back());
+    if (timing) {
+        timing[0] = acc[0]; timing[1] = acc[1]; timing[2] = acc[2]; timing[3] = acc[3];
+        timing[4] = tot_ms * 1e-3; timing[5] = (double)total_it; timing[6] = (double)ipm_iters; timing[7] = 0.0;
+    }
+    return ptr_check_disc_status(h, "gusto_solve");
 }
 
 }  // extern "C"

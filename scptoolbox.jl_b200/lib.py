@@ -51,6 +51,9 @@ SIGNATURES = {
     "scpb_ptr_solve": (C.c_int32, [C.c_void_p, C.c_int32, _dp, _dp, _dp, C.c_void_p, _dp, _dp, _dp, _ip, _ip,
                                    _dp, _dp, _ip, _dp]),
     "scpb_scvx_attach": (C.c_int32, [C.c_void_p, C.c_void_p, _ip, _ip, _dp, _dp]),
+    "scpb_gusto_attach": (C.c_int32, [C.c_void_p, C.c_void_p, _ip, _ip, _dp, _dp, _dp]),
+    "scpb_gusto_solve": (C.c_int32, [C.c_void_p, C.c_int32, _dp, _dp, _dp, C.c_void_p, _dp, _dp, _dp, _ip, _ip,
+                                     _dp, _dp, _ip, _dp, _dp, _dp]),
     "scpb_scvx_solve": (C.c_int32, [C.c_void_p, C.c_int32, _dp, _dp, _dp, C.c_void_p, _dp, _dp, _dp, _ip, _ip,
                                     _dp, _dp, _ip, _dp, _dp]),
     "scpb_debug_level_profile": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
@@ -84,6 +87,12 @@ class PtrDesc(C.Structure):
 class ScvxDesc(C.Structure):        # scpb_scvx_desc (include/scpb.h)
     _fields_ = [(k, C.c_double) for k in ("lam", "rho_0", "rho_1", "rho_2", "beta_sh", "beta_gr", "eta_init", "eta_lb",
                                            "eta_ub")] + [(k, C.c_int32) for k in ("oeta", "n_ic", "n_tc", "reserved")]
+
+
+class GustoDesc(C.Structure):       # scpb_gusto_desc (include/scpb.h)
+    _fields_ = [(k, C.c_double) for k in ("lam_init", "lam_max", "rho_0", "rho_1", "beta_sh", "beta_gr", "gamma_fail",
+                                           "eta_init", "eta_lb", "eta_ub", "mu")] + \
+               [(k, C.c_int32) for k in ("iter_mu", "q_tr", "oeta", "osl", "nsq", "reserved")]
 
 
 CONE_STATUS = {0: "OPTIMAL", 1: "ITERATION_LIMIT", 2: "NUMERICAL_ERROR", 3: "ALMOST_OPTIMAL", 4: "INFEASIBLE",

@@ -156,6 +156,7 @@ class ConicTemplate:
         self.var_stage = []       # stage label per variable (-1 global, -2 derive from neighbours)
         self.eq, self.ineq, self.socs = [], [], []
         self.cost = Expr()
+        self.sq_log = {}          # epigraph variable of a sumsq -> its squared rows (GuSTO evaluates them on the device)
 
     def new_variable(self, shape, name, S=None, c=None, stage=None):
         """@new_variable + @scale: returns Expr array in physical units x = S*xh + c.
@@ -235,6 +236,7 @@ class ConicTemplate:
         quadratic-to-SOC bridge; the minimiser is identical)."""
         q = self._aux(1, stage)[0]
         self.socs.append([q + 1.0] + [Expr.lift(e) * 2.0 for e in exprs] + [q - 1.0])
+        self.sq_log[next(iter(q.t))] = [Expr.lift(e) for e in exprs]
         return q
 
     def add_cost(self, e):

@@ -25,6 +25,7 @@ class TrajectoryProblem:
         self.p_stage = None
         self.guess = None
         self.phi = None          # terminal cost  phi(x_expr, p_expr, pbm) -> Expr     (problem.jl:365-368)
+        self.S = None            # GuSTO: input quadratic penalty S(t,k,p,pbm) of the running cost   (problem.jl:405)
         self.Gamma = None        # running cost   Gamma(t,k,x,u,p,pbm) -> Expr          (problem.jl:392-394)
         self.X = None            # X(t,k,x,p,pbm,ocp): emits cone rows into ocp        (problem.jl:487-523)
         self.U = None            # U(t,k,u,p,pbm,ocp)                                  (problem.jl:534-543)
@@ -63,8 +64,14 @@ def problem_set_terminal_cost(pbm, phi):
     pbm.phi = lambda x, p: phi(x, p, pbm)
 
 
-def problem_set_running_cost(pbm, Gamma):
-    pbm.Gamma = lambda t, k, x, u, p: Gamma(t, k, x, u, p, pbm)
+def problem_set_running_cost(pbm, SGamma, algo="ptr"):
+    """problem_set_running_cost! (problem.jl:390-418).  SCvx / PTR: the running cost Gamma(t, k, x, u, p, pbm).  GuSTO: the
+    input quadratic penalty S(t, k, p, pbm) of the running cost u' S u (convex: constant in p); the input-affine and
+    additive terms l and g of the GuSTO cost (problem.jl:395-400) are not mirrored."""
+    if algo == "gusto":
+        pbm.S = lambda t, k, p: SGamma(t, k, p, pbm)
+    else:
+        pbm.Gamma = lambda t, k, x, u, p: SGamma(t, k, x, u, p, pbm)
 
 
 def problem_set_dynamics(pbm, model_id, par, fcols=(0,), A_struct=None, B_struct=None):

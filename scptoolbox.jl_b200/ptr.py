@@ -158,7 +158,8 @@ class SourceMap:
         self.oxh = o; o += N * nx
         self.ouh = o; o += N * nu
         self.oph = o; o += np_
-        self.oeta = o; o += 1          # SCvx trust-region radius (scvx.jl:245); unused by PTR
+        self.oeta = o; o += 1          # SCvx / GuSTO trust-region radius (scvx.jl:245, gusto.jl:229); unused by PTR
+        self.osl = o; o += 1           # GuSTO: sqrt(lambda), the soft-penalty weight (gusto.jl:228)
         self.nsrc = o
         self.N, self.nx, self.nu, self.np, self.ns, self.nf, self.ng = N, nx, nu, np_, ns, nf, ng
 
@@ -319,6 +320,13 @@ class SCPProblem:
         else:
             prg.zero([Pf[1]])
         prg.add_cost((trapz(list(P), t) + Pf[0] + Pf[1]) * (pars.lam if scvx else pars.wvc))
+        self._finish(prg)
+
+    def _finish(self, prg):
+        """compile the template, order the KKT system stage-wise, create the device objects"""
+        pars, traj, sc, sm = self.pars, self.traj, self.scale, self.sm
+        N, nx, nu, np_ = pars.N, traj.nx, traj.nu, traj.np
+        ns, nf, ng = sm.ns, sm.nf, sm.ng
         self.template = prg
         self.cp = cp = prg.compile()
         # one extra W row for the cost constant c0
@@ -424,6 +432,65 @@ def solve(pbm: SCPProblem, guesses=None, **cone_opts) -> SCPBatchSolution:
     tm = dict(discretize=timing[0], formulate=timing[1], solve=timing[2], overhead=timing[3], total=timing[4],
               lockstep_iterations=int(timing[5]), ipm_iterations=int(timing[6]))
     return SCPBatchSolution(names, iters, J, pbm.t, xd, ud, p, dev, feas, tm, status)
+
+
+def correct_convex(pbm: SCPProblem, guesses, **cone_opts):
+    """correct_convex! (scp.jl:275-361) for a batch of guesses: the closest trajectory, in the scaled L1 sense, that
+    satisfies the convex path constraints X and U at every node -- what GuSTO and SCvx apply to the initial guess
+    (gusto.jl:517-526, scvx.jl:563).  One template (sources = the guess), one batched call of the GPU cone solver."""
+    traj, pars, sc, h, t = pbm.traj, pbm.pars, pbm.scale, pbm.handle, pbm.t
+    N, nx, nu, np_ = pars.N, traj.nx, traj.nu, traj.np
+    xd0 = np.ascontiguousarray(guesses[0], dtype=np.float64)
+    ud0 = np.ascontiguousarray(guesses[1], dtype=np.float64)
+    p0 = np.ascontiguousarray(guesses[2], dtype=np.float64)
+    B = xd0.shape[0]
+    cc = getattr(pbm, "_cc", None)
+    if cc is None:
+        ox, ou, op = 1, 1 + N * nx, 1 + N * nx + N * nu
+        prg = ConicTemplate(op + np_, l1_block=0)
+        x = prg.new_variable((nx, N), "x", sc.Sx, sc.cx, stage="col")
+        u = prg.new_variable((nu, N), "u", sc.Su, sc.cu, stage="col")
+        p = prg.new_variable(np_, "p", sc.Sp, sc.cp, stage=(traj.p_stage(N) if traj.p_stage else None))
+        for k in range(N):
+            if traj.X is not None:
+                traj.X(prg, t[k], k + 1, x[:, k], p)
+            if traj.U is not None:
+                traj.U(prg, t[k], k + 1, u[:, k], p)
+        ex = prg.new_variable(N, "tau_x", stage="idx"); eu = prg.new_variable(N, "tau_u", stage="idx")
+        ep = prg.new_variable(1, "tau_p", stage=None)
+        for k in range(N):
+            prg.l1([ex[k]] + [(x[i, k] - Expr(None, Lin.src(ox + k * nx + i))) * (1.0 / sc.Sx[i]) for i in range(nx)],
+                   "x_variation", stage=k)
+            prg.l1([eu[k]] + [(u[i, k] - Expr(None, Lin.src(ou + k * nu + i))) * (1.0 / sc.Su[i]) for i in range(nu)],
+                   "u_variation", stage=k)
+        prg.l1([ep[0]] + [(p[i] - Expr(None, Lin.src(op + i))) * (1.0 / sc.Sp[i]) for i in range(np_)], "p_variation", stage=-1)
+        J = Expr()
+        for k in range(N):
+            J = J + ex[k] + eu[k]
+        prg.add_cost(J + ep[0])
+        cp = prg.compile()
+        perm = ordering.stage_order(cp["A"], cp["G"], cp["var_stage"], N)
+        cc = pbm._cc = dict(prg=prg, cp=cp, perm=perm)
+    prg, cp = cc["prg"], cc["cp"]
+    src = np.concatenate([np.ones((B, 1)), xd0.reshape(B, -1), ud0.reshape(B, -1), p0], axis=1)
+    vals = np.asarray((cp["W"] @ src.T).T)
+    n, p_, m, nA, nG = cp["n"], cp["p"], cp["m"], cp["nnzA"], cp["nnzG"]
+    cone = lib.ConeProblem(h, cp["A"], cp["G"], cp["l"], cp["soc_dims"], perm=cc["perm"])
+    try:
+        out = cone.solve(vals[:, :nA], vals[:, nA:nA + nG], vals[:, cp["off_c"]:cp["off_c"] + n],
+                         vals[:, cp["off_b"]:cp["off_b"] + p_], vals[:, cp["off_h"]:cp["off_h"] + m], **cone_opts)
+    finally:
+        cone.close()
+    bad = [int(s_) for s_ in out["status"] if s_ not in (0, 3)]
+    if bad:
+        raise lib.ScpbError("Solver failed to find the closest initial guess that satisfies the convex constraints "
+                            f"({lib.CONE_STATUS.get(bad[0], bad[0])})")
+    z = out["x"]
+    vx, vu, vp = prg.blocks["x"][0], prg.blocks["u"][0], prg.blocks["p"][0]
+    xd = z[:, vx:vx + N * nx].reshape(B, N, nx) * sc.Sx + sc.cx
+    ud = z[:, vu:vu + N * nu].reshape(B, N, nu) * sc.Su + sc.cu
+    pp = z[:, vp:vp + np_] * sc.Sp + sc.cp
+    return np.ascontiguousarray(xd), np.ascontiguousarray(ud), np.ascontiguousarray(pp)
 
 
 def propagate(pbm: SCPProblem, sol: SCPBatchSolution, res=None) -> SCPBatchSolution:

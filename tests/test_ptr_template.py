@@ -329,3 +329,81 @@ def test_freeflyer_template_matches_oracle_subproblem(pkg, monkeypatch):
     ox, (nx_, _) = bx["x"][0], bx["x"][1]
     oxo = prg.blocks["x"][0]
     assert np.abs(r1["z"][ox:ox + nx_ * N] - r2["z"][oxo:oxo + nx_ * N]).max() <= 1e-5
+
+
+def test_gusto_template_matches_oracle_subproblem(pkg, monkeypatch):
+    """BASELINE config C4 (quadrotor GuSTO): the GuSTO flavour of the template (un-relaxed dynamics and boundary
+    conditions, quadratic soft penalties through rotated cones with the per-seed sources sqrt(lambda) and eta) filled with
+    oracle quantities is the oracle's GuSTO subproblem: same sizes, same optimal value, same trajectory.  Also checks the
+    rows handed to scpb_gusto_attach: J = affine + weighted squares reproduces the oracle's original_cost, the last row is
+    L_tr."""
+    from oracle import conic, gusto as ogusto
+    N = 10
+    pbo = problems.QuadrotorProblem(N)
+    xd, ud, p = pbo.guess(N)
+    rng = np.random.default_rng(4)
+    xd = xd + 1e-2 * rng.standard_normal(xd.shape); ud = ud + 1e-2 * rng.standard_normal(ud.shape)
+    kw = dict(lam_init=1e4, lam_max=1e9, rho_0=0.1, rho_1=0.9, beta_sh=2.0, beta_gr=2.0, gamma_fail=5.0, eta_init=10.0,
+              eta_lb=1e-3, eta_ub=10.0, mu=0.8, iter_mu=6, eps_abs=0.0, eps_rel=0.0, feas_tol=1e-3)
+    P = ogusto.GuSTO(pbo, ogusto.Parameters(N=N, Nsub=15, iter_max=15, **kw))
+    ref = P.make_solution(xd, ud, p)
+    lam, eta = 5e4, 0.7
+    prg, hnd = P.build(ref, lam, eta)
+    ocp = prg.compile()
+    ex = pkg.examples.quadrotor
+    mdl = ex.QuadrotorProblem()
+    traj = pkg.problem.TrajectoryProblem(mdl)
+    ex.define_problem(traj, "gusto", handle=None)
+    xb, ub, pb_ = optr.compute_bbox(pbo, N)           # advise every variable: no GPU on this box
+    for i, r in enumerate(xb): pkg.problem.problem_advise_scale(traj, "state", i, r)
+    for i, r in enumerate(ub): pkg.problem.problem_advise_scale(traj, "input", i, r)
+    pars = pkg.gusto.Parameters(N, 15, 15, pkg.ptr.FOH, kw["lam_init"], kw["lam_max"], kw["rho_0"], kw["rho_1"], kw["beta_sh"],
+                                kw["beta_gr"], kw["gamma_fail"], kw["eta_init"], kw["eta_lb"], kw["eta_ub"], kw["mu"],
+                                kw["iter_mu"], 0.0, 0.0, 1e-3, "quad", 100.0, np.inf, np.inf)
+
+    class FakeHandle:
+        def model_set(self, *a): pass
+    monkeypatch.setattr(pkg.lib, "ConeProblem", lambda *a, **k: type("C", (), {"c": None, "close": lambda s: None})())
+    fake = FakeHandle()
+    fake.lib = type("L", (), {"scpb_ptr_setup": staticmethod(lambda *a: 0), "scpb_gusto_attach": staticmethod(lambda *a: 0)})()
+    fake.h = None
+    fake._check = lambda rc, what: None
+    pbm = pkg.gusto.GuSTOProblem(pars, traj, fake, l1_block=0)
+    cp, sm = pbm.cp, pbm.sm
+    assert np.abs(pbm.scale.Sx - P.scale.Sx).max() < 1e-12 and np.abs(pbm.scale.Su - P.scale.Su).max() < 1e-9
+    src = _sources(sm, pbo, P, ref)
+    src[sm.oeta] = eta; src[sm.osl] = np.sqrt(lam)
+    vals = pbm.W @ src
+    n, p_, m = cp["n"], cp["p"], cp["m"]
+    assert (n, p_, m, cp["l"]) == (ocp["c"].size, ocp["A"].shape[0], ocp["G"].shape[0], ocp["l"])
+    assert sorted(cp["soc_dims"]) == sorted(ocp["q"])
+    A = sp.csr_matrix((vals[:cp["nnzA"]], cp["A"].indices, cp["A"].indptr), shape=(p_, n))
+    G = sp.csr_matrix((vals[cp["nnzA"]:cp["nnzA"] + cp["nnzG"]], cp["G"].indices, cp["G"].indptr), shape=(m, n))
+    mine = dict(c=vals[cp["off_c"]:cp["off_c"] + n], c0=vals[-1], A=A, b=vals[cp["off_b"]:cp["off_b"] + p_], G=G,
+                h=vals[cp["off_h"]:cp["off_h"] + m], l=cp["l"], q=list(cp["soc_dims"]))
+    r1 = conic.solve_ipm(mine, tol=1e-9)
+    r2 = conic.solve_ipm(ocp, tol=1e-9)
+    print("gusto template:", r1["status"], r2["status"], r1["obj"], r2["obj"])
+    assert r1["status"] in ("OPTIMAL", "ALMOST_OPTIMAL") and r2["status"] in ("OPTIMAL", "ALMOST_OPTIMAL")
+    assert abs(r1["obj"] - r2["obj"]) <= 1e-6 * max(1.0, abs(r2["obj"]))     # two runs of a tol-1e-9 solver, |obj| ~ 1e6
+    bx = pbm.template.blocks
+    for name, cnt in (("x", 6 * N), ("u", 4 * N), ("p", 1)):
+        o1, o2 = bx[name][0], prg.blocks[name][0]
+        assert np.abs(r1["z"][o1:o1 + cnt] - r2["z"][o2:o2 + cnt]).max() <= 1e-5, name
+    # the rows of scpb_gusto_attach at the oracle's solution
+    z2 = r2["z"]
+    val = np.vectorize(lambda e: e.value(z2), otypes=[float])
+    xs, us, ps = val(hnd["x"]).T, val(hnd["u"]).T, val(hnd["p"])
+    sc = pbm.scale
+    zq = np.zeros(n)
+    zq[bx["x"][0]:bx["x"][0] + 6 * N] = ((xs - sc.cx) / sc.Sx).ravel()
+    zq[bx["u"][0]:bx["u"][0] + 4 * N] = ((us - sc.cu) / sc.Su).ravel()
+    zq[bx["p"][0]] = (ps[0] - sc.cp[0]) / sc.Sp[0]
+    rp, ci, v, c0 = pbm.Q
+    nsq = pbm.gdesc.nsq
+    rows = np.array([c0[r] + v[rp[r]:rp[r + 1]] @ zq[ci[rp[r]:rp[r + 1]]] for r in range(nsq + 1)])
+    J = rows[0] + (pbm.Q_w[:nsq] * rows[1:] ** 2).sum()
+    assert abs(J - P.original_cost(xs, us, ps)) <= 1e-12 * max(1.0, abs(J))
+    r = nsq + 1
+    Ltr = c0[r] + v[rp[r]:rp[r + 1]] @ r1["z"][ci[rp[r]:rp[r + 1]]]
+    assert abs(Ltr - conic.Aff.lift(hnd["L_tr"]).value(z2)) <= 1e-7 * max(1.0, abs(Ltr))
