@@ -38,15 +38,20 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="seeds in the batch (per GPU with --weak)")
+    ap.add_argument("--batch", type=int, default=None, help="seeds in the batch (per GPU with --weak); default 256 "
+                                                              "(ptr / scvx), 1024 (gusto)")
     ap.add_argument("--weak", action="store_true", help="weak scaling: --batch seeds on EVERY GPU (default: strong, "
                                                         "the batch is cut into ceil(batch/N) seeds per GPU)")
-    ap.add_argument("--N", type=int, default=100)
-    ap.add_argument("--Nsub", type=int, default=100)
+    ap.add_argument("--N", type=int, default=None, help="time nodes; default 100 (starship), 60 (quadrotor GuSTO)")
+    ap.add_argument("--Nsub", type=int, default=None, help="RK4 sub-steps per interval; default 100 (starship), 15 (quadrotor)")
     ap.add_argument("--cpu-seeds", type=int, default=0, help="seeds in the CPU sample (0 = one per host thread)")
-    ap.add_argument("--algo", default="ptr", choices=["ptr", "scvx"],
-                    help="ptr: the north-star workload (default); scvx: BASELINE configs[2], starship SCvx")
-    return ap.parse_args()
+    ap.add_argument("--algo", default="ptr", choices=["ptr", "scvx", "gusto"],
+                    help="ptr: the north-star workload (default); scvx: BASELINE configs[2], starship SCvx; "
+                         "gusto: BASELINE configs[3], quadrotor obstacle avoidance with GuSTO")
+    a = ap.parse_args()
+    dN, dNsub, dB = (60, 15, 1024) if a.algo == "gusto" else (100, 100, 256)
+    a.N = a.N or dN; a.Nsub = a.Nsub or dNsub; a.batch = a.batch or dB
+    return a
 
 
 class ClockSampler:
@@ -116,7 +121,42 @@ PTR = dict(iter_max=15, wvc=1e3, wtr=0.1, eps_abs=1e-5, eps_rel=0.01 / 100, feas
 # SCvx constants of the reference test (starship_flip/tests.jl:69-121)
 SCVX = dict(iter_max=100, lam=5e2, rho_0=0.0, rho_1=0.1, rho_2=0.7, beta_sh=2.0, beta_gr=2.0, eta_init=1.0, eta_lb=1e-8,
             eta_ub=10.0, eps_abs=1e-5, eps_rel=0.01 / 100, feas_tol=5e-3)
+# GuSTO constants of the reference test (quadrotor/tests.jl:81-145) with its commented-out stopping tolerances switched on
+GUSTO = dict(iter_max=15, lam_init=1e4, lam_max=1e9, rho_0=0.1, rho_1=0.9, beta_sh=2.0, beta_gr=2.0, gamma_fail=5.0,
+             eta_init=10.0, eta_lb=1e-3, eta_ub=10.0, mu=0.8, iter_mu=6, eps_abs=1e-5, eps_rel=0.01 / 100, feas_tol=1e-3)
 ALGO = "ptr"
+
+
+def workload_name(args):
+    if args.algo == "gusto":
+        return f"quadrotor GuSTO N={args.N} Nsub={args.Nsub}"
+    return f"starship_flip {args.algo.upper()} N={args.N} Nsub={args.Nsub}"
+
+
+def algo_constants(algo):
+    return {"ptr": PTR, "scvx": SCVX, "gusto": GUSTO}[algo]
+
+
+def make_seeds_c4(base, nb, seed, r0, rf):
+    """Synthetic seeds as SURVEY 8(d) specifies them for C4: the straight-line guess plus a lateral (horizontal, normal to
+    the r0 -> rf line) half-sine of amplitude U[-1, 1] m -- which side of the obstacles the guess passes --, and the flight
+    time tdil drawn from U[1, 2.5] s; seed 0 of stream 0 is the nominal guess."""
+    rng = np.random.default_rng(0x5C94 + seed)
+    x, u, p = base
+    N = x.shape[0]
+    d = np.asarray(rf, float) - np.asarray(r0, float)
+    lat = np.array([-d[1], d[0], 0.0]); lat /= np.linalg.norm(lat)
+    bump = np.sin(np.pi * np.arange(N) / (N - 1))
+    X, U, P = [], [], []
+    for b in range(nb):
+        pert = bool(b or seed)
+        xb = np.array(x, dtype=float)
+        pb = np.array(p, dtype=float)
+        if pert:
+            xb[:, 0:3] += rng.uniform(-1.0, 1.0) * bump[:, None] * lat[None, :]
+            pb[0] = rng.uniform(1.0, 2.5)
+        X.append(xb); U.append(np.array(u, dtype=float)); P.append(pb)
+    return np.array(X), np.array(U), np.array(P)
 
 
 def make_seeds(base, Sx, Su, nb, seed, cx=None, cu=None):
@@ -147,6 +187,22 @@ def oracle_worker(args):
     N, Nsub, hs, xd, ud, p = args[:6]
     algo = args[6] if len(args) > 6 else "ptr"
     from oracle import problems, ptr as optr, scvx as oscvx
+    if algo == "gusto":
+        from oracle import gusto as ogusto
+        pb = problems.QuadrotorProblem(N)
+        c = {k: v for k, v in GUSTO.items()}
+        P = ogusto.GuSTO(pb, ogusto.Parameters(N=N, Nsub=Nsub, solver_tol=1e-9, **c))
+        t0 = time.perf_counter()
+        try:
+            guess = optr.correct_convex(pb, P.scale, N, xd, ud, p, tol=1e-9)      # generate_initial_guess (gusto.jl:517-526)
+        except RuntimeError as e:
+            return 0, {"discretize": 0.0, "formulate": 0.0, "solve": time.perf_counter() - t0}, f"SCP_FAILED ({e})"
+        out = P.solve(guess)
+        tm = {"discretize": 0.0, "formulate": 0.0, "solve": 0.0}
+        for s in out["history"]:
+            for k in tm:
+                tm[k] += s.timing.get(k, 0.0)
+        return out["iterations"], tm, out["status"]
     pb = problems.StarshipProblem(N)
     pb.hs = hs
     if algo == "scvx":
@@ -177,9 +233,9 @@ def cpu_run(N, Nsub, hs, X, U, P, nproc):
     return its, wall, ph, [r[2] for r in res]
 
 
-def oracle_base_guess(N):
+def oracle_base_guess(N, algo="ptr"):
     from oracle import problems
-    pb = problems.StarshipProblem(N)
+    pb = problems.QuadrotorProblem(N) if algo == "gusto" else problems.StarshipProblem(N)
     g = pb.guess(N)
     return pb, g
 
@@ -206,14 +262,15 @@ def run_reference(args, rank):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
             "higher_is_better": True, "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"starship_flip {args.algo.upper()} N={args.N} Nsub={args.Nsub}",
+            "config": {"workload": workload_name(args),
                        "batch_total": args.batch * (args.gpus if args.weak else 1),
-                       "algorithm_constants": (SCVX if args.algo == "scvx" else PTR)},
+                       "algorithm_constants": algo_constants(args.algo)},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{nseeds} of {args.batch} seeds per step, one single-threaded process per core "
-                                       f"(oracle: C discretize + Python formulate + HiGHS LP); cores = "
+                                       f"(oracle: C discretize + Python formulate + "
+                                       f"{'interior-point SOCP' if args.algo == 'gusto' else 'HiGHS LP'}); cores = "
                                        f"min(visible CPUs {os.cpu_count()}, cgroup cpu.max quota)",
-                             "phase_cpu_seconds": ph},
+                             "phase_cpu_seconds": ph, "seeds_solved": sum(x == "SCP_SOLVED" for x in st)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -240,12 +297,18 @@ def run_ours(args, rank, local_rank, world):
     N, Nsub = args.N, args.Nsub
     Btot = args.batch * world if args.weak else args.batch      # seeds in the whole job
     h = pkg.Handle(local_rank)
-    ex = pkg.examples.starship
-    mdl = ex.StarshipProblem()
+    ex = pkg.examples.quadrotor if args.algo == "gusto" else pkg.examples.starship
+    mdl = ex.QuadrotorProblem() if args.algo == "gusto" else ex.StarshipProblem()
     traj = pkg.problem.TrajectoryProblem(mdl)
-    ex.define_problem(traj, "ptr", handle=h)
-    algo = pkg.scvx if args.algo == "scvx" else pkg.ptr
-    if args.algo == "scvx":
+    ex.define_problem(traj, args.algo if args.algo == "gusto" else "ptr", handle=h)
+    algo = {"scvx": pkg.scvx, "ptr": pkg.ptr, "gusto": pkg.gusto}[args.algo]
+    if args.algo == "gusto":
+        c = GUSTO
+        pars = pkg.gusto.Parameters(N, Nsub, c["iter_max"], pkg.ptr.FOH, c["lam_init"], c["lam_max"], c["rho_0"], c["rho_1"],
+                                    c["beta_sh"], c["beta_gr"], c["gamma_fail"], c["eta_init"], c["eta_lb"], c["eta_ub"],
+                                    c["mu"], c["iter_mu"], c["eps_abs"], c["eps_rel"], c["feas_tol"], "quad", 100.0, np.inf,
+                                    np.inf, None, {"verbose": 0, "maxit": 100})
+    elif args.algo == "scvx":
         pars = pkg.scvx.Parameters(N=N, Nsub=Nsub, disc_method=pkg.ptr.FOH, q_tr=np.inf, q_exit=np.inf,
                                    solver_opts={"verbose": 0, "maxit": 100}, **SCVX)
     else:
@@ -254,7 +317,11 @@ def run_ours(args, rank, local_rank, world):
     base = traj.guess(N)                     # nominal guess (GPU SOCP batch); outside the timed region
     pbm = algo.create(pars, traj, h)
     sc = pbm.scale
-    X, U, P = make_seeds(base, sc.Sx, sc.Su, Btot, 0, sc.cx, sc.cu)      # the whole batch, identical on every rank
+    if args.algo == "gusto":
+        X, U, P = make_seeds_c4(base, Btot, 0, mdl.r0, mdl.rf)
+        mdl.hs = 0.0
+    else:
+        X, U, P = make_seeds(base, sc.Sx, sc.Su, Btot, 0, sc.cx, sc.cu)      # the whole batch, identical on every rank
     lo, hi = pkg.sharded.shard_bounds(Btot, world, rank)
     Bloc = hi - lo
     info = pbm.cone.info()
@@ -349,7 +416,8 @@ def run_ours(args, rank, local_rank, world):
             cits, cwall, cph, _ = cpu_run(N, Nsub, mdl.hs, X[:nseeds], U[:nseeds], P[:nseeds], min(cores, nseeds))
             cpu = {"value": cits / cwall, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{nseeds} of {Btot} seeds, full {args.algo.upper()} solve each, one single-threaded process per core "
-                             f"(oracle: C discretize + Python formulate + HiGHS LP); cores = min(visible CPUs "
+                             f"(oracle: C discretize + Python formulate + "
+                             f"{'interior-point SOCP' if args.algo == 'gusto' else 'HiGHS LP'}); cores = min(visible CPUs "
                              f"{os.cpu_count()}, cgroup cpu.max quota)",
                    "phase_cpu_seconds": cph}
         nb_in = int(X.nbytes + U.nbytes + P.nbytes)
@@ -357,11 +425,13 @@ def run_ours(args, rank, local_rank, world):
                 "ms_per_step": 1e3 * dev_t / args.steps, "higher_is_better": True,
                 "scaling": "weak" if args.weak else "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"starship_flip {args.algo.upper()} N={N} Nsub={Nsub}", "batch_total": Btot,
+                "config": {"workload": workload_name(args), "batch_total": Btot,
                            "batch_per_gpu": -(-Btot // world), "partition": "contiguous blocks of ceil(batch_total / n_gpus) seeds",
-                           "algorithm_constants": (SCVX if args.algo == "scvx" else PTR),
-                           "seeds": "SURVEY 8(d): x += 0.05*Sx*N(0,1), u += 0.05*Su*N(0,1) clipped to the advised ranges, "
-                                    "(t1, t2) x U[0.8, 1.2]",
+                           "algorithm_constants": algo_constants(args.algo),
+                           "seeds": ("SURVEY 8(d): straight line + lateral half-sine of amplitude U[-1, 1] m, tdil ~ U[1, 2.5] s"
+                                     if args.algo == "gusto" else
+                                     "SURVEY 8(d): x += 0.05*Sx*N(0,1), u += 0.05*Su*N(0,1) clipped to the advised ranges, "
+                                     "(t1, t2) x U[0.8, 1.2]"),
                            "seeds_solved": int(solved), "seeds_total": Btot,
                            "scp_iterations_per_step": its / args.steps,
                            "scp_iterations_min_median_max": [int(itv.min()), float(np.median(itv)), int(itv.max())],

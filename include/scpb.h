@@ -105,6 +105,13 @@ int32_t scpb_propagate(scpb_handle h, int32_t method, int32_t B, int32_t N, int3
  * shared by the whole batch; values differ per seed.  perm (nullable) is the elimination order of
  * the n variables followed by the p equality rows (perm[k] = node eliminated k-th, variables are
  * 0..n-1, equality rows n..n+p-1); the host template supplies a stage-wise nested dissection. */
+/* Host-side helper (no GPU work): a reverse Cuthill-McKee elimination order of the reduced KKT graph for callers that
+ * have no stage information (the MathOptInterface shim); writes perm[n + p].  The SCP templates supply a better,
+ * stage-wise order themselves. */
+int32_t scpb_order_rcm(int32_t n, int32_t p, int32_t m, const int32_t *A_rowptr, const int32_t *A_colind,
+                       const int32_t *G_rowptr, const int32_t *G_colind, int32_t l, int32_t nsoc,
+                       const int32_t *soc_dims, int32_t *perm);
+
 typedef struct scpb_cone_s *scpb_cone;
 
 typedef struct {
@@ -206,12 +213,13 @@ int32_t scpb_scvx_solve(scpb_ptr ptr, int32_t B, const double *xd0, const double
 /* ---- batched GuSTO loop: replaces the body of GuSTO.solve (src/solvers/gusto.jl:425-502, pen = :quad) for B seeds ----
  * Same template machinery: scpb_ptr_setup with the GuSTO flavour of the subproblem (scptoolbox.jl_b200/gusto.py, mirror of
  * gusto.jl:218-287, 534-1190): dynamics and boundary conditions un-relaxed, the nonconvex path constraints and the trust
- * region enter through quadratic soft penalties lambda max(0, .)^2 lowered to rotated second-order cones, with the
- * per-seed sources `oeta` (trust-region radius eta) and `osl` (sqrt(lambda)).  scpb_gusto_attach adds the algorithm
+ * region enter through quadratic soft penalties lambda max(0, .)^2 -- epigraphs q >= v^2 as rotated second-order cones,
+ * lambda as a cost coefficient, so the cone entries stay O(1) whatever lambda is -- with the
+ * per-seed sources `oeta` (trust-region radius eta) and `olam` (the penalty weight lambda).  scpb_gusto_attach adds the algorithm
  * constants (gusto.jl:58-85) and the sparse rows Q over the scaled solver variables (constants Q_const):
  *   row 0            affine part of the original cost J(x,u,p)            (x, u, p blocks only)
  *   rows 1..nsq      rows r_j whose weighted squares complete it: J = row0 + sum_j Q_weight[j-1] r_j^2   (x, u, p only)
- *   row nsq+1        L_tr, the soft trust-region cost as the subproblem measures it (any solver variable)
+ *   row nsq+1        L_tr / lambda, the soft trust-region cost as the subproblem measures it (any solver variable)
  * With the dynamics / constraint packs these give, per iteration and seed, J, J_st, J_tr, J_aug of the new iterate
  * (gusto.jl:399-418), the convexification error rho (update_trust_region!, :1245-1293), the update rule for the
  * reference, eta and lambda (update_rule!, :1310-1427, incl. the mu-shrink of :268) and the stopping rule (:1203-1231).
@@ -219,7 +227,7 @@ int32_t scpb_scvx_solve(scpb_ptr ptr, int32_t B, const double *xd0, const double
  * (0/1 solved, 2+16*cone status failed), iterations, cost = J_aug, deviation, feas, and the final eta and lambda. */
 typedef struct {
     double lam_init, lam_max, rho_0, rho_1, beta_sh, beta_gr, gamma_fail, eta_init, eta_lb, eta_ub, mu;
-    int32_t iter_mu, q_tr /* 0 = Inf, 1, 2 */, oeta, osl, nsq, reserved;
+    int32_t iter_mu, q_tr /* 0 = Inf, 1, 2 */, oeta, olam, nsq, reserved;
 } scpb_gusto_desc;
 int32_t scpb_gusto_attach(scpb_ptr ptr, const scpb_gusto_desc *desc, const int32_t *Q_rowptr, const int32_t *Q_colind,
                           const double *Q_vals, const double *Q_const, const double *Q_weight);
@@ -236,6 +244,12 @@ int32_t scpb_debug_fp64_peak(scpb_handle h, double *tflops);
  * only when the environment variable SCPB_LEVEL_PROFILE is set: out[0..L) numeric factorisation, out[L..2L)
  * forward substitution, out[2L..3L) backward substitution (L = info[2] levels); cap >= 3L. */
 int32_t scpb_debug_level_profile(scpb_cone cone, int64_t *out, int32_t cap);
+
+/* Diagnostic: with the environment variable SCPB_IPM_TRACE=<seed index> set, the last scpb_cone_solve / scpb_*_solve
+ * launch records for that seed one row per interior-point iteration: {iteration, primal residual, dual residual, gap,
+ * primal cost, dual cost, previous primal step, previous dual step, static regularisation, sigma*mu}.  Copies up to
+ * cap_rows rows of 10 doubles into out; returns the number of rows copied (>= 0) or a negative error code. */
+int32_t scpb_debug_ipm_trace(scpb_cone cone, double *out, int32_t cap_rows);
 
 /* ---- test hook: CPU interpreter of the solver's index programs for ONE seed (no GPU needed) ----
  * Assembles M = [dI + G'W^-2 G, A'; A, -dI] from (Av, Gv, wm), factors it with the level-scheduled

@@ -20,6 +20,8 @@ struct scpb_cone_s {
     int *d_status = nullptr, *d_iters = nullptr;
     double *d_scal = nullptr;  // pobj, dobj, res[3]
     long long *d_prof = nullptr;
+    double *d_trace = nullptr;   // SCPB_IPM_TRACE diagnostic
+    int trace_rows = 0;
 };
 
 static const int *upload_ints(scpb_cone_s *c, const std::vector<int> &v)
@@ -148,6 +150,19 @@ int scpb_internal_cone_run(scpb_cone_s *c, const IpmOpts &o, const int *skip)
         c->D.sn = (c->sn_ok && c->D.vsmem && e && e[0] == '1') ? 1 : 0;
     }
     c->D.lvl_prof = (c->d_prof && getenv("SCPB_LEVEL_PROFILE")) ? 1 : 0;   // diagnostic: per-level cycle counters of CTA 0
+    c->D.trace = nullptr;
+    if (const char *e = getenv("SCPB_IPM_TRACE")) {   // diagnostic: per-iteration residual trace of one seed (last launch)
+        const int rows = o.maxit + 2;
+        if (c->trace_rows < rows) {
+            if (c->d_trace) cudaFree(c->d_trace);
+            c->d_trace = nullptr; c->trace_rows = 0;
+            if (cudaMalloc((void **)&c->d_trace, sizeof(double) * 10 * (size_t)rows) == cudaSuccess) c->trace_rows = rows;
+        }
+        if (c->d_trace) {
+            cudaMemsetAsync(c->d_trace, 0, sizeof(double) * 10 * (size_t)c->trace_rows, h->stream);
+            c->D.trace = c->d_trace; c->D.trace_seed = atoi(e);
+        }
+    }
 #define SCPB_LAUNCH_IPM(NT_, SN_)                                                                                        \
     {                                                                                                                    \
         SCPB_CUDA(h, cudaFuncSetAttribute(k_ipm_solve<NT_, SN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -278,6 +293,16 @@ int32_t scpb_debug_level_profile(scpb_cone c, int64_t *out, int32_t cap)
     return SCPB_OK;
 }
 
+int32_t scpb_debug_ipm_trace(scpb_cone c, double *out, int32_t cap_rows)
+{
+    if (!c || !out || cap_rows <= 0) return SCPB_ERR_ARG;
+    if (!c->d_trace) return SCPB_ERR_STATE;
+    const int rows = cap_rows < c->trace_rows ? cap_rows : c->trace_rows;
+    cudaStreamSynchronize(c->h->stream);
+    if (cudaMemcpy(out, c->d_trace, sizeof(double) * 10 * (size_t)rows, cudaMemcpyDeviceToHost) != cudaSuccess) return SCPB_ERR_CUDA;
+    return rows;
+}
+
 /* test hook: one assemble + factor + solve of the reduced KKT system ON THE DEVICE (the code path of k_ipm_solve,
  * supernodal or scalar by SCPB_SUPERNODAL) for B seeds; rhs / sol in natural node order [B][n+p]; wm[B][nwm] is W^-2
  * (LP rows: one weight; SOC: dense q x q blocks); bad[B] = 1 when the factorisation flagged lost inertia. */
@@ -347,6 +372,8 @@ int32_t scpb_cone_free(scpb_cone c)
     if (c->d_status) cudaFree(c->d_status);
     if (c->d_iters) cudaFree(c->d_iters);
     if (c->d_scal) cudaFree(c->d_scal);
+    if (c->d_prof) cudaFree(c->d_prof);
+    if (c->d_trace) cudaFree(c->d_trace);
     delete c;
     return SCPB_OK;
 }

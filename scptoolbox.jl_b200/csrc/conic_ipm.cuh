@@ -71,6 +71,8 @@ struct IpmData {  // group-blocked device arrays, all for B seeds
     int lvl_prof;      // 1: also record per-level cycles behind prof[12..]
     int sn;            // 1: supernodal factorisation / sweeps (conic_sn.cuh); 0: scalar level-scheduled programs
     long long *prof;   // [8] cycle counters of CTA 0: equilibrate, init, residuals, scaling+assemble, factor, solves, line search+update, total
+    double *trace;     // diagnostic (SCPB_IPM_TRACE=<seed>): per-iteration rows of 10 doubles for seed trace_seed, or nullptr
+    int trace_seed;
 };
 
 enum { IPM_OPTIMAL = 0, IPM_MAXIT = 1, IPM_NUMERICAL = 2, IPM_ALMOST = 3, IPM_PINF = 4, IPM_DINF = 5 };
@@ -1196,6 +1198,11 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
             const double relgap = gap / fmax(fmax(fabs(pcost), fabs(dcost)), 1.0);
             s_mu[q] = gap / deg;
             s_save[q] = 0;
+            if (D.trace && (int)g * G + q == D.trace_seed && !s_done[q]) {   // it, pres, dres, gap, pcost, dcost, last steps, delta, sigma*mu
+                double *tr_ = D.trace + 10 * (size_t)it;
+                tr_[0] = it; tr_[1] = pres; tr_[2] = dres; tr_[3] = gap; tr_[4] = pcost; tr_[5] = dcost;
+                tr_[6] = it ? s_alpha[q] : 0.0; tr_[7] = it ? s_alpha_d[q] : 0.0; tr_[8] = s_delta[q]; tr_[9] = it ? s_sigmu[q] : 0.0;
+            }
             if (!s_done[q]) {
                 s_iters[q] = it;
                 const double acc = fmax(fmax(pres, dres), fmin(gap, relgap));
@@ -1211,8 +1218,11 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
                 else if (pres <= O.feastol && dres <= O.feastol && (gap <= O.abstol || relgap <= O.reltol)) {
                     s_done[q] = 1; s_status[q] = IPM_OPTIMAL;
                 }
-                else if (it >= 2 && pinf <= O.feastol) { s_done[q] = 1; s_status[q] = IPM_PINF; s_save[q] = 1; }
-                else if (it >= 2 && dinf <= O.feastol) { s_done[q] = 1; s_status[q] = IPM_DINF; s_save[q] = 1; } else if (s_stall[q] >= 3 && s_best[q] <= 1e-6) { s_done[q] = 1; s_status[q] = IPM_NUMERICAL; }  // numerical floor
+                // (a certificate at 1e-8 relative is a proof whatever optimality tolerance was asked for: tighter requests
+                // would only let the diverging iterates run into the numerical floor first)
+                else if (it >= 2 && pinf <= fmax(O.feastol, 1e-8)) { s_done[q] = 1; s_status[q] = IPM_PINF; s_save[q] = 1; }
+                else if (it >= 2 && dinf <= fmax(O.feastol, 1e-8)) { s_done[q] = 1; s_status[q] = IPM_DINF; s_save[q] = 1; }
+                else if (s_stall[q] >= 3 && s_best[q] <= 1e-6) { s_done[q] = 1; s_status[q] = IPM_NUMERICAL; }  // numerical floor
                 else if (it == O.maxit) { s_done[q] = 1; s_status[q] = IPM_MAXIT; }
             }
         }

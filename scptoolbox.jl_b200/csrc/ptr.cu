@@ -33,8 +33,8 @@ struct PtrDev {
     ModelPar par;
     const double *eta = nullptr;   // SCvx / GuSTO: per-seed trust-region radius written to source oeta (scvx.jl:245)
     int oeta = 0;
-    const double *lam = nullptr;   // GuSTO: per-seed soft-penalty weight; sqrt(lambda) is written to source osl (gusto.jl:228)
-    int osl = 0;
+    const double *lam = nullptr;   // GuSTO: per-seed soft-penalty weight lambda, written to source olam (gusto.jl:228)
+    int olam = 0;
 };
 
 __device__ __forceinline__ size_t gaddr(int b, int G, long long E, long long e)
@@ -70,7 +70,7 @@ __global__ void k_linearize(const PtrDev d, const double *xd, const double *ud, 
         for (int j = 0; j < d.np; j++) d.src[gaddr(b, G, E, d.oph + j)] = (pp[j] - d.cp[j]) / d.Sp[j];
         d.src[gaddr(b, G, E, 0)] = 1.0;
         if (d.eta) d.src[gaddr(b, G, E, d.oeta)] = d.eta[b];
-        if (d.lam) d.src[gaddr(b, G, E, d.osl)] = sqrt(d.lam[b]);
+        if (d.lam) d.src[gaddr(b, G, E, d.olam)] = d.lam[b];
     }
 }
 
@@ -569,7 +569,7 @@ __global__ void k_gusto_step(const GustoDev d)
         for (int k = d.Q_rp[r]; k < d.Q_rp[r + 1]; k++) acc = fma(d.Q_v[k], gusto_var(d, x, u, p, d.Q_ci[k]), acc);
         J += r == 0 ? acc : d.Q_w[r - 1] * acc * acc;
     }
-    // soft trust-region cost as the subproblem measured it (J_tr = value(L_tr), gusto.jl:409)
+    // soft trust-region cost as the subproblem measured it (J_tr = value(L_tr), gusto.jl:409); the row is L_tr / lambda
     double J_tr = d.Q_c[d.nsq + 1];
     for (int k = d.Q_rp[d.nsq + 1]; k < d.Q_rp[d.nsq + 2]; k++) J_tr = fma(d.Q_v[k], d.xsol[gaddr(b, d.G, d.n, d.Q_ci[k])], J_tr);
     // trapezoid sums of the node terms
@@ -591,6 +591,7 @@ __global__ void k_gusto_step(const GustoDev d)
         viol |= nf[k];
     }
     const double eta = d.eta[b], lam = d.lam[b];
+    J_tr *= lam;
     const double J_aug = J + J_st + J_tr, L_aug = d.L_aug[b];
     // deviation from the reference (solution_deviation, scp.jl:909-931)
     const int q = d.q_exit;
@@ -1046,9 +1047,9 @@ int32_t scpb_gusto_attach(scpb_ptr s, const scpb_gusto_desc *desc, const int32_t
     if (!desc || !Q_rowptr || !Q_colind || !Q_vals || !Q_const || (desc->nsq > 0 && !Q_weight))
         return set_err(h, SCPB_ERR_ARG, "gusto_attach: null pointer");
     const scpb_ptr_desc &d = s->d;
-    if (desc->oeta <= 0 || desc->oeta >= d.nsrc || desc->osl <= 0 || desc->osl >= d.nsrc || desc->osl == desc->oeta ||
+    if (desc->oeta <= 0 || desc->oeta >= d.nsrc || desc->olam <= 0 || desc->olam >= d.nsrc || desc->olam == desc->oeta ||
         desc->nsq < 0 || desc->q_tr < 0 || desc->q_tr > 2)
-        return set_err(h, SCPB_ERR_ARG, "gusto_attach: bad descriptor (oeta=%d, osl=%d, nsq=%d, q_tr=%d)", desc->oeta, desc->osl,
+        return set_err(h, SCPB_ERR_ARG, "gusto_attach: bad descriptor (oeta=%d, olam=%d, nsq=%d, q_tr=%d)", desc->oeta, desc->olam,
                        desc->nsq, desc->q_tr);
     if (s->scvx) return set_err(h, SCPB_ERR_STATE, "gusto_attach: the problem already carries the SCvx extras");
     const ConeSymbolic *S = scpb_internal_cone_sym(s->cone);
@@ -1119,7 +1120,7 @@ int32_t scpb_gusto_solve(scpb_ptr s, int32_t B, const double *xd0, const double 
     pd.B = B; pd.G = G; pd.N = d.N; pd.nx = d.nx; pd.nu = d.nu; pd.np = d.np; pd.ns = d.ns;
     pd.nsrc = d.nsrc; pd.oC = d.oC; pd.oD = d.oD; pd.oG = d.oG; pd.ors = d.ors; pd.oxh = d.oxh; pd.ouh = d.ouh; pd.oph = d.oph;
     pd.t_grid = s->tgrid; pd.Sx = Sx; pd.cx = cx; pd.Su = Su; pd.cu = cu; pd.Sp = Sp; pd.cp = cp;
-    pd.src = s->src; pd.par = s->par; pd.eta = s->eta; pd.oeta = v.oeta; pd.lam = s->lam; pd.osl = v.osl;
+    pd.src = s->src; pd.par = s->par; pd.eta = s->eta; pd.oeta = v.oeta; pd.lam = s->lam; pd.olam = v.olam;
     AsmDev ad{};
     ad.B = B; ad.G = G; ad.nsrc = d.nsrc; ad.nval = d.nval; ad.nnzA = (int)S->A_ci.size(); ad.nnzG = (int)S->G_ci.size();
     ad.n = S->n; ad.p = S->p; ad.m = S->m; ad.W_rp = s->W_rp; ad.W_ci = s->W_ci; ad.W_v = s->W_v; ad.src = s->src;

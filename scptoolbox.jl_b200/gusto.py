@@ -12,8 +12,10 @@ Subproblem (Subproblem ctor gusto.jl:218-287; add_cost! :534-553; dynamics and b
   * soft trust region (gusto.jl:1056-1164): |x^_k - x^_ref,k|_q <= dx_lq[k], |p^ - p^_ref|_q <= dp_lq,
     dx_lq[k] + dp_lq - (eta + tr[k]) <= 0 and the same soft penalty on tr[k].
 The quadratic terms reach the linear-objective cone solver as one rotated second-order cone per node and cost group,
-q >= sum_i (sqrt(lambda) v_i)^2 (JuMP lowers ECOS' quadratic objectives the same way); sqrt(lambda) and eta are PER-SEED
-device sources, so one compiled template serves every seed and every iteration.
+q >= sum_i v_i^2 with the cost lambda q (JuMP lowers ECOS' quadratic objectives to the same cone; keeping lambda out of
+the cone keeps its entries O(1): with sqrt(lambda) v inside, q reaches 1e4..1e6 in the first iterations and every such
+cone sits at relative distance ~4/q from its boundary, which wrecks the Nesterov-Todd scaling).  lambda and eta are
+PER-SEED device sources, so one compiled template serves every seed and every iteration.
 The loop body on the device (csrc/ptr.cu, scpb_gusto_*): nonconvex costs J, J_st of the new iterate, the convexification
 error rho (cost error + dynamics error, update_trust_region! :1245-1293), the trust-region / penalty update rule
 (update_rule! :1310-1427 incl. the mu-shrink of :268) and the stopping rule (:1203-1231).
@@ -85,7 +87,7 @@ class GuSTOProblem(SCPProblem):
         x = prg.new_variable((nx, N), "x", sc.Sx, sc.cx, stage="col")
         u = prg.new_variable((nu, N), "u", sc.Su, sc.cu, stage="col")
         p = prg.new_variable(np_, "p", sc.Sp, sc.cp, stage=(traj.p_stage(N) if traj.p_stage else None))
-        sl = Lin.src(sm.osl)                     # sqrt(lambda), per seed
+        lam = Lin.src(sm.olam)                   # lambda, per seed
         eta = Expr(None, Lin.src(sm.oeta))       # trust-region radius, per seed
         # ---- original cost: terminal + trapz of u' S u (S constant, PSD) ----
         S = np.asarray(traj.S(t[0], 1, None), dtype=float)
@@ -122,9 +124,9 @@ class GuSTOProblem(SCPProblem):
                 for i in range(ns):
                     prg.nonpos([-uu[i]])
                     prg.nonpos([lhs[i] + Expr(None, rs[i]) + uu[i] - vv[i]], "soft_path")
-                    vs.append(vv[i].scale_lin(sl))
+                    vs.append(vv[i])
             L_st_nodes.append(prg.sumsq(vs, "state_penalty", stage=k) if vs else Expr())
-        L_st = trapz(L_st_nodes, t)
+        L_st = trapz(L_st_nodes, t).scale_lin(lam)
         # ---- soft trust region ----
         q = pars.q_tr
         cone = {1: prg.l1, 2: prg.soc, np.inf: prg.linf}[q]
@@ -144,8 +146,9 @@ class GuSTOProblem(SCPProblem):
             prg.nonpos([dx_lq[k] + dp_lq[0] - (tr[k] + eta)], "trust_region_bound")
             prg.nonpos([-tu[k]])
             prg.nonpos([tr[k] + tu[k] - tv[k]])
-            L_tr_nodes.append(prg.sumsq([tv[k].scale_lin(sl)], "trust_penalty", stage=k))
-        L_tr = trapz(L_tr_nodes, t)
+            L_tr_nodes.append(prg.sumsq([tv[k]], "trust_penalty", stage=k))
+        L_tr1 = trapz(L_tr_nodes, t)               # L_tr / lambda
+        L_tr = L_tr1.scale_lin(lam)
         prg.add_cost(L); prg.add_cost(L_st); prg.add_cost(L_tr)
         # ---- dynamics, un-relaxed ----
         from .problem import dltv_masks
@@ -180,7 +183,7 @@ class GuSTOProblem(SCPProblem):
                     rows.append(r); wts.append(coef.t.get(0, 0.0))
             else:
                 aff_t[v] = coef
-        qrows = [Expr(aff_t, Lx.c)] + rows + [Expr.lift(L_tr)]
+        qrows = [Expr(aff_t, Lx.c)] + rows + [Expr.lift(L_tr1)]
         self.Q = _rows_matrix(qrows, self.cp["n"])
         self.Q_w = np.ascontiguousarray(wts if wts else [0.0], dtype=np.float64)
         d = lib.GustoDesc()
@@ -189,7 +192,7 @@ class GuSTOProblem(SCPProblem):
             setattr(d, k_, float(getattr(pars, k_)))
         d.iter_mu = int(pars.iter_mu)
         d.q_tr = {np.inf: 0, 1: 1, 2: 2}[pars.q_tr]
-        d.oeta, d.osl, d.nsq = sm.oeta, sm.osl, len(rows)
+        d.oeta, d.olam, d.nsq = sm.oeta, sm.olam, len(rows)
         self.gdesc = d
         qm = self.Q
         h = self.handle

@@ -42,6 +42,7 @@ SIGNATURES = {
     "scpb_propagate": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _dp, _dp, _dp, _dp]),
     "scpb_cone_setup": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _ip, _ip, _ip, _ip, C.c_int32,
                                     C.c_int32, _ip, _ip, C.POINTER(C.c_void_p)]),
+    "scpb_order_rcm": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _ip, _ip, _ip, _ip, C.c_int32, C.c_int32, _ip, _ip]),
     "scpb_cone_info": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64)]),
     "scpb_cone_free": (C.c_int32, [C.c_void_p]),
     "scpb_cone_solve": (C.c_int32, [C.c_void_p, C.c_int32, _dp, _dp, _dp, _dp, _dp, C.c_void_p,
@@ -56,6 +57,7 @@ SIGNATURES = {
                                      _dp, _dp, _ip, _dp, _dp, _dp]),
     "scpb_scvx_solve": (C.c_int32, [C.c_void_p, C.c_int32, _dp, _dp, _dp, C.c_void_p, _dp, _dp, _dp, _ip, _ip,
                                     _dp, _dp, _ip, _dp, _dp]),
+    "scpb_debug_ipm_trace": (C.c_int32, [C.c_void_p, _dp, C.c_int32]),
     "scpb_debug_level_profile": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
     "scpb_debug_kkt_solve": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _ip, _ip, _ip, _ip, C.c_int32, C.c_int32,
                                          _ip, _ip, _dp, _dp, _dp, C.c_double, C.c_double, _dp, _dp, C.POINTER(C.c_int64)]),
@@ -92,7 +94,7 @@ class ScvxDesc(C.Structure):        # scpb_scvx_desc (include/scpb.h)
 class GustoDesc(C.Structure):       # scpb_gusto_desc (include/scpb.h)
     _fields_ = [(k, C.c_double) for k in ("lam_init", "lam_max", "rho_0", "rho_1", "beta_sh", "beta_gr", "gamma_fail",
                                            "eta_init", "eta_lb", "eta_ub", "mu")] + \
-               [(k, C.c_int32) for k in ("iter_mu", "q_tr", "oeta", "osl", "nsq", "reserved")]
+               [(k, C.c_int32) for k in ("iter_mu", "q_tr", "oeta", "olam", "nsq", "reserved")]
 
 
 CONE_STATUS = {0: "OPTIMAL", 1: "ITERATION_LIMIT", 2: "NUMERICAL_ERROR", 3: "ALMOST_OPTIMAL", 4: "INFEASIBLE",
@@ -284,6 +286,15 @@ class ConeProblem:
         d["cycles"]["factor_count"] = fc & 0xffffffff      # interior-point iterations of CTA 0
         d["cycles"]["factor_retries"] = fc >> 32           # factorisations repeated with a larger static regularisation
         return d
+
+    def ipm_trace(self, rows=256):
+        """rows of the SCPB_IPM_TRACE diagnostic (see include/scpb.h); empty when tracing is off"""
+        buf = np.zeros((rows, 10))
+        n = self.lib.scpb_debug_ipm_trace(self.c, buf.ctypes.data_as(_dp), rows)
+        if n <= 0:
+            return buf[:0]
+        buf = buf[:n]
+        return buf[(buf[:, 0] > 0) | (np.arange(n) == 0)]
 
     def level_profile(self):
         """(3, levels) cycle counters [factor, forward, backward] of CTA 0 (needs SCPB_LEVEL_PROFILE=1)."""

@@ -159,7 +159,7 @@ class SourceMap:
         self.ouh = o; o += N * nu
         self.oph = o; o += np_
         self.oeta = o; o += 1          # SCvx / GuSTO trust-region radius (scvx.jl:245, gusto.jl:229); unused by PTR
-        self.osl = o; o += 1           # GuSTO: sqrt(lambda), the soft-penalty weight (gusto.jl:228)
+        self.olam = o; o += 1          # GuSTO: lambda, the soft-penalty weight (gusto.jl:228)
         self.nsrc = o
         self.N, self.nx, self.nu, self.np, self.ns, self.nf, self.ng = N, nx, nu, np_, ns, nf, ng
 

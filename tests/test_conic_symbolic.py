@@ -141,3 +141,47 @@ def test_supernodal_program_on_the_product_template(pkg, monkeypatch):
     scale = max(1.0, np.abs(s1).max())
     assert np.abs(s1 - s2).max() <= 1e-8 * scale
     assert i2["sn_levels"] * 3 <= i1["levels"] and i2["max_rows"] <= 32 and i2["max_width"] <= 10, (i1, i2)
+
+
+def test_native_rcm_order(pkg):
+    """scpb_order_rcm (csrc/ordering.cu; used by the MathOptInterface shim, julia/SCPToolboxB200.jl): a permutation of the
+    KKT nodes with every equality row behind its variables, and a fill within 10 % of the scipy heuristic of
+    ordering.rcm_order (and not above the emission order's) on the rocket PTR subproblem (SOC cones)."""
+    import ctypes as C
+    from oracle import problems, ptr as optr
+    N = 12
+    pbo = problems.RocketProblem(N)
+    xd, ud, p = problems.test_trajectory(pbo, 1, N, seed=3)
+    P = optr.PTR(pbo, optr.Parameters(N=N, Nsub=15, iter_max=5, wvc=1e3, wtr=0.1, eps_abs=1e-5, eps_rel=1e-4, feas_tol=1e-3))
+    prg, _ = P.build(P.make_solution(xd[0], ud[0], p[0]))
+    cp = prg.compile()
+    A = cp["A"].tocsr(); G = cp["G"].tocsr(); A.sort_indices(); G.sort_indices()
+    n, pp, m = A.shape[1], A.shape[0], G.shape[0]
+    L = pkg.lib.load()
+    perm = np.zeros(n + pp, dtype=np.int32)
+    keep = [np.ascontiguousarray(x, dtype=np.int32) for x in (A.indptr, A.indices, G.indptr, G.indices, cp["q"])]
+    ptr = [k.ctypes.data_as(pkg.lib._ip) for k in keep]
+    rc = L.scpb_order_rcm(n, pp, m, ptr[0], ptr[1], ptr[2], ptr[3], cp["l"], len(cp["q"]), ptr[4], perm.ctypes.data_as(pkg.lib._ip))
+    assert rc == 0
+    assert sorted(perm.tolist()) == list(range(n + pp))
+    pos = np.empty(n + pp, dtype=int); pos[perm] = np.arange(n + pp)
+    for r in range(pp):
+        cols = A.indices[A.indptr[r]:A.indptr[r + 1]]
+        assert pos[n + r] > pos[cols].max()
+    assert L.scpb_order_rcm(n, pp, m, ptr[0], ptr[1], ptr[2], ptr[3], cp["l"] + 1, len(cp["q"]), ptr[4], perm.ctypes.data_as(pkg.lib._ip)) != 0
+    rng = np.random.default_rng(0)
+    nwm = cp["l"] + sum(int(q) ** 2 for q in cp["q"])
+    wm = np.zeros(nwm); wm[:cp["l"]] = rng.uniform(0.5, 2.0, cp["l"])
+    o = cp["l"]
+    for q in cp["q"]:
+        wm[o:o + q * q] = np.eye(q).ravel(); o += q * q
+    rhs = rng.standard_normal(n + pp)
+    fill = {}
+    for name, pr in (("native", perm), ("scipy", pkg.ordering.rcm_order(A, G)), ("natural", np.arange(n + pp, dtype=np.int32))):
+        sol, info = pkg.lib.debug_kkt_solve(A, G, cp["l"], cp["q"], pr, A.data, G.data, wm, 1e-9, rhs)
+        fill[name] = info["nnzL"]
+        K = sp.bmat([[1e-9 * sp.eye(n) + G.T @ sp.block_diag([sp.diags(wm[:cp["l"]])] + [sp.eye(int(q)) for q in cp["q"]]) @ G, A.T],
+                     [A, -1e-9 * sp.eye(pp)]]).tocsc()
+        assert np.abs(K @ sol - rhs).max() <= 1e-6 * np.abs(rhs).max()
+    print("nnzL", fill)
+    assert fill["native"] <= 1.1 * fill["scipy"] and fill["native"] <= fill["natural"]

@@ -372,7 +372,7 @@ def test_gusto_template_matches_oracle_subproblem(pkg, monkeypatch):
     cp, sm = pbm.cp, pbm.sm
     assert np.abs(pbm.scale.Sx - P.scale.Sx).max() < 1e-12 and np.abs(pbm.scale.Su - P.scale.Su).max() < 1e-9
     src = _sources(sm, pbo, P, ref)
-    src[sm.oeta] = eta; src[sm.osl] = np.sqrt(lam)
+    src[sm.oeta] = eta; src[sm.olam] = lam
     vals = pbm.W @ src
     n, p_, m = cp["n"], cp["p"], cp["m"]
     assert (n, p_, m, cp["l"]) == (ocp["c"].size, ocp["A"].shape[0], ocp["G"].shape[0], ocp["l"])
@@ -405,5 +405,5 @@ def test_gusto_template_matches_oracle_subproblem(pkg, monkeypatch):
     J = rows[0] + (pbm.Q_w[:nsq] * rows[1:] ** 2).sum()
     assert abs(J - P.original_cost(xs, us, ps)) <= 1e-12 * max(1.0, abs(J))
     r = nsq + 1
-    Ltr = c0[r] + v[rp[r]:rp[r + 1]] @ r1["z"][ci[rp[r]:rp[r + 1]]]
+    Ltr = lam * (c0[r] + v[rp[r]:rp[r + 1]] @ r1["z"][ci[rp[r]:rp[r + 1]]])
     assert abs(Ltr - conic.Aff.lift(hnd["L_tr"]).value(z2)) <= 1e-7 * max(1.0, abs(Ltr))
