@@ -9,6 +9,8 @@ that does not converge (measured, profiles/r2_parity_vs_tolerance.txt) -- so a 1
 subproblem solutions tighter than that, on both sides.  The auxiliary gimbal-rate pair (x[7], u[2]) only enters two-sided
 rate constraints (definition.jl:544,740-743), is not determined by the LP (two exact solvers differ by 0.4 of its range
 on the very first subproblem) and is reported, not asserted."""
+import os
+
 import numpy as np
 import pytest
 
@@ -259,8 +261,19 @@ def test_bench_configuration_parity(pkg, handle):
     X0, U0, P0 = bench.make_seeds(g, sc.Sx, sc.Su, nb, 0, sc.cx, sc.cu)
     sol = pkg.ptr.solve(pbm, (X0, U0, P0), **TOL)
     pbm.close()
-    with mp.get_context("fork").Pool(min(nb, 8)) as pool:
-        refs = pool.map(_oracle_ptr_worker, [(N, Nsub, pbo.hs, X0[b], U0[b], P0[b], OTOL) for b in range(nb)], chunksize=1)
+    # the oracle side (its interior point at 1e-11, ~3 CPU-minutes per seed at N = 100) is a committed fixture
+    # (scripts/make_golden_bench.py); it is recomputed here only when the fixture's seeds are not this test's seeds
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_ptr_bench_seeds.npz")
+    refs = None
+    if os.path.exists(gold):
+        gd = np.load(gold)
+        if (gd["X0"].shape == X0.shape and np.allclose(gd["X0"], X0, rtol=0, atol=1e-12)
+                and np.allclose(gd["U0"], U0, rtol=0, atol=1e-12) and np.allclose(gd["P0"], P0, rtol=0, atol=1e-12) and float(gd["tol"]) == OTOL):
+            refs = [(str(gd["status"][b]), int(gd["iterations"][b]), gd["xd"][b], gd["ud"][b], gd["p"][b],
+                     float(gd["J_aug"][b]), bool(gd["feas"][b])) for b in range(nb)]
+    if refs is None:
+        with mp.get_context("fork").Pool(min(nb, 8)) as pool:
+            refs = pool.map(_oracle_ptr_worker, [(N, Nsub, pbo.hs, X0[b], U0[b], P0[b], OTOL) for b in range(nb)], chunksize=1)
     for b in range(nb):
         st, its, xd, ud, p, J, feas = refs[b]
         ex7 = np.abs((sol.xd[b][:, :7] - xd[:, :7]) / sc.Sx[:7]).max()
