@@ -141,11 +141,13 @@ int32_t scpb_cone_setup(scpb_handle h, int32_t n, int32_t p, int32_t m,
                         const int32_t *G_rowptr, const int32_t *G_colind,
                         int32_t l, int32_t nsoc, const int32_t *soc_dims, const int32_t *perm,
                         scpb_cone *out);
-/* info[20] = {n+p, nnz(L), elimination-tree levels, factor ops, assembly ops, |W^-2|, group, capacity,
+/* info[24] = {n+p, nnz(L), elimination-tree levels, factor ops, assembly ops, |W^-2|, group, capacity,
  *             8 SM-cycle counters of the last launch (CTA 0): equilibrate, start point, residuals,
  *             scaling+assembly, factorisation, KKT solves, line search+update, total;
  *             forward-substitution cycles, backward-substitution cycles, number of LDL' solves,
- *             number of factorisations (= interior-point iterations of CTA 0)} */
+ *             number of factorisations (= interior-point iterations of CTA 0);
+ *             hybrid program: cut the last launch ran (0 = it ran the scalar / supernodal variant), scalar levels
+ *             incl. the bridge level, top supernodal levels, cut it was built with (0 = not built)} */
 int32_t scpb_cone_info(scpb_cone c, int64_t *info);
 int32_t scpb_cone_free(scpb_cone c);
 /* host arrays, seed-major: Avals[B][nnzA], Gvals[B][nnzG], c[B][n], b[B][p], h[B][m];
@@ -268,6 +270,15 @@ int32_t scpb_debug_kkt_solve_sn(int32_t n, int32_t p, int32_t m, const int32_t *
                              const int32_t *G_rowptr, const int32_t *G_colind, int32_t l, int32_t nsoc,
                              const int32_t *soc_dims, const int32_t *perm, const double *Avals,
                              const double *Gvals, const double *wm, double delta, double delta_dyn,
+                             const double *rhs, double *sol, int64_t *info);
+/* The same hook for the hybrid program (scalar level-scheduled programs below supernodal level `cut`, register-resident
+ * panels addressed in place on the scalar storage above it; SCPB_HYBRID selects it in the solver kernel): info[8] =
+ * {scalar levels incl. the bridge level, top supernodal levels, top supernodes, top columns, bridge factor items, bridge
+ * factor ops, bridge forward items, scalar levels of the plain program}.  SCPB_ERR_UNSUPPORTED when the split is empty. */
+int32_t scpb_debug_kkt_solve_hy(int32_t n, int32_t p, int32_t m, const int32_t *A_rowptr, const int32_t *A_colind,
+                             const int32_t *G_rowptr, const int32_t *G_colind, int32_t l, int32_t nsoc,
+                             const int32_t *soc_dims, const int32_t *perm, const double *Avals,
+                             const double *Gvals, const double *wm, double delta, double delta_dyn, int32_t cut,
                              const double *rhs, double *sol, int64_t *info);
 /* The same single KKT solve executed ON THE DEVICE by the code path of the solver kernel (supernodal panels, or the
  * scalar programs with SCPB_SUPERNODAL=0) for B seeds: Avals[B][nnzA], Gvals[B][nnzG], wm[B][|W^-2|] (LP rows one

@@ -5,10 +5,17 @@
 #define CONIC_IPM_IMPL
 #include "conic_ipm.cuh"
 
+#ifndef SCPB_HYBRID_DEFAULT_CUT
+#define SCPB_HYBRID_DEFAULT_CUT 0   // hybrid program off unless SCPB_HYBRID=<cut> is set (see scpb_cone_setup)
+#endif
+
 struct scpb_cone_s {
     scpb_handle_s *h = nullptr;
     ConeSymbolic S;
     IpmProgram P{};
+    IpmProgram P_hy{};    // hybrid program (scalar arrays replaced, top supernodes in .hy); valid when hy_ok
+    bool hy_ok = false;
+    int hy_used = 0;      // cut of the hybrid program the last launch ran (0: it ran another variant)
     std::vector<void *> dev_ints;
     // data buffers (grow-only), sized for (ngroups*G) seeds
     int capB = 0, capG = 0, lanes = 0;
@@ -149,7 +156,13 @@ int scpb_internal_cone_run(scpb_cone_s *c, const IpmOpts &o, const int *skip)
         const char *e = getenv("SCPB_SUPERNODAL");
         c->D.sn = (c->sn_ok && c->D.vsmem && e && e[0] == '1') ? 1 : 0;
     }
+    // hybrid program (built at setup, SCPB_HYBRID): scalar programs below the cut, in-place panels above; needs the
+    // shared-memory substitution vector like the supernodal variant
+    const bool hy = c->hy_ok && c->D.vsmem && !c->D.sn;
+    const IpmProgram &Pl = hy ? c->P_hy : c->P;
+    c->hy_used = hy ? c->S.hy_cut : 0;
     c->D.lvl_prof = (c->d_prof && getenv("SCPB_LEVEL_PROFILE")) ? 1 : 0;   // diagnostic: per-level cycle counters of CTA 0
+    if (hy && c->S.hy_nlevels + c->S.hy_ntl > c->S.nlevels) c->D.lvl_prof = 0;   // the counters are sized by the scalar levels
     c->D.trace = nullptr;
     if (const char *e = getenv("SCPB_IPM_TRACE")) {   // diagnostic: per-iteration residual trace of one seed (last launch)
         const int rows = o.maxit + 2;
@@ -166,10 +179,10 @@ int scpb_internal_cone_run(scpb_cone_s *c, const IpmOpts &o, const int *skip)
 #define SCPB_LAUNCH_IPM(NT_, SN_)                                                                                        \
     {                                                                                                                    \
         SCPB_CUDA(h, cudaFuncSetAttribute(k_ipm_solve<NT_, SN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_ipm_solve<NT_, SN_><<<ng, NT_, smem, h->stream>>>(c->P, c->D, o);                                              \
+        k_ipm_solve<NT_, SN_><<<ng, NT_, smem, h->stream>>>(Pl, c->D, o);                                                \
     }
-    if (o.threads >= 1024) { if (c->D.sn) SCPB_LAUNCH_IPM(1024, 1) else SCPB_LAUNCH_IPM(1024, 0) }
-    else { if (c->D.sn) SCPB_LAUNCH_IPM(512, 1) else SCPB_LAUNCH_IPM(512, 0) }
+    if (o.threads >= 1024) { if (c->D.sn) SCPB_LAUNCH_IPM(1024, 1) else if (hy) SCPB_LAUNCH_IPM(1024, 2) else SCPB_LAUNCH_IPM(1024, 0) }
+    else { if (c->D.sn) SCPB_LAUNCH_IPM(512, 1) else if (hy) SCPB_LAUNCH_IPM(512, 2) else SCPB_LAUNCH_IPM(512, 0) }
 #undef SCPB_LAUNCH_IPM
     h->launches++;
     SCPB_CUDA(h, cudaGetLastError());
@@ -194,6 +207,7 @@ IpmOpts scpb_internal_make_opts(const scpb_cone_opts *o)
     r.threads = (o && o->threads > 0) ? o->threads : 1024;
     r.nref_aff = 0;
     r.reftol = 1e-13;
+    if (const char *e = getenv("SCPB_REFTOL")) { const double v = atof(e); if (v > 0) r.reftol = v; }   // experiments
     return r;
 }
 
@@ -259,6 +273,25 @@ int32_t scpb_cone_setup(scpb_handle h, int32_t n, int32_t p, int32_t m, const in
     P.fwp_lvl = upload_ints(c, S.fwp_lvl); P.bwp_lvl = upload_ints(c, S.bwp_lvl);
     P.fwp_R = upload_ints(c, S.fwp_R); P.bwp_R = upload_ints(c, S.bwp_R);
     P.Lr_pc = (const int2 *)upload_ints(c, S.Lr_pc); P.ft_op = (const int2 *)upload_ints(c, S.ft_op);
+    // hybrid program: SCPB_HYBRID=<cut> (supernodal level at which the in-place panels take over; 0 = off)
+    {
+        const char *e = getenv("SCPB_HYBRID");
+        const int cut = e ? atoi(e) : SCPB_HYBRID_DEFAULT_CUT;
+        if (cut > 0 && cone_symbolic_build_hybrid(c->S, cut)) {
+            IpmProgram &H = c->P_hy;
+            H = P;
+            H.nlevels = S.hy_nlevels;
+            H.fa_item = (const int4 *)upload_ints(c, S.hy_fa_item); H.fb_item = (const int4 *)upload_ints(c, S.hy_fb_item);
+            H.fa_lvl = upload_ints(c, S.hy_fa_lvl); H.fa_R = upload_ints(c, S.hy_fa_R); H.fb_lvl = upload_ints(c, S.hy_fb_lvl);
+            H.ft_op = (const int2 *)upload_ints(c, S.hy_ft_op);
+            H.fwp_item = (const int4 *)upload_ints(c, S.hy_fwp_item); H.bwp_item = (const int4 *)upload_ints(c, S.hy_bwp_item);
+            H.fwp_lvl = upload_ints(c, S.hy_fwp_lvl); H.bwp_lvl = upload_ints(c, S.hy_bwp_lvl);
+            H.fwp_R = upload_ints(c, S.hy_fwp_R); H.bwp_R = upload_ints(c, S.hy_bwp_R);
+            H.hy.desc = (const int4 *)upload_ints(c, S.hy_desc); H.hy.tl_ptr = upload_ints(c, S.hy_tl_ptr);
+            H.hy.upd_dst = upload_ints(c, S.hy_upd_dst); H.hy.rows = P.sn.rows; H.hy.ntl = S.hy_ntl;
+            c->hy_ok = true;
+        }
+    }
     for (void *d : c->dev_ints)
         if (!d) {
             scpb_cone_free(c);
@@ -273,6 +306,7 @@ int32_t scpb_cone_info(scpb_cone c, int64_t *info)
     if (!c || !info) return SCPB_ERR_ARG;
     info[0] = c->S.nk; info[1] = c->S.nnzL; info[2] = c->S.nlevels; info[3] = c->S.factor_ops;
     info[4] = (int64_t)c->S.as_a.size(); info[5] = c->S.nwm; info[6] = c->capG; info[7] = c->capB;
+    info[20] = c->hy_used; info[21] = c->hy_ok ? c->S.hy_nlevels : 0; info[22] = c->hy_ok ? c->S.hy_ntl : 0; info[23] = c->hy_ok ? c->S.hy_cut : 0;
     if (c->d_prof) {   // info[8..15]: cycle counters of the last launch (CTA 0)
         long long hp[12];
         if (cudaMemcpy(hp, c->d_prof, sizeof hp, cudaMemcpyDeviceToHost) == cudaSuccess)

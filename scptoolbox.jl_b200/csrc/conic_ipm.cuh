@@ -31,6 +31,8 @@ struct IpmProgram {  // device copies of ConeSymbolic index arrays
     const int4 *fw_item, *bw_item;
     const int4 *fwp_item, *bwp_item, *fa_item, *fb_item;
     SnProgram sn;            // supernodal program (used when IpmData.sn is set)
+    HyProgram hy;            // top supernodes of the hybrid program (kernel variant SN = 2; the scalar program arrays of
+                             // this struct are then the hybrid ones and nlevels counts the low levels + the bridge level)
     int ysize;               // doubles per seed of the Y array: max(nnzL + nk, supernodal panels)
     const int *sn_pos;       // target id -> panel offset
     const int *fa_lvl, *fa_R, *fb_lvl;
@@ -98,6 +100,7 @@ struct Ctx {
     int sn;                             // supernodal mode
     double *Ypanels;                    // supernodal mode: this group's panels (the Y array, one seed after the other)
     const struct SnArgs *s_sn;          // supernodal mode: argument block of the panel kernels, in shared memory
+    const struct HyArgs *s_hy;          // hybrid mode: argument block of the top-panel phases, in shared memory
     size_t ysize;                       // doubles per seed of the Y array
     const int *s_done;                  // shared: per-seed "finished" flags (finished seeds skip the per-seed panel work)
     double *s_delta;                    // shared: per-seed static regularisation
@@ -465,12 +468,74 @@ __device__ __forceinline__ void kkt_ldl_solve_sn(const IpmProgram &P, Ctx &c, co
     c.t_fw += t1_ - t0_; c.t_bw += t2_ - t1_; c.t_ldl_n += 1;
 }
 
+// ---- hybrid program: the top supernodes (conic_sn.cuh, hy_*), one warp per (supernode, seed) item, one barrier per
+// top level.  Separate noinline functions whose arguments come from shared memory, like the supernodal ones.
+struct HyArgs {
+    HyProgram hy;
+    double *Y, *Ls, *invD;          // group-blocked, offset to this CTA's group
+    const int *s_done;              // shared: finished seeds are skipped
+    const double *s_delta;          // shared: per-seed static regularisation
+    int *s_bad;                     // shared: per-seed "inertia lost" flags
+    double rho_min, bad_abs;
+    int o_vs, nnzL, G, nwarps;
+    long long *lprof;               // [3][ntl] cycle counters behind the scalar ones (CTA 0, thread 0) or nullptr
+};
+
+template <class F>
+__device__ __forceinline__ void hy_for_items(const HyArgs &a, int tl, int tid, F &&f)
+{
+    const int i0 = a.hy.tl_ptr[tl], nit = (a.hy.tl_ptr[tl + 1] - i0) * a.G;
+    const int gsh = 31 - __clz(a.G);
+    int it = tid >> 5;
+    int4 d0 = make_int4(0, 0, 0, 0), d1 = d0;
+    if (it < nit) { const int q = 2 * (i0 + (it >> gsh)); d0 = a.hy.desc[q]; d1 = a.hy.desc[q + 1]; }
+    while (it < nit) {
+        const int sgi = it & (a.G - 1);
+        const int4 c0 = d0, c1 = d1;
+        const int nx = it + a.nwarps;
+        if (nx < nit) { const int q = 2 * (i0 + (nx >> gsh)); d0 = a.hy.desc[q]; d1 = a.hy.desc[q + 1]; }
+        if (!a.s_done[sgi]) f(c0, c1, sgi);    // warp-uniform
+        it = nx;
+    }
+}
+
+__device__ __noinline__ void kkt_factor_top(const HyArgs *ap, int tid)
+{
+    const HyArgs a = *ap;
+    long long *lp = (tid == 0) ? a.lprof : nullptr;
+    long long tl_ = lp ? clock64() : 0;
+    for (int tl = 0; tl < a.hy.ntl; tl++) {
+        hy_for_items(a, tl, tid, [&](const int4 d0, const int4 d1, int sgi) {
+            const double dl = a.s_delta[sgi];
+            hy_factor_panel<32>(d0, d1, a.hy.upd_dst, a.Y, a.Ls, a.invD, a.nnzL, a.G, sgi, 0.5 * dl, fmax(dl, a.rho_min), a.bad_abs,
+                                &a.s_bad[sgi]); });
+        __syncthreads();
+        if (lp) { const long long tn = clock64(); lp[tl] += tn - tl_; tl_ = tn; }
+    }
+}
+
+template <int DIR>
+__device__ __noinline__ void kkt_sweep_top(const HyArgs *ap, int tid)
+{
+    const HyArgs a = *ap;
+    double *vs = (double *)(ipm_smem + a.o_vs);
+    long long *lp = (tid == 0 && a.lprof) ? a.lprof + (DIR > 0 ? 1 : 2) * a.hy.ntl : nullptr;
+    long long tl_ = lp ? clock64() : 0;
+    for (int st = 0; st < a.hy.ntl; st++) {
+        const int tl = DIR > 0 ? st : a.hy.ntl - 1 - st;
+        if (DIR > 0) hy_for_items(a, tl, tid, [&](const int4 d0, const int4 d1, int sgi) { hy_forward_panel<32>(d0, d1, a.hy.rows, a.Ls, vs, a.G, sgi); });
+        else hy_for_items(a, tl, tid, [&](const int4 d0, const int4 d1, int sgi) { hy_backward_panel<32>(d0, d1, a.hy.rows, a.Ls, vs, a.G, sgi); });
+        __syncthreads();
+        if (lp) { const long long tn = clock64(); lp[tl] += tn - tl_; tl_ = tn; }
+    }
+}
+
 // SN (compile time): the supernodal kernels are instantiated only in the kernel variant that uses them -- their mere
 // presence as call sites costs the default (scalar) variant ~3 KB of spill traffic per thread (ptxas -v)
 template <int SN>
 __device__ __forceinline__ void kkt_factor(const IpmProgram &P, Ctx &c, double *Y, double *Ls, double *invD)
 {
-    if constexpr (SN) { kkt_factor_sn(c.s_sn, c.tid); return; }
+    if constexpr (SN == 1) { kkt_factor_sn(c.s_sn, c.tid); return; }
     FactorArgs a;
     a.fa_item = P.fa_item; a.fb_item = P.fb_item; a.ft_op = P.ft_op;
     a.Y = Y; a.Ls = Ls; a.Lrow = c.Lrow; a.invD = invD;
@@ -478,6 +543,7 @@ __device__ __forceinline__ void kkt_factor(const IpmProgram &P, Ctx &c, double *
     a.nl = P.nlevels; a.nnzLd = P.nnzL; a.G = c.G; a.sg = c.sg; a.slot = c.slot; a.nslots = c.nslots;
     a.lprof = c.lprof;
     kkt_factor_levels(a);
+    if constexpr (SN == 2) kkt_factor_top(c.s_hy, c.tid);
 }
 
 // ---- shared-memory, prefetching substitution ------------------------------------------------------------
@@ -577,6 +643,7 @@ __device__ __noinline__ void solve_sweep(const SweepArgs a)
 #undef IPM_CONSUME
 }
 
+template <int SN>
 __device__ __forceinline__ void kkt_ldl_solve_smem(const IpmProgram &P, Ctx &c, const double *Ls, const double *invD, double *v)
 {
     const int G = c.G, sg = c.sg;
@@ -590,8 +657,10 @@ __device__ __forceinline__ void kkt_ldl_solve_smem(const IpmProgram &P, Ctx &c, 
     a.lprof = c.lprof ? c.lprof + P.nlevels : nullptr;
     solve_sweep<1>(a);
     if (P.nlevels <= 1) __syncthreads();
+    if constexpr (SN == 2) kkt_sweep_top<1>(c.s_hy, c.tid);   // after the bridge level: column-oriented top panels
     const long long t1_ = clock64();
     for (int i = c.slot; i < P.nk; i += c.nslots) vs[i * G + sg] *= invD[GI(i)];
+    if constexpr (SN == 2) { __syncthreads(); kkt_sweep_top<-1>(c.s_hy, c.tid); }
     // backward: the top level holds roots only (empty columns)
     a.items = P.bwp_item; a.idxarr = P.L_ri; a.vals = Ls; a.o_lvl = c.o_bwl; a.o_R = c.o_bwR; a.lv0 = P.nlevels - 2;
     a.lprof = c.lprof ? c.lprof + 2 * P.nlevels : nullptr;
@@ -607,8 +676,8 @@ __device__ __forceinline__ void kkt_ldl_solve_smem(const IpmProgram &P, Ctx &c, 
 template <int SN>
 __device__ __forceinline__ void kkt_ldl_solve(const IpmProgram &P, Ctx &c, const double *Ls, const double *invD, double *v)
 {
-    if constexpr (SN) { kkt_ldl_solve_sn(P, c, invD, v); return; }
-    if (c.vs) { kkt_ldl_solve_smem(P, c, Ls, invD, v); return; }
+    if constexpr (SN == 1) { kkt_ldl_solve_sn(P, c, invD, v); return; }
+    if (SN == 2 || c.vs) { kkt_ldl_solve_smem<SN>(P, c, Ls, invD, v); return; }
     set_lanes(c, c.Rmax);
     const int G = c.G, sg = c.sg;
     for (int lv = 0; lv < P.nlevels; lv++) {   // forward, rows of L
@@ -983,6 +1052,7 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
     double *const s_delta = ipm_s_delta;
     int *const s_bad = ipm_s_bad;
     __shared__ SnArgs s_snargs;
+    __shared__ HyArgs s_hyargs;
 
     int *s_lv = ipm_smem;   // [9][nlevels+1]: lvl_ptr | fa_lvl | fb_lvl | - | fa_R | fwp_lvl | bwp_lvl | fwp_R | bwp_R
     const int nl1 = P.nlevels + 1;
@@ -1004,7 +1074,7 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
     c.Rmax = D.R;
     c.t_fw = c.t_bw = c.t_ldl_n = 0;
     c.lprof = (blockIdx.x == 0 && threadIdx.x == 0 && D.prof && D.lvl_prof) ? D.prof + 12 : nullptr;
-    if (c.lprof) for (int i = 0; i < 3 * P.nlevels; i++) c.lprof[i] = 0;
+    if (c.lprof) for (int i = 0; i < 3 * (P.nlevels + (SN == 2 ? P.hy.ntl : 0)); i++) c.lprof[i] = 0;
     set_lanes(c, c.Rmax);
     __syncthreads();
     c.red = s_red; c.out = s_out;
@@ -1031,7 +1101,15 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
     c.s_done = s_done; c.s_delta = s_delta; c.s_bad = s_bad; c.rho_min = O.rho_min; c.bad_abs = O.bad_abs;
     if (threadIdx.x == 0) { ipm_s_reg[0] = O.rho_min; ipm_s_reg[1] = O.bad_abs; }
     c.s_sn = &s_snargs;
-    if (SN && threadIdx.x == 0) {
+    c.s_hy = &s_hyargs;
+    if (SN == 2 && threadIdx.x == 0) {
+        HyArgs a;
+        a.hy = P.hy; a.Y = Y; a.Ls = Ls; a.invD = invD; a.s_done = s_done; a.s_delta = s_delta; a.s_bad = s_bad;
+        a.rho_min = O.rho_min; a.bad_abs = O.bad_abs; a.o_vs = c.o_vs; a.nnzL = P.nnzL; a.G = D.G; a.nwarps = NT / 32;
+        a.lprof = (blockIdx.x == 0 && D.prof && D.lvl_prof) ? D.prof + 12 + 3 * P.nlevels : nullptr;
+        s_hyargs = a;
+    }
+    if (SN == 1 && threadIdx.x == 0) {
         SnArgs a;
         a.sn = P.sn; a.Y = Y; a.invD = invD; a.vs = c.vs; a.s_done = s_done; a.s_delta = s_delta; a.s_bad = s_bad;
         a.rho_min = O.rho_min; a.bad_abs = O.bad_abs; a.ysize = (size_t)P.ysize; a.G = D.G; a.tid = 0; a.nwarps = NT / 32;

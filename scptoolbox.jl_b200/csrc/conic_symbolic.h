@@ -24,7 +24,7 @@
 #endif
 // supernodal panels (conic_sn.cuh): a panel is held by a lane group, one lane per row, at most CONIC_SN_WMAX columns
 // in registers; wider runs of columns are cut into several supernodes
-#define CONIC_SN_WMAX 12
+#define CONIC_SN_WMAX 8
 #define CONIC_SN_RMAX 32
 #define CONIC_SN_R1MAX 10   // single-column panels up to this height are handled by ONE thread (leaf levels)
 // lane-group size of an R x w panel (1, 8, 16 or 32 lanes; 0: the panel does not fit a warp -> scalar programs only)
@@ -102,6 +102,21 @@ struct ConeSymbolic {
     std::vector<int> sn_upd_xy;                      // the pair itself, packed x | y << 16 (indices into the below rows)
     std::vector<int> sn_sign;                        // expected pivot sign of each column (+1 / -1)
     std::vector<int> sn_cls_ptr;                     // [nlevels][5]: level nodes sorted by lane-group size 1 | 8 | 16 | 32 (conic_sn.cuh)
+    // ---- hybrid program (cone_symbolic_build_hybrid): the columns of the supernodes at supernodal level >= hy_cut (the
+    // "top" of the elimination tree: few, wide, tall panels -- nested-dissection separators and the dense border) are
+    // factored and substituted as register-resident panels, one lane per row, straight on the SCALAR storage (a
+    // supernode's columns are consecutive in the CSC arrays of L); everything below keeps the scalar level-scheduled
+    // gather programs.  hy_nlevels scalar levels: the levels of the low columns plus one "bridge" level in which every
+    // top target gathers its contributions from low columns (factorisation) / every top row gathers from low columns
+    // (forward substitution) in one wide, barrier-free pass.  Bench KKT: 88 scalar levels -> 20 + 17 supernodal ones.
+    int hy_cut = 0, hy_nlevels = 0, hy_ntl = 0;
+    std::vector<int> hy_fa_item, hy_fa_lvl, hy_fa_R, hy_fb_item, hy_fb_lvl, hy_ft_op;
+    std::vector<int> hy_fwp_item, hy_fwp_lvl, hy_fwp_R, hy_bwp_item, hy_bwp_lvl, hy_bwp_R;
+    std::vector<int> hy_tl_ptr;     // hy_ntl + 1 -> index into the descriptor list
+    std::vector<int> hy_desc;       // 8 ints per top supernode in top-level order: {first column, width, rows, L_cp[first]},
+                                    // {offset into sn_rows, offset into hy_upd_dst, pivot signs (bit c: column c expects +), 0}
+    std::vector<int> hy_upd_dst;    // below-row pairs (x >= y) of a top supernode -> TARGET id (L position | nnzL + column)
+    std::vector<int> hy_is_top;     // per node (tests)
     bool sn_fits = true;                             // every panel fits a warp's scratch
     long long sn_panel_size = 0;
     int sn_nlevels = 0;
@@ -567,5 +582,172 @@ inline bool cone_symbolic_build(ConeSymbolic &S, int n, int p, int m, const int 
         build(S.Lr_rp, S.fwp_item, S.fwp_lvl, S.fwp_R);
         build(S.L_cp, S.bwp_item, S.bwp_lvl, S.bwp_R);
     }
+    return true;
+}
+
+// Hybrid program for the supernodes at supernodal level >= cut (see ConeSymbolic::hy_*).  Returns false (and leaves
+// hy_cut = 0) when the split is empty on either side or a top panel does not fit a warp.
+inline bool cone_symbolic_build_hybrid(ConeSymbolic &S, int cut)
+{
+    S.hy_cut = 0; S.hy_nlevels = 0; S.hy_ntl = 0;
+    const int nk = S.nk, ns = (int)S.sn_first.size();
+    if (cut <= 0 || cut >= S.sn_nlevels || nk == 0) return false;
+    std::vector<int> slev(ns, 0), sn_of(nk, 0), node_lvl(nk, 0), col_of_pos(S.nnzL, 0);
+    for (int lv = 0; lv < S.sn_nlevels; lv++)
+        for (int w = S.sn_lvl_ptr[lv]; w < S.sn_lvl_ptr[lv + 1]; w++) slev[S.sn_lvl_nodes[w]] = lv;
+    for (int s = 0; s < ns; s++)
+        for (int c = 0; c < S.sn_width[s]; c++) sn_of[S.sn_first[s] + c] = s;
+    for (int lv = 0; lv < S.nlevels; lv++)
+        for (int w = S.lvl_ptr[lv]; w < S.lvl_ptr[lv + 1]; w++) node_lvl[S.lvl_nodes[w]] = lv;
+    for (int j = 0; j < nk; j++)
+        for (int q = S.L_cp[j]; q < S.L_cp[j + 1]; q++) col_of_pos[q] = j;
+    S.hy_is_top.assign(nk, 0);
+    int ntop = 0, Lb = 0;
+    for (int j = 0; j < nk; j++) {
+        S.hy_is_top[j] = slev[sn_of[j]] >= cut ? 1 : 0;
+        ntop += S.hy_is_top[j];
+        if (!S.hy_is_top[j]) Lb = std::max(Lb, node_lvl[j] + 1);
+    }
+    if (ntop == 0 || ntop == nk) return false;
+    for (int s = 0; s < ns; s++)
+        if (slev[s] >= cut && (S.sn_nrows[s] > CONIC_SN_RMAX || S.sn_width[s] > CONIC_SN_WMAX)) return false;
+    const std::vector<int> &top = S.hy_is_top;
+    const int nl = Lb + 1;   // low levels 0..Lb-1, bridge level Lb
+    auto tcol = [&](int t) { return t >= S.nnzL ? t - S.nnzL : col_of_pos[t]; };
+    std::vector<int> rowpos(S.nnzL);
+    for (int w = 0; w < S.nnzL; w++) rowpos[S.Lr_pos[w]] = w;
+
+    // ---- factorisation: phase A items (target, op range), phase B items, per level ----
+    S.hy_ft_op = S.ft_op;
+    struct Tgt { int t, k0, k1; };
+    std::vector<std::vector<Tgt>> lvl_tgts(nl);
+    for (int lv = 0; lv < S.nlevels; lv++)
+        for (int w = S.ft_lvl_ptr[lv]; w < S.ft_lvl_ptr[lv + 1]; w++) {
+            const int t = S.ft_target[w], j = tcol(t);
+            if (!top[j]) { lvl_tgts[lv].push_back({t, S.ft_op_ptr[w], S.ft_op_ptr[w + 1]}); continue; }
+            const int k0 = (int)(S.hy_ft_op.size() / 2);
+            for (int k = S.ft_op_ptr[w]; k < S.ft_op_ptr[w + 1]; k++)
+                if (!top[col_of_pos[S.ft_op_a[k]]]) { S.hy_ft_op.push_back(S.ft_op[2 * (size_t)k]); S.hy_ft_op.push_back(S.ft_op[2 * (size_t)k + 1]); }
+            const int k1 = (int)(S.hy_ft_op.size() / 2);
+            if (k1 > k0) lvl_tgts[Lb].push_back({t, k0, k1});
+        }
+    {
+        const int PF = CONIC_FACTOR_PF, SLOTS = 512, RMAX = 4;
+        S.hy_fa_item.clear(); S.hy_fa_lvl.assign(nl + 1, 0); S.hy_fa_R.assign(nl, 1);
+        S.hy_fb_item.clear(); S.hy_fb_lvl.assign(nl + 1, 0);
+        for (int lv = 0; lv < nl; lv++) {
+            int bestR = 1; long long bestp = -1, bestw = -1;
+            for (int R = 1; R <= RMAX; R *= 2) {
+                long long items = 0;
+                for (const Tgt &g : lvl_tgts[lv]) items += (g.k1 - g.k0 + R * PF - 1) / (R * PF);
+                const long long passes = (items * R + SLOTS - 1) / SLOTS, waste = items * R;
+                if (bestp < 0 || passes < bestp || (passes == bestp && waste < bestw)) { bestp = passes; bestw = waste; bestR = R; }
+            }
+            S.hy_fa_R[lv] = bestR;
+            const int cap = bestR * PF;
+            for (const Tgt &g : lvl_tgts[lv]) {
+                const int split = (g.k1 - g.k0 > cap) ? 1 : 0;
+                for (int k = g.k0; k < g.k1; k += cap) {
+                    S.hy_fa_item.push_back(g.t); S.hy_fa_item.push_back(k);
+                    S.hy_fa_item.push_back(std::min(k + cap, g.k1)); S.hy_fa_item.push_back(split);
+                }
+            }
+            S.hy_fa_lvl[lv + 1] = (int)(S.hy_fa_item.size() / 4);
+            if (lv < S.nlevels && lv < Lb)
+                for (int w = S.lvl_ptr[lv]; w < S.lvl_ptr[lv + 1]; w++) {
+                    const int j = S.lvl_nodes[w];
+                    if (top[j]) continue;
+                    const int pos = (S.as_sign[S.nnzL + j] > 0) ? 1 : 0;
+                    S.hy_fb_item.push_back(S.nnzL + j); S.hy_fb_item.push_back(j); S.hy_fb_item.push_back(0); S.hy_fb_item.push_back(pos | 2);
+                    for (int q = S.L_cp[j]; q < S.L_cp[j + 1]; q++) {
+                        S.hy_fb_item.push_back(q); S.hy_fb_item.push_back(j); S.hy_fb_item.push_back(rowpos[q]); S.hy_fb_item.push_back(pos);
+                    }
+                }
+            S.hy_fb_lvl[lv + 1] = (int)(S.hy_fb_item.size() / 4);
+        }
+        if (S.hy_fa_item.empty()) S.hy_fa_item.assign(4, 0);
+        if (S.hy_fb_item.empty()) S.hy_fb_item.assign(4, 0);
+    }
+    // ---- substitutions: (node, entry range) runs per level ----
+    {
+        const int PF = CONIC_SOLVE_PF, SLOTS = 512, RMAX = 4;
+        struct Run { int i, k0, k1; };
+        auto emit = [&](const std::vector<std::vector<Run>> &runs, std::vector<int> &item, std::vector<int> &lvl, std::vector<int> &Rl) {
+            item.clear(); lvl.assign(nl + 1, 0); Rl.assign(nl, 1);
+            for (int lv = 0; lv < nl; lv++) {
+                int bestR = 1; long long bestp = -1, bestw = -1;
+                for (int R = 1; R <= RMAX; R *= 2) {
+                    long long items = 0;
+                    for (const Run &r : runs[lv]) items += (r.k1 - r.k0 + R * PF - 1) / (R * PF);
+                    const long long passes = (items * R + SLOTS - 1) / SLOTS, waste = items * R;
+                    if (bestp < 0 || passes < bestp || (passes == bestp && waste < bestw)) { bestp = passes; bestw = waste; bestR = R; }
+                }
+                Rl[lv] = bestR;
+                const int cap = bestR * PF;
+                // a node whose entries end up in more than one item (long run, or several runs) combines them with atomics
+                std::vector<int> nitems(nk, 0);
+                for (const Run &r : runs[lv]) nitems[r.i] += (r.k1 - r.k0 + cap - 1) / cap;
+                for (const Run &r : runs[lv])
+                    for (int k = r.k0; k < r.k1; k += cap) {
+                        item.push_back(r.i); item.push_back(k); item.push_back(std::min(k + cap, r.k1)); item.push_back(nitems[r.i] > 1 ? 1 : 0);
+                    }
+                lvl[lv + 1] = (int)(item.size() / 4);
+            }
+            if (item.empty()) item.assign(4, 0);
+        };
+        std::vector<std::vector<Run>> fr(nl), br(nl);
+        for (int i = 0; i < nk; i++) {
+            if (!top[i]) {
+                if (S.Lr_rp[i + 1] > S.Lr_rp[i]) fr[node_lvl[i]].push_back({i, S.Lr_rp[i], S.Lr_rp[i + 1]});
+                if (S.L_cp[i + 1] > S.L_cp[i]) br[node_lvl[i]].push_back({i, S.L_cp[i], S.L_cp[i + 1]});
+                continue;
+            }
+            // top row: the runs of LOW columns (the top columns reach it through the panel sweeps)
+            int k = S.Lr_rp[i];
+            const int ke = S.Lr_rp[i + 1];
+            while (k < ke) {
+                while (k < ke && top[S.Lr_col[k]]) k++;
+                const int k0 = k;
+                while (k < ke && !top[S.Lr_col[k]]) k++;
+                if (k > k0) fr[Lb].push_back({i, k0, k});
+            }
+        }
+        emit(fr, S.hy_fwp_item, S.hy_fwp_lvl, S.hy_fwp_R);
+        emit(br, S.hy_bwp_item, S.hy_bwp_lvl, S.hy_bwp_R);
+    }
+    // ---- top supernodes: descriptors in level order, update scatter lists as target ids ----
+    {
+        auto lpos = [&](int i, int j) -> int {
+            auto b = S.L_ri.begin() + S.L_cp[j], e = S.L_ri.begin() + S.L_cp[j + 1];
+            auto it = std::lower_bound(b, e, i);
+            return (it != e && *it == i) ? (int)(it - S.L_ri.begin()) : -1;
+        };
+        const int ntl = S.sn_nlevels - cut;
+        S.hy_tl_ptr.assign(ntl + 1, 0); S.hy_desc.clear(); S.hy_upd_dst.clear();
+        for (int tl = 0; tl < ntl; tl++) {
+            for (int w_ = S.sn_lvl_ptr[cut + tl]; w_ < S.sn_lvl_ptr[cut + tl + 1]; w_++) {
+                const int s = S.sn_lvl_nodes[w_], a = S.sn_first[s], w = S.sn_width[s], R = S.sn_nrows[s];
+                for (int c = 0; c + 1 < w; c++)   // the closed-form panel addressing needs consecutive CSC columns
+                    if (S.L_cp[a + c + 1] - S.L_cp[a + c] != R - c - 1) { S.err = "internal: top supernode is not a dense trapezoid"; return false; }
+                int sign = 0;
+                for (int c = 0; c < w; c++) sign |= (S.as_sign[(size_t)S.nnzL + a + c] > 0 ? 1 : 0) << c;
+                const int *below = &S.sn_rows[S.sn_rows_ptr[s] + w];
+                const int u0 = (int)S.hy_upd_dst.size();
+                for (int y = 0; y < R - w; y++)
+                    for (int x = y; x < R - w; x++) {
+                        const int t = (x == y) ? S.nnzL + below[y] : lpos(below[x], below[y]);
+                        if (t < 0) { S.err = "internal: hybrid update falls outside the L pattern"; return false; }
+                        S.hy_upd_dst.push_back(t);
+                    }
+                const int d[8] = {a, w, R, S.L_cp[a], S.sn_rows_ptr[s], u0, sign, 0};
+                S.hy_desc.insert(S.hy_desc.end(), d, d + 8);
+            }
+            S.hy_tl_ptr[tl + 1] = (int)(S.hy_desc.size() / 8);
+        }
+        S.hy_desc.resize(S.hy_desc.size() + 8, 0);
+        S.hy_ntl = ntl;
+    }
+    S.hy_nlevels = nl;
+    S.hy_cut = cut;
     return true;
 }

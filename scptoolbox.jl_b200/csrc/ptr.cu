@@ -8,6 +8,8 @@
 //   accept/stop: k_ptr_step -- solution_deviation (scp.jl:909-931) + check_stopping_criterion! (ptr.jl:908-932)
 // Seeds that have stopped are frozen (their iterate is re-extracted unchanged) so a finished or failed
 // seed never stalls the batch.
+#include <algorithm>
+#include <cstdio>
 #include "handle.cuh"
 #include "discretize.cuh"
 #include "constraints.cuh"
@@ -258,6 +260,24 @@ static T *up(scpb_ptr_s *s, const T *src, size_t n)
     if (n) cudaMemcpy(d, src, sizeof(T) * n, cudaMemcpyHostToDevice);
     s->dev.push_back(d);
     return (T *)d;
+}
+
+// diagnostic (SCPB_IPM_STATS=1): distribution of the interior-point iteration counts of one solver launch over its live
+// seeds -- the launch lasts as long as its slowest seed group
+static void ipm_launch_stats(const std::vector<int> &hit, const std::vector<int> &hdone, int launch)
+{
+    static const bool on = getenv("SCPB_IPM_STATS") != nullptr;
+    if (!on) return;
+    std::vector<int> v;
+    for (size_t b = 0; b < hit.size(); b++) if (!hdone[b]) v.push_back(hit[b]);
+    if (v.empty()) return;
+    std::sort(v.begin(), v.end());
+    long long sum = 0;
+    for (int x : v) sum += x;
+    size_t am = 0;
+    for (size_t b = 0; b < hit.size(); b++) if (!hdone[b] && (hdone[am] || hit[b] > hit[am])) am = b;
+    fprintf(stderr, "[scpb] launch %d: live %zu  ipm iterations min %d  median %d  p90 %d  max %d  mean %.1f  argmax %zu\n", launch,
+            v.size(), v.front(), v[v.size() / 2], v[(v.size() * 9) / 10], v.back(), (double)sum / v.size(), am);
 }
 
 static int ptr_reserve(scpb_ptr_s *s, int B, int G)
@@ -813,7 +833,7 @@ int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *u
     const int Bpad = s->capB;
     int it = 1, nact = B, total_it = 0;
     long long ipm_iters = 0;
-    std::vector<int> hit(B);
+    std::vector<int> hit(B), hdone(B, 0);   // hdone: seeds that were already finished when the solver was launched (skipped)
     for (; it <= d.iter_max; it++) {
         launch_linearize(s, pd, nbn, st);
         const long long tot = (long long)d.nval * Bpad;
@@ -835,7 +855,10 @@ int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *u
         SCPB_CUDA(h, cudaMemcpyAsync(&nact, s->nactive, sizeof(int), cudaMemcpyDeviceToHost, st));
         mark(); phase.push_back(3);
         SCPB_CUDA(h, cudaStreamSynchronize(st));
-        for (int b = 0; b < B; b++) ipm_iters += hit[b];
+        for (int b = 0; b < B; b++) if (!hdone[b]) ipm_iters += hit[b];   // skipped seeds keep a stale count in D->iters
+        ipm_launch_stats(hit, hdone, total_it + 1);
+        SCPB_CUDA(h, cudaMemcpyAsync(hdone.data(), s->done, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+        SCPB_CUDA(h, cudaStreamSynchronize(st));
         total_it++;
         if (nact == 0) break;
     }
@@ -982,7 +1005,7 @@ int32_t scpb_scvx_solve(scpb_ptr s, int32_t B, const double *xd0, const double *
     const int Bpad = s->capB;
     int it = 1, nact = B, total_it = 0;
     long long ipm_iters = 0;
-    std::vector<int> hit(B);
+    std::vector<int> hit(B), hdone(B, 0);   // hdone: seeds that were already finished when the solver was launched (skipped)
     const long long span = (long long)(d.oC - d.oA) * B;
     for (; it <= d.iter_max; it++) {
         if (pack) k_linearize<Constr<SCPB_MODEL_STARSHIP>><<<nbn, 128, 0, st>>>(pd, s->xd, s->ud, s->p);
@@ -1009,7 +1032,10 @@ int32_t scpb_scvx_solve(scpb_ptr s, int32_t B, const double *xd0, const double *
         SCPB_CUDA(h, cudaMemcpyAsync(&nact, s->nactive, sizeof(int), cudaMemcpyDeviceToHost, st));
         mark(); phase.push_back(3);
         SCPB_CUDA(h, cudaStreamSynchronize(st));
-        for (int b = 0; b < B; b++) ipm_iters += hit[b];
+        for (int b = 0; b < B; b++) if (!hdone[b]) ipm_iters += hit[b];   // skipped seeds keep a stale count in D->iters
+        ipm_launch_stats(hit, hdone, total_it + 1);
+        SCPB_CUDA(h, cudaMemcpyAsync(hdone.data(), s->done, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+        SCPB_CUDA(h, cudaStreamSynchronize(st));
         total_it++;
         if (nact == 0) break;
     }
@@ -1161,7 +1187,7 @@ int32_t scpb_gusto_solve(scpb_ptr s, int32_t B, const double *xd0, const double 
     const int Bpad = s->capB;
     int it = 1, nact = B, total_it = 0;
     long long ipm_iters = 0;
-    std::vector<int> hit(B);
+    std::vector<int> hit(B), hdone(B, 0);   // hdone: seeds that were already finished when the solver was launched (skipped)
     const long long span = (long long)(d.oC - d.oA) * B;
     for (; it <= d.iter_max; it++) {
         launch_linearize(s, pd, nbn, st);
@@ -1187,7 +1213,10 @@ int32_t scpb_gusto_solve(scpb_ptr s, int32_t B, const double *xd0, const double 
         SCPB_CUDA(h, cudaMemcpyAsync(&nact, s->nactive, sizeof(int), cudaMemcpyDeviceToHost, st));
         mark(); phase.push_back(3);
         SCPB_CUDA(h, cudaStreamSynchronize(st));
-        for (int b = 0; b < B; b++) ipm_iters += hit[b];
+        for (int b = 0; b < B; b++) if (!hdone[b]) ipm_iters += hit[b];   // skipped seeds keep a stale count in D->iters
+        ipm_launch_stats(hit, hdone, total_it + 1);
+        SCPB_CUDA(h, cudaMemcpyAsync(hdone.data(), s->done, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+        SCPB_CUDA(h, cudaStreamSynchronize(st));
         total_it++;
         if (nact == 0) break;
     }

@@ -63,6 +63,9 @@ SIGNATURES = {
                                          _ip, _ip, _dp, _dp, _dp, C.c_double, C.c_double, _dp, _dp, C.POINTER(C.c_int64)]),
     "scpb_debug_kkt_solve_sn": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _ip, _ip, _ip, _ip, C.c_int32, C.c_int32,
                                          _ip, _ip, _dp, _dp, _dp, C.c_double, C.c_double, _dp, _dp, C.POINTER(C.c_int64)]),
+    "scpb_debug_kkt_solve_hy": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _ip, _ip, _ip, _ip, C.c_int32, C.c_int32,
+                                         _ip, _ip, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int32, _dp, _dp,
+                                         C.POINTER(C.c_int64)]),
     "scpb_debug_fp64_peak": (C.c_int32, [C.c_void_p, _dp]),
     "scpb_debug_kkt_solve_dev": (C.c_int32, [C.c_void_p, C.c_int32, _dp, _dp, _dp, C.c_double, _dp, _dp, _ip]),
     "scpb_debug_kkt_new": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _ip, _ip, _ip, _ip, C.c_int32, C.c_int32, _ip, _ip,
@@ -275,13 +278,14 @@ class ConeProblem:
         self.l, self.soc_dims = int(l), list(soc_dims)
 
     def info(self):
-        buf = (C.c_int64 * 20)()
+        buf = (C.c_int64 * 24)()
         self.lib.scpb_cone_info(self.c, buf)
         keys = ["nk", "nnzL", "levels", "factor_ops", "assembly_ops", "nwm", "group", "capacity"]
         d = dict(zip(keys, [int(v) for v in buf[:8]]))
         d["cycles"] = dict(zip(["equilibrate", "start_point", "residuals", "scale_assemble", "factor", "kkt_solves",
                                 "linesearch_update", "total", "ldl_forward", "ldl_backward", "ldl_count",
                                 "factor_count"], [int(v) for v in buf[8:20]]))
+        d["hybrid"] = dict(zip(["cut_used", "levels", "top_levels", "cut_built"], [int(v) for v in buf[20:24]]))
         fc = d["cycles"]["factor_count"]
         d["cycles"]["factor_count"] = fc & 0xffffffff      # interior-point iterations of CTA 0
         d["cycles"]["factor_retries"] = fc >> 32           # factorisations repeated with a larger static regularisation
@@ -347,9 +351,10 @@ class ConeProblem:
         return out
 
 
-def debug_kkt_solve(A, G, l, soc_dims, perm, Avals, Gvals, wm, delta, rhs, delta_dyn=0.0, supernodal=False):
+def debug_kkt_solve(A, G, l, soc_dims, perm, Avals, Gvals, wm, delta, rhs, delta_dyn=0.0, supernodal=False, hybrid_cut=0):
     """CPU interpreter of the index programs for one seed (test hook, see include/scpb.h); supernodal=True runs the
-    dense-panel program of the next kernel generation instead of the scalar level-scheduled one."""
+    dense-panel program instead of the scalar level-scheduled one, hybrid_cut > 0 the hybrid program (scalar below that
+    supernodal level, in-place panels above)."""
     lib = load()
     A = A.tocsr(); G = G.tocsr(); A.sort_indices(); G.sort_indices()
     n, p, m = A.shape[1], A.shape[0], G.shape[0]
@@ -359,6 +364,15 @@ def debug_kkt_solve(A, G, l, soc_dims, perm, Avals, Gvals, wm, delta, rhs, delta
     Av, pAv = _f64(Avals); Gv, pGv = _f64(Gvals); wmv, pwm = _f64(wm); r, pr = _f64(rhs)
     sol = np.zeros(n + p)
     info = (C.c_int64 * 8)()
+    if hybrid_cut > 0:
+        rc = lib.scpb_debug_kkt_solve_hy(n, p, m, a0[1], a1[1], g0[1], g1[1], int(l), len(soc_dims), sd[1], pm[1],
+                                         pAv, pGv, pwm, float(delta), float(delta_dyn), int(hybrid_cut), pr,
+                                         sol.ctypes.data_as(_dp), info)
+        if rc != 0:
+            raise ScpbError(f"scpb_debug_kkt_solve_hy failed ({rc})")
+        keys = ("levels", "top_levels", "top_supernodes", "top_columns", "bridge_factor_items", "bridge_factor_ops",
+                "bridge_forward_items", "scalar_levels")
+        return sol, dict(zip(keys, [int(v) for v in info]))
     if supernodal:
         rc = lib.scpb_debug_kkt_solve_sn(n, p, m, a0[1], a1[1], g0[1], g1[1], int(l), len(soc_dims), sd[1], pm[1],
                                          pAv, pGv, pwm, float(delta), float(delta_dyn), pr, sol.ctypes.data_as(_dp), info)

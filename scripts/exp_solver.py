@@ -15,17 +15,23 @@ mdl = ex.StarshipProblem(); traj = pkg.problem.TrajectoryProblem(mdl); ex.define
 P = dict(bench.PTR); P["iter_max"] = int(os.environ.get("ITER_MAX", str(P["iter_max"])))
 pars = pkg.ptr.Parameters(N=N, Nsub=Nsub, disc_method=pkg.ptr.FOH, q_tr=np.inf, q_exit=np.inf, **P)
 base = traj.guess(N)
-pbm = pkg.ptr.create(pars, traj, h)
-X, U, Pp = bench.make_seeds(base, pbm.scale.Sx, pbm.scale.Su, B, 0, pbm.scale.cx, pbm.scale.cu)
-variants = [("sn0 t1024", "0", dict()), ("sn1 t1024", "1", dict()), ("sn0 t512", "0", dict(threads=512)),
-            ("sn0 tol1e-10", "0", dict(feastol=1e-10, abstol=1e-10, reltol=1e-10)),
-            ("sn0 old-delta", "0", dict(delta=1e-9, delta_dyn=1e-9))]
+variants = [("sn0 t1024", dict(SCPB_SUPERNODAL="0", SCPB_HYBRID="0"), dict()),
+            ("sn1 t1024", dict(SCPB_SUPERNODAL="1", SCPB_HYBRID="0"), dict()),
+            ("sn0 t512", dict(SCPB_SUPERNODAL="0", SCPB_HYBRID="0"), dict(threads=512)),
+            ("sn0 tol1e-10", dict(SCPB_SUPERNODAL="0", SCPB_HYBRID="0"), dict(feastol=1e-10, abstol=1e-10, reltol=1e-10))]
+for cut in range(2, 13):
+    variants.append((f"hy{cut} t1024", dict(SCPB_SUPERNODAL="0", SCPB_HYBRID=str(cut)), dict()))
 want = sys.argv[4:]
 ref = None
-for name, sn, opts in variants:
-    if want and not any(w in name for w in want):
+seeds = None
+for name, env, opts in variants:
+    if want and not any(w == name.split()[0] or w == name for w in want):
         continue
-    os.environ["SCPB_SUPERNODAL"] = sn
+    os.environ.update(env)        # SCPB_HYBRID is read when the cone problem is set up, SCPB_SUPERNODAL at every launch
+    pbm = pkg.ptr.create(pars, traj, h)
+    if seeds is None:
+        seeds = bench.make_seeds(base, pbm.scale.Sx, pbm.scale.Su, B, 0, pbm.scale.cx, pbm.scale.cu)
+    X, U, Pp = seeds
     best = None
     for rep in range(2):
         t = time.time()
@@ -34,7 +40,8 @@ for name, sn, opts in variants:
         if best is None or sol.timing["solve"] < best[0].timing["solve"]:
             best = (sol, dt)
     sol, dt = best
-    cyc = pbm.cone.info()["cycles"]
+    info = pbm.cone.info()
+    cyc = info["cycles"]
     tot = max(1, cyc["total"])
     shares = {k: round(v / tot, 3) for k, v in cyc.items() if k not in ("total", "ldl_count", "factor_count", "factor_retries")}
     st = {s: sol.status.count(s) for s in set(sol.status)}
@@ -43,9 +50,11 @@ for name, sn, opts in variants:
                ipm_per_solve=round(sol.timing["ipm_iterations"] / max(1, sol.iterations.sum()), 2),
                solves_per_ipm=round(cyc["ldl_count"] / max(1, cyc["factor_count"]), 2), shares=shares,
                retries_cta0=cyc["factor_retries"], ipm_its_cta0=cyc["factor_count"],
-               ms_per_ipm_it_cta0=round(cyc["total"] / 1.965e6 / max(1, cyc["factor_count"]), 3))
+               ms_per_ipm_it_cta0=round(cyc["total"] / 1.965e6 / max(1, cyc["factor_count"]), 3), hybrid=info["hybrid"])
     if ref is None:
         ref = sol
     else:
-        out["max_dx_vs_first"] = float(np.abs(sol.xd - ref.xd).max()); out["max_dJ_vs_first"] = float(np.abs(sol.cost - ref.cost).max())
+        out["max_dx_vs_first"] = float(np.abs((sol.xd - ref.xd) / pbm.scale.Sx).max()); out["max_dJ_vs_first"] = float(np.abs(sol.cost - ref.cost).max())
+        out["iters_equal_first"] = bool((sol.iterations == ref.iterations).all())
     print(json.dumps(out), flush=True)
+    pbm.close()

@@ -22,6 +22,19 @@ cyc = info["cycles"]
 print("cycles", cyc)
 nf, ns = max(cyc["factor_count"], 1), max(cyc["ldl_count"], 1)
 print("lvl  factor_us  fw_us  bw_us   (per call, 1.965 GHz)")
-for l in range(lp.shape[1]):
+for l in range(lp.shape[1] if not info["hybrid"]["cut_used"] else 0):
     print(f"{l:3d} {lp[0, l] / nf / 1965:9.2f} {lp[1, l] / ns / 1965:7.2f} {lp[2, l] / ns / 1965:7.2f}")
-print("sum", lp[0].sum() / nf / 1965, lp[1].sum() / ns / 1965, lp[2].sum() / ns / 1965)
+hy = info["hybrid"]
+if hy["cut_used"]:   # hybrid program: [3][scalar levels incl. bridge] then [3][top levels], both packed at the front
+    raw = lp.reshape(-1)
+    nl, ntl = hy["levels"], hy["top_levels"]
+    sc = raw[:3 * nl].reshape(3, nl); tp = raw[3 * nl:3 * (nl + ntl)].reshape(3, ntl)
+    print("hybrid cut", hy["cut_used"], "scalar levels (last = bridge)", nl, "top levels", ntl)
+    for l in range(nl):
+        print(f"s{l:3d} {sc[0, l] / nf / 1965:9.2f} {sc[1, l] / ns / 1965:7.2f} {sc[2, l] / ns / 1965:7.2f}")
+    for l in range(ntl):
+        print(f"t{l:3d} {tp[0, l] / nf / 1965:9.2f} {tp[1, l] / ns / 1965:7.2f} {tp[2, l] / ns / 1965:7.2f}")
+    print("sum scalar", sc[0].sum() / nf / 1965, sc[1].sum() / ns / 1965, sc[2].sum() / ns / 1965,
+          "top", tp[0].sum() / nf / 1965, tp[1].sum() / ns / 1965, tp[2].sum() / ns / 1965)
+else:
+    print("sum", lp[0].sum() / nf / 1965, lp[1].sum() / ns / 1965, lp[2].sum() / ns / 1965)

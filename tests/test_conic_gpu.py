@@ -128,13 +128,20 @@ def _dense_kkt(A, G, l, soc, wm, delta):
     return np.block([[H, Ad.T], [Ad, -delta * np.eye(p)]])
 
 
-@pytest.mark.parametrize("sn", ["1", "0"])
+def _variant(monkeypatch, sn):
+    """kernel variant: "1" supernodal panels, "0" scalar level-scheduled programs, "hN" hybrid program with cut N"""
+    monkeypatch.setenv("SCPB_SUPERNODAL", "1" if sn == "1" else "0")
+    monkeypatch.setenv("SCPB_HYBRID", sn[1:] if sn.startswith("h") else "0")
+
+
+@pytest.mark.parametrize("sn", ["1", "0", "h1", "h2"])
 @pytest.mark.parametrize("seed,n,p,l,soc", [(0, 12, 4, 9, []), (1, 20, 7, 15, [3, 4]), (2, 30, 10, 25, [5]),
                                             (4, 15, 5, 0, [3, 3, 4])])
 def test_device_kkt_solve_matches_dense(handle, pkg, monkeypatch, sn, seed, n, p, l, soc):
     """One reduced-KKT assemble + factor + solve through the kernel's own code path (supernodal panels held in
-    registers, conic_sn.cuh; and the scalar level-scheduled programs with SCPB_SUPERNODAL=0) against numpy."""
-    monkeypatch.setenv("SCPB_SUPERNODAL", sn)
+    registers, conic_sn.cuh; the scalar level-scheduled programs with SCPB_SUPERNODAL=0; the hybrid program that runs
+    the top of the elimination tree as in-place panels, SCPB_HYBRID=<cut>) against numpy."""
+    _variant(monkeypatch, sn)
     rng = np.random.default_rng(seed)
     m = l + sum(soc)
     A = sp.random(p, n, density=0.4, random_state=rng.integers(1 << 30), format="csr")
@@ -168,11 +175,11 @@ def test_device_kkt_solve_matches_dense(handle, pkg, monkeypatch, sn, seed, n, p
         cone.close()
 
 
-@pytest.mark.parametrize("sn", ["1", "0"])
+@pytest.mark.parametrize("sn", ["1", "0", "h3", "h6", "h9"])
 def test_device_kkt_solve_on_the_product_template(handle, pkg, monkeypatch, sn):
     """The bench-shaped KKT (product template with the L1 lowering, stage ordering, N = 24): the device factorisation and
     substitutions agree with the CPU interpreter of the same programs, seed by seed."""
-    monkeypatch.setenv("SCPB_SUPERNODAL", sn)
+    _variant(monkeypatch, sn)
     ex = pkg.examples.starship
     mdl = ex.StarshipProblem(); mdl.hs = 100.0
     traj = pkg.problem.TrajectoryProblem(mdl)
@@ -193,6 +200,8 @@ def test_device_kkt_solve_on_the_product_template(handle, pkg, monkeypatch, sn):
         ref, info = pkg.lib.debug_kkt_solve(A, G, cp["l"], [], pbm.perm, Av[k], Gv[k], wm[k], 1e-9, rhs[k], delta_dyn=1e-12)
         assert bad[k] == 0
         assert np.abs(sol[k] - ref).max() <= 1e-8 * max(1.0, np.abs(ref).max()), (sn, k, np.abs(sol[k] - ref).max())
+    if sn.startswith("h"):   # the hybrid variant really ran (it needs the shared-memory vector, which N = 24 has)
+        assert pbm.cone.info()["hybrid"]["cut_used"] == int(sn[1:]), pbm.cone.info()["hybrid"]
     pbm.close()
 
 

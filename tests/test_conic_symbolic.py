@@ -141,6 +141,13 @@ def test_supernodal_program_on_the_product_template(pkg, monkeypatch):
     scale = max(1.0, np.abs(s1).max())
     assert np.abs(s1 - s2).max() <= 1e-8 * scale
     assert i2["sn_levels"] * 3 <= i1["levels"] and i2["max_rows"] <= 32 and i2["max_width"] <= 10, (i1, i2)
+    # hybrid program: scalar programs below the cut + one bridge level, in-place panels above; same solution, and the
+    # dependent steps (scalar levels + top supernodal levels) stay well below the scalar level count
+    for cut in (3, 6, 9):
+        s3, i3 = pkg.lib.debug_kkt_solve(*args, delta_dyn=1e-7, hybrid_cut=cut)
+        assert np.abs(s1 - s3).max() <= 1e-8 * scale, (cut, np.abs(s1 - s3).max())
+        assert i3["scalar_levels"] == i1["levels"] and i3["levels"] + i3["top_levels"] <= 0.6 * i1["levels"], (cut, i3)
+        assert i3["top_levels"] == i2["sn_levels"] - cut and i3["top_supernodes"] > 0
 
 
 def test_native_rcm_order(pkg):
