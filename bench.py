@@ -342,7 +342,7 @@ def run_ours(args, rank, local_rank, world):
         sampler.start()
     n0 = h.launches
     dev_t, wall_t, ipm, phases = 0.0, 0.0, 0, {"discretize": 0.0, "formulate": 0.0, "solve": 0.0, "overhead": 0.0}
-    its, lock = 0, 0
+    its, lock, k1_init = 0, 0, 0.0
     barrier()
     for _ in range(args.steps):
         l2_flush.zero_(); tc.synchronize()
@@ -356,6 +356,7 @@ def run_ours(args, rank, local_rank, world):
         if loc is not None:
             dev_t += loc.timing["total"]     # CUDA events on the library's stream, H2D/D2H copies and the gather excluded
             ipm += loc.timing["ipm_iterations"]; lock += loc.timing["lockstep_iterations"]
+            k1_init += loc.timing.get("initial_discretize", 0.0)
             for k in phases:
                 phases[k] += loc.timing[k]
     barrier()
@@ -384,8 +385,22 @@ def run_ours(args, rank, local_rank, world):
                     + nsolve * (2 * nnzL + 4 * nk)         # forward+backward substitutions
                     + (2 + 2 * nsolve) * nnzK              # residual / refinement SpMVs (K and K')
                     + 12 * (n_ + p_ + 2 * m_))             # vector updates
-        k_ms = 1e3 * phases["solve"] / max(lock, 1)
-        ach = q_it * ipm / max(phases["solve"], 1e-12) / 1e9
+        nch = int(loc.timing.get("chunks", 0))
+        if nch > 1:
+            # streamed chains: the step is n_chunks concurrent sequences of small k_ipm_solve launches (one CTA per seed
+            # group), so a single launch says nothing about the device.  achieved = algorithmic bytes of ALL launches of the
+            # step / the device time of the whole step (the other kernels of a chain overlap with the solves of the other
+            # chains and cannot be subtracted); kernel_ms / kernel_share are those of chunk 0's own chain
+            ng = -(-Bloc // pbm.cone.info()["group"]) if pbm.cone.info()["group"] else Bloc
+            c0 = min(Bloc, -(-ng // nch) * max(pbm.cone.info()["group"], 1))
+            k_ms = 1e3 * phases["solve"] / max(args.steps * int(loc.iterations[:c0].max()), 1)
+            ach = q_it * ipm / max(dev_t, 1e-12) / 1e9
+            chain = sum(phases.values())
+            k_share = phases["solve"] / max(chain, 1e-12)
+        else:
+            k_ms = 1e3 * phases["solve"] / max(lock, 1)
+            ach = q_it * ipm / max(phases["solve"], 1e-12) / 1e9
+            k_share = phases["solve"] / max(dev_t, 1e-12)
         peak, peak_src = measured_peak()
         traffic = None
         for fn in ("r2_ipm_ncu_summary.json", "r1_ipm_ncu_summary.json"):
@@ -398,6 +413,8 @@ def run_ours(args, rank, local_rank, world):
         ncalls = lock + args.steps                           # one discretize! per lock-step iteration + the initial guess
         w_seed = k1_flops_per_seed(N, Nsub, traj.nx, traj.nu, traj.np)
         k1_s = phases["discretize"] / max(ncalls, 1)
+        if nch > 1:                                          # K1 timed alone: the initial full-batch discretize! of each step
+            k1_s = k1_init / max(args.steps, 1)
         try:
             fp64_peak = h.fp64_peak()
         except Exception:
@@ -407,7 +424,7 @@ def run_ours(args, rank, local_rank, world):
                    "frac": (k1_ach / fp64_peak) if fp64_peak else None, "traffic": None, "kernel": "k_discretize_foh",
                    "kernel_ms": 1e3 * k1_s, "algorithmic_flops_per_seed_per_call": w_seed, "seeds_per_launch": Bloc,
                    "peak_source": "measured in this run (scpb_debug_fp64_peak: register-resident fp64 FMA microkernel)",
-                   "kernel_share_of_step": phases["discretize"] / max(dev_t, 1e-12)}
+                   "kernel_share_of_step": phases["discretize"] / max(sum(phases.values()) if nch > 1 else dev_t, 1e-12)}
         # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ----
         cpu = None
         if world == 1:
@@ -435,8 +452,11 @@ def run_ours(args, rank, local_rank, world):
                            "seeds_solved": int(solved), "seeds_total": Btot,
                            "scp_iterations_per_step": its / args.steps,
                            "scp_iterations_min_median_max": [int(itv.min()), float(np.median(itv)), int(itv.max())],
-                           "lockstep_iterations_per_step_rank0": lock / args.steps,
-                           "frozen_seed_fraction_rank0": 1.0 - (float(loc.iterations.sum()) / max(1, Bloc * (lock / args.steps))),
+                           "longest_chain_iterations_per_step_rank0": lock / args.steps,
+                           "chains_rank0": (f"{nch} chunks of seed groups, each its own stream and PTR sequence (no lock-step)"
+                                            if nch > 1 else "one lock-step loop over the batch"),
+                           "frozen_seed_fraction_rank0": (None if nch > 1 else
+                                                          1.0 - (float(loc.iterations.sum()) / max(1, Bloc * (lock / args.steps)))),
                            "l2": "256 MiB buffer written between timed steps; solver working set (1.1 GB for 256 seeds) >> L2"},
                 "gpu_launches": int(ln[0]),
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": nb_in,
@@ -448,7 +468,10 @@ def run_ours(args, rank, local_rank, world):
                              "traffic": traffic, "peak_source": peak_src, "kernel": "k_ipm_solve",
                              "kernel_ms": k_ms, "algorithmic_bytes_per_ipm_iteration_per_seed": q_it,
                              "ipm_iterations_per_launch": ipm / max(lock, 1), "ldl_solves_per_ipm_iteration": nsolve,
-                             "kernel_share_of_step": phases["solve"] / max(dev_t, 1e-12),
+                             "kernel_share_of_step": k_share,
+                             "accounting": ("streamed chains: achieved = bytes of all launches of the step / device time of the "
+                                            "step; kernel_ms, kernel_share_of_step and phase_seconds_per_step are those of "
+                                            "chunk 0's chain") if nch > 1 else "lock-step: per launch",
                              "kernel_cycle_shares": {k: v / max(cyc["total"], 1) for k, v in cyc.items()
                                                      if k not in ("total", "ldl_count", "factor_count", "factor_retries")}},
                 "roofline_k1": roof_k1,

@@ -186,8 +186,12 @@ int32_t scpb_ptr_free(scpb_ptr s);
 /* host arrays: initial guesses xd0[B][N][nx], ud0[B][N][nu], p0[B][np]; outputs the final iterates, per-seed
  * status (0 = stopping criterion met, 1 = iter_max reached [the reference still reports SCP_SOLVED],
  * 2+16*cone_status = SCP_FAILED), iteration counts, J_aug, deviation, dynamic feasibility flags and
- * timing[8] = {discretize, formulate, solve, overhead, total seconds, lock-step iterations,
- * interior-point iterations summed over seeds and subproblems, 0}. */
+ * timing[10] = {discretize, formulate, solve, overhead, total seconds, longest PTR chain (iterations),
+ * interior-point iterations summed over seeds and subproblems, number of seed chunks, seconds of the initial
+ * full-batch discretize!, 0}.  The batch is cut into chunks of whole seed groups and every chunk runs its own sequence of
+ * PTR iterations on its own CUDA stream (seeds are independent; SCPB_PTR_CHUNKS=<n> sets the number of chunks, default 64,
+ * 0 or 1 = one lock-step loop over the whole batch): the four phase times are then those of chunk 0's chain, the total is
+ * the whole call. */
 int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *ud0, const double *p0,
                        const scpb_cone_opts *opts, double *xd, double *ud, double *p, int32_t *status,
                        int32_t *iters, double *J, double *deviation, int32_t *feas, double *timing);

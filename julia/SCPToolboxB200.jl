@@ -123,6 +123,7 @@ end
 # xd0[nx,N,B], ud0[nu,N,B], p0[np,B] in Julia's column-major layout are exactly the (B,N,nx) row-major arrays of the C ABI
 function ptr_solve(h::Handle, ptr, B, xd0, ud0, p0, opts::ConeOpts, xd, ud, p, status::Vector{Int32}, iters::Vector{Int32},
                    J::Vector{Float64}, dev::Vector{Float64}, feas::Vector{Int32}, timing::Vector{Float64})
+    length(timing) >= 10 || throw(ArgumentError("timing needs 10 entries (include/scpb.h)"))
     check(h, ccall((:scpb_ptr_solve, libscpb), Int32,
         (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{ConeOpts}, Ptr{Float64}, Ptr{Float64},
          Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}),

@@ -137,11 +137,17 @@ static int cone_reserve(scpb_cone_s *c, int B, int G)
 }
 
 // run the solver on the data currently in the grouped buffers (device-resident entry, internal API)
-int scpb_internal_cone_run(scpb_cone_s *c, const IpmOpts &o, const int *skip)
+// `st` (nullptr: the handle's stream) and the chunk [g0, g0 + ngc) of seed groups (ngc = 0: all groups) let the caller run
+// independent chunks of a batch on different streams (ptr.cu)
+int scpb_internal_cone_run(scpb_cone_s *c, const IpmOpts &o, const int *skip, cudaStream_t st, int g0, int ngc)
 {
     c->D.skip = skip;
     scpb_handle_s *h = c->h;
-    const int ng = (c->D.B + c->D.G - 1) / c->D.G;
+    if (!st) st = h->stream;
+    const int ng_all = (c->D.B + c->D.G - 1) / c->D.G;
+    const int ng = ngc > 0 ? (g0 + ngc <= ng_all ? ngc : ng_all - g0) : ng_all;
+    if (ng <= 0) return SCPB_OK;
+    c->D.g0 = ngc > 0 ? g0 : 0;
     // dynamic shared memory: level pointers (+ the substitution vector when nk*G doubles fit next to the
     // ~20 KB of static shared memory; B200 allows 227 KB per CTA)
     size_t smem = sizeof(int) * ((9 * (size_t)(c->S.nlevels + 1) + 3) & ~(size_t)3);
@@ -172,14 +178,14 @@ int scpb_internal_cone_run(scpb_cone_s *c, const IpmOpts &o, const int *skip)
             if (cudaMalloc((void **)&c->d_trace, sizeof(double) * 10 * (size_t)rows) == cudaSuccess) c->trace_rows = rows;
         }
         if (c->d_trace) {
-            cudaMemsetAsync(c->d_trace, 0, sizeof(double) * 10 * (size_t)c->trace_rows, h->stream);
+            cudaMemsetAsync(c->d_trace, 0, sizeof(double) * 10 * (size_t)c->trace_rows, st);
             c->D.trace = c->d_trace; c->D.trace_seed = atoi(e);
         }
     }
 #define SCPB_LAUNCH_IPM(NT_, SN_)                                                                                        \
     {                                                                                                                    \
         SCPB_CUDA(h, cudaFuncSetAttribute(k_ipm_solve<NT_, SN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_ipm_solve<NT_, SN_><<<ng, NT_, smem, h->stream>>>(Pl, c->D, o);                                                \
+        k_ipm_solve<NT_, SN_><<<ng, NT_, smem, st>>>(Pl, c->D, o);                                                       \
     }
     if (o.threads >= 1024) { if (c->D.sn) SCPB_LAUNCH_IPM(1024, 1) else if (hy) SCPB_LAUNCH_IPM(1024, 2) else SCPB_LAUNCH_IPM(1024, 0) }
     else { if (c->D.sn) SCPB_LAUNCH_IPM(512, 1) else if (hy) SCPB_LAUNCH_IPM(512, 2) else SCPB_LAUNCH_IPM(512, 0) }
@@ -206,7 +212,11 @@ IpmOpts scpb_internal_make_opts(const scpb_cone_opts *o)
     r.equil = (o && o->equil >= 0) ? o->equil : 5;
     r.threads = (o && o->threads > 0) ? o->threads : 1024;
     r.nref_aff = 0;
-    r.reftol = 1e-13;
+    // iterative refinement stops at |residual| <= reftol (1 + |rhs|): two digits below the requested feasibility, inside
+    // [1e-13, 1e-11].  At ECOS' default 1e-8 that is 1e-11 -- measured on the bench: 2.06 instead of 2.19 LDL' solves per
+    // interior-point iteration, the same iteration counts, -13 % solve time (profiles/r2_experiments.md); the 1e-11
+    // parity runs keep 1e-13
+    r.reftol = fmin(1e-11, fmax(1e-13, 1e-2 * r.feastol));
     if (const char *e = getenv("SCPB_REFTOL")) { const double v = atof(e); if (v > 0) r.reftol = v; }   // experiments
     return r;
 }
@@ -378,7 +388,7 @@ int32_t scpb_debug_kkt_solve_dev(scpb_cone c, int32_t B, const double *Avals, co
     oo.delta = delta;
     IpmOpts o = scpb_internal_make_opts(&oo);
     c->D.debug_kkt = 1;
-    rc = scpb_internal_cone_run(c, o, nullptr);
+    rc = scpb_internal_cone_run(c, o, nullptr, nullptr, 0, 0);
     c->D.debug_kkt = 0;
     if (rc) return rc;
     k_from_grouped<<<(unsigned)(((long long)nk * B + 255) / 256), 256, 0, st>>>(c->D.rhs, c->stage, nk, B, G);
@@ -450,7 +460,7 @@ int32_t scpb_cone_solve(scpb_cone c, int32_t B, const double *Avals, const doubl
         return rc;
     IpmOpts o = scpb_internal_make_opts(opts);
     SCPB_CUDA(h, cudaEventRecord(h->ev0, st));
-    rc = scpb_internal_cone_run(c, o, nullptr);
+    rc = scpb_internal_cone_run(c, o, nullptr, nullptr, 0, 0);
     if (rc) return rc;
     SCPB_CUDA(h, cudaEventRecord(h->ev1, st));
     auto get = [&](double *dst, const double *src, size_t E) -> int {

@@ -55,6 +55,7 @@ struct IpmOpts {
 
 struct IpmData {  // group-blocked device arrays, all for B seeds
     int B, G, R;   // R: lanes per sparse row (power of two, G*R <= 32)
+    int g0;        // first seed group of this launch (a launch may cover a chunk of the groups; CTA i works on group g0 + i)
     // problem data
     double *Av, *Gv, *c, *b, *h;  // equilibrated in place by the solver
     // iterates
@@ -1079,7 +1080,7 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
     __syncthreads();
     c.red = s_red; c.out = s_out;
     const int G = c.G, sg = c.sg;
-    const size_t g = blockIdx.x;
+    const size_t g = (size_t)blockIdx.x + D.g0;
     const int seed = (int)g * G + sg;
     const bool live = seed < D.B;  // padded seeds replicate work harmlessly (arrays are padded)
     (void)live;

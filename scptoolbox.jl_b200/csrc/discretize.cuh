@@ -50,6 +50,7 @@ struct DiscArgs {
     double *dnorm;          // [B][N-1]  ||iSx*defect||_inf per segment
     int *status;            // device word, OR-ed with 1 on a singular pivot
     const int *skip;        // nullable [B]: seeds marked non-zero are left untouched (SCP seeds that have stopped)
+    int b0 = 0, nb = 0;     // chunk of seeds [b0, b0 + nb) this launch works on (nb = 0: all B); arrays stay indexed by seed
     ModelPar par;
 };
 
@@ -74,8 +75,9 @@ __global__ void __launch_bounds__(128) k_discretize_foh(const DiscArgs a)
     const int wib = threadIdx.x >> 5;
     const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nseg = a.N - 1;
-    if (gw >= (long long)a.B * nseg) return;
-    const int b = (int)(gw / nseg), k = (int)(gw % nseg);
+    if (gw >= (long long)(a.nb > 0 ? a.nb : a.B) * nseg) return;
+    const int b = a.b0 + (int)(gw / nseg), k = (int)(gw % nseg);
+    if (b >= a.B) return;
     if (a.skip && a.skip[b]) return;     // warp-uniform: the whole warp works on seed b
     double *Q = smem + wib * QSZ;
 
@@ -328,9 +330,12 @@ __global__ void __launch_bounds__(128) k_discretize_foh(const DiscArgs a)
 }
 
 // feas[b] = all_k !(dnorm[b][k] > feas_tol)   (NaN compares false, as in the reference)
-static __global__ void k_feas_reduce(const double *dnorm, int B, int nseg, double feas_tol, int *feas, const int *skip)
+static __global__ void k_feas_reduce(const double *dnorm, int B, int nseg, double feas_tol, int *feas, const int *skip,
+                                     int b0 = 0, int nb = 0)
 {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (nb > 0 ? nb : B)) return;
+    const int b = b0 + q;
     if (b >= B) return;
     if (skip && skip[b]) return;
     int ok = 1;

@@ -18,14 +18,14 @@
 
 // pieces of conic_api.cu used here
 struct scpb_cone_s;
-int scpb_internal_cone_run(scpb_cone_s *c, const IpmOpts &o, const int *skip);
+int scpb_internal_cone_run(scpb_cone_s *c, const IpmOpts &o, const int *skip, cudaStream_t st, int g0, int ngc);
 int scpb_internal_cone_reserve(scpb_cone_s *c, int B, int G, int lanes);
 IpmData *scpb_internal_cone_data(scpb_cone_s *c);
 const ConeSymbolic *scpb_internal_cone_sym(scpb_cone_s *c);
 scpb_handle_s *scpb_internal_cone_handle(scpb_cone_s *c);
 IpmOpts scpb_internal_make_opts(const scpb_cone_opts *o);
 int scpb_internal_pick_group(int B, int want);
-int scpb_internal_discretize(scpb_handle_s *h, DiscArgs &a, double feas_tol, int *feas, int method);
+int scpb_internal_discretize(scpb_handle_s *h, DiscArgs &a, double feas_tol, int *feas, int method, cudaStream_t st);
 
 struct PtrDev {
     int B, G, N, nx, nu, np, ns;
@@ -37,6 +37,7 @@ struct PtrDev {
     int oeta = 0;
     const double *lam = nullptr;   // GuSTO: per-seed soft-penalty weight lambda, written to source olam (gusto.jl:228)
     int olam = 0;
+    int b0 = 0, nb = 0;            // chunk of seeds [b0, b0 + nb) of this launch (nb = 0: all B)
 };
 
 __device__ __forceinline__ size_t gaddr(int b, int G, long long E, long long e)
@@ -49,8 +50,9 @@ template <class CP>
 __global__ void k_linearize(const PtrDev d, const double *xd, const double *ud, const double *p)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)d.B * d.N) return;
-    const int b = (int)(i / d.N), k = (int)(i % d.N);
+    if (i >= (long long)(d.nb > 0 ? d.nb : d.B) * d.N) return;
+    const int b = d.b0 + (int)(i / d.N), k = (int)(i % d.N);
+    if (b >= d.B) return;
     const double *x = xd + ((size_t)b * d.N + k) * d.nx, *u = ud + ((size_t)b * d.N + k) * d.nu, *pp = p + (size_t)b * d.np;
     const int G = d.G;
     const long long E = d.nsrc;
@@ -78,6 +80,7 @@ __global__ void k_linearize(const PtrDev d, const double *xd, const double *ud, 
 
 struct AsmDev {
     int B, G, nsrc, nval, nnzA, nnzG, n, p, m;
+    int b0 = 0, nbp = 0;   // chunk of whole seed groups [b0, b0 + nbp) of this launch (nbp = 0: all padded seeds)
     const int *W_rp, *W_ci;
     const double *W_v;
     const double *src;
@@ -88,9 +91,9 @@ struct AsmDev {
 __global__ void k_assemble(const AsmDev a)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int Bp = ((a.B + a.G - 1) / a.G) * a.G;
+    const int Bp = a.nbp > 0 ? a.nbp : ((a.B + a.G - 1) / a.G) * a.G;
     if (i >= (long long)a.nval * Bp) return;
-    const int sd = (int)(i % Bp);
+    const int sd = a.b0 + (int)(i % Bp);
     long long e = i / Bp;
     const int G = a.G, gq = sd / G, sg = sd % G;
     const double *s = a.src + (size_t)gq * a.nsrc * G + sg;
@@ -108,6 +111,9 @@ __global__ void k_assemble(const AsmDev a)
 
 struct StepDev {
     int B, G, N, nx, nu, np, n, vx, vu, vp, iter, q_exit;  // q_exit: 0 = Inf, 1, 2
+    int b0 = 0, nb = 0;                                     // chunk of seeds [b0, b0 + nb) of this launch (nb = 0: all B)
+    const int *cone_iters = nullptr;                        // streamed loop: interior-point iterations of the last solve ...
+    unsigned long long *ipm_total = nullptr;                // ... summed over the live seeds into this device counter
     double eps_abs, eps_rel;
     const double *Sx, *cx, *Su, *cu, *Sp, *cp;
     const double *xsol;       // grouped solver x (scaled variables)
@@ -124,8 +130,9 @@ struct StepDev {
 __global__ void k_extract(const StepDev d)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)d.B * d.N) return;
-    const int b = (int)(i / d.N), k = (int)(i % d.N);
+    if (i >= (long long)(d.nb > 0 ? d.nb : d.B) * d.N) return;
+    const int b = d.b0 + (int)(i / d.N), k = (int)(i % d.N);
+    if (b >= d.B) return;
     const bool frozen = d.done[b] != 0;
     const int G = d.G;
     for (int j = 0; j < d.nx; j++) {
@@ -154,9 +161,12 @@ __device__ __forceinline__ double qnorm_acc(double acc, double v, int q)
 // one thread per seed: deviation, predicted improvement, stopping rule, acceptance (ptr.jl:908-932, 509)
 __global__ void k_ptr_step(const StepDev d)
 {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int q_ = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q_ >= (d.nb > 0 ? d.nb : d.B)) return;
+    const int b = d.b0 + q_;
     if (b >= d.B) return;
     if (d.done[b]) return;
+    if (d.ipm_total) atomicAdd(d.ipm_total, (unsigned long long)d.cone_iters[b]);
     const int cs = d.cone_status[b];
     if (!(cs == IPM_OPTIMAL || cs == IPM_ALMOST)) {  // unsafe_solution, scp.jl:965-980
         d.done[b] = 1; d.status[b] = 2 + 16 * cs; d.iters[b] = d.iter;
@@ -223,6 +233,9 @@ struct scpb_ptr_s {
     double *Q_w = nullptr;
     double *lam = nullptr, *nodeq = nullptr;
     int *nodef = nullptr;
+    // streamed PTR loop (scpb_ptr_solve): one stream per chunk of seed groups, device counter of interior-point iterations
+    std::vector<cudaStream_t> chunk_streams;
+    unsigned long long *d_ipm_total = nullptr;
 };
 
 // the handle may have been pointed at another model pack since scpb_ptr_setup (several problems can share one handle):
@@ -334,7 +347,7 @@ static OutView grouped(double *src, int G, long long nsrc, long long off, long l
 }
 
 static int run_discretize(scpb_ptr_s *s, int B, int G, const double *xd, const double *ud, const double *p,
-                          double *srcbuf = nullptr, const int *skip = nullptr)
+                          double *srcbuf = nullptr, const int *skip = nullptr, cudaStream_t st = nullptr, int b0 = 0, int nb = 0)
 {
     double *sb = srcbuf ? srcbuf : s->src;
     const scpb_ptr_desc &d = s->d;
@@ -347,6 +360,7 @@ static int run_discretize(scpb_ptr_s *s, int B, int G, const double *xd, const d
     a.psB = d.np; a.psE = 1;
     a.f_packed = 1;
     a.skip = skip;     // seeds that have stopped keep their DLTV blocks, defects and feasibility flag
+    a.b0 = b0; a.nb = nb;
     const long long nx = d.nx, nu = d.nu;
     a.A = grouped(sb, G, d.nsrc, d.oA, nx * nx);
     a.Bm = grouped(sb, G, d.nsrc, d.oBm, nx * nu);
@@ -356,7 +370,7 @@ static int run_discretize(scpb_ptr_s *s, int B, int G, const double *xd, const d
     a.E = grouped(sb, G, d.nsrc, d.oE, nx * nx);
     OutView df{}; df.ptr = s->defect; df.Gq = 1; df.sGrp = (long long)(d.N - 1) * nx; df.sB = 0; df.sK = nx; df.sE = 1;
     a.defect = df;
-    return scpb_internal_discretize(s->h, a, d.feas_tol, s->feas, SCPB_FOH);
+    return scpb_internal_discretize(s->h, a, d.feas_tol, s->feas, SCPB_FOH, st);
 }
 
 
@@ -765,6 +779,8 @@ int32_t scpb_ptr_free(scpb_ptr s)
     cudaStreamSynchronize(s->h->stream);
     for (void *q : s->dev) if (q) cudaFree(q);
     for (void *q : s->bb) if (q) cudaFree(q);
+    for (cudaStream_t q : s->chunk_streams) if (q) cudaStreamDestroy(q);
+    if (s->d_ipm_total) cudaFree(s->d_ipm_total);
     delete s;
     return SCPB_OK;
 }
@@ -833,6 +849,77 @@ int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *u
     const int Bpad = s->capB;
     int it = 1, nact = B, total_it = 0;
     long long ipm_iters = 0;
+    // ---- streamed chains (default): seeds are independent, so the batch is cut into chunks of whole seed groups and every
+    // chunk runs ITS OWN sequence of iter_max PTR iterations on its own stream, with no host synchronisation in between: a
+    // finished seed turns its share of every later kernel into a no-op (skip masks), a finished chunk costs a few empty
+    // launches.  In lock-step every solver launch lasts as long as the slowest of ALL seeds (measured on the bench:
+    // median 37, max 73 interior-point iterations in the later subproblems); streamed, a chunk only waits for its own seeds
+    // and the batch takes max-over-chunks of the sums instead of the sum of the maxima.  SCPB_PTR_CHUNKS=<n> sets the
+    // number of chunks (default 64 <= concurrent-kernel limit; 0 or 1 = lock-step loop below, which also serves the
+    // SCPB_IPM_STATS diagnostic).
+    int max_chunks = 64;
+    if (const char *e = getenv("SCPB_PTR_CHUNKS")) max_chunks = atoi(e);
+    const int ng_all = (B + G - 1) / G;
+    int n_chunks = 0;
+    if (max_chunks > 1 && ng_all >= 2 && !getenv("SCPB_IPM_STATS")) {
+        const int cg = (ng_all + max_chunks - 1) / max_chunks;   // seed groups per chunk
+        n_chunks = (ng_all + cg - 1) / cg;
+        while ((int)s->chunk_streams.size() < n_chunks) {
+            cudaStream_t q = nullptr;
+            SCPB_CUDA(h, cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+            s->chunk_streams.push_back(q);
+        }
+        if (!s->d_ipm_total) SCPB_CUDA(h, cudaMalloc((void **)&s->d_ipm_total, sizeof(unsigned long long)));
+        SCPB_CUDA(h, cudaMemsetAsync(s->d_ipm_total, 0, sizeof(unsigned long long), st));
+        sd.cone_iters = D->iters; sd.ipm_total = s->d_ipm_total;
+        EventList sync_ev;   // fork / join events (no timing)
+        auto sync_event = [&]() { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); sync_ev.ev.push_back(e); return e; };
+        cudaEvent_t e_fork = sync_event();
+        SCPB_CUDA(h, cudaEventRecord(e_fork, st));
+        for (int c = 0; c < n_chunks; c++) SCPB_CUDA(h, cudaStreamWaitEvent(s->chunk_streams[c], e_fork, 0));
+        auto mark0 = [&](int ph) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s->chunk_streams[0]); ev.push_back(e); phase.push_back(ph); };
+        mark0(-1);   // chunk 0 carries the phase timers: its own chain is one of the n_chunks concurrent critical paths
+        for (it = 1; it <= d.iter_max; it++) {
+            for (int c = 0; c < n_chunks; c++) {
+                cudaStream_t cs = s->chunk_streams[c];
+                const int b0 = c * cg * G;
+                const int nbp = std::min(cg * G, Bpad - b0), nb = std::min(nbp, B - b0);
+                if (nb <= 0) continue;
+                const int nbn_c = (int)(((long long)nb * d.N + 127) / 128);
+                pd.b0 = b0; pd.nb = nb;
+                launch_linearize(s, pd, nbn_c, cs);
+                ad.b0 = b0; ad.nbp = nbp;
+                k_assemble<<<(unsigned)(((long long)d.nval * nbp + 255) / 256), 256, 0, cs>>>(ad);
+                h->launches += 2;
+                if (c == 0) mark0(1);
+                if ((rc = scpb_internal_cone_run(s->cone, o, s->done, cs, b0 / G, nbp / G))) return rc;
+                if (c == 0) mark0(2);
+                sd.iter = it; sd.b0 = b0; sd.nb = nb;
+                k_extract<<<nbn_c, 128, 0, cs>>>(sd);
+                h->launches++;
+                if (c == 0) mark0(3);
+                if ((rc = run_discretize(s, B, G, s->xn, s->un, s->pn, nullptr, s->done, cs, b0, nb))) return rc;
+                if (c == 0) mark0(0);
+                k_ptr_step<<<(nb + 127) / 128, 128, 0, cs>>>(sd);
+                h->launches++;
+                if (c == 0) mark0(3);
+            }
+        }
+        for (int c = 0; c < n_chunks; c++) {   // join
+            cudaEvent_t e = sync_event();
+            SCPB_CUDA(h, cudaEventRecord(e, s->chunk_streams[c]));
+            SCPB_CUDA(h, cudaStreamWaitEvent(st, e, 0));
+        }
+        mark(); phase.push_back(-1);
+        unsigned long long tot_ipm = 0;
+        SCPB_CUDA(h, cudaMemcpyAsync(&tot_ipm, s->d_ipm_total, sizeof tot_ipm, cudaMemcpyDeviceToHost, st));
+        std::vector<int> hiters(B);
+        SCPB_CUDA(h, cudaMemcpyAsync(hiters.data(), s->iters, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+        SCPB_CUDA(h, cudaStreamSynchronize(st));
+        ipm_iters = (long long)tot_ipm;
+        for (int b = 0; b < B; b++) total_it = std::max(total_it, hiters[b]);   // the longest chain
+        it = d.iter_max + 1;   // skip the lock-step loop
+    }
     std::vector<int> hit(B), hdone(B, 0);   // hdone: seeds that were already finished when the solver was launched (skipped)
     for (; it <= d.iter_max; it++) {
         launch_linearize(s, pd, nbn, st);
@@ -840,7 +927,7 @@ int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *u
         k_assemble<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ad);
         h->launches += 2;
         mark(); phase.push_back(1);
-        if ((rc = scpb_internal_cone_run(s->cone, o, s->done))) return rc;
+        if ((rc = scpb_internal_cone_run(s->cone, o, s->done, nullptr, 0, 0))) return rc;
         mark(); phase.push_back(2);
         SCPB_CUDA(h, cudaMemcpyAsync(hit.data(), D->iters, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
         sd.iter = it;
@@ -882,7 +969,10 @@ int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *u
     cudaEventElapsedTime(&tot_ms, ev.front(), ev.back());
     if (timing) {
         timing[0] = acc[0]; timing[1] = acc[1]; timing[2] = acc[2]; timing[3] = acc[3];
-        timing[4] = tot_ms * 1e-3; timing[5] = (double)total_it; timing[6] = (double)ipm_iters; timing[7] = 0.0;
+        timing[4] = tot_ms * 1e-3; timing[5] = (double)total_it; timing[6] = (double)ipm_iters; timing[7] = (double)n_chunks;
+        float k1_ms = 0.f;   // the initial full-batch discretize! (K1 timed alone, before the chains fork)
+        cudaEventElapsedTime(&k1_ms, ev[0], ev[1]);
+        timing[8] = k1_ms * 1e-3; timing[9] = 0.0;
     }
     return ptr_check_disc_status(h, "ptr_solve");
 }
@@ -1014,7 +1104,7 @@ int32_t scpb_scvx_solve(scpb_ptr s, int32_t B, const double *xd0, const double *
         k_assemble<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ad);
         h->launches += 2;
         mark(); phase.push_back(1);
-        if ((rc = scpb_internal_cone_run(s->cone, o, s->done))) return rc;
+        if ((rc = scpb_internal_cone_run(s->cone, o, s->done, nullptr, 0, 0))) return rc;
         mark(); phase.push_back(2);
         SCPB_CUDA(h, cudaMemcpyAsync(hit.data(), D->iters, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
         sd.iter = it;
@@ -1195,7 +1285,7 @@ int32_t scpb_gusto_solve(scpb_ptr s, int32_t B, const double *xd0, const double 
         k_assemble<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ad);
         h->launches += 2;
         mark(); phase.push_back(1);
-        if ((rc = scpb_internal_cone_run(s->cone, o, s->done))) return rc;
+        if ((rc = scpb_internal_cone_run(s->cone, o, s->done, nullptr, 0, 0))) return rc;
         mark(); phase.push_back(2);
         SCPB_CUDA(h, cudaMemcpyAsync(hit.data(), D->iters, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
         sd.iter = it;

@@ -11,26 +11,29 @@ static int check_model(scpb_handle_s *h)
 }
 
 template <class M>
-static int launch_disc(scpb_handle_s *h, DiscArgs &a, int method)
+static int launch_disc(scpb_handle_s *h, DiscArgs &a, int method, cudaStream_t st)
 {
     constexpr int QSZ = (M::NU + M::NF + 1) * M::NX;
     const int wpb = 4;
-    const long long warps = (long long)a.B * (a.N - 1);
+    const long long warps = (long long)(a.nb > 0 ? a.nb : a.B) * (a.N - 1);
     const int blocks = (int)((warps + wpb - 1) / wpb);
     const size_t smem = sizeof(double) * QSZ * wpb;
     if (method == SCPB_IMPULSE) {
-        if constexpr (M::IMPULSE) k_discretize_foh<M, 1><<<blocks, wpb * 32, smem, h->stream>>>(a);
+        if constexpr (M::IMPULSE) k_discretize_foh<M, 1><<<blocks, wpb * 32, smem, st>>>(a);
         else return set_err(h, SCPB_ERR_UNSUPPORTED, "model %d has no impulse semantics (IMPULSE discretization)", h->model_id);
     } else {
-        k_discretize_foh<M, 0><<<blocks, wpb * 32, smem, h->stream>>>(a);
+        k_discretize_foh<M, 0><<<blocks, wpb * 32, smem, st>>>(a);
     }
     h->launches++;
     return SCPB_OK;
 }
 
 // Launch K1 (+ the feasibility reduction when feas != nullptr). All pointers are device pointers.
-int scpb_internal_discretize(scpb_handle_s *h, DiscArgs &a, double feas_tol, int *feas, int method)
+// `st`: stream to launch on (nullptr: the handle's); a.b0 / a.nb select a chunk of seeds (ptr.cu runs the SCP chains of
+// different seed chunks on different streams)
+int scpb_internal_discretize(scpb_handle_s *h, DiscArgs &a, double feas_tol, int *feas, int method, cudaStream_t st)
 {
+    if (!st) st = h->stream;
     int rc = check_model(h);
     if (rc) return rc;
     if (method != SCPB_FOH && method != SCPB_IMPULSE) return set_err(h, SCPB_ERR_ARG, "unknown discretization method %d", method);
@@ -42,17 +45,18 @@ int scpb_internal_discretize(scpb_handle_s *h, DiscArgs &a, double feas_tol, int
     if (!dn) return set_err(h, SCPB_ERR_CUDA, "scratch allocation failed");
     a.dnorm = dn;
     switch (h->model_id) {
-    case SCPB_MODEL_DBLINT: rc = launch_disc<Model<SCPB_MODEL_DBLINT>>(h, a, method); break;
-    case SCPB_MODEL_ROCKET: rc = launch_disc<Model<SCPB_MODEL_ROCKET>>(h, a, method); break;
-    case SCPB_MODEL_STARSHIP: rc = launch_disc<Model<SCPB_MODEL_STARSHIP>>(h, a, method); break;
-    case SCPB_MODEL_QUADROTOR: rc = launch_disc<Model<SCPB_MODEL_QUADROTOR>>(h, a, method); break;
-    case SCPB_MODEL_FREEFLYER: rc = launch_disc<Model<SCPB_MODEL_FREEFLYER>>(h, a, method); break;
-    case SCPB_MODEL_RENDEZVOUS2D: rc = launch_disc<Model<SCPB_MODEL_RENDEZVOUS2D>>(h, a, method); break;
+    case SCPB_MODEL_DBLINT: rc = launch_disc<Model<SCPB_MODEL_DBLINT>>(h, a, method, st); break;
+    case SCPB_MODEL_ROCKET: rc = launch_disc<Model<SCPB_MODEL_ROCKET>>(h, a, method, st); break;
+    case SCPB_MODEL_STARSHIP: rc = launch_disc<Model<SCPB_MODEL_STARSHIP>>(h, a, method, st); break;
+    case SCPB_MODEL_QUADROTOR: rc = launch_disc<Model<SCPB_MODEL_QUADROTOR>>(h, a, method, st); break;
+    case SCPB_MODEL_FREEFLYER: rc = launch_disc<Model<SCPB_MODEL_FREEFLYER>>(h, a, method, st); break;
+    case SCPB_MODEL_RENDEZVOUS2D: rc = launch_disc<Model<SCPB_MODEL_RENDEZVOUS2D>>(h, a, method, st); break;
     default: return set_err(h, SCPB_ERR_MODEL, "unknown model id %d", h->model_id);
     }
     if (rc) return rc;
     if (feas) {
-        k_feas_reduce<<<(a.B + 127) / 128, 128, 0, h->stream>>>(dn, a.B, a.N - 1, feas_tol, feas, a.skip);
+        const int cnt = a.nb > 0 ? a.nb : a.B;
+        k_feas_reduce<<<(cnt + 127) / 128, 128, 0, st>>>(dn, a.B, a.N - 1, feas_tol, feas, a.skip, a.b0, a.nb);
         h->launches++;
     }
     SCPB_CUDA(h, cudaGetLastError());
@@ -175,7 +179,7 @@ int32_t scpb_discretize_dev(scpb_handle h, int32_t method, int32_t B, int32_t N,
     a.B = B; a.N = N; a.Nsub = Nsub;
     a.t_grid = t_grid; a.xd = xd; a.ud = ud; a.p = p; a.iSx = iSx_diag;
     julia_views(a, h->nx, h->nu, h->np, A, Bm, Bp, F, r, E, defect);
-    return scpb_internal_discretize(h, a, feas_tol, feas, method);
+    return scpb_internal_discretize(h, a, feas_tol, feas, method, nullptr);
 }
 
 int32_t scpb_discretize(scpb_handle h, int32_t method, int32_t B, int32_t N, int32_t Nsub,
@@ -215,7 +219,7 @@ int32_t scpb_discretize(scpb_handle h, int32_t method, int32_t B, int32_t N, int
     a.t_grid = d_t; a.xd = d_x; a.ud = d_u; a.p = d_p; a.iSx = d_s;
     julia_views(a, h->nx, h->nu, h->np, d_A, d_Bm, d_Bp, d_F, d_r, d_E, d_df);
     SCPB_CUDA(h, cudaEventRecord(h->ev0, st));
-    rc = scpb_internal_discretize(h, a, feas_tol, dfeas, method);
+    rc = scpb_internal_discretize(h, a, feas_tol, dfeas, method, nullptr);
     if (rc) return rc;
     SCPB_CUDA(h, cudaEventRecord(h->ev1, st));
     if (A) SCPB_CUDA(h, cudaMemcpyAsync(A, d_A, sizeof(double) * s_A, cudaMemcpyDeviceToHost, st));

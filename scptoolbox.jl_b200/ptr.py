@@ -417,7 +417,7 @@ def solve(pbm: SCPProblem, guesses=None, **cone_opts) -> SCPBatchSolution:
         setattr(o, k_, v)
     xd, ud, p = np.empty_like(xd0), np.empty_like(ud0), np.empty_like(p0)
     status = np.zeros(B, dtype=np.int32); iters = np.zeros(B, dtype=np.int32); feas = np.zeros(B, dtype=np.int32)
-    J = np.empty(B); dev = np.empty(B); timing = np.zeros(8)
+    J = np.empty(B); dev = np.empty(B); timing = np.zeros(10)
     dp = lambda a: a.ctypes.data_as(lib._dp)
     ip = lambda a: a.ctypes.data_as(lib._ip)
     rc = h.lib.scpb_ptr_solve(pbm.ptr, B, dp(xd0), dp(ud0), dp(p0), C.cast(C.byref(o), C.c_void_p), dp(xd), dp(ud),
@@ -430,7 +430,8 @@ def solve(pbm: SCPProblem, guesses=None, **cone_opts) -> SCPBatchSolution:
         else:
             names.append(f"SCP_FAILED ({lib.CONE_STATUS.get((int(s_) - 2) // 16, '?')})")
     tm = dict(discretize=timing[0], formulate=timing[1], solve=timing[2], overhead=timing[3], total=timing[4],
-              lockstep_iterations=int(timing[5]), ipm_iterations=int(timing[6]))
+              lockstep_iterations=int(timing[5]), ipm_iterations=int(timing[6]), chunks=int(timing[7]),
+              initial_discretize=timing[8])
     return SCPBatchSolution(names, iters, J, pbm.t, xd, ud, p, dev, feas, tm, status)
 
 
