@@ -24,7 +24,7 @@ struct scpb_cone_s {
     IpmData D{};
     double *stage = nullptr;  // seed-major staging on device
     size_t stage_cap = 0;
-    int *d_status = nullptr, *d_iters = nullptr;
+    int *d_status = nullptr, *d_iters = nullptr, *d_warm = nullptr;
     double *d_scal = nullptr;  // pobj, dobj, res[3]
     long long *d_prof = nullptr;
     double *d_trace = nullptr;   // SCPB_IPM_TRACE diagnostic
@@ -83,7 +83,8 @@ static int cone_reserve(scpb_cone_s *c, int B, int G)
     if (c->d_status) cudaFree(c->d_status);
     if (c->d_iters) cudaFree(c->d_iters);
     if (c->d_scal) cudaFree(c->d_scal);
-    c->d_status = nullptr; c->d_iters = nullptr; c->d_scal = nullptr;
+    if (c->d_warm) cudaFree(c->d_warm);
+    c->d_status = nullptr; c->d_iters = nullptr; c->d_scal = nullptr; c->d_warm = nullptr;
     c->capB = 0; c->capG = 0;
     {
         IpmData z{};
@@ -103,6 +104,7 @@ static int cone_reserve(scpb_cone_s *c, int B, int G)
     D.Av = Av; D.Gv = Gv; D.c = cc; D.b = bb; D.h = hh;
     D.x = al(n); D.y = al(p); D.z = al(m); D.s = al(m);
     D.xb = al(n); D.yb = al(p); D.zb = al(m); D.sb = al(m);
+    D.xw = al(n); D.yw = al(p); D.zw = al(m); D.sw = al(m);
     D.eqD = al(n); D.eqA = al(p); D.eqG = al(m);
     D.rx = al(n); D.ry = al(p); D.rz = al(m); D.lam = al(m); D.wm = al(S.nwm); D.socw = al(m - S.l + 1);
     D.soceta = al(S.nsoc + 1);
@@ -113,7 +115,9 @@ static int cone_reserve(scpb_cone_s *c, int B, int G)
     for (double *q : c->bufs) ok = ok && q != nullptr;
     ok = ok && cudaMalloc((void **)&c->d_status, sizeof(int) * Bpad) == cudaSuccess &&
          cudaMalloc((void **)&c->d_iters, sizeof(int) * Bpad) == cudaSuccess &&
-         cudaMalloc((void **)&c->d_scal, sizeof(double) * 5 * Bpad) == cudaSuccess;
+         cudaMalloc((void **)&c->d_scal, sizeof(double) * 5 * Bpad) == cudaSuccess &&
+         cudaMalloc((void **)&c->d_warm, sizeof(int) * Bpad) == cudaSuccess &&
+         cudaMemset(c->d_warm, 0, sizeof(int) * Bpad) == cudaSuccess;
     if (!ok) {
         cudaGetLastError();
         for (double *q : c->bufs) if (q) cudaFree(q);
@@ -121,13 +125,14 @@ static int cone_reserve(scpb_cone_s *c, int B, int G)
         if (c->d_status) cudaFree(c->d_status);
         if (c->d_iters) cudaFree(c->d_iters);
         if (c->d_scal) cudaFree(c->d_scal);
-        c->d_status = nullptr; c->d_iters = nullptr; c->d_scal = nullptr;
+        if (c->d_warm) cudaFree(c->d_warm);
+        c->d_status = nullptr; c->d_iters = nullptr; c->d_scal = nullptr; c->d_warm = nullptr;
         IpmData z{};
         z.R = c->D.R; z.prof = c->D.prof;
         c->D = z;
         return set_err(h, SCPB_ERR_CUDA, "cone solver: device allocation failed (B=%d)", B);
     }
-    D.status = c->d_status; D.iters = c->d_iters;
+    D.status = c->d_status; D.iters = c->d_iters; D.warm = c->d_warm;
     D.pobj = c->d_scal; D.dobj = c->d_scal + Bpad; D.res = c->d_scal + 2 * (size_t)Bpad;
     if (!c->d_prof && cudaMalloc((void **)&c->d_prof, sizeof(long long) * (12 + 3 * (size_t)c->S.nlevels)) != cudaSuccess) c->d_prof = nullptr;
     D.prof = c->d_prof;
@@ -212,6 +217,9 @@ IpmOpts scpb_internal_make_opts(const scpb_cone_opts *o)
     r.equil = (o && o->equil >= 0) ? o->equil : 5;
     r.threads = (o && o->threads > 0) ? o->threads : 1024;
     r.nref_aff = 0;
+    r.warm = 0;              // set per launch by the SCP loops (ptr.cu) from their second iteration on
+    r.mu_warm = 1e-4;
+    if (const char *e = getenv("SCPB_WARM_MU")) { const double v = atof(e); if (v > 0) r.mu_warm = v; }   // experiments
     // iterative refinement stops at |residual| <= reftol (1 + |rhs|): two digits below the requested feasibility, inside
     // [1e-13, 1e-11].  At ECOS' default 1e-8 that is 1e-11 -- measured on the bench: 2.06 instead of 2.19 LDL' solves per
     // interior-point iteration, the same iteration counts, -13 % solve time (profiles/r2_experiments.md); the 1e-11
@@ -415,6 +423,7 @@ int32_t scpb_cone_free(scpb_cone c)
     if (c->stage) cudaFree(c->stage);
     if (c->d_status) cudaFree(c->d_status);
     if (c->d_iters) cudaFree(c->d_iters);
+    if (c->d_warm) cudaFree(c->d_warm);
     if (c->d_scal) cudaFree(c->d_scal);
     if (c->d_prof) cudaFree(c->d_prof);
     if (c->d_trace) cudaFree(c->d_trace);

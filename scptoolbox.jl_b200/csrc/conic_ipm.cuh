@@ -51,6 +51,8 @@ struct IpmOpts {
     int threads;              // CTA size: 512 or 1024
     int nref_aff;             // refinement steps for the predictor (affine) direction
     double reftol;
+    int warm;                 // 1: seeds whose IpmData.warm flag is set start from their stored warm point (see k_ipm_solve)
+    double mu_warm;           // complementarity level (gap / cone degree, equilibrated units) at which the warm point is taken
 };
 
 struct IpmData {  // group-blocked device arrays, all for B seeds
@@ -62,6 +64,10 @@ struct IpmData {  // group-blocked device arrays, all for B seeds
     double *x, *y, *z, *s;
     double *eqD, *eqA, *eqG;     // Ruiz equilibration factors (columns, equality rows, cone rows)
     double *xb, *yb, *zb, *sb;   // best iterate so far (restored when the run ends without reaching the tolerances)
+    double *xw, *yw, *zw, *sw;   // warm point of every seed, in the caller's units: the first iterate of the LAST solve whose
+                                 // complementarity was below IpmOpts.mu_warm -- interior and roughly centred, so the next,
+                                 // slightly different program of the same seed (the next SCP iteration) can start from it
+    int *warm;                   // [B] 1: the warm point of this seed is usable
     // work
     double *rx, *ry, *rz, *lam, *wm, *socw, *soceta;
     double *dx, *dy, *dz, *ds, *dsa, *dza, *tm, *gm, *r1, *r2, *e1, *e2, *rhs, *Y, *Ls, *Lrow, *invD;
@@ -1049,6 +1055,7 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
     __shared__ int s_done[IPM_MAXG], s_status[IPM_MAXG], s_iters[IPM_MAXG], s_alldone, s_save[IPM_MAXG], s_stall[IPM_MAXG];
     __shared__ double s_best[IPM_MAXG], s_bp[IPM_MAXG], s_bd[IPM_MAXG], s_br[3 * IPM_MAXG];
     __shared__ double s_alpha_d[IPM_MAXG];
+    __shared__ int s_warm[IPM_MAXG], s_wsaved[IPM_MAXG], s_wsave[IPM_MAXG], s_allwarm, s_redo;
     __shared__ int s_skip[IPM_MAXG];
     double *const s_delta = ipm_s_delta;
     int *const s_bad = ipm_s_bad;
@@ -1133,6 +1140,8 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
         s_skip[c.tid] = sk; s_done[c.tid] = sk;
         s_status[c.tid] = IPM_MAXIT; s_iters[c.tid] = 0; s_best[c.tid] = CUDART_INF; s_save[c.tid] = 0; s_stall[c.tid] = 0;
         s_delta[c.tid] = O.delta; s_bad[c.tid] = 0;
+        s_warm[c.tid] = (!sk && O.warm && D.warm && D.warm[sd]) ? 1 : 0;
+        s_wsaved[c.tid] = 0; s_wsave[c.tid] = 0;
     }
     __syncthreads();
     {
@@ -1184,55 +1193,81 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
         }
         __syncthreads();
     }
-    // ---- starting point (CVXOPT conelp 7.1 / ECOS init): factor with W = I ----
-    set_identity_scaling(P, c, wm, socw, soceta);
-    __syncthreads();
-    IPM_FACTOR()
-    // solve 1: [0;b;h] -> x, s = h - G x
-    for (int v = c.slot; v < P.n; v += c.nslots) r1[GI(v)] = 0.0;
-    __syncthreads();
-    kkt_solve<SN>(P, c, D, Av, Gv, wm, socw, soceta, r1, bb, hh, x, dy, dz, tm, gm, e1, e2, rhs, Ls, invD, O.nref);
-    for (int r = c.slot; r < P.m; r += c.nslots) s[GI(r)] = -dz[GI(r)];
-    __syncthreads();
-    {
-        double vv[1] = {cone_shift_partial(P, c, s)};
-        double w2[1] = {0.0};
-        for (int r = c.slot; r < P.m; r += c.nslots) w2[0] += s[GI(r)] * s[GI(r)];
-        seed_reduce<1>(c, vv, 2);
-        const double ts = s_out[sg];
-        __syncthreads();
-        seed_reduce<1>(c, w2, 0);
-        const double ns = sqrt(s_out[sg]);
-        if (ts >= -1e-8 * fmax(1.0, ns)) {
-            const double sh = 1.0 + ts;
-            for (int r = c.slot; r < P.l; r += c.nslots) s[GI(r)] += sh;
-            for (int k = c.slot; k < P.nsoc; k += c.nslots) s[GI(P.soc_off[k])] += sh;
-        }
-        __syncthreads();
+    // ---- warm start: a seed whose previous solve left a warm point starts from it (converted to this program's
+    // equilibrated units: x/D, y/E_A, z/E_G, s*E_G; cone membership of s and z is unaffected, the scalings are positive and
+    // uniform inside a second-order cone).  If that run does not end OPTIMAL / ALMOST_OPTIMAL / with a certificate, the
+    // whole group is solved again from the cold starting point (restart_cold below).
+    int tried_cold = 0;
+restart_cold:
+    if (c.tid == 0) {
+        int all = 1;
+        for (int q = 0; q < G; q++) all &= (s_warm[q] || s_skip[q]);
+        s_allwarm = all;
     }
-    // solve 2: [-c;0;0] -> y, z
-    for (int v = c.slot; v < P.n; v += c.nslots) r1[GI(v)] = -cc[GI(v)];
-    for (int r = c.slot; r < P.p; r += c.nslots) r2[GI(r)] = 0.0;
-    for (int r = c.slot; r < P.m; r += c.nslots) rz[GI(r)] = 0.0;
     __syncthreads();
-    kkt_solve<SN>(P, c, D, Av, Gv, wm, socw, soceta, r1, r2, rz, dx, y, z, tm, gm, e1, e2, rhs, Ls, invD, O.nref);
-    {
-        double vv[1] = {cone_shift_partial(P, c, z)};
-        double w2[1] = {0.0};
-        for (int r = c.slot; r < P.m; r += c.nslots) w2[0] += z[GI(r)] * z[GI(r)];
-        seed_reduce<1>(c, vv, 2);
-        const double tz = s_out[sg];
+    if (!s_allwarm) {
+        // ---- starting point (CVXOPT conelp 7.1 / ECOS init): factor with W = I ----
+        set_identity_scaling(P, c, wm, socw, soceta);
         __syncthreads();
-        seed_reduce<1>(c, w2, 0);
-        const double nz = sqrt(s_out[sg]);
-        if (tz >= -1e-8 * fmax(1.0, nz)) {
-            const double sh = 1.0 + tz;
-            for (int r = c.slot; r < P.l; r += c.nslots) z[GI(r)] += sh;
-            for (int k = c.slot; k < P.nsoc; k += c.nslots) z[GI(P.soc_off[k])] += sh;
+        IPM_FACTOR()
+        // solve 1: [0;b;h] -> x, s = h - G x
+        for (int v = c.slot; v < P.n; v += c.nslots) r1[GI(v)] = 0.0;
+        __syncthreads();
+        kkt_solve<SN>(P, c, D, Av, Gv, wm, socw, soceta, r1, bb, hh, x, dy, dz, tm, gm, e1, e2, rhs, Ls, invD, O.nref);
+        for (int r = c.slot; r < P.m; r += c.nslots) s[GI(r)] = -dz[GI(r)];
+        __syncthreads();
+        {
+            double vv[1] = {cone_shift_partial(P, c, s)};
+            double w2[1] = {0.0};
+            for (int r = c.slot; r < P.m; r += c.nslots) w2[0] += s[GI(r)] * s[GI(r)];
+            seed_reduce<1>(c, vv, 2);
+            const double ts = s_out[sg];
+            __syncthreads();
+            seed_reduce<1>(c, w2, 0);
+            const double ns = sqrt(s_out[sg]);
+            if (ts >= -1e-8 * fmax(1.0, ns)) {
+                const double sh = 1.0 + ts;
+                for (int r = c.slot; r < P.l; r += c.nslots) s[GI(r)] += sh;
+                for (int k = c.slot; k < P.nsoc; k += c.nslots) s[GI(P.soc_off[k])] += sh;
+            }
+            __syncthreads();
         }
+        // solve 2: [-c;0;0] -> y, z
+        for (int v = c.slot; v < P.n; v += c.nslots) r1[GI(v)] = -cc[GI(v)];
+        for (int r = c.slot; r < P.p; r += c.nslots) r2[GI(r)] = 0.0;
+        for (int r = c.slot; r < P.m; r += c.nslots) rz[GI(r)] = 0.0;
         __syncthreads();
-    }
+        kkt_solve<SN>(P, c, D, Av, Gv, wm, socw, soceta, r1, r2, rz, dx, y, z, tm, gm, e1, e2, rhs, Ls, invD, O.nref);
+        {
+            double vv[1] = {cone_shift_partial(P, c, z)};
+            double w2[1] = {0.0};
+            for (int r = c.slot; r < P.m; r += c.nslots) w2[0] += z[GI(r)] * z[GI(r)];
+            seed_reduce<1>(c, vv, 2);
+            const double tz = s_out[sg];
+            __syncthreads();
+            seed_reduce<1>(c, w2, 0);
+            const double nz = sqrt(s_out[sg]);
+            if (tz >= -1e-8 * fmax(1.0, nz)) {
+                const double sh = 1.0 + tz;
+                for (int r = c.slot; r < P.l; r += c.nslots) z[GI(r)] += sh;
+                for (int k = c.slot; k < P.nsoc; k += c.nslots) z[GI(P.soc_off[k])] += sh;
+            }
+            __syncthreads();
+        }
 
+
+    }
+    if (s_warm[sg]) {
+        const bool eq = O.equil > 0;
+        for (int i = c.slot; i < P.n; i += c.nslots) x[GI(i)] = eq ? D.xw[g * (size_t)P.n * G + GI(i)] / eqD[GI(i)] : D.xw[g * (size_t)P.n * G + GI(i)];
+        for (int i = c.slot; i < P.p; i += c.nslots) y[GI(i)] = eq ? D.yw[g * (size_t)P.p * G + GI(i)] / eqA[GI(i)] : D.yw[g * (size_t)P.p * G + GI(i)];
+        for (int i = c.slot; i < P.m; i += c.nslots) {
+            const double e_ = eq ? eqG[GI(i)] : 1.0;
+            z[GI(i)] = D.zw[g * (size_t)P.m * G + GI(i)] / e_;
+            s[GI(i)] = D.sw[g * (size_t)P.m * G + GI(i)] * e_;
+        }
+    }
+    __syncthreads();
     PROF(1)
     const double deg = (double)(P.l + P.nsoc);
     for (int it = 0; it <= O.maxit; it++) {
@@ -1277,6 +1312,10 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
             const double relgap = gap / fmax(fmax(fabs(pcost), fabs(dcost)), 1.0);
             s_mu[q] = gap / deg;
             s_save[q] = 0;
+            s_wsave[q] = 0;
+            if (!s_done[q] && !s_wsaved[q] && D.warm && isfinite(pres) && isfinite(dres) && gap >= 0.0 && gap / deg <= O.mu_warm) {
+                s_wsave[q] = 1; s_wsaved[q] = 1;   // the warm point of the NEXT solve of this seed: first iterate this close to the path's end
+            }
             if (D.trace && (int)g * G + q == D.trace_seed && !s_done[q]) {   // it, pres, dres, gap, pcost, dcost, last steps, delta, sigma*mu
                 double *tr_ = D.trace + 10 * (size_t)it;
                 tr_[0] = it; tr_[1] = pres; tr_[2] = dres; tr_[3] = gap; tr_[4] = pcost; tr_[5] = dcost;
@@ -1310,6 +1349,16 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
             for (int i = c.slot; i < P.n; i += c.nslots) xb[GI(i)] = x[GI(i)];
             for (int i = c.slot; i < P.p; i += c.nslots) yb[GI(i)] = y[GI(i)];
             for (int i = c.slot; i < P.m; i += c.nslots) { zb[GI(i)] = z[GI(i)]; sb[GI(i)] = s[GI(i)]; }
+        }
+        if (s_wsave[sg]) {   // in the caller's units (the next program is equilibrated differently)
+            const bool eq = O.equil > 0;
+            for (int i = c.slot; i < P.n; i += c.nslots) D.xw[g * (size_t)P.n * G + GI(i)] = eq ? x[GI(i)] * eqD[GI(i)] : x[GI(i)];
+            for (int i = c.slot; i < P.p; i += c.nslots) D.yw[g * (size_t)P.p * G + GI(i)] = eq ? y[GI(i)] * eqA[GI(i)] : y[GI(i)];
+            for (int i = c.slot; i < P.m; i += c.nslots) {
+                const double e_ = eq ? eqG[GI(i)] : 1.0;
+                D.zw[g * (size_t)P.m * G + GI(i)] = z[GI(i)] * e_;
+                D.sw[g * (size_t)P.m * G + GI(i)] = s[GI(i)] / e_;
+            }
         }
         __syncthreads();
         if (c.tid == 0) {
@@ -1423,6 +1472,28 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
         D.prof[8] = c.t_fw; D.prof[9] = c.t_bw; D.prof[10] = c.t_ldl_n; D.prof[11] = n_fact | (n_retry << 32);
     }
 #undef PROF
+    // ---- a warm-started seed that did not reach the tolerances: the group starts again from the cold starting point ----
+    __syncthreads();
+    if (c.tid == 0) {
+        int redo = 0;
+        if (!tried_cold)
+            for (int q = 0; q < G; q++)
+                if (s_warm[q] && !s_skip[q] && s_status[q] != IPM_OPTIMAL && s_status[q] != IPM_PINF && s_status[q] != IPM_DINF &&
+                    !(s_best[q] <= 10.0 * fmax(O.feastol, O.reltol)))
+                    redo = 1;
+        s_redo = redo;
+    }
+    __syncthreads();
+    if (s_redo) {
+        tried_cold = 1;
+        if (c.tid < G) {
+            const int q = c.tid;
+            s_done[q] = s_skip[q]; s_status[q] = IPM_MAXIT; s_iters[q] = 0; s_best[q] = CUDART_INF; s_save[q] = 0; s_stall[q] = 0;
+            s_delta[q] = O.delta; s_bad[q] = 0; s_warm[q] = 0; s_wsaved[q] = 0; s_wsave[q] = 0;
+        }
+        __syncthreads();
+        goto restart_cold;
+    }
     // ---- epilogue: the best iterate is the answer (ECOS reports its best point the same way) ----
     __syncthreads();
     // the numerical floor of the fp64 normal-equation factorisation sits within ~10x of ECOS' 1e-8 targets
@@ -1446,6 +1517,7 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
         const int sd = (int)g * G + c.tid;
         if (sd < D.B && !s_skip[c.tid]) {
             D.status[sd] = s_status[c.tid]; D.iters[sd] = s_iters[c.tid];
+            if (D.warm) D.warm[sd] = (s_wsaved[c.tid] && (s_status[c.tid] == IPM_OPTIMAL || s_status[c.tid] == IPM_ALMOST)) ? 1 : 0;
             D.pobj[sd] = s_bp[c.tid]; D.dobj[sd] = s_bd[c.tid];
             D.res[sd] = s_br[c.tid]; D.res[D.B + sd] = s_br[IPM_MAXG + c.tid]; D.res[2 * D.B + sd] = s_br[2 * IPM_MAXG + c.tid];
         }

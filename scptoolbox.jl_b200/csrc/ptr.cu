@@ -204,6 +204,10 @@ __global__ void k_ptr_step(const StepDev d)
 }
 
 // ----------------------------------------------------------------------------------------------
+#ifndef SCPB_PTR_DEFAULT_CHUNKS
+#define SCPB_PTR_DEFAULT_CHUNKS 0   // streamed PTR chains are opt-in (SCPB_PTR_CHUNKS=<n>): see scpb_ptr_solve
+#endif
+
 struct scpb_ptr_s {
     scpb_handle_s *h = nullptr;
     scpb_cone_s *cone = nullptr;
@@ -810,6 +814,7 @@ int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *u
     SCPB_CUDA(h, cudaMemcpyAsync(s->p, p0, sizeof(double) * nP, cudaMemcpyHostToDevice, st));
     SCPB_CUDA(h, cudaMemsetAsync(s->src, 0, sizeof(double) * (size_t)d.nsrc * s->capB, st));
     SCPB_CUDA(h, cudaMemsetAsync(s->done, 0, sizeof(int) * s->capB, st));
+    if (D->warm) SCPB_CUDA(h, cudaMemsetAsync(D->warm, 0, sizeof(int) * s->capB, st));   // warm points of an earlier batch are not this batch's
     SCPB_CUDA(h, cudaMemsetAsync(s->iters, 0, sizeof(int) * s->capB, st));
     std::vector<int> init_status(s->capB, 1);
     SCPB_CUDA(h, cudaMemcpyAsync(s->status, init_status.data(), sizeof(int) * s->capB, cudaMemcpyHostToDevice, st));
@@ -857,7 +862,8 @@ int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *u
     // and the batch takes max-over-chunks of the sums instead of the sum of the maxima.  SCPB_PTR_CHUNKS=<n> sets the
     // number of chunks (default 64 <= concurrent-kernel limit; 0 or 1 = lock-step loop below, which also serves the
     // SCPB_IPM_STATS diagnostic).
-    int max_chunks = 64;
+    const bool no_warm = getenv("SCPB_NO_WARM") != nullptr;
+    int max_chunks = SCPB_PTR_DEFAULT_CHUNKS;
     if (const char *e = getenv("SCPB_PTR_CHUNKS")) max_chunks = atoi(e);
     const int ng_all = (B + G - 1) / G;
     int n_chunks = 0;
@@ -892,7 +898,11 @@ int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *u
                 k_assemble<<<(unsigned)(((long long)d.nval * nbp + 255) / 256), 256, 0, cs>>>(ad);
                 h->launches += 2;
                 if (c == 0) mark0(1);
-                if ((rc = scpb_internal_cone_run(s->cone, o, s->done, cs, b0 / G, nbp / G))) return rc;
+                {
+                    IpmOpts ow = o;
+                    ow.warm = (it > 1 && !no_warm) ? 1 : 0;
+                    if ((rc = scpb_internal_cone_run(s->cone, ow, s->done, cs, b0 / G, nbp / G))) return rc;
+                }
                 if (c == 0) mark0(2);
                 sd.iter = it; sd.b0 = b0; sd.nb = nb;
                 k_extract<<<nbn_c, 128, 0, cs>>>(sd);
@@ -927,7 +937,12 @@ int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *u
         k_assemble<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ad);
         h->launches += 2;
         mark(); phase.push_back(1);
-        if ((rc = scpb_internal_cone_run(s->cone, o, s->done, nullptr, 0, 0))) return rc;
+        {   // from the second subproblem on every seed starts the interior-point method from the warm point its previous
+            // solve stored (the subproblems of consecutive PTR iterations differ little); SCPB_NO_WARM=1 turns it off
+            IpmOpts ow = o;
+            ow.warm = (it > 1 && !no_warm) ? 1 : 0;
+            if ((rc = scpb_internal_cone_run(s->cone, ow, s->done, nullptr, 0, 0))) return rc;
+        }
         mark(); phase.push_back(2);
         SCPB_CUDA(h, cudaMemcpyAsync(hit.data(), D->iters, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
         sd.iter = it;

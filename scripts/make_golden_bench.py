@@ -16,7 +16,7 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 from oracle import problems, ptr as optr  # noqa: E402
 
-N, NSUB, NB, TOL = 100, 100, 8, 1e-11
+N, NSUB, NB, TOL = 100, 100, 8, 1e-12
 
 
 def worker(args):

@@ -261,14 +261,16 @@ def test_bench_configuration_parity(pkg, handle):
     X0, U0, P0 = bench.make_seeds(g, sc.Sx, sc.Su, nb, 0, sc.cx, sc.cu)
     sol = pkg.ptr.solve(pbm, (X0, U0, P0), **TOL)
     pbm.close()
-    # the oracle side (its interior point at 1e-11, ~3 CPU-minutes per seed at N = 100) is a committed fixture
+    # the oracle side (~3 CPU-minutes per seed at N = 100) is a committed fixture, computed with the oracle's interior
+    # point at 1e-12: at 1e-11 the ORACLE is itself 3.7e-6 (inputs) away from its own 1e-12 run on seed 0
+    # (profiles/r2_parity_vs_tolerance.txt), which is what the first version of this test measured against the product
     # (scripts/make_golden_bench.py); it is recomputed here only when the fixture's seeds are not this test's seeds
     gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_ptr_bench_seeds.npz")
     refs = None
     if os.path.exists(gold):
         gd = np.load(gold)
         if (gd["X0"].shape == X0.shape and np.allclose(gd["X0"], X0, rtol=0, atol=1e-12)
-                and np.allclose(gd["U0"], U0, rtol=0, atol=1e-12) and np.allclose(gd["P0"], P0, rtol=0, atol=1e-12) and float(gd["tol"]) == OTOL):
+                and np.allclose(gd["U0"], U0, rtol=0, atol=1e-12) and np.allclose(gd["P0"], P0, rtol=0, atol=1e-12) and float(gd["tol"]) <= OTOL):
             refs = [(str(gd["status"][b]), int(gd["iterations"][b]), gd["xd"][b], gd["ud"][b], gd["p"][b],
                      float(gd["J_aug"][b]), bool(gd["feas"][b])) for b in range(nb)]
     if refs is None:
