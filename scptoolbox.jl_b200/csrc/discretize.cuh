@@ -62,8 +62,11 @@ __device__ __forceinline__ double shfl_d(double v, int src)
 // IMP = 1: IMPULSE discretization (discretization.jl:186-193, 304-340, 384-390): the segment starts from the
 // impulse-updated state x_k + f(t_k, -k, x_k, u_k, p), coasts with u = 0, and B_k = A_k * B(t_k, -k, x_k, u_k, p) (one
 // input block: Bm; Bp is written as zero).  Phi, F, r and E columns are the FOH ones evaluated at u = 0.
-template <class M, int IMP>
-__global__ void __launch_bounds__(128) k_discretize_foh(const DiscArgs a)
+// MB: resident 128-thread blocks per SM the register allocation is held to (2: 255 registers, no spills; 3: 168; 4: 128
+// with a few hundred bytes of spills) -- more warps per scheduler to hide the fixed-latency chains of the stage, chosen
+// by measurement (scpb_api.cu: launch_disc)
+template <class M, int IMP, int MB = 2>
+__global__ void __launch_bounds__(128, MB) k_discretize_foh(const DiscArgs a)
 {
     constexpr int NX = M::NX, NU = M::NU, NF = M::NF, NPD = M::NPD;
     constexpr int C = NX + 2 * NU + NF + 1 + NX;  // columns of [Phi PB- PB+ PF Pr PE]

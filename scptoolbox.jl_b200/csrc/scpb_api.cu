@@ -1,7 +1,12 @@
 // scpb_api.cu -- C ABI entry points (include/scpb.h): lifetime, model selection, discretize.
+#include <cstdlib>
 #include "handle.cuh"
 #include "discretize.cuh"
 #include "propagate.cuh"
+
+#ifndef SCPB_K1_DEFAULT_MB
+#define SCPB_K1_DEFAULT_MB 2   // resident K1 blocks per SM the register allocation targets (SCPB_K1_MB overrides: 2, 3, 4)
+#endif
 
 static int check_model(scpb_handle_s *h)
 {
@@ -22,7 +27,10 @@ static int launch_disc(scpb_handle_s *h, DiscArgs &a, int method, cudaStream_t s
         if constexpr (M::IMPULSE) k_discretize_foh<M, 1><<<blocks, wpb * 32, smem, st>>>(a);
         else return set_err(h, SCPB_ERR_UNSUPPORTED, "model %d has no impulse semantics (IMPULSE discretization)", h->model_id);
     } else {
-        k_discretize_foh<M, 0><<<blocks, wpb * 32, smem, st>>>(a);
+        static const int mb = [] { const char *e = getenv("SCPB_K1_MB"); return e ? atoi(e) : SCPB_K1_DEFAULT_MB; }();
+        if (mb == 3) k_discretize_foh<M, 0, 3><<<blocks, wpb * 32, smem, st>>>(a);
+        else if (mb == 4) k_discretize_foh<M, 0, 4><<<blocks, wpb * 32, smem, st>>>(a);
+        else k_discretize_foh<M, 0, 2><<<blocks, wpb * 32, smem, st>>>(a);
     }
     h->launches++;
     return SCPB_OK;

@@ -9,7 +9,8 @@ N, Nsub, B = 100, 100, int(os.environ.get("B", "256"))
 h = pkg.Handle(0)
 ex = pkg.examples.starship
 mdl = ex.StarshipProblem(); traj = pkg.problem.TrajectoryProblem(mdl); ex.define_problem(traj, "ptr", handle=h)
-pars = pkg.ptr.Parameters(N=N, Nsub=Nsub, disc_method=pkg.ptr.FOH, q_tr=np.inf, q_exit=np.inf, **bench.PTR)
+PT = dict(bench.PTR); PT["iter_max"] = int(os.environ.get("ITER_MAX", str(PT["iter_max"])))
+pars = pkg.ptr.Parameters(N=N, Nsub=Nsub, disc_method=pkg.ptr.FOH, q_tr=np.inf, q_exit=np.inf, **PT)
 pbm = pkg.ptr.create(pars, traj, h)
 X, U, Pp = bench.make_seeds(traj.guess(N), pbm.scale.Sx, pbm.scale.Su, B, 0, pbm.scale.cx, pbm.scale.cu)
 ref = None
@@ -25,7 +26,7 @@ for ch in sys.argv[1:]:
         if best is None or sol.timing["total"] < best.timing["total"]:
             best = sol
     sol = best
-    out = dict(chunks=ch, warm=("SCPB_NO_WARM" not in os.environ), conn=os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"), total_s=round(sol.timing["total"], 4),
+    out = dict(k1_mb=os.environ.get("SCPB_K1_MB"), chunks=ch, warm=("SCPB_NO_WARM" not in os.environ), conn=os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"), total_s=round(sol.timing["total"], 4),
                it_per_s=round(float(sol.iterations.sum()) / sol.timing["total"], 1),
                timing={k: (round(v, 4) if isinstance(v, float) else v) for k, v in sol.timing.items()},
                iters=[int(sol.iterations.min()), float(np.median(sol.iterations)), int(sol.iterations.max())],
