@@ -51,6 +51,7 @@ struct IpmOpts {
     int threads;              // CTA size: 512 or 1024
     int nref_aff;             // refinement steps for the predictor (affine) direction
     double reftol;
+    double mu_tight;          // below this complementarity (gap / cone degree) the refinement tolerance is 1e-13 whatever reftol says
     int warm;                 // 1: seeds whose IpmData.warm flag is set start from their stored warm point (see k_ipm_solve)
     double mu_warm;           // complementarity level (gap / cone degree, equilibrated units) at which the warm point is taken
 };
@@ -115,7 +116,9 @@ struct Ctx {
     double rho_min, bad_abs;
     double *vs;                         // shared-memory substitution vector (nullptr: use global memory)
     double *Lrow;                       // row-ordered copy of the scaled factor (forward substitution)
-    double reftol;                      // iterative refinement stops once |residual|_inf <= reftol*(1+|rhs|_inf)
+    double reftol;                      // iterative refinement stops once |residual|_inf <= reftol*(1+|rhs|_inf) ...
+    const double *s_mu;                 // ... reftol while the seed's complementarity gap/deg is above mu_tight, 1e-13 below it
+    double mu_tight;                    //     (shared: per-seed mu of the current iterate)
     double *red;   // shared: [10][IPM_NT_MAX/32][IPM_MAXG]
     double *out;   // shared: [10][IPM_MAXG]
 };
@@ -791,7 +794,10 @@ __device__ __forceinline__ void kkt_solve(const IpmProgram &P, Ctx &c, const Ipm
             int again = 0;
             for (int q = 0; q < G; q++) {
                 const double res = c.out[q], ref = c.out[IPM_MAXG + q];
-                if (!(res <= c.reftol * (1.0 + ref))) again = 1;   // NaN counts as "not converged"
+                // early iterations only need a direction; the last ones (small mu: the scaling matrix spans > 20 orders of
+                // magnitude) need every digit, or the iterates stall a decade or two above the requested gap
+                const double tol_ = (c.s_mu[q] > c.mu_tight) ? c.reftol : fmin(c.reftol, 1e-13);
+                if (!(res <= tol_ * (1.0 + ref))) again = 1;   // NaN counts as "not converged"
             }
             *c.flag = again;
         }
@@ -1078,7 +1084,7 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
     c.o_vs = (9 * (P.nlevels + 1) + 3) & ~3;
     c.vs = D.vsmem ? (double *)(s_lv + c.o_vs) : nullptr;
     c.G = D.G; c.tid = threadIdx.x; c.sg = c.tid % c.G; c.slot = c.tid / c.G; c.nslots = NT / c.G; c.nwarps = NT / 32;
-    c.flag = &s_flag; c.reftol = O.reftol;
+    c.flag = &s_flag; c.reftol = O.reftol; c.s_mu = s_mu; c.mu_tight = O.mu_tight;
     c.Rmax = D.R;
     c.t_fw = c.t_bw = c.t_ldl_n = 0;
     c.lprof = (blockIdx.x == 0 && threadIdx.x == 0 && D.prof && D.lvl_prof) ? D.prof + 12 : nullptr;
@@ -1140,6 +1146,7 @@ __global__ void __launch_bounds__(NT) k_ipm_solve(const IpmProgram P, const IpmD
         s_skip[c.tid] = sk; s_done[c.tid] = sk;
         s_status[c.tid] = IPM_MAXIT; s_iters[c.tid] = 0; s_best[c.tid] = CUDART_INF; s_save[c.tid] = 0; s_stall[c.tid] = 0;
         s_delta[c.tid] = O.delta; s_bad[c.tid] = 0;
+        s_mu[c.tid] = CUDART_INF;
         s_warm[c.tid] = (!sk && O.warm && D.warm && D.warm[sd]) ? 1 : 0;
         s_wsaved[c.tid] = 0; s_wsave[c.tid] = 0;
     }
@@ -1313,8 +1320,13 @@ restart_cold:
             s_mu[q] = gap / deg;
             s_save[q] = 0;
             s_wsave[q] = 0;
-            if (!s_done[q] && !s_wsaved[q] && D.warm && isfinite(pres) && isfinite(dres) && gap >= 0.0 && gap / deg <= O.mu_warm) {
-                s_wsave[q] = 1; s_wsaved[q] = 1;   // the warm point of the NEXT solve of this seed: first iterate this close to the path's end
+            // the warm point of the NEXT solve of this seed: the first iterate this close to the path's end.  A warm-started
+            // run begins at about that level already: it only replaces the point by an iterate of ITS OWN path (it >= 1) that
+            // is still inside [0.1, 1] mu_warm -- otherwise the stored point would creep towards the boundary from one SCP
+            // iteration to the next -- and keeps the one it started from if no iterate qualifies
+            if (!s_done[q] && !s_wsaved[q] && D.warm && isfinite(pres) && isfinite(dres) && gap >= 0.0 && gap / deg <= O.mu_warm &&
+                (!s_warm[q] || (it >= 1 && gap / deg >= 0.1 * O.mu_warm))) {
+                s_wsave[q] = 1; s_wsaved[q] = 1;
             }
             if (D.trace && (int)g * G + q == D.trace_seed && !s_done[q]) {   // it, pres, dres, gap, pcost, dcost, last steps, delta, sigma*mu
                 double *tr_ = D.trace + 10 * (size_t)it;
@@ -1517,7 +1529,7 @@ restart_cold:
         const int sd = (int)g * G + c.tid;
         if (sd < D.B && !s_skip[c.tid]) {
             D.status[sd] = s_status[c.tid]; D.iters[sd] = s_iters[c.tid];
-            if (D.warm) D.warm[sd] = (s_wsaved[c.tid] && (s_status[c.tid] == IPM_OPTIMAL || s_status[c.tid] == IPM_ALMOST)) ? 1 : 0;
+            if (D.warm) D.warm[sd] = ((s_wsaved[c.tid] || s_warm[c.tid]) && (s_status[c.tid] == IPM_OPTIMAL || s_status[c.tid] == IPM_ALMOST)) ? 1 : 0;
             D.pobj[sd] = s_bp[c.tid]; D.dobj[sd] = s_bd[c.tid];
             D.res[sd] = s_br[c.tid]; D.res[D.B + sd] = s_br[IPM_MAXG + c.tid]; D.res[2 * D.B + sd] = s_br[2 * IPM_MAXG + c.tid];
         }

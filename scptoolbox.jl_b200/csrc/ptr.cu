@@ -862,7 +862,12 @@ int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *u
     // and the batch takes max-over-chunks of the sums instead of the sum of the maxima.  SCPB_PTR_CHUNKS=<n> sets the
     // number of chunks (default 64 <= concurrent-kernel limit; 0 or 1 = lock-step loop below, which also serves the
     // SCPB_IPM_STATS diagnostic).
-    const bool no_warm = getenv("SCPB_NO_WARM") != nullptr;
+    // interior-point warm start across PTR iterations: built and correct, but measured slower on the bench workload (the
+    // median iteration count of the later subproblems drops from 37 to 28-33, the slowest seed of a launch gets slower:
+    // profiles/r2_experiments.md section 7) -- opt-in with SCPB_WARM=1
+    const bool no_warm = getenv("SCPB_WARM") == nullptr || getenv("SCPB_NO_WARM") != nullptr;
+    int warm_from = 5;   // first PTR iteration whose subproblems start from the stored warm points (SCPB_WARM_FROM)
+    if (const char *e = getenv("SCPB_WARM_FROM")) warm_from = atoi(e);
     int max_chunks = SCPB_PTR_DEFAULT_CHUNKS;
     if (const char *e = getenv("SCPB_PTR_CHUNKS")) max_chunks = atoi(e);
     const int ng_all = (B + G - 1) / G;
@@ -900,7 +905,7 @@ int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *u
                 if (c == 0) mark0(1);
                 {
                     IpmOpts ow = o;
-                    ow.warm = (it > 1 && !no_warm) ? 1 : 0;
+                    ow.warm = (it >= warm_from && !no_warm) ? 1 : 0;
                     if ((rc = scpb_internal_cone_run(s->cone, ow, s->done, cs, b0 / G, nbp / G))) return rc;
                 }
                 if (c == 0) mark0(2);
@@ -940,7 +945,7 @@ int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *u
         {   // from the second subproblem on every seed starts the interior-point method from the warm point its previous
             // solve stored (the subproblems of consecutive PTR iterations differ little); SCPB_NO_WARM=1 turns it off
             IpmOpts ow = o;
-            ow.warm = (it > 1 && !no_warm) ? 1 : 0;
+            ow.warm = (it >= warm_from && !no_warm) ? 1 : 0;
             if ((rc = scpb_internal_cone_run(s->cone, ow, s->done, nullptr, 0, 0))) return rc;
         }
         mark(); phase.push_back(2);

@@ -288,3 +288,32 @@ def test_bench_configuration_parity(pkg, handle):
         tol = 1e-6 if its < 15 else 1e-4
         assert max(ex7, eu2, ep) <= tol and dJ <= (1e-7 if its < 15 else 1e-5)
         assert bool(sol.feas[b]) == feas
+
+
+def test_streamed_chains_equal_the_lockstep_loop(pkg, handle, monkeypatch):
+    """scpb_ptr_solve with SCPB_PTR_CHUNKS (chunks of seed groups running their own PTR sequences on their own streams,
+    no host synchronisation) returns what the lock-step loop returns: same statuses, same iteration counts, same
+    trajectories (up to the run-to-run rounding of the solver's atomics), and reports its chunk count."""
+    N, Nsub, nb = 12, 40, 7
+    mdl, traj, pars = _setup(pkg, handle, N, Nsub)
+    pbo = problems.StarshipProblem(N)
+    g = pbo.guess(N)
+    mdl.hs = pbo.hs
+    sc = optr.Scaling(pbo, N)
+    rng = np.random.default_rng(3)
+    X0 = np.array([g[0] + (0.02 * sc.Sx * rng.standard_normal(g[0].shape) if b else 0.0) for b in range(nb)])
+    U0 = np.array([g[1] + (0.02 * sc.Su * rng.standard_normal(g[1].shape) if b else 0.0) for b in range(nb)])
+    P0 = np.array([g[2] * (1 + (0.05 * rng.uniform(-1, 1, g[2].shape) if b else 0.0)) for b in range(nb)])
+    pbm = pkg.ptr.create(pars, traj, handle)
+    monkeypatch.setenv("SCPB_PTR_CHUNKS", "0")
+    ref = pkg.ptr.solve(pbm, (X0, U0, P0))
+    assert ref.timing["chunks"] == 0
+    for chunks in ("3", "16"):
+        monkeypatch.setenv("SCPB_PTR_CHUNKS", chunks)
+        sol = pkg.ptr.solve(pbm, (X0, U0, P0))
+        assert sol.timing["chunks"] == min(int(chunks), nb)          # one seed per group at this batch size
+        assert sol.status == ref.status and (sol.iterations == ref.iterations).all(), (sol.status, sol.iterations, ref.iterations)
+        assert np.abs((sol.xd - ref.xd)[:, :, :7] / sc.Sx[:7]).max() <= 1e-7 and np.abs(sol.cost - ref.cost).max() <= 1e-8
+        assert (sol.feas == ref.feas).all()
+        assert sol.timing["ipm_iterations"] > 0 and sol.timing["lockstep_iterations"] == int(ref.iterations.max())
+    pbm.close()
