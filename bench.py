@@ -6,8 +6,10 @@
 
 Workload (config.workload): BASELINE.json's north-star case -- starship_flip PTR, N=100 nodes, Nsub=100,
 256 randomly perturbed initial guesses ("seeds"), fp64.  One "step" = one complete batched PTR solve
-of those seeds (discretize! + formulate + conic solve + discretize! + stopping test, in lock step until every
-seed stops) INCLUDING the final gather; the metric is SCP iterations per second = sum over seeds of PTR iterations / time.
+of those seeds (discretize! + formulate + conic solve + discretize! + stopping test, until every seed stops)
+INCLUDING the final gather; the metric is SCP iterations per second = sum over seeds of PTR iterations / time.
+The PTR loop runs as streamed chains (32 chunks of seed groups, each its own CUDA stream and PTR sequence, one hardware
+queue per chunk: the two environment defaults set below); SCPB_PTR_CHUNKS=0 gives the lock-step loop.
 Seeds are independent: with N GPUs the 256 seeds are cut into blocks of ceil(256/N) per rank (SURVEY 8(e);
 "scaling": "strong"), no collective on the data path, one NCCL all_gather of the per-seed results at the end, inside
 the timed region (scptoolbox.jl_b200/sharded.py).  --weak keeps 256 seeds per GPU instead ("scaling": "weak").
@@ -23,6 +25,11 @@ import threading
 import time
 
 import numpy as np
+
+# streamed PTR chains (scpb_ptr_solve): one hardware queue per chunk, or a 100 ms solver kernel at the head of a shared
+# queue blocks the small kernels of another chunk behind it.  Must be in the environment before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+os.environ.setdefault("SCPB_PTR_CHUNKS", "32")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
