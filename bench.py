@@ -144,6 +144,17 @@ def algo_constants(algo):
     return {"ptr": PTR, "scvx": SCVX, "gusto": GUSTO}[algo]
 
 
+def workload_config(args, Btot, world):
+    """The `config` object of the JSON line: what is solved -- identical in both arms (what happened in a run is `run`)."""
+    return {"workload": workload_name(args), "batch_total": Btot, "batch_per_gpu": -(-Btot // world),
+            "partition": "contiguous blocks of ceil(batch_total / n_gpus) seeds",
+            "algorithm_constants": algo_constants(args.algo),
+            "seeds": ("SURVEY 8(d): straight line + lateral half-sine of amplitude U[-1, 1] m, tdil ~ U[1, 2.5] s"
+                      if args.algo == "gusto" else
+                      "SURVEY 8(d): x += 0.05*Sx*N(0,1), u += 0.05*Su*N(0,1) clipped to the advised ranges, (t1, t2) x U[0.8, 1.2]"),
+            "l2": "256 MiB buffer written between timed steps; solver working set (1.2 GB for 256 seeds) >> L2"}
+
+
 def make_seeds_c4(base, nb, seed, r0, rf):
     """Synthetic seeds as SURVEY 8(d) specifies them for C4: the straight-line guess plus a lateral (horizontal, normal to
     the r0 -> rf line) half-sine of amplitude U[-1, 1] m -- which side of the obstacles the guess passes --, and the flight
@@ -269,9 +280,7 @@ def run_reference(args, rank):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
             "higher_is_better": True, "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": workload_name(args),
-                       "batch_total": args.batch * (args.gpus if args.weak else 1),
-                       "algorithm_constants": algo_constants(args.algo)},
+            "config": workload_config(args, args.batch * (args.gpus if args.weak else 1), max(1, args.gpus)),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{nseeds} of {args.batch} seeds per step, one single-threaded process per core "
                                        f"(oracle: C discretize + Python formulate + "
@@ -449,22 +458,15 @@ def run_ours(args, rank, local_rank, world):
                 "ms_per_step": 1e3 * dev_t / args.steps, "higher_is_better": True,
                 "scaling": "weak" if args.weak else "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload_name(args), "batch_total": Btot,
-                           "batch_per_gpu": -(-Btot // world), "partition": "contiguous blocks of ceil(batch_total / n_gpus) seeds",
-                           "algorithm_constants": algo_constants(args.algo),
-                           "seeds": ("SURVEY 8(d): straight line + lateral half-sine of amplitude U[-1, 1] m, tdil ~ U[1, 2.5] s"
-                                     if args.algo == "gusto" else
-                                     "SURVEY 8(d): x += 0.05*Sx*N(0,1), u += 0.05*Su*N(0,1) clipped to the advised ranges, "
-                                     "(t1, t2) x U[0.8, 1.2]"),
-                           "seeds_solved": int(solved), "seeds_total": Btot,
-                           "scp_iterations_per_step": its / args.steps,
-                           "scp_iterations_min_median_max": [int(itv.min()), float(np.median(itv)), int(itv.max())],
-                           "longest_chain_iterations_per_step_rank0": lock / args.steps,
-                           "chains_rank0": (f"{nch} chunks of seed groups, each its own stream and PTR sequence (no lock-step)"
-                                            if nch > 1 else "one lock-step loop over the batch"),
-                           "frozen_seed_fraction_rank0": (None if nch > 1 else
-                                                          1.0 - (float(loc.iterations.sum()) / max(1, Bloc * (lock / args.steps)))),
-                           "l2": "256 MiB buffer written between timed steps; solver working set (1.1 GB for 256 seeds) >> L2"},
+                "config": workload_config(args, Btot, world),
+                "run": {"seeds_solved": int(solved), "seeds_total": Btot,
+                        "scp_iterations_per_step": its / args.steps,
+                        "scp_iterations_min_median_max": [int(itv.min()), float(np.median(itv)), int(itv.max())],
+                        "longest_chain_iterations_per_step_rank0": lock / args.steps,
+                        "chains_rank0": (f"{nch} chunks of seed groups, each its own stream and PTR sequence (no lock-step)"
+                                         if nch > 1 else "one lock-step loop over the batch"),
+                        "frozen_seed_fraction_rank0": (None if nch > 1 else
+                                                       1.0 - (float(loc.iterations.sum()) / max(1, Bloc * (lock / args.steps))))},
                 "gpu_launches": int(ln[0]),
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": nb_in,
                         "d2h_bytes_per_step": int(nb_in + Btot * (4 * 3 + 8 * 2)),
