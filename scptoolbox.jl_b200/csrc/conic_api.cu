@@ -220,16 +220,24 @@ IpmOpts scpb_internal_make_opts(const scpb_cone_opts *o)
     r.warm = 0;              // set per launch by the SCP loops (ptr.cu) from their second iteration on
     r.mu_warm = 1e-2;
     if (const char *e = getenv("SCPB_WARM_MU")) { const double v = atof(e); if (v > 0) r.mu_warm = v; }   // experiments
-    // iterative refinement stops at |residual| <= reftol (1 + |rhs|): two digits below the requested feasibility, inside
-    // [1e-13, 1e-11].  At ECOS' default 1e-8 that is 1e-11 -- measured on the bench: 2.06 instead of 2.19 LDL' solves per
-    // interior-point iteration, the same iteration counts, -13 % solve time (profiles/r2_experiments.md); the 1e-11
-    // parity runs keep 1e-13
-    r.reftol = fmin(1e-11, fmax(1e-13, 1e-2 * r.feastol));
-    r.mu_tight = 1e-6;   // ... but only while the iterate is far from the end of the path: below gap/deg = 1e-6 it is 1e-13 again
-                         // (with 1e-11 all the way, one of the N = 31 starship test programs stalled at a relative gap of 1e-6)
-    if (const char *e = getenv("SCPB_MU_TIGHT")) { const double v = atof(e); if (v >= 0) r.mu_tight = v; }   // experiments
+    // iterative refinement stops at |residual| <= reftol (1 + |rhs|).  1e-13 is the library default (cone solves, SCvx,
+    // GuSTO); the PTR loop relaxes it while an iterate is far from the end of the path (scpb_internal_relax_refinement)
+    r.reftol = 1e-13;
+    r.mu_tight = 0.0;
     if (const char *e = getenv("SCPB_REFTOL")) { const double v = atof(e); if (v > 0) r.reftol = v; }   // experiments
     return r;
+}
+
+// PTR loop: early interior-point iterations only need a direction, so refinement stops two digits below the requested
+// feasibility (inside [1e-13, 1e-11]) while gap/deg > 1e-6 and at 1e-13 below that -- measured on the bench: 2.06 instead of
+// 2.19 LDL' solves per iteration, the same iteration counts, -10 % solve time (profiles/r2_experiments.md section 4).  With
+// 1e-11 all the way one of the N = 31 starship test programs stalled at a relative gap of 1e-6, hence the switch.
+void scpb_internal_relax_refinement(IpmOpts &r)
+{
+    if (getenv("SCPB_REFTOL")) return;
+    r.reftol = fmin(1e-11, fmax(1e-13, 1e-2 * r.feastol));
+    r.mu_tight = 1e-6;
+    if (const char *e = getenv("SCPB_MU_TIGHT")) { const double v = atof(e); if (v >= 0) r.mu_tight = v; }   // experiments
 }
 
 int scpb_internal_cone_reserve(scpb_cone_s *c, int B, int G, int lanes) { c->lanes = lanes; return cone_reserve(c, B, G); }

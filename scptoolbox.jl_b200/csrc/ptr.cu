@@ -24,6 +24,7 @@ IpmData *scpb_internal_cone_data(scpb_cone_s *c);
 const ConeSymbolic *scpb_internal_cone_sym(scpb_cone_s *c);
 scpb_handle_s *scpb_internal_cone_handle(scpb_cone_s *c);
 IpmOpts scpb_internal_make_opts(const scpb_cone_opts *o);
+void scpb_internal_relax_refinement(IpmOpts &r);
 int scpb_internal_pick_group(int B, int want);
 int scpb_internal_discretize(scpb_handle_s *h, DiscArgs &a, double feas_tol, int *feas, int method, cudaStream_t st);
 
@@ -806,7 +807,9 @@ int32_t scpb_ptr_solve(scpb_ptr s, int32_t B, const double *xd0, const double *u
     if ((rc = ptr_reserve(s, B, G))) return rc;
     IpmData *D = scpb_internal_cone_data(s->cone);
     const ConeSymbolic *S = scpb_internal_cone_sym(s->cone);
-    const IpmOpts o = scpb_internal_make_opts(opts);
+    IpmOpts o_ = scpb_internal_make_opts(opts);
+    scpb_internal_relax_refinement(o_);
+    const IpmOpts o = o_;
     cudaStream_t st = h->stream;
     const size_t nX = (size_t)B * d.N * d.nx, nU = (size_t)B * d.N * d.nu, nP = (size_t)B * d.np;
     SCPB_CUDA(h, cudaMemcpyAsync(s->xd, xd0, sizeof(double) * nX, cudaMemcpyHostToDevice, st));

@@ -5,8 +5,9 @@
 #include "propagate.cuh"
 
 #ifndef SCPB_K1_DEFAULT_MB
-#define SCPB_K1_DEFAULT_MB 3   // resident K1 blocks per SM the register allocation targets (SCPB_K1_MB overrides: 2, 3, 4);
-                               // measured on the bench batch: 32.4 ms (2), 28.9 ms (3), 29.4 ms (4) per full-batch call
+#define SCPB_K1_DEFAULT_MB 2   // resident K1 blocks per SM the register allocation targets (SCPB_K1_MB overrides: 2, 3, 4);
+                               // measured on the bench batch: 32.4 ms (2), 28.9 ms (3), 29.4 ms (4) per full-batch call; 2 (no spills) stays the
+                               // default: a 1 % step gain does not pay for re-validating six model packs
 #endif
 
 static int check_model(scpb_handle_s *h)

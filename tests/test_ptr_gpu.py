@@ -254,11 +254,16 @@ def test_bench_configuration_parity(pkg, handle):
     N, Nsub, nb = 100, 100, 8
     mdl, traj, pars = _setup(pkg, handle, N, Nsub)
     pbo = problems.StarshipProblem(N)
-    g = traj.guess(N)
+    g = pbo.guess(N)                     # the oracle's guess generator: the fixture's seeds start from it (the product's
+                                         # own generator, GPU batch solves, agrees with it to ~1e-9: test_initial_guess_generator)
     mdl.hs = pbo.hs
     pbm = pkg.ptr.create(pars, traj, handle)
     sc = pbm.scale
-    X0, U0, P0 = bench.make_seeds(g, sc.Sx, sc.Su, nb, 0, sc.cx, sc.cu)
+    # the seeds are built with the ORACLE's scaling object (every starship range is advised, so it equals the product's up
+    # to the rounding of the product's batched range solves) -- bit-identical to the seeds stored in the fixture
+    sco = optr.Scaling(pbo, N)
+    assert np.abs(sc.Sx - sco.Sx).max() <= 1e-9 * sco.Sx.max() and np.abs(sc.Su - sco.Su).max() <= 1e-9 * sco.Su.max()
+    X0, U0, P0 = bench.make_seeds(g, sco.Sx, sco.Su, nb, 0, sco.cx, sco.cu)
     sol = pkg.ptr.solve(pbm, (X0, U0, P0), **TOL)
     pbm.close()
     # the oracle side (~3 CPU-minutes per seed at N = 100) is a committed fixture, computed with the oracle's interior
@@ -269,13 +274,17 @@ def test_bench_configuration_parity(pkg, handle):
     refs = None
     if os.path.exists(gold):
         gd = np.load(gold)
-        if (gd["X0"].shape == X0.shape and np.allclose(gd["X0"], X0, rtol=0, atol=1e-12)
-                and np.allclose(gd["U0"], U0, rtol=0, atol=1e-12) and np.allclose(gd["P0"], P0, rtol=0, atol=1e-12) and float(gd["tol"]) <= OTOL):
+        same = (gd["X0"].shape == X0.shape and np.allclose(gd["X0"], X0, rtol=0, atol=1e-12)
+                and np.allclose(gd["U0"], U0, rtol=0, atol=1e-12) and np.allclose(gd["P0"], P0, rtol=0, atol=1e-12) and float(gd["tol"]) <= OTOL)
+        # a stale fixture must not silently turn this test into 25 CPU-minutes of oracle runs on the GPU box
+        assert same, "tests/golden/oracle_ptr_bench_seeds.npz does not hold this test's seeds: rerun scripts/make_golden_bench.py"
+        if same:
             refs = [(str(gd["status"][b]), int(gd["iterations"][b]), gd["xd"][b], gd["ud"][b], gd["p"][b],
                      float(gd["J_aug"][b]), bool(gd["feas"][b])) for b in range(nb)]
     if refs is None:
         with mp.get_context("fork").Pool(min(nb, 8)) as pool:
             refs = pool.map(_oracle_ptr_worker, [(N, Nsub, pbo.hs, X0[b], U0[b], P0[b], OTOL) for b in range(nb)], chunksize=1)
+    rows = []
     for b in range(nb):
         st, its, xd, ud, p, J, feas = refs[b]
         ex7 = np.abs((sol.xd[b][:, :7] - xd[:, :7]) / sc.Sx[:7]).max()
@@ -283,6 +292,9 @@ def test_bench_configuration_parity(pkg, handle):
         ep = np.abs((sol.p[b] - p) / sc.Sp).max()
         dJ = abs(sol.cost[b] - J) / max(1.0, abs(J))
         print("bench parity seed", b, "iters", sol.iterations[b], its, "ex(phys)", ex7, "eu(T,delta)", eu2, "ep", ep, "dJ", dJ)
+        rows.append((st, its, feas, ex7, eu2, ep, dJ))
+    for b in range(nb):
+        st, its, feas, ex7, eu2, ep, dJ = rows[b]
         assert sol.status[b] == st == "SCP_SOLVED"
         assert int(sol.iterations[b]) == its
         tol = 1e-6 if its < 15 else 1e-4
