@@ -290,7 +290,7 @@ int32_t scpb_debug_kkt_solve_hy(int32_t n, int32_t p, int32_t m, const int32_t *
  * factorisation flagged lost inertia.  GPU tests compare it with scpb_debug_kkt_solve. */
 int32_t scpb_debug_kkt_solve_dev(scpb_cone cone, int32_t B, const double *Avals, const double *Gvals, const double *wm,
                                  double delta, const double *rhs, double *sol, int32_t *bad);
-/* Stateful variant of the scalar interpreter for numerics studies on the CPU (scripts/emu_ipm.py): symbolic analysis
+/* Stateful variant of the scalar interpreter for numerics studies on the CPU: symbolic analysis
  * once (scpb_debug_kkt_new), then any number of factorisations and solves.  scpb_debug_kkt_factor applies the kernel's
  * dynamic regularisation (a pivot with sgn*d <= tau becomes sgn*rho) and returns the number of rejected pivots that
  * were NOT small (|d| > bad_abs or non-finite: the inertia was lost to cancellation), or a negative error code;
