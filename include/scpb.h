@@ -122,7 +122,7 @@ typedef struct {
     int32_t maxit;                  /* <=0: 100 ("maxit" of solver_opts)                 */
     int32_t nref;                   /* <0: at most 3 iterative-refinement steps          */
     int32_t verbose;                /* accepted, ignored ("verbose" of solver_opts)      */
-    int32_t group;                  /* seeds per CTA (power of two <= 32); 0 = automatic */
+    int32_t group;                  /* seeds per CTA (power of two <= 8);  0 = automatic */
     int32_t equil;                  /* Ruiz equilibration passes; <0: default 5, 0: off    */
     int32_t threads;                /* threads per CTA: 1024 (default) or 512              */
     int32_t lanes;                  /* lanes per sparse row in the fallback substitution that is used when the

@@ -156,7 +156,7 @@ def test_gusto_outcomes_match_oracle(pkg, handle):
         assert (sol.status[b] == "SCP_SOLVED") == ok_o
         if ok_o:
             nsolved += 1
-            _compare(sol, b, refs[b], sc, 1e-2, 1e-5)   # measured: trajectory up to 3.4e-3 (seed 3, 8 iterations), J_aug up to 4e-6
+            _compare(sol, b, refs[b], sc, 2e-2, 2e-5)   # measured: trajectory up to 4.8e-3 (seed 13, 8 iterations), J_aug up to 5.4e-6
         if P0[b][0] < 1.12:   # first subproblem infeasible: a clear case ends with the certificate (test_infeasible_guess_is_
             # reported), a marginal one (tdil = 1.106 s against the ~1.13 s limit) exhausts the iterations -- in the oracle too
             assert sol.status[b].startswith("SCP_FAILED") and int(sol.iterations[b]) == 1
