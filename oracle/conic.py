@@ -3,7 +3,7 @@
 Plays the role of the reference's parser + JuMP + ECOS stack for the oracle:
   * `ConeProgram`  ~ ConicProgram (src/parser/program.jl:63-76) with @new_variable /
     @add_constraint / @add_cost semantics; cones as in src/parser/cone.jl:36-47
-    (ZERO z==0, NONPOS z<=0, L1 |x|_1<=t, SOC |x|_2<=t, LINF |x|_inf<=t).
+    (ZERO z==0, NONPOS z<=0, L1 |x|_1<=t, SOC |x|_2<=t, LINF |x|_inf<=t, GEOM geomean(x1,x2)>=t).
   * L1 / LINF are lowered exactly like MathOptInterface's NormOneBridge / NormInfinityBridge
     (the path JuMP takes for ECOS): aux y_i >= |x_i|, sum(y) <= t;  -t <= x_i <= t.
   * compiled form (ECOS / CVXOPT convention):   min c'z  s.t.  A z = b,  G z + s = h,  s in K,
@@ -153,6 +153,15 @@ class ConeProgram:
 
     def soc(self, exprs, name=""):
         self.socs.append([Aff.lift(e) for e in exprs])
+
+    def geom(self, exprs, name=""):
+        """[t, x1, x2]: geomean(x1, x2) >= t (cone.jl:45, MOI.GeometricMeanCone(3)) -- every GEOM use of the reference has
+        two entries (ptr.jl:615, scvx.jl:659, gusto.jl:1129, double_integrator/definition.jl:80).  MathOptInterface's
+        bridges hand ECOS the rotated second-order cone x1 x2 >= t^2, x >= 0, i.e. |(2 t, x1 - x2)|_2 <= x1 + x2."""
+        if len(exprs) != 3:
+            raise NotImplementedError("GEOM cone over more than two entries")
+        t, x1, x2 = (Aff.lift(e) for e in exprs)
+        self.socs.append([x1 + x2, t * 2.0, x1 - x2])
 
     def add_cost(self, expr):
         self.cost = self.cost + Aff.lift(expr)

@@ -242,21 +242,30 @@ class PTR:
             prg.zero([lhs[i] + lf[i] + vtc[i] for i in range(g.size)], "terminal_condition")
         # trust region
         q = pars.q_tr
-        cone = {1: prg.l1, 2: prg.soc, np.inf: prg.linf}[q]
+        cone = {1: prg.l1, 2: prg.soc, 4: prg.soc, np.inf: prg.linf}[q]     # q2cone, ptr.jl:582
         xh_ref = (ref.xd - sc.cx) * sc.iSx
         uh_ref = (ref.ud - sc.cu) * sc.iSu
         ph_ref = (ref.p - sc.cp) * sc.iSp
+
+        def bound(d_lq, eta, name):
+            if q == 4:      # ptr.jl:604-630: w with |d_lq| <= w (SOC) and geomean(eta, 1) >= w (GEOM), i.e. d_lq^2 <= eta
+                w = prg.new_variable(1, f"w_{name}_{prg.nvar}")
+                prg.soc([w[0], d_lq], name)
+                prg.geom([w[0], eta, 1.0], name)
+            else:
+                prg.nonpos([d_lq - eta])
+
         dp_lq = prg.new_variable(1, "dp_lq")
         cone([dp_lq[0]] + [(p[i] - sc.cp[i]) * sc.iSp[i] - ph_ref[i] for i in range(np_)], "parameter_trust_region")
-        prg.nonpos([dp_lq[0] - eta_p[0]])
+        bound(dp_lq[0], eta_p[0], "parameter_trust_region")
         dx_lq = prg.new_variable(N, "dx_lq")
         for k in range(N):
             cone([dx_lq[k]] + [(x[i, k] - sc.cx[i]) * sc.iSx[i] - xh_ref[k, i] for i in range(nx)], "state_trust_region")
-            prg.nonpos([dx_lq[k] - eta_x[k]])
+            bound(dx_lq[k], eta_x[k], "state_trust_region")
         du_lq = prg.new_variable(N, "du_lq")
         for k in range(N):
             cone([du_lq[k]] + [(u[i, k] - sc.cu[i]) * sc.iSu[i] - uh_ref[k, i] for i in range(nu)], "input_trust_region")
-            prg.nonpos([du_lq[k] - eta_u[k]])
+            bound(du_lq[k], eta_u[k], "input_trust_region")
         # cost
         if hasattr(pb, "cost_emit"):        # convex non-affine cost: the problem adds its epigraph cones to the program
             J = pb.cost_emit(prg, x, u, p, t)

@@ -229,6 +229,15 @@ class ConicTemplate:
     def soc(self, exprs, name=""):
         self.socs.append([Expr.lift(e) for e in exprs])
 
+    def geom(self, exprs, name=""):
+        """[t, x1, x2]: geomean(x1, x2) >= t (GEOM, cone.jl:45,161-162; all uses in the reference have two entries:
+        ptr.jl:615,667,720, scvx.jl:659, gusto.jl:1129) as the second-order cone |(2 t, x1 - x2)|_2 <= x1 + x2 that
+        MathOptInterface's GeoMean -> RSOC -> SOC bridges give ECOS."""
+        if len(exprs) != 3:
+            raise NotImplementedError("GEOM cone over more than two entries")
+        t, x1, x2 = (Expr.lift(e) for e in exprs)
+        self.socs.append([x1 + x2, t * 2.0, x1 - x2])
+
     def sumsq(self, exprs, name="", stage=-2):
         """epigraph of a sum of squares: returns q (a new variable, as Expr) with  sum_i e_i^2 <= q  imposed as the
         rotated second-order cone |(2 e_1, ..., 2 e_n, q - 1)|_2 <= q + 1.  This is how a convex quadratic running cost

@@ -262,27 +262,40 @@ class SCPProblem:
             prg.zero([g[i] + vtc[i] for i in range(len(g))], "terminal_condition")
         # trust region (ptr.jl:565-743)
         q = pars.q_tr
-        cone = {1: prg.l1, 2: prg.soc, np.inf: prg.linf}[q]
+        if q == 4 and scvx:
+            raise NotImplementedError("q_tr = 4 is built for the PTR template only")
+        cone = {1: prg.l1, 2: prg.soc, 4: prg.soc, np.inf: prg.linf}[q]
+
+        def bound(d_lq, eta, name, stage):
+            """d_lq <= eta, or for q_tr = 4 the squared two-norm trust region d_lq^2 <= eta (ptr.jl:604-630): |d_lq| <= w
+            (a two-entry SOC) and geomean(eta, 1) >= w (GEOM)."""
+            if q == 4:
+                w = prg.new_variable(1, f"w_{name}_{prg.nvar}", stage=stage)
+                prg.soc([w[0], d_lq], name)
+                prg.geom([w[0], eta, 1.0], name)
+            else:
+                prg.nonpos([d_lq - eta])
+
         dp_lq = prg.new_variable(1, "dp_lq", stage=None)
         ph_ref = sm.vec(sm.oph, 0, np_)
         cone([dp_lq[0]] + [(p[i] - sc.cp[i]) * (1.0 / sc.Sp[i]) - Expr(None, ph_ref[i]) for i in range(np_)],
              "parameter_trust_region")
         if not scvx:
-            prg.nonpos([dp_lq[0] - eta_p[0]])
+            bound(dp_lq[0], eta_p[0], "parameter_trust_region", None)
         dx_lq = prg.new_variable(N, "dx_lq", stage="idx")
         for k in range(N):
             xr = sm.vec(sm.oxh, k, nx)
             cone([dx_lq[k]] + [(x[i, k] - sc.cx[i]) * (1.0 / sc.Sx[i]) - Expr(None, xr[i]) for i in range(nx)],
                  "state_trust_region")
             if not scvx:
-                prg.nonpos([dx_lq[k] - eta_x[k]])
+                bound(dx_lq[k], eta_x[k], "state_trust_region", k)
         du_lq = prg.new_variable(N, "du_lq", stage="idx")
         for k in range(N):
             ur = sm.vec(sm.ouh, k, nu)
             cone([du_lq[k]] + [(u[i, k] - sc.cu[i]) * (1.0 / sc.Su[i]) - Expr(None, ur[i]) for i in range(nu)],
                  "input_trust_region")
             if not scvx:
-                prg.nonpos([du_lq[k] - eta_u[k]])
+                bound(du_lq[k], eta_u[k], "input_trust_region", k)
         if scvx:                # trust_region_bound (scvx.jl:649-674): dx_lq[k] + du_lq[k] + dp_lq <= eta
             eta_src = Expr(None, Lin.src(sm.oeta))
             for k in range(N):

@@ -78,7 +78,7 @@ def lcvx_program(choice):
     for k in range(N):
         P.nonpos([sg[0, k] - 2.0]); P.nonpos([1.0 - sg[0, k]])
         P.l1([sg[0, k], u[0, k]])
-        P.soc([s2[0, k] + 1.0, sg[0, k] * 2.0, s2[0, k] - 1.0])
+        P.geom([sg[0, k], s2[0, k], 1.0])          # GEOM (sigma; sigma2, 1), definition.jl:80-83
         if k < N - 1:
             for i in range(2):
                 P.zero([x[i, k + 1] - (x[0, k] * A[i, 0] + x[1, k] * A[i, 1] + u[0, k] * Bm[i] + u[0, k + 1] * Bp[i] + w[i])])

@@ -136,3 +136,22 @@ def test_l1_and_linf_epigraphs_agree_across_solvers(seed):
     # no feasible point does better (random search around the optimum + the two anchors)
     cand = [a, b, ip["z"][:n]] + [ip["z"][:n] + 0.05 * rng.standard_normal(n) for _ in range(200)]
     assert min(f(np.clip(v, -2, 2)) for v in cand) >= ip["obj"] - 1e-6
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_geom_cone_is_the_squared_norm_epigraph(seed):
+    """The q_tr = 4 trust region of ptr.jl:604-630: |d|_2 <= d_lq (SOC), |d_lq| <= w (SOC), geomean(eta, 1) >= w (GEOM)
+    makes eta the epigraph of |d|_2^2.  With d pinned to a given vector, min eta must return its squared norm."""
+    rng = np.random.default_rng(seed)
+    n = 5
+    a = rng.standard_normal(n)
+    P = conic.ConeProgram()
+    d = _var(P, n, "d"); d_lq = _var(P, 1, "d_lq"); w = _var(P, 1, "w"); eta = _var(P, 1, "eta")
+    P.zero([d[i] - float(a[i]) for i in range(n)])
+    P.soc([d_lq[0]] + [d[i] for i in range(n)])
+    P.soc([w[0], d_lq[0]])
+    P.geom([w[0], eta[0], 1.0])
+    P.add_cost(eta[0])
+    out = conic.solve_ipm(P.compile(), tol=1e-10)
+    assert out["status"] in ("OPTIMAL", "ALMOST_OPTIMAL")
+    assert abs(out["obj"] - a @ a) <= 1e-7 * max(1.0, a @ a)

@@ -184,9 +184,10 @@ def test_scvx_template_matches_oracle_subproblem(pkg, monkeypatch):
     assert np.abs(q - want).max() <= 1e-10 * max(1.0, np.abs(want).max())
 
 
-@pytest.mark.parametrize("q_tr", [1, 2])
+@pytest.mark.parametrize("q_tr", [1, 2, 4])
 def test_template_other_trust_region_norms(pkg, monkeypatch, q_tr):
-    """q_tr in {1, 2} (ptr.jl:582: L1 / SOC trust-region cones instead of LINF): template == oracle subproblem."""
+    """q_tr in {1, 2, 4} (ptr.jl:582: L1 / SOC trust-region cones instead of LINF; 4 = squared two-norm through the GEOM
+    cone, ptr.jl:604-630): template == oracle subproblem."""
     N = 7
     pbo = problems.StarshipProblem(N)
     xd, ud, p = problems.test_trajectory(pbo, 1, N, seed=q_tr)
@@ -216,6 +217,8 @@ def test_template_other_trust_region_norms(pkg, monkeypatch, q_tr):
     assert list(cp["soc_dims"]) == list(ocp["q"])
     if q_tr == 2:
         assert sorted(set(cp["soc_dims"])) == [4, 9, 11]      # input, state and parameter trust regions
+    if q_tr == 4:
+        assert sorted(set(cp["soc_dims"])) == [2, 3, 4, 9, 11]   # ... plus |d_lq| <= w and the lowered GEOM cones
     A = sp.csr_matrix((vals[:cp["nnzA"]], cp["A"].indices, cp["A"].indptr), shape=(p_, n))
     G = sp.csr_matrix((vals[cp["nnzA"]:cp["nnzA"] + cp["nnzG"]], cp["G"].indices, cp["G"].indptr), shape=(m, n))
     tol = 1e-12
