@@ -38,10 +38,14 @@ def test_reference_arm_other_ranks_are_silent():
 
 
 def test_committed_gpu_bench_line_has_the_contract_keys():
-    d = json.load(open(os.path.join(ROOT, "profiles", "r1_bench_final.json")))
+    d = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_final.json")))
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "gpu_launches", "e2e", "roofline", "cpu_baseline", "clocks"):
         assert k in d, k
     r = d["roofline"]
     assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and r["unit"] == "GB/s"
     assert d["gpu_launches"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["warmup"] >= 3
+    k1 = d["roofline_k1"]
+    assert k1["bound"] == "fp64" and k1["unit"] == "TFLOP/s" and abs(k1["frac"] - k1["achieved"] / k1["peak"]) < 1e-12
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["clocks"]["reasons"] == []
+    assert set(d["config"]) == {"workload", "batch_total", "batch_per_gpu", "partition", "algorithm_constants", "seeds", "l2"}
