@@ -416,6 +416,8 @@ def solve(pbm: SCPProblem, guesses=None, **cone_opts) -> SCPBatchSolution:
     if guesses is None:
         x0, u0, p0 = traj.guess(pars.N)
         guesses = (x0[None], u0[None], p0[None])
+    if hasattr(guesses, "xd") and hasattr(guesses, "ud"):      # warm start from an earlier batch solution (solve(pbm, warm),
+        guesses = (guesses.xd, guesses.ud, guesses.p)           # scp.jl:532-539: its discrete trajectory is the initial guess)
     xd0 = np.ascontiguousarray(guesses[0], dtype=np.float64)
     ud0 = np.ascontiguousarray(guesses[1], dtype=np.float64)
     p0 = np.ascontiguousarray(guesses[2], dtype=np.float64)
