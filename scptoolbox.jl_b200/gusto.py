@@ -218,6 +218,7 @@ def solve(pbm: GuSTOProblem, guesses=None, project_guess=True, **cone_opts) -> S
         guesses = (x0[None], u0[None], p0[None])
     if hasattr(guesses, "xd") and hasattr(guesses, "ud"):      # warm start from an earlier batch solution (solve(pbm, warm),
         guesses = (guesses.xd, guesses.ud, guesses.p)           # scp.jl:532-539: its discrete trajectory is the initial guess)
+        project_guess = False                                   # gusto.jl:434-438: a warm start is not re-projected
     xd0 = np.ascontiguousarray(guesses[0], dtype=np.float64)
     ud0 = np.ascontiguousarray(guesses[1], dtype=np.float64)
     p0 = np.ascontiguousarray(guesses[2], dtype=np.float64)
