@@ -127,7 +127,7 @@ class SCvx(PTR):
             prg.zero([lhs[i] + lf[i] + vtc[i] for i in range(g.size)], "terminal_condition")
         # trust region (scvx.jl:578-678)
         q = pars.q_tr
-        cone = {1: prg.l1, 2: prg.soc, np.inf: prg.linf}[q]
+        cone = {1: prg.l1, 2: prg.soc, 4: prg.soc, np.inf: prg.linf}[q]
         xh_ref = (ref.xd - sc.cx) * sc.iSx
         uh_ref = (ref.ud - sc.cu) * sc.iSu
         ph_ref = (ref.p - sc.cp) * sc.iSp
@@ -140,7 +140,12 @@ class SCvx(PTR):
         for k in range(N):
             cone([du_lq[k]] + [(u[i, k] - sc.cu[i]) * sc.iSu[i] - uh_ref[k, i] for i in range(nu)], "input_trust_region")
         for k in range(N):
-            prg.nonpos([dx_lq[k] + du_lq[k] + dp_lq[0] - eta], "trust_region_bound")
+            if q == 4:      # scvx.jl:646-662: |(dx_lq, du_lq, dp_lq)|_2 <= w, geomean(eta, 1) >= w
+                w = prg.new_variable(1, f"w_tr_{k}")
+                prg.soc([w[0], dx_lq[k], du_lq[k], dp_lq[0]], "trust_region_bound")
+                prg.geom([w[0], eta, 1.0], "trust_region_bound")
+            else:
+                prg.nonpos([dx_lq[k] + du_lq[k] + dp_lq[0] - eta], "trust_region_bound")
         # cost (scvx.jl:689-701, 804-901)
         L = pb.cost_aff(x, u, p, t) if hasattr(pb, "cost_aff") else conic.Aff()
         prg.add_cost(L)

@@ -262,8 +262,6 @@ class SCPProblem:
             prg.zero([g[i] + vtc[i] for i in range(len(g))], "terminal_condition")
         # trust region (ptr.jl:565-743)
         q = pars.q_tr
-        if q == 4 and scvx:
-            raise NotImplementedError("q_tr = 4 is built for the PTR template only")
         cone = {1: prg.l1, 2: prg.soc, 4: prg.soc, np.inf: prg.linf}[q]
 
         def bound(d_lq, eta, name, stage):
@@ -299,7 +297,12 @@ class SCPProblem:
         if scvx:                # trust_region_bound (scvx.jl:649-674): dx_lq[k] + du_lq[k] + dp_lq <= eta
             eta_src = Expr(None, Lin.src(sm.oeta))
             for k in range(N):
-                prg.nonpos([dx_lq[k] + du_lq[k] + dp_lq[0] - eta_src], "trust_region_bound")
+                if q == 4:      # scvx.jl:646-662: |(dx_lq, du_lq, dp_lq)|_2 <= w (SOC), geomean(eta, 1) >= w (GEOM)
+                    w = prg.new_variable(1, f"w_tr_{k}", stage=k)
+                    prg.soc([w[0], dx_lq[k], du_lq[k], dp_lq[0]], "trust_region_bound")
+                    prg.geom([w[0], eta_src, 1.0], "trust_region_bound")
+                else:
+                    prg.nonpos([dx_lq[k] + du_lq[k] + dp_lq[0] - eta_src], "trust_region_bound")
         # cost (ptr.jl:753-895, scp.jl:552-601)
         J = Expr()
         traj.ocp = prg          # a convex (non-affine) running cost adds its epigraph to the program (parser.sumsq)

@@ -127,9 +127,11 @@ def test_rocket_template_matches_oracle_subproblem(pkg, monkeypatch):
     assert abs(vals[-1] - ocp["c0"]) <= 1e-12
 
 
-def test_scvx_template_matches_oracle_subproblem(pkg, monkeypatch):
+@pytest.mark.parametrize("q_tr", [np.inf, 2, 4])
+def test_scvx_template_matches_oracle_subproblem(pkg, monkeypatch, q_tr):
     """SCvx flavour of the template (trust-region radius as a device source, lambda penalty, no eta variables) against
-    the oracle's numeric SCvx subproblem (oracle/scvx.py restating scvx.jl:225-303, 578-701, 804-901)."""
+    the oracle's numeric SCvx subproblem (oracle/scvx.py restating scvx.jl:225-303, 578-701, 804-901), for the LINF, SOC and
+    squared-two-norm (GEOM, scvx.jl:646-662) trust regions."""
     from oracle import scvx as oscvx
     N = 9
     pbo = problems.StarshipProblem(N)
@@ -137,7 +139,7 @@ def test_scvx_template_matches_oracle_subproblem(pkg, monkeypatch):
     pbo.hs = 77.0
     kw = dict(lam=5e2, rho_0=0.0, rho_1=0.1, rho_2=0.7, beta_sh=2.0, beta_gr=2.0, eta_init=1.0, eta_lb=1e-8, eta_ub=10.0,
               eps_abs=1e-5, eps_rel=1e-4, feas_tol=5e-3)
-    S = oscvx.SCvx(pbo, oscvx.Parameters(N=N, Nsub=60, iter_max=5, **kw))
+    S = oscvx.SCvx(pbo, oscvx.Parameters(N=N, Nsub=60, iter_max=5, q_tr=q_tr, **kw))
     ref = S.make_solution(xd[0], ud[0], p[0])
     eta = 0.37
     prg, _ = S.build(ref, eta)
@@ -146,7 +148,7 @@ def test_scvx_template_matches_oracle_subproblem(pkg, monkeypatch):
     mdl = ex.StarshipProblem(); mdl.hs = 77.0
     traj = pkg.problem.TrajectoryProblem(mdl)
     ex.define_problem(traj, "scvx", handle=None)
-    pars = pkg.scvx.Parameters(N=N, Nsub=60, iter_max=5, disc_method=pkg.ptr.FOH, q_tr=np.inf, q_exit=np.inf, **kw)
+    pars = pkg.scvx.Parameters(N=N, Nsub=60, iter_max=5, disc_method=pkg.ptr.FOH, q_tr=q_tr, q_exit=np.inf, **kw)
 
     class FakeHandle:
         def model_set(self, *a): pass
