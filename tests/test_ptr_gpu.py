@@ -300,7 +300,10 @@ def test_bench_configuration_parity(pkg, handle):
     #   J_aug     7.2e-8   1.5e-2        8.2e-5   4.0e-10  4.0e-6   1.8e-6   5.8e-6   5.3e-4
     # At N = 100 with 0.05*S perturbations the converged TRAJECTORY is only loosely determined by subproblem solutions of
     # interior-point accuracy: the oracle at 1e-10 is itself 1.1e-4 / 2.6e-4 away from the oracle at 1e-12 on seed 2
-    # (an amplification of 1e6, profiles/r2_parity_vs_tolerance.txt), and the LP subproblems have flat directions.  What IS
+    # (an amplification of 1e6, profiles/r2_parity_vs_tolerance.txt), and two variants of the oracle's own interior point
+    # (with / without equilibration, both at 1e-12) end 0.89 apart on seed 1 and 1.3e-4 / 1.8e-3 apart on seed 5 -- the
+    # product-vs-oracle figures of those seeds -- but 2e-4 and 3e-7 apart on seeds 2 and 7, where the product is further
+    # off than that ambiguity (profiles/r2_parity_ill_conditioning.txt): a gap of the product's solver accuracy.  What IS
     # determined -- status, iteration count, feasibility flag, the augmented cost -- is asserted per seed; on the
     # trajectory the test asserts that half of the seeds agree to 1e-3 (states) and reports the rest.
     for b in range(nb):
